@@ -1,0 +1,181 @@
+/*
+ * srwn.h -- C ABI of the B200-native SR-WaveNet hot path (libsrwn.so).
+ *
+ * The reference (tachitachi/SR-WaveNet) has no FFI: its boundary is the Python API of
+ * ops.py / model.py, every call ending in one tf.Session.run.  Each entry point below
+ * replaces one such graph evaluation; the reference interface it stands in for is cited
+ * as file:line (relative to the reference tree).  The Python shim in
+ * sr-wavenet_b200/{ops,model}.py keeps the reference's names and argument meaning and
+ * calls these functions through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every function returns an int status (SRWN_OK == 0); srwn_last_error() gives the
+ *     message of the last failure on the calling thread.
+ *   - all tensor pointers are DEVICE pointers owned by the caller, dense, fp32,
+ *     channels-last [B, T, C] exactly like the reference's tensors, unless a parameter
+ *     is documented as host memory.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *   - no hidden allocation after srwn_create/srwn_commit_weights: scratch memory is a
+ *     caller-owned workspace sized by srwn_workspace_bytes().
+ *   - a handle is not thread-safe; use one handle per GPU / per host thread.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with SRWN_ERR_CUDA.
+ */
+#ifndef SRWN_H_
+#define SRWN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRWN_ABI_VERSION 1
+
+enum srwn_status {
+  SRWN_OK = 0,
+  SRWN_ERR_INVALID = 1,      /* bad argument / shape */
+  SRWN_ERR_CUDA = 2,         /* CUDA runtime error (message has the cudaError string) */
+  SRWN_ERR_WEIGHTS = 3,      /* unknown / missing / mis-shaped variable */
+  SRWN_ERR_UNSUPPORTED = 4,  /* configuration outside what the kernels are built for */
+  SRWN_ERR_WORKSPACE = 5     /* workspace too small */
+};
+
+enum srwn_kind {
+  SRWN_TEACHER = 0,          /* WaveNetAutoEncoder decoder stack, model.py:158-200 */
+  SRWN_STUDENT = 1           /* ParallelWaveNet IAF flows,        model.py:415-535 */
+};
+
+enum srwn_precision {
+  SRWN_FP32 = 0,             /* fp32 FFMA path, parity <= 1e-4 relative */
+  SRWN_BF16 = 1              /* bf16 operands on tcgen05, fp32 accumulate/residual stream */
+};
+
+enum srwn_op {               /* argument of srwn_workspace_bytes */
+  SRWN_OP_TEACHER_LOGITS = 0,
+  SRWN_OP_TEACHER_NLL = 1,
+  SRWN_OP_TEACHER_GENERATE = 2,
+  SRWN_OP_STUDENT_FORWARD = 3
+};
+
+/* Constructor arguments of WaveNetAutoEncoder (model.py:76-77) / ParallelWaveNet
+ * (model.py:291-292) that shape the hot path.  `dilations` is the plain list the
+ * reference passes (teacher.py:55-57); it is copied. */
+typedef struct srwn_config {
+  int32_t kind;               /* enum srwn_kind */
+  int32_t n_layers;           /* len(dilations) */
+  const int32_t* dilations;   /* host pointer, n_layers entries */
+  int32_t filter_width;       /* model.py:76 filter_width (kernels are built for 2) */
+  int32_t dilation_channels;  /* R, residual channels (32) */
+  int32_t skip_channels;      /* S (teacher.py:62 -> 128) */
+  int32_t cond_channels;      /* latent_channels + condition_size: width of `encoding` */
+  int32_t pool_stride;        /* P: T == P * encoding frames (model.py:183) */
+  int32_t num_mixtures;       /* M, teacher only: logits have 4*M channels */
+  int32_t num_flows;          /* student only (student.py:71 -> 4) */
+} srwn_config_t;
+
+typedef struct srwn_ctx* srwn_handle_t;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+int srwn_abi_version(void);
+const char* srwn_last_error(void);
+
+/* Replaces graph construction in WaveNetAutoEncoder.__init__/createDecoder
+ * (model.py:76-135,158-200) or ParallelWaveNet.__init__/createNetwork
+ * (model.py:291-314,489-535).  Allocates the device weight arena on the current device. */
+int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out);
+int srwn_destroy(srwn_handle_t h);
+
+/* Replaces tf.train.Saver.restore / variable assignment (model.py:217-228,540-555).
+ * `name` is the TF variable name (e.g. "WaveNetAutoEncoder/Decoder/conv1d_3/kernel",
+ * "ParallelWaveNet/Flow2/Flow2/dilated_conv_7_filter/dilated_conv_7_Kernel"); `data` is
+ * HOST fp32 in TF layout ([K,Cin,Cout] kernels).  Dead variables of the reference graph
+ * (the `_gate` convs ops.py:31-33; the student's skip convs model.py:438-454) are
+ * accepted and ignored.  Returns SRWN_ERR_WEIGHTS for unknown names or wrong shapes. */
+int srwn_set_weight(srwn_handle_t h, const char* name, const float* data,
+                    const int64_t* shape, int32_t ndim);
+/* Reads a variable back (tf.train.Saver.save, model.py:230-239). `data` is HOST memory
+ * with room for `count` floats. */
+int srwn_get_weight(srwn_handle_t h, const char* name, float* data, int64_t count);
+/* Checks that every live variable was set and builds the packed operand images the
+ * kernels read (bf16 UMMA layouts, summed skip bias). Must follow any srwn_set_weight. */
+int srwn_commit_weights(srwn_handle_t h, void* stream);
+
+/* 1 if `op` (enum srwn_op) is built for `precision` with this handle's configuration, else 0. */
+int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision);
+int srwn_workspace_bytes(srwn_handle_t h, int32_t op, int32_t B, int32_t T,
+                         int32_t precision, size_t* bytes);
+
+/* ---- teacher (model.py:158-200) ------------------------------------------------- */
+/* get_logits(inputs, encoding) (model.py:279-285): x [B,T] teacher-forcing audio,
+ * enc [B,T/P,C] -> logits [B,T,4M]. */
+int srwn_teacher_logits(srwn_handle_t h, const float* x, const float* enc, float* logits,
+                        int32_t B, int32_t T, int32_t precision,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* loss_encoding (model.py:114-115): decoder teacher-forced on x_in, mixture-of-logistics
+ * negative log-likelihood of x_scored (the reference scores the same audio; distillation
+ * scores the student's output against logits of the real audio, model.py:374).
+ * nll_out [B,T] (ops.py:175, sum_all=False) and/or nll_sum [1] (ops.py:172); either
+ * may be NULL.  logits_out [B,T,4M] optional (NULL to skip the store). */
+int srwn_teacher_nll(srwn_handle_t h, const float* x_in, const float* enc,
+                     const float* x_scored, float* nll_out, float* nll_sum,
+                     float* logits_out, int32_t B, int32_t T, int32_t precision,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* The autoregressive loop of teacher.py:153-170 restated with per-layer dilation
+ * queues: x[t] = clip(MoL_sample(logits_t)), logits_t from x[<t] and enc[t/P].
+ * u1 [B,T,M], u2 [B,T] are the uniforms of ops.py:187,196 (injected for parity).
+ * x_out [B,T]; logits_out [B,T,4M] optional. */
+int srwn_teacher_generate(srwn_handle_t h, const float* enc, const float* u1,
+                          const float* u2, float* x_out, float* logits_out,
+                          int32_t B, int32_t T,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- student (model.py:415-535) ------------------------------------------------- */
+/* generate(sess, inputs, encoding) (model.py:570-576): z [B,T] logistic noise ->
+ * out [B,T] = clip(z*s_tot + mu_tot, -1, 1) (model.py:535); s_tot, mu_tot [B,T]
+ * (model.py:517-533) and x_last [B,T] (chained flow output) are optional outputs. */
+int srwn_student_forward(srwn_handle_t h, const float* z, const float* enc, float* out,
+                         float* s_tot, float* mu_tot, float* x_last,
+                         int32_t B, int32_t T, int32_t precision,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stateless ops (ops.py) ----------------------------------------------------- */
+/* _DilatedCausalConv1d / DilatedCausalConv1d (ops.py:6-20): x [B,T,Cin],
+ * filters [K,Cin,Cout], bias [Cout] or NULL -> y [B,T,Cout]. */
+int srwn_dilated_causal_conv1d(const float* x, const float* filters, const float* bias,
+                               float* y, int32_t B, int32_t T, int32_t Cin, int32_t Cout,
+                               int32_t K, int32_t dilation, void* stream);
+/* ResidualDilationLayer (ops.py:23-46): x [B,T,R] -> dense [B,T,R], skip [B,T,S]
+ * (skip_k/skip_b/skip may be NULL). Gate = sigmoid(tanh(filter_conv)) as in ops.py:33. */
+int srwn_residual_dilation_layer(const float* x, const float* filt_k, const float* filt_b,
+                                 const float* res_k, const float* res_b,
+                                 const float* skip_k, const float* skip_b,
+                                 float* dense, float* skip, int32_t B, int32_t T,
+                                 int32_t R, int32_t S, int32_t K, int32_t dilation,
+                                 void* stream);
+/* RightShift (ops.py:78-80). */
+int srwn_right_shift(const float* x, float* y, int32_t B, int32_t T, int32_t C,
+                     int32_t shift, void* stream);
+/* ResizeEmbeddingNearestNeighbor (ops.py:64-74): x [B,L,C] -> y [B,out_size,C]. */
+int srwn_resize_nearest(const float* x, float* y, int32_t B, int32_t L, int32_t C,
+                        int32_t out_size, void* stream);
+/* discretized_mix_logistic_loss (ops.py:124-175): x [B,T], l [B,T,4M];
+ * nll_out [B,T] and/or nll_sum [1] (either may be NULL). */
+int srwn_mol_loss(const float* x, const float* l, float* nll_out, float* nll_sum,
+                  int32_t B, int32_t T, int32_t M, void* stream);
+/* sample_from_discretized_mix_logistic (ops.py:178-201) with injected uniforms:
+ * l [B,T,4M], u1 [B,T,M], u2 [B,T] -> out [B,T]; idx_out [B,T] int32 (the Gumbel-argmax
+ * mixture index of ops.py:187) optional. */
+int srwn_mol_sample(const float* l, const float* u1, const float* u2, float* out,
+                    int32_t* idx_out, int32_t B, int32_t T, int32_t M, void* stream);
+
+/* Number of kernels this library launched on behalf of the calling process since load
+ * (bench.py's gpu_launches). */
+int64_t srwn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRWN_H_ */

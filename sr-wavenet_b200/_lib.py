@@ -1,0 +1,88 @@
+"""ctypes binding of libsrwn.so (include/srwn.h).  No torch types cross this boundary:
+tensors are passed as raw device pointers (``tensor.data_ptr()``) and the stream as the
+``cudaStream_t`` integer.  There is no fallback: if the library is missing, ``load()`` raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrwn.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_WEIGHTS, ERR_UNSUPPORTED, ERR_WORKSPACE = range(6)
+TEACHER, STUDENT = 0, 1
+FP32, BF16 = 0, 1
+OP_TEACHER_LOGITS, OP_TEACHER_NLL, OP_TEACHER_GENERATE, OP_STUDENT_FORWARD = range(4)
+PRECISIONS = {"fp32": FP32, "bf16": BF16}
+
+
+class SrwnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libsrwn error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("n_layers", ctypes.c_int32),
+                ("dilations", ctypes.POINTER(ctypes.c_int32)), ("filter_width", ctypes.c_int32),
+                ("dilation_channels", ctypes.c_int32), ("skip_channels", ctypes.c_int32),
+                ("cond_channels", ctypes.c_int32), ("pool_stride", ctypes.c_int32),
+                ("num_mixtures", ctypes.c_int32), ("num_flows", ctypes.c_int32)]
+
+
+_vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+_fp = ctypes.c_void_p   # device float* (raw address)
+
+# name -> (restype, argtypes); every symbol include/srwn.h declares
+SIGNATURES = {
+    "srwn_abi_version": (ctypes.c_int, []),
+    "srwn_last_error": (ctypes.c_char_p, []),
+    "srwn_launch_count": (_i64, []),
+    "srwn_create": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.POINTER(_vp)]),
+    "srwn_destroy": (ctypes.c_int, [_vp]),
+    "srwn_set_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(_i64), _i32]),
+    "srwn_get_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, _i64]),
+    "srwn_commit_weights": (ctypes.c_int, [_vp, _vp]),
+    "srwn_supports": (ctypes.c_int, [_vp, _i32, _i32]),
+    "srwn_workspace_bytes": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, ctypes.POINTER(_sz)]),
+    "srwn_teacher_logits": (ctypes.c_int, [_vp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_teacher_nll": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_teacher_generate": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_student_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_dilated_causal_conv1d": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "srwn_residual_dilation_layer": (ctypes.c_int, [_fp] * 9 + [_i32] * 6 + [_vp]),
+    "srwn_right_shift": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),
+    "srwn_resize_nearest": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),
+    "srwn_mol_loss": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp]),
+    "srwn_mol_sample": (ctypes.c_int, [_fp, _fp, _fp, _fp, _vp, _i32, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads libsrwn.so (built in-tree by ``__graft_entry__.build()``).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libsrwn.so not found at %s: build it with `python __graft_entry__.py` "
+            "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.srwn_abi_version() != 1:
+        raise RuntimeError("libsrwn.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != OK:
+        raise SrwnError(rc, load().srwn_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(load().srwn_launch_count())

@@ -1,0 +1,378 @@
+// fp32 FFMA path of the residual stack (parity path, <= 1e-4 relative vs the oracle).
+//
+// One launch per layer; the residual stream round-trips through HBM as fp32.  This is the
+// reference-grade path and the GPU-side cross-check for the fused bf16 tcgen05 kernel
+// (fused_bf16.cu), which is the one the benchmark times.
+//
+// Stored tensor convention: `hc_i` = the block input of layer i = h_i + upsampled
+// conditioning of layer i (model.py:183 adds it before ResidualDilationLayer, so it also
+// feeds the `inputs + residual` term at ops.py:40 and is zero-padded like the rest).
+#include "common.cuh"
+
+// cond[b][frame][layer][r] = enc[b][frame][:] @ cond_k[layer] + cond_b[layer]   (model.py:180/431)
+__global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
+                       const float* __restrict__ cond_b, float* __restrict__ cond,
+                       int frames_total, int L, int C) {
+  __shared__ float s_enc[kMaxCond];
+  const int bf = blockIdx.x;
+  if (threadIdx.x < C) s_enc[threadIdx.x] = enc[(size_t)bf * C + threadIdx.x];
+  __syncthreads();
+  for (int o = threadIdx.x; o < L * kR; o += blockDim.x) {
+    const int l = o / kR, r = o % kR;
+    const float* wk = cond_k + (size_t)l * C * kR + r;
+    float acc = cond_b[l * kR + r];
+    for (int c = 0; c < C; c++) acc = fmaf(s_enc[c], wk[(size_t)c * kR], acc);
+    cond[(size_t)bf * L * kR + o] = acc;
+  }
+}
+
+// hc_0[b][t][r] = x[t-2]*k[0][r] + x[t-1]*k[1][r] + b[r] + cond[b][t/P][0][r]
+// (RightShift ops.py:78-80, then the K=2, d=1 causal conv model.py:173/424)
+__global__ void k_front(const float* __restrict__ x, const float* __restrict__ fk,
+                        const float* __restrict__ fb, const float* __restrict__ cond,
+                        float* __restrict__ hc, int T, int P, int L, int frames) {
+  const int b = blockIdx.y;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over T*R
+  if (idx >= (int64_t)T * kR) return;
+  const int t = (int)(idx / kR), r = (int)(idx % kR);
+  const float* xb = x + (size_t)b * T;
+  const float xm2 = t >= 2 ? xb[t - 2] : 0.f, xm1 = t >= 1 ? xb[t - 1] : 0.f;
+  float v = fmaf(xm2, fk[r], fmaf(xm1, fk[kR + r], fb[r]));
+  v += cond[(((size_t)b * frames + t / P) * L + 0) * kR + r];
+  hc[((size_t)b * T + t) * kR + r] = v;
+}
+
+// One residual block (ops.py:23-46) on a tile of 64 time steps.
+constexpr int kTT = 64;       // time steps per CTA
+constexpr int kAP = kR + 4;   // padded row pitch (floats), keeps 16-byte alignment
+struct LayerSmem {
+  float a_tap[kTT][kAP];
+  float a_cur[kTT][kAP];
+  float c[kTT][kAP];
+  float wf[2 * kR][kR];
+  float wr[kR][kR];
+  float ws[kR][kS];
+  float bf[kR], br[kR], bs[kS];
+};
+
+template <bool SKIP>
+__global__ void __launch_bounds__(256)
+k_layer_f32(const float* __restrict__ hc_in, float* __restrict__ hc_out, float* __restrict__ skip,
+            const float* __restrict__ filt_k, const float* __restrict__ filt_b,
+            const float* __restrict__ res_k, const float* __restrict__ res_b,
+            const float* __restrict__ skip_k, const float* __restrict__ skip_b,
+            const float* __restrict__ cond_next,   // cond + (layer+1)*R, or nullptr for the last layer
+            int T, int d, int P, int L, int frames, int skip_init) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LayerSmem& s = *reinterpret_cast<LayerSmem*>(smem_raw);
+  const int b = blockIdx.y, t0 = blockIdx.x * kTT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* hb = hc_in + (size_t)b * T * kR;
+
+  // stage operands: current rows, rows d steps back (zero before the utterance start), weights
+  for (int i = tid; i < kTT * (kR / 4); i += 256) {
+    const int row = i / (kR / 4), q = i % (kR / 4);
+    const int t = t0 + row;
+    float4 cur = make_float4(0, 0, 0, 0), tap = cur;
+    if (t < T) {
+      cur = *reinterpret_cast<const float4*>(hb + (size_t)t * kR + q * 4);
+      if (t - d >= 0) tap = *reinterpret_cast<const float4*>(hb + (size_t)(t - d) * kR + q * 4);
+    }
+    *reinterpret_cast<float4*>(&s.a_cur[row][q * 4]) = cur;
+    *reinterpret_cast<float4*>(&s.a_tap[row][q * 4]) = tap;
+  }
+  for (int i = tid; i < 2 * kR * kR; i += 256) (&s.wf[0][0])[i] = filt_k[i];
+  for (int i = tid; i < kR * kR; i += 256) (&s.wr[0][0])[i] = res_k[i];
+  if (SKIP) for (int i = tid; i < kR * kS; i += 256) (&s.ws[0][0])[i] = skip_k[i];
+  if (tid < kR) { s.bf[tid] = filt_b[tid]; s.br[tid] = res_b[tid]; }
+  if (SKIP && tid < kS) s.bs[tid] = skip_b[tid];
+  __syncthreads();
+
+  const int r0 = warp * 8;     // this warp owns rows r0..r0+7; lane = output channel
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) acc[r] = s.bf[lane];
+  // filter conv: W[0] pairs with x[t-d], W[1] with x[t] (ops.py:6-10)
+#pragma unroll 4
+  for (int k4 = 0; k4 < kR / 4; k4++) {
+    const float w0 = s.wf[k4 * 4 + 0][lane], w1 = s.wf[k4 * 4 + 1][lane],
+                w2 = s.wf[k4 * 4 + 2][lane], w3 = s.wf[k4 * 4 + 3][lane];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const float4 a = *reinterpret_cast<const float4*>(&s.a_tap[r0 + r][k4 * 4]);
+      acc[r] = fmaf(a.x, w0, acc[r]); acc[r] = fmaf(a.y, w1, acc[r]);
+      acc[r] = fmaf(a.z, w2, acc[r]); acc[r] = fmaf(a.w, w3, acc[r]);
+    }
+  }
+#pragma unroll 4
+  for (int k4 = 0; k4 < kR / 4; k4++) {
+    const float w0 = s.wf[kR + k4 * 4 + 0][lane], w1 = s.wf[kR + k4 * 4 + 1][lane],
+                w2 = s.wf[kR + k4 * 4 + 2][lane], w3 = s.wf[kR + k4 * 4 + 3][lane];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const float4 a = *reinterpret_cast<const float4*>(&s.a_cur[r0 + r][k4 * 4]);
+      acc[r] = fmaf(a.x, w0, acc[r]); acc[r] = fmaf(a.y, w1, acc[r]);
+      acc[r] = fmaf(a.z, w2, acc[r]); acc[r] = fmaf(a.w, w3, acc[r]);
+    }
+  }
+  // gate: tanh, then sigmoid OF THE TANH (ops.py:28,33), product (ops.py:36)
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const float f = tanhf(acc[r]);
+    const float g = 1.0f / (1.0f + expf(-f));
+    s.c[r0 + r][lane] = f * g;
+  }
+  __syncwarp();
+
+  // residual 1x1 (ops.py:39) and dense = (inputs + residual) * sqrt(1/2) (ops.py:40)
+#pragma unroll
+  for (int r = 0; r < 8; r++) acc[r] = s.br[lane];
+#pragma unroll 4
+  for (int k4 = 0; k4 < kR / 4; k4++) {
+    const float w0 = s.wr[k4 * 4 + 0][lane], w1 = s.wr[k4 * 4 + 1][lane],
+                w2 = s.wr[k4 * 4 + 2][lane], w3 = s.wr[k4 * 4 + 3][lane];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const float4 a = *reinterpret_cast<const float4*>(&s.c[r0 + r][k4 * 4]);
+      acc[r] = fmaf(a.x, w0, acc[r]); acc[r] = fmaf(a.y, w1, acc[r]);
+      acc[r] = fmaf(a.z, w2, acc[r]); acc[r] = fmaf(a.w, w3, acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int t = t0 + r0 + r;
+    if (t < T) {
+      float v = (s.a_cur[r0 + r][lane] + acc[r]) * SRWN_SQRT_HALF;
+      if (cond_next) v += cond_next[((size_t)b * frames + t / P) * L * kR + lane];
+      hc_out[((size_t)b * T + t) * kR + lane] = v;
+    }
+  }
+
+  if (SKIP) {   // skip 1x1 (ops.py:44), accumulated over layers (model.py:190)
+    float sk[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) sk[r][j] = s.bs[lane + 32 * j];
+#pragma unroll 2
+    for (int k4 = 0; k4 < kR / 4; k4++) {
+      float w[4][4];
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[kk][j] = s.ws[k4 * 4 + kk][lane + 32 * j];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const float4 a = *reinterpret_cast<const float4*>(&s.c[r0 + r][k4 * 4]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          sk[r][j] = fmaf(a.x, w[0][j], sk[r][j]); sk[r][j] = fmaf(a.y, w[1][j], sk[r][j]);
+          sk[r][j] = fmaf(a.z, w[2][j], sk[r][j]); sk[r][j] = fmaf(a.w, w[3][j], sk[r][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int t = t0 + r0 + r;
+      if (t < T) {
+        float* dst = skip + ((size_t)b * T + t) * kS + lane;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float prev = skip_init ? 0.f : dst[32 * j];
+          dst[32 * j] = prev + sk[r][j];
+        }
+      }
+    }
+  }
+}
+
+int run_stack_f32(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T,
+                  float* h0, float* h1, float* skip, float* cond, float** h_final,
+                  cudaStream_t st) {
+  const float* w = stack_w(c, stack);
+  const StackOffsets& o = c->off;
+  const int L = c->cfg.n_layers, P = c->cfg.pool_stride, C = c->cfg.cond_channels;
+  const int frames = T / P;
+  const bool with_skip = c->cfg.kind == SRWN_TEACHER;
+  k_cond<<<B * frames, 256, 0, st>>>(enc, w + o.cond_k, w + o.cond_b, cond, B * frames, L, C);
+  SRWN_LAUNCH_CHECK();
+  {
+    dim3 grid((unsigned)(((int64_t)T * kR + 255) / 256), B);
+    k_front<<<grid, 256, 0, st>>>(xin, w + o.front_k, w + o.front_b, cond, h0, T, P, L, frames);
+    SRWN_LAUNCH_CHECK();
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    SRWN_CUDA(cudaFuncSetAttribute(k_layer_f32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(LayerSmem)));
+    SRWN_CUDA(cudaFuncSetAttribute(k_layer_f32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(LayerSmem)));
+    attr_done = true;
+  }
+  float* cur = h0;
+  float* nxt = h1;
+  dim3 grid((T + kTT - 1) / kTT, B);
+  for (int l = 0; l < L; l++) {
+    const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
+    if (with_skip)
+      k_layer_f32<true><<<grid, 256, sizeof(LayerSmem), st>>>(
+          cur, nxt, skip, w + o.filt_k + (size_t)l * 2 * kR * kR, w + o.filt_b + (size_t)l * kR,
+          w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR,
+          w + o.skip_k + (size_t)l * kR * kS, w + o.skip_b + (size_t)l * kS, cond_next, T,
+          c->dilations[l], P, L, frames, l == 0);
+    else
+      k_layer_f32<false><<<grid, 256, sizeof(LayerSmem), st>>>(
+          cur, nxt, nullptr, w + o.filt_k + (size_t)l * 2 * kR * kR, w + o.filt_b + (size_t)l * kR,
+          w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR, nullptr, nullptr,
+          cond_next, T, c->dilations[l], P, L, frames, 0);
+    SRWN_LAUNCH_CHECK();
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  *h_final = cur;
+  return SRWN_OK;
+}
+
+// ---- teacher head: relu -> 1x1 S->S -> relu -> 1x1 S->4M (model.py:191-196) ------------
+constexpr int kHT = 64;
+__global__ void __launch_bounds__(256)
+k_head_f32(const float* __restrict__ skip, const float* __restrict__ w1, const float* __restrict__ b1,
+           const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ logits,
+           int64_t n_rows, int O) {
+  __shared__ __align__(16) float s_a[kHT][kS + 4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * kHT;
+  for (int i = tid; i < kHT * (kS / 4); i += 256) {
+    const int row = i / (kS / 4), q = i % (kS / 4);
+    float4 v = make_float4(0, 0, 0, 0);
+    if (row0 + row < n_rows) v = *reinterpret_cast<const float4*>(skip + (row0 + row) * kS + q * 4);
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    *reinterpret_cast<float4*>(&s_a[row][q * 4]) = v;
+  }
+  __syncthreads();
+  const int r0 = warp * 8;
+  float acc[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[r][j] = b1[lane + 32 * j];
+  for (int k4 = 0; k4 < kS / 4; k4++) {
+    float w[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) w[kk][j] = __ldg(w1 + (size_t)(k4 * 4 + kk) * kS + lane + 32 * j);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const float4 a = *reinterpret_cast<const float4*>(&s_a[r0 + r][k4 * 4]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        acc[r][j] = fmaf(a.x, w[0][j], acc[r][j]); acc[r][j] = fmaf(a.y, w[1][j], acc[r][j]);
+        acc[r][j] = fmaf(a.z, w[2][j], acc[r][j]); acc[r][j] = fmaf(a.w, w[3][j], acc[r][j]);
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) s_a[r0 + r][lane + 32 * j] = fmaxf(acc[r][j], 0.f);
+  __syncwarp();
+  float lg[8];
+  const int oc = lane < O ? lane : 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) lg[r] = b2[oc];
+  for (int k4 = 0; k4 < kS / 4; k4++) {
+    const float w0 = __ldg(w2 + (size_t)(k4 * 4 + 0) * O + oc), w1v = __ldg(w2 + (size_t)(k4 * 4 + 1) * O + oc),
+                w2v = __ldg(w2 + (size_t)(k4 * 4 + 2) * O + oc), w3 = __ldg(w2 + (size_t)(k4 * 4 + 3) * O + oc);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const float4 a = *reinterpret_cast<const float4*>(&s_a[r0 + r][k4 * 4]);
+      lg[r] = fmaf(a.x, w0, lg[r]); lg[r] = fmaf(a.y, w1v, lg[r]);
+      lg[r] = fmaf(a.z, w2v, lg[r]); lg[r] = fmaf(a.w, w3, lg[r]);
+    }
+  }
+  if (lane < O) {
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (row0 + r0 + r < n_rows) logits[(row0 + r0 + r) * O + lane] = lg[r];
+  }
+}
+
+int run_teacher_head_f32(srwn_ctx* c, const float* skip, float* logits, int B, int T, cudaStream_t st) {
+  const float* w = stack_w(c, 0);
+  const StackOffsets& o = c->off;
+  const int64_t n = (int64_t)B * T;
+  k_head_f32<<<(unsigned)((n + kHT - 1) / kHT), 256, 0, st>>>(
+      skip, w + o.head1_k, w + o.head1_b, w + o.head2_k, w + o.head2_b, logits, n,
+      4 * c->cfg.num_mixtures);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+// ---- student flow head + affine (model.py:451-452, 479-482) ---------------------------------
+// params = relu(h) @ W[R][2] + b; scale = exp(p0); mean = p1; out = x*scale + mean
+__global__ void k_flow_head(const float* __restrict__ h, const float* __restrict__ xin,
+                            const float* __restrict__ hk, const float* __restrict__ hb,
+                            float* __restrict__ scale, float* __restrict__ mean,
+                            float* __restrict__ xout, int64_t n) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gid >> 3;          // 8 lanes per time step
+  const int q = (int)(gid & 7);
+  float p0 = 0.f, p1 = 0.f;
+  if (row < n) {
+    const float4 v = *reinterpret_cast<const float4*>(h + row * kR + q * 4);
+    const float e[4] = {fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      p0 = fmaf(e[i], hk[(q * 4 + i) * 2 + 0], p0);
+      p1 = fmaf(e[i], hk[(q * 4 + i) * 2 + 1], p1);
+    }
+  }
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {
+    p0 += __shfl_xor_sync(0xffffffffu, p0, s);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, s);
+  }
+  if (row < n && q == 0) {
+    const float sc = expf(p0 + hb[0]);       // no clamp on the log-scale (model.py:479)
+    const float mu = p1 + hb[1];
+    scale[row] = sc; mean[row] = mu;
+    xout[row] = fmaf(xin[row], sc, mu);      // model.py:482
+  }
+}
+
+int run_flow_head_f32(srwn_ctx* c, int stack, const float* h, const float* xin, float* scale,
+                      float* mean, float* xout, int B, int T, cudaStream_t st) {
+  const float* w = stack_w(c, stack);
+  const int64_t n = (int64_t)B * T;
+  k_flow_head<<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(h, xin, w + c->off.head1_k,
+                                                               w + c->off.head1_b, scale, mean, xout, n);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+// s_tot = prod s_f; mu_tot = sum_f mu_f * prod_{j>f} s_j in the reference's loop order
+// (model.py:517-533); out = clip(z*s_tot + mu_tot, -1, 1) (model.py:535)
+__global__ void k_flow_compose(const float* __restrict__ z, const float* __restrict__ scales,
+                               const float* __restrict__ means, int F, float* __restrict__ out,
+                               float* __restrict__ s_tot, float* __restrict__ mu_tot, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float st = 1.f, mt = 0.f;
+  for (int f = 0; f < F; f++) {
+    st *= scales[(size_t)f * n + i];
+    float mu = means[(size_t)f * n + i];
+    for (int j = f + 1; j < F; j++) mu *= scales[(size_t)j * n + i];
+    mt += mu;
+  }
+  if (s_tot) s_tot[i] = st;
+  if (mu_tot) mu_tot[i] = mt;
+  out[i] = fminf(fmaxf(fmaf(z[i], st, mt), -1.f), 1.f);
+}
+
+int run_flow_compose(const float* z, const float* scales, const float* means, int F, float* out,
+                     float* s_tot, float* mu_tot, int64_t n, cudaStream_t st) {
+  k_flow_compose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, scales, means, F, out, s_tot, mu_tot, n);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}

@@ -1,0 +1,436 @@
+"""Python-facing mirror of the reference's ``model.py`` for the hot path: same class names,
+constructor arguments and method names/argument meaning as ``WaveNetAutoEncoder``
+(model.py:75-285) and ``ParallelWaveNet`` (model.py:290-656).  Each former ``sess.run`` is one
+call into libsrwn.so (include/srwn.h).  Like the reference's ``feed_dict`` boundary, methods take
+NumPy arrays (or torch tensors) and return NumPy arrays; CUDA tensors in -> CUDA tensors out,
+with no host copies (used for device-resident benchmarking).
+
+Outside the hot path: the teacher encoder (``encode`` / ``reconstruct``) and
+training (``train`` / ``train_fast``) raise NotImplementedError.
+"""
+import ctypes
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, synth
+
+
+def _as_i32_array(values):
+    arr = (ctypes.c_int32 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+class _Engine(object):
+    """Owns one libsrwn handle plus the caller-side workspace and pinned staging buffers."""
+
+    def __init__(self, kind, dilations, filter_width, dilation_channels, skip_channels, cond_channels,
+                 pool_stride, num_mixtures=0, num_flows=0):
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("the SR-WaveNet hot path needs a CUDA device (no CPU fallback)")
+        self._dil = _as_i32_array(dilations)
+        cfg = _lib.Config(kind, len(dilations), self._dil, filter_width, dilation_channels, skip_channels,
+                          cond_channels, pool_stride, num_mixtures, num_flows)
+        h = ctypes.c_void_p()
+        _lib.check(lib.srwn_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self.lib, self.h, self.kind = lib, h, kind
+        self.cond_channels = cond_channels
+        self.pool_stride = pool_stride
+        self._ws = None
+        self._pinned = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.srwn_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_weights(self, weights, prefix_filter=None):
+        for name, arr in weights.items():
+            if prefix_filter and not name.startswith(prefix_filter):
+                continue
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+            _lib.check(self.lib.srwn_set_weight(self.h, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
+                                                shape, a.ndim))
+        _lib.check(self.lib.srwn_commit_weights(self.h, torch.cuda.current_stream().cuda_stream))
+
+    def get_weight(self, name, shape):
+        out = np.empty(shape, dtype=np.float32)
+        _lib.check(self.lib.srwn_get_weight(self.h, name.encode(), out.ctypes.data_as(ctypes.c_void_p), out.size))
+        return out
+
+    def workspace(self, op, B, T, precision):
+        n = ctypes.c_size_t()
+        _lib.check(self.lib.srwn_workspace_bytes(self.h, op, B, T, precision, ctypes.byref(n)))
+        if self._ws is None or self._ws.numel() < n.value:
+            self._ws = None
+            self._ws = torch.empty(max(n.value, 256), dtype=torch.uint8, device="cuda")
+        return self._ws.data_ptr(), self._ws.numel()
+
+    def to_device(self, a, key):
+        """NumPy / CPU tensor -> CUDA fp32 tensor through a persistent pinned staging buffer."""
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.float().contiguous(), True
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        t = t.float().contiguous()
+        if not t.is_pinned():
+            buf = self._pinned.get(key)
+            if buf is None or buf.shape != t.shape:
+                buf = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
+                self._pinned[key] = buf
+            buf.copy_(t)
+            t = buf
+        return t.to("cuda", non_blocking=True), False
+
+    def to_host(self, t, on_device):
+        if on_device:
+            return t
+        key = ("out", tuple(t.shape))
+        buf = self._pinned.get(key)
+        if buf is None:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._pinned[key] = buf
+        buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return buf.numpy().copy()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _with_conditions(encoding, conditions, condition_size):
+    """model.py:161-167 / 495-500: tile the global condition over frames and concatenate."""
+    if condition_size > 0:
+        if conditions is None:
+            raise ValueError("condition_size > 0 needs `conditions`")
+        if isinstance(encoding, torch.Tensor):
+            c = torch.as_tensor(conditions, dtype=torch.float32, device=encoding.device)
+            return torch.cat([encoding, c[:, None, :].expand(-1, encoding.shape[1], -1)], dim=2)
+        c = np.asarray(conditions, dtype=np.float32)
+        return np.concatenate([encoding, np.tile(c[:, None, :], [1, encoding.shape[1], 1])], axis=2)
+    return encoding
+
+
+class _CheckpointMixin(object):
+    """npz stand-in for tf.train.Saver (model.py:217-239): ``<logdir>/model.ckpt-<step>.npz`` plus a
+    ``checkpoint`` state file; ``save`` is throttled to once per 60 s unless ``force``."""
+
+    def _save(self, logdir, global_step, force):
+        if force or time.time() - self.last_checkpoint_time > 60:
+            if not os.path.isdir(logdir):
+                os.makedirs(logdir)
+            path = os.path.join(logdir, 'model.ckpt-%d' % global_step)
+            np.savez(path + '.npz', **self.get_weights())
+            with open(os.path.join(logdir, 'checkpoint'), 'w') as f:
+                f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
+            self.last_checkpoint_time = time.time()
+            return True
+        return False
+
+    def _load(self, logdir):
+        if logdir is not None and os.path.exists(logdir):
+            state = os.path.join(logdir, 'checkpoint')
+            if os.path.exists(state):
+                with open(state) as f:
+                    name = f.readline().split('"')[1]
+                path = os.path.join(logdir, name + '.npz')
+                if not os.path.exists(path):
+                    print('Could not find checkpoint at %s' % path)
+                    return False
+                with np.load(path) as z:
+                    self.set_weights({k: z[k] for k in z.files})
+                print('Restoring previous session')
+                return True
+        return None
+
+
+class WaveNetAutoEncoder(_CheckpointMixin):
+    """model.py:75-285.  Decoder path only (the hot path); constructor signature kept verbatim."""
+
+    def __init__(self, input_size, condition_size, num_mixtures, dilations, filter_width=2,
+                 encoder_channels=128, dilation_channels=32, skip_channels=256, latent_channels=16,
+                 pool_stride=512, name='WaveNetAutoEncoder', learning_rate=0.001):
+        self.input_size = input_size
+        self.condition_size = condition_size
+        self.num_mixtures = num_mixtures
+        self.dilations = list(dilations)
+        self.filter_width = filter_width
+        self.encoder_channels = encoder_channels
+        self.dilation_channels = dilation_channels
+        self.skip_channels = skip_channels
+        self.latent_channels = latent_channels
+        self.pool_stride = pool_stride
+        self.name = name
+        self.learning_rate = learning_rate
+        self.precision = "fp32"
+        self.last_checkpoint_time = time.time()
+        self.createNetwork()
+
+    # -- graph construction stand-ins ------------------------------------------------------
+    def createNetwork(self):
+        """model.py:202-215: the reference builds placeholders + encoder + two decoder instances;
+        here it creates the decoder engine and Glorot-initialised variables."""
+        self._eng = _Engine(_lib.TEACHER, self.dilations, self.filter_width, self.dilation_channels,
+                            self.skip_channels, self.latent_channels + self.condition_size,
+                            self.pool_stride, num_mixtures=self.num_mixtures)
+        w = synth.make_teacher_weights(self.dilations, self.filter_width, self.dilation_channels,
+                                       self.skip_channels, self.latent_channels + self.condition_size,
+                                       self.num_mixtures, seed=None, dead_vars=True)
+        for k in w:                      # TF initialises biases to zero (ops.py:18)
+            if k.endswith('Bias') or k.endswith('/bias'):
+                w[k][...] = 0
+        self._weights = {}
+        self.set_weights(w)
+
+    def createEncoder(self, h, reuse=False):
+        raise NotImplementedError("the teacher encoder (model.py:137-155) is outside the hot path; "
+                                  "pass a precomputed `encoding`")
+
+    def createDecoder(self, truth, encoding, conditions, reuse=False, u1=None, u2=None, precision=None):
+        """model.py:158-200 -> (logits [B,T,4M], out [B,T]).  truth [B,T,1] or [B,T]."""
+        from . import ops
+        truth2 = truth[..., 0] if getattr(truth, "ndim", 2) == 3 else truth
+        logits = self.get_logits(truth2, encoding, conditions, precision=precision)
+        out = ops.sample_from_discretized_mix_logistic(logits, self.num_mixtures, u1, u2)
+        out = out[..., 0]
+        if not isinstance(logits, torch.Tensor):
+            out = out.cpu().numpy()
+        return logits, out
+
+    # -- weights -----------------------------------------------------------------------------
+    def set_weights(self, weights):
+        """name -> ndarray with TF variable names (``WaveNetAutoEncoder/Decoder/...``)."""
+        self._eng.set_weights(weights)
+        self._weights.update({k: np.array(v, dtype=np.float32) for k, v in weights.items()})
+
+    def get_weights(self):
+        return dict(self._weights)
+
+    def available_precisions(self):
+        return ["fp32", "bf16"] if _fused_available(self._eng) else ["fp32"]
+
+    def load(self, logdir):
+        return self._load(logdir)
+
+    def save(self, logdir, global_step, force=False):
+        return self._save(logdir, global_step, force)
+
+    # -- sess.run wrappers -------------------------------------------------------------------
+    def train(self, inputs, conditions=None):
+        raise NotImplementedError("teacher training (model.py:242-248) is outside the hot path")
+
+    def encode(self, inputs, conditions=None):
+        raise NotImplementedError("the teacher encoder (model.py:250-255) is outside the hot path")
+
+    def reconstruct(self, inputs, conditions=None):
+        raise NotImplementedError("reconstruct (model.py:257-262) needs the encoder; use "
+                                  "reconstruct_with_encoding(inputs, encoding)")
+
+    def _prec(self, precision):
+        return _lib.PRECISIONS[precision or self.precision]
+
+    def get_logits(self, inputs, encoding, conditions=None, precision=None):
+        """model.py:279-285 -> logits [B,T,4M]."""
+        eng = self._eng
+        enc = _with_conditions(encoding, conditions, self.condition_size)
+        x, on_dev = eng.to_device(inputs, "x")
+        e, _ = eng.to_device(enc, "enc")
+        B, T = x.shape
+        self._check(e, B, T)
+        prec = self._prec(precision)
+        ws, wsn = eng.workspace(_lib.OP_TEACHER_LOGITS, B, T, prec)
+        logits = torch.empty(B, T, 4 * self.num_mixtures, dtype=torch.float32, device="cuda")
+        _lib.check(eng.lib.srwn_teacher_logits(eng.h, x.data_ptr(), e.data_ptr(), logits.data_ptr(), B, T,
+                                               prec, ws, wsn, _stream()))
+        return eng.to_host(logits, on_dev)
+
+    def nll(self, inputs, encoding, conditions=None, scored=None, sum_all=True, precision=None):
+        """``loss_encoding`` of model.py:114-115: teacher-forced mixture-of-logistics negative
+        log-likelihood.  ``scored`` (default: ``inputs``) is the audio whose likelihood is taken
+        (model.py:374 scores the student's output against logits of the real audio).
+        Returns a Python float (sum_all=True, ops.py:172) or [B,T,1] (ops.py:175)."""
+        eng = self._eng
+        enc = _with_conditions(encoding, conditions, self.condition_size)
+        x, on_dev = eng.to_device(inputs, "x")
+        e, _ = eng.to_device(enc, "enc")
+        xs = x if scored is None else eng.to_device(scored, "xs")[0]
+        B, T = x.shape
+        self._check(e, B, T)
+        prec = self._prec(precision)
+        ws, wsn = eng.workspace(_lib.OP_TEACHER_NLL, B, T, prec)
+        if sum_all:
+            out = torch.empty(1, dtype=torch.float32, device="cuda")
+            _lib.check(eng.lib.srwn_teacher_nll(eng.h, x.data_ptr(), e.data_ptr(), xs.data_ptr(), None,
+                                                out.data_ptr(), None, B, T, prec, ws, wsn, _stream()))
+            return out if on_dev else float(eng.to_host(out, False)[0])
+        out = torch.empty(B, T, 1, dtype=torch.float32, device="cuda")
+        _lib.check(eng.lib.srwn_teacher_nll(eng.h, x.data_ptr(), e.data_ptr(), xs.data_ptr(), out.data_ptr(),
+                                            None, None, B, T, prec, ws, wsn, _stream()))
+        return eng.to_host(out, on_dev)
+
+    def reconstruct_with_encoding(self, inputs, encoding, conditions=None, u1=None, u2=None,
+                                  precision=None):
+        """model.py:264-270 -> [B,T]: one teacher-forced pass + parallel sampling from the logits
+        (``out_from_encoding``).  ``u1``/``u2`` inject the sampler's uniforms (ops.py:187,196)."""
+        _, out = self.createDecoder(inputs, encoding, conditions, reuse=True, u1=u1, u2=u2,
+                                    precision=precision)
+        return out
+
+    def generate(self, encoding, conditions=None, u1=None, u2=None, num_samples=None,
+                 return_logits=False, zero_last=False):
+        """Autoregressive generation, the queue-based restatement of teacher.py:153-170:
+        x[t] = clip(MoL_sample(logits_t)) with logits_t from x[<t] and encoding[t // pool_stride].
+        ``zero_last=True`` reproduces teacher.py:170, which zeroes the final sample."""
+        eng = self._eng
+        enc = _with_conditions(encoding, conditions, self.condition_size)
+        e, on_dev = eng.to_device(enc, "enc")
+        B = e.shape[0]
+        T = num_samples if num_samples is not None else e.shape[1] * self.pool_stride
+        self._check(e, B, T)
+        lo, hi = 1e-5, 1.0 - 1e-5
+        u1 = torch.rand(B, T, self.num_mixtures, device="cuda") * (hi - lo) + lo if u1 is None \
+            else eng.to_device(u1, "u1")[0]
+        u2 = torch.rand(B, T, device="cuda") * (hi - lo) + lo if u2 is None else eng.to_device(u2, "u2")[0]
+        ws, wsn = eng.workspace(_lib.OP_TEACHER_GENERATE, B, T, _lib.FP32)
+        x = torch.empty(B, T, dtype=torch.float32, device="cuda")
+        logits = torch.empty(B, T, 4 * self.num_mixtures, dtype=torch.float32, device="cuda") \
+            if return_logits else None
+        _lib.check(eng.lib.srwn_teacher_generate(eng.h, e.data_ptr(), u1.data_ptr(), u2.data_ptr(),
+                                                 x.data_ptr(), logits.data_ptr() if return_logits else None,
+                                                 B, T, ws, wsn, _stream()))
+        if zero_last:
+            x[:, T - 1:] = 0            # teacher.py:170
+        if return_logits:
+            return eng.to_host(x, on_dev), eng.to_host(logits, on_dev)
+        return eng.to_host(x, on_dev)
+
+    def _check(self, e, B, T):
+        if e.ndim != 3 or e.shape[0] != B or e.shape[2] != self.latent_channels + self.condition_size:
+            raise ValueError("encoding must be [B, T/pool_stride, %d]" % (self.latent_channels + self.condition_size))
+        if e.shape[1] * self.pool_stride != T:
+            raise ValueError("T=%d must equal pool_stride * frames = %d (model.py:183)"
+                             % (T, e.shape[1] * self.pool_stride))
+
+
+def _fused_available(eng):
+    op = _lib.OP_TEACHER_LOGITS if eng.kind == _lib.TEACHER else _lib.OP_STUDENT_FORWARD
+    return bool(eng.lib.srwn_supports(eng.h, op, _lib.BF16))
+
+
+class ParallelWaveNet(_CheckpointMixin):
+    """model.py:290-656.  ``teacher`` is a checkpoint directory in the reference; here it may also
+    be a ``WaveNetAutoEncoder`` instance or None.  Methods keep the explicit ``sess`` first argument
+    (ignored)."""
+
+    def __init__(self, input_size, condition_size, dilations, teacher, num_flows=2, filter_width=2,
+                 dilation_channels=32, skip_channels=256, latent_channels=16, pool_stride=512,
+                 name='ParallelWaveNet', alpha=1.0, beta=1.0, gamma=1.0, learning_rate=0.001):
+        self.input_size = input_size
+        self.condition_size = condition_size
+        self.dilations = list(dilations)
+        self.teacher = teacher
+        self.num_flows = num_flows
+        self.filter_width = filter_width
+        self.dilation_channels = dilation_channels
+        self.skip_channels = skip_channels
+        self.latent_channels = latent_channels
+        self.pool_stride = pool_stride
+        self.name = name
+        self.alpha, self.beta, self.gamma = alpha, beta, gamma
+        self.learning_rate = learning_rate
+        self.precision = "fp32"
+        self.last_checkpoint_time = time.time()
+        self.createNetwork()
+
+    def createNetwork(self):
+        """model.py:489-535."""
+        self._eng = _Engine(_lib.STUDENT, self.dilations, self.filter_width, self.dilation_channels,
+                            self.skip_channels, self.latent_channels + self.condition_size,
+                            self.pool_stride, num_flows=self.num_flows)
+        w = synth.make_student_weights(self.dilations, self.num_flows, self.filter_width,
+                                       self.dilation_channels, self.skip_channels,
+                                       self.latent_channels + self.condition_size, seed=None)
+        for k in w:
+            if k.endswith('Bias') or k.endswith('/bias'):
+                w[k][...] = 0
+        self._weights = {}
+        self.set_weights(w)
+
+    def createPartialFlow(self, inputs, encoding, scope):
+        raise NotImplementedError("flows run fused inside generate(); see srwn_student_forward")
+
+    createFlow = createPartialFlow
+
+    def set_weights(self, weights):
+        """name -> ndarray with TF variable names (``ParallelWaveNet/Flow{f}/Flow{f}/...``)."""
+        self._eng.set_weights(weights)
+        self._weights.update({k: np.array(v, dtype=np.float32) for k, v in weights.items()})
+
+    def get_weights(self):
+        return dict(self._weights)
+
+    def available_precisions(self):
+        return ["fp32", "bf16"] if _fused_available(self._eng) else ["fp32"]
+
+    def load(self, sess, logdir):
+        if isinstance(self.teacher, str):
+            pass   # the reference restores the imported teacher meta-graph here (model.py:543-544)
+        return self._load(logdir)
+
+    def save(self, sess, logdir, global_step, force=False):
+        return self._save(logdir, global_step, force)
+
+    def _forward(self, inputs, encoding, conditions, precision=None, want=("out",)):
+        eng = self._eng
+        enc = _with_conditions(encoding, conditions, self.condition_size)
+        z, on_dev = eng.to_device(inputs, "z")
+        e, _ = eng.to_device(enc, "enc")
+        B, T = z.shape
+        if e.ndim != 3 or e.shape[0] != B or e.shape[1] * self.pool_stride != T:
+            raise ValueError("encoding must be [B, T/pool_stride, C] with T == pool_stride * frames")
+        prec = _lib.PRECISIONS[precision or self.precision]
+        ws, wsn = eng.workspace(_lib.OP_STUDENT_FORWARD, B, T, prec)
+        bufs = {k: torch.empty(B, T, dtype=torch.float32, device="cuda") for k in set(want) | {"out"}}
+        g = lambda k: bufs[k].data_ptr() if k in bufs else None
+        _lib.check(eng.lib.srwn_student_forward(eng.h, z.data_ptr(), e.data_ptr(), g("out"), g("s_tot"),
+                                                g("mu_tot"), g("x_last"), B, T, prec, ws, wsn, _stream()))
+        return bufs, on_dev
+
+    def generate(self, sess, inputs, encoding, conditions=None, precision=None):
+        """model.py:570-576 -> out [B,T,1] = clip(z*s_tot + mu_tot, -1, 1)."""
+        bufs, on_dev = self._forward(inputs, encoding, conditions, precision)
+        return self._eng.to_host(bufs["out"][:, :, None], on_dev)
+
+    def forward_all(self, inputs, encoding, conditions=None, precision=None):
+        """out, s_tot, mu_tot (model.py:517-535) and the chained flow output, each [B,T]."""
+        bufs, on_dev = self._forward(inputs, encoding, conditions, precision,
+                                     want=("out", "s_tot", "mu_tot", "x_last"))
+        return {k: self._eng.to_host(v, on_dev) for k, v in bufs.items()}
+
+    def getEntropy_fast(self, sess, inputs, encoding, conditions=None):
+        """model.py:595-600: reduce_sum(log(s_tot) + 2) over the whole batch (model.py:356)."""
+        bufs, _ = self._forward(inputs, encoding, conditions, want=("s_tot",))
+        return float((torch.log(bufs["s_tot"]) + 2.0).sum().item())
+
+    def getEntropy(self, sess, inputs, encoding, conditions=None):
+        """model.py:578-593: per-example entropies."""
+        bufs, _ = self._forward(inputs, encoding, conditions, want=("s_tot",))
+        return (torch.log(bufs["s_tot"]) + 2.0).sum(dim=1).double().cpu().numpy()
+
+    def train(self, sess, inputs, truth, encoding, conditions=None):
+        raise NotImplementedError("distillation training (model.py:603-642) is not built yet")
+
+    train_fast = train
+
+    def encode(self, sess, inputs, conditions=None):
+        raise NotImplementedError("the teacher encoder (model.py:644-649) is outside the hot path")
+
+    def reconstruct(self, sess, inputs, conditions=None):
+        raise NotImplementedError("reconstruct (model.py:651-656) needs the teacher encoder")
