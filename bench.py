@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the SR-WaveNet hot path on B200 (contract: see the task statement / DESIGN.md).
+
+Workload (BASELINE.json configs[1]): teacher WaveNet teacher-forced log-likelihood, batch
+32 x 64000 samples per GPU (weak scaling: every rank scores its own 32 utterances, no data-path
+collective).  One step = one scoring pass over one batch.  `value` is timed with CUDA events on
+inputs already resident in HBM; `e2e` goes through the Python API with pinned host buffers
+(H2D of audio + encoding and D2H of the log-likelihood inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ...]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE_TEACHER = 468576      # 30*14336 + 37888 + 128 + 480
+FLOP_PER_SAMPLE_STUDENT = 740224      # 4*184576 + 1920
+BYTES_PER_SAMPLE_LAYER_F32 = 1280     # fp32 per-layer kernel: h read+write (2*128 B) + skip RMW (2*512 B)
+BYTES_PER_SAMPLE_AR = 7684            # fp32 queue pop+push (2*30*32*4 B) + 4 B sample
+METRIC = "audio samples/sec"
+UNIT = "samples/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), tf=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, source="fallback")   # B200_PROFILING.md
+
+
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_samples_per_s(B, T, repeats, warm=1):
+    """Times oracle/torch_cpu.py (the stand-in for the reference's TF CPU path) on this host."""
+    import torch
+    from sr_wavenet_b200 import synth
+    from oracle.torch_cpu import TeacherCPU
+    torch.set_num_threads(os.cpu_count() or 1)
+    dil = synth.DEFAULT_DILATIONS
+    cpu = TeacherCPU(synth.make_teacher_weights(dil), dil, 128, 5)
+    x, enc = synth.synthetic_audio(B, T), synth.synthetic_encoding(B, T // 128)
+    for _ in range(warm):
+        cpu.nll(x, enc)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu.nll(x, enc)
+        times.append(time.perf_counter() - t0)
+    return B * T / min(times), B * T / (sum(times) / len(times)), torch.get_num_threads(), times
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU port of the reference path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    B, T = 2, 64000
+    best, mean, cores, times = cpu_port_samples_per_s(B, T, args.steps, warm=max(1, args.warmup))
+    ms = 1e3 * sum(times) / len(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mean, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "teacher WaveNet teacher-forced log-likelihood (BASELINE.json configs[1])",
+                   "sample": "each step scores %d x %d samples on the host" % (B, T),
+                   "note": "TensorFlow 1.x (the reference runtime) is not installable here; this is the "
+                           "PyTorch-CPU fp32 port oracle/torch_cpu.py of the same graph"},
+        "cpu_baseline": {"value": mean, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d steps of %d x %d samples, mean" % (args.steps, B, T)},
+        "e2e": {"value": mean, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="teacher_nll", choices=["teacher_nll", "student", "generate"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config)")
+    ap.add_argument("--length", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):
+        ge.build()
+    import sr_wavenet_b200 as srwn
+    from sr_wavenet_b200 import synth, shard
+
+    rank, local_rank, world = shard.init_from_env()
+    torch.cuda.set_device(local_rank)
+    peaks = load_peaks()
+    dil = synth.DEFAULT_DILATIONS
+    P = 128
+
+    defaults = {"teacher_nll": (32, 64000), "student": (64 // max(world, 1) if world > 1 else 8, 64000),
+                "generate": (256, 16000)}
+    B, T = defaults[args.workload]
+    if args.workload == "student":
+        B = 8          # configs[2]: 64 x 64000 over 8 GPUs = 8 per GPU (weak scaling unit)
+    B = args.batch or B
+    T = args.length or T
+
+    # synthetic inputs, seeded per global utterance index so ranks see different audio
+    g0 = rank * B
+    enc_h = synth.synthetic_encoding(B, T // P, seed=4321 + rank)
+    if args.workload == "student":
+        model = srwn.ParallelWaveNet(T, 0, dil, None, num_flows=4, skip_channels=128, latent_channels=32,
+                                     pool_stride=P)
+        model.set_weights(synth.make_student_weights(dil, 4))
+        x_h = synth.logistic_noise(B, T, seed=777 + rank)
+        flop_per_sample = FLOP_PER_SAMPLE_STUDENT
+    else:
+        model = srwn.WaveNetAutoEncoder(T, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=P)
+        model.set_weights(synth.make_teacher_weights(dil))
+        x_h = synth.synthetic_audio(B, T, seed=1234 + g0)
+        flop_per_sample = FLOP_PER_SAMPLE_TEACHER
+    prec = args.precision
+    if prec == "auto":
+        prec = "bf16" if "bf16" in model.available_precisions() else "fp32"
+    if args.workload == "generate":
+        prec = "fp32"
+        u1_h, u2_h = synth.sampler_uniforms(B, T, seed=999 + rank)
+
+    x_d, enc_d = torch.from_numpy(x_h).cuda(), torch.from_numpy(enc_h).cuda()
+    x_p, enc_p = torch.from_numpy(x_h).pin_memory(), torch.from_numpy(enc_h).pin_memory()
+    if args.workload == "generate":
+        u1_d, u2_d = torch.from_numpy(u1_h).cuda(), torch.from_numpy(u2_h).cuda()
+        u1_p, u2_p = torch.from_numpy(u1_h).pin_memory(), torch.from_numpy(u2_h).pin_memory()
+
+    def step_device():
+        if args.workload == "teacher_nll":
+            return model.nll(x_d, enc_d, precision=prec)
+        if args.workload == "student":
+            return model.generate(None, x_d, enc_d, precision=prec)
+        return model.generate(enc_d, u1=u1_d, u2=u2_d)
+
+    def step_e2e():
+        if args.workload == "teacher_nll":
+            return model.nll(x_p, enc_p, precision=prec)            # float on the host
+        if args.workload == "student":
+            return model.generate(None, x_p, enc_p, precision=prec)  # ndarray on the host
+        return model.generate(enc_p, u1=u1_p, u2=u2_p)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    model._eng.set_profiling(True)
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    shard.barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = srwn._lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms, kern_launches, kern_name = [], 0, ""
+    torch.cuda.synchronize()
+    for a, b in ev:
+        flush.fill_(1)                      # L2 flush between timed iterations (not timed)
+        a.record()
+        step_device()
+        b.record()
+        km, kern_launches, kern_name = model._eng.last_kernel_ms()
+        kern_ms.append(km)
+    torch.cuda.synchronize()
+    launches = srwn._lib.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    shard.barrier()
+
+    # end to end through the public API with pinned host buffers
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    shard.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    total_ms_max, e2e_s_max = shard.reduce_scalars([total_ms, e2e_s], "max")
+    units, = shard.reduce_scalars([float(B * T * args.steps)], "sum")
+    value = units / (total_ms_max * 1e-3)
+    e2e_value = units / e2e_s_max
+    h2d = x_h.nbytes + enc_h.nbytes + (u1_h.nbytes + u2_h.nbytes if args.workload == "generate" else 0)
+    d2h = 4 if args.workload == "teacher_nll" else B * T * 4
+
+    # roofline of the dominant kernel, from this run's CUDA-event bracket around its launches
+    k_ms = sum(kern_ms) / len(kern_ms) / max(kern_launches, 1)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("%s/%s" % (args.workload, prec))
+    if args.workload == "generate":
+        ach = BYTES_PER_SAMPLE_AR * B * T / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s"}
+    elif prec == "bf16":
+        ach = flop_per_sample * B * T / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s"}
+    else:
+        ach = BYTES_PER_SAMPLE_LAYER_F32 * B * T / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s"}
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=kern_name,
+                launches_per_step=kern_launches, kernel_ms=k_ms, peak_source=peaks["source"])
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "teacher_nll":
+        best, mean, cores, times = cpu_port_samples_per_s(4, 64000, repeats=3)
+        cpu_baseline = {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "teacher log-likelihood on 4 x 64000 samples, best of 3 "
+                                  "(oracle/torch_cpu.py; TF 1.x not installable)"}
+
+    if rank == 0:
+        names = {"teacher_nll": "teacher WaveNet teacher-forced log-likelihood (BASELINE.json configs[1])",
+                 "student": "student IAF parallel synthesis, 4 flows (BASELINE.json configs[2])",
+                 "generate": "teacher autoregressive fast generation, dilation queues (BASELINE.json configs[3])"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": names[args.workload], "batch_per_gpu": B, "global_batch": B * world,
+                       "samples_per_utterance": T, "layers": len(dil), "parallelism": "batch-sharded x%d" % world,
+                       "l2": "flushed between timed iterations (256 MiB write)", "precision_path": prec},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,13 @@ int srwn_mol_loss(const float* x, const float* l, float* nll_out, float* nll_sum
 int srwn_mol_sample(const float* l, const float* u1, const float* u2, float* out,
                     int32_t* idx_out, int32_t B, int32_t T, int32_t M, void* stream);
 
+/* Optional timing of the dominant kernel(s) of the last call on this handle: when enabled, the
+ * library brackets them with CUDA events on the launch stream.  srwn_last_kernel_ms waits for
+ * the closing event and returns the elapsed time of those `launches` back-to-back launches and
+ * the kernel's name (static string).  Used by bench.py's roofline. */
+int srwn_set_profiling(srwn_handle_t h, int32_t enable);
+int srwn_last_kernel_ms(srwn_handle_t h, float* ms, int32_t* launches, const char** name);
+
 /* Number of kernels this library launched on behalf of the calling process since load
  * (bench.py's gpu_launches). */
 int64_t srwn_launch_count(void);

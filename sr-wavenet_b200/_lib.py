@@ -42,6 +42,9 @@ SIGNATURES = {
     "srwn_set_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(_i64), _i32]),
     "srwn_get_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, _i64]),
     "srwn_commit_weights": (ctypes.c_int, [_vp, _vp]),
+    "srwn_set_profiling": (ctypes.c_int, [_vp, _i32]),
+    "srwn_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32),
+                                           ctypes.POINTER(ctypes.c_char_p)]),
     "srwn_supports": (ctypes.c_int, [_vp, _i32, _i32]),
     "srwn_workspace_bytes": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, ctypes.POINTER(_sz)]),
     "srwn_teacher_logits": (ctypes.c_int, [_vp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),

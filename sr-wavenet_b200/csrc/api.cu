@@ -184,6 +184,8 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
   c->committed = false;
   c->d_weights = nullptr; c->d_dilations = nullptr; c->d_queue_off = nullptr;
   c->d_packed = nullptr; c->packed_bytes = 0;
+  c->profiling = 0; c->prof_launches = 0; c->prof_name = "";
+  c->prof_ev[0] = c->prof_ev[1] = nullptr;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
 
   const size_t L = cfg->n_layers, R = kR, S = c->cfg.skip_channels, C = cfg->cond_channels,
@@ -230,6 +232,7 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
 
 extern "C" int srwn_destroy(srwn_handle_t h) {
   if (!h) return SRWN_OK;
+  if (h->prof_ev[0]) { cudaEventDestroy(h->prof_ev[0]); cudaEventDestroy(h->prof_ev[1]); }
   cudaFree(h->d_weights); cudaFree(h->d_dilations); cudaFree(h->d_queue_off); cudaFree(h->d_packed);
   delete reinterpret_cast<CtxBox*>(h);
   return SRWN_OK;
@@ -334,6 +337,28 @@ static int check_bt(const srwn_ctx* c, int B, int T) {
     return srwn_fail(SRWN_ERR_INVALID, "T=%d must be a multiple of pool_stride=%d (model.py:183)", T,
                      c->cfg.pool_stride);
   if (!c->committed) return srwn_fail(SRWN_ERR_WEIGHTS, "weights not committed (srwn_commit_weights)");
+  return SRWN_OK;
+}
+
+extern "C" int srwn_set_profiling(srwn_handle_t h, int32_t enable) {
+  if (!h) return srwn_fail(SRWN_ERR_INVALID, "srwn_set_profiling: null handle");
+  if (enable && !h->prof_ev[0]) {
+    SRWN_CUDA(cudaEventCreate(&h->prof_ev[0]));
+    SRWN_CUDA(cudaEventCreate(&h->prof_ev[1]));
+  }
+  h->profiling = enable ? 1 : 0;
+  h->prof_launches = 0;
+  return SRWN_OK;
+}
+
+extern "C" int srwn_last_kernel_ms(srwn_handle_t h, float* ms, int32_t* launches, const char** name) {
+  if (!h || !ms) return srwn_fail(SRWN_ERR_INVALID, "srwn_last_kernel_ms: null argument");
+  if (!h->profiling || h->prof_launches == 0)
+    return srwn_fail(SRWN_ERR_INVALID, "no profiled call yet (srwn_set_profiling)");
+  SRWN_CUDA(cudaEventSynchronize(h->prof_ev[1]));
+  SRWN_CUDA(cudaEventElapsedTime(ms, h->prof_ev[0], h->prof_ev[1]));
+  if (launches) *launches = h->prof_launches;
+  if (name) *name = h->prof_name;
   return SRWN_OK;
 }
 

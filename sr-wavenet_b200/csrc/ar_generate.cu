@@ -217,6 +217,7 @@ int run_ar_generate(srwn_ctx* c, const float* enc, const float* u1, const float*
   p.queues = queues; p.cond = cond; p.u1 = u1; p.u2 = u2; p.x_out = x_out; p.logits_out = logits_out;
   p.B = B; p.T = T; p.L = c->cfg.n_layers; p.P = c->cfg.pool_stride; p.frames = frames;
   p.M = c->cfg.num_mixtures; p.sum_d = c->sum_dilation;
+  ProfScope prof(c, st, "k_ar_generate", 1);
   if (B > c->sm_count) {
     k_ar_generate<2><<<(B + 1) / 2, 256, 0, st>>>(p);
   } else {

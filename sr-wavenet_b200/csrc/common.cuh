@@ -70,6 +70,20 @@ struct srwn_ctx {
   // packed bf16 operand images for the tcgen05 path (built at commit)
   void* d_packed;
   size_t packed_bytes;
+  // optional timing of the dominant kernel(s) of the last call (srwn_set_profiling)
+  int profiling;
+  cudaEvent_t prof_ev[2];
+  int prof_launches;
+  const char* prof_name;
+};
+
+// brackets the dominant kernel launches of a call with CUDA events on the launch stream
+struct ProfScope {
+  srwn_ctx* c; cudaStream_t st;
+  ProfScope(srwn_ctx* c_, cudaStream_t st_, const char* name, int launches) : c(c_), st(st_) {
+    if (c->profiling) { c->prof_name = name; c->prof_launches = launches; cudaEventRecord(c->prof_ev[0], st); }
+  }
+  ~ProfScope() { if (c->profiling) cudaEventRecord(c->prof_ev[1], st); }
 };
 
 inline const float* stack_w(const srwn_ctx* c, int stack) {

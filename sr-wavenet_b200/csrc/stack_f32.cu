@@ -212,6 +212,7 @@ int run_stack_f32(srwn_ctx* c, int stack, const float* xin, const float* enc, in
   float* cur = h0;
   float* nxt = h1;
   dim3 grid((T + kTT - 1) / kTT, B);
+  ProfScope prof(c, st, with_skip ? "k_layer_f32<true>" : "k_layer_f32<false>", L);
   for (int l = 0; l < L; l++) {
     const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
     if (with_skip)

@@ -65,6 +65,15 @@ class _Engine(object):
         _lib.check(self.lib.srwn_get_weight(self.h, name.encode(), out.ctypes.data_as(ctypes.c_void_p), out.size))
         return out
 
+    def set_profiling(self, enable):
+        _lib.check(self.lib.srwn_set_profiling(self.h, int(bool(enable))))
+
+    def last_kernel_ms(self):
+        """(elapsed ms, launches, kernel name) of the dominant kernel(s) of the last call."""
+        ms, n, name = ctypes.c_float(), ctypes.c_int32(), ctypes.c_char_p()
+        _lib.check(self.lib.srwn_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(name)))
+        return ms.value, n.value, name.value.decode()
+
     def workspace(self, op, B, T, precision):
         n = ctypes.c_size_t()
         _lib.check(self.lib.srwn_workspace_bytes(self.h, op, B, T, precision, ctypes.byref(n)))

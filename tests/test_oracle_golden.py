@@ -153,3 +153,16 @@ def test_oracle_fp32_tracks_fp64(golden_small, dtype):
     lg32 = orc.teacher_decoder_logits(tw, g["x"], g["enc"], dil, int(g["P"]))
     assert lg32.dtype == np.float32
     assert np.abs(lg32 - g["logits"]).max() < 1e-4
+
+
+def test_torch_cpu_port_matches_numpy_oracle(golden_default):
+    """The timed CPU baseline (oracle/torch_cpu.py) computes the same thing as the NumPy oracle."""
+    from oracle.torch_cpu import TeacherCPU
+    g = golden_default
+    dil = synth.DEFAULT_DILATIONS
+    B, T, P = int(g["B"]), int(g["T"]), int(g["P"])
+    tw = synth.make_teacher_weights(dil, seed=42)
+    x, enc = synth.synthetic_audio(B, T, seed=1234), synth.synthetic_encoding(B, T // P, 32, seed=4321)
+    cpu = TeacherCPU(tw, dil, P, 5)
+    assert np.abs(cpu.logits(x, enc).numpy() - g["logits"]).max() < 1e-4
+    assert abs(cpu.nll(x, enc) - float(g["nll_sum"])) < 1e-4 * abs(float(g["nll_sum"]))
