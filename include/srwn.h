@@ -50,7 +50,8 @@ enum srwn_kind {
 
 enum srwn_precision {
   SRWN_FP32 = 0,             /* fp32 FFMA path, parity <= 1e-4 relative */
-  SRWN_BF16 = 1              /* bf16 operands on tcgen05, fp32 accumulate/residual stream */
+  SRWN_BF16 = 1,             /* fused tcgen05 kernel, bf16 MMA operands, fp32 accumulate / residual stream */
+  SRWN_FP16 = 2              /* same kernel with fp16 MMA operands (8x smaller operand rounding) */
 };
 
 enum srwn_op {               /* argument of srwn_workspace_bytes */
@@ -103,6 +104,10 @@ int srwn_get_weight(srwn_handle_t h, const char* name, float* data, int64_t coun
  * kernels read (bf16 UMMA layouts, summed skip bias). Must follow any srwn_set_weight. */
 int srwn_commit_weights(srwn_handle_t h, void* stream);
 
+/* Synchronises `stream` and reports whether the last fused-kernel call that used this workspace
+ * aborted (a bounded on-device pipeline wait expired; outputs are then invalid). */
+int srwn_check_async_error(srwn_handle_t h, int32_t op, int32_t B, int32_t T, int32_t precision,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* 1 if `op` (enum srwn_op) is built for `precision` with this handle's configuration, else 0. */
 int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision);
 int srwn_workspace_bytes(srwn_handle_t h, int32_t op, int32_t B, int32_t T,

@@ -10,9 +10,9 @@ LIB_PATH = os.path.join(_HERE, "libsrwn.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WEIGHTS, ERR_UNSUPPORTED, ERR_WORKSPACE = range(6)
 TEACHER, STUDENT = 0, 1
-FP32, BF16 = 0, 1
+FP32, BF16, FP16 = 0, 1, 2
 OP_TEACHER_LOGITS, OP_TEACHER_NLL, OP_TEACHER_GENERATE, OP_STUDENT_FORWARD = range(4)
-PRECISIONS = {"fp32": FP32, "bf16": BF16}
+PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
 
 
 class SrwnError(RuntimeError):
@@ -45,6 +45,7 @@ SIGNATURES = {
     "srwn_set_profiling": (ctypes.c_int, [_vp, _i32]),
     "srwn_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32),
                                            ctypes.POINTER(ctypes.c_char_p)]),
+    "srwn_check_async_error": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "srwn_supports": (ctypes.c_int, [_vp, _i32, _i32]),
     "srwn_workspace_bytes": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, ctypes.POINTER(_sz)]),
     "srwn_teacher_logits": (ctypes.c_int, [_vp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),

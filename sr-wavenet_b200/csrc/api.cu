@@ -362,12 +362,23 @@ extern "C" int srwn_last_kernel_ms(srwn_handle_t h, float* ms, int32_t* launches
   return SRWN_OK;
 }
 
+extern "C" int srwn_check_async_error(srwn_handle_t h, int32_t op, int32_t B, int32_t T, int32_t precision,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return srwn_fail(SRWN_ERR_INVALID, "srwn_check_async_error: null handle");
+  if (precision == SRWN_FP32 || op == SRWN_OP_TEACHER_GENERATE) {
+    SRWN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return SRWN_OK;
+  }
+  return fused_check_error(workspace, workspace_bytes, h, B, T, (cudaStream_t)stream);
+}
+
 extern "C" int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision) {
   if (!h) return 0;
   const bool teacher_op = op == SRWN_OP_TEACHER_LOGITS || op == SRWN_OP_TEACHER_NLL || op == SRWN_OP_TEACHER_GENERATE;
   if (teacher_op != (h->cfg.kind == SRWN_TEACHER) || op < 0 || op > SRWN_OP_STUDENT_FORWARD) return 0;
   if (precision == SRWN_FP32) return 1;
-  if (precision == SRWN_BF16) return op != SRWN_OP_TEACHER_GENERATE && fused_supported(h) ? 1 : 0;
+  if (precision == SRWN_BF16 || precision == SRWN_FP16)
+    return op != SRWN_OP_TEACHER_GENERATE && fused_supported(h) ? 1 : 0;
   return 0;
 }
 
@@ -379,7 +390,7 @@ extern "C" int srwn_workspace_bytes(srwn_handle_t h, int32_t op, int32_t B, int3
     case SRWN_OP_TEACHER_LOGITS:
     case SRWN_OP_TEACHER_NLL:
       if (h->cfg.kind != SRWN_TEACHER) return srwn_fail(SRWN_ERR_INVALID, "not a teacher handle");
-      *bytes = precision == SRWN_BF16 ? fused_workspace_bytes(h, op, B, T)
+      *bytes = precision != SRWN_FP32 ? fused_workspace_bytes(h, op, B, T)
                                       : carve_f32(h, op, B, T, nullptr, 0, true).bytes;
       return SRWN_OK;
     case SRWN_OP_TEACHER_GENERATE:
@@ -388,7 +399,7 @@ extern "C" int srwn_workspace_bytes(srwn_handle_t h, int32_t op, int32_t B, int3
       return SRWN_OK;
     case SRWN_OP_STUDENT_FORWARD:
       if (h->cfg.kind != SRWN_STUDENT) return srwn_fail(SRWN_ERR_INVALID, "not a student handle");
-      *bytes = precision == SRWN_BF16 ? fused_workspace_bytes(h, op, B, T)
+      *bytes = precision != SRWN_FP32 ? fused_workspace_bytes(h, op, B, T)
                                       : carve_f32(h, op, B, T, nullptr, 0, false).bytes;
       return SRWN_OK;
   }
@@ -411,9 +422,9 @@ extern "C" int srwn_teacher_logits(srwn_handle_t h, const float* x, const float*
   if (h->cfg.kind != SRWN_TEACHER) return srwn_fail(SRWN_ERR_INVALID, "not a teacher handle");
   int rc = check_bt(h, B, T);
   if (rc) return rc;
-  if (precision == SRWN_BF16)
-    return run_teacher_fused_bf16(h, x, enc, nullptr, nullptr, nullptr, logits, B, T, workspace,
-                                  workspace_bytes, (cudaStream_t)stream);
+  if (precision == SRWN_BF16 || precision == SRWN_FP16)
+    return run_teacher_fused_bf16(h, x, enc, nullptr, nullptr, nullptr, logits, B, T,
+                                  precision == SRWN_FP16, workspace, workspace_bytes, (cudaStream_t)stream);
   if (precision != SRWN_FP32) return srwn_fail(SRWN_ERR_INVALID, "unknown precision %d", precision);
   F32Ws w = carve_f32(h, SRWN_OP_TEACHER_LOGITS, B, T, workspace, workspace_bytes, false);
   if (!workspace || w.bytes > workspace_bytes)
@@ -429,9 +440,9 @@ extern "C" int srwn_teacher_nll(srwn_handle_t h, const float* x_in, const float*
   if (h->cfg.kind != SRWN_TEACHER) return srwn_fail(SRWN_ERR_INVALID, "not a teacher handle");
   int rc = check_bt(h, B, T);
   if (rc) return rc;
-  if (precision == SRWN_BF16)
+  if (precision == SRWN_BF16 || precision == SRWN_FP16)
     return run_teacher_fused_bf16(h, x_in, enc, x_scored, nll_out, nll_sum, logits_out, B, T,
-                                  workspace, workspace_bytes, (cudaStream_t)stream);
+                                  precision == SRWN_FP16, workspace, workspace_bytes, (cudaStream_t)stream);
   if (precision != SRWN_FP32) return srwn_fail(SRWN_ERR_INVALID, "unknown precision %d", precision);
   F32Ws w = carve_f32(h, SRWN_OP_TEACHER_NLL, B, T, workspace, workspace_bytes, logits_out == nullptr);
   if (!workspace || w.bytes > workspace_bytes)
@@ -463,9 +474,9 @@ extern "C" int srwn_student_forward(srwn_handle_t h, const float* z, const float
   int rc = check_bt(h, B, T);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == SRWN_BF16)
-    return run_student_fused_bf16(h, z, enc, out, s_tot, mu_tot, x_last, B, T, workspace,
-                                  workspace_bytes, st);
+  if (precision == SRWN_BF16 || precision == SRWN_FP16)
+    return run_student_fused_bf16(h, z, enc, out, s_tot, mu_tot, x_last, B, T, precision == SRWN_FP16,
+                                  workspace, workspace_bytes, st);
   if (precision != SRWN_FP32) return srwn_fail(SRWN_ERR_INVALID, "unknown precision %d", precision);
   F32Ws w = carve_f32(h, SRWN_OP_STUDENT_FORWARD, B, T, workspace, workspace_bytes, false);
   if (!workspace || w.bytes > workspace_bytes)

@@ -130,8 +130,9 @@ int fused_pack_weights(srwn_ctx* c, cudaStream_t st);
 size_t fused_workspace_bytes(const srwn_ctx* c, int op, int B, int T);
 int run_teacher_fused_bf16(srwn_ctx* c, const float* x_in, const float* enc,
                            const float* x_scored, float* nll_out, float* nll_sum,
-                           float* logits_out, int B, int T, void* ws, size_t ws_bytes,
+                           float* logits_out, int B, int T, int fp16, void* ws, size_t ws_bytes,
                            cudaStream_t st);
 int run_student_fused_bf16(srwn_ctx* c, const float* z, const float* enc, float* out,
-                           float* s_tot, float* mu_tot, float* x_last, int B, int T,
+                           float* s_tot, float* mu_tot, float* x_last, int B, int T, int fp16,
                            void* ws, size_t ws_bytes, cudaStream_t st);
+int fused_check_error(void* ws, size_t ws_bytes, const srwn_ctx* c, int B, int T, cudaStream_t st);

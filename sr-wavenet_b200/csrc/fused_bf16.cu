@@ -1,18 +1,870 @@
-// Fused bf16 tcgen05 residual-stack kernel (placeholder until the kernel lands).
+// Fused residual-stack kernel on tcgen05 tensor cores (sm_100a), 16-bit operands, fp32 accumulate.
+//
+// One persistent, warp-specialised CTA per SM streams a contiguous piece of the (utterance, time)
+// line in chunks of 384 time steps (3 MMA tiles of 128 rows = TMEM lanes).  For a chunk, ALL
+// layers run on-chip:
+//   * the residual stream lives in fp32 registers of the epilogue thread that owns the row,
+//   * its 16-bit image (the conv operand) lives in shared memory in the UMMA canonical K-major
+//     no-swizzle layout [k-chunk][row][8 elems]; the dilated tap of layer l is the SAME buffer
+//     addressed d_l rows earlier, so the "halo" costs no copy inside a chunk,
+//   * rows older than the chunk (the last d_l inputs of every layer) come from a small per-CTA
+//     ring in global memory (L2 resident) written by the previous chunk,
+//   * the skip sum over layers accumulates in TMEM (128 fp32 columns per tile) and never leaves
+//     the SM; the output head (relu, 1x1 S->S, relu, 1x1 S->4M) and the mixture-of-logistics
+//     likelihood run from TMEM as the chunk's epilogue.
+// Warp roles: warps 0-11 = three epilogue warpgroups (one per tile; tcgen05.ld -> gate math ->
+// 16-bit operand stores), warp 12 = MMA issuer (event driven, one elected thread) + TMEM owner,
+// warp 13 = loader (cp.async.bulk weights per layer, cp.async ring -> halo rows).
+// A piece that starts mid-utterance first recomputes the receptive field (sum of dilations,
+// rounded up to whole chunks) with outputs discarded, so pieces are independent (no inter-CTA
+// synchronisation) and results do not depend on the partition.
+//
+// Reference semantics: ops.py:6-46 (block, gate = sigmoid(tanh(.)) per ops.py:33),
+// model.py:172-196 (decoder), model.py:423-452 + 479-482 (student flow), ops.py:124-175 (NLL).
 #include "common.cuh"
+#include "mol.cuh"
+#include <cuda_fp16.h>
+#include <algorithm>
 
-bool fused_supported(const srwn_ctx* c) { return false; }
-size_t fused_packed_bytes(const srwn_ctx* c) { return 0; }
-int fused_pack_weights(srwn_ctx* c, cudaStream_t st) { return SRWN_OK; }
-size_t fused_workspace_bytes(const srwn_ctx* c, int op, int B, int T) { return 256; }
+const float* srwn_host_weights(srwn_ctx* c);
+__global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
+                       const float* __restrict__ cond_b, float* __restrict__ cond,
+                       int frames_total, int L, int C);
+
+namespace fused {
+
+constexpr int kTile = 128;
+constexpr int kTiles = 3;
+constexpr int kChunk = kTile * kTiles;          // 384 time steps per chunk
+constexpr int kHalo = 512;                      // largest dilation the layout supports
+constexpr int kRows = kHalo + kChunk;           // rows per activation buffer
+constexpr int kMaxLayers = 40;
+constexpr int kThreads = 14 * 32;
+constexpr int kMmaWarp = 12, kLoadWarp = 13;
+constexpr int kMaxSeg = 8;
+
+// packed operand image (bytes, per layer): WF [8 kc][32 n][8] | WRS [4 kc][160 or 32 n][8]
+constexpr int kWfBytes = 64 * 32 * 2;           // 4096
+constexpr int kWrsTeacher = 32 * 160 * 2;       // 10240
+constexpr int kWrsStudent = 32 * 32 * 2;        // 2048
+constexpr int kH1Bytes = 128 * 128 * 2;         // 32768
+constexpr int kH2Bytes = 128 * 32 * 2;          // 8192
+
+struct Seg { int b, t_start, t_out, t_end; };
+
+struct Params {
+  const uint8_t* packed;      // per-stack packed image
+  const float* x_in;          // [B][T] stack input (audio / noise / previous flow output)
+  const float* x_scored;      // teacher: audio whose likelihood is taken (may be null)
+  const float* cb;            // [B][frames][L+1][32] fp32: folded biases + conditioning
+  uint8_t* rings;             // per-CTA history rings
+  const Seg* segs;            // [grid][kMaxSeg]
+  const int* nseg;            // [grid]
+  float* logits_out;          // teacher, optional [B][T][O]
+  float* nll_out;             // teacher, optional [B][T]
+  double* nll_partial;        // teacher, optional [grid]
+  float* scale_out;           // student [B][T]
+  float* mean_out;            // student [B][T]
+  float* x_out;               // student [B][T]
+  int* err;                   // device error flag
+  int T, L, P, frames, O, M;
+  int ring_bytes_per_cta;
+  int dil[kMaxLayers];
+  int ring_off[kMaxLayers];   // byte offset of layer l's ring inside a CTA's ring block
+};
+
+// ---- shared memory map ------------------------------------------------------------------
+struct SmemMap {
+  static constexpr int hbuf = 0;                                  // 2 x [4][kRows][16 B]
+  static constexpr int hbuf_bytes = 4 * kRows * 16;               // 57344
+  static constexpr int cbuf = hbuf + 2 * hbuf_bytes;              // 3 x [4][128][16 B]
+  static constexpr int cbuf_bytes = 4 * kTile * 16;               // 8192
+  static constexpr int wst = cbuf + kTiles * cbuf_bytes;          // 2 stages
+  static constexpr int wst_bytes = kWfBytes + kWrsTeacher;        // 14336
+  static constexpr int head = wst + 2 * wst_bytes;                // H1 | H2 (teacher)
+  static constexpr int bias = head + kH1Bytes + kH2Bytes;         // [kMaxLayers][32] filter bias fp32
+  static constexpr int hbias = bias + kMaxLayers * 32 * 4;        // skip_b_sum[128] | h1_b[128] | h2_b[32] | flow hk[64] hb[2]
+  static constexpr int front = hbias + (128 + 128 + 32 + 64 + 4) * 4;   // fk[64]
+  static constexpr int bars = front + 64 * 4;
+  static constexpr int n_bars = 32;
+  static constexpr int misc = bars + n_bars * 8;                  // tmem ptr, abort flag
+  static constexpr int total = misc + 64;
+};
+static_assert(SmemMap::total <= 232448, "shared memory budget");
+// A3/A4 (head operands, 3 x 32 KB) overlay the two activation buffers
+static_assert(kTiles * 16 * kTile * 16 <= 2 * SmemMap::hbuf_bytes, "head operand overlay");
+
+enum Bar {
+  BAR_D1 = 0,      // [3] MMA -> epilogue: filter-conv accumulator ready
+  BAR_C = 3,       // [3] epilogue -> MMA: gate operand written (128 arrivals)
+  BAR_D2 = 6,      // [3] MMA -> epilogue: residual (+skip) accumulator ready
+  BAR_H = 9,       // [3] epilogue -> MMA: next layer's operand rows written (128 arrivals)
+  BAR_WFULL = 12,  // [2] loader -> MMA: layer weights landed (tx bytes)
+  BAR_WEMPTY = 14, // [2] MMA -> loader: all MMAs of the layer retired
+  BAR_HALO = 16,   // [2] loader -> MMA/epilogue: halo rows of the layer landed
+  BAR_G1 = 18,     // [2] MMA -> loader/epilogue: all filter-conv MMAs of the layer retired
+  BAR_HDA = 20,    // [3] epilogue -> MMA: head operand written (128 arrivals)
+  BAR_HDD = 23,    // [3] MMA -> epilogue: head accumulator ready
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a stuck pipeline raises the abort flag instead of hanging the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity, volatile int* abort_flag) {
+  if (mbar_test(a, parity)) return true;
+  const long long t0 = clock64();
+  while (true) {
+    if (mbar_test(a, parity)) return true;
+    if (*abort_flag) return false;
+    if (clock64() - t0 > 4000000000LL) { *abort_flag = 1; return false; }
+  }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle canonical layout: 8-row x 16-byte core matrices; rows 16 B apart,
+// 8-row groups SBO apart, 16-byte K chunks LBO apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// cute::UMMA::InstrDescriptor: c=F32 (bit 4), a/b format (bits 7,10: F16=0, BF16=1), K-major, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (FP16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// stores one row (32 values) as 4 x 16 B into a [kc][rows][8] operand buffer
+template <bool FP16>
+__device__ __forceinline__ void store_row(uint8_t* buf, int rows_per_kc, int row, const float* v) {
+#pragma unroll
+  for (int kc = 0; kc < 4; kc++) {
+    uint4 q;
+    q.x = pack2<FP16>(v[kc * 8 + 0], v[kc * 8 + 1]); q.y = pack2<FP16>(v[kc * 8 + 2], v[kc * 8 + 3]);
+    q.z = pack2<FP16>(v[kc * 8 + 4], v[kc * 8 + 5]); q.w = pack2<FP16>(v[kc * 8 + 6], v[kc * 8 + 7]);
+    *reinterpret_cast<uint4*>(buf + ((size_t)kc * rows_per_kc + row) * 16) = q;
+  }
+}
+
+// ---- the kernel --------------------------------------------------------------------------
+template <bool TEACHER, bool FP16>
+__global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t sbase = smem_u32(smem);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SmemMap::misc);
+  auto bar = [&](int i) { return sbase + SmemMap::bars + i * 8; };
+  const int L = p.L;
+  constexpr int wrs_bytes = TEACHER ? kWrsTeacher : kWrsStudent;
+  constexpr int layer_bytes = kWfBytes + wrs_bytes;
+  constexpr int wrs_rows = TEACHER ? 160 : 32;
+
+  // ---- one-time setup ---------------------------------------------------------------------
+  if (tid == 0) {
+    for (int i = 0; i < 3; i++) {
+      mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_C + i), kTile); mbar_init(bar(BAR_D2 + i), 1);
+      mbar_init(bar(BAR_H + i), kTile); mbar_init(bar(BAR_HDA + i), kTile); mbar_init(bar(BAR_HDD + i), 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), 1);
+      mbar_init(bar(BAR_HALO + i), 1); mbar_init(bar(BAR_G1 + i), 1);
+    }
+    *abort_flag = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {  // resident constants: biases, front conv, head weights (plain loads; made visible below)
+    const uint8_t* pk = p.packed;
+    const size_t off_fixed = (size_t)L * layer_bytes;     // [filter bias L*32 f32][front 96 f32 -> 64 used][head...]
+    const float* fbias = reinterpret_cast<const float*>(pk + off_fixed);
+    float* s_bias = reinterpret_cast<float*>(smem + SmemMap::bias);
+    for (int i = tid; i < L * 32; i += kThreads) s_bias[i] = fbias[i];
+    const float* ffront = fbias + kMaxLayers * 32;
+    float* s_front = reinterpret_cast<float*>(smem + SmemMap::front);
+    for (int i = tid; i < 64; i += kThreads) s_front[i] = ffront[i];
+    const float* fhb = ffront + 64;
+    float* s_hb = reinterpret_cast<float*>(smem + SmemMap::hbias);
+    for (int i = tid; i < 128 + 128 + 32 + 64 + 4; i += kThreads) s_hb[i] = fhb[i];
+    if (TEACHER) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(fhb + 128 + 128 + 32 + 64 + 4));
+      uint4* dst = reinterpret_cast<uint4*>(smem + SmemMap::head);
+      for (int i = tid; i < (kH1Bytes + kH2Bytes) / 16; i += kThreads) dst[i] = src[i];
+    }
+  }
+  fence_async_smem();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const Seg* segs = p.segs + (size_t)blockIdx.x * kMaxSeg;
+  const int nseg = p.nseg[blockIdx.x];
+  uint8_t* ring = p.rings + (size_t)blockIdx.x * p.ring_bytes_per_cta;
+  const int uses0 = (L + 1) >> 1, uses1 = L >> 1;     // per-chunk phases of the parity-indexed barriers
+  int chunk_idx = 0;                                  // chunks processed so far (phase bookkeeping)
+  int head_idx = 0;                                   // chunks with a head phase so far
+  double nll_acc = 0.0;
+
+  for (int si = 0; si < nseg; si++) {
+    const Seg sg = segs[si];
+    for (int t0 = sg.t_start; t0 < sg.t_end; t0 += kChunk, chunk_idx++) {
+      const bool warm = TEACHER ? (t0 + kChunk <= sg.t_out) : false;   // student chunks always need h (cheap)
+      const bool do_head = TEACHER && !warm;
+      const int u0[2] = {chunk_idx * uses0, chunk_idx * uses1};        // phase base of parity-indexed barriers
+
+      if (warp == kLoadWarp) {
+        // ================= loader: weights (bulk copy) + halo rows (cp.async) per layer ============
+        for (int l = 0; l < L; l++) {
+          const int s = l & 1;
+          const int use = u0[s] + (l >> 1);                  // how many times stage s was used before
+          if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag)) break;
+          if (lane == 0) {
+            mbar_expect_tx(bar(BAR_WFULL + s), layer_bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sbase + SmemMap::wst + s * SmemMap::wst_bytes),
+                           "l"(p.packed + (size_t)l * layer_bytes), "r"(layer_bytes), "r"(bar(BAR_WFULL + s)) : "memory");
+          }
+          // halo rows of layer l: inputs at t0-d .. t0-1 (zeros before the segment start)
+          if (l >= 2 && !mbar_wait(bar(BAR_G1 + s), (use - 1) & 1, abort_flag)) break;   // G1 of layer l-2 retired
+          const int d = p.dil[l];
+          const uint8_t* rl = ring + p.ring_off[l];
+          const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
+          const int slot0 = t0 % d;                            // (t0 - d + i) mod d == (t0 + i) mod d
+          for (int kc = 0; kc < 4; kc++) {
+            for (int i = lane; i < d; i += 32) {
+              const uint32_t dst = dst0 + (uint32_t)(kc * kRows + kHalo - d + i) * 16;
+              if (t0 - d + i >= sg.t_start) {
+                int slot = slot0 + i; if (slot >= d) slot -= d;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rl + ((size_t)kc * d + slot) * 16) : "memory");
+              } else {
+                asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+              }
+            }
+          }
+          asm volatile("cp.async.wait_all;" ::: "memory");
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_HALO + s));
+        }
+      } else if (warp == kMmaWarp) {
+        // ================= MMA issuer (one thread, event driven) =================================
+        if (lane == 0) {
+          constexpr uint32_t fmt = FP16 ? 0u : 1u;
+          constexpr uint32_t id32 = make_idesc(fmt, 128, 32), id128 = make_idesc(fmt, 128, 128);
+          int n_g1[3] = {0, 0, 0}, n_g2[3] = {0, 0, 0}, hs[3] = {0, 0, 0};
+          int w_seen = 0, halo_seen = 0, g2_count = 0;      // layers whose weights / halo were observed
+          int done = 0;
+          const int per_tile_ops = 2 * L + (do_head ? 2 : 0);
+          int issued = 0;
+          const long long tstart = clock64();
+          while (issued < 3 * per_tile_ops) {
+            bool progress = false;
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+              // ---- residual / skip GEMM of layer n_g2[m] ----
+              if (n_g2[m] < n_g1[m]) {
+                const int l = n_g2[m];
+                if (mbar_test(bar(BAR_C + m), (chunk_idx * L + l) & 1)) {
+                  tc_fence_after();
+                  const uint32_t wb = sbase + SmemMap::wst + (l & 1) * SmemMap::wst_bytes + kWfBytes;
+                  const uint32_t ab = sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes;
+#pragma unroll
+                  for (int j = 0; j < 2; j++) {
+                    const uint64_t ad = make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128);
+                    tc_mma(tmem + m * 32, ad, make_desc(wb + (2 * j * wrs_rows) * 16, wrs_rows * 16, 128), id32, j);
+                    if (TEACHER && !warm)
+                      tc_mma(tmem + 128 + m * 128, ad, make_desc(wb + (2 * j * wrs_rows + 32) * 16, wrs_rows * 16, 128),
+                             id128, (l > 0 || j > 0) ? 1u : 0u);
+                  }
+                  tc_commit(bar(BAR_D2 + m));
+                  n_g2[m]++; issued++; progress = true;
+                  if (++g2_count == 3) { g2_count = 0; tc_commit(bar(BAR_WEMPTY + (l & 1))); }
+                }
+              }
+              // ---- filter-conv GEMM of layer n_g1[m] ----
+              const int l = n_g1[m];
+              if (l < L && n_g2[m] == l && (m == 0 || n_g1[m - 1] > l)) {
+                bool ready = true;
+                if (w_seen <= l) {
+                  if (mbar_test(bar(BAR_WFULL + (l & 1)), (u0[l & 1] + (l >> 1)) & 1)) w_seen = l + 1; else ready = false;
+                }
+                if (ready && halo_seen <= l) {
+                  if (mbar_test(bar(BAR_HALO + (l & 1)), (u0[l & 1] + (l >> 1)) & 1)) halo_seen = l + 1; else ready = false;
+                }
+                if (ready && mbar_test(bar(BAR_H + m), (chunk_idx * L + l) & 1)) {
+                  tc_fence_after();
+                  const uint32_t hb = sbase + SmemMap::hbuf + (l & 1) * SmemMap::hbuf_bytes;
+                  const uint32_t wb = sbase + SmemMap::wst + (l & 1) * SmemMap::wst_bytes;
+                  const int d = p.dil[l];
+#pragma unroll
+                  for (int j = 0; j < 4; j++) {     // K = 64: steps 0,1 = tap rows (W[0]), 2,3 = current rows (W[1])
+                    const int row0 = kHalo + m * kTile - (j < 2 ? d : 0);
+                    const uint64_t ad = make_desc(hb + (uint32_t)((2 * (j & 1)) * kRows + row0) * 16, kRows * 16, 128);
+                    const uint64_t bd = make_desc(wb + (2 * j * 32) * 16, 32 * 16, 128);
+                    tc_mma(tmem + m * 32, ad, bd, id32, j);
+                  }
+                  tc_commit(bar(BAR_D1 + m));
+                  if (m == 2) tc_commit(bar(BAR_G1 + (l & 1)));
+                  n_g1[m]++; issued++; progress = true;
+                }
+              }
+              // ---- output head (teacher): relu(skip) @ H1, relu(.) @ H2 ----
+              if (do_head && n_g2[m] == L && hs[m] < 2) {
+                if (mbar_test(bar(BAR_HDA + m), (head_idx * 2 + hs[m]) & 1)) {
+                  tc_fence_after();
+                  const uint32_t ab = sbase + SmemMap::hbuf + m * (16 * kTile * 16);
+                  const uint32_t wb = sbase + SmemMap::head + (hs[m] == 0 ? 0 : kH1Bytes);
+                  const int nrows = hs[m] == 0 ? 128 : 32;
+#pragma unroll
+                  for (int j = 0; j < 8; j++)
+                    tc_mma(hs[m] == 0 ? tmem + 128 + m * 128 : tmem + m * 32,
+                           make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128),
+                           make_desc(wb + (2 * j * nrows) * 16, nrows * 16, 128), hs[m] == 0 ? id128 : id32, j);
+                  tc_commit(bar(BAR_HDD + m));
+                  hs[m]++; issued++; progress = true;
+                }
+              }
+            }
+            if (!progress) {
+              if (*abort_flag) break;
+              if (clock64() - tstart > 8000000000LL) { *abort_flag = 1; break; }
+            }
+          }
+          (void)done;
+        }
+        __syncwarp();
+      } else {
+        // ================= epilogue warpgroup: tile m, row = TMEM lane ============================
+        const int m = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        const int t = t0 + m * kTile + row;
+        const bool in_utt = t < p.T;
+        int frame = (t0 + m * kTile) / p.P;
+        if (frame > p.frames - 1) frame = p.frames - 1;
+        const float* cb = p.cb + ((size_t)sg.b * p.frames + frame) * (size_t)(L + 1) * 32;
+        const float* s_bias = reinterpret_cast<const float*>(smem + SmemMap::bias);
+        const float* s_front = reinterpret_cast<const float*>(smem + SmemMap::front);
+        const int rc = m * kTile + row;                 // row inside the chunk
+        float h[32], v[32];
+        bool alive = true;
+
+        // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
+        {
+          const float* xb = p.x_in + (size_t)sg.b * p.T;
+          const float xm1 = (t >= 1 && t - 1 < p.T) ? __ldg(xb + t - 1) : 0.f;
+          const float xm2 = (t >= 2 && t - 2 < p.T) ? __ldg(xb + t - 2) : 0.f;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb) + j4);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const int j = j4 * 4 + q;
+              h[j] = fmaf(xm2, s_front[j], fmaf(xm1, s_front[32 + j], cc[q]));
+            }
+          }
+          alive = mbar_wait(bar(BAR_HALO + 0), u0[0] & 1, abort_flag);      // ring 0 was read for this chunk
+          store_row<FP16>(smem + SmemMap::hbuf, kRows, kHalo + rc, h);
+          const int d0 = p.dil[0];
+          if (rc >= kChunk - d0) store_row<FP16>(ring + p.ring_off[0], d0, t % d0, h);
+          fence_async_smem();
+          mbar_arrive(bar(BAR_H + m));
+        }
+
+        for (int l = 0; l < L && alive; l++) {
+          const uint32_t ph = (chunk_idx * L + l) & 1;
+          // ---- gate: tanh, sigmoid of the tanh, product (ops.py:28,33,36) ----
+          if (!mbar_wait(bar(BAR_D1 + m), ph, abort_flag)) { alive = false; break; }
+          tc_fence_after();
+          tc_ld32(tmem + lane_addr + m * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + l * 32 + j4 * 4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float f = tanh_fast(v[j4 * 4 + q] + bb[q]);
+              const float g = fmaf(0.5f, tanh_fast(0.5f * f), 0.5f);
+              v[j4 * 4 + q] = f * g;
+            }
+          }
+          store_row<FP16>(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, v);
+          tc_fence_before();
+          fence_async_smem();
+          mbar_arrive(bar(BAR_C + m));
+
+          // ---- residual: dense = (inputs + residual) * sqrt(1/2) (ops.py:39-40), next conditioning ----
+          if (!mbar_wait(bar(BAR_D2 + m), ph, abort_flag)) { alive = false; break; }
+          tc_fence_after();
+          tc_ld32(tmem + lane_addr + m * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb + (size_t)(l + 1) * 32) + j4);
+            h[j4 * 4 + 0] = fmaf(h[j4 * 4 + 0] + v[j4 * 4 + 0], SRWN_SQRT_HALF, c4.x);
+            h[j4 * 4 + 1] = fmaf(h[j4 * 4 + 1] + v[j4 * 4 + 1], SRWN_SQRT_HALF, c4.y);
+            h[j4 * 4 + 2] = fmaf(h[j4 * 4 + 2] + v[j4 * 4 + 2], SRWN_SQRT_HALF, c4.z);
+            h[j4 * 4 + 3] = fmaf(h[j4 * 4 + 3] + v[j4 * 4 + 3], SRWN_SQRT_HALF, c4.w);
+          }
+          if (l + 1 < L) {
+            const int s = (l + 1) & 1;
+            // activation buffer s is free once the filter-conv MMAs of layer l-1 retired, and
+            // ring l+1 may be overwritten once this chunk's halo of layer l+1 was read
+            if (l >= 1 && !mbar_wait(bar(BAR_G1 + s), (u0[s] + ((l - 1) >> 1)) & 1, abort_flag)) { alive = false; break; }
+            if (!mbar_wait(bar(BAR_HALO + s), (u0[s] + ((l + 1) >> 1)) & 1, abort_flag)) { alive = false; break; }
+            store_row<FP16>(smem + SmemMap::hbuf + s * SmemMap::hbuf_bytes, kRows, kHalo + rc, h);
+            const int dn = p.dil[l + 1];
+            if (rc >= kChunk - dn) store_row<FP16>(ring + p.ring_off[l + 1], dn, t % dn, h);
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(bar(BAR_H + m));
+          } else {
+            tc_fence_before();
+          }
+        }
+
+        if (TEACHER) {
+          if (do_head && alive) {
+            const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
+            uint8_t* a3 = smem + SmemMap::hbuf + m * (16 * kTile * 16);
+            // all filter-conv MMAs of the last layer retired -> both activation buffers are free
+            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag);
+            // relu(sum of skips + summed skip biases) -> operand of the S->S conv (model.py:190-193)
+            for (int q = 0; q < 4 && alive; q++) {
+              tc_ld32(tmem + lane_addr + 128 + m * 128 + q * 32, v);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + s_hb[q * 32 + j], 0.f);
+              store_row<FP16>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, v);
+            }
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(bar(BAR_HDA + m));
+            alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2) & 1, abort_flag);
+            tc_fence_after();
+            for (int q = 0; q < 4 && alive; q++) {        // relu(. + b1) -> operand of the S->4M conv (model.py:194-196)
+              tc_ld32(tmem + lane_addr + 128 + m * 128 + q * 32, v);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + s_hb[128 + q * 32 + j], 0.f);
+              store_row<FP16>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, v);
+            }
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(bar(BAR_HDA + m));
+            alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2 + 1) & 1, abort_flag);
+            tc_fence_after();
+            tc_ld32(tmem + lane_addr + m * 32, v);
+            tc_wait_ld();
+            tc_fence_before();
+            if (alive && in_utt && t >= sg.t_out) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] += s_hb[256 + j];
+              const size_t at = (size_t)sg.b * p.T + t;
+              if (p.logits_out) {
+                float* dst = p.logits_out + at * p.O;
+                if (p.O == 20) {
+#pragma unroll
+                  for (int j = 0; j < 5; j++)
+                    reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                  for (int j = 0; j < p.O; j++) dst[j] = v[j];
+                }
+              }
+              if (p.x_scored) {
+                const float nl = mol_nll_one(__ldg(p.x_scored + at), v, p.M);     // ops.py:124-175
+                if (p.nll_out) p.nll_out[at] = nl;
+                nll_acc += (double)nl;
+              }
+            }
+          }
+        } else if (alive) {
+          // student flow head: relu -> 1x1 R->2; scale = exp(p0), mean = p1; out = x*scale + mean
+          // (model.py:451-452, 479-482)
+          const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
+          const float* hk = s_hb + 288;
+          float p0 = hk[64], p1 = hk[65];
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float e = fmaxf(h[j], 0.f);
+            p0 = fmaf(e, hk[2 * j], p0);
+            p1 = fmaf(e, hk[2 * j + 1], p1);
+          }
+          if (in_utt && t >= sg.t_out) {
+            const size_t at = (size_t)sg.b * p.T + t;
+            const float sc = expf(p0);
+            p.scale_out[at] = sc;
+            p.mean_out[at] = p1;
+            p.x_out[at] = fmaf(__ldg(p.x_in + at), sc, p1);
+          }
+        }
+      }
+      if (do_head) head_idx++;
+      tc_fence_before();
+      __syncthreads();          // chunk boundary: every role is quiescent, buffers and rings are consistent
+      tc_fence_after();
+      if (*abort_flag) break;
+    }
+    if (*abort_flag) break;
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------
+  if (TEACHER && p.nll_partial) {
+    double* s_red = reinterpret_cast<double*>(smem + SmemMap::cbuf);     // reuse (everything is quiescent)
+    for (int s = 16; s >= 1; s >>= 1) nll_acc += __shfl_xor_sync(0xffffffffu, nll_acc, s);
+    if (lane == 0) s_red[warp] = nll_acc;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0;
+      for (int w = 0; w < 12; w++) tot += s_red[w];
+      p.nll_partial[blockIdx.x] = tot;
+    }
+  }
+  if (tid == 0 && *abort_flag) atomicExch(p.err, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// sums the per-CTA partial log-likelihoods in a fixed order (deterministic for a given partition)
+__global__ void k_sum_partials(const double* __restrict__ part, int n, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double tot = 0;
+    for (int i = 0; i < n; i++) tot += part[i];
+    *out = (float)tot;
+  }
+}
+
+// cb[b][frame][0] = front bias + cond_0; cb[..][l+1] = sqrt(1/2)*res_bias_l + cond_{l+1} (0 past the last layer)
+__global__ void k_fold_bias(const float* __restrict__ cond, const float* __restrict__ front_b,
+                            const float* __restrict__ res_b, float* __restrict__ cb, int L) {
+  const int bf = blockIdx.x;
+  for (int o = threadIdx.x; o < (L + 1) * 32; o += blockDim.x) {
+    const int i = o / 32, j = o % 32;
+    float v = i < L ? cond[((size_t)bf * L + i) * 32 + j] : 0.f;
+    v += i == 0 ? front_b[j] : SRWN_SQRT_HALF * res_b[(i - 1) * 32 + j];
+    cb[(size_t)bf * (L + 1) * 32 + o] = v;
+  }
+}
+
+}  // namespace fused
+
+using namespace fused;
+
+// ---- host side ---------------------------------------------------------------------------------
+static size_t stack_image_bytes(const srwn_ctx* c) {
+  const bool teacher = c->cfg.kind == SRWN_TEACHER;
+  const size_t layer_bytes = kWfBytes + (teacher ? kWrsTeacher : kWrsStudent);
+  size_t n = (size_t)c->cfg.n_layers * layer_bytes;
+  n += (size_t)(kMaxLayers * 32 + 64 + 128 + 128 + 32 + 64 + 4) * 4;
+  if (teacher) n += kH1Bytes + kH2Bytes;
+  return (n + 255) & ~(size_t)255;
+}
+
+bool fused_supported(const srwn_ctx* c) {
+  if (c->cfg.n_layers > kMaxLayers || c->cfg.pool_stride % kTile != 0) return false;
+  for (int d : c->dilations) if (d > kHalo) return false;
+  if (c->cfg.kind == SRWN_TEACHER && 4 * c->cfg.num_mixtures > 32) return false;
+  return true;
+}
+
+size_t fused_packed_bytes(const srwn_ctx* c) {
+  return fused_supported(c) ? 2 * (size_t)c->n_stacks * stack_image_bytes(c) : 0;   // [bf16 | fp16] images
+}
+
+static uint16_t to_bits(float f, bool fp16) {
+  if (fp16) { __half h = __float2half_rn(f); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// element (n, k) of a K-major operand with `rows` N-rows: [k/8][n][k%8]
+static inline size_t kmajor_idx(int n, int k, int rows) { return ((size_t)(k / 8) * rows + n) * 8 + (k % 8); }
+
+int fused_pack_weights(srwn_ctx* c, cudaStream_t st) {
+  if (!fused_supported(c) || !c->d_packed) return SRWN_OK;
+  const bool teacher = c->cfg.kind == SRWN_TEACHER;
+  const int L = c->cfg.n_layers, O = 4 * c->cfg.num_mixtures;
+  const size_t img = stack_image_bytes(c);
+  const size_t layer_bytes = kWfBytes + (teacher ? kWrsTeacher : kWrsStudent);
+  const int wrs_rows = teacher ? 160 : 32;
+  std::vector<uint8_t> host(2 * (size_t)c->n_stacks * img, 0);
+  const float* W = srwn_host_weights(c);
+  const StackOffsets& o = c->off;
+  for (int fmt = 0; fmt < 2; fmt++) {
+    const bool fp16 = fmt == 1;
+    for (int s = 0; s < c->n_stacks; s++) {
+      const float* w = W + (size_t)s * c->stack_floats;
+      uint8_t* base = host.data() + ((size_t)fmt * c->n_stacks + s) * img;
+      for (int l = 0; l < L; l++) {
+        uint16_t* wf = reinterpret_cast<uint16_t*>(base + (size_t)l * layer_bytes);
+        uint16_t* wrs = reinterpret_cast<uint16_t*>(base + (size_t)l * layer_bytes + kWfBytes);
+        const float* fk = w + o.filt_k + (size_t)l * 2 * kR * kR;      // [2][Cin][Cout]
+        for (int k = 0; k < 64; k++)
+          for (int n = 0; n < 32; n++) wf[kmajor_idx(n, k, 32)] = to_bits(fk[(size_t)k * kR + n], fp16);
+        const float* rk = w + o.res_k + (size_t)l * kR * kR;          // [Cin][Cout]
+        for (int k = 0; k < 32; k++)
+          for (int n = 0; n < 32; n++) wrs[kmajor_idx(n, k, wrs_rows)] = to_bits(rk[(size_t)k * kR + n], fp16);
+        if (teacher) {
+          const float* sk = w + o.skip_k + (size_t)l * kR * kS;       // [Cin][S]
+          for (int k = 0; k < 32; k++)
+            for (int n = 0; n < kS; n++) wrs[kmajor_idx(32 + n, k, wrs_rows)] = to_bits(sk[(size_t)k * kS + n], fp16);
+        }
+      }
+      float* fx = reinterpret_cast<float*>(base + (size_t)L * layer_bytes);
+      for (int l = 0; l < L; l++)
+        for (int j = 0; j < 32; j++) fx[l * 32 + j] = w[o.filt_b + (size_t)l * kR + j];
+      float* ffront = fx + kMaxLayers * 32;
+      for (int j = 0; j < 64; j++) ffront[j] = w[o.front_k + j];       // [2][R]
+      float* fhb = ffront + 64;
+      if (teacher) {
+        for (int j = 0; j < 128; j++) { fhb[j] = w[o.skip_b_sum + j]; fhb[128 + j] = w[o.head1_b + j]; }
+        for (int j = 0; j < 32; j++) fhb[256 + j] = j < O ? w[o.head2_b + j] : 0.f;
+        uint16_t* h1 = reinterpret_cast<uint16_t*>(fhb + 128 + 128 + 32 + 64 + 4);
+        uint16_t* h2 = h1 + 128 * 128;
+        for (int k = 0; k < 128; k++) {
+          for (int n = 0; n < 128; n++) h1[kmajor_idx(n, k, 128)] = to_bits(w[o.head1_k + (size_t)k * kS + n], fp16);
+          for (int n = 0; n < 32; n++) h2[kmajor_idx(n, k, 32)] = to_bits(n < O ? w[o.head2_k + (size_t)k * O + n] : 0.f, fp16);
+        }
+      } else {
+        for (int j = 0; j < 64; j++) fhb[288 + j] = w[o.head1_k + j];  // [R][2]
+        fhb[288 + 64] = w[o.head1_b + 0]; fhb[288 + 65] = w[o.head1_b + 1];
+      }
+    }
+  }
+  SRWN_CUDA(cudaMemcpyAsync(c->d_packed, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+  SRWN_CUDA(cudaStreamSynchronize(st));
+  return SRWN_OK;
+}
+
+// ---- work partition: equal-cost contiguous pieces of the (utterance, chunk) line -------------------
+struct Partition { std::vector<Seg> segs; std::vector<int> nseg; int grid; };
+
+static bool try_partition(int B, int T, int warm_chunks, int grid, double budget, Partition* out) {
+  const int NC = (T + kChunk - 1) / kChunk;
+  std::vector<Seg> segs((size_t)grid * kMaxSeg);
+  std::vector<int> nseg(grid, 0);
+  int cta = 0;
+  double used = 0;
+  for (int b = 0; b < B; b++) {
+    int c0 = 0;
+    while (c0 < NC) {
+      if (cta >= grid) return false;
+      const int warm = c0 == 0 ? 0 : std::min(warm_chunks, c0);
+      double room = budget - used - 0.85 * warm;
+      int take = (int)room;
+      if (take < 1 || nseg[cta] >= kMaxSeg) {
+        if (used == 0 && nseg[cta] < kMaxSeg) take = 1; else { cta++; used = 0; continue; }
+      }
+      take = std::min(take, NC - c0);
+      Seg s;
+      s.b = b; s.t_start = (c0 - warm) * kChunk; s.t_out = c0 * kChunk;
+      s.t_end = std::min(T, (c0 + take) * kChunk);
+      segs[(size_t)cta * kMaxSeg + nseg[cta]++] = s;
+      used += take + 0.85 * warm;
+      c0 += take;
+    }
+  }
+  if (out) { out->segs.swap(segs); out->nseg.swap(nseg); out->grid = grid; }
+  return true;
+}
+
+static Partition make_partition(int B, int T, int sum_d, int grid) {
+  const int NC = (T + kChunk - 1) / kChunk;
+  const int warm_chunks = (sum_d + kChunk - 1) / kChunk;
+  const long long total = (long long)B * NC;
+  if (total < grid) grid = (int)total;
+  double lo = (double)total / grid, hi = lo + warm_chunks + 2;
+  Partition best;
+  while (!try_partition(B, T, warm_chunks, grid, hi, &best)) hi *= 1.5;
+  for (int it = 0; it < 24; it++) {
+    const double mid = 0.5 * (lo + hi);
+    Partition cand;
+    if (try_partition(B, T, warm_chunks, grid, mid, &cand)) { hi = mid; best = cand; } else lo = mid;
+  }
+  return best;
+}
+
+struct FusedWs {
+  float *cond, *cb; uint8_t* rings; Seg* segs; int* nseg; double* partial; int* err;
+  float *scales, *means, *xa, *xb;
+  size_t bytes;
+};
+
+static FusedWs carve_fused(const srwn_ctx* c, int B, int T, void* ws, size_t cap) {
+  WsCarver w(ws, cap);
+  FusedWs r{};
+  const size_t frames = T / c->cfg.pool_stride, L = c->cfg.n_layers, n = (size_t)B * T;
+  const int grid = c->sm_count > 0 ? c->sm_count : 148;
+  r.cond = w.take<float>((size_t)B * frames * L * 32);
+  r.cb = w.take<float>((size_t)B * frames * (L + 1) * 32);
+  r.rings = w.take<uint8_t>((size_t)grid * ((size_t)c->sum_dilation * 64 + 256));
+  r.segs = w.take<Seg>((size_t)grid * kMaxSeg);
+  r.nseg = w.take<int>(grid);
+  r.partial = w.take<double>(grid);
+  r.err = w.take<int>(4);
+  if (c->cfg.kind == SRWN_STUDENT) {
+    r.scales = w.take<float>(n * c->cfg.num_flows);
+    r.means = w.take<float>(n * c->cfg.num_flows);
+    r.xa = w.take<float>(n);
+    r.xb = w.take<float>(n);
+  }
+  r.bytes = w.used;
+  return r;
+}
+
+size_t fused_workspace_bytes(const srwn_ctx* c, int op, int B, int T) {
+  return carve_fused(c, B, T, nullptr, 0).bytes;
+}
+
+template <bool TEACHER>
+static int launch_fused(srwn_ctx* c, const Params& p, int grid, int fp16, cudaStream_t st) {
+  auto kern = fp16 ? k_fused<TEACHER, true> : k_fused<TEACHER, false>;
+  SRWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemMap::total));
+  kern<<<grid, kThreads, SmemMap::total, st>>>(p);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const FusedWs& w, Params* p,
+                   Partition* part, bool first, int fp16, cudaStream_t st) {
+  const int L = c->cfg.n_layers, P = c->cfg.pool_stride, frames = T / P;
+  const float* sw = stack_w(c, stack);
+  k_cond<<<B * frames, 256, 0, st>>>(enc, sw + c->off.cond_k, sw + c->off.cond_b, w.cond, B * frames, L,
+                                     c->cfg.cond_channels);
+  SRWN_LAUNCH_CHECK();
+  k_fold_bias<<<B * frames, 256, 0, st>>>(w.cond, sw + c->off.front_b, sw + c->off.res_b, w.cb, L);
+  SRWN_LAUNCH_CHECK();
+  if (first) {
+    *part = make_partition(B, T, c->sum_dilation, c->sm_count);
+    SRWN_CUDA(cudaMemcpyAsync(w.segs, part->segs.data(), part->segs.size() * sizeof(Seg), cudaMemcpyHostToDevice, st));
+    SRWN_CUDA(cudaMemcpyAsync(w.nseg, part->nseg.data(), part->nseg.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SRWN_CUDA(cudaMemsetAsync(w.err, 0, 16, st));
+    SRWN_CUDA(cudaStreamSynchronize(st));     // the partition vectors are host temporaries
+  }
+  memset(p, 0, sizeof(*p));
+  const size_t img = stack_image_bytes(c);
+  p->packed = (const uint8_t*)c->d_packed + ((size_t)(fp16 ? 1 : 0) * c->n_stacks + stack) * img;
+  p->cb = w.cb; p->rings = w.rings; p->segs = w.segs; p->nseg = w.nseg; p->err = w.err;
+  p->T = T; p->L = L; p->P = P; p->frames = frames;
+  p->O = 4 * c->cfg.num_mixtures; p->M = c->cfg.num_mixtures;
+  p->ring_bytes_per_cta = c->sum_dilation * 64 + 256;
+  int off = 0;
+  for (int l = 0; l < L; l++) { p->dil[l] = c->dilations[l]; p->ring_off[l] = off; off += c->dilations[l] * 64; }
+  return SRWN_OK;
+}
 
 int run_teacher_fused_bf16(srwn_ctx* c, const float* x_in, const float* enc, const float* x_scored,
-                           float* nll_out, float* nll_sum, float* logits_out, int B, int T, void* ws,
-                           size_t ws_bytes, cudaStream_t st) {
-  return srwn_fail(SRWN_ERR_UNSUPPORTED, "bf16 fused path not built");
+                           float* nll_out, float* nll_sum, float* logits_out, int B, int T, int fp16,
+                           void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!fused_supported(c)) return srwn_fail(SRWN_ERR_UNSUPPORTED, "fused 16-bit path needs dilations <= %d, layers <= %d, pool_stride %% 128 == 0", kHalo, kMaxLayers);
+  FusedWs w = carve_fused(c, B, T, ws, ws_bytes);
+  if (!ws || w.bytes > ws_bytes) return srwn_fail(SRWN_ERR_WORKSPACE, "workspace too small: need %zu bytes", w.bytes);
+  Params p;
+  Partition part;
+  int rc = prepare(c, 0, enc, B, T, w, &p, &part, true, fp16, st);
+  if (rc) return rc;
+  p.x_in = x_in; p.x_scored = x_scored; p.logits_out = logits_out; p.nll_out = nll_out;
+  p.nll_partial = (x_scored && nll_sum) ? w.partial : nullptr;
+  {
+    ProfScope prof(c, st, fp16 ? "k_fused<teacher,fp16>" : "k_fused<teacher,bf16>", 1);
+    rc = launch_fused<true>(c, p, part.grid, fp16, st);
+    if (rc) return rc;
+  }
+  if (p.nll_partial) {
+    k_sum_partials<<<1, 32, 0, st>>>(w.partial, part.grid, nll_sum);
+    SRWN_LAUNCH_CHECK();
+  }
+  return SRWN_OK;
 }
+
 int run_student_fused_bf16(srwn_ctx* c, const float* z, const float* enc, float* out, float* s_tot,
-                           float* mu_tot, float* x_last, int B, int T, void* ws, size_t ws_bytes,
+                           float* mu_tot, float* x_last, int B, int T, int fp16, void* ws, size_t ws_bytes,
                            cudaStream_t st) {
-  return srwn_fail(SRWN_ERR_UNSUPPORTED, "bf16 fused path not built");
+  if (!fused_supported(c)) return srwn_fail(SRWN_ERR_UNSUPPORTED, "fused 16-bit path needs dilations <= %d, layers <= %d, pool_stride %% 128 == 0", kHalo, kMaxLayers);
+  FusedWs w = carve_fused(c, B, T, ws, ws_bytes);
+  if (!ws || w.bytes > ws_bytes) return srwn_fail(SRWN_ERR_WORKSPACE, "workspace too small: need %zu bytes", w.bytes);
+  const size_t n = (size_t)B * T;
+  const int F = c->cfg.num_flows;
+  const float* xin = z;
+  Partition part;
+  for (int f = 0; f < F; f++) {                     // model.py:509-513: flows are strictly sequential
+    Params p;
+    int rc = prepare(c, f, enc, B, T, w, &p, &part, f == 0, fp16, st);
+    if (rc) return rc;
+    float* xout = (f == F - 1 && x_last) ? x_last : ((f & 1) ? w.xb : w.xa);
+    p.x_in = xin; p.scale_out = w.scales + (size_t)f * n; p.mean_out = w.means + (size_t)f * n; p.x_out = xout;
+    ProfScope prof(c, st, fp16 ? "k_fused<student,fp16>" : "k_fused<student,bf16>", 1);
+    rc = launch_fused<false>(c, p, part.grid, fp16, st);
+    if (rc) return rc;
+    xin = xout;
+  }
+  return run_flow_compose(z, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
+}
+
+// reads the device-side abort flag of the last fused launch (synchronises the stream)
+int fused_check_error(void* ws, size_t ws_bytes, const srwn_ctx* c, int B, int T, cudaStream_t st) {
+  FusedWs w = carve_fused(c, B, T, ws, ws_bytes);
+  int flag = 0;
+  SRWN_CUDA(cudaStreamSynchronize(st));
+  SRWN_CUDA(cudaMemcpy(&flag, w.err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) return srwn_fail(SRWN_ERR_CUDA, "fused kernel aborted: a pipeline wait timed out");
+  return SRWN_OK;
 }

@@ -74,6 +74,12 @@ class _Engine(object):
         _lib.check(self.lib.srwn_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(name)))
         return ms.value, n.value, name.value.decode()
 
+    def check_async(self, op, B, T, precision):
+        """Synchronises and raises if the last fused launch aborted on the device."""
+        ws, wsn = self.workspace(op, B, T, precision)
+        _lib.check(self.lib.srwn_check_async_error(self.h, op, B, T, precision, ws, wsn,
+                                                   torch.cuda.current_stream().cuda_stream))
+
     def workspace(self, op, B, T, precision):
         n = ctypes.c_size_t()
         _lib.check(self.lib.srwn_workspace_bytes(self.h, op, B, T, precision, ctypes.byref(n)))
@@ -223,7 +229,7 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         return dict(self._weights)
 
     def available_precisions(self):
-        return ["fp32", "bf16"] if _fused_available(self._eng) else ["fp32"]
+        return ["fp32", "bf16", "fp16"] if _fused_available(self._eng) else ["fp32"]
 
     def load(self, logdir):
         return self._load(logdir)
@@ -386,7 +392,7 @@ class ParallelWaveNet(_CheckpointMixin):
         return dict(self._weights)
 
     def available_precisions(self):
-        return ["fp32", "bf16"] if _fused_available(self._eng) else ["fp32"]
+        return ["fp32", "bf16", "fp16"] if _fused_available(self._eng) else ["fp32"]
 
     def load(self, sess, logdir):
         if isinstance(self.teacher, str):
