@@ -136,7 +136,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="teacher_nll", choices=["teacher_nll", "student", "generate"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config)")
     ap.add_argument("--length", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -187,7 +187,7 @@ def main():
         flop_per_sample = FLOP_PER_SAMPLE_TEACHER
     prec = args.precision
     if prec == "auto":
-        prec = "bf16" if "bf16" in model.available_precisions() else "fp32"
+        prec = "fp16" if "fp16" in model.available_precisions() else "fp32"
     if args.workload == "generate":
         prec = "fp32"
         u1_h, u2_h = synth.sampler_uniforms(B, T, seed=999 + rank)
@@ -268,7 +268,7 @@ def main():
     if args.workload == "generate":
         ach = BYTES_PER_SAMPLE_AR * B * T / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s"}
-    elif prec == "bf16":
+    elif prec in ("bf16", "fp16"):
         ach = flop_per_sample * B * T / (k_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s"}
     else:
@@ -291,7 +291,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[prec],
             "data": "synthetic",
             "config": {"workload": names[args.workload], "batch_per_gpu": B, "global_batch": B * world,
                        "samples_per_utterance": T, "layers": len(dil), "parallelism": "batch-sharded x%d" % world,

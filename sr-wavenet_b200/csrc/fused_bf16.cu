@@ -39,8 +39,8 @@ constexpr int kChunk = kTile * kTiles;          // 384 time steps per chunk
 constexpr int kHalo = 512;                      // largest dilation the layout supports
 constexpr int kRows = kHalo + kChunk;           // rows per activation buffer
 constexpr int kMaxLayers = 40;
-constexpr int kThreads = 14 * 32;
-constexpr int kMmaWarp = 12, kLoadWarp = 13;
+constexpr int kThreads = 16 * 32;
+constexpr int kMmaWarp = 12, kLoadWarp = 15;     // warps 12,13,14 issue MMAs for tiles 0,1,2
 constexpr int kMaxSeg = 8;
 
 // packed operand image (bytes, per layer): WF [8 kc][32 n][8] | WRS [4 kc][160 or 32 n][8]
@@ -125,14 +125,24 @@ __device__ __forceinline__ bool mbar_test(uint32_t a, uint32_t parity) {
                "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking poll (test_wait never suspends the thread, unlike try_wait)
+__device__ __forceinline__ uint32_t mbar_poll(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok;
+}
 // bounded wait: a stuck pipeline raises the abort flag instead of hanging the GPU
-__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity, volatile int* abort_flag) {
+__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity, volatile int* abort_flag, int code = 0) {
   if (mbar_test(a, parity)) return true;
   const long long t0 = clock64();
   while (true) {
     if (mbar_test(a, parity)) return true;
     if (*abort_flag) return false;
-    if (clock64() - t0 > 4000000000LL) { *abort_flag = 1; return false; }
+    if (clock64() - t0 > 1000000000LL) {
+      if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = code;   // first failing wait wins
+      return false;
+    }
   }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
-  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 8);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 8);   // [0] flag [1] code [2..4] g1_issued
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SmemMap::misc);
   auto bar = [&](int i) { return sbase + SmemMap::bars + i * 8; };
   const int L = p.L;
@@ -215,10 +225,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
       mbar_init(bar(BAR_H + i), kTile); mbar_init(bar(BAR_HDA + i), kTile); mbar_init(bar(BAR_HDD + i), 1);
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), 1);
-      mbar_init(bar(BAR_HALO + i), 1); mbar_init(bar(BAR_G1 + i), 1);
+      mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), kTiles);
+      mbar_init(bar(BAR_HALO + i), 1); mbar_init(bar(BAR_G1 + i), kTiles);
     }
-    *abort_flag = 0;
+    abort_flag[0] = 0; abort_flag[1] = 0; abort_flag[2] = 0; abort_flag[3] = 0; abort_flag[4] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {  // resident constants: biases, front conv, head weights (plain loads; made visible below)
@@ -269,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         for (int l = 0; l < L; l++) {
           const int s = l & 1;
           const int use = u0[s] + (l >> 1);                  // how many times stage s was used before
-          if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag)) break;
+          if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag, 0x1000000 | l)) break;
           if (lane == 0) {
             mbar_expect_tx(bar(BAR_WFULL + s), layer_bytes);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -277,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
                            "l"(p.packed + (size_t)l * layer_bytes), "r"(layer_bytes), "r"(bar(BAR_WFULL + s)) : "memory");
           }
           // halo rows of layer l: inputs at t0-d .. t0-1 (zeros before the segment start)
-          if (l >= 2 && !mbar_wait(bar(BAR_G1 + s), (use - 1) & 1, abort_flag)) break;   // G1 of layer l-2 retired
+          if (l >= 2 && !mbar_wait(bar(BAR_G1 + s), (use - 1) & 1, abort_flag, 0x1100000 | l)) break;   // G1 of layer l-2 retired
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
@@ -298,91 +308,88 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(BAR_HALO + s));
         }
-      } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (one thread, event driven) =================================
+      } else if (warp >= kMmaWarp) {
+        // ================= MMA issuers: warp 12+m drives tile m (one elected thread each) ==========
+        // Static per-tile sequence with blocking (hardware-suspended) waits: H -> filter-conv GEMM ->
+        // C -> residual/skip GEMM, per layer; then the two head GEMMs.  Tiles issue the filter conv of
+        // a layer in order (tile m's tap rows can live in tile m-1's rows), tracked by a shared counter.
         if (lane == 0) {
+          const int m = warp - kMmaWarp;
           constexpr uint32_t fmt = FP16 ? 0u : 1u;
           constexpr uint32_t id32 = make_idesc(fmt, 128, 32), id128 = make_idesc(fmt, 128, 128);
-          int n_g1[3] = {0, 0, 0}, n_g2[3] = {0, 0, 0}, hs[3] = {0, 0, 0};
-          int w_seen = 0, halo_seen = 0, g2_count = 0;      // layers whose weights / halo were observed
-          int done = 0;
-          const int per_tile_ops = 2 * L + (do_head ? 2 : 0);
-          int issued = 0;
-          const long long tstart = clock64();
-          while (issued < 3 * per_tile_ops) {
-            bool progress = false;
-#pragma unroll
-            for (int m = 0; m < 3; m++) {
-              // ---- residual / skip GEMM of layer n_g2[m] ----
-              if (n_g2[m] < n_g1[m]) {
-                const int l = n_g2[m];
-                if (mbar_test(bar(BAR_C + m), (chunk_idx * L + l) & 1)) {
-                  tc_fence_after();
-                  const uint32_t wb = sbase + SmemMap::wst + (l & 1) * SmemMap::wst_bytes + kWfBytes;
-                  const uint32_t ab = sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes;
-#pragma unroll
-                  for (int j = 0; j < 2; j++) {
-                    const uint64_t ad = make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128);
-                    tc_mma(tmem + m * 32, ad, make_desc(wb + (2 * j * wrs_rows) * 16, wrs_rows * 16, 128), id32, j);
-                    if (TEACHER && !warm)
-                      tc_mma(tmem + 128 + m * 128, ad, make_desc(wb + (2 * j * wrs_rows + 32) * 16, wrs_rows * 16, 128),
-                             id128, (l > 0 || j > 0) ? 1u : 0u);
-                  }
-                  tc_commit(bar(BAR_D2 + m));
-                  n_g2[m]++; issued++; progress = true;
-                  if (++g2_count == 3) { g2_count = 0; tc_commit(bar(BAR_WEMPTY + (l & 1))); }
+          volatile int* g1_issued = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 16);   // [3] running counts
+          bool ok = true;
+          for (int l = 0; l < L && ok; l++) {
+            const int s = l & 1;
+            const uint32_t ph = (chunk_idx * L + l) & 1, phs = (u0[s] + (l >> 1)) & 1;
+            ok = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l) &&
+                 mbar_wait(bar(BAR_HALO + s), phs, abort_flag, 0x3100000 | (m << 8) | l) &&
+                 mbar_wait(bar(BAR_H + m), ph, abort_flag, 0x3200000 | (m << 8) | l);
+            if (!ok) break;
+            if (m > 0) {
+              const int want = chunk_idx * L + l + 1;
+              const long long ts = clock64();
+              while (g1_issued[m - 1] < want) {
+                if (*abort_flag) { ok = false; break; }
+                if (clock64() - ts > 1000000000LL) {
+                  if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = 0x3300000 | (m << 8) | l;
+                  ok = false; break;
                 }
               }
-              // ---- filter-conv GEMM of layer n_g1[m] ----
-              const int l = n_g1[m];
-              if (l < L && n_g2[m] == l && (m == 0 || n_g1[m - 1] > l)) {
-                bool ready = true;
-                if (w_seen <= l) {
-                  if (mbar_test(bar(BAR_WFULL + (l & 1)), (u0[l & 1] + (l >> 1)) & 1)) w_seen = l + 1; else ready = false;
-                }
-                if (ready && halo_seen <= l) {
-                  if (mbar_test(bar(BAR_HALO + (l & 1)), (u0[l & 1] + (l >> 1)) & 1)) halo_seen = l + 1; else ready = false;
-                }
-                if (ready && mbar_test(bar(BAR_H + m), (chunk_idx * L + l) & 1)) {
-                  tc_fence_after();
-                  const uint32_t hb = sbase + SmemMap::hbuf + (l & 1) * SmemMap::hbuf_bytes;
-                  const uint32_t wb = sbase + SmemMap::wst + (l & 1) * SmemMap::wst_bytes;
-                  const int d = p.dil[l];
-#pragma unroll
-                  for (int j = 0; j < 4; j++) {     // K = 64: steps 0,1 = tap rows (W[0]), 2,3 = current rows (W[1])
-                    const int row0 = kHalo + m * kTile - (j < 2 ? d : 0);
-                    const uint64_t ad = make_desc(hb + (uint32_t)((2 * (j & 1)) * kRows + row0) * 16, kRows * 16, 128);
-                    const uint64_t bd = make_desc(wb + (2 * j * 32) * 16, 32 * 16, 128);
-                    tc_mma(tmem + m * 32, ad, bd, id32, j);
-                  }
-                  tc_commit(bar(BAR_D1 + m));
-                  if (m == 2) tc_commit(bar(BAR_G1 + (l & 1)));
-                  n_g1[m]++; issued++; progress = true;
-                }
-              }
-              // ---- output head (teacher): relu(skip) @ H1, relu(.) @ H2 ----
-              if (do_head && n_g2[m] == L && hs[m] < 2) {
-                if (mbar_test(bar(BAR_HDA + m), (head_idx * 2 + hs[m]) & 1)) {
-                  tc_fence_after();
-                  const uint32_t ab = sbase + SmemMap::hbuf + m * (16 * kTile * 16);
-                  const uint32_t wb = sbase + SmemMap::head + (hs[m] == 0 ? 0 : kH1Bytes);
-                  const int nrows = hs[m] == 0 ? 128 : 32;
-#pragma unroll
-                  for (int j = 0; j < 8; j++)
-                    tc_mma(hs[m] == 0 ? tmem + 128 + m * 128 : tmem + m * 32,
-                           make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128),
-                           make_desc(wb + (2 * j * nrows) * 16, nrows * 16, 128), hs[m] == 0 ? id128 : id32, j);
-                  tc_commit(bar(BAR_HDD + m));
-                  hs[m]++; issued++; progress = true;
-                }
-              }
+              if (!ok) break;
+              __threadfence_block();
             }
-            if (!progress) {
-              if (*abort_flag) break;
-              if (clock64() - tstart > 8000000000LL) { *abort_flag = 1; break; }
+            tc_fence_after();
+            {
+              const uint32_t hb = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
+              const uint32_t wb = sbase + SmemMap::wst + s * SmemMap::wst_bytes;
+              const int d = p.dil[l];
+#pragma unroll
+              for (int j = 0; j < 4; j++) {     // K = 64: steps 0,1 = tap rows (W[0]), 2,3 = current rows (W[1])
+                const int row0 = kHalo + m * kTile - (j < 2 ? d : 0);
+                const uint64_t ad = make_desc(hb + (uint32_t)((2 * (j & 1)) * kRows + row0) * 16, kRows * 16, 128);
+                const uint64_t bd = make_desc(wb + (2 * j * 32) * 16, 32 * 16, 128);
+                tc_mma(tmem + m * 32, ad, bd, id32, j);
+              }
+              tc_commit(bar(BAR_D1 + m));
+              tc_commit(bar(BAR_G1 + s));               // 3 arrivals (one per tile) complete the phase
+              __threadfence_block();
+              g1_issued[m] = chunk_idx * L + l + 1;
+            }
+            if (!mbar_wait(bar(BAR_C + m), ph, abort_flag, 0x3400000 | (m << 8) | l)) { ok = false; break; }
+            tc_fence_after();
+            {
+              const uint32_t wb = sbase + SmemMap::wst + s * SmemMap::wst_bytes + kWfBytes;
+              const uint32_t ab = sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes;
+#pragma unroll
+              for (int j = 0; j < 2; j++) {
+                const uint64_t ad = make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128);
+                tc_mma(tmem + m * 32, ad, make_desc(wb + (2 * j * wrs_rows) * 16, wrs_rows * 16, 128), id32, j);
+                if (TEACHER && !warm)
+                  tc_mma(tmem + 128 + m * 128, ad, make_desc(wb + (2 * j * wrs_rows + 32) * 16, wrs_rows * 16, 128),
+                         id128, (l > 0 || j > 0) ? 1u : 0u);
+              }
+              tc_commit(bar(BAR_D2 + m));
+              tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
             }
           }
-          (void)done;
+          if (do_head && ok) {
+            // ---- output head (teacher): relu(skip) @ H1, then relu(.) @ H2 ----
+#pragma unroll
+            for (int hs = 0; hs < 2 && ok; hs++) {
+              if (!mbar_wait(bar(BAR_HDA + m), (head_idx * 2 + hs) & 1, abort_flag, 0x3500000 | (m << 8) | hs)) { ok = false; break; }
+              tc_fence_after();
+              const uint32_t ab = sbase + SmemMap::hbuf + m * (16 * kTile * 16);
+              const uint32_t wb = sbase + SmemMap::head + (hs == 0 ? 0 : kH1Bytes);
+              const int nrows = hs == 0 ? 128 : 32;
+#pragma unroll
+              for (int j = 0; j < 8; j++)
+                tc_mma(hs == 0 ? tmem + 128 + m * 128 : tmem + m * 32,
+                       make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128),
+                       make_desc(wb + (2 * j * nrows) * 16, nrows * 16, 128), hs == 0 ? id128 : id32, j);
+              tc_commit(bar(BAR_HDD + m));
+            }
+          }
         }
         __syncwarp();
       } else {
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
               h[j] = fmaf(xm2, s_front[j], fmaf(xm1, s_front[32 + j], cc[q]));
             }
           }
-          alive = mbar_wait(bar(BAR_HALO + 0), u0[0] & 1, abort_flag);      // ring 0 was read for this chunk
+          alive = mbar_wait(bar(BAR_HALO + 0), u0[0] & 1, abort_flag, 0x2000000 | (m << 8));      // ring 0 was read for this chunk
           store_row<FP16>(smem + SmemMap::hbuf, kRows, kHalo + rc, h);
           const int d0 = p.dil[0];
           if (rc >= kChunk - d0) store_row<FP16>(ring + p.ring_off[0], d0, t % d0, h);
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         for (int l = 0; l < L && alive; l++) {
           const uint32_t ph = (chunk_idx * L + l) & 1;
           // ---- gate: tanh, sigmoid of the tanh, product (ops.py:28,33,36) ----
-          if (!mbar_wait(bar(BAR_D1 + m), ph, abort_flag)) { alive = false; break; }
+          if (!mbar_wait(bar(BAR_D1 + m), ph, abort_flag, 0x2100000 | (m << 8) | l)) { alive = false; break; }
           tc_fence_after();
           tc_ld32(tmem + lane_addr + m * 32, v);
           tc_wait_ld();
@@ -448,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           mbar_arrive(bar(BAR_C + m));
 
           // ---- residual: dense = (inputs + residual) * sqrt(1/2) (ops.py:39-40), next conditioning ----
-          if (!mbar_wait(bar(BAR_D2 + m), ph, abort_flag)) { alive = false; break; }
+          if (!mbar_wait(bar(BAR_D2 + m), ph, abort_flag, 0x2200000 | (m << 8) | l)) { alive = false; break; }
           tc_fence_after();
           tc_ld32(tmem + lane_addr + m * 32, v);
           tc_wait_ld();
@@ -464,8 +471,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             const int s = (l + 1) & 1;
             // activation buffer s is free once the filter-conv MMAs of layer l-1 retired, and
             // ring l+1 may be overwritten once this chunk's halo of layer l+1 was read
-            if (l >= 1 && !mbar_wait(bar(BAR_G1 + s), (u0[s] + ((l - 1) >> 1)) & 1, abort_flag)) { alive = false; break; }
-            if (!mbar_wait(bar(BAR_HALO + s), (u0[s] + ((l + 1) >> 1)) & 1, abort_flag)) { alive = false; break; }
+            if (l >= 1 && !mbar_wait(bar(BAR_G1 + s), (u0[s] + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l)) { alive = false; break; }
+            if (!mbar_wait(bar(BAR_HALO + s), (u0[s] + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l)) { alive = false; break; }
             store_row<FP16>(smem + SmemMap::hbuf + s * SmemMap::hbuf_bytes, kRows, kHalo + rc, h);
             const int dn = p.dil[l + 1];
             if (rc >= kChunk - dn) store_row<FP16>(ring + p.ring_off[l + 1], dn, t % dn, h);
@@ -482,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
             uint8_t* a3 = smem + SmemMap::hbuf + m * (16 * kTile * 16);
             // all filter-conv MMAs of the last layer retired -> both activation buffers are free
-            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag);
+            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8));
             // relu(sum of skips + summed skip biases) -> operand of the S->S conv (model.py:190-193)
             for (int q = 0; q < 4 && alive; q++) {
               tc_ld32(tmem + lane_addr + 128 + m * 128 + q * 32, v);
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(BAR_HDA + m));
-            alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2) & 1, abort_flag);
+            alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2) & 1, abort_flag, 0x2600000 | (m << 8));
             tc_fence_after();
             for (int q = 0; q < 4 && alive; q++) {        // relu(. + b1) -> operand of the S->4M conv (model.py:194-196)
               tc_ld32(tmem + lane_addr + 128 + m * 128 + q * 32, v);
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(BAR_HDA + m));
-            alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2 + 1) & 1, abort_flag);
+            alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2 + 1) & 1, abort_flag, 0x2700000 | (m << 8));
             tc_fence_after();
             tc_ld32(tmem + lane_addr + m * 32, v);
             tc_wait_ld();
@@ -570,11 +577,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
     __syncthreads();
     if (tid == 0) {
       double tot = 0;
-      for (int w = 0; w < 12; w++) tot += s_red[w];
+      for (int w = 0; w < 12; w++) tot += s_red[w];   // epilogue warps only
       p.nll_partial[blockIdx.x] = tot;
     }
   }
-  if (tid == 0 && *abort_flag) atomicExch(p.err, 1);
+  if (tid == 0 && *abort_flag && atomicCAS(p.err, 0, 1) == 0) {
+    p.err[1] = abort_flag[1]; p.err[2] = chunk_idx; p.err[3] = blockIdx.x;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -865,6 +874,11 @@ int fused_check_error(void* ws, size_t ws_bytes, const srwn_ctx* c, int B, int T
   int flag = 0;
   SRWN_CUDA(cudaStreamSynchronize(st));
   SRWN_CUDA(cudaMemcpy(&flag, w.err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) return srwn_fail(SRWN_ERR_CUDA, "fused kernel aborted: a pipeline wait timed out");
+  if (flag) {
+    int info[4] = {0, 0, 0, 0};
+    cudaMemcpy(info, w.err, sizeof(info), cudaMemcpyDeviceToHost);
+    return srwn_fail(SRWN_ERR_CUDA, "fused kernel aborted: pipeline wait timed out (code 0x%x, chunk %d, cta %d)",
+                     info[1], info[2], info[3]);
+  }
   return SRWN_OK;
 }
