@@ -25,6 +25,7 @@
 #include "mol.cuh"
 #include <cuda_fp16.h>
 #include <algorithm>
+#include <cstdlib>
 
 const float* srwn_host_weights(srwn_ctx* c);
 __global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
@@ -67,6 +68,8 @@ struct Params {
   float* mean_out;            // student [B][T]
   float* x_out;               // student [B][T]
   int* err;                   // device error flag
+  long long* trace;           // optional [7 roles][kMaxLayers][12] clock64 stamps of CTA 0 (tuning aid)
+  int trace_chunk;
   int T, L, P, frames, O, M;
   int ring_bytes_per_cta;
   int dil[kMaxLayers];
@@ -85,7 +88,8 @@ struct SmemMap {
   static constexpr int bias = head + kH1Bytes + kH2Bytes;         // [kMaxLayers][32] filter bias fp32
   static constexpr int hbias = bias + kMaxLayers * 32 * 4;        // skip_b_sum[128] | h1_b[128] | h2_b[32] | flow hk[64] hb[2]
   static constexpr int front = hbias + (128 + 128 + 32 + 64 + 4) * 4;   // fk[64]
-  static constexpr int bars = front + 64 * 4;
+  static constexpr int cbs = front + 64 * 4;                      // [3 tiles][kMaxLayers+1][32] folded bias + conditioning of the chunk
+  static constexpr int bars = cbs + kTiles * (kMaxLayers + 1) * 32 * 4;
   static constexpr int n_bars = 32;
   static constexpr int misc = bars + n_bars * 8;                  // tmem ptr, abort flag
   static constexpr int total = misc + 64;
@@ -186,10 +190,27 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// gate of ops.py:28,33,36: f = tanh(a); out = f * sigmoid(f).  f lies in [-1,1], where
+// sigmoid(f) = 0.5 + f*P(f^2) with a degree-3 minimax P (max error 1.1e-7 in fp32 evaluation),
+// so the gate costs one MUFU (tanh.approx, rel. error 2^-11) plus FMA-pipe work.
+__device__ __forceinline__ float gate(float a) {
+  const float f = tanh_fast(a);
+  const float s = f * f;
+  float pz = fmaf(s, -0.00016942188085522503f, 0.0020539257675409317f);
+  pz = fmaf(s, pz, -0.020825408399105072f);
+  pz = fmaf(s, pz, 0.24999941885471344f);
+  return fmaf(s, pz, 0.5f * f);
 }
 
 // stores one row (32 values) as 4 x 16 B into a [kc][rows][8] operand buffer
@@ -203,6 +224,11 @@ __device__ __forceinline__ void store_row(uint8_t* buf, int rows_per_kc, int row
     *reinterpret_cast<uint4*>(buf + ((size_t)kc * rows_per_kc + row) * 16) = q;
   }
 }
+
+#define TRACE(role, layer, slot)                                                            \
+  do {                                                                                      \
+    if (tracing) p.trace[((role) * kMaxLayers + (layer)) * 12 + (slot)] = clock64();      \
+  } while (0)
 
 // ---- the kernel --------------------------------------------------------------------------
 template <bool TEACHER, bool FP16>
@@ -273,12 +299,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
       const bool warm = TEACHER ? (t0 + kChunk <= sg.t_out) : false;   // student chunks always need h (cheap)
       const bool do_head = TEACHER && !warm;
       const int u0[2] = {chunk_idx * uses0, chunk_idx * uses1};        // phase base of parity-indexed barriers
+      const bool tracing_chunk = p.trace != nullptr && blockIdx.x == 0 && chunk_idx == p.trace_chunk;
 
       if (warp == kLoadWarp) {
         // ================= loader: weights (bulk copy) + halo rows (cp.async) per layer ============
         for (int l = 0; l < L; l++) {
           const int s = l & 1;
           const int use = u0[s] + (l >> 1);                  // how many times stage s was used before
+          const bool tracing = tracing_chunk && lane == 0;
+          TRACE(6, l, 0);
           if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag, 0x1000000 | l)) break;
           if (lane == 0) {
             mbar_expect_tx(bar(BAR_WFULL + s), layer_bytes);
@@ -286,8 +315,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
                          ::"r"(sbase + SmemMap::wst + s * SmemMap::wst_bytes),
                            "l"(p.packed + (size_t)l * layer_bytes), "r"(layer_bytes), "r"(bar(BAR_WFULL + s)) : "memory");
           }
+          TRACE(6, l, 1);
           // halo rows of layer l: inputs at t0-d .. t0-1 (zeros before the segment start)
           if (l >= 2 && !mbar_wait(bar(BAR_G1 + s), (use - 1) & 1, abort_flag, 0x1100000 | l)) break;   // G1 of layer l-2 retired
+          TRACE(6, l, 2);
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
@@ -307,25 +338,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(BAR_HALO + s));
+          TRACE(6, l, 3);
         }
       } else if (warp >= kMmaWarp) {
         // ================= MMA issuers: warp 12+m drives tile m (one elected thread each) ==========
         // Static per-tile sequence with blocking (hardware-suspended) waits: H -> filter-conv GEMM ->
         // C -> residual/skip GEMM, per layer; then the two head GEMMs.  Tiles issue the filter conv of
         // a layer in order (tile m's tap rows can live in tile m-1's rows), tracked by a shared counter.
-        if (lane == 0) {
-          const int m = warp - kMmaWarp;
+        // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform
+        // registers; only the tcgen05 instructions are predicated on one elected lane.
+        {
+          const int m = __shfl_sync(0xffffffffu, warp - kMmaWarp, 0);
+          const bool leader = elect_one();
           constexpr uint32_t fmt = FP16 ? 0u : 1u;
           constexpr uint32_t id32 = make_idesc(fmt, 128, 32), id128 = make_idesc(fmt, 128, 128);
           volatile int* g1_issued = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 16);   // [3] running counts
           bool ok = true;
+          const bool tracing = tracing_chunk && leader;
           for (int l = 0; l < L && ok; l++) {
             const int s = l & 1;
             const uint32_t ph = (chunk_idx * L + l) & 1, phs = (u0[s] + (l >> 1)) & 1;
+            TRACE(3 + m, l, 0);
             ok = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l) &&
                  mbar_wait(bar(BAR_HALO + s), phs, abort_flag, 0x3100000 | (m << 8) | l) &&
                  mbar_wait(bar(BAR_H + m), ph, abort_flag, 0x3200000 | (m << 8) | l);
             if (!ok) break;
+            TRACE(3 + m, l, 1);
             if (m > 0) {
               const int want = chunk_idx * L + l + 1;
               const long long ts = clock64();
@@ -340,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
               __threadfence_block();
             }
             tc_fence_after();
-            {
+            if (leader) {
               const uint32_t hb = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
               const uint32_t wb = sbase + SmemMap::wst + s * SmemMap::wst_bytes;
               const int d = p.dil[l];
@@ -356,9 +394,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
               __threadfence_block();
               g1_issued[m] = chunk_idx * L + l + 1;
             }
+            __syncwarp();
+            TRACE(3 + m, l, 2);
             if (!mbar_wait(bar(BAR_C + m), ph, abort_flag, 0x3400000 | (m << 8) | l)) { ok = false; break; }
+            TRACE(3 + m, l, 3);
             tc_fence_after();
-            {
+            if (leader) {
               const uint32_t wb = sbase + SmemMap::wst + s * SmemMap::wst_bytes + kWfBytes;
               const uint32_t ab = sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes;
 #pragma unroll
@@ -372,6 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
               tc_commit(bar(BAR_D2 + m));
               tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
             }
+            __syncwarp();
+            TRACE(3 + m, l, 4);
           }
           if (do_head && ok) {
             // ---- output head (teacher): relu(skip) @ H1, then relu(.) @ H2 ----
@@ -379,15 +422,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             for (int hs = 0; hs < 2 && ok; hs++) {
               if (!mbar_wait(bar(BAR_HDA + m), (head_idx * 2 + hs) & 1, abort_flag, 0x3500000 | (m << 8) | hs)) { ok = false; break; }
               tc_fence_after();
-              const uint32_t ab = sbase + SmemMap::hbuf + m * (16 * kTile * 16);
-              const uint32_t wb = sbase + SmemMap::head + (hs == 0 ? 0 : kH1Bytes);
-              const int nrows = hs == 0 ? 128 : 32;
+              if (leader) {
+                const uint32_t ab = sbase + SmemMap::hbuf + m * (16 * kTile * 16);
+                const uint32_t wb = sbase + SmemMap::head + (hs == 0 ? 0 : kH1Bytes);
+                const int nrows = hs == 0 ? 128 : 32;
 #pragma unroll
-              for (int j = 0; j < 8; j++)
-                tc_mma(hs == 0 ? tmem + 128 + m * 128 : tmem + m * 32,
-                       make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128),
-                       make_desc(wb + (2 * j * nrows) * 16, nrows * 16, 128), hs == 0 ? id128 : id32, j);
-              tc_commit(bar(BAR_HDD + m));
+                for (int j = 0; j < 8; j++)
+                  tc_mma(hs == 0 ? tmem + 128 + m * 128 : tmem + m * 32,
+                         make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128),
+                         make_desc(wb + (2 * j * nrows) * 16, nrows * 16, 128), hs == 0 ? id128 : id32, j);
+                tc_commit(bar(BAR_HDD + m));
+              }
+              __syncwarp();
             }
           }
         }
@@ -401,12 +447,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         const bool in_utt = t < p.T;
         int frame = (t0 + m * kTile) / p.P;
         if (frame > p.frames - 1) frame = p.frames - 1;
-        const float* cb = p.cb + ((size_t)sg.b * p.frames + frame) * (size_t)(L + 1) * 32;
+        const float* cb_g = p.cb + ((size_t)sg.b * p.frames + frame) * (size_t)(L + 1) * 32;
+        float* cb = reinterpret_cast<float*>(smem + SmemMap::cbs) + m * (kMaxLayers + 1) * 32;
+        for (int i = row; i < (L + 1) * 32; i += kTile) cb[i] = __ldg(cb_g + i);     // one latent frame per tile
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + m) : "memory");
         const float* s_bias = reinterpret_cast<const float*>(smem + SmemMap::bias);
         const float* s_front = reinterpret_cast<const float*>(smem + SmemMap::front);
         const int rc = m * kTile + row;                 // row inside the chunk
         float h[32], v[32];
         bool alive = true;
+        const bool tracing = tracing_chunk && row == 0;
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
         {
@@ -415,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           const float xm2 = (t >= 2 && t - 2 < p.T) ? __ldg(xb + t - 2) : 0.f;
 #pragma unroll
           for (int j4 = 0; j4 < 8; j4++) {
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb) + j4);
+            const float4 c4 = *(reinterpret_cast<const float4*>(cb) + j4);
             const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -433,52 +483,70 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
 
         for (int l = 0; l < L && alive; l++) {
           const uint32_t ph = (chunk_idx * L + l) & 1;
+          TRACE(m, l, 0);
           // ---- gate: tanh, sigmoid of the tanh, product (ops.py:28,33,36) ----
           if (!mbar_wait(bar(BAR_D1 + m), ph, abort_flag, 0x2100000 | (m << 8) | l)) { alive = false; break; }
+          TRACE(m, l, 1);
           tc_fence_after();
           tc_ld32(tmem + lane_addr + m * 32, v);
           tc_wait_ld();
+          TRACE(m, l, 2);
 #pragma unroll
           for (int j4 = 0; j4 < 8; j4++) {
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + l * 32 + j4 * 4);
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              const float f = tanh_fast(v[j4 * 4 + q] + bb[q]);
-              const float g = fmaf(0.5f, tanh_fast(0.5f * f), 0.5f);
-              v[j4 * 4 + q] = f * g;
+              v[j4 * 4 + q] = gate(v[j4 * 4 + q] + bb[q]);
             }
           }
           store_row<FP16>(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, v);
+          TRACE(m, l, 3);
           tc_fence_before();
           fence_async_smem();
+          TRACE(m, l, 4);
           mbar_arrive(bar(BAR_C + m));
+          TRACE(m, l, 5);
+          // poll (non-blocking) the two conditions the next operand store depends on while the
+          // residual GEMM runs; they are almost always already satisfied
+          uint32_t g1_ok = 1, halo_ok = 1;
+          if (l + 1 < L) {
+            const int sn = (l + 1) & 1;
+            if (l >= 1) g1_ok = mbar_poll(bar(BAR_G1 + sn), (u0[sn] + ((l - 1) >> 1)) & 1);
+            halo_ok = mbar_poll(bar(BAR_HALO + sn), (u0[sn] + ((l + 1) >> 1)) & 1);
+          }
 
           // ---- residual: dense = (inputs + residual) * sqrt(1/2) (ops.py:39-40), next conditioning ----
           if (!mbar_wait(bar(BAR_D2 + m), ph, abort_flag, 0x2200000 | (m << 8) | l)) { alive = false; break; }
+          TRACE(m, l, 6);
           tc_fence_after();
           tc_ld32(tmem + lane_addr + m * 32, v);
           tc_wait_ld();
+          TRACE(m, l, 7);
 #pragma unroll
           for (int j4 = 0; j4 < 8; j4++) {
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb + (size_t)(l + 1) * 32) + j4);
+            const float4 c4 = *(reinterpret_cast<const float4*>(cb + (l + 1) * 32) + j4);
             h[j4 * 4 + 0] = fmaf(h[j4 * 4 + 0] + v[j4 * 4 + 0], SRWN_SQRT_HALF, c4.x);
             h[j4 * 4 + 1] = fmaf(h[j4 * 4 + 1] + v[j4 * 4 + 1], SRWN_SQRT_HALF, c4.y);
             h[j4 * 4 + 2] = fmaf(h[j4 * 4 + 2] + v[j4 * 4 + 2], SRWN_SQRT_HALF, c4.z);
             h[j4 * 4 + 3] = fmaf(h[j4 * 4 + 3] + v[j4 * 4 + 3], SRWN_SQRT_HALF, c4.w);
           }
+          TRACE(m, l, 8);
           if (l + 1 < L) {
             const int s = (l + 1) & 1;
             // activation buffer s is free once the filter-conv MMAs of layer l-1 retired, and
             // ring l+1 may be overwritten once this chunk's halo of layer l+1 was read
-            if (l >= 1 && !mbar_wait(bar(BAR_G1 + s), (u0[s] + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l)) { alive = false; break; }
-            if (!mbar_wait(bar(BAR_HALO + s), (u0[s] + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l)) { alive = false; break; }
+            if (!g1_ok && !mbar_wait(bar(BAR_G1 + s), (u0[s] + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l)) { alive = false; break; }
+            if (!halo_ok && !mbar_wait(bar(BAR_HALO + s), (u0[s] + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l)) { alive = false; break; }
+            TRACE(m, l, 9);
             store_row<FP16>(smem + SmemMap::hbuf + s * SmemMap::hbuf_bytes, kRows, kHalo + rc, h);
             const int dn = p.dil[l + 1];
             if (rc >= kChunk - dn) store_row<FP16>(ring + p.ring_off[l + 1], dn, t % dn, h);
+            TRACE(m, l, 10);
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(BAR_H + m));
+            TRACE(m, l, 11);
           } else {
             tc_fence_before();
           }
@@ -522,6 +590,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
 #pragma unroll
               for (int j = 0; j < 32; j++) v[j] += s_hb[256 + j];
               const size_t at = (size_t)sg.b * p.T + t;
+              float nl = 0.f;
+              if (p.x_scored) {                      // ops.py:124-175; M == 5 keeps the logits in registers
+                const float xs = __ldg(p.x_scored + at);
+                if (p.M == 5) nl = mol_nll_fixed<5>(xs, v);
+                else {
+                  float lg[32];
+#pragma unroll
+                  for (int j = 0; j < 32; j++) lg[j] = v[j];
+                  nl = mol_nll_one(xs, lg, p.M);
+                }
+              }
               if (p.logits_out) {
                 float* dst = p.logits_out + at * p.O;
                 if (p.O == 20) {
@@ -529,11 +608,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
                   for (int j = 0; j < 5; j++)
                     reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 } else {
-                  for (int j = 0; j < p.O; j++) dst[j] = v[j];
+#pragma unroll
+                  for (int j = 0; j < 32; j++) if (j < p.O) dst[j] = v[j];
                 }
               }
               if (p.x_scored) {
-                const float nl = mol_nll_one(__ldg(p.x_scored + at), v, p.M);     // ops.py:124-175
                 if (p.nll_out) p.nll_out[at] = nl;
                 nll_acc += (double)nl;
               }
@@ -752,7 +831,7 @@ static Partition make_partition(int B, int T, int sum_d, int grid) {
 }
 
 struct FusedWs {
-  float *cond, *cb; uint8_t* rings; Seg* segs; int* nseg; double* partial; int* err;
+  float *cond, *cb; uint8_t* rings; Seg* segs; int* nseg; double* partial; int* err; long long* trace;
   float *scales, *means, *xa, *xb;
   size_t bytes;
 };
@@ -769,6 +848,7 @@ static FusedWs carve_fused(const srwn_ctx* c, int B, int T, void* ws, size_t cap
   r.nseg = w.take<int>(grid);
   r.partial = w.take<double>(grid);
   r.err = w.take<int>(4);
+  r.trace = w.take<long long>(7 * kMaxLayers * 12);
   if (c->cfg.kind == SRWN_STUDENT) {
     r.scales = w.take<float>(n * c->cfg.num_flows);
     r.means = w.take<float>(n * c->cfg.num_flows);
@@ -811,6 +891,8 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   memset(p, 0, sizeof(*p));
   const size_t img = stack_image_bytes(c);
   p->packed = (const uint8_t*)c->d_packed + ((size_t)(fp16 ? 1 : 0) * c->n_stacks + stack) * img;
+  p->trace = getenv("SRWN_TRACE") ? w.trace : nullptr;
+  p->trace_chunk = getenv("SRWN_TRACE") ? atoi(getenv("SRWN_TRACE")) : 0;
   p->cb = w.cb; p->rings = w.rings; p->segs = w.segs; p->nseg = w.nseg; p->err = w.err;
   p->T = T; p->L = L; p->P = P; p->frames = frames;
   p->O = 4 * c->cfg.num_mixtures; p->M = c->cfg.num_mixtures;
@@ -880,5 +962,15 @@ int fused_check_error(void* ws, size_t ws_bytes, const srwn_ctx* c, int B, int T
     return srwn_fail(SRWN_ERR_CUDA, "fused kernel aborted: pipeline wait timed out (code 0x%x, chunk %d, cta %d)",
                      info[1], info[2], info[3]);
   }
+  return SRWN_OK;
+}
+
+// tuning aid: copies the clock64 trace of CTA 0 (see SRWN_TRACE) to the host
+extern "C" int srwn_debug_read_trace(srwn_handle_t h, int32_t B, int32_t T, void* ws, size_t ws_bytes,
+                                     long long* out, int32_t count) {
+  FusedWs w = carve_fused(h, B, T, ws, ws_bytes);
+  if (count > 7 * kMaxLayers * 12) count = 7 * kMaxLayers * 12;
+  SRWN_CUDA(cudaDeviceSynchronize());
+  SRWN_CUDA(cudaMemcpy(out, w.trace, sizeof(long long) * count, cudaMemcpyDeviceToHost));
   return SRWN_OK;
 }

@@ -48,6 +48,51 @@ __device__ __forceinline__ float mol_nll_one(float x, const float* lg, int M) {
   return -(best + logf(s));                           // ops.py:117-122,172-175
 }
 
+// Same as mol_nll_one with the mixture count fixed at compile time (all indexing static, so the
+// logits stay in registers).
+template <int M>
+__device__ __forceinline__ float mol_nll_fixed(float x, const float* lg) {
+  float mx = lg[0];
+#pragma unroll
+  for (int m = 1; m < M; m++) mx = fmaxf(mx, lg[m]);
+  float se = 0.f;
+#pragma unroll
+  for (int m = 0; m < M; m++) se += expf(lg[m] - mx);
+  const float lse_p = mx + logf(se);
+  float lp[M];
+  float best = -INFINITY;
+#pragma unroll
+  for (int m = 0; m < M; m++) {
+    const float mean = lg[M + m];
+    const float ls = fmaxf(lg[2 * M + m], -7.f);
+    const float inv = expf(-ls);
+    const float c = x - mean;
+    const float plus = inv * (c + 1.f / 255.f);
+    const float mn = inv * (c - 1.f / 255.f);
+    const float mid = inv * c;
+    float v;
+    if (x < -0.999f) {
+      v = plus - srwn_softplus(plus);
+    } else if (x > 0.999f) {
+      v = -srwn_softplus(mn);
+    } else {
+      float a = plus, b = mn;
+      if (mid > 0.f) { a = -mn; b = -plus; }
+      const float ea = expf(a), eb = expf(b);
+      const float delta = -ea * expm1f(b - a) / ((1.f + ea) * (1.f + eb));
+      if (delta > 1e-5f) v = logf(fmaxf(delta, 1e-12f));
+      else v = mid - ls - 2.f * srwn_softplus(mid) - 4.8481163902538321f;
+    }
+    v += lg[m] - lse_p;
+    lp[m] = v;
+    best = fmaxf(best, v);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int m = 0; m < M; m++) s += expf(lp[m] - best);
+  return -(best + logf(s));
+}
+
 // ops.py:178-201 with the uniforms injected; *k_out = Gumbel-argmax mixture index (ops.py:187).
 __device__ __forceinline__ float mol_sample_one(const float* lg, const float* u1, float u2, int M,
                                                 int* k_out) {
