@@ -179,7 +179,7 @@ def main():
                                      pool_stride=P)
         model.set_weights(synth.make_student_weights(dil, 4))
         x_h = synth.logistic_noise(B, T, seed=777 + rank)
-        flop_per_sample = FLOP_PER_SAMPLE_STUDENT
+        flop_per_sample = FLOP_PER_SAMPLE_STUDENT / 4.0     # the dominant kernel is one flow (one launch per flow)
     else:
         model = srwn.WaveNetAutoEncoder(T, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=P)
         model.set_weights(synth.make_teacher_weights(dil))

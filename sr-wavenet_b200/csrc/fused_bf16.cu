@@ -359,6 +359,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             const int s = l & 1;
             const uint32_t ph = (chunk_idx * L + l) & 1, phs = (u0[s] + (l >> 1)) & 1;
             TRACE(3 + m, l, 0);
+            // descriptors are data independent: build them before blocking so that only the MMA
+            // issue itself sits on the critical path after a barrier flips
+            const uint32_t hb = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
+            const uint32_t wb = sbase + SmemMap::wst + s * SmemMap::wst_bytes;
+            const uint32_t ab = sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes;
+            const int d = p.dil[l];
+            uint64_t a1[4], b1[4], a2[2], b2r[2], b2s[2];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {     // K = 64: steps 0,1 = tap rows (W[0]), 2,3 = current rows (W[1])
+              const int row0 = kHalo + m * kTile - (j < 2 ? d : 0);
+              a1[j] = make_desc(hb + (uint32_t)((2 * (j & 1)) * kRows + row0) * 16, kRows * 16, 128);
+              b1[j] = make_desc(wb + (2 * j * 32) * 16, 32 * 16, 128);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              a2[j] = make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128);
+              b2r[j] = make_desc(wb + kWfBytes + (2 * j * wrs_rows) * 16, wrs_rows * 16, 128);
+              b2s[j] = make_desc(wb + kWfBytes + (2 * j * wrs_rows + 32) * 16, wrs_rows * 16, 128);
+            }
+            const uint32_t skip_acc0 = l > 0 ? 1u : 0u;
             ok = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l) &&
                  mbar_wait(bar(BAR_HALO + s), phs, abort_flag, 0x3100000 | (m << 8) | l) &&
                  mbar_wait(bar(BAR_H + m), ph, abort_flag, 0x3200000 | (m << 8) | l);
@@ -375,23 +395,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
                 }
               }
               if (!ok) break;
-              __threadfence_block();
             }
             tc_fence_after();
             if (leader) {
-              const uint32_t hb = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
-              const uint32_t wb = sbase + SmemMap::wst + s * SmemMap::wst_bytes;
-              const int d = p.dil[l];
 #pragma unroll
-              for (int j = 0; j < 4; j++) {     // K = 64: steps 0,1 = tap rows (W[0]), 2,3 = current rows (W[1])
-                const int row0 = kHalo + m * kTile - (j < 2 ? d : 0);
-                const uint64_t ad = make_desc(hb + (uint32_t)((2 * (j & 1)) * kRows + row0) * 16, kRows * 16, 128);
-                const uint64_t bd = make_desc(wb + (2 * j * 32) * 16, 32 * 16, 128);
-                tc_mma(tmem + m * 32, ad, bd, id32, j);
-              }
+              for (int j = 0; j < 4; j++) tc_mma(tmem + m * 32, a1[j], b1[j], id32, j);
               tc_commit(bar(BAR_D1 + m));
               tc_commit(bar(BAR_G1 + s));               // 3 arrivals (one per tile) complete the phase
-              __threadfence_block();
               g1_issued[m] = chunk_idx * L + l + 1;
             }
             __syncwarp();
@@ -400,15 +410,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             TRACE(3 + m, l, 3);
             tc_fence_after();
             if (leader) {
-              const uint32_t wb = sbase + SmemMap::wst + s * SmemMap::wst_bytes + kWfBytes;
-              const uint32_t ab = sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes;
 #pragma unroll
               for (int j = 0; j < 2; j++) {
-                const uint64_t ad = make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128);
-                tc_mma(tmem + m * 32, ad, make_desc(wb + (2 * j * wrs_rows) * 16, wrs_rows * 16, 128), id32, j);
-                if (TEACHER && !warm)
-                  tc_mma(tmem + 128 + m * 128, ad, make_desc(wb + (2 * j * wrs_rows + 32) * 16, wrs_rows * 16, 128),
-                         id128, (l > 0 || j > 0) ? 1u : 0u);
+                tc_mma(tmem + m * 32, a2[j], b2r[j], id32, j);
+                if (TEACHER && !warm) tc_mma(tmem + 128 + m * 128, a2[j], b2s[j], id128, j > 0 ? 1u : skip_acc0);
               }
               tc_commit(bar(BAR_D2 + m));
               tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
@@ -972,5 +977,74 @@ extern "C" int srwn_debug_read_trace(srwn_handle_t h, int32_t B, int32_t T, void
   if (count > 7 * kMaxLayers * 12) count = 7 * kMaxLayers * 12;
   SRWN_CUDA(cudaDeviceSynchronize());
   SRWN_CUDA(cudaMemcpy(out, w.trace, sizeof(long long) * count, cudaMemcpyDeviceToHost));
+  return SRWN_OK;
+}
+
+// ---- tuning aid: cost of back-to-back tcgen05.mma dispatches (one CTA, garbage operands) ------------
+namespace fused {
+__global__ void __launch_bounds__(128, 1) k_mma_bench(long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t mbar;
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 ones
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&mbar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  fence_async_smem();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  uint32_t phase = 0;
+  if (warp == 0) {
+    const bool leader = elect_one();
+    // configs: {N, number of MMAs, same accumulator?}
+    const int cfgN[8] = {32, 32, 32, 128, 160, 256, 32, 160};
+    const int cfgCnt[8] = {1, 4, 16, 4, 4, 4, 16, 16};
+    const int cfgIndep[8] = {0, 0, 0, 0, 0, 0, 1, 0};
+    for (int c = 0; c < 8; c++) {
+      for (int rep = 0; rep < 3; rep++) {
+        const int N = cfgN[c];
+        const uint32_t idesc = make_idesc(0, 128, N);
+        __syncwarp();
+        const long long t0 = clock64();
+        if (leader) {
+          for (int i = 0; i < cfgCnt[c]; i++) {
+            const uint64_t ad = make_desc(sbase + (i & 3) * 4096, 2048, 128);
+            const uint64_t bd = make_desc(sbase + 32768 + (i & 3) * 512, 16 * N, 128);
+            tc_mma(tmem + (cfgIndep[c] ? (i & 7) * 32 : 0), ad, bd, idesc, i > 0 ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&mbar));
+        }
+        __syncwarp();
+        const long long t1 = clock64();
+        while (!mbar_test(smem_u32(&mbar), phase)) {}
+        phase ^= 1;
+        const long long t2 = clock64();
+        if (leader && rep == 2) { out[c * 2] = t1 - t0; out[c * 2 + 1] = t2 - t0; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+}  // namespace fused
+
+extern "C" int srwn_debug_mma_bench(long long* host_out16) {
+  long long* d = nullptr;
+  SRWN_CUDA(cudaMalloc(&d, 16 * sizeof(long long)));
+  SRWN_CUDA(cudaFuncSetAttribute(fused::k_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  fused::k_mma_bench<<<1, 128, 65536>>>(d);
+  SRWN_CUDA(cudaDeviceSynchronize());
+  SRWN_CUDA(cudaMemcpy(host_out16, d, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  cudaFree(d);
   return SRWN_OK;
 }
