@@ -40,8 +40,6 @@ constexpr int kChunk = kTile * kTiles;          // 384 time steps per chunk
 constexpr int kHalo = 512;                      // largest dilation the layout supports
 constexpr int kRows = kHalo + kChunk;           // rows per activation buffer
 constexpr int kMaxLayers = 40;
-constexpr int kThreads = 16 * 32;
-constexpr int kMmaWarp = 12, kLoadWarp = 15;     // warps 12,13,14 issue MMAs for tiles 0,1,2
 constexpr int kMaxSeg = 8;
 
 // packed operand image (bytes, per layer): WF [8 kc][32 n][8] | WRS [4 kc][160 or 32 n][8]
@@ -171,6 +169,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+template <int N> __device__ __forceinline__ void tc_ld(uint32_t taddr, float* v) {
+  if (N == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle canonical layout: 8-row x 16-byte core matrices; rows 16 B apart,
@@ -230,9 +239,23 @@ __device__ __forceinline__ void store_row(uint8_t* buf, int rows_per_kc, int row
     if (tracing) p.trace[((role) * kMaxLayers + (layer)) * 12 + (slot)] = clock64();      \
   } while (0)
 
+// stores NC consecutive channels (starting at channel c0, a multiple of 8) of one row
+template <bool FP16, int NC>
+__device__ __forceinline__ void store_cols(uint8_t* buf, int rows_per_kc, int row, int c0, const float* v) {
+#pragma unroll
+  for (int k = 0; k < NC / 8; k++) {
+    uint4 q;
+    q.x = pack2<FP16>(v[k * 8 + 0], v[k * 8 + 1]); q.y = pack2<FP16>(v[k * 8 + 2], v[k * 8 + 3]);
+    q.z = pack2<FP16>(v[k * 8 + 4], v[k * 8 + 5]); q.w = pack2<FP16>(v[k * 8 + 6], v[k * 8 + 7]);
+    *reinterpret_cast<uint4*>(buf + ((size_t)(c0 / 8 + k) * rows_per_kc + row) * 16) = q;
+  }
+}
+
 // ---- the kernel --------------------------------------------------------------------------
-template <bool TEACHER, bool FP16>
-__global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
+template <bool TEACHER, bool FP16, int SPLIT>
+__global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params p) {
+  constexpr int kThreads = (12 * SPLIT + 4) * 32;
+  constexpr int kMmaWarp = 12 * SPLIT, kLoadWarp = 12 * SPLIT + 3;   // warps kMmaWarp..+2 issue MMAs for tiles 0,1,2
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
@@ -247,8 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
     for (int i = 0; i < 3; i++) {
-      mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_C + i), kTile); mbar_init(bar(BAR_D2 + i), 1);
-      mbar_init(bar(BAR_H + i), kTile); mbar_init(bar(BAR_HDA + i), kTile); mbar_init(bar(BAR_HDD + i), 1);
+      mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_C + i), kTile * SPLIT); mbar_init(bar(BAR_D2 + i), 1);
+      mbar_init(bar(BAR_H + i), kTile * SPLIT); mbar_init(bar(BAR_HDA + i), kTile * SPLIT); mbar_init(bar(BAR_HDD + i), 1);
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), kTiles);
@@ -444,8 +467,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         }
         __syncwarp();
       } else {
-        // ================= epilogue warpgroup: tile m, row = TMEM lane ============================
-        const int m = warp >> 2;
+        // ================= epilogue warps: tile m, row = TMEM lane, column slice `half` ===========
+        // SPLIT warpgroups share a tile; each thread owns NC = 32/SPLIT residual channels of its row.
+        constexpr int NC = 32 / SPLIT;
+        const int m = warp / (4 * SPLIT);
+        const int half = (warp / 4) % SPLIT;
+        const int c0 = half * NC;                       // first channel owned by this thread
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const int t = t0 + m * kTile + row;
@@ -454,14 +481,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         if (frame > p.frames - 1) frame = p.frames - 1;
         const float* cb_g = p.cb + ((size_t)sg.b * p.frames + frame) * (size_t)(L + 1) * 32;
         float* cb = reinterpret_cast<float*>(smem + SmemMap::cbs) + m * (kMaxLayers + 1) * 32;
-        for (int i = row; i < (L + 1) * 32; i += kTile) cb[i] = __ldg(cb_g + i);     // one latent frame per tile
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + m) : "memory");
+        for (int i = half * kTile + row; i < (L + 1) * 32; i += kTile * SPLIT) cb[i] = __ldg(cb_g + i);   // one latent frame per tile
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + m), "r"(kTile * SPLIT) : "memory");
         const float* s_bias = reinterpret_cast<const float*>(smem + SmemMap::bias);
         const float* s_front = reinterpret_cast<const float*>(smem + SmemMap::front);
         const int rc = m * kTile + row;                 // row inside the chunk
-        float h[32], v[32];
+        float h[NC], v[32];
         bool alive = true;
-        const bool tracing = tracing_chunk && row == 0;
+        const bool tracing = tracing_chunk && row == 0 && half == 0;
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
         {
@@ -469,19 +496,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           const float xm1 = (t >= 1 && t - 1 < p.T) ? __ldg(xb + t - 1) : 0.f;
           const float xm2 = (t >= 2 && t - 2 < p.T) ? __ldg(xb + t - 2) : 0.f;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; j4++) {
-            const float4 c4 = *(reinterpret_cast<const float4*>(cb) + j4);
-            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const int j = j4 * 4 + q;
-              h[j] = fmaf(xm2, s_front[j], fmaf(xm1, s_front[32 + j], cc[q]));
-            }
-          }
+          for (int j = 0; j < NC; j++)
+            h[j] = fmaf(xm2, s_front[c0 + j], fmaf(xm1, s_front[32 + c0 + j], cb[c0 + j]));
           alive = mbar_wait(bar(BAR_HALO + 0), u0[0] & 1, abort_flag, 0x2000000 | (m << 8));      // ring 0 was read for this chunk
-          store_row<FP16>(smem + SmemMap::hbuf, kRows, kHalo + rc, h);
+          store_cols<FP16, NC>(smem + SmemMap::hbuf, kRows, kHalo + rc, c0, h);
           const int d0 = p.dil[0];
-          if (rc >= kChunk - d0) store_row<FP16>(ring + p.ring_off[0], d0, t % d0, h);
+          if (rc >= kChunk - d0) store_cols<FP16, NC>(ring + p.ring_off[0], d0, t % d0, c0, h);
           fence_async_smem();
           mbar_arrive(bar(BAR_H + m));
         }
@@ -493,19 +513,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           if (!mbar_wait(bar(BAR_D1 + m), ph, abort_flag, 0x2100000 | (m << 8) | l)) { alive = false; break; }
           TRACE(m, l, 1);
           tc_fence_after();
-          tc_ld32(tmem + lane_addr + m * 32, v);
+          tc_ld<NC>(tmem + lane_addr + m * 32 + c0, v);
           tc_wait_ld();
           TRACE(m, l, 2);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; j4++) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + l * 32 + j4 * 4);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              v[j4 * 4 + q] = gate(v[j4 * 4 + q] + bb[q]);
-            }
-          }
-          store_row<FP16>(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, v);
+          for (int j = 0; j < NC; j++) v[j] = gate(v[j] + s_bias[l * 32 + c0 + j]);
+          store_cols<FP16, NC>(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, c0, v);
           TRACE(m, l, 3);
           tc_fence_before();
           fence_async_smem();
@@ -525,17 +538,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           if (!mbar_wait(bar(BAR_D2 + m), ph, abort_flag, 0x2200000 | (m << 8) | l)) { alive = false; break; }
           TRACE(m, l, 6);
           tc_fence_after();
-          tc_ld32(tmem + lane_addr + m * 32, v);
+          tc_ld<NC>(tmem + lane_addr + m * 32 + c0, v);
           tc_wait_ld();
           TRACE(m, l, 7);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; j4++) {
-            const float4 c4 = *(reinterpret_cast<const float4*>(cb + (l + 1) * 32) + j4);
-            h[j4 * 4 + 0] = fmaf(h[j4 * 4 + 0] + v[j4 * 4 + 0], SRWN_SQRT_HALF, c4.x);
-            h[j4 * 4 + 1] = fmaf(h[j4 * 4 + 1] + v[j4 * 4 + 1], SRWN_SQRT_HALF, c4.y);
-            h[j4 * 4 + 2] = fmaf(h[j4 * 4 + 2] + v[j4 * 4 + 2], SRWN_SQRT_HALF, c4.z);
-            h[j4 * 4 + 3] = fmaf(h[j4 * 4 + 3] + v[j4 * 4 + 3], SRWN_SQRT_HALF, c4.w);
-          }
+          for (int j = 0; j < NC; j++) h[j] = fmaf(h[j] + v[j], SRWN_SQRT_HALF, cb[(l + 1) * 32 + c0 + j]);
           TRACE(m, l, 8);
           if (l + 1 < L) {
             const int s = (l + 1) & 1;
@@ -544,9 +551,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             if (!g1_ok && !mbar_wait(bar(BAR_G1 + s), (u0[s] + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l)) { alive = false; break; }
             if (!halo_ok && !mbar_wait(bar(BAR_HALO + s), (u0[s] + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l)) { alive = false; break; }
             TRACE(m, l, 9);
-            store_row<FP16>(smem + SmemMap::hbuf + s * SmemMap::hbuf_bytes, kRows, kHalo + rc, h);
+            store_cols<FP16, NC>(smem + SmemMap::hbuf + s * SmemMap::hbuf_bytes, kRows, kHalo + rc, c0, h);
             const int dn = p.dil[l + 1];
-            if (rc >= kChunk - dn) store_row<FP16>(ring + p.ring_off[l + 1], dn, t % dn, h);
+            if (rc >= kChunk - dn) store_cols<FP16, NC>(ring + p.ring_off[l + 1], dn, t % dn, c0, h);
             TRACE(m, l, 10);
             tc_fence_before();
             fence_async_smem();
@@ -561,37 +568,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           if (do_head && alive) {
             const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
             uint8_t* a3 = smem + SmemMap::hbuf + m * (16 * kTile * 16);
+            constexpr int QN = 4 / SPLIT;               // 32-column groups of the 128 skip channels per thread
             // all filter-conv MMAs of the last layer retired -> both activation buffers are free
             alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8));
             // relu(sum of skips + summed skip biases) -> operand of the S->S conv (model.py:190-193)
-            for (int q = 0; q < 4 && alive; q++) {
-              tc_ld32(tmem + lane_addr + 128 + m * 128 + q * 32, v);
+            for (int qq = 0; qq < QN && alive; qq++) {
+              const int q = half * QN + qq;
+              tc_ld<32>(tmem + lane_addr + 128 + m * 128 + q * 32, v);
               tc_wait_ld();
 #pragma unroll
               for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + s_hb[q * 32 + j], 0.f);
-              store_row<FP16>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, v);
+              store_cols<FP16, 32>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, 0, v);
             }
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(BAR_HDA + m));
             alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2) & 1, abort_flag, 0x2600000 | (m << 8));
             tc_fence_after();
-            for (int q = 0; q < 4 && alive; q++) {        // relu(. + b1) -> operand of the S->4M conv (model.py:194-196)
-              tc_ld32(tmem + lane_addr + 128 + m * 128 + q * 32, v);
+            for (int qq = 0; qq < QN && alive; qq++) {        // relu(. + b1) -> operand of the S->4M conv (model.py:194-196)
+              const int q = half * QN + qq;
+              tc_ld<32>(tmem + lane_addr + 128 + m * 128 + q * 32, v);
               tc_wait_ld();
 #pragma unroll
               for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + s_hb[128 + q * 32 + j], 0.f);
-              store_row<FP16>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, v);
+              store_cols<FP16, 32>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, 0, v);
             }
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(BAR_HDA + m));
             alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2 + 1) & 1, abort_flag, 0x2700000 | (m << 8));
             tc_fence_after();
-            tc_ld32(tmem + lane_addr + m * 32, v);
-            tc_wait_ld();
+            if (half == 0) {                             // one thread per row finishes the logits / likelihood
+              tc_ld<32>(tmem + lane_addr + m * 32, v);
+              tc_wait_ld();
+            }
             tc_fence_before();
-            if (alive && in_utt && t >= sg.t_out) {
+            if (half == 0 && alive && in_utt && t >= sg.t_out) {
 #pragma unroll
               for (int j = 0; j < 32; j++) v[j] += s_hb[256 + j];
               const size_t at = (size_t)sg.b * p.T + t;
@@ -625,22 +637,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           }
         } else if (alive) {
           // student flow head: relu -> 1x1 R->2; scale = exp(p0), mean = p1; out = x*scale + mean
-          // (model.py:451-452, 479-482)
+          // (model.py:451-452, 479-482); column slices combine through shared memory
           const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
           const float* hk = s_hb + 288;
-          float p0 = hk[64], p1 = hk[65];
+          float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
+          for (int j = 0; j < NC; j++) {
             const float e = fmaxf(h[j], 0.f);
-            p0 = fmaf(e, hk[2 * j], p0);
-            p1 = fmaf(e, hk[2 * j + 1], p1);
+            p0 = fmaf(e, hk[2 * (c0 + j)], p0);
+            p1 = fmaf(e, hk[2 * (c0 + j) + 1], p1);
           }
-          if (in_utt && t >= sg.t_out) {
+          if (SPLIT > 1) {
+            float2* xch = reinterpret_cast<float2*>(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes);   // gate operand buffer is idle now
+            if (half != 0) xch[(half - 1) * kTile + row] = make_float2(p0, p1);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + m), "r"(kTile * SPLIT) : "memory");
+            if (half == 0)
+              for (int hh = 1; hh < SPLIT; hh++) { const float2 o = xch[(hh - 1) * kTile + row]; p0 += o.x; p1 += o.y; }
+          }
+          if (half == 0 && in_utt && t >= sg.t_out) {
             const size_t at = (size_t)sg.b * p.T + t;
-            const float sc = expf(p0);
+            const float sc = expf(p0 + hk[64]);
+            const float mu = p1 + hk[65];
             p.scale_out[at] = sc;
-            p.mean_out[at] = p1;
-            p.x_out[at] = fmaf(__ldg(p.x_in + at), sc, p1);
+            p.mean_out[at] = mu;
+            p.x_out[at] = fmaf(__ldg(p.x_in + at), sc, mu);
           }
         }
       }
@@ -661,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
     __syncthreads();
     if (tid == 0) {
       double tot = 0;
-      for (int w = 0; w < 12; w++) tot += s_red[w];   // epilogue warps only
+      for (int w = 0; w < 12 * SPLIT; w++) tot += s_red[w];   // epilogue warps only
       p.nll_partial[blockIdx.x] = tot;
     }
   }
@@ -870,9 +890,13 @@ size_t fused_workspace_bytes(const srwn_ctx* c, int op, int B, int T) {
 
 template <bool TEACHER>
 static int launch_fused(srwn_ctx* c, const Params& p, int grid, int fp16, cudaStream_t st) {
-  auto kern = fp16 ? k_fused<TEACHER, true> : k_fused<TEACHER, false>;
+  // SPLIT=2 (two epilogue warpgroups per tile, 896 threads, 72 regs) measured slower than SPLIT=1
+  // (3.99 vs 3.41 ms at 32x64000): the limiter is the SMEM-fed tensor pipe + hand-off chain, not epilogue math
+  static const int split = getenv("SRWN_SPLIT") ? atoi(getenv("SRWN_SPLIT")) : 1;
+  auto kern = split == 2 ? (fp16 ? k_fused<TEACHER, true, 2> : k_fused<TEACHER, false, 2>)
+                         : (fp16 ? k_fused<TEACHER, true, 1> : k_fused<TEACHER, false, 1>);
   SRWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemMap::total));
-  kern<<<grid, kThreads, SmemMap::total, st>>>(p);
+  kern<<<grid, (12 * split + 4) * 32, SmemMap::total, st>>>(p);
   SRWN_LAUNCH_CHECK();
   return SRWN_OK;
 }
