@@ -68,6 +68,7 @@ struct Params {
   int* err;                   // device error flag
   long long* trace;           // optional [7 roles][kMaxLayers][12] clock64 stamps of CTA 0 (tuning aid)
   int trace_chunk;
+  int dbg;                    // tuning experiments (SRWN_DBG): wrong results, timing only
   int T, L, P, frames, O, M;
   int ring_bytes_per_cta;
   int dil[kMaxLayers];
@@ -97,16 +98,14 @@ static_assert(SmemMap::total <= 232448, "shared memory budget");
 static_assert(kTiles * 16 * kTile * 16 <= 2 * SmemMap::hbuf_bytes, "head operand overlay");
 
 enum Bar {
-  BAR_D1 = 0,      // [3] MMA -> epilogue: filter-conv accumulator ready
-  BAR_C = 3,       // [3] epilogue -> MMA: gate operand written (128 arrivals)
-  BAR_D2 = 6,      // [3] MMA -> epilogue: residual (+skip) accumulator ready
-  BAR_H = 9,       // [3] epilogue -> MMA: next layer's operand rows written (128 arrivals)
-  BAR_WFULL = 12,  // [2] loader -> MMA: layer weights landed (tx bytes)
-  BAR_WEMPTY = 14, // [2] MMA -> loader: all MMAs of the layer retired
-  BAR_HALO = 16,   // [2] loader -> MMA/epilogue: halo rows of the layer landed
-  BAR_G1 = 18,     // [2] MMA -> loader/epilogue: all filter-conv MMAs of the layer retired
-  BAR_HDA = 20,    // [3] epilogue -> MMA: head operand written (128 arrivals)
-  BAR_HDD = 23,    // [3] MMA -> epilogue: head accumulator ready
+  BAR_D1 = 0,      // [3] MMA -> tile group: filter-conv accumulator ready (tcgen05.commit)
+  BAR_D2 = 3,      // [3] MMA -> tile group: residual accumulator ready (tcgen05.commit)
+  BAR_HD = 6,      // [3 tiles][2 layer parities] tile group -> higher tiles: input rows of a layer stored (128 arrivals)
+  BAR_WFULL = 12,  // [2] loader -> tile groups: layer weights landed (tx bytes)
+  BAR_WEMPTY = 14, // [2] MMA -> loader: all residual/skip MMAs of the layer retired (3 commits)
+  BAR_HALO = 16,   // [2] loader -> tile groups: halo rows of the layer landed
+  BAR_G1 = 18,     // [2] MMA -> loader/tile groups: all filter-conv MMAs of the layer retired (3 commits)
+  BAR_HDD = 20,    // [3] MMA -> tile group: head accumulator ready
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -128,11 +127,11 @@ __device__ __forceinline__ bool mbar_test(uint32_t a, uint32_t parity) {
   return ok != 0;
 }
 // non-blocking poll (test_wait never suspends the thread, unlike try_wait)
-__device__ __forceinline__ uint32_t mbar_poll(uint32_t a, uint32_t parity) {
+__device__ __forceinline__ bool mbar_poll(uint32_t a, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-  return ok;
+  return ok != 0;
 }
 // bounded wait: a stuck pipeline raises the abort flag instead of hanging the GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity, volatile int* abort_flag, int code = 0) {
@@ -153,7 +152,22 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void group_sync(int m) { asm volatile("bar.sync %0, %1;" ::"r"(1 + m), "r"(128) : "memory"); }
+// group barrier that also ANDs a predicate over the 128 threads of the tile group
+__device__ __forceinline__ bool group_sync_and(int m, bool pred) {
+  uint32_t r;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %3, 0;\n\tbarrier.cta.red.and.pred q, %1, %2, p;\n\t"
+               "selp.u32 %0, 1, 0, q;\n\t}" : "=r"(r) : "r"(1 + m), "r"(128), "r"((uint32_t)pred) : "memory");
+  return r != 0;
+}
+// ACC: 0 = overwrite the accumulator, 1 = accumulate
+template <int ACC>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "n"(ACC) : "memory");
+}
+__device__ __forceinline__ void tc_mma_dyn(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
@@ -169,21 +183,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                : "r"(taddr));
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr));
-}
-template <int N> __device__ __forceinline__ void tc_ld(uint32_t taddr, float* v) {
-  if (N == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
-}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle canonical layout: 8-row x 16-byte core matrices; rows 16 B apart,
-// 8-row groups SBO apart, 16-byte K chunks LBO apart (cute::UMMA::SmemDescriptor, version 1)
+// 8-row groups SBO (=128 B) apart, 16-byte K chunks LBO apart (cute::UMMA::SmemDescriptor, version 1).
+// `lo` = (shared address >> 4) | ((LBO >> 4) << 16); the high word is the same for every operand here.
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)0x4008u << 32) | lo; }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
@@ -210,16 +215,32 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 
-// gate of ops.py:28,33,36: f = tanh(a); out = f * sigmoid(f).  f lies in [-1,1], where
-// sigmoid(f) = 0.5 + f*P(f^2) with a degree-3 minimax P (max error 1.1e-7 in fp32 evaluation),
-// so the gate costs one MUFU (tanh.approx, rel. error 2^-11) plus FMA-pipe work.
-__device__ __forceinline__ float gate(float a) {
-  const float f = tanh_fast(a);
-  const float s = f * f;
-  float pz = fmaf(s, -0.00016942188085522503f, 0.0020539257675409317f);
-  pz = fmaf(s, pz, -0.020825408399105072f);
-  pz = fmaf(s, pz, 0.24999941885471344f);
-  return fmaf(s, pz, 0.5f * f);
+// ---- packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of math) -------------
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) { f2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// gate of ops.py:28,33,36 on two channels: f = tanh(a); out = f * sigmoid(f).  f lies in [-1,1], where
+// sigmoid(f) = 0.5 + f*P(f^2) with a degree-2 minimax P (max error of the product 1.5e-6, far below the
+// 16-bit operand rounding), so the gate costs one MUFU (tanh.approx) per channel plus packed FMA-pipe work.
+template <bool FP16>
+__device__ __forceinline__ uint32_t gate2(f2_t a) {
+  float a0, a1;
+  upk(a, a0, a1);
+#if SRWN_EXP & 2
+  return pack2<FP16>(a0, a1);
+#endif
+  const f2_t f = pk(tanh_fast(a0), tanh_fast(a1));
+  const f2_t s = mul2(f, f);
+  f2_t t = fma2(s, pk(0.0017294071149080992f, 0.0017294071149080992f), pk(-0.020638039335608482f, -0.020638039335608482f));
+  t = fma2(s, t, pk(0.2499687224626541f, 0.2499687224626541f));
+  const f2_t c = fma2(f, pk(0.5f, 0.5f), mul2(s, t));
+  float c0, c1;
+  upk(c, c0, c1);
+  return pack2<FP16>(c0, c1);
 }
 
 // stores one row (32 values) as 4 x 16 B into a [kc][rows][8] operand buffer
@@ -233,33 +254,46 @@ __device__ __forceinline__ void store_row(uint8_t* buf, int rows_per_kc, int row
     *reinterpret_cast<uint4*>(buf + ((size_t)kc * rows_per_kc + row) * 16) = q;
   }
 }
+// same, from 16 already packed 16-bit pairs
+__device__ __forceinline__ void store_row_packed(uint8_t* buf, int rows_per_kc, int row, const uint32_t* w) {
+#pragma unroll
+  for (int kc = 0; kc < 4; kc++)
+    *reinterpret_cast<uint4*>(buf + ((size_t)kc * rows_per_kc + row) * 16) =
+        make_uint4(w[kc * 4 + 0], w[kc * 4 + 1], w[kc * 4 + 2], w[kc * 4 + 3]);
+}
 
+#ifndef SRWN_EXP
+#define SRWN_EXP 0      // tuning experiments (compile-time; non-zero values give wrong results, timing only)
+#endif
+#if !(SRWN_EXP & 16)      // production builds carry no trace code (it costs ~10 % even when disabled at run time)
+#define TRACE(role, layer, slot) do {} while (0)
+#else
 #define TRACE(role, layer, slot)                                                            \
   do {                                                                                      \
     if (tracing) p.trace[((role) * kMaxLayers + (layer)) * 12 + (slot)] = clock64();      \
   } while (0)
+#endif
 
-// stores NC consecutive channels (starting at channel c0, a multiple of 8) of one row
-template <bool FP16, int NC>
-__device__ __forceinline__ void store_cols(uint8_t* buf, int rows_per_kc, int row, int c0, const float* v) {
-#pragma unroll
-  for (int k = 0; k < NC / 8; k++) {
-    uint4 q;
-    q.x = pack2<FP16>(v[k * 8 + 0], v[k * 8 + 1]); q.y = pack2<FP16>(v[k * 8 + 2], v[k * 8 + 3]);
-    q.z = pack2<FP16>(v[k * 8 + 4], v[k * 8 + 5]); q.w = pack2<FP16>(v[k * 8 + 6], v[k * 8 + 7]);
-    *reinterpret_cast<uint4*>(buf + ((size_t)(c0 / 8 + k) * rows_per_kc + row) * 16) = q;
-  }
-}
+#if SRWN_EXP & 1
+#define LOOP_FENCE() do {} while (0)
+#else
+#define LOOP_FENCE() fence_async_smem()
+#endif
 
 // ---- the kernel --------------------------------------------------------------------------
-template <bool TEACHER, bool FP16, int SPLIT>
-__global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params p) {
-  constexpr int kThreads = (12 * SPLIT + 4) * 32;
-  constexpr int kMmaWarp = 12 * SPLIT, kLoadWarp = 12 * SPLIT + 3;   // warps kMmaWarp..+2 issue MMAs for tiles 0,1,2
+// 13 warps: warp 0 = loader + TMEM owner, warps 1..12 = three tile groups of four warps, one warp per
+// SMSP (row = TMEM lane = 32*(warp&3) + lane).  Warp w sits on SMSP q = w&3 at level j = (w-1)/4 and
+// belongs to tile (j+q+1)%3, so that tile m's MMA-issuing warp is the highest warp id of SMSP m (the
+// arbiter prefers high warp ids, and tcgen05 issue from a busy SMSP is what the layer chain waits on).
+constexpr int kThreads = 13 * 32;
+constexpr int kLoadWarp = 0;
+
+template <bool TEACHER, bool FP16>
+__global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
-  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 8);   // [0] flag [1] code [2..4] g1_issued
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 8);   // [0] flag [1] code
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SmemMap::misc);
   auto bar = [&](int i) { return sbase + SmemMap::bars + i * 8; };
   const int L = p.L;
@@ -270,20 +304,20 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
     for (int i = 0; i < 3; i++) {
-      mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_C + i), kTile * SPLIT); mbar_init(bar(BAR_D2 + i), 1);
-      mbar_init(bar(BAR_H + i), kTile * SPLIT); mbar_init(bar(BAR_HDA + i), kTile * SPLIT); mbar_init(bar(BAR_HDD + i), 1);
+      mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_D2 + i), 1); mbar_init(bar(BAR_HDD + i), 1);
+      mbar_init(bar(BAR_HD + 2 * i), kTile); mbar_init(bar(BAR_HD + 2 * i + 1), kTile);
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), kTiles);
       mbar_init(bar(BAR_HALO + i), 1); mbar_init(bar(BAR_G1 + i), kTiles);
     }
-    abort_flag[0] = 0; abort_flag[1] = 0; abort_flag[2] = 0; abort_flag[3] = 0; abort_flag[4] = 0;
+    abort_flag[0] = 0; abort_flag[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {  // resident constants: biases, front conv, head weights (plain loads; made visible below)
-    const uint8_t* pk = p.packed;
+    const uint8_t* pk_ = p.packed;
     const size_t off_fixed = (size_t)L * layer_bytes;     // [filter bias L*32 f32][front 96 f32 -> 64 used][head...]
-    const float* fbias = reinterpret_cast<const float*>(pk + off_fixed);
+    const float* fbias = reinterpret_cast<const float*>(pk_ + off_fixed);
     float* s_bias = reinterpret_cast<float*>(smem + SmemMap::bias);
     for (int i = tid; i < L * 32; i += kThreads) s_bias[i] = fbias[i];
     const float* ffront = fbias + kMaxLayers * 32;
@@ -299,7 +333,7 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
     }
   }
   fence_async_smem();
-  if (warp == kMmaWarp) {
+  if (warp == kLoadWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -315,6 +349,7 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
   int chunk_idx = 0;                                  // chunks processed so far (phase bookkeeping)
   int head_idx = 0;                                   // chunks with a head phase so far
   double nll_acc = 0.0;
+  const bool elected = elect_one();
 
   for (int si = 0; si < nseg; si++) {
     const Seg sg = segs[si];
@@ -345,150 +380,81 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
-          const int slot0 = t0 % d;                            // (t0 - d + i) mod d == (t0 + i) mod d
-          for (int kc = 0; kc < 4; kc++) {
-            for (int i = lane; i < d; i += 32) {
-              const uint32_t dst = dst0 + (uint32_t)(kc * kRows + kHalo - d + i) * 16;
-              if (t0 - d + i >= sg.t_start) {
-                int slot = slot0 + i; if (slot >= d) slot -= d;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rl + ((size_t)kc * d + slot) * 16) : "memory");
-              } else {
-                asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+          const int slot0 = (int)((unsigned)t0 % (unsigned)d);   // (t0 - d + i) mod d == (t0 + i) mod d
+          if (t0 - d >= sg.t_start) {
+            // every halo row exists: per 16-byte K chunk the ring is one or two contiguous pieces, moved by
+            // bulk copies that complete on the HALO barrier (no generic-proxy stores, no fence)
+            if (lane == 0) {
+              mbar_expect_tx(bar(BAR_HALO + s), (uint32_t)(4 * d * 16));
+              const uint32_t n1 = (uint32_t)(d - slot0) * 16, n2 = (uint32_t)slot0 * 16;
+#pragma unroll
+              for (int kc = 0; kc < 4; kc++) {
+                const uint32_t dst = dst0 + (uint32_t)(kc * kRows + kHalo - d) * 16;
+                const uint8_t* src = rl + (size_t)kc * d * 16;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(src + (size_t)slot0 * 16), "r"(n1), "r"(bar(BAR_HALO + s)) : "memory");
+                if (n2)
+                  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                               ::"r"(dst + n1), "l"(src), "r"(n2), "r"(bar(BAR_HALO + s)) : "memory");
               }
             }
-          }
-          asm volatile("cp.async.wait_all;" ::: "memory");
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_HALO + s));
-          TRACE(6, l, 3);
-        }
-      } else if (warp >= kMmaWarp) {
-        // ================= MMA issuers: warp 12+m drives tile m (one elected thread each) ==========
-        // Static per-tile sequence with blocking (hardware-suspended) waits: H -> filter-conv GEMM ->
-        // C -> residual/skip GEMM, per layer; then the two head GEMMs.  Tiles issue the filter conv of
-        // a layer in order (tile m's tap rows can live in tile m-1's rows), tracked by a shared counter.
-        // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform
-        // registers; only the tcgen05 instructions are predicated on one elected lane.
-        {
-          const int m = __shfl_sync(0xffffffffu, warp - kMmaWarp, 0);
-          const bool leader = elect_one();
-          constexpr uint32_t fmt = FP16 ? 0u : 1u;
-          constexpr uint32_t id32 = make_idesc(fmt, 128, 32), id128 = make_idesc(fmt, 128, 128);
-          volatile int* g1_issued = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 16);   // [3] running counts
-          bool ok = true;
-          const bool tracing = tracing_chunk && leader;
-          for (int l = 0; l < L && ok; l++) {
-            const int s = l & 1;
-            const uint32_t ph = (chunk_idx * L + l) & 1, phs = (u0[s] + (l >> 1)) & 1;
-            TRACE(3 + m, l, 0);
-            // descriptors are data independent: build them before blocking so that only the MMA
-            // issue itself sits on the critical path after a barrier flips
-            const uint32_t hb = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
-            const uint32_t wb = sbase + SmemMap::wst + s * SmemMap::wst_bytes;
-            const uint32_t ab = sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes;
-            const int d = p.dil[l];
-            uint64_t a1[4], b1[4], a2[2], b2r[2], b2s[2];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {     // K = 64: steps 0,1 = tap rows (W[0]), 2,3 = current rows (W[1])
-              const int row0 = kHalo + m * kTile - (j < 2 ? d : 0);
-              a1[j] = make_desc(hb + (uint32_t)((2 * (j & 1)) * kRows + row0) * 16, kRows * 16, 128);
-              b1[j] = make_desc(wb + (2 * j * 32) * 16, 32 * 16, 128);
-            }
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-              a2[j] = make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128);
-              b2r[j] = make_desc(wb + kWfBytes + (2 * j * wrs_rows) * 16, wrs_rows * 16, 128);
-              b2s[j] = make_desc(wb + kWfBytes + (2 * j * wrs_rows + 32) * 16, wrs_rows * 16, 128);
-            }
-            const uint32_t skip_acc0 = l > 0 ? 1u : 0u;
-            ok = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l) &&
-                 mbar_wait(bar(BAR_HALO + s), phs, abort_flag, 0x3100000 | (m << 8) | l) &&
-                 mbar_wait(bar(BAR_H + m), ph, abort_flag, 0x3200000 | (m << 8) | l);
-            if (!ok) break;
-            TRACE(3 + m, l, 1);
-            if (m > 0) {
-              const int want = chunk_idx * L + l + 1;
-              const long long ts = clock64();
-              while (g1_issued[m - 1] < want) {
-                if (*abort_flag) { ok = false; break; }
-                if (clock64() - ts > 1000000000LL) {
-                  if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = 0x3300000 | (m << 8) | l;
-                  ok = false; break;
+            __syncwarp();
+          } else {
+            // segment start: rows before it are the zero padding of ops.py:9
+            for (int kc = 0; kc < 4; kc++) {
+              for (int i = lane; i < d; i += 32) {
+                const uint32_t dst = dst0 + (uint32_t)(kc * kRows + kHalo - d + i) * 16;
+                if (t0 - d + i >= sg.t_start) {
+                  int slot = slot0 + i; if (slot >= d) slot -= d;
+                  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rl + ((size_t)kc * d + slot) * 16) : "memory");
+                } else {
+                  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
                 }
               }
-              if (!ok) break;
             }
-            tc_fence_after();
-            if (leader) {
-#pragma unroll
-              for (int j = 0; j < 4; j++) tc_mma(tmem + m * 32, a1[j], b1[j], id32, j);
-              tc_commit(bar(BAR_D1 + m));
-              tc_commit(bar(BAR_G1 + s));               // 3 arrivals (one per tile) complete the phase
-              g1_issued[m] = chunk_idx * L + l + 1;
-            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            fence_async_smem();
             __syncwarp();
-            TRACE(3 + m, l, 2);
-            if (!mbar_wait(bar(BAR_C + m), ph, abort_flag, 0x3400000 | (m << 8) | l)) { ok = false; break; }
-            TRACE(3 + m, l, 3);
-            tc_fence_after();
-            if (leader) {
-#pragma unroll
-              for (int j = 0; j < 2; j++) {
-                tc_mma(tmem + m * 32, a2[j], b2r[j], id32, j);
-                if (TEACHER && !warm) tc_mma(tmem + 128 + m * 128, a2[j], b2s[j], id128, j > 0 ? 1u : skip_acc0);
-              }
-              tc_commit(bar(BAR_D2 + m));
-              tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
-            }
-            __syncwarp();
-            TRACE(3 + m, l, 4);
+            if (lane == 0) mbar_arrive(bar(BAR_HALO + s));
           }
-          if (do_head && ok) {
-            // ---- output head (teacher): relu(skip) @ H1, then relu(.) @ H2 ----
-#pragma unroll
-            for (int hs = 0; hs < 2 && ok; hs++) {
-              if (!mbar_wait(bar(BAR_HDA + m), (head_idx * 2 + hs) & 1, abort_flag, 0x3500000 | (m << 8) | hs)) { ok = false; break; }
-              tc_fence_after();
-              if (leader) {
-                const uint32_t ab = sbase + SmemMap::hbuf + m * (16 * kTile * 16);
-                const uint32_t wb = sbase + SmemMap::head + (hs == 0 ? 0 : kH1Bytes);
-                const int nrows = hs == 0 ? 128 : 32;
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                  tc_mma(hs == 0 ? tmem + 128 + m * 128 : tmem + m * 32,
-                         make_desc(ab + (2 * j * kTile) * 16, kTile * 16, 128),
-                         make_desc(wb + (2 * j * nrows) * 16, nrows * 16, 128), hs == 0 ? id128 : id32, j);
-                tc_commit(bar(BAR_HDD + m));
-              }
-              __syncwarp();
-            }
-          }
+          TRACE(6, l, 3);
         }
-        __syncwarp();
       } else {
-        // ================= epilogue warps: tile m, row = TMEM lane, column slice `half` ===========
-        // SPLIT warpgroups share a tile; each thread owns NC = 32/SPLIT residual channels of its row.
-        constexpr int NC = 32 / SPLIT;
-        const int m = warp / (4 * SPLIT);
-        const int half = (warp / 4) % SPLIT;
-        const int c0 = half * NC;                       // first channel owned by this thread
-        const int row = (warp & 3) * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        // ================= tile group m: MMA issue + epilogues; row = TMEM lane ====================
+        // Per layer: [rows of the layer input stored] -> group barrier -> filter-conv GEMM (4 MMAs) ->
+        // gate epilogue -> group barrier -> residual GEMM (2 MMAs, committed first) + skip GEMM (2 MMAs,
+        // accumulating in TMEM, off the critical path) -> residual epilogue -> next layer's rows.
+        // All control flow is uniform across the group (an aborted wait keeps walking the barriers).
+        const int gw = warp & 3, m = (((warp - 1) >> 2) + gw + 1) % 3;
+        // MMA issue is spread over SMSPs: tile m's issuer is its warp on SMSP m (tcgen05 instructions
+        // serialise within an SMSP)
+        const bool issuer = gw == m;
+        const bool leader = issuer && elected;
+        const int row = gw * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(gw * 32) << 16;
         const int t = t0 + m * kTile + row;
         const bool in_utt = t < p.T;
         int frame = (t0 + m * kTile) / p.P;
         if (frame > p.frames - 1) frame = p.frames - 1;
         const float* cb_g = p.cb + ((size_t)sg.b * p.frames + frame) * (size_t)(L + 1) * 32;
         float* cb = reinterpret_cast<float*>(smem + SmemMap::cbs) + m * (kMaxLayers + 1) * 32;
-        for (int i = half * kTile + row; i < (L + 1) * 32; i += kTile * SPLIT) cb[i] = __ldg(cb_g + i);   // one latent frame per tile
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + m), "r"(kTile * SPLIT) : "memory");
+        for (int i = row; i < (L + 1) * 32; i += kTile) cb[i] = __ldg(cb_g + i);   // one latent frame per tile
+        group_sync(m);
         const float* s_bias = reinterpret_cast<const float*>(smem + SmemMap::bias);
         const float* s_front = reinterpret_cast<const float*>(smem + SmemMap::front);
         const int rc = m * kTile + row;                 // row inside the chunk
-        float h[NC], v[32];
+        f2_t h2[16];                                    // fp32 residual stream of this row, packed pairs
+        float v[32];
+        uint32_t w16[16];
         bool alive = true;
-        const bool tracing = tracing_chunk && row == 0 && half == 0;
+        const bool tracing = tracing_chunk && row == 0;
+        constexpr uint32_t fmt = FP16 ? 0u : 1u;
+        constexpr uint32_t id32 = make_idesc(fmt, 128, 32), id128 = make_idesc(fmt, 128, 128), id160 = make_idesc(fmt, 128, 160); (void)id160;
+        // descriptor low words that do not depend on the layer
+        const uint32_t hb_lo0 = ((sbase + SmemMap::hbuf) >> 4) + (uint32_t)(kHalo + m * kTile) + ((uint32_t)kRows << 16);
+        const uint32_t wb_lo0 = (sbase + SmemMap::wst) >> 4;
+        const uint32_t ab_lo = ((sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes) >> 4) + ((uint32_t)kTile << 16);
+        const uint32_t d_conv = tmem + m * 160, d_skip = tmem + m * 160 + 32;
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
         {
@@ -496,68 +462,154 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
           const float xm1 = (t >= 1 && t - 1 < p.T) ? __ldg(xb + t - 1) : 0.f;
           const float xm2 = (t >= 2 && t - 2 < p.T) ? __ldg(xb + t - 2) : 0.f;
 #pragma unroll
-          for (int j = 0; j < NC; j++)
-            h[j] = fmaf(xm2, s_front[c0 + j], fmaf(xm1, s_front[32 + c0 + j], cb[c0 + j]));
+          for (int j = 0; j < 16; j++) {
+            const float a = fmaf(xm2, s_front[2 * j], fmaf(xm1, s_front[32 + 2 * j], cb[2 * j]));
+            const float b = fmaf(xm2, s_front[2 * j + 1], fmaf(xm1, s_front[32 + 2 * j + 1], cb[2 * j + 1]));
+            h2[j] = pk(a, b);
+            w16[j] = pack2<FP16>(a, b);
+          }
           alive = mbar_wait(bar(BAR_HALO + 0), u0[0] & 1, abort_flag, 0x2000000 | (m << 8));      // ring 0 was read for this chunk
-          store_cols<FP16, NC>(smem + SmemMap::hbuf, kRows, kHalo + rc, c0, h);
+          store_row_packed(smem + SmemMap::hbuf, kRows, kHalo + rc, w16);
           const int d0 = p.dil[0];
-          if (rc >= kChunk - d0) store_cols<FP16, NC>(ring + p.ring_off[0], d0, t % d0, c0, h);
+          if (rc >= kChunk - d0) store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);
           fence_async_smem();
-          mbar_arrive(bar(BAR_H + m));
+          mbar_arrive(bar(BAR_HD + 2 * m + 0));
         }
 
-        for (int l = 0; l < L && alive; l++) {
-          const uint32_t ph = (chunk_idx * L + l) & 1;
+        for (int l = 0; l < L; l++) {
+          const int s = l & 1, sn = s ^ 1;
+          const uint32_t ph = (chunk_idx * L + l) & 1, phs = (u0[s] + (l >> 1)) & 1;
           TRACE(m, l, 0);
-          // ---- gate: tanh, sigmoid of the tanh, product (ops.py:28,33,36) ----
-          if (!mbar_wait(bar(BAR_D1 + m), ph, abort_flag, 0x2100000 | (m << 8) | l)) { alive = false; break; }
+          // ---- filter-conv GEMM: K = 64, steps 0,1 = tap rows (W[0], d rows earlier), 2,3 = current rows (W[1])
+          const uint32_t hb_lo = hb_lo0 + (uint32_t)(s * (SmemMap::hbuf_bytes >> 4));
+          const uint32_t wb_lo = wb_lo0 + (uint32_t)(s * (SmemMap::wst_bytes >> 4));
+          const uint32_t dl = (uint32_t)p.dil[l];
+          const uint32_t b1_lo = wb_lo + (32u << 16);
+          const uint32_t b2_lo = wb_lo + (kWfBytes >> 4) + ((uint32_t)wrs_rows << 16);
+          // the conditions the GEMM depends on are checked by different warps in parallel; the group
+          // barrier then publishes them (and this tile's operand rows) to the issuing lane
+          if (gw == ((m + 3) & 3)) alive = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l) && alive;
+          if (gw == ((m + 1) & 3) && m >= 1) alive = mbar_wait(bar(BAR_HD + 2 * (m - 1) + s), phs, abort_flag, 0x3100000 | (m << 8) | l) && alive;
+          if (gw == ((m + 2) & 3) && m >= 2) alive = mbar_wait(bar(BAR_HD + 2 * (m - 2) + s), phs, abort_flag, 0x3200000 | (m << 8) | l) && alive;
+          group_sync(m);
           TRACE(m, l, 1);
-          tc_fence_after();
-          tc_ld<NC>(tmem + lane_addr + m * 32 + c0, v);
-          tc_wait_ld();
+          if (issuer) {
+            tc_fence_after();
+            if (leader) {
+              tc_mma<0>(d_conv, desc_from_lo(hb_lo - dl), desc_from_lo(b1_lo), id32);
+              tc_mma<1>(d_conv, desc_from_lo(hb_lo - dl + 2 * kRows), desc_from_lo(b1_lo + 64), id32);
+              tc_mma<1>(d_conv, desc_from_lo(hb_lo), desc_from_lo(b1_lo + 128), id32);
+              tc_mma<1>(d_conv, desc_from_lo(hb_lo + 2 * kRows), desc_from_lo(b1_lo + 192), id32);
+              tc_commit(bar(BAR_D1 + m));
+              tc_commit(bar(BAR_G1 + s));               // 3 arrivals (one per tile) complete the phase
+            }
+            __syncwarp();
+          }
           TRACE(m, l, 2);
-#pragma unroll
-          for (int j = 0; j < NC; j++) v[j] = gate(v[j] + s_bias[l * 32 + c0 + j]);
-          store_cols<FP16, NC>(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, c0, v);
-          TRACE(m, l, 3);
-          tc_fence_before();
-          fence_async_smem();
-          TRACE(m, l, 4);
-          mbar_arrive(bar(BAR_C + m));
-          TRACE(m, l, 5);
-          // poll (non-blocking) the two conditions the next operand store depends on while the
-          // residual GEMM runs; they are almost always already satisfied
-          uint32_t g1_ok = 1, halo_ok = 1;
-          if (l + 1 < L) {
-            const int sn = (l + 1) & 1;
-            if (l >= 1) g1_ok = mbar_poll(bar(BAR_G1 + sn), (u0[sn] + ((l - 1) >> 1)) & 1);
-            halo_ok = mbar_poll(bar(BAR_HALO + sn), (u0[sn] + ((l + 1) >> 1)) & 1);
+          // while the GEMM runs: poll the two conditions the next operand store depends on
+          //  - activation buffer sn is free once the filter-conv MMAs of layer l-1 retired (all tiles),
+          //  - ring l+1 may be overwritten once this chunk's halo of layer l+1 was read
+          bool next_ok = true;
+          if (l + 1 < L && !issuer) {
+            if (l >= 1) next_ok = mbar_poll(bar(BAR_G1 + sn), (u0[sn] + ((l - 1) >> 1)) & 1);
+            next_ok = mbar_poll(bar(BAR_HALO + sn), (u0[sn] + ((l + 1) >> 1)) & 1) && next_ok;
           }
 
-          // ---- residual: dense = (inputs + residual) * sqrt(1/2) (ops.py:39-40), next conditioning ----
-          if (!mbar_wait(bar(BAR_D2 + m), ph, abort_flag, 0x2200000 | (m << 8) | l)) { alive = false; break; }
-          TRACE(m, l, 6);
+          // ---- gate: tanh, sigmoid of the tanh, product (ops.py:28,33,36) ----
+          alive = mbar_wait(bar(BAR_D1 + m), ph, abort_flag, 0x2100000 | (m << 8) | l) && alive;
+          TRACE(m, l, 3);
           tc_fence_after();
-          tc_ld<NC>(tmem + lane_addr + m * 32 + c0, v);
+          tc_ld32(d_conv + lane_addr, v);
           tc_wait_ld();
-          TRACE(m, l, 7);
+          TRACE(m, l, 4);
+          {
+            const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(s_bias + l * 32);
+            const f2_t neg1 = pk(-1.f, -1.f); (void)neg1;
 #pragma unroll
-          for (int j = 0; j < NC; j++) h[j] = fmaf(h[j] + v[j], SRWN_SQRT_HALF, cb[(l + 1) * 32 + c0 + j]);
+            for (int q = 0; q < 8; q++) {
+              const ulonglong2 bb = b2[q];
+              const f2_t d0 = pk(v[4 * q], v[4 * q + 1]), d1 = pk(v[4 * q + 2], v[4 * q + 3]);
+              w16[2 * q] = gate2<FP16>(add2(d0, bb.x));
+              w16[2 * q + 1] = gate2<FP16>(add2(d1, bb.y));
+#if SRWN_EXP & 32
+              // merged variant: the residual GEMM accumulates on top of the filter-conv accumulator (one N=160
+              // MMA then serves residual and skip): keep h - conv so that h + residual = (h - conv) + accumulator
+              h2[2 * q] = fma2(d0, neg1, h2[2 * q]);
+              h2[2 * q + 1] = fma2(d1, neg1, h2[2 * q + 1]);
+#endif
+            }
+          }
+          store_row_packed(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, w16);
+          tc_fence_before();
+          LOOP_FENCE();
+          TRACE(m, l, 5);
+          next_ok = group_sync_and(m, next_ok);         // true: every polling warp saw both conditions
+          TRACE(m, l, 6);
+          if (issuer) {
+            tc_fence_after();
+            if (leader) {
+#if SRWN_EXP & 32
+              if (TEACHER && !warm && l > 0 && !(SRWN_EXP & 8)) {
+                // residual (32 columns, on top of the conv accumulator) + skip sum (128 columns) in one N=160 MMA
+                tc_mma<1>(d_conv, desc_from_lo(ab_lo), desc_from_lo(b2_lo), id160);
+                tc_mma<1>(d_conv, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows), id160);
+              } else {
+                tc_mma<1>(d_conv, desc_from_lo(ab_lo), desc_from_lo(b2_lo), id32);
+                tc_mma<1>(d_conv, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows), id32);
+                if (TEACHER && !warm && !(SRWN_EXP & 8)) {           // first layer: the skip accumulator starts fresh
+                  tc_mma<0>(d_skip, desc_from_lo(ab_lo), desc_from_lo(b2_lo + 32), id128);
+                  tc_mma<1>(d_skip, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
+                }
+              }
+              tc_commit(bar(BAR_D2 + m));
+#else
+              // residual first (it is what the layer chain waits for); the skip sum accumulates in TMEM behind it
+              tc_mma<0>(d_conv, desc_from_lo(ab_lo), desc_from_lo(b2_lo), id32);
+              tc_mma<1>(d_conv, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows), id32);
+              tc_commit(bar(BAR_D2 + m));
+              if (TEACHER && !warm && !(SRWN_EXP & 8)) {
+                tc_mma_dyn(d_skip, desc_from_lo(ab_lo), desc_from_lo(b2_lo + 32), id128, l > 0 ? 1u : 0u);
+                tc_mma<1>(d_skip, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
+              }
+#endif
+              tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
+            }
+            __syncwarp();
+          }
+          TRACE(m, l, 7);
+
+          // ---- residual: dense = (inputs + residual) * sqrt(1/2) (ops.py:39-40), next conditioning ----
+          alive = mbar_wait(bar(BAR_D2 + m), ph, abort_flag, 0x2200000 | (m << 8) | l) && alive;
           TRACE(m, l, 8);
+          tc_fence_after();
+          tc_ld32(d_conv + lane_addr, v);
+          tc_wait_ld();
+          {
+            const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(cb + (l + 1) * 32);
+            const f2_t sq = pk(SRWN_SQRT_HALF, SRWN_SQRT_HALF);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const ulonglong2 cc = c2[q];
+              h2[2 * q] = fma2(add2(h2[2 * q], pk(v[4 * q], v[4 * q + 1])), sq, cc.x);
+              h2[2 * q + 1] = fma2(add2(h2[2 * q + 1], pk(v[4 * q + 2], v[4 * q + 3])), sq, cc.y);
+            }
+          }
+          TRACE(m, l, 9);
           if (l + 1 < L) {
-            const int s = (l + 1) & 1;
-            // activation buffer s is free once the filter-conv MMAs of layer l-1 retired, and
-            // ring l+1 may be overwritten once this chunk's halo of layer l+1 was read
-            if (!g1_ok && !mbar_wait(bar(BAR_G1 + s), (u0[s] + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l)) { alive = false; break; }
-            if (!halo_ok && !mbar_wait(bar(BAR_HALO + s), (u0[s] + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l)) { alive = false; break; }
-            TRACE(m, l, 9);
-            store_cols<FP16, NC>(smem + SmemMap::hbuf + s * SmemMap::hbuf_bytes, kRows, kHalo + rc, c0, h);
-            const int dn = p.dil[l + 1];
-            if (rc >= kChunk - dn) store_cols<FP16, NC>(ring + p.ring_off[l + 1], dn, t % dn, c0, h);
+#pragma unroll
+            for (int j = 0; j < 16; j++) { float a, b; upk(h2[j], a, b); w16[j] = pack2<FP16>(a, b); }
+            if (!next_ok) {                             // rare: the polls were too early
+              if (l >= 1) alive = mbar_wait(bar(BAR_G1 + sn), (u0[sn] + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l) && alive;
+              alive = mbar_wait(bar(BAR_HALO + sn), (u0[sn] + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l) && alive;
+            }
             TRACE(m, l, 10);
+            store_row_packed(smem + SmemMap::hbuf + sn * SmemMap::hbuf_bytes, kRows, kHalo + rc, w16);
             tc_fence_before();
-            fence_async_smem();
-            mbar_arrive(bar(BAR_H + m));
+            LOOP_FENCE();
+            mbar_arrive(bar(BAR_HD + 2 * m + sn));
+            // history for the next chunk (read by the loader after the chunk-end barrier)
+            const int dn = p.dil[l + 1];
+            if (!(SRWN_EXP & 4) && rc >= kChunk - dn) store_row_packed(ring + p.ring_off[l + 1], dn, t % dn, w16);
             TRACE(m, l, 11);
           } else {
             tc_fence_before();
@@ -565,45 +617,49 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
         }
 
         if (TEACHER) {
-          if (do_head && alive) {
+          if (do_head) {
             const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
             uint8_t* a3 = smem + SmemMap::hbuf + m * (16 * kTile * 16);
-            constexpr int QN = 4 / SPLIT;               // 32-column groups of the 128 skip channels per thread
+            const uint32_t a3_lo = ((sbase + SmemMap::hbuf + m * (16 * kTile * 16)) >> 4) + ((uint32_t)kTile << 16);
             // all filter-conv MMAs of the last layer retired -> both activation buffers are free
-            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8));
-            // relu(sum of skips + summed skip biases) -> operand of the S->S conv (model.py:190-193)
-            for (int qq = 0; qq < QN && alive; qq++) {
-              const int q = half * QN + qq;
-              tc_ld<32>(tmem + lane_addr + 128 + m * 128 + q * 32, v);
-              tc_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + s_hb[q * 32 + j], 0.f);
-              store_cols<FP16, 32>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, 0, v);
-            }
-            tc_fence_before();
-            fence_async_smem();
-            mbar_arrive(bar(BAR_HDA + m));
-            alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2) & 1, abort_flag, 0x2600000 | (m << 8));
+            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8)) && alive;
+            // the skip accumulator is complete once this tile's last skip MMA retired (WEMPTY commit of the last layer)
+            alive = mbar_wait(bar(BAR_WEMPTY + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag, 0x2510000 | (m << 8)) && alive;
             tc_fence_after();
-            for (int qq = 0; qq < QN && alive; qq++) {        // relu(. + b1) -> operand of the S->4M conv (model.py:194-196)
-              const int q = half * QN + qq;
-              tc_ld<32>(tmem + lane_addr + 128 + m * 128 + q * 32, v);
-              tc_wait_ld();
+#pragma unroll 1
+            for (int hs = 0; hs < 2; hs++) {
+              // hs = 0: relu(sum of skips + summed skip biases) -> operand of the S->S conv (model.py:190-193)
+              // hs = 1: relu(. + b1) -> operand of the S->4M conv (model.py:194-196)
+              for (int q = 0; q < 4; q++) {
+                tc_ld32(d_skip + lane_addr + q * 32, v);
+                tc_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + s_hb[128 + q * 32 + j], 0.f);
-              store_cols<FP16, 32>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, 0, v);
+                for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + s_hb[hs * 128 + q * 32 + j], 0.f);
+                store_row<FP16>(a3 + (size_t)q * 4 * kTile * 16, kTile, row, v);
+              }
+              tc_fence_before();
+              fence_async_smem();
+              group_sync(m);
+              if (issuer) {
+                tc_fence_after();
+                if (leader && !*abort_flag) {
+                  const uint32_t wlo = ((sbase + SmemMap::head + (hs == 0 ? 0 : kH1Bytes)) >> 4) + ((uint32_t)(hs == 0 ? 128 : 32) << 16);
+                  const int nrows = hs == 0 ? 128 : 32;
+#pragma unroll
+                  for (int j = 0; j < 8; j++)
+                    tc_mma_dyn(hs == 0 ? d_skip : d_conv, desc_from_lo(a3_lo + 2 * j * kTile), desc_from_lo(wlo + 2 * j * nrows),
+                               hs == 0 ? id128 : id32, j);
+                  tc_commit(bar(BAR_HDD + m));
+                }
+                __syncwarp();
+              }
+              alive = mbar_wait(bar(BAR_HDD + m), (head_idx * 2 + hs) & 1, abort_flag, 0x2600000 | (m << 8) | hs) && alive;
+              tc_fence_after();
             }
+            tc_ld32(d_conv + lane_addr, v);
+            tc_wait_ld();
             tc_fence_before();
-            fence_async_smem();
-            mbar_arrive(bar(BAR_HDA + m));
-            alive = alive && mbar_wait(bar(BAR_HDD + m), (head_idx * 2 + 1) & 1, abort_flag, 0x2700000 | (m << 8));
-            tc_fence_after();
-            if (half == 0) {                             // one thread per row finishes the logits / likelihood
-              tc_ld<32>(tmem + lane_addr + m * 32, v);
-              tc_wait_ld();
-            }
-            tc_fence_before();
-            if (half == 0 && alive && in_utt && t >= sg.t_out) {
+            if (alive && in_utt && t >= sg.t_out) {
 #pragma unroll
               for (int j = 0; j < 32; j++) v[j] += s_hb[256 + j];
               const size_t at = (size_t)sg.b * p.T + t;
@@ -635,26 +691,21 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
               }
             }
           }
-        } else if (alive) {
+        } else {
           // student flow head: relu -> 1x1 R->2; scale = exp(p0), mean = p1; out = x*scale + mean
-          // (model.py:451-452, 479-482); column slices combine through shared memory
+          // (model.py:451-452, 479-482)
           const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
           const float* hk = s_hb + 288;
           float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < NC; j++) {
-            const float e = fmaxf(h[j], 0.f);
-            p0 = fmaf(e, hk[2 * (c0 + j)], p0);
-            p1 = fmaf(e, hk[2 * (c0 + j) + 1], p1);
+          for (int j = 0; j < 16; j++) {
+            float a, b;
+            upk(h2[j], a, b);
+            const float e0 = fmaxf(a, 0.f), e1 = fmaxf(b, 0.f);
+            p0 = fmaf(e0, hk[4 * j], p0); p1 = fmaf(e0, hk[4 * j + 1], p1);
+            p0 = fmaf(e1, hk[4 * j + 2], p0); p1 = fmaf(e1, hk[4 * j + 3], p1);
           }
-          if (SPLIT > 1) {
-            float2* xch = reinterpret_cast<float2*>(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes);   // gate operand buffer is idle now
-            if (half != 0) xch[(half - 1) * kTile + row] = make_float2(p0, p1);
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + m), "r"(kTile * SPLIT) : "memory");
-            if (half == 0)
-              for (int hh = 1; hh < SPLIT; hh++) { const float2 o = xch[(hh - 1) * kTile + row]; p0 += o.x; p1 += o.y; }
-          }
-          if (half == 0 && in_utt && t >= sg.t_out) {
+          if (alive && in_utt && t >= sg.t_out) {
             const size_t at = (size_t)sg.b * p.T + t;
             const float sc = expf(p0 + hk[64]);
             const float mu = p1 + hk[65];
@@ -666,6 +717,7 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
       }
       if (do_head) head_idx++;
       tc_fence_before();
+      asm volatile("fence.proxy.async;" ::: "memory");   // ring rows (generic stores) -> next chunk's bulk loads
       __syncthreads();          // chunk boundary: every role is quiescent, buffers and rings are consistent
       tc_fence_after();
       if (*abort_flag) break;
@@ -681,7 +733,7 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
     __syncthreads();
     if (tid == 0) {
       double tot = 0;
-      for (int w = 0; w < 12 * SPLIT; w++) tot += s_red[w];   // epilogue warps only
+      for (int w = 1; w <= 12; w++) tot += s_red[w];   // tile-group warps only
       p.nll_partial[blockIdx.x] = tot;
     }
   }
@@ -690,7 +742,7 @@ __global__ void __launch_bounds__((12 * SPLIT + 4) * 32, 1) k_fused(const Params
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kLoadWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
@@ -890,13 +942,9 @@ size_t fused_workspace_bytes(const srwn_ctx* c, int op, int B, int T) {
 
 template <bool TEACHER>
 static int launch_fused(srwn_ctx* c, const Params& p, int grid, int fp16, cudaStream_t st) {
-  // SPLIT=2 (two epilogue warpgroups per tile, 896 threads, 72 regs) measured slower than SPLIT=1
-  // (3.99 vs 3.41 ms at 32x64000): the limiter is the SMEM-fed tensor pipe + hand-off chain, not epilogue math
-  static const int split = getenv("SRWN_SPLIT") ? atoi(getenv("SRWN_SPLIT")) : 1;
-  auto kern = split == 2 ? (fp16 ? k_fused<TEACHER, true, 2> : k_fused<TEACHER, false, 2>)
-                         : (fp16 ? k_fused<TEACHER, true, 1> : k_fused<TEACHER, false, 1>);
+  auto kern = fp16 ? k_fused<TEACHER, true> : k_fused<TEACHER, false>;
   SRWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemMap::total));
-  kern<<<grid, (12 * split + 4) * 32, SmemMap::total, st>>>(p);
+  kern<<<grid, kThreads, SmemMap::total, st>>>(p);
   SRWN_LAUNCH_CHECK();
   return SRWN_OK;
 }
@@ -922,6 +970,7 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   p->packed = (const uint8_t*)c->d_packed + ((size_t)(fp16 ? 1 : 0) * c->n_stacks + stack) * img;
   p->trace = getenv("SRWN_TRACE") ? w.trace : nullptr;
   p->trace_chunk = getenv("SRWN_TRACE") ? atoi(getenv("SRWN_TRACE")) : 0;
+  p->dbg = getenv("SRWN_DBG") ? atoi(getenv("SRWN_DBG")) : 0;
   p->cb = w.cb; p->rings = w.rings; p->segs = w.segs; p->nseg = w.nseg; p->err = w.err;
   p->T = T; p->L = L; p->P = P; p->frames = frames;
   p->O = 4 * c->cfg.num_mixtures; p->M = c->cfg.num_mixtures;
@@ -1005,15 +1054,32 @@ extern "C" int srwn_debug_read_trace(srwn_handle_t h, int32_t B, int32_t T, void
 }
 
 // ---- tuning aid: cost of back-to-back tcgen05.mma dispatches (one CTA, garbage operands) ------------
+// Test c: warps listed in `mask` each issue CNT MMAs of width N (descriptors precomputed, fully unrolled)
+// into their own TMEM columns and commit; out[c] = {max issue clocks, max issue+complete clocks}.
 namespace fused {
-__global__ void __launch_bounds__(128, 1) k_mma_bench(long long* out) {
+template <int N, int CNT>
+__device__ __forceinline__ void bench_issue(uint32_t tmem_col, uint32_t a_lo, uint32_t b_lo, uint32_t mbar_addr) {
+  constexpr uint32_t idesc = make_idesc(0, 128, N);
+#pragma unroll
+  for (int i = 0; i < CNT; i++) {
+    if (i == 0) tc_mma<0>(tmem_col, desc_from_lo(a_lo), desc_from_lo(b_lo), idesc);
+    else tc_mma<1>(tmem_col, desc_from_lo(a_lo + (i & 3) * 256), desc_from_lo(b_lo + (i & 3) * 64), idesc);
+  }
+  tc_commit(mbar_addr);
+}
+
+__global__ void __launch_bounds__(416, 1) k_mma_bench(long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar[16];
+  __shared__ long long s_t[16][2];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 ones
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&mbar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  for (int i = threadIdx.x; i < 65536 / 4; i += 416) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 ones
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; i++) mbar_init(smem_u32(&mbar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   fence_async_smem();
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
@@ -1023,34 +1089,40 @@ __global__ void __launch_bounds__(128, 1) k_mma_bench(long long* out) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const bool leader = elect_one();
+  const uint32_t a_lo = (sbase >> 4) + (128u << 16), b_lo = ((sbase + 32768) >> 4) + (32u << 16);
   uint32_t phase = 0;
-  if (warp == 0) {
-    const bool leader = elect_one();
-    // configs: {N, number of MMAs, same accumulator?}
-    const int cfgN[8] = {32, 32, 32, 128, 160, 256, 32, 160};
-    const int cfgCnt[8] = {1, 4, 16, 4, 4, 4, 16, 16};
-    const int cfgIndep[8] = {0, 0, 0, 0, 0, 0, 1, 0};
-    for (int c = 0; c < 8; c++) {
-      for (int rep = 0; rep < 3; rep++) {
-        const int N = cfgN[c];
-        const uint32_t idesc = make_idesc(0, 128, N);
-        __syncwarp();
-        const long long t0 = clock64();
+  // tests: {warp mask, shape}: shape 0 = 4 x N32, 1 = 16 x N32, 2 = 2 x N160, 3 = 8 x N128
+  const unsigned masks[12] = {0x1, 0x1, 0x1, 0x1, 0x7, 0x7, 0x111, 0x111, 0x7, 0x111, 0x1111, 0xF};
+  const int shapes[12] = {0, 1, 2, 3, 0, 1, 0, 1, 2, 2, 1, 1};
+  for (int c = 0; c < 12; c++) {
+    for (int rep = 0; rep < 3; rep++) {
+      __syncthreads();
+      const bool mine = (masks[c] >> warp) & 1;
+      long long t0 = clock64(), t1 = t0, t2 = t0;
+      if (mine) {
+        const uint32_t col = tmem + (warp % 3) * 160;
+        const uint32_t mb = smem_u32(&mbar[warp]);
         if (leader) {
-          for (int i = 0; i < cfgCnt[c]; i++) {
-            const uint64_t ad = make_desc(sbase + (i & 3) * 4096, 2048, 128);
-            const uint64_t bd = make_desc(sbase + 32768 + (i & 3) * 512, 16 * N, 128);
-            tc_mma(tmem + (cfgIndep[c] ? (i & 7) * 32 : 0), ad, bd, idesc, i > 0 ? 1u : 0u);
-          }
-          tc_commit(smem_u32(&mbar));
+          if (shapes[c] == 0) bench_issue<32, 4>(col, a_lo, b_lo, mb);
+          else if (shapes[c] == 1) bench_issue<32, 16>(col, a_lo, b_lo, mb);
+          else if (shapes[c] == 2) bench_issue<160, 2>(col, a_lo, b_lo, mb);
+          else bench_issue<128, 8>(col, a_lo, b_lo, mb);
         }
         __syncwarp();
-        const long long t1 = clock64();
-        while (!mbar_test(smem_u32(&mbar), phase)) {}
-        phase ^= 1;
-        const long long t2 = clock64();
-        if (leader && rep == 2) { out[c * 2] = t1 - t0; out[c * 2 + 1] = t2 - t0; }
+        t1 = clock64();
+        while (!mbar_test(mb, phase)) {}
+        t2 = clock64();
       }
+      if (mine && leader) { s_t[warp][0] = t1 - t0; s_t[warp][1] = t2 - t0; }
+      __syncthreads();
+      if (threadIdx.x == 0 && rep == 2) {
+        long long a = 0, b = 0;
+        for (int w = 0; w < 13; w++) if ((masks[c] >> w) & 1) { a = max(a, s_t[w][0]); b = max(b, s_t[w][1]); }
+        out[c * 2] = a; out[c * 2 + 1] = b;
+      }
+      if (mine) phase ^= 1;   // this warp's barrier completed one phase
+      __syncthreads();
     }
   }
   tc_fence_before();
@@ -1062,13 +1134,13 @@ __global__ void __launch_bounds__(128, 1) k_mma_bench(long long* out) {
 }
 }  // namespace fused
 
-extern "C" int srwn_debug_mma_bench(long long* host_out16) {
+extern "C" int srwn_debug_mma_bench(long long* host_out24) {
   long long* d = nullptr;
-  SRWN_CUDA(cudaMalloc(&d, 16 * sizeof(long long)));
+  SRWN_CUDA(cudaMalloc(&d, 24 * sizeof(long long)));
   SRWN_CUDA(cudaFuncSetAttribute(fused::k_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  fused::k_mma_bench<<<1, 128, 65536>>>(d);
+  fused::k_mma_bench<<<1, 416, 65536>>>(d);
   SRWN_CUDA(cudaDeviceSynchronize());
-  SRWN_CUDA(cudaMemcpy(host_out16, d, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  SRWN_CUDA(cudaMemcpy(host_out24, d, 24 * sizeof(long long), cudaMemcpyDeviceToHost));
   cudaFree(d);
   return SRWN_OK;
 }

@@ -4,8 +4,11 @@ import torch
 from sr_wavenet_b200 import _lib
 torch.zeros(1).cuda()
 lib = _lib.load()
-out = (ctypes.c_longlong * 16)()
+out = (ctypes.c_longlong * 24)()
 _lib.check(lib.srwn_debug_mma_bench(out))
-names = ["1 x N32", "4 x N32 (same acc)", "16 x N32 (same acc)", "4 x N128", "4 x N160", "4 x N256", "16 x N32 (8 accs)", "16 x N160"]
+names = ["1 warp : 4 x N32", "1 warp : 16 x N32", "1 warp : 2 x N160", "1 warp : 8 x N128",
+         "warps 0,1,2 : 4 x N32 each", "warps 0,1,2 : 16 x N32 each", "warps 0,4,8 : 4 x N32 each",
+         "warps 0,4,8 : 16 x N32 each", "warps 0,1,2 : 2 x N160 each", "warps 0,4,8 : 2 x N160 each",
+         "warps 0,4,8,12 : 16 x N32 each", "warps 0,1,2,3 : 16 x N32 each"]
 for i, n in enumerate(names):
-    print("%-22s issue %5d clk   issue+complete %5d clk" % (n, out[2 * i], out[2 * i + 1]))
+    print("%-32s issue %5d clk   issue+complete %5d clk" % (n, out[2 * i], out[2 * i + 1]))

@@ -21,16 +21,13 @@ lib.srwn_debug_read_trace.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_
 _lib.check(lib.srwn_debug_read_trace(eng.h, B, T, ws, wsn, out, n))
 tr = np.array(out[:], dtype=np.int64).reshape(7, 40, 12)
 L0, L1 = int(sys.argv[1]) if len(sys.argv) > 1 else 10, int(sys.argv[2]) if len(sys.argv) > 2 else 14
-base = tr[3, L0, 0]
-names_e = ["waitD1", "D1rdy", "ld1", "math1+st", "fence", "arriveC", "D2rdy", "ld2", "math2", "waits", "stores", "arriveH"]
-names_i = ["start", "W/HALO/H ok", "G1 issued", "C ok", "G2 issued"]
-names_l = ["start", "Wempty ok", "G1 ok", "halo arrive"]
+names_e = ["top", "sync1", "G1iss", "D1rdy", "ld1", "math1", "sync2", "G2iss", "D2rdy", "math2", "waits", "arriveH"]
+names_l = ["start", "Wempty ok", "G1 ok", "halo arrive", "cp issued", "cp landed"]
+base = tr[0, L0, 0]
 for l in range(L0, L1):
     print("layer %d (d=%d)" % (l, dil[l]))
     for t in range(3):
-        print("  epi%d : " % t + " ".join("%s=%d" % (nm, tr[t, l, i] - base) for i, nm in enumerate(names_e)))
-    for t in range(3):
-        print("  iss%d : " % t + " ".join("%s=%d" % (nm, tr[3 + t, l, i] - base) for i, nm in enumerate(names_i)))
+        print("  tile%d : " % t + " ".join("%s=%d" % (nm, tr[t, l, i] - base) for i, nm in enumerate(names_e)))
     print("  load : " + " ".join("%s=%d" % (nm, tr[6, l, i] - base) for i, nm in enumerate(names_l)))
-per = (tr[3, 29, 0] - tr[3, 1, 0]) / 28.0
-print("avg clocks per layer (issuer 0):", per)
+per = (tr[0, 29, 0] - tr[0, 1, 0]) / 28.0
+print("avg clocks per layer (tile 0):", per)
