@@ -356,25 +356,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
     for (int t0 = sg.t_start; t0 < sg.t_end; t0 += kChunk, chunk_idx++) {
       const bool warm = TEACHER ? (t0 + kChunk <= sg.t_out) : false;   // student chunks always need h (cheap)
       const bool do_head = TEACHER && !warm;
-      const int u0[2] = {chunk_idx * uses0, chunk_idx * uses1};        // phase base of parity-indexed barriers
+      const int u0e = chunk_idx * uses0, u0o = chunk_idx * uses1;      // phase base of parity-indexed barriers
+#define U0(par) ((par) ? u0o : u0e)
       const bool tracing_chunk = p.trace != nullptr && blockIdx.x == 0 && chunk_idx == p.trace_chunk;
 
       if (warp == kLoadWarp) {
         // ================= loader: weights (bulk copy) + halo rows (cp.async) per layer ============
         for (int l = 0; l < L; l++) {
           const int s = l & 1;
-          const int use = u0[s] + (l >> 1);                  // how many times stage s was used before
+          const int use = U0(s) + (l >> 1);                  // how many times stage s was used before
           const bool tracing = tracing_chunk && lane == 0;
           TRACE(6, l, 0);
-          if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag, 0x1000000 | l)) break;
-          if (lane == 0) {
-            mbar_expect_tx(bar(BAR_WFULL + s), layer_bytes);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(sbase + SmemMap::wst + s * SmemMap::wst_bytes),
-                           "l"(p.packed + (size_t)l * layer_bytes), "r"(layer_bytes), "r"(bar(BAR_WFULL + s)) : "memory");
-          }
-          TRACE(6, l, 1);
-          // halo rows of layer l: inputs at t0-d .. t0-1 (zeros before the segment start)
+          // halo rows of layer l: inputs at t0-d .. t0-1 (zeros before the segment start).  The halo goes first:
+          // its condition (filter-conv MMAs of layer l-2 retired) holds earlier than the weight stage's.
           if (l >= 2 && !mbar_wait(bar(BAR_G1 + s), (use - 1) & 1, abort_flag, 0x1100000 | l)) break;   // G1 of layer l-2 retired
           TRACE(6, l, 2);
           const int d = p.dil[l];
@@ -417,6 +411,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_HALO + s));
           }
+          if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag, 0x1000000 | l)) break;
+          if (lane == 0) {
+            mbar_expect_tx(bar(BAR_WFULL + s), layer_bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sbase + SmemMap::wst + s * SmemMap::wst_bytes),
+                           "l"(p.packed + (size_t)l * layer_bytes), "r"(layer_bytes), "r"(bar(BAR_WFULL + s)) : "memory");
+          }
+          TRACE(6, l, 1);
           TRACE(6, l, 3);
         }
       } else {
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             h2[j] = pk(a, b);
             w16[j] = pack2<FP16>(a, b);
           }
-          alive = mbar_wait(bar(BAR_HALO + 0), u0[0] & 1, abort_flag, 0x2000000 | (m << 8));      // ring 0 was read for this chunk
+          alive = mbar_wait(bar(BAR_HALO + 0), U0(0) & 1, abort_flag, 0x2000000 | (m << 8));      // ring 0 was read for this chunk
           store_row_packed(smem + SmemMap::hbuf, kRows, kHalo + rc, w16);
           const int d0 = p.dil[0];
           if (rc >= kChunk - d0) store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
 
         for (int l = 0; l < L; l++) {
           const int s = l & 1, sn = s ^ 1;
-          const uint32_t ph = (chunk_idx * L + l) & 1, phs = (u0[s] + (l >> 1)) & 1;
+          const uint32_t ph = (chunk_idx * L + l) & 1, phs = (U0(s) + (l >> 1)) & 1;
           TRACE(m, l, 0);
           // ---- filter-conv GEMM: K = 64, steps 0,1 = tap rows (W[0], d rows earlier), 2,3 = current rows (W[1])
           const uint32_t hb_lo = hb_lo0 + (uint32_t)(s * (SmemMap::hbuf_bytes >> 4));
@@ -511,8 +513,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           //  - ring l+1 may be overwritten once this chunk's halo of layer l+1 was read
           bool next_ok = true;
           if (l + 1 < L && !issuer) {
-            if (l >= 1) next_ok = mbar_poll(bar(BAR_G1 + sn), (u0[sn] + ((l - 1) >> 1)) & 1);
-            next_ok = mbar_poll(bar(BAR_HALO + sn), (u0[sn] + ((l + 1) >> 1)) & 1) && next_ok;
+            if (l >= 1) next_ok = mbar_poll(bar(BAR_G1 + sn), (U0(sn) + ((l - 1) >> 1)) & 1);
+            next_ok = mbar_poll(bar(BAR_HALO + sn), (U0(sn) + ((l + 1) >> 1)) & 1) && next_ok;
           }
 
           // ---- gate: tanh, sigmoid of the tanh, product (ops.py:28,33,36) ----
@@ -599,8 +601,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
 #pragma unroll
             for (int j = 0; j < 16; j++) { float a, b; upk(h2[j], a, b); w16[j] = pack2<FP16>(a, b); }
             if (!next_ok) {                             // rare: the polls were too early
-              if (l >= 1) alive = mbar_wait(bar(BAR_G1 + sn), (u0[sn] + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l) && alive;
-              alive = mbar_wait(bar(BAR_HALO + sn), (u0[sn] + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l) && alive;
+              if (l >= 1) alive = mbar_wait(bar(BAR_G1 + sn), (U0(sn) + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l) && alive;
+              alive = mbar_wait(bar(BAR_HALO + sn), (U0(sn) + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l) && alive;
             }
             TRACE(m, l, 10);
             store_row_packed(smem + SmemMap::hbuf + sn * SmemMap::hbuf_bytes, kRows, kHalo + rc, w16);
@@ -622,9 +624,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             uint8_t* a3 = smem + SmemMap::hbuf + m * (16 * kTile * 16);
             const uint32_t a3_lo = ((sbase + SmemMap::hbuf + m * (16 * kTile * 16)) >> 4) + ((uint32_t)kTile << 16);
             // all filter-conv MMAs of the last layer retired -> both activation buffers are free
-            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8)) && alive;
+            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (U0((L - 1) & 1) + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8)) && alive;
             // the skip accumulator is complete once this tile's last skip MMA retired (WEMPTY commit of the last layer)
-            alive = mbar_wait(bar(BAR_WEMPTY + ((L - 1) & 1)), (u0[(L - 1) & 1] + ((L - 1) >> 1)) & 1, abort_flag, 0x2510000 | (m << 8)) && alive;
+            alive = mbar_wait(bar(BAR_WEMPTY + ((L - 1) & 1)), (U0((L - 1) & 1) + ((L - 1) >> 1)) & 1, abort_flag, 0x2510000 | (m << 8)) && alive;
             tc_fence_after();
 #pragma unroll 1
             for (int hs = 0; hs < 2; hs++) {
