@@ -25,6 +25,7 @@ FLOP_PER_SAMPLE_TEACHER = 468576      # 30*14336 + 37888 + 128 +
 FLOP_PER_SAMPLE_STUDENT = 740224      # 4*184576 + 1920
 BYTES_PER_SAMPLE_LAYER_F32 = 1280     # fp32 per-layer kernel: h read+write (2*128 B) + skip RMW (2*512 B)
 BYTES_PER_SAMPLE_AR = 7684            # fp32 queue pop+push (2*30*32*4 B) + 4 B sample
+BYTES_PER_SAMPLE_AR_F16 = 3844        # same with 16-bit queue state (2*30*32*2 B) + 4 B sample
 METRIC = "audio samples/sec"
 UNIT = "samples/s"
 
@@ -186,10 +187,11 @@ def main():
         x_h = synth.synthetic_audio(B, T, seed=1234 + g0)
         flop_per_sample = FLOP_PER_SAMPLE_TEACHER
     prec = args.precision
-    if prec == "auto":
+    if prec == "auto" and args.workload != "generate":
         prec = "fp16" if "fp16" in model.available_precisions() else "fp32"
     if args.workload == "generate":
-        prec = "fp32"
+        if prec in ("auto", "fp16", "bf16"):     # tensor-core generation kernel (fp16 operands and queue state)
+            prec = "fp16"
         u1_h, u2_h = synth.sampler_uniforms(B, T, seed=999 + rank)
 
     x_d, enc_d = torch.from_numpy(x_h).cuda(), torch.from_numpy(enc_h).cuda()
@@ -203,14 +205,14 @@ def main():
             return model.nll(x_d, enc_d, precision=prec)
         if args.workload == "student":
             return model.generate(None, x_d, enc_d, precision=prec)
-        return model.generate(enc_d, u1=u1_d, u2=u2_d)
+        return model.generate(enc_d, u1=u1_d, u2=u2_d, precision=prec)
 
     def step_e2e():
         if args.workload == "teacher_nll":
             return model.nll(x_p, enc_p, precision=prec)            # float on the host
         if args.workload == "student":
             return model.generate(None, x_p, enc_p, precision=prec)  # ndarray on the host
-        return model.generate(enc_p, u1=u1_p, u2=u2_p)
+        return model.generate(enc_p, u1=u1_p, u2=u2_p, precision=prec)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -269,7 +271,8 @@ def main():
         with open(tpath) as f:
             traffic = json.load(f).get("%s/%s" % (args.workload, prec))
     if args.workload == "generate":
-        ach = BYTES_PER_SAMPLE_AR * B * T / (k_ms * 1e-3) / 1e9
+        # queue pop + push of 32 channels per layer + the sample: 7684 B with fp32 state, 3844 B with fp16 state
+        ach = (BYTES_PER_SAMPLE_AR if prec == "fp32" else BYTES_PER_SAMPLE_AR_F16) * B * T / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s"}
     elif prec in ("bf16", "fp16"):
         ach = flop_per_sample * B * T / (k_ms * 1e-3) / 1e12

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SRWN_ABI_VERSION 1
+#define SRWN_ABI_VERSION 2
 
 enum srwn_status {
   SRWN_OK = 0,
@@ -131,10 +131,12 @@ int srwn_teacher_nll(srwn_handle_t h, const float* x_in, const float* enc,
 /* The autoregressive loop of teacher.py:153-170 restated with per-layer dilation
  * queues: x[t] = clip(MoL_sample(logits_t)), logits_t from x[<t] and enc[t/P].
  * u1 [B,T,M], u2 [B,T] are the uniforms of ops.py:187,196 (injected for parity).
- * x_out [B,T]; logits_out [B,T,4M] optional. */
+ * x_out [B,T]; logits_out [B,T,4M] optional.
+ * precision: SRWN_FP32 = fp32 FFMA kernel (parity grade); SRWN_FP16 = tensor-core kernel
+ * (mma.sync, fp16 operands and queue state, fp32 accumulate and residual stream). */
 int srwn_teacher_generate(srwn_handle_t h, const float* enc, const float* u1,
                           const float* u2, float* x_out, float* logits_out,
-                          int32_t B, int32_t T,
+                          int32_t B, int32_t T, int32_t precision,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- student (model.py:415-535) ------------------------------------------------- */

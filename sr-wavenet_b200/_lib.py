@@ -8,6 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRWN_LIB") or os.path.join(_HERE, "libsrwn.so")   # SRWN_LIB: tuning builds (tools/exp_build.sh)
 
+ABI_VERSION = 2      # SRWN_ABI_VERSION in include/srwn.h
 OK, ERR_INVALID, ERR_CUDA, ERR_WEIGHTS, ERR_UNSUPPORTED, ERR_WORKSPACE = range(6)
 TEACHER, STUDENT = 0, 1
 FP32, BF16, FP16 = 0, 1, 2
@@ -50,7 +51,7 @@ SIGNATURES = {
     "srwn_workspace_bytes": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, ctypes.POINTER(_sz)]),
     "srwn_teacher_logits": (ctypes.c_int, [_vp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "srwn_teacher_nll": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
-    "srwn_teacher_generate": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_teacher_generate": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "srwn_student_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "srwn_dilated_causal_conv1d": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "srwn_residual_dilation_layer": (ctypes.c_int, [_fp] * 9 + [_i32] * 6 + [_vp]),
@@ -77,7 +78,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.srwn_abi_version() != 1:
+    if lib.srwn_abi_version() != ABI_VERSION:
         raise RuntimeError("libsrwn.so ABI version mismatch")
     _lib = lib
     return lib

@@ -183,7 +183,7 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
   c->device = dev;
   c->committed = false;
   c->d_weights = nullptr; c->d_dilations = nullptr; c->d_queue_off = nullptr;
-  c->d_packed = nullptr; c->packed_bytes = 0;
+  c->d_packed = nullptr; c->packed_bytes = 0; c->d_ar_packed = nullptr;
   c->profiling = 0; c->prof_launches = 0; c->prof_name = "";
   c->prof_ev[0] = c->prof_ev[1] = nullptr;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -233,6 +233,7 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
 extern "C" int srwn_destroy(srwn_handle_t h) {
   if (!h) return SRWN_OK;
   if (h->prof_ev[0]) { cudaEventDestroy(h->prof_ev[0]); cudaEventDestroy(h->prof_ev[1]); }
+  cudaFree(h->d_ar_packed);
   cudaFree(h->d_weights); cudaFree(h->d_dilations); cudaFree(h->d_queue_off); cudaFree(h->d_packed);
   delete reinterpret_cast<CtxBox*>(h);
   return SRWN_OK;
@@ -303,6 +304,10 @@ extern "C" int srwn_commit_weights(srwn_handle_t h, void* stream) {
   }
   int rc = fused_pack_weights(h, (cudaStream_t)stream);
   if (rc != SRWN_OK) return rc;
+  if (h->cfg.kind == SRWN_TEACHER) {
+    rc = ar_mma_pack_weights(h, (cudaStream_t)stream);
+    if (rc != SRWN_OK) return rc;
+  }
   h->committed = true;
   return SRWN_OK;
 }
@@ -365,10 +370,11 @@ extern "C" int srwn_last_kernel_ms(srwn_handle_t h, float* ms, int32_t* launches
 extern "C" int srwn_check_async_error(srwn_handle_t h, int32_t op, int32_t B, int32_t T, int32_t precision,
                                       void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return srwn_fail(SRWN_ERR_INVALID, "srwn_check_async_error: null handle");
-  if (precision == SRWN_FP32 || op == SRWN_OP_TEACHER_GENERATE) {
+  if (precision == SRWN_FP32) {
     SRWN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return SRWN_OK;
   }
+  if (op == SRWN_OP_TEACHER_GENERATE) return ar_mma_check_error(h, B, T, workspace, workspace_bytes, (cudaStream_t)stream);
   return fused_check_error(workspace, workspace_bytes, h, B, T, (cudaStream_t)stream);
 }
 
@@ -377,8 +383,8 @@ extern "C" int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision) {
   const bool teacher_op = op == SRWN_OP_TEACHER_LOGITS || op == SRWN_OP_TEACHER_NLL || op == SRWN_OP_TEACHER_GENERATE;
   if (teacher_op != (h->cfg.kind == SRWN_TEACHER) || op < 0 || op > SRWN_OP_STUDENT_FORWARD) return 0;
   if (precision == SRWN_FP32) return 1;
-  if (precision == SRWN_BF16 || precision == SRWN_FP16)
-    return op != SRWN_OP_TEACHER_GENERATE && fused_supported(h) ? 1 : 0;
+  if (op == SRWN_OP_TEACHER_GENERATE) return precision == SRWN_FP16 && ar_mma_supported(h) ? 1 : 0;
+  if (precision == SRWN_BF16 || precision == SRWN_FP16) return fused_supported(h) ? 1 : 0;
   return 0;
 }
 
@@ -395,7 +401,7 @@ extern "C" int srwn_workspace_bytes(srwn_handle_t h, int32_t op, int32_t B, int3
       return SRWN_OK;
     case SRWN_OP_TEACHER_GENERATE:
       if (h->cfg.kind != SRWN_TEACHER) return srwn_fail(SRWN_ERR_INVALID, "not a teacher handle");
-      *bytes = ar_workspace_bytes(h, B, T);
+      *bytes = precision == SRWN_FP16 ? ar_mma_workspace_bytes(h, B, T) : ar_workspace_bytes(h, B, T);
       return SRWN_OK;
     case SRWN_OP_STUDENT_FORWARD:
       if (h->cfg.kind != SRWN_STUDENT) return srwn_fail(SRWN_ERR_INVALID, "not a student handle");
@@ -455,11 +461,16 @@ extern "C" int srwn_teacher_nll(srwn_handle_t h, const float* x_in, const float*
 
 extern "C" int srwn_teacher_generate(srwn_handle_t h, const float* enc, const float* u1,
                                      const float* u2, float* x_out, float* logits_out, int32_t B,
-                                     int32_t T, void* workspace, size_t workspace_bytes, void* stream) {
+                                     int32_t T, int32_t precision, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
   if (!h || !enc || !u1 || !u2 || !x_out) return srwn_fail(SRWN_ERR_INVALID, "srwn_teacher_generate: null argument");
   if (h->cfg.kind != SRWN_TEACHER) return srwn_fail(SRWN_ERR_INVALID, "not a teacher handle");
   int rc = check_bt(h, B, T);
   if (rc) return rc;
+  if (precision == SRWN_FP16)
+    return run_ar_mma(h, enc, u1, u2, x_out, logits_out, B, T, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (precision != SRWN_FP32)
+    return srwn_fail(SRWN_ERR_UNSUPPORTED, "generation runs in fp32 (FFMA kernel) or fp16 (tensor-core kernel)");
   return run_ar_generate(h, enc, u1, u2, x_out, logits_out, B, T, workspace, workspace_bytes,
                          (cudaStream_t)stream);
 }

@@ -1,0 +1,607 @@
+// Autoregressive teacher generation on tensor cores (fp16 operands, fp32 accumulate / residual stream).
+//
+// Same recurrence as ar_generate.cu (the queue restatement of teacher.py:153-170), organised for the
+// per-sample latency chain x[t] -> 30 gated layers -> head -> sampler -> x[t+1], which is what bounds
+// this workload (BASELINE.json configs[3]: 256 utterances x 16000 strictly sequential steps):
+//   * one CTA owns 8 utterances (rows 0..7 of the m16n8k16 tiles) for all T steps;
+//   * CHAIN warp: the whole layer chain for those rows with warp-level mma.sync -- filter conv
+//     [8x64]x[64x32], gate, residual 1x1 [8x32]x[32x32] -- with every chain weight (B fragments, 6 KB per
+//     layer, 184 KB) resident in shared memory; accumulator fragments turn into the next A fragments in
+//     registers, so a layer costs two short MMA bursts and one gate, no shared-memory round trip;
+//   * SKIP warps (8): the skip 1x1 (ops.py:44) is off the chain -- the chain warp drops the gate output
+//     c_l into a per-layer slot, the skip warps multiply it by Ws_l (16 skip channels per warp) and keep
+//     the sum over layers (model.py:190) in accumulator registers; they then run the head's S->S conv
+//     (model.py:193) cooperatively;
+//   * PRODUCER warp: streams the skip / head weights (280 KB per step, L2 resident) through a 3-stage
+//     cp.async.bulk ring;
+//   * the chain warp finishes the head (S->4M), and 8 of its lanes run the mixture-of-logistics sampler
+//     (ops.py:178-201) and feed x[t] back;
+//   * dilation queues (fp16 images of each layer's input, 64 B per utterance and slot) live in global
+//     memory / L2; the pop of layer l+2 is prefetched while layer l runs.
+#include "common.cuh"
+#include "mol.cuh"
+#include <cuda_fp16.h>
+#include <vector>
+#include <cstdio>
+
+const float* srwn_host_weights(srwn_ctx* c);
+__global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
+                       const float* __restrict__ cond_b, float* __restrict__ cond,
+                       int frames_total, int L, int C);
+namespace fused {
+__global__ void k_fold_bias(const float* __restrict__ cond, const float* __restrict__ front_b,
+                            const float* __restrict__ res_b, float* __restrict__ cb, int L);
+}
+
+namespace armma {
+
+constexpr int kU = 8;                         // utterances per CTA
+constexpr int kMaxL = 30;                     // chain weights of 30 layers fill shared memory
+constexpr int kChainLayerBytes = 4096 + 2048 + 128;   // Wf fragments | Wr fragments | filter bias (fp32)
+constexpr int kItemBytes = 8192;              // one ring item: skip weights of a layer / a quarter of H1 / H2
+constexpr int kStages = 3;
+constexpr int kSlotBytes = 512;               // gate output of one layer: [lane][4 x b32]
+constexpr int kThreads = 11 * 32;
+constexpr int kChainWarp = 0, kProducerWarp = 4;      // SMSP 0 hosts only these two (and idle warp 8)
+
+struct Smem {
+  static constexpr int chain = 0;
+  static constexpr int ring = chain + kMaxL * kChainLayerBytes;          // 188160
+  static constexpr int cslots = ring + kStages * kItemBytes;             // 212736
+  static constexpr int misc = cslots + kMaxL * kSlotBytes;               // 228096
+  // misc: front fk[64] fb.. (256 B) | head biases bsum[128] b1[128] b2[32] (1152 B) | logits [8][24] (768 B) | barriers
+  static constexpr int front = misc;
+  static constexpr int hbias = front + 256;
+  static constexpr int logits = hbias + 1152;
+  static constexpr int bars = logits + 768;
+  static constexpr int n_bars = 2 * kStages + kMaxL + 2;
+  static constexpr int flags = bars + n_bars * 8 + 16;     // per-layer step counters: gate slot l holds step (flag - 1)
+  static constexpr int total = flags + kMaxL * 4;
+};
+static_assert(Smem::total <= 232448, "shared memory budget");
+
+struct Params {
+  const uint8_t* chain_w;     // [L][kChainLayerBytes]
+  const uint8_t* stream;      // [L + 5][kItemBytes]
+  const float* fixed;         // fk[64] | bsum[128] b1[128] b2[32]
+  const float* cb;            // [B][frames][L+1][32] folded biases + conditioning (fused::k_fold_bias)
+  uint8_t* queues;            // [grid][sum_d][kSlotBytes]
+  const float* u1;            // [B][T][M]
+  const float* u2;            // [B][T]
+  float* x_out;               // [B][T]
+  float* logits_out;          // [B][T][4M] or null
+  int* err;
+  int B, T, L, P, frames, M, sum_d;
+  int dil[kMaxL];
+  int qoff[kMaxL];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a stuck pipeline raises the abort flag instead of hanging the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity, volatile int* abort_flag) {
+  if (mbar_try(a, parity)) return true;
+  const long long t0 = clock64();
+  while (true) {
+    if (mbar_try(a, parity)) return true;
+    if (*abort_flag) return false;
+    if (clock64() - t0 > 2000000000LL) { *abort_flag = 1; return false; }
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// D(16x8, fp32) += A(16x16, fp16, row) * B(16x8, fp16, col); rows 8..15 of A are zero padding (a1 = a3 = 0)
+__device__ __forceinline__ void mma8(float (&d)[2], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  float z0 = 0.f, z1 = 0.f;
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(z0), "+f"(z1)
+               : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// ops.py:28,33,36: f = tanh(a); f * sigmoid(f), sigmoid on [-1,1] as 0.5 + f*P(f^2) (error 1.5e-6)
+__device__ __forceinline__ float gate(float a) {
+  const float f = tanh_fast(a);
+  const float s = f * f;
+  float t = fmaf(s, 0.0017294071149080992f, -0.020638039335608482f);
+  t = fmaf(s, t, 0.2499687224626541f);
+  return fmaf(f, 0.5f, s * t);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+// resident, read-only after setup: the compiler may hoist these loads (no volatile, no memory clobber)
+__device__ __forceinline__ uint4 lds128_ro(uint32_t a) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;              // fragment row / column-pair index
+  const int L = p.L, O = 4 * p.M;
+  const int n_items = L + 5;
+  // hidden-layer exchange tiles (16 x 256 B used): behind the gate slots when there is room, else on top of
+  // slots 0..15, which every skip warp has left by then (the 3-stage ring keeps them within 3 layers of each other)
+  const int hid_slot = (L + 16 <= kMaxL) ? L : 0;
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + Smem::bars + Smem::n_bars * 8);
+  auto bar = [&](int i) { return sbase + Smem::bars + i * 8; };
+  // barrier indices: wfull[3] | wempty[3] | cfull[L] | hid1 | hid2
+  const int B_WFULL = 0, B_WEMPTY = kStages, B_CFULL = 2 * kStages, B_HID1 = 2 * kStages + kMaxL, B_HID2 = B_HID1 + 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_WFULL + s)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_WEMPTY + s)), "r"(8));
+    }
+    for (int l = 0; l < kMaxL; l++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_CFULL + l)), "r"(32));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_HID1)), "r"(256));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_HID2)), "r"(256));
+    *abort_flag = 0;
+    for (int l = 0; l < kMaxL; l++) reinterpret_cast<volatile int*>(smem + Smem::flags)[l] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {  // resident chain weights + small constants
+    const uint4* src = reinterpret_cast<const uint4*>(p.chain_w);
+    uint4* dst = reinterpret_cast<uint4*>(smem + Smem::chain);
+    for (int i = tid; i < L * kChainLayerBytes / 16; i += kThreads) dst[i] = src[i];
+    float* sf = reinterpret_cast<float*>(smem + Smem::front);
+    for (int i = tid; i < 64; i += kThreads) sf[i] = p.fixed[i];
+    float* sh = reinterpret_cast<float*>(smem + Smem::hbias);
+    for (int i = tid; i < 288; i += kThreads) sh[i] = p.fixed[64 + i];
+  }
+  __syncthreads();
+
+  const int b0 = blockIdx.x * kU;
+  const bool pow2 = p.sum_d < 0;      // host encodes "all dilations are powers of two" in the sign
+  const int sum_d = pow2 ? -p.sum_d : p.sum_d;
+
+  if (warp == kProducerWarp) {
+    // ================= producer: skip / head weights, L2 -> shared ring ===========================
+    if (lane == 0) {
+      long long it = 0;
+      for (int t = 0; t < p.T; t++) {
+        for (int i = 0; i < n_items; i++, it++) {
+          const int s = (int)(it % kStages);
+          if (!mbar_wait(bar(B_WEMPTY + s), (uint32_t)(((it / kStages) & 1) ^ 1), abort_flag)) { t = p.T; break; }
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar(B_WFULL + s)), "r"(kItemBytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(sbase + Smem::ring + s * kItemBytes), "l"(p.stream + (size_t)i * kItemBytes),
+                         "r"(kItemBytes), "r"(bar(B_WFULL + s)) : "memory");
+        }
+      }
+    }
+    return;
+  }
+  if (warp == 8) return;
+
+  if (warp == kChainWarp) {
+    // ================= chain warp ==================================================================
+    const int bg = min(b0 + g, p.B - 1);               // utterance of fragment row g (clamped: padding rows repeat the last one)
+    const float* cb_b = p.cb + (size_t)bg * p.frames * (L + 1) * 32;
+    uint8_t* qbase = p.queues + (size_t)blockIdx.x * sum_d * kSlotBytes + lane * 16;
+    const float* sf = reinterpret_cast<const float*>(smem + Smem::front);
+    float xm1 = 0.f, xm2 = 0.f;                         // x[t-1], x[t-2] of utterance g
+    float h[4][2];                                      // residual stream: n-tile j, columns 8j+2q, 8j+2q+1 of row g
+    uint32_t hA[4];                                     // its fp16 image as A fragments: kt0 (a0,a2), kt1 (a0,a2)
+    long long it_base = 0;                              // ring item counter at the start of the step
+    const int ub = b0 + lane;                           // sampler lanes 0..7: utterance b0+lane
+    const bool samp = lane < kU && ub < p.B;
+
+    long long tm_a = 0, tm_b = 0, tm_c = 0, tl1 = 0, tl2 = 0, tl3 = 0;
+    for (int t = 0; t < p.T; t++, it_base += n_items) {
+      const long long c0 = clock64();
+      const int frame = t / p.P;
+      const float* cbf = cb_b + (size_t)frame * (L + 1) * 32 + 2 * q;
+      // sampler noise of this step (latency hidden behind the layer chain)
+      float u1v[8], u2v = 0.5f;
+#pragma unroll
+      for (int m = 0; m < 8; m++) u1v[m] = 0.5f;
+      if (samp) {
+        for (int m = 0; m < p.M; m++) u1v[m] = __ldg(p.u1 + ((size_t)ub * p.T + t) * p.M + m);
+        u2v = __ldg(p.u2 + (size_t)ub * p.T + t);
+      }
+      // queue slot of every layer at this step (byte offsets), computed by one lane per layer
+      {
+        int* sq = reinterpret_cast<int*>(smem + Smem::logits);          // the logits scratch is idle during the chain
+        if (lane < L) {
+          const int d = p.dil[lane];
+          sq[lane] = (p.qoff[lane] + (pow2 ? (t & (d - 1)) : (t % d))) * kSlotBytes;
+        }
+        __syncwarp();
+      }
+      const volatile int* sq = reinterpret_cast<const volatile int*>(smem + Smem::logits);
+      // pops of layers 0 and 1; folded bias + conditioning of layers 0, 1, 2 (rotating registers, no arrays
+      // indexed by the layer: those would live in local memory)
+      int ofs0 = sq[0], ofs1 = L > 1 ? sq[1] : 0, ofs2 = L > 2 ? sq[2] : 0;
+      uint4 tap0 = *reinterpret_cast<const uint4*>(qbase + ofs0);
+      uint4 tap1 = L > 1 ? *reinterpret_cast<const uint4*>(qbase + ofs1) : make_uint4(0, 0, 0, 0);
+      float2 cb0[4], cbA[4], cbB[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        cb0[j] = *reinterpret_cast<const float2*>(cbf + 8 * j);
+        cbA[j] = *reinterpret_cast<const float2*>(cbf + 32 + 8 * j);
+        cbB[j] = L >= 2 ? *reinterpret_cast<const float2*>(cbf + 64 + 8 * j) : make_float2(0.f, 0.f);
+      }
+      // front: RightShift + K=2 causal conv on one channel (model.py:172-173) + bias + conditioning of layer 0
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = 8 * j + 2 * q;
+        h[j][0] = fmaf(xm2, sf[c], fmaf(xm1, sf[32 + c], cb0[j].x));
+        h[j][1] = fmaf(xm2, sf[c + 1], fmaf(xm1, sf[32 + c + 1], cb0[j].y));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) hA[j] = pack_h2(h[j][0], h[j][1]);
+      uint4 wf[8];                                       // filter-conv B fragments of the current layer
+#pragma unroll
+      for (int i = 0; i < 8; i++) wf[i] = lds128_ro(sbase + Smem::chain + lane * 16 + i * 512);
+
+      for (int l = 0; l < L; l++) {
+        const uint32_t wl = sbase + Smem::chain + l * kChainLayerBytes + lane * 16;
+#ifdef SRWN_AR_TIMING
+        const long long s0 = clock64();
+#endif
+        const uint4 tap = tap0;
+        const int ofs = ofs0;
+        tap0 = tap1; ofs0 = ofs1; ofs1 = ofs2;
+        if (l + 2 < L) tap1 = *reinterpret_cast<const uint4*>(qbase + ofs1);   // prefetch the pop two layers ahead
+        if (l + 3 < L) ofs2 = sq[l + 3];
+        float2 cb_next[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          cb_next[j] = cbA[j];
+          cbA[j] = cbB[j];
+          if (l + 3 <= L) cbB[j] = *reinterpret_cast<const float2*>(cbf + (l + 3) * 32 + 8 * j);
+        }
+        // ---- filter conv (ops.py:6-10): taps (k-tiles 0,1: W[0] on h[t-d]) and current (k-tiles 2,3: W[1] on h[t]);
+        //      eight independent MMAs first, their eight dependants second
+        float acc[4][2], acc2[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          acc[j][0] = acc[j][1] = acc2[j][0] = acc2[j][1] = 0.f;
+          mma8(acc[j], tap.x, tap.y, wf[2 * j].x, wf[2 * j].y);
+          mma8(acc2[j], hA[0], hA[1], wf[2 * j + 1].x, wf[2 * j + 1].y);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          mma8(acc[j], tap.z, tap.w, wf[2 * j].z, wf[2 * j].w);
+          mma8(acc2[j], hA[2], hA[3], wf[2 * j + 1].z, wf[2 * j + 1].w);
+        }
+        uint4 wr[4];                                     // residual B fragments: land while the gate runs
+#pragma unroll
+        for (int j = 0; j < 4; j++) wr[j] = lds128_ro(wl + 4096 + j * 512);
+        // push h[t] (the slot held h[t-d] until now)
+        *reinterpret_cast<uint4*>(qbase + ofs) = make_uint4(hA[0], hA[1], hA[2], hA[3]);
+        // ---- gate (ops.py:28,33,36) -> A fragments of the residual / skip convs
+        const float* bf = reinterpret_cast<const float*>(smem + Smem::chain + l * kChainLayerBytes + 6144) + 2 * q;
+        uint32_t cA[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float2 b = *reinterpret_cast<const float2*>(bf + 8 * j);
+          cA[j] = pack_h2(gate(acc[j][0] + acc2[j][0] + b.x), gate(acc[j][1] + acc2[j][1] + b.y));
+        }
+#ifdef SRWN_AR_TIMING
+        const long long s1 = clock64() + (cA[0] & 0);
+#endif
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Smem::cslots + l * kSlotBytes + lane * 16),
+                     "r"(cA[0]), "r"(cA[1]), "r"(cA[2]), "r"(cA[3]) : "memory");
+        // publish the slot with a plain flag store: shared-memory accesses of one warp are performed in program
+        // order, so a reader that sees the flag sees the slot.  (An mbarrier arrive has release semantics and made
+        // the chain wait for the queue push -- a global store -- to be acknowledged: ~450 clocks per layer.)
+        if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sbase + Smem::flags + l * 4), "r"(t + 1) : "memory");
+#ifdef SRWN_AR_TIMING
+        const long long s2 = clock64();
+#endif
+        if (l + 1 < L) {                                 // next layer's filter-conv fragments
+#pragma unroll
+          for (int i = 0; i < 8; i++) wf[i] = lds128_ro(wl + kChainLayerBytes + i * 512);
+        }
+        // ---- residual 1x1 (ops.py:39) and dense = (inputs + residual) * sqrt(1/2) (ops.py:40); the folded
+        //      term carries sqrt(1/2)*bias and the next layer's conditioning (model.py:183)
+        float r[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { r[j][0] = r[j][1] = 0.f; mma8(r[j], cA[0], cA[1], wr[j].x, wr[j].y); }
+#pragma unroll
+        for (int j = 0; j < 4; j++) mma8(r[j], cA[2], cA[3], wr[j].z, wr[j].w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          h[j][0] = fmaf(h[j][0] + r[j][0], SRWN_SQRT_HALF, cb_next[j].x);
+          h[j][1] = fmaf(h[j][1] + r[j][1], SRWN_SQRT_HALF, cb_next[j].y);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) hA[j] = pack_h2(h[j][0], h[j][1]);
+#ifdef SRWN_AR_TIMING
+        const long long s3 = clock64() + (hA[0] & 0);
+        tl1 += s1 - s0; tl2 += s2 - s1; tl3 += s3 - s2;
+#endif
+      }
+      __syncwarp();                                      // the slot offsets are dead: the scratch becomes logits again
+
+      // ---- head, last stage: relu(hidden) @ H2 -> logits (model.py:194-196) -------------------------
+      const long long c1 = clock64();
+      if (!mbar_wait(bar(B_HID2), (uint32_t)(t & 1), abort_flag)) break;
+      const long long c2 = clock64();
+      const long long it = it_base + L + 4;
+      const int st = (int)(it % kStages);
+      if (!mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag)) break;
+      float lg[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+      {
+        const uint32_t hb = sbase + Smem::cslots + (hid_slot + 8) * kSlotBytes + lane * 8;   // hid2 tiles
+        const uint32_t wb = sbase + Smem::ring + st * kItemBytes + lane * 16;
+#pragma unroll
+        for (int kp = 0; kp < 4; kp++) {
+          const uint2 a0 = lds64(hb + (2 * kp) * kSlotBytes), a1 = lds64(hb + (2 * kp + 1) * kSlotBytes);
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            const uint4 w = lds128(wb + (j * 4 + kp) * 512);
+            mma8(lg[j], a0.x, a0.y, w.x, w.y);
+            mma8(lg[j], a1.x, a1.y, w.z, w.w);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane < 8) mbar_arrive(bar(B_WEMPTY + st));    // this item has one consumer warp: 8 lanes stand in for 8 warps
+      {
+        const float* b2 = reinterpret_cast<const float*>(smem + Smem::hbias) + 256;
+        float* sl = reinterpret_cast<float*>(smem + Smem::logits) + g * 24;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          sl[8 * j + 2 * q] = lg[j][0] + b2[8 * j + 2 * q];
+          sl[8 * j + 2 * q + 1] = lg[j][1] + b2[8 * j + 2 * q + 1];
+        }
+      }
+      __syncwarp();
+      float xs = 0.f;
+      if (samp) {
+        const float* sl = reinterpret_cast<const float*>(smem + Smem::logits) + lane * 24;
+        float lgv[24];
+#pragma unroll
+        for (int j = 0; j < 24; j++) lgv[j] = sl[j];
+        int k;
+        xs = mol_sample_one(lgv, u1v, u2v, p.M, &k);    // ops.py:178-201
+        p.x_out[(size_t)ub * p.T + t] = xs;
+        if (p.logits_out) {
+          float* dst = p.logits_out + ((size_t)ub * p.T + t) * O;
+          for (int j = 0; j < O; j++) dst[j] = lgv[j];
+        }
+      }
+      __syncwarp();
+      xm2 = xm1;
+      xm1 = __shfl_sync(0xffffffffu, xs, g);
+      const long long c3 = clock64();
+      tm_a += c1 - c0; tm_b += c2 - c1; tm_c += c3 - c2;
+    }
+#ifdef SRWN_AR_TIMING
+    if (lane == 0 && blockIdx.x == 0) printf("chain: layers %lld clk/step, wait skip/head %lld, head+sampler %lld | per layer: conv+gate %lld, slot+arrive %lld, residual %lld\n", tm_a / p.T, tm_b / p.T, tm_c / p.T, tl1 / p.T / L, tl2 / p.T / L, tl3 / p.T / L);
+#endif
+    if (lane == 0 && *abort_flag) atomicExch(p.err, 1);
+    return;
+  }
+
+  // ================= skip warps: skip 1x1 summed over layers, then the S->S conv of the head =========
+  const int sw = warp < 4 ? warp - 1 : (warp < 8 ? warp - 2 : warp - 3);     // warps 1,2,3,5,6,7,9,10 -> 0..7
+  const float* shb = reinterpret_cast<const float*>(smem + Smem::hbias);
+  long long it = 0;
+  for (int t = 0; t < p.T; t++) {
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};        // skip sum, n-tiles 2sw, 2sw+1 (model.py:190)
+    bool ok = true;
+    for (int l = 0; l < L && ok; l++, it++) {
+      const int st = (int)(it % kStages);
+      ok = mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag);
+      if (ok) {                                          // gate slot of layer l written for step t?
+        const uint32_t fa = sbase + Smem::flags + l * 4;
+        int seen, spins = 0;
+        do {
+          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(fa) : "memory");
+          if (seen != t + 1 && (++spins & 1023) == 0 && *abort_flag) { ok = false; break; }
+        } while (seen != t + 1);
+      }
+      if (!ok) break;
+      const uint4 a = lds128(sbase + Smem::cslots + l * kSlotBytes + lane * 16);
+      const uint32_t wb = sbase + Smem::ring + st * kItemBytes + sw * 1024 + lane * 16;
+      const uint4 w0 = lds128(wb), w1 = lds128(wb + 512);
+      mma8(acc[0], a.x, a.y, w0.x, w0.y);
+      mma8(acc[1], a.x, a.y, w1.x, w1.y);
+      mma8(acc[0], a.z, a.w, w0.z, w0.w);
+      mma8(acc[1], a.z, a.w, w1.z, w1.w);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_WEMPTY + st));
+    }
+    if (!ok) break;
+    // relu(sum of skips + summed skip biases) -> A k-tile `sw` of the S->S conv (model.py:190-193); slots 0..7
+    {
+      const int c = 16 * sw + 2 * q;
+      const uint32_t a0 = pack_h2(fmaxf(acc[0][0] + shb[c], 0.f), fmaxf(acc[0][1] + shb[c + 1], 0.f));
+      const uint32_t a2 = pack_h2(fmaxf(acc[1][0] + shb[c + 8], 0.f), fmaxf(acc[1][1] + shb[c + 9], 0.f));
+      asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sbase + Smem::cslots + (hid_slot + sw) * kSlotBytes + lane * 8), "r"(a0), "r"(a2) : "memory");
+      mbar_arrive(bar(B_HID1));
+    }
+    if (!mbar_wait(bar(B_HID1), (uint32_t)(t & 1), abort_flag)) break;
+    float hd[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int i = 0; i < 4 && ok; i++, it++) {           // H1 arrives as 4 items of two k-tiles each
+      const int st = (int)(it % kStages);
+      ok = mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag);
+      if (!ok) break;
+      const uint32_t wb = sbase + Smem::ring + st * kItemBytes + sw * 1024 + lane * 16;
+      const uint4 w0 = lds128(wb), w1 = lds128(wb + 512);
+      const uint2 a0 = lds64(sbase + Smem::cslots + (hid_slot + 2 * i) * kSlotBytes + lane * 8);
+      const uint2 a1 = lds64(sbase + Smem::cslots + (hid_slot + 2 * i + 1) * kSlotBytes + lane * 8);
+      mma8(hd[0], a0.x, a0.y, w0.x, w0.y);
+      mma8(hd[1], a0.x, a0.y, w1.x, w1.y);
+      mma8(hd[0], a1.x, a1.y, w0.z, w0.w);
+      mma8(hd[1], a1.x, a1.y, w1.z, w1.w);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_WEMPTY + st));
+    }
+    if (!ok) break;
+    it++;                                               // the H2 item belongs to the chain warp
+    {
+      const int c = 16 * sw + 2 * q;
+      const uint32_t a0 = pack_h2(fmaxf(hd[0][0] + shb[128 + c], 0.f), fmaxf(hd[0][1] + shb[128 + c + 1], 0.f));
+      const uint32_t a2 = pack_h2(fmaxf(hd[1][0] + shb[128 + c + 8], 0.f), fmaxf(hd[1][1] + shb[128 + c + 9], 0.f));
+      asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sbase + Smem::cslots + (hid_slot + 8 + sw) * kSlotBytes + lane * 8), "r"(a0), "r"(a2) : "memory");
+      mbar_arrive(bar(B_HID2));
+    }
+  }
+}
+
+}  // namespace armma
+
+// ---- host -------------------------------------------------------------------------------------------
+static inline uint16_t h16(float f) { __half h = __float2half_rn(f); return *reinterpret_cast<uint16_t*>(&h); }
+
+// B fragment pair of W [K][N] (row stride ld) for n-tile nt and k-tiles kt, kt+1, as the 16 bytes lane (g,q) loads:
+// {b0(kt), b1(kt), b0(kt+1), b1(kt+1)}, b0 = (W[16kt+2q][n], W[16kt+2q+1][n]), b1 = rows +8, n = 8nt+g
+static void pack_frag_pair(uint8_t* dst, const float* W, int ld, int K, int N, int kt, int nt) {
+  uint16_t* o = reinterpret_cast<uint16_t*>(dst);
+  for (int lane = 0; lane < 32; lane++) {
+    const int g = lane >> 2, q = lane & 3, n = 8 * nt + g;
+    for (int half = 0; half < 2; half++) {
+      const int k0 = 16 * (kt + half) + 2 * q;
+      const int ks[4] = {k0, k0 + 1, k0 + 8, k0 + 9};
+      for (int e = 0; e < 4; e++) {
+        const float v = (ks[e] < K && n < N) ? W[(size_t)ks[e] * ld + n] : 0.f;
+        o[lane * 8 + half * 4 + e] = h16(v);
+      }
+    }
+  }
+}
+
+bool ar_mma_supported(const srwn_ctx* c) {
+  return c->cfg.kind == SRWN_TEACHER && c->cfg.n_layers <= armma::kMaxL && (c->cfg.n_layers <= armma::kMaxL - 16 || c->cfg.n_layers >= 20) && 4 * c->cfg.num_mixtures <= 24 &&
+         c->cfg.num_mixtures <= 8;
+}
+
+static size_t ar_mma_image_bytes(const srwn_ctx* c) {
+  return (size_t)c->cfg.n_layers * armma::kChainLayerBytes + (size_t)(c->cfg.n_layers + 5) * armma::kItemBytes + 352 * 4;
+}
+
+int ar_mma_pack_weights(srwn_ctx* c, cudaStream_t st) {
+  if (!ar_mma_supported(c)) return SRWN_OK;
+  const int L = c->cfg.n_layers, O = 4 * c->cfg.num_mixtures;
+  const size_t n = ar_mma_image_bytes(c);
+  if (!c->d_ar_packed) SRWN_CUDA(cudaMalloc(&c->d_ar_packed, n));
+  std::vector<uint8_t> host(n, 0);
+  const float* w = srwn_host_weights(c);
+  const StackOffsets& o = c->off;
+  uint8_t* chain = host.data();
+  uint8_t* stream = chain + (size_t)L * armma::kChainLayerBytes;
+  float* fixed = reinterpret_cast<float*>(stream + (size_t)(L + 5) * armma::kItemBytes);
+  for (int l = 0; l < L; l++) {
+    uint8_t* cl = chain + (size_t)l * armma::kChainLayerBytes;
+    const float* fk = w + o.filt_k + (size_t)l * 2 * kR * kR;      // [2][Cin][Cout] = K 64 x N 32
+    for (int j = 0; j < 4; j++) {
+      pack_frag_pair(cl + (2 * j) * 512, fk, kR, 64, 32, 0, j);
+      pack_frag_pair(cl + (2 * j + 1) * 512, fk, kR, 64, 32, 2, j);
+    }
+    const float* rk = w + o.res_k + (size_t)l * kR * kR;
+    for (int j = 0; j < 4; j++) pack_frag_pair(cl + 4096 + j * 512, rk, kR, 32, 32, 0, j);
+    memcpy(cl + 6144, w + o.filt_b + (size_t)l * kR, 32 * 4);
+    uint8_t* it = stream + (size_t)l * armma::kItemBytes;           // skip weights: [warp][n-tile local]
+    const float* sk = w + o.skip_k + (size_t)l * kR * kS;
+    for (int sw = 0; sw < 8; sw++)
+      for (int nl = 0; nl < 2; nl++) pack_frag_pair(it + sw * 1024 + nl * 512, sk, kS, 32, 128, 0, 2 * sw + nl);
+  }
+  for (int i = 0; i < 4; i++) {                                      // H1: item i = k-tiles 2i, 2i+1
+    uint8_t* it = stream + (size_t)(L + i) * armma::kItemBytes;
+    for (int sw = 0; sw < 8; sw++)
+      for (int nl = 0; nl < 2; nl++) pack_frag_pair(it + sw * 1024 + nl * 512, w + o.head1_k, kS, 128, 128, 2 * i, 2 * sw + nl);
+  }
+  {                                                                  // H2: [n-tile][k-tile pair]
+    uint8_t* it = stream + (size_t)(L + 4) * armma::kItemBytes;
+    for (int j = 0; j < 3; j++)
+      for (int kp = 0; kp < 4; kp++) pack_frag_pair(it + (j * 4 + kp) * 512, w + o.head2_k, O, 128, O, 2 * kp, j);
+  }
+  memcpy(fixed, w + o.front_k, 64 * 4);
+  memcpy(fixed + 64, w + o.skip_b_sum, 128 * 4);
+  memcpy(fixed + 192, w + o.head1_b, 128 * 4);
+  for (int j = 0; j < O; j++) fixed[320 + j] = w[o.head2_b + j];
+  SRWN_CUDA(cudaMemcpyAsync(c->d_ar_packed, host.data(), n, cudaMemcpyHostToDevice, st));
+  SRWN_CUDA(cudaStreamSynchronize(st));
+  return SRWN_OK;
+}
+
+struct ArMmaWs { uint8_t* queues; float *cond, *cb; int* err; size_t bytes; int grid; };
+
+static ArMmaWs carve_ar_mma(const srwn_ctx* c, int B, int T, void* ws, size_t cap) {
+  WsCarver w(ws, cap);
+  ArMmaWs r{};
+  const size_t frames = T / c->cfg.pool_stride, L = c->cfg.n_layers;
+  r.grid = (B + armma::kU - 1) / armma::kU;
+  r.queues = w.take<uint8_t>((size_t)r.grid * c->sum_dilation * armma::kSlotBytes);
+  r.cond = w.take<float>((size_t)B * frames * L * 32);
+  r.cb = w.take<float>((size_t)B * frames * (L + 1) * 32);
+  r.err = w.take<int>(4);
+  r.bytes = w.used;
+  return r;
+}
+
+size_t ar_mma_workspace_bytes(const srwn_ctx* c, int B, int T) { return carve_ar_mma(c, B, T, nullptr, 0).bytes; }
+
+int run_ar_mma(srwn_ctx* c, const float* enc, const float* u1, const float* u2, float* x_out,
+               float* logits_out, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ar_mma_supported(c) || !c->d_ar_packed)
+    return srwn_fail(SRWN_ERR_UNSUPPORTED, "fp16 generation kernel supports up to %d layers and 6 mixtures", armma::kMaxL);
+  ArMmaWs w = carve_ar_mma(c, B, T, ws, ws_bytes);
+  if (!ws || w.bytes > ws_bytes) return srwn_fail(SRWN_ERR_WORKSPACE, "workspace too small: need %zu bytes", w.bytes);
+  const int L = c->cfg.n_layers, frames = T / c->cfg.pool_stride;
+  SRWN_CUDA(cudaMemsetAsync(w.queues, 0, (size_t)w.grid * c->sum_dilation * armma::kSlotBytes, st));   // zero padding of ops.py:9
+  SRWN_CUDA(cudaMemsetAsync(w.err, 0, 16, st));
+  const float* sw = stack_w(c, 0);
+  k_cond<<<B * frames, 256, 0, st>>>(enc, sw + c->off.cond_k, sw + c->off.cond_b, w.cond, B * frames, L, c->cfg.cond_channels);
+  SRWN_LAUNCH_CHECK();
+  fused::k_fold_bias<<<B * frames, 256, 0, st>>>(w.cond, sw + c->off.front_b, sw + c->off.res_b, w.cb, L);
+  SRWN_LAUNCH_CHECK();
+  armma::Params p;
+  memset(&p, 0, sizeof(p));
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(c->d_ar_packed);
+  p.chain_w = img;
+  p.stream = img + (size_t)L * armma::kChainLayerBytes;
+  p.fixed = reinterpret_cast<const float*>(p.stream + (size_t)(L + 5) * armma::kItemBytes);
+  p.cb = w.cb; p.queues = w.queues; p.u1 = u1; p.u2 = u2; p.x_out = x_out; p.logits_out = logits_out; p.err = w.err;
+  p.B = B; p.T = T; p.L = L; p.P = c->cfg.pool_stride; p.frames = frames; p.M = c->cfg.num_mixtures;
+  bool pow2 = true;
+  int off = 0;
+  for (int l = 0; l < L; l++) {
+    p.dil[l] = c->dilations[l]; p.qoff[l] = off; off += c->dilations[l];
+    if (c->dilations[l] & (c->dilations[l] - 1)) pow2 = false;
+  }
+  p.sum_d = pow2 ? -c->sum_dilation : c->sum_dilation;
+  SRWN_CUDA(cudaFuncSetAttribute(armma::k_ar_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, armma::Smem::total));
+  ProfScope prof(c, st, "k_ar_mma", 1);
+  armma::k_ar_mma<<<w.grid, armma::kThreads, armma::Smem::total, st>>>(p);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+int ar_mma_check_error(const srwn_ctx* c, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st) {
+  ArMmaWs w = carve_ar_mma(c, B, T, ws, ws_bytes);
+  int flag = 0;
+  SRWN_CUDA(cudaStreamSynchronize(st));
+  SRWN_CUDA(cudaMemcpy(&flag, w.err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) return srwn_fail(SRWN_ERR_CUDA, "generation kernel aborted: pipeline wait timed out");
+  return SRWN_OK;
+}

@@ -70,6 +70,7 @@ struct srwn_ctx {
   // packed bf16 operand images for the tcgen05 path (built at commit)
   void* d_packed;
   size_t packed_bytes;
+  void* d_ar_packed;                  // fragment-ordered fp16 weights of the tensor-core generation kernel (built at commit)
   // optional timing of the dominant kernel(s) of the last call (srwn_set_profiling)
   int profiling;
   cudaEvent_t prof_ev[2];
@@ -123,6 +124,13 @@ size_t ar_workspace_bytes(const srwn_ctx* c, int B, int T);
 int run_ar_generate(srwn_ctx* c, const float* enc, const float* u1, const float* u2,
                     float* x_out, float* logits_out, int B, int T, void* ws, size_t ws_bytes,
                     cudaStream_t st);
+// ar_mma.cu
+bool ar_mma_supported(const srwn_ctx* c);
+int ar_mma_pack_weights(srwn_ctx* c, cudaStream_t st);
+size_t ar_mma_workspace_bytes(const srwn_ctx* c, int B, int T);
+int run_ar_mma(srwn_ctx* c, const float* enc, const float* u1, const float* u2, float* x_out,
+               float* logits_out, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st);
+int ar_mma_check_error(const srwn_ctx* c, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st);
 // fused_bf16.cu
 bool fused_supported(const srwn_ctx* c);
 size_t fused_packed_bytes(const srwn_ctx* c);

@@ -299,10 +299,12 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         return out
 
     def generate(self, encoding, conditions=None, u1=None, u2=None, num_samples=None,
-                 return_logits=False, zero_last=False):
+                 return_logits=False, zero_last=False, precision="fp32"):
         """Autoregressive generation, the queue-based restatement of teacher.py:153-170:
         x[t] = clip(MoL_sample(logits_t)) with logits_t from x[<t] and encoding[t // pool_stride].
-        ``zero_last=True`` reproduces teacher.py:170, which zeroes the final sample."""
+        ``zero_last=True`` reproduces teacher.py:170, which zeroes the final sample.
+        ``precision``: "fp32" (parity-grade FFMA kernel) or "fp16" (tensor-core kernel, fp16 operands
+        and queue state, fp32 accumulate / residual stream)."""
         eng = self._eng
         enc = _with_conditions(encoding, conditions, self.condition_size)
         e, on_dev = eng.to_device(enc, "enc")
@@ -313,13 +315,18 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         u1 = torch.rand(B, T, self.num_mixtures, device="cuda") * (hi - lo) + lo if u1 is None \
             else eng.to_device(u1, "u1")[0]
         u2 = torch.rand(B, T, device="cuda") * (hi - lo) + lo if u2 is None else eng.to_device(u2, "u2")[0]
-        ws, wsn = eng.workspace(_lib.OP_TEACHER_GENERATE, B, T, _lib.FP32)
+        prec = _lib.PRECISIONS[precision]
+        if not eng.lib.srwn_supports(eng.h, _lib.OP_TEACHER_GENERATE, prec):
+            raise RuntimeError("generate(precision=%r) is not supported for this configuration" % precision)
+        ws, wsn = eng.workspace(_lib.OP_TEACHER_GENERATE, B, T, prec)
         x = torch.empty(B, T, dtype=torch.float32, device="cuda")
         logits = torch.empty(B, T, 4 * self.num_mixtures, dtype=torch.float32, device="cuda") \
             if return_logits else None
         _lib.check(eng.lib.srwn_teacher_generate(eng.h, e.data_ptr(), u1.data_ptr(), u2.data_ptr(),
                                                  x.data_ptr(), logits.data_ptr() if return_logits else None,
-                                                 B, T, ws, wsn, _stream()))
+                                                 B, T, prec, ws, wsn, _stream()))
+        if prec != _lib.FP32:
+            eng.check_async(_lib.OP_TEACHER_GENERATE, B, T, prec)
         if zero_last:
             x[:, T - 1:] = 0            # teacher.py:170
         if return_logits:

@@ -195,6 +195,47 @@ def test_generate_self_consistency_long(srwn):
     assert x.min() >= -1 and x.max() <= 1
 
 
+def _mixture_index(logits, u1, M):
+    """ops.py:187: Gumbel-argmax over the mixture logits."""
+    return np.argmax(logits[..., :M] - np.log(-np.log(u1)), axis=-1)
+
+
+@pytest.mark.parametrize("cfg", ["default", "small"])
+def test_generate_fp16_tensor_core_path(srwn, cfg):
+    """Tensor-core generation kernel (fp16 operands + fp16 queue state, fp32 accumulate / stream).
+    (1) against the oracle's queue restatement on the prefix where both pick the same mixture component
+    (a flipped near-tie legitimately forks the trajectory): <= 2e-2 max-abs on logits and audio;
+    (2) size-independent property: teacher-forcing the generated audio through the fp32 path reproduces
+    the logits the generator saw (<= 1e-2, the fp16 operand bound) and the same mixture choices."""
+    if cfg == "default":
+        dil, C, M, P, B, T = synth.DEFAULT_DILATIONS, 32, 5, 128, 11, 512
+    else:
+        dil, C, M, P, B, T = [1, 2, 4, 8, 3, 5], 8, 3, 64, 3, 256
+    t, w = _teacher(srwn, dil, C=C, M=M, P=P, seed=7)
+    if not srwn._lib.load().srwn_supports(t._eng.h, srwn._lib.OP_TEACHER_GENERATE, srwn._lib.FP16):
+        pytest.skip("fp16 generation kernel does not cover this configuration")
+    enc = synth.synthetic_encoding(B, T // P, channels=C)
+    u1, u2 = synth.sampler_uniforms(B, T, num_mixtures=M)
+    x, lg = t.generate(enc, u1=u1, u2=u2, return_logits=True, precision="fp16")
+    assert x.min() >= -1 and x.max() <= 1 and np.isfinite(lg).all()
+    # (2) self-consistency through the fp32 teacher-forced path
+    tf_logits = t.get_logits(x, enc, precision="fp32")
+    assert np.abs(tf_logits - lg).max() <= 1e-2
+    k_ar, k_tf = _mixture_index(lg, u1, M), _mixture_index(tf_logits, u1, M)
+    assert (k_ar == k_tf).mean() >= 0.995
+    # (1) oracle prefix
+    Tq = min(T, 256)
+    ref_x, ref_lg = orc.queue_ar(f64(w), enc.astype(np.float64), dil, P, M, u1.astype(np.float64),
+                                 u2.astype(np.float64), Tq, return_logits=True)
+    k_ref = _mixture_index(ref_lg, u1[:, :Tq], M)
+    for b in range(B):
+        same = k_ref[b] == k_ar[b, :Tq]
+        n = Tq if same.all() else int(np.argmin(same))
+        assert n >= 32, "trajectory forked after %d steps" % n
+        assert np.abs(lg[b, :n] - ref_lg[b, :n]).max() <= 2e-2
+        assert np.abs(x[b, :n] - ref_x[b, :n]).max() <= 2e-2
+
+
 def test_student_golden_small(srwn, golden_small):
     g = golden_small
     dil = [int(d) for d in g["dilations"]]
