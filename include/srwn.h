@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SRWN_ABI_VERSION 2
+#define SRWN_ABI_VERSION 3
 
 enum srwn_status {
   SRWN_OK = 0,
@@ -58,7 +58,8 @@ enum srwn_op {               /* argument of srwn_workspace_bytes */
   SRWN_OP_TEACHER_LOGITS = 0,
   SRWN_OP_TEACHER_NLL = 1,
   SRWN_OP_TEACHER_GENERATE = 2,
-  SRWN_OP_STUDENT_FORWARD = 3
+  SRWN_OP_STUDENT_FORWARD = 3,
+  SRWN_OP_STUDENT_TRAIN = 4    /* workspace of srwn_student_forward_train + srwn_student_backward */
 };
 
 /* Constructor arguments of WaveNetAutoEncoder (model.py:76-77) / ParallelWaveNet
@@ -147,6 +148,37 @@ int srwn_student_forward(srwn_handle_t h, const float* z, const float* enc, floa
                          float* s_tot, float* mu_tot, float* x_last,
                          int32_t B, int32_t T, int32_t precision,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- student distillation step (model.py:356-401, student.py:107 train_fast) ------------------
+ * The reference builds one graph: student forward, loss (teacher cross-entropy of the student's
+ * samples - alpha * entropy + gamma * spectral power loss) / B, gradients, clip_by_global_norm(1),
+ * Adam.  Here the device side is four calls; the host glue (model.py mirror) supplies the loss
+ * gradients between them and the NCCL all-reduce of `grads` across ranks before srwn_adam_step:
+ *   1. srwn_student_forward_train: fp32 forward that keeps every layer input in `workspace`
+ *      (size: srwn_workspace_bytes(op = SRWN_OP_STUDENT_TRAIN)); out/s_tot/mu_tot [B,T].
+ *   2. caller: d_pre = dLoss/d(z*s_tot + mu_tot) [B,T] (zero where model.py:535 clips) and
+ *      d_s_extra = dLoss/ds_tot from terms that use s_tot directly (the entropy, model.py:356).
+ *      srwn_mol_loss_grad gives d(-log p)/dx of ops.py:124-175 for fixed logits.
+ *   3. srwn_student_backward: gradients of every student variable into `grads`, a flat fp32
+ *      buffer of srwn_param_count() elements laid out like the weight arena
+ *      (srwn_weight_offset(name) locates a variable); same workspace as step 1.
+ *   4. srwn_adam_step: tf.clip_by_global_norm(clip) + tf.train.AdamOptimizer update of the
+ *      device weights (m, v: caller-owned fp32 state of srwn_param_count() elements, zeroed at
+ *      start; step counts from 1; scratch: 1 float).  Call srwn_commit_weights afterwards before
+ *      using the 16-bit paths (their packed operand images are rebuilt from the device weights). */
+int srwn_param_count(srwn_handle_t h, int64_t* count);
+int srwn_weight_offset(srwn_handle_t h, const char* name, int64_t* offset, int64_t* count);
+int srwn_student_forward_train(srwn_handle_t h, const float* z, const float* enc, float* out,
+                               float* s_tot, float* mu_tot, int32_t B, int32_t T,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int srwn_student_backward(srwn_handle_t h, const float* z, const float* enc, const float* d_pre,
+                          const float* d_s_extra, float* grads, int32_t B, int32_t T,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int srwn_mol_loss_grad(const float* x, const float* l, float* dx, float* nll_out,
+                       int32_t B, int32_t T, int32_t M, void* stream);
+int srwn_adam_step(srwn_handle_t h, const float* grads, float* m, float* v, float* scratch,
+                   float clip_norm, float lr, float beta1, float beta2, float eps, int32_t step,
+                   void* stream);
 
 /* ---- stateless ops (ops.py) ----------------------------------------------------- */
 /* _DilatedCausalConv1d / DilatedCausalConv1d (ops.py:6-20): x [B,T,Cin],

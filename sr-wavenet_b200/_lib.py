@@ -8,11 +8,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRWN_LIB") or os.path.join(_HERE, "libsrwn.so")   # SRWN_LIB: tuning builds (tools/exp_build.sh)
 
-ABI_VERSION = 2      # SRWN_ABI_VERSION in include/srwn.h
+ABI_VERSION = 3      # SRWN_ABI_VERSION in include/srwn.h
 OK, ERR_INVALID, ERR_CUDA, ERR_WEIGHTS, ERR_UNSUPPORTED, ERR_WORKSPACE = range(6)
 TEACHER, STUDENT = 0, 1
 FP32, BF16, FP16 = 0, 1, 2
-OP_TEACHER_LOGITS, OP_TEACHER_NLL, OP_TEACHER_GENERATE, OP_STUDENT_FORWARD = range(4)
+OP_TEACHER_LOGITS, OP_TEACHER_NLL, OP_TEACHER_GENERATE, OP_STUDENT_FORWARD, OP_STUDENT_TRAIN = range(5)
 PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
 
 
@@ -53,6 +53,13 @@ SIGNATURES = {
     "srwn_teacher_nll": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "srwn_teacher_generate": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "srwn_student_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_param_count": (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
+    "srwn_weight_offset": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "srwn_student_forward_train": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_student_backward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_mol_loss_grad": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp]),
+    "srwn_adam_step": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                      ctypes.c_float, ctypes.c_float, _i32, _vp]),
     "srwn_dilated_causal_conv1d": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "srwn_residual_dilation_layer": (ctypes.c_int, [_fp] * 9 + [_i32] * 6 + [_vp]),
     "srwn_right_shift": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),

@@ -181,7 +181,7 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
   if (cfg->kind == SRWN_STUDENT) { c->cfg.skip_channels = cfg->skip_channels > 0 ? cfg->skip_channels : kS; c->cfg.num_mixtures = 0; }
   c->n_stacks = cfg->kind == SRWN_TEACHER ? 1 : cfg->num_flows;
   c->device = dev;
-  c->committed = false;
+  c->committed = false; c->device_dirty = false;
   c->d_weights = nullptr; c->d_dilations = nullptr; c->d_queue_off = nullptr;
   c->d_packed = nullptr; c->packed_bytes = 0; c->d_ar_packed = nullptr;
   c->profiling = 0; c->prof_launches = 0; c->prof_name = "";
@@ -281,6 +281,12 @@ const float* srwn_host_weights(srwn_ctx* c) { return mirror(c)->w.data(); }
 
 extern "C" int srwn_commit_weights(srwn_handle_t h, void* stream) {
   if (!h) return srwn_fail(SRWN_ERR_INVALID, "srwn_commit_weights: null handle");
+  if (h->device_dirty) {     // training steps updated the device copy: refresh the host mirror the packers read
+    SRWN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    SRWN_CUDA(cudaMemcpy(mirror(h)->w.data(), h->d_weights, (size_t)h->n_stacks * h->stack_floats * sizeof(float),
+                         cudaMemcpyDeviceToHost));
+    h->device_dirty = false;
+  }
   static const VarKind kinds[] = {V_FRONT_K, V_FRONT_B, V_HEAD1_K, V_HEAD1_B, V_HEAD2_K, V_HEAD2_B};
   for (int s = 0; s < h->n_stacks; s++) {
     for (VarKind k : kinds)
@@ -381,6 +387,7 @@ extern "C" int srwn_check_async_error(srwn_handle_t h, int32_t op, int32_t B, in
 extern "C" int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision) {
   if (!h) return 0;
   const bool teacher_op = op == SRWN_OP_TEACHER_LOGITS || op == SRWN_OP_TEACHER_NLL || op == SRWN_OP_TEACHER_GENERATE;
+  if (op == SRWN_OP_STUDENT_TRAIN) return h->cfg.kind == SRWN_STUDENT && precision == SRWN_FP32 ? 1 : 0;
   if (teacher_op != (h->cfg.kind == SRWN_TEACHER) || op < 0 || op > SRWN_OP_STUDENT_FORWARD) return 0;
   if (precision == SRWN_FP32) return 1;
   if (op == SRWN_OP_TEACHER_GENERATE) return precision == SRWN_FP16 && ar_mma_supported(h) ? 1 : 0;
@@ -408,6 +415,11 @@ extern "C" int srwn_workspace_bytes(srwn_handle_t h, int32_t op, int32_t B, int3
       *bytes = precision != SRWN_FP32 ? fused_workspace_bytes(h, op, B, T)
                                       : carve_f32(h, op, B, T, nullptr, 0, false).bytes;
       return SRWN_OK;
+  }
+  if (op == SRWN_OP_STUDENT_TRAIN) {
+    if (h->cfg.kind != SRWN_STUDENT) return srwn_fail(SRWN_ERR_INVALID, "not a student handle");
+    *bytes = train_workspace_bytes(h, B, T);
+    return SRWN_OK;
   }
   return srwn_fail(SRWN_ERR_INVALID, "unknown op %d", op);
 }
@@ -506,4 +518,61 @@ extern "C" int srwn_student_forward(srwn_handle_t h, const float* z, const float
     xin = xout;
   }
   return run_flow_compose(z, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
+}
+
+// ---- student distillation step (model.py:356-401) ----------------------------------------------
+extern "C" int srwn_param_count(srwn_handle_t h, int64_t* count) {
+  if (!h || !count) return srwn_fail(SRWN_ERR_INVALID, "srwn_param_count: null argument");
+  *count = (int64_t)h->n_stacks * (int64_t)h->stack_floats;
+  return SRWN_OK;
+}
+
+extern "C" int srwn_weight_offset(srwn_handle_t h, const char* name, int64_t* offset, int64_t* count) {
+  if (!h || !name || !offset || !count) return srwn_fail(SRWN_ERR_INVALID, "srwn_weight_offset: null argument");
+  VarRef r = parse_name(h, name);
+  if (r.kind == V_BAD || r.kind == V_DEAD)
+    return srwn_fail(SRWN_ERR_WEIGHTS, "variable '%s' is not stored (unknown or dead)", name);
+  int64_t want[3]; int nd; size_t off, cnt;
+  if (!var_layout(h, r.kind, r.layer, want, &nd, &off, &cnt))
+    return srwn_fail(SRWN_ERR_WEIGHTS, "variable '%s' does not exist in this model kind", name);
+  *offset = (int64_t)((size_t)r.stack * h->stack_floats + off);
+  *count = (int64_t)cnt;
+  return SRWN_OK;
+}
+
+extern "C" int srwn_student_forward_train(srwn_handle_t h, const float* z, const float* enc, float* out,
+                                          float* s_tot, float* mu_tot, int32_t B, int32_t T, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  if (!h || !z || !enc || !out) return srwn_fail(SRWN_ERR_INVALID, "srwn_student_forward_train: null argument");
+  if (h->cfg.kind != SRWN_STUDENT) return srwn_fail(SRWN_ERR_INVALID, "not a student handle");
+  int rc = check_bt(h, B, T);
+  if (rc) return rc;
+  return run_student_forward_train(h, z, enc, out, s_tot, mu_tot, B, T, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int srwn_student_backward(srwn_handle_t h, const float* z, const float* enc, const float* d_pre,
+                                     const float* d_s_extra, float* grads, int32_t B, int32_t T, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (!h || !z || !enc || !d_pre || !grads) return srwn_fail(SRWN_ERR_INVALID, "srwn_student_backward: null argument");
+  if (h->cfg.kind != SRWN_STUDENT) return srwn_fail(SRWN_ERR_INVALID, "not a student handle");
+  if (h->cfg.num_flows > 16) return srwn_fail(SRWN_ERR_UNSUPPORTED, "backward supports up to 16 flows");
+  int rc = check_bt(h, B, T);
+  if (rc) return rc;
+  return run_student_backward(h, z, enc, d_pre, d_s_extra, grads, B, T, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int srwn_mol_loss_grad(const float* x, const float* l, float* dx, float* nll_out, int32_t B, int32_t T,
+                                  int32_t M, void* stream) {
+  if (!x || !l || !dx) return srwn_fail(SRWN_ERR_INVALID, "srwn_mol_loss_grad: null argument");
+  if (B < 1 || T < 1 || M < 1 || M > 8) return srwn_fail(SRWN_ERR_INVALID, "srwn_mol_loss_grad: bad B/T/M");
+  return run_mol_nll_grad(x, l, dx, nll_out, B, T, M, (cudaStream_t)stream);
+}
+
+extern "C" int srwn_adam_step(srwn_handle_t h, const float* grads, float* m, float* v, float* scratch, float clip_norm,
+                              float lr, float beta1, float beta2, float eps, int32_t step, void* stream) {
+  if (!h || !grads || !m || !v || !scratch) return srwn_fail(SRWN_ERR_INVALID, "srwn_adam_step: null argument");
+  if (step < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_adam_step: step counts from 1");
+  if (!h->committed) return srwn_fail(SRWN_ERR_WEIGHTS, "weights not committed (srwn_commit_weights)");
+  h->device_dirty = true;
+  return run_adam(h, grads, m, v, scratch, clip_norm, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
 }

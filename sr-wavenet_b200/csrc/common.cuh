@@ -65,6 +65,7 @@ struct srwn_ctx {
   int sum_dilation;                   // sum of dilations (queue rows per utterance)
   int32_t* d_queue_off;               // [L] prefix sums of dilations
   bool committed;
+  bool device_dirty;                  // device weights changed by srwn_adam_step: host mirror and packed images are stale
   int device;
   int sm_count;
   // packed bf16 operand images for the tcgen05 path (built at commit)
@@ -124,6 +125,15 @@ size_t ar_workspace_bytes(const srwn_ctx* c, int B, int T);
 int run_ar_generate(srwn_ctx* c, const float* enc, const float* u1, const float* u2,
                     float* x_out, float* logits_out, int B, int T, void* ws, size_t ws_bytes,
                     cudaStream_t st);
+// train_f32.cu
+size_t train_workspace_bytes(const srwn_ctx* c, int B, int T);
+int run_student_forward_train(srwn_ctx* c, const float* z, const float* enc, float* out, float* s_tot,
+                              float* mu_tot, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st);
+int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const float* d_pre, const float* d_s_extra,
+                         float* grads, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st);
+int run_mol_nll_grad(const float* x, const float* l, float* dx, float* nll, int B, int T, int M, cudaStream_t st);
+int run_adam(srwn_ctx* c, const float* grads, float* m, float* v, float* scratch1, float clip, float lr, float b1, float b2,
+             float eps, int step, cudaStream_t st);
 // ar_mma.cu
 bool ar_mma_supported(const srwn_ctx* c);
 int ar_mma_pack_weights(srwn_ctx* c, cudaStream_t st);

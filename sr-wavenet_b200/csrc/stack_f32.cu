@@ -233,6 +233,35 @@ int run_stack_f32(srwn_ctx* c, int stack, const float* xin, const float* enc, in
   return SRWN_OK;
 }
 
+// Same stack (student: no skip conv), keeping every layer input for the backward pass (train_f32.cu):
+// acts [L+1][B][T][R], acts[l] = block input of layer l, acts[L] = stack output.
+int run_stack_f32_acts(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T,
+                       float* acts, float* cond, cudaStream_t st) {
+  const float* w = stack_w(c, stack);
+  const StackOffsets& o = c->off;
+  const int L = c->cfg.n_layers, P = c->cfg.pool_stride, C = c->cfg.cond_channels;
+  const int frames = T / P;
+  const size_t n = (size_t)B * T;
+  k_cond<<<B * frames, 256, 0, st>>>(enc, w + o.cond_k, w + o.cond_b, cond, B * frames, L, C);
+  SRWN_LAUNCH_CHECK();
+  {
+    dim3 grid((unsigned)(((int64_t)T * kR + 255) / 256), B);
+    k_front<<<grid, 256, 0, st>>>(xin, w + o.front_k, w + o.front_b, cond, acts, T, P, L, frames);
+    SRWN_LAUNCH_CHECK();
+  }
+  SRWN_CUDA(cudaFuncSetAttribute(k_layer_f32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LayerSmem)));
+  dim3 grid((T + kTT - 1) / kTT, B);
+  for (int l = 0; l < L; l++) {
+    const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
+    k_layer_f32<false><<<grid, 256, sizeof(LayerSmem), st>>>(
+        acts + (size_t)l * n * kR, acts + (size_t)(l + 1) * n * kR, nullptr, w + o.filt_k + (size_t)l * 2 * kR * kR,
+        w + o.filt_b + (size_t)l * kR, w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR, nullptr, nullptr,
+        cond_next, T, c->dilations[l], P, L, frames, 0);
+    SRWN_LAUNCH_CHECK();
+  }
+  return SRWN_OK;
+}
+
 // ---- teacher head: relu -> 1x1 S->S -> relu -> 1x1 S->4M (model.py:191-196) ------------
 constexpr int kHT = 64;
 __global__ void __launch_bounds__(256)

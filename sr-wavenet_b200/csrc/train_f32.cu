@@ -1,0 +1,551 @@
+// Student distillation step, device side (fp32): forward that keeps every layer input, and the backward pass
+// of the IAF flows (model.py:415-535) given the gradient of the loss (model.py:356-379) with respect to the
+// network output.  Layer-at-a-time FFMA kernels; activations and their gradients round-trip HBM in fp32.
+//
+//   forward (per flow f):  x_0 = front(x_{f-1}) + cond_0;  x_{l+1} = (x_l + Wr c_l + br) sqrt(1/2) + cond_{l+1},
+//                          c_l = f sigmoid(f), f = tanh(W0 x_l[t-d] + W1 x_l[t] + bf)          (ops.py:23-46, F1-F3)
+//                          p = relu(x_L) Wh + bh;  s_f = exp(p0), mu_f = p1, x_f = x_{f-1} s_f + mu_f (model.py:479-482)
+//   compose:               S = prod s_f,  M = sum_f mu_f prod_{j>f} s_j,  out = clip(z S + M)   (model.py:517-535)
+//   backward:              reverse of the above; weight gradients are reduced per CTA (registers -> one partial
+//                          row per CTA) and summed by a second kernel in a fixed order (deterministic).
+#include "common.cuh"
+#include "mol.cuh"
+
+__global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
+                       const float* __restrict__ cond_b, float* __restrict__ cond,
+                       int frames_total, int L, int C);
+__global__ void k_front(const float* __restrict__ x, const float* __restrict__ fk,
+                        const float* __restrict__ fb, const float* __restrict__ cond,
+                        float* __restrict__ hc, int T, int P, int L, int frames);
+int run_stack_f32_acts(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T,
+                       float* acts, float* cond, cudaStream_t st);
+
+namespace train {
+
+constexpr int kTT = 64;             // time steps per tile
+constexpr int kAP = kR + 4;         // padded pitch
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- gate backward ------------------------------------------------------------------------------------
+// g = dL/dx_{l+1}; recomputes a, f, c from x_l; writes da = dL/da; accumulates dWr [32][32], dbr [32].
+struct GateSmem {
+  float a_tap[kTT][kAP], a_cur[kTT][kAP], c[kTT][kAP], g[kTT][kAP];
+  float wf[2 * kR][kR], wr[kR][kR + 1], bf[kR];
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float* __restrict__ da_out,
+           const float* __restrict__ filt_k, const float* __restrict__ filt_b, const float* __restrict__ res_k,
+           float* __restrict__ partial,            // [gridDim.x][kR*kR + kR]: dWr | dbr
+           int B, int T, int d) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GateSmem& s = *reinterpret_cast<GateSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2 * kR * kR; i += kThreads) (&s.wf[0][0])[i] = filt_k[i];
+  for (int i = tid; i < kR * kR; i += kThreads) s.wr[i / kR][i % kR] = res_k[i];
+  if (tid < kR) s.bf[tid] = filt_b[tid];
+  const int tiles_per_b = (T + kTT - 1) / kTT;
+  const int n_tiles = B * tiles_per_b;
+  float gw[4] = {0.f, 0.f, 0.f, 0.f};      // dWr[warp*4 + i][lane]
+  float gb = 0.f;                          // dbr[lane] (warp 0)
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
+    const float* xb = x_l + (size_t)b * T * kR;
+    const float* gbp = g_in + (size_t)b * T * kR;
+    __syncthreads();
+    for (int i = tid; i < kTT * (kR / 4); i += kThreads) {
+      const int row = i / (kR / 4), q = i % (kR / 4);
+      const int t = t0 + row;
+      float4 cur = make_float4(0, 0, 0, 0), tap = cur, gg = cur;
+      if (t < T) {
+        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + q * 4);
+        gg = *reinterpret_cast<const float4*>(gbp + (size_t)t * kR + q * 4);
+        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + q * 4);
+      }
+      gg.x *= SRWN_SQRT_HALF; gg.y *= SRWN_SQRT_HALF; gg.z *= SRWN_SQRT_HALF; gg.w *= SRWN_SQRT_HALF;   // dres
+      *reinterpret_cast<float4*>(&s.a_cur[row][q * 4]) = cur;
+      *reinterpret_cast<float4*>(&s.a_tap[row][q * 4]) = tap;
+      *reinterpret_cast<float4*>(&s.g[row][q * 4]) = gg;
+    }
+    __syncthreads();
+    const int r0 = warp * 8;               // rows r0..r0+7, lane = channel
+    float acc[8], fv[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = s.bf[lane];
+#pragma unroll 4
+    for (int k = 0; k < kR; k++) {
+      const float w0 = s.wf[k][lane], w1 = s.wf[kR + k][lane];
+#pragma unroll
+      for (int r = 0; r < 8; r++) acc[r] = fmaf(s.a_tap[r0 + r][k], w0, fmaf(s.a_cur[r0 + r][k], w1, acc[r]));
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      fv[r] = tanhf(acc[r]);
+      s.c[r0 + r][lane] = fv[r] * sigmoidf_(fv[r]);
+    }
+    // dc[k] = sum_n Wr[k][n] dres[n]   (lane = k)
+    float dc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) dc[r] = 0.f;
+#pragma unroll 4
+    for (int n = 0; n < kR; n++) {
+      const float w = s.wr[lane][n];
+#pragma unroll
+      for (int r = 0; r < 8; r++) dc[r] = fmaf(s.g[r0 + r][n], w, dc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int t = t0 + r0 + r;
+      const float f = fv[r], sg = sigmoidf_(f);
+      const float df = dc[r] * (sg + f * sg * (1.f - sg));        // d(f sigmoid(f))/df
+      const float da = df * (1.f - f * f);                        // tanh'
+      if (t < T) da_out[((size_t)b * T + t) * kR + lane] = da;
+    }
+    __syncthreads();
+    // dWr[k][n] += sum_t c[t][k] dres[t][n]; dbr[n] += sum_t dres[t][n]   (rows past T hold zeros in g)
+    for (int t = 0; t < kTT; t++) {
+      const float gn = s.g[t][lane];
+#pragma unroll
+      for (int i = 0; i < 4; i++) gw[i] = fmaf(s.c[t][warp * 4 + i], gn, gw[i]);
+      if (warp == 0) gb += gn;
+    }
+  }
+  float* pp = partial + (size_t)blockIdx.x * (kR * kR + kR);
+#pragma unroll
+  for (int i = 0; i < 4; i++) pp[(warp * 4 + i) * kR + lane] = gw[i];
+  if (warp == 0) pp[kR * kR + lane] = gb;
+}
+
+// ---- conv backward ------------------------------------------------------------------------------------
+// dx_l[t] = g[t] sqrt(1/2) + da[t] W1^T + da[t+d] W0^T;  dWf0 += x_l[t-d]^T da[t], dWf1 += x_l[t]^T da[t],
+// dbf += sum da;  dcond_l[b][t/P] += dx_l[t] (one tile lies inside one latent frame when P % 64 == 0, else atomics).
+struct ConvSmem {
+  float a_tap[kTT][kAP], a_cur[kTT][kAP], da[kTT][kAP], da_f[kTT][kAP];
+  float w0t[kR][kR + 1], w1t[kR][kR + 1];      // transposed: [n][k]
+  float red[8][kR];
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const float* __restrict__ da_in,
+           float* __restrict__ dx_out, const float* __restrict__ filt_k,
+           float* __restrict__ partial,            // [gridDim.x][2*kR*kR + kR]: dWf | dbf
+           float* __restrict__ dcond,              // [B][frames][kR] for this layer (zero-initialised), atomics
+           int B, int T, int d, int P, int frames) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kR * kR; i += kThreads) {
+    const int k = i / kR, n = i % kR;
+    s.w0t[n][k] = filt_k[i];
+    s.w1t[n][k] = filt_k[kR * kR + i];
+  }
+  const int tiles_per_b = (T + kTT - 1) / kTT;
+  const int n_tiles = B * tiles_per_b;
+  float gw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // dWf[warp*8 + i][lane] over the 64 stacked input rows
+  float gb = 0.f;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
+    const float* xb = x_l + (size_t)b * T * kR;
+    const float* db = da_in + (size_t)b * T * kR;
+    __syncthreads();
+    for (int i = tid; i < kTT * (kR / 4); i += kThreads) {
+      const int row = i / (kR / 4), q = i % (kR / 4);
+      const int t = t0 + row;
+      float4 cur = make_float4(0, 0, 0, 0), tap = cur, a = cur, af = cur;
+      if (t < T) {
+        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + q * 4);
+        a = *reinterpret_cast<const float4*>(db + (size_t)t * kR + q * 4);
+        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + q * 4);
+        if (t + d < T) af = *reinterpret_cast<const float4*>(db + (size_t)(t + d) * kR + q * 4);
+      }
+      *reinterpret_cast<float4*>(&s.a_cur[row][q * 4]) = cur;
+      *reinterpret_cast<float4*>(&s.a_tap[row][q * 4]) = tap;
+      *reinterpret_cast<float4*>(&s.da[row][q * 4]) = a;
+      *reinterpret_cast<float4*>(&s.da_f[row][q * 4]) = af;
+    }
+    __syncthreads();
+    const int r0 = warp * 8;
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = 0.f;
+    // dx[t][k = lane] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]
+#pragma unroll 4
+    for (int n = 0; n < kR; n++) {
+      const float w1 = s.w1t[n][lane], w0 = s.w0t[n][lane];
+#pragma unroll
+      for (int r = 0; r < 8; r++) acc[r] = fmaf(s.da[r0 + r][n], w1, fmaf(s.da_f[r0 + r][n], w0, acc[r]));
+    }
+    float csum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int t = t0 + r0 + r;
+      if (t < T) {
+        const size_t at = ((size_t)b * T + t) * kR + lane;
+        const float v = fmaf(g_in[at], SRWN_SQRT_HALF, acc[r]);
+        dx_out[at] = v;
+        if (P % kTT == 0) csum += v;
+        else atomicAdd(dcond + ((size_t)b * frames + t / P) * kR + lane, v);
+      }
+    }
+    if (P % kTT == 0) {
+      s.red[warp][lane] = csum;
+      __syncthreads();
+      if (warp == 0 && t0 < T) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += s.red[w][lane];
+        atomicAdd(dcond + ((size_t)b * frames + t0 / P) * kR + lane, tot);
+      }
+    }
+    // dWf[k][n] += sum_t A[t][k] da[t][n] with A = [tap | cur] (rows past T hold zeros in da)
+    for (int t = 0; t < kTT; t++) {
+      const float an = s.da[t][lane];
+      const float* arow = warp < 4 ? &s.a_tap[t][warp * 8] : &s.a_cur[t][(warp - 4) * 8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) gw[i] = fmaf(arow[i], an, gw[i]);
+      if (warp == 0) gb += an;
+    }
+  }
+  float* pp = partial + (size_t)blockIdx.x * (2 * kR * kR + kR);
+#pragma unroll
+  for (int i = 0; i < 8; i++) pp[(warp * 8 + i) * kR + lane] = gw[i];
+  if (warp == 0) pp[2 * kR * kR + lane] = gb;
+}
+
+// sums `rows` partial rows (row pitch `pitch`) of width `w` into dst (+=), one thread per column, fixed order
+__global__ void k_reduce_partials(const float* __restrict__ partial, int rows, int pitch, int w, float* __restrict__ dst) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= w) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; r++) acc += partial[(size_t)r * pitch + j];
+  dst[j] += acc;
+}
+
+// ---- flow head backward (model.py:451-452, 479-482) ---------------------------------------------------
+// inputs per sample: d_scale, d_mean (from the composition), d_xout (from the next flow's front conv), x_prev, scale;
+// outputs: d x_L [n][32], d x_prev (direct term) [n]; head weight gradients through per-CTA partials [64 + 2].
+__global__ void __launch_bounds__(256)
+k_bwd_flow_head(const float* __restrict__ h, const float* __restrict__ x_prev, const float* __restrict__ scale,
+                const float* __restrict__ d_scale, const float* __restrict__ d_mean, const float* __restrict__ d_xout,
+                const float* __restrict__ hk, float* __restrict__ dh, float* __restrict__ dx_prev,
+                float* __restrict__ partial, int64_t n) {
+  __shared__ float s_red[8][66];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float k0 = hk[lane * 2], k1 = hk[lane * 2 + 1];
+  float g0 = 0.f, g1 = 0.f, gb0 = 0.f, gb1 = 0.f;          // dW[lane][0..1], db
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
+    const float sc = scale[row];
+    const float dxo = d_xout ? d_xout[row] : 0.f;
+    const float ds = d_scale[row] + dxo * x_prev[row];      // x_f = x_{f-1} s_f + mu_f
+    const float dm = d_mean[row] + dxo;
+    const float dp0 = ds * sc, dp1 = dm;                    // s = exp(p0), mu = p1
+    const float hv = h[row * kR + lane];
+    const float e = fmaxf(hv, 0.f);
+    dh[row * kR + lane] = hv > 0.f ? fmaf(k0, dp0, k1 * dp1) : 0.f;
+    g0 = fmaf(e, dp0, g0); g1 = fmaf(e, dp1, g1);
+    if (lane == 0) { dx_prev[row] = dxo * sc; gb0 += dp0; gb1 += dp1; }
+  }
+  s_red[warp][lane * 2] = g0; s_red[warp][lane * 2 + 1] = g1;
+  if (lane == 0) { s_red[warp][64] = gb0; s_red[warp][65] = gb1; }
+  __syncthreads();
+  if (tid < 66) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; w++) tot += s_red[w][tid];
+    partial[(size_t)blockIdx.x * 66 + tid] = tot;
+  }
+}
+
+// ---- front backward (RightShift + K=2 causal conv on one channel, model.py:172-173/423-424) -------------
+// h_0[t][r] = x[t-2] k0[r] + x[t-1] k1[r] + b[r] + cond_0;  dx[t] = sum_r dh0[t+2][r] k0[r] + dh0[t+1][r] k1[r]
+__global__ void __launch_bounds__(256)
+k_bwd_front(const float* __restrict__ x_in, const float* __restrict__ dh0, const float* __restrict__ fk,
+            float* __restrict__ dx_in,                 // += (accumulates onto the direct term), may be null
+            float* __restrict__ partial,               // [gridDim.x][96]: dk0 | dk1 | db
+            int B, int T) {
+  __shared__ float s_red[8][96];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float k0 = fk[lane], k1 = fk[kR + lane];
+  float g0 = 0.f, g1 = 0.f, gb = 0.f;
+  const int64_t n = (int64_t)B * T;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
+    const int t = (int)(row % T);
+    const float dv = dh0[row * kR + lane];
+    const float xm2 = t >= 2 ? x_in[row - 2] : 0.f, xm1 = t >= 1 ? x_in[row - 1] : 0.f;
+    g0 = fmaf(xm2, dv, g0); g1 = fmaf(xm1, dv, g1); gb += dv;
+    if (dx_in) {
+      float v = (t + 2 < T ? dh0[(row + 2) * kR + lane] * k0 : 0.f) + (t + 1 < T ? dh0[(row + 1) * kR + lane] * k1 : 0.f);
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) dx_in[row] += v;
+    }
+  }
+  s_red[warp][lane] = g0; s_red[warp][32 + lane] = g1; s_red[warp][64 + lane] = gb;
+  __syncthreads();
+  if (tid < 96) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; w++) tot += s_red[w][tid];
+    partial[(size_t)blockIdx.x * 96 + tid] = tot;
+  }
+}
+
+// conditioning 1x1 (model.py:431): cond[bf][l][r] = enc[bf][:] Wc_l[:, r] + bc_l[r]
+// dWc_l[c][r] += sum_bf enc[bf][c] dcond_l[bf][r];  dbc_l[r] += sum_bf dcond_l[bf][r].   grid = L, block = 256
+__global__ void k_bwd_cond(const float* __restrict__ enc, const float* __restrict__ dcond,   // dcond [L][BF][32]
+                           float* __restrict__ dWc, float* __restrict__ dbc, int BF, int C) {
+  const int l = blockIdx.x;
+  const float* dl = dcond + (size_t)l * BF * kR;
+  for (int o = threadIdx.x; o < (C + 1) * kR; o += blockDim.x) {
+    const int c = o / kR, r = o % kR;
+    float acc = 0.f;
+    if (c < C) for (int bf = 0; bf < BF; bf++) acc = fmaf(enc[(size_t)bf * C + c], dl[(size_t)bf * kR + r], acc);
+    else for (int bf = 0; bf < BF; bf++) acc += dl[(size_t)bf * kR + r];
+    if (c < C) dWc[((size_t)l * C + c) * kR + r] += acc; else dbc[(size_t)l * kR + r] += acc;
+  }
+}
+
+// ---- composition backward (model.py:517-535) ----------------------------------------------------------
+// pre = z S + M;  given d_pre (already masked by the clip) and d_S_extra (entropy term): d s_f, d mu_f.
+__global__ void k_bwd_compose(const float* __restrict__ z, const float* __restrict__ scales, const float* __restrict__ means,
+                              const float* __restrict__ d_pre, const float* __restrict__ d_s_extra, int F,
+                              float* __restrict__ d_scales, float* __restrict__ d_means, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s[16], mu[16];
+  for (int f = 0; f < F; f++) { s[f] = scales[(size_t)f * n + i]; mu[f] = means[(size_t)f * n + i]; }
+  float S = 1.f;
+  for (int f = 0; f < F; f++) S *= s[f];
+  const float dM = d_pre[i];
+  const float dS = fmaf(dM, z[i], d_s_extra ? d_s_extra[i] : 0.f);
+  for (int f = 0; f < F; f++) {
+    float tail = 1.f;                                   // prod_{j>f} s_j
+    for (int j = f + 1; j < F; j++) tail *= s[j];
+    d_means[(size_t)f * n + i] = dM * tail;
+    float others = 1.f;                                 // S / s_f without dividing
+    for (int j = 0; j < F; j++) if (j != f) others *= s[j];
+    float acc = dS * others;
+    for (int k = 0; k < f; k++) {                       // mu_k prod_{j>k, j != f} s_j
+      float pr = mu[k];
+      for (int j = k + 1; j < F; j++) if (j != f) pr *= s[j];
+      acc = fmaf(dM, pr, acc);
+    }
+    d_scales[(size_t)f * n + i] = acc;
+  }
+}
+
+// ---- loss pieces ----------------------------------------------------------------------------------------
+// d/dx of the mixture-of-logistics negative log-likelihood (ops.py:124-175) for fixed logits; nll optional.
+__global__ void k_mol_nll_grad(const float* __restrict__ x, const float* __restrict__ l, float* __restrict__ dx,
+                               float* __restrict__ nll, int64_t n, int M) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float xv = x[i];
+  const float* lg = l + i * 4 * M;
+  float mx = lg[0];
+  for (int m = 1; m < M; m++) mx = fmaxf(mx, lg[m]);
+  float se = 0.f;
+  for (int m = 0; m < M; m++) se += expf(lg[m] - mx);
+  const float lse_p = mx + logf(se);
+  float lp[8], dv[8], best = -INFINITY;
+  for (int m = 0; m < M; m++) {
+    const float mean = lg[M + m], ls = fmaxf(lg[2 * M + m], -7.f), inv = expf(-ls), c = xv - mean;
+    const float plus = inv * (c + 1.f / 255.f), mn = inv * (c - 1.f / 255.f), mid = inv * c;
+    float v, d;
+    if (xv < -0.999f) { v = plus - srwn_softplus(plus); d = inv * train::sigmoidf_(-plus); }
+    else if (xv > 0.999f) { v = -srwn_softplus(mn); d = -inv * train::sigmoidf_(mn); }
+    else {
+      float a = plus, bb = mn;
+      if (mid > 0.f) { a = -mn; bb = -plus; }
+      const float ea = expf(a), eb = expf(bb);
+      const float delta = -ea * expm1f(bb - a) / ((1.f + ea) * (1.f + eb));
+      if (delta > 1e-5f) {
+        v = logf(fmaxf(delta, 1e-12f));
+        // d/dx log(sig(plus) - sig(min)) = inv (sig'(plus) - sig'(min)) / delta, and sig' = sig - sig^2 gives
+        // sig'(plus) - sig'(min) = delta (1 - sig(plus) - sig(min)): no division, no cancellation
+        d = inv * (train::sigmoidf_(-plus) - train::sigmoidf_(mn));
+      } else {
+        v = mid - ls - 2.f * srwn_softplus(mid) - 4.8481163902538321f;
+        d = inv * (1.f - 2.f * train::sigmoidf_(mid));
+      }
+    }
+    lp[m] = v + lg[m] - lse_p; dv[m] = d;
+    best = fmaxf(best, lp[m]);
+  }
+  float ssum = 0.f, dsum = 0.f;
+  for (int m = 0; m < M; m++) { const float e = expf(lp[m] - best); ssum += e; dsum = fmaf(e, dv[m], dsum); }
+  dx[i] = -dsum / ssum;
+  if (nll) nll[i] = -(best + logf(ssum));
+}
+
+// Adam as tf.train.AdamOptimizer applies it (model.py:382, 401): lr_t = lr sqrt(1-b2^t)/(1-b1^t);
+// m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; w -= lr_t m / (sqrt(v) + eps).  `scale` = clip_by_global_norm factor.
+__global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       const float* __restrict__ gnorm_sq, float clip, float lr_t, float b1, float b2, float eps, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gn = sqrtf(*gnorm_sq);
+  const float scale = clip > 0.f ? clip / fmaxf(gn, clip) : 1.f;      // tf.clip_by_global_norm (model.py:385)
+  const float gi = g[i] * scale;
+  const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+  m[i] = mi; v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+__global__ void k_sumsq(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+  __shared__ double s_red[256];
+  double acc = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)g[i] * g[i];
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s >= 1; s >>= 1) { if (threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0) *out = (float)s_red[0];
+}
+
+}  // namespace train
+
+// ---- host ----------------------------------------------------------------------------------------------
+struct TrainWs {
+  float *acts, *cond, *scales, *means, *xs, *g0, *g1, *da, *dcond, *d_scales, *d_means, *dxa, *dxb, *partial;
+  size_t bytes; int grid;
+};
+
+static TrainWs carve_train(const srwn_ctx* c, int B, int T, void* ws, size_t cap) {
+  WsCarver w(ws, cap);
+  TrainWs r{};
+  const size_t n = (size_t)B * T, L = c->cfg.n_layers, F = c->cfg.num_flows, frames = T / c->cfg.pool_stride;
+  r.grid = 2 * (c->sm_count > 0 ? c->sm_count : 148);
+  r.acts = w.take<float>(F * (L + 1) * n * kR);
+  r.cond = w.take<float>((size_t)B * frames * L * kR);
+  r.scales = w.take<float>(F * n);
+  r.means = w.take<float>(F * n);
+  r.xs = w.take<float>(F * n);                              // flow outputs x_f
+  r.g0 = w.take<float>(n * kR);
+  r.g1 = w.take<float>(n * kR);
+  r.da = w.take<float>(n * kR);
+  r.dcond = w.take<float>(L * (size_t)B * frames * kR);     // [L][B*frames][32] of the current flow
+  r.d_scales = w.take<float>(F * n);
+  r.d_means = w.take<float>(F * n);
+  r.dxa = w.take<float>(n);
+  r.dxb = w.take<float>(n);
+  r.partial = w.take<float>((size_t)r.grid * (2 * kR * kR + kR));
+  r.bytes = w.used;
+  return r;
+}
+
+size_t train_workspace_bytes(const srwn_ctx* c, int B, int T) { return carve_train(c, B, T, nullptr, 0).bytes; }
+
+// forward of all flows in fp32, keeping every layer input (model.py:489-535)
+int run_student_forward_train(srwn_ctx* c, const float* z, const float* enc, float* out, float* s_tot,
+                              float* mu_tot, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TrainWs w = carve_train(c, B, T, ws, ws_bytes);
+  if (!ws || w.bytes > ws_bytes) return srwn_fail(SRWN_ERR_WORKSPACE, "workspace too small: need %zu bytes", w.bytes);
+  const size_t n = (size_t)B * T;
+  const int F = c->cfg.num_flows, L = c->cfg.n_layers;
+  const float* xin = z;
+  for (int f = 0; f < F; f++) {
+    float* acts = w.acts + (size_t)f * (L + 1) * n * kR;
+    int rc = run_stack_f32_acts(c, f, xin, enc, B, T, acts, w.cond, st);
+    if (rc) return rc;
+    rc = run_flow_head_f32(c, f, acts + (size_t)L * n * kR, xin, w.scales + (size_t)f * n, w.means + (size_t)f * n,
+                           w.xs + (size_t)f * n, B, T, st);
+    if (rc) return rc;
+    xin = w.xs + (size_t)f * n;
+  }
+  return run_flow_compose(z, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
+}
+
+// backward: d_pre [B,T] = dLoss/d(z S + M) (caller applies the clip mask), d_s_extra [B,T] = extra dLoss/dS (entropy);
+// grads: flat buffer in the layout of the weight arena (n_stacks x stack_floats), overwritten.
+int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const float* d_pre, const float* d_s_extra,
+                         float* grads, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace train;
+  TrainWs w = carve_train(c, B, T, ws, ws_bytes);
+  if (!ws || w.bytes > ws_bytes) return srwn_fail(SRWN_ERR_WORKSPACE, "workspace too small: need %zu bytes", w.bytes);
+  const size_t n = (size_t)B * T;
+  const int F = c->cfg.num_flows, L = c->cfg.n_layers, P = c->cfg.pool_stride, frames = T / P, C = c->cfg.cond_channels;
+  const int BF = B * frames;
+  const StackOffsets& o = c->off;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SRWN_CUDA(cudaFuncSetAttribute(k_bwd_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GateSmem)));
+    SRWN_CUDA(cudaFuncSetAttribute(k_bwd_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
+    attr_done = true;
+  }
+  SRWN_CUDA(cudaMemsetAsync(grads, 0, (size_t)c->n_stacks * c->stack_floats * sizeof(float), st));
+  k_bwd_compose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, w.scales, w.means, d_pre, d_s_extra, F, w.d_scales, w.d_means, (int64_t)n);
+  SRWN_LAUNCH_CHECK();
+  const int grid = w.grid;
+  float* dx_next = nullptr;                  // dLoss/dx_f arriving from flow f+1's front conv (null for the last flow)
+  float* dx_cur = w.dxa;
+  for (int f = F - 1; f >= 0; f--) {
+    const float* sw = stack_w(c, f);
+    float* gs = grads + (size_t)f * c->stack_floats;
+    const float* acts = w.acts + (size_t)f * (L + 1) * n * kR;
+    const float* x_prev = f == 0 ? z : w.xs + (size_t)(f - 1) * n;
+    // head: d x_L, direct d x_{f-1}
+    k_bwd_flow_head<<<grid, 256, 0, st>>>(acts + (size_t)L * n * kR, x_prev, w.scales + (size_t)f * n, w.d_scales + (size_t)f * n,
+                                          w.d_means + (size_t)f * n, dx_next, sw + o.head1_k, w.g0, dx_cur, w.partial, (int64_t)n);
+    SRWN_LAUNCH_CHECK();
+    k_reduce_partials<<<1, 64, 0, st>>>(w.partial, grid, 66, 64, gs + o.head1_k);
+    SRWN_LAUNCH_CHECK();
+    k_reduce_partials<<<1, 32, 0, st>>>(w.partial + 64, grid, 66, 2, gs + o.head1_b);
+    SRWN_LAUNCH_CHECK();
+    SRWN_CUDA(cudaMemsetAsync(w.dcond, 0, (size_t)L * BF * kR * sizeof(float), st));
+    float* g = w.g0;
+    float* gn = w.g1;
+    for (int l = L - 1; l >= 0; l--) {
+      const float* x_l = acts + (size_t)l * n * kR;
+      const int d = c->dilations[l];
+      k_bwd_gate<<<grid, kThreads, sizeof(GateSmem), st>>>(x_l, g, w.da, sw + o.filt_k + (size_t)l * 2 * kR * kR,
+                                                           sw + o.filt_b + (size_t)l * kR, sw + o.res_k + (size_t)l * kR * kR,
+                                                           w.partial, B, T, d);
+      SRWN_LAUNCH_CHECK();
+      k_reduce_partials<<<(kR * kR + 255) / 256, 256, 0, st>>>(w.partial, grid, kR * kR + kR, kR * kR, gs + o.res_k + (size_t)l * kR * kR);
+      SRWN_LAUNCH_CHECK();
+      k_reduce_partials<<<1, 32, 0, st>>>(w.partial + kR * kR, grid, kR * kR + kR, kR, gs + o.res_b + (size_t)l * kR);
+      SRWN_LAUNCH_CHECK();
+      // x_l carries cond_l (added before the block, model.py:183; for l = 0 by the front): dcond_l = sum over the frame of dx_l
+      k_bwd_conv<<<grid, kThreads, sizeof(ConvSmem), st>>>(x_l, g, w.da, gn, sw + o.filt_k + (size_t)l * 2 * kR * kR, w.partial,
+                                                           w.dcond + (size_t)l * BF * kR, B, T, d, P, frames);
+      SRWN_LAUNCH_CHECK();
+      k_reduce_partials<<<(2 * kR * kR + 255) / 256, 256, 0, st>>>(w.partial, grid, 2 * kR * kR + kR, 2 * kR * kR, gs + o.filt_k + (size_t)l * 2 * kR * kR);
+      SRWN_LAUNCH_CHECK();
+      k_reduce_partials<<<1, 32, 0, st>>>(w.partial + 2 * kR * kR, grid, 2 * kR * kR + kR, kR, gs + o.filt_b + (size_t)l * kR);
+      SRWN_LAUNCH_CHECK();
+      float* tmp = g; g = gn; gn = tmp;
+    }
+    // g = dLoss/dx_0 (front output incl. cond_0)
+    k_bwd_front<<<grid, 256, 0, st>>>(x_prev, g, sw + o.front_k, f > 0 ? dx_cur : nullptr, w.partial, B, T);
+    SRWN_LAUNCH_CHECK();
+    k_reduce_partials<<<1, 64, 0, st>>>(w.partial, grid, 96, 64, gs + o.front_k);
+    SRWN_LAUNCH_CHECK();
+    k_reduce_partials<<<1, 32, 0, st>>>(w.partial + 64, grid, 96, 32, gs + o.front_b);
+    SRWN_LAUNCH_CHECK();
+    // conditioning: every layer's dcond -> dWc, dbc
+    k_bwd_cond<<<L, 256, 0, st>>>(enc, w.dcond, gs + o.cond_k, gs + o.cond_b, BF, C);
+    SRWN_LAUNCH_CHECK();
+    dx_next = dx_cur;
+    dx_cur = dx_cur == w.dxa ? w.dxb : w.dxa;
+  }
+  return SRWN_OK;
+}
+
+int run_mol_nll_grad(const float* x, const float* l, float* dx, float* nll, int B, int T, int M, cudaStream_t st) {
+  const int64_t n = (int64_t)B * T;
+  train::k_mol_nll_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, l, dx, nll, n, M);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+int run_adam(srwn_ctx* c, const float* grads, float* m, float* v, float* scratch1, float clip, float lr, float b1, float b2,
+             float eps, int step, cudaStream_t st) {
+  const int64_t n = (int64_t)c->n_stacks * c->stack_floats;
+  train::k_sumsq<<<1, 256, 0, st>>>(grads, n, scratch1);
+  SRWN_LAUNCH_CHECK();
+  const float lr_t = lr * sqrtf(1.f - powf(b2, (float)step)) / (1.f - powf(b1, (float)step));
+  train::k_adam<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->d_weights, grads, m, v, scratch1, clip, lr_t, b1, b2, eps, n);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}

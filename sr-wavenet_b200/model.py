@@ -418,6 +418,8 @@ class ParallelWaveNet(_CheckpointMixin):
         if e.ndim != 3 or e.shape[0] != B or e.shape[1] * self.pool_stride != T:
             raise ValueError("encoding must be [B, T/pool_stride, C] with T == pool_stride * frames")
         prec = _lib.PRECISIONS[precision or self.precision]
+        if prec != _lib.FP32 and getattr(self, "_packed_stale", False):
+            self.sync_weights()
         ws, wsn = eng.workspace(_lib.OP_STUDENT_FORWARD, B, T, prec)
         bufs = {k: torch.empty(B, T, dtype=torch.float32, device="cuda") for k in set(want) | {"out"}}
         g = lambda k: bufs[k].data_ptr() if k in bufs else None
@@ -446,10 +448,127 @@ class ParallelWaveNet(_CheckpointMixin):
         bufs, _ = self._forward(inputs, encoding, conditions, want=("s_tot",))
         return (torch.log(bufs["s_tot"]) + 2.0).sum(dim=1).double().cpu().numpy()
 
-    def train(self, sess, inputs, truth, encoding, conditions=None):
-        raise NotImplementedError("distillation training (model.py:603-642) is not built yet")
+    # ---- distillation (model.py:316-401, 603-642) -------------------------------------------------
+    def _teacher_logits(self, truth, enc, teacher_logits, teacher_precision):
+        """stop_gradient(teacher decoder teacher-forced on the REAL audio) (model.py:326-334, F5)."""
+        if teacher_logits is not None:
+            return self._eng.to_device(teacher_logits, "tlogits")[0]
+        if not isinstance(self.teacher, WaveNetAutoEncoder):
+            raise RuntimeError("train needs `teacher` to be a WaveNetAutoEncoder (or pass teacher_logits=)")
+        prec = teacher_precision or ("fp16" if "fp16" in self.teacher.available_precisions() else "fp32")
+        return self.teacher.get_logits(truth, enc, precision=prec)
 
-    train_fast = train
+    def loss_and_grads(self, inputs, truth, encoding, conditions=None, teacher_logits=None,
+                       teacher_precision=None, batch_norm=None):
+        """One forward + backward of the distillation graph (model.py:356-384) on the device.
+        Returns (loss, power_loss, entropy, flat_grads) with flat_grads a CUDA fp32 tensor laid out like the
+        library's weight arena (see ``grad_of``).  ``batch_norm`` overrides the divisor B of model.py:379
+        (the global batch under data parallelism)."""
+        eng = self._eng
+        enc = _with_conditions(encoding, conditions, self.condition_size)
+        z, _ = eng.to_device(inputs, "z")
+        x, _ = eng.to_device(truth, "truth")
+        e, _ = eng.to_device(enc, "enc")
+        B, T = z.shape
+        if e.ndim != 3 or e.shape[0] != B or e.shape[1] * self.pool_stride != T or x.shape != z.shape:
+            raise ValueError("inputs/truth must be [B,T], encoding [B, T/pool_stride, C]")
+        tl = self._teacher_logits(x, e, teacher_logits, teacher_precision).contiguous()
+        M = tl.shape[2] // 4
+        ws, wsn = eng.workspace(_lib.OP_STUDENT_TRAIN, B, T, _lib.FP32)
+        out = torch.empty(B, T, dtype=torch.float32, device="cuda")
+        s_tot, mu_tot = torch.empty_like(out), torch.empty_like(out)
+        _lib.check(eng.lib.srwn_student_forward_train(eng.h, z.data_ptr(), e.data_ptr(), out.data_ptr(),
+                                                      s_tot.data_ptr(), mu_tot.data_ptr(), B, T, ws, wsn, _stream()))
+        norm = float(batch_norm or B)
+        # cross-entropy against the teacher's mixture (model.py:374-375): value + d/d out
+        d_ce, nll = torch.empty_like(out), torch.empty_like(out)
+        _lib.check(eng.lib.srwn_mol_loss_grad(out.data_ptr(), tl.data_ptr(), d_ce.data_ptr(), nll.data_ptr(), B, T, M, _stream()))
+        # spectral power loss (model.py:360-371): torch.stft stands in for tf.contrib.signal.stft(x, 512, 256)
+        # (SURVEY.md 8(f)-2: host-side glue, next in line for a fused kernel)
+        power, d_pow = self._power_loss(x, out)
+        entropy = (torch.log(s_tot) + 2.0).sum()                                   # model.py:356
+        loss = (self.beta * nll.double().sum() - self.alpha * entropy.double() + power.double()) / norm
+        # d loss / d pre, pre = z*s_tot + mu_tot: tf.minimum/maximum pass the gradient inside [-1, 1] (model.py:535)
+        pre = z * s_tot + mu_tot
+        mask = ((pre >= -1.0) & (pre <= 1.0)).float()
+        d_pre = ((self.beta * d_ce + d_pow) * mask / norm).contiguous()
+        d_s = (-(self.alpha / norm) / s_tot).contiguous()                          # entropy term, model.py:377
+        n = ctypes.c_int64()
+        _lib.check(eng.lib.srwn_param_count(eng.h, ctypes.byref(n)))
+        grads = torch.empty(n.value, dtype=torch.float32, device="cuda")
+        _lib.check(eng.lib.srwn_student_backward(eng.h, z.data_ptr(), e.data_ptr(), d_pre.data_ptr(), d_s.data_ptr(),
+                                                 grads.data_ptr(), B, T, ws, wsn, _stream()))
+        return loss, power, entropy, grads
+
+    def _power_loss(self, truth, out):
+        """gamma * || mean_t |STFT(truth)|^2 - mean_t |STFT(out)|^2 ||^2 (model.py:360-371) and d/d out."""
+        if not hasattr(self, "_hann") or self._hann.device != out.device:
+            self._hann = torch.hann_window(512, periodic=True, dtype=torch.float32, device=out.device)
+
+        def power(sig):
+            spec = torch.stft(sig, n_fft=512, hop_length=256, win_length=512, window=self._hann, center=False,
+                              return_complex=True)
+            return (spec.real ** 2 + spec.imag ** 2).mean(dim=2)
+        o = out.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            p = ((power(truth) - power(o)) ** 2).sum() * self.gamma
+            g, = torch.autograd.grad(p, o)
+        return p.detach(), g
+
+    def grad_of(self, flat_grads, name):
+        """View of one variable's gradient inside ``flat_grads`` (TF variable name)."""
+        off, cnt = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._eng.lib.srwn_weight_offset(self._eng.h, name.encode(), ctypes.byref(off), ctypes.byref(cnt)))
+        return flat_grads[off.value:off.value + cnt.value]
+
+    def apply_gradients(self, flat_grads, clip_norm=1.0, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        """tf.clip_by_global_norm(grads, 1.0) + AdamOptimizer(learning_rate).apply_gradients (model.py:382-401).
+        Under torch.distributed the caller all-reduces ``flat_grads`` first (``train_fast`` does)."""
+        eng = self._eng
+        if not hasattr(self, "_adam"):
+            self._adam = dict(m=torch.zeros_like(flat_grads), v=torch.zeros_like(flat_grads),
+                              scratch=torch.zeros(4, dtype=torch.float32, device="cuda"), step=0)
+        a = self._adam
+        a["step"] += 1
+        _lib.check(eng.lib.srwn_adam_step(eng.h, flat_grads.data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(),
+                                          a["scratch"].data_ptr(), float(clip_norm), float(self.learning_rate),
+                                          float(beta1), float(beta2), float(epsilon), a["step"], _stream()))
+        self._packed_stale = True
+
+    def sync_weights(self):
+        """Re-packs the 16-bit operand images from the (trained) device weights and refreshes ``get_weights``."""
+        eng = self._eng
+        _lib.check(eng.lib.srwn_commit_weights(eng.h, _stream()))
+        for k, v in list(self._weights.items()):
+            try:
+                self._weights[k] = eng.get_weight(k, v.shape)
+            except _lib.SrwnError:
+                pass      # dead variables (gate conv, student skip conv) are not stored
+        self._packed_stale = False
+
+    def train_fast(self, sess, inputs, truth, encoding, conditions=None, teacher_logits=None, teacher_precision=None):
+        """model.py:634-642: one optimisation step, returns (loss, power_loss).  With torch.distributed
+        initialised, ranks hold batch shards: the loss is normalised by the global batch, the flat gradient is
+        summed with one NCCL all-reduce before the global-norm clip, and every rank applies
+        the same Adam update."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        B = int(np.shape(inputs)[0])
+        loss, power, _, grads = self.loss_and_grads(inputs, truth, encoding, conditions, teacher_logits,
+                                                    teacher_precision, batch_norm=B * world)
+        if world > 1:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+            lp = torch.stack([loss.double(), power.double()])
+            dist.all_reduce(lp, op=dist.ReduceOp.SUM)
+            loss, power = lp[0], lp[1]
+        self.apply_gradients(grads)
+        return float(loss), float(power)
+
+    def train(self, sess, inputs, truth, encoding, conditions=None, **kw):
+        """model.py:603-632 averages per-example gradients on the host and applies them once; with a loss that is
+        a sum over the batch divided by B (model.py:379) this equals one batched step except for the power
+        loss's norm, which the reference takes per example there.  The batched graph is used."""
+        return self.train_fast(sess, inputs, truth, encoding, conditions, **kw)
 
     def encode(self, sess, inputs, conditions=None):
         raise NotImplementedError("the teacher encoder (model.py:644-649) is outside the hot path")

@@ -1,0 +1,109 @@
+"""-m gpu: the distillation step (model.py:356-401) through the C ABI vs the torch float64 gradient oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import distill_torch as dt
+from sr_wavenet_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def srwn(lib):
+    import sr_wavenet_b200
+    assert torch.cuda.is_available()
+    return sr_wavenet_b200
+
+
+def _student(srwn, dil, F, C, P, seed=11, lr=1e-3, **kw):
+    s = srwn.ParallelWaveNet(input_size=0, condition_size=0, dilations=dil, teacher=None, num_flows=F,
+                             skip_channels=128, latent_channels=C, pool_stride=P, learning_rate=lr, **kw)
+    w = synth.make_student_weights(dil, num_flows=F, latent_channels=C, seed=seed)
+    s.set_weights(w)
+    return s, w
+
+
+def _inputs(B, T, P, C, M, seed=5):
+    rng = np.random.default_rng(seed)
+    z = rng.logistic(0, 1, size=(B, T)).astype(np.float32)
+    truth = synth.synthetic_audio(B, T)
+    enc = rng.normal(0, 1, size=(B, T // P, C)).astype(np.float32)
+    tl = (rng.normal(0, 1, size=(B, T, 4 * M)) * 0.5).astype(np.float32)
+    return z, truth, enc, tl
+
+
+def test_mol_loss_grad_matches_autograd(srwn):
+    lib = srwn._lib.load()
+    rng = np.random.default_rng(3)
+    B, T, M = 2, 512, 5
+    l = (rng.normal(0, 1.5, size=(B, T, 4 * M))).astype(np.float32)
+    l[:, :, 2 * M:3 * M] -= 3.0                 # narrow components: exercises every branch of ops.py:150-167
+    x = np.clip(rng.normal(0, 0.7, size=(B, T)), -1, 1).astype(np.float32)
+    x[0, :8] = -1.0
+    x[1, :8] = 1.0
+    xt = torch.tensor(x.astype(np.float64), requires_grad=True)
+    nll = dt.mol_nll(xt, torch.tensor(l.astype(np.float64)), M)
+    g_ref, = torch.autograd.grad(nll, xt)
+    xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(l).cuda()
+    dx, out = torch.empty_like(xd), torch.empty_like(xd)
+    srwn._lib.check(lib.srwn_mol_loss_grad(xd.data_ptr(), ld.data_ptr(), dx.data_ptr(), out.data_ptr(), B, T, M,
+                                           torch.cuda.current_stream().cuda_stream))
+    np.testing.assert_allclose(out.double().sum().item(), float(nll), rtol=1e-5)
+    g = dx.cpu().numpy().astype(np.float64)
+    scale = np.abs(g_ref.numpy()).max()
+    assert np.abs(g - g_ref.numpy()).max() <= 2e-4 * scale
+
+
+@pytest.mark.parametrize("cfg", ["small", "default"])
+def test_gradients_match_oracle(srwn, cfg):
+    if cfg == "small":
+        dil, F, C, P, M, B, T = [1, 2, 4, 3], 2, 8, 64, 3, 3, 832     # ragged: T not a multiple of the 64-row tile
+    else:
+        dil, F, C, P, M, B, T = synth.DEFAULT_DILATIONS, 4, 32, 128, 5, 1, 1280
+    s, w = _student(srwn, dil, F, C, P, alpha=0.25, beta=1.0, gamma=1.0)
+    z, truth, enc, tl = _inputs(B, T, P, C, M)
+    loss, power, ent, flat = s.loss_and_grads(z, truth, enc, teacher_logits=tl)
+    rl, rp, re, rg = dt.loss_and_grads({k: v.astype(np.float64) for k, v in w.items()}, z, truth, enc, tl, dil, P, F,
+                                       alpha=0.25, beta=1.0, gamma=1.0)
+    np.testing.assert_allclose(float(ent), re, rtol=1e-4)
+    np.testing.assert_allclose(float(power), rp, rtol=2e-3)
+    np.testing.assert_allclose(float(loss), rl, rtol=1e-3)
+    gmax = max(np.abs(v).max() for v in rg.values())
+    checked = 0
+    for name, ref in rg.items():
+        if "_gate/" in name or not np.any(ref):
+            continue                                             # dead variables are not stored
+        got = s.grad_of(flat, name).cpu().numpy().reshape(ref.shape)
+        tol = 2e-3 * max(np.abs(ref).max(), 1e-3 * gmax)         # fp32 kernels + fp32 loss gradients vs float64
+        assert np.abs(got - ref).max() <= tol, (name, np.abs(got - ref).max(), np.abs(ref).max())
+        checked += 1
+    assert checked == F * (2 + 6 * len(dil) + 2)
+
+
+def test_adam_step_and_training_reduces_loss(srwn):
+    dil, F, C, P, M, B, T = [1, 2, 4, 8], 2, 8, 128, 3, 2, 1024
+    s, w = _student(srwn, dil, F, C, P, lr=2e-3, alpha=0.25, beta=1.0, gamma=1.0)
+    z, truth, enc, tl = _inputs(B, T, P, C, M)
+    # one step against the reference formulas (tf.clip_by_global_norm + AdamOptimizer)
+    _, _, _, flat = s.loss_and_grads(z, truth, enc, teacher_logits=tl)
+    names = [k for k in w if "_gate/" not in k and not k.endswith(("conv1d_2/kernel", "conv1d_2/bias", "conv1d_5/kernel",
+             "conv1d_5/bias", "conv1d_8/kernel", "conv1d_8/bias", "conv1d_11/kernel", "conv1d_11/bias"))]
+    g = [s.grad_of(flat, k).cpu().numpy().astype(np.float64).reshape(w[k].shape) for k in names]
+    gnorm = float(torch.linalg.vector_norm(flat.double()).item())
+    ref = dt.adam_reference([w[k].astype(np.float64) for k in names], g, [np.zeros_like(x) for x in g],
+                            [np.zeros_like(x) for x in g], step=1, lr=2e-3, gnorm=gnorm)
+    s.apply_gradients(flat)
+    s.sync_weights()
+    new = s.get_weights()
+    for k, (wr, _, _) in zip(names, ref):
+        np.testing.assert_allclose(new[k], wr, rtol=0, atol=2e-6)
+    # a few more steps: the loss goes down, and the re-packed 16-bit path follows the trained weights
+    l0, _ = s.train_fast(None, z, truth, enc, teacher_logits=tl)
+    for _ in range(5):
+        l1, p1 = s.train_fast(None, z, truth, enc, teacher_logits=tl)
+    assert np.isfinite(l1) and l1 < l0
+    out32 = s.generate(None, z, enc, precision="fp32")
+    if "fp16" in s.available_precisions():
+        out16 = s.generate(None, z, enc, precision="fp16")
+        assert np.abs(out16 - out32).max() <= 2e-2
