@@ -26,6 +26,9 @@ FLOP_PER_SAMPLE_STUDENT = 740224      # 4*184576 + 1920
 BYTES_PER_SAMPLE_LAYER_F32 = 1280     # fp32 per-layer kernel: h read+write (2*128 B) + skip RMW (2*512 B)
 BYTES_PER_SAMPLE_AR = 7684            # fp32 queue pop+push (2*30*32*4 B) + 4 B sample
 BYTES_PER_SAMPLE_AR_F16 = 3844        # same with 16-bit queue state (2*30*32*2 B) + 4 B sample
+# distillation backward (fp32, layer at a time): per (sample, layer, flow) the gate kernel reads x_l and g and writes
+# da (3 x 128 B), the conv kernel reads x_l, g, da and writes dx (4 x 128 B): 896 B; x 30 layers x 4 flows
+BYTES_PER_SAMPLE_BWD = 4 * 30 * 896
 METRIC = "audio samples/sec"
 UNIT = "samples/s"
 
@@ -136,7 +139,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="teacher_nll", choices=["teacher_nll", "student", "generate"])
+    ap.add_argument("--workload", default="teacher_nll", choices=["teacher_nll", "student", "generate", "distill"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config)")
     ap.add_argument("--length", type=int, default=0)
@@ -165,7 +168,7 @@ def main():
     P = 128
 
     defaults = {"teacher_nll": (32, 64000), "student": (64 // max(world, 1) if world > 1 else 8, 64000),
-                "generate": (256, 16000)}
+                "generate": (256, 16000), "distill": (4, 64000)}
     B, T = defaults[args.workload]
     if args.workload == "student":
         B = 8          # configs[2]: 64 x 64000 over 8 GPUs = 8 per GPU (weak scaling unit)
@@ -175,9 +178,15 @@ def main():
     # synthetic inputs, seeded per global utterance index so ranks see different audio
     g0 = rank * B
     enc_h = synth.synthetic_encoding(B, T // P, seed=4321 + rank)
-    if args.workload == "student":
-        model = srwn.ParallelWaveNet(T, 0, dil, None, num_flows=4, skip_channels=128, latent_channels=32,
-                                     pool_stride=P)
+    truth_h = None
+    if args.workload in ("student", "distill"):
+        teacher = None
+        if args.workload == "distill":      # configs[4]: the teacher scores the REAL audio (model.py:326-334)
+            teacher = srwn.WaveNetAutoEncoder(T, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=P)
+            teacher.set_weights(synth.make_teacher_weights(dil))
+            truth_h = synth.synthetic_audio(B, T, seed=1234 + g0)
+        model = srwn.ParallelWaveNet(T, 0, dil, teacher, num_flows=4, skip_channels=128, latent_channels=32,
+                                     pool_stride=P, alpha=0.25, beta=1.0, gamma=1.0, learning_rate=1e-4)   # student.py:30-33
         model.set_weights(synth.make_student_weights(dil, 4))
         x_h = synth.logistic_noise(B, T, seed=777 + rank)
         flop_per_sample = FLOP_PER_SAMPLE_STUDENT / 4.0     # the dominant kernel is one flow (one launch per flow)
@@ -189,6 +198,8 @@ def main():
     prec = args.precision
     if prec == "auto" and args.workload != "generate":
         prec = "fp16" if "fp16" in model.available_precisions() else "fp32"
+    if args.workload == "distill":
+        prec = "fp32"                           # student forward/backward run in fp32; the teacher uses its fp16 path
     if args.workload == "generate":
         if prec in ("auto", "fp16", "bf16"):     # tensor-core generation kernel (fp16 operands and queue state)
             prec = "fp16"
@@ -200,7 +211,12 @@ def main():
         u1_d, u2_d = torch.from_numpy(u1_h).cuda(), torch.from_numpy(u2_h).cuda()
         u1_p, u2_p = torch.from_numpy(u1_h).pin_memory(), torch.from_numpy(u2_h).pin_memory()
 
+    if truth_h is not None:
+        truth_d, truth_p = torch.from_numpy(truth_h).cuda(), torch.from_numpy(truth_h).pin_memory()
+
     def step_device():
+        if args.workload == "distill":
+            return model.train_fast(None, x_d, truth_d, enc_d)
         if args.workload == "teacher_nll":
             return model.nll(x_d, enc_d, precision=prec)
         if args.workload == "student":
@@ -208,6 +224,8 @@ def main():
         return model.generate(enc_d, u1=u1_d, u2=u2_d, precision=prec)
 
     def step_e2e():
+        if args.workload == "distill":
+            return model.train_fast(None, x_p, truth_p, enc_p)      # (loss, power_loss) floats on the host
         if args.workload == "teacher_nll":
             return model.nll(x_p, enc_p, precision=prec)            # float on the host
         if args.workload == "student":
@@ -236,7 +254,7 @@ def main():
         km, kern_launches, kern_name = model._eng.last_kernel_ms()
         kern_ms.append(km)
     torch.cuda.synchronize()
-    if prec != "fp32" and args.workload != "generate":     # a fused launch that aborted on the device is not a measurement
+    if prec != "fp32" and args.workload not in ("generate", "distill"):     # a fused launch that aborted on the device is not a measurement
         model._eng.check_async(srwn._lib.OP_TEACHER_NLL if args.workload == "teacher_nll" else srwn._lib.OP_STUDENT_FORWARD,
                                B, T, srwn._lib.PRECISIONS[prec])
     launches = srwn._lib.launch_count() - launches0
@@ -260,8 +278,9 @@ def main():
     units, = shard.reduce_scalars([float(B * T * args.steps)], "sum")
     value = units / (total_ms_max * 1e-3)
     e2e_value = units / e2e_s_max
-    h2d = x_h.nbytes + enc_h.nbytes + (u1_h.nbytes + u2_h.nbytes if args.workload == "generate" else 0)
-    d2h = 4 if args.workload == "teacher_nll" else B * T * 4
+    h2d = x_h.nbytes + enc_h.nbytes + (u1_h.nbytes + u2_h.nbytes if args.workload == "generate" else 0) + \
+        (truth_h.nbytes if truth_h is not None else 0)
+    d2h = 4 if args.workload == "teacher_nll" else 16 if args.workload == "distill" else B * T * 4
 
     # roofline of the dominant kernel, from this run's CUDA-event bracket around its launches
     k_ms = sum(kern_ms) / len(kern_ms) / max(kern_launches, 1)
@@ -270,7 +289,10 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("%s/%s" % (args.workload, prec))
-    if args.workload == "generate":
+    if args.workload == "distill":
+        ach = BYTES_PER_SAMPLE_BWD * B * T / (k_ms * kern_launches * 1e-3) / 1e9     # the bracket spans the whole backward
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s"}
+    elif args.workload == "generate":
         # queue pop + push of 32 channels per layer + the sample: 7684 B with fp32 state, 3844 B with fp16 state
         ach = (BYTES_PER_SAMPLE_AR if prec == "fp32" else BYTES_PER_SAMPLE_AR_F16) * B * T / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s"}
@@ -293,7 +315,9 @@ def main():
     if rank == 0:
         names = {"teacher_nll": "teacher WaveNet teacher-forced log-likelihood (BASELINE.json configs[1])",
                  "student": "student IAF parallel synthesis, 4 flows (BASELINE.json configs[2])",
-                 "generate": "teacher autoregressive fast generation, dilation queues (BASELINE.json configs[3])"}
+                 "generate": "teacher autoregressive fast generation, dilation queues (BASELINE.json configs[3])",
+                 "distill": "student distillation training step: teacher scores real audio, KL + power loss, "
+                            "all-reduce + clip + Adam (BASELINE.json configs[4])"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,

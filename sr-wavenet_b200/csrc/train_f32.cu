@@ -477,6 +477,7 @@ int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const fl
   k_bwd_compose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, w.scales, w.means, d_pre, d_s_extra, F, w.d_scales, w.d_means, (int64_t)n);
   SRWN_LAUNCH_CHECK();
   const int grid = w.grid;
+  ProfScope prof(c, st, "k_bwd_gate+k_bwd_conv (student backward)", F * L * 2);
   float* dx_next = nullptr;                  // dLoss/dx_f arriving from flow f+1's front conv (null for the last flow)
   float* dx_cur = w.dxa;
   for (int f = F - 1; f >= 0; f--) {
