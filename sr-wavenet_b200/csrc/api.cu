@@ -184,6 +184,7 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
   c->committed = false; c->device_dirty = false;
   c->d_weights = nullptr; c->d_dilations = nullptr; c->d_queue_off = nullptr;
   c->d_packed = nullptr; c->packed_bytes = 0; c->d_ar_packed = nullptr;
+  c->d_part = nullptr; c->part_B = c->part_T = c->part_grid = 0;
   c->profiling = 0; c->prof_launches = 0; c->prof_name = "";
   c->prof_ev[0] = c->prof_ev[1] = nullptr;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -233,7 +234,7 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
 extern "C" int srwn_destroy(srwn_handle_t h) {
   if (!h) return SRWN_OK;
   if (h->prof_ev[0]) { cudaEventDestroy(h->prof_ev[0]); cudaEventDestroy(h->prof_ev[1]); }
-  cudaFree(h->d_ar_packed);
+  cudaFree(h->d_ar_packed); cudaFree(h->d_part);
   cudaFree(h->d_weights); cudaFree(h->d_dilations); cudaFree(h->d_queue_off); cudaFree(h->d_packed);
   delete reinterpret_cast<CtxBox*>(h);
   return SRWN_OK;

@@ -71,6 +71,8 @@ struct srwn_ctx {
   // packed bf16 operand images for the tcgen05 path (built at commit)
   void* d_packed;
   size_t packed_bytes;
+  void* d_part;                       // cached work partition of the fused kernel for (part_B, part_T): segs | nseg
+  int part_B, part_T, part_grid;
   void* d_ar_packed;                  // fragment-ordered fp16 weights of the tensor-core generation kernel (built at commit)
   // optional timing of the dominant kernel(s) of the last call (srwn_set_profiling)
   int profiling;

@@ -771,6 +771,42 @@ __global__ void k_fold_bias(const float* __restrict__ cond, const float* __restr
   }
 }
 
+
+// conditioning 1x1 (model.py:180/431) and the bias folding above in one pass, 8 latent frames per CTA so that the
+// conditioning weights are read once per 8 frames:
+// cb[bf][l] = enc[bf] @ Wc_l + bc_l + (l == 0 ? front_b : sqrt(1/2) res_b[l-1]);  cb[bf][L] = sqrt(1/2) res_b[L-1]
+constexpr int kCondRows = 8;
+__global__ void __launch_bounds__(256)
+k_cond_fold(const float* __restrict__ enc, const float* __restrict__ cond_k, const float* __restrict__ cond_b,
+            const float* __restrict__ front_b, const float* __restrict__ res_b, float* __restrict__ cb,
+            int BF, int L, int C) {
+  __shared__ float s_enc[kCondRows][kMaxCond];
+  const int bf0 = blockIdx.x * kCondRows;
+  for (int i = threadIdx.x; i < kCondRows * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    s_enc[r][c] = bf0 + r < BF ? enc[(size_t)(bf0 + r) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < (L + 1) * 32; o += blockDim.x) {
+    const int l = o / 32, j = o % 32;
+    float acc[kCondRows];
+    const float base = (l < L ? cond_b[l * 32 + j] : 0.f) + (l == 0 ? front_b[j] : SRWN_SQRT_HALF * res_b[(l - 1) * 32 + j]);
+#pragma unroll
+    for (int r = 0; r < kCondRows; r++) acc[r] = base;
+    if (l < L) {
+      const float* wk = cond_k + (size_t)l * C * 32 + j;
+      for (int c = 0; c < C; c++) {
+        const float w = __ldg(wk + (size_t)c * 32);
+#pragma unroll
+        for (int r = 0; r < kCondRows; r++) acc[r] = fmaf(s_enc[r][c], w, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kCondRows; r++)
+      if (bf0 + r < BF) cb[(size_t)(bf0 + r) * (L + 1) * 32 + o] = acc[r];
+  }
+}
+
 }  // namespace fused
 
 using namespace fused;
@@ -955,17 +991,25 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
                    Partition* part, bool first, int fp16, cudaStream_t st) {
   const int L = c->cfg.n_layers, P = c->cfg.pool_stride, frames = T / P;
   const float* sw = stack_w(c, stack);
-  k_cond<<<B * frames, 256, 0, st>>>(enc, sw + c->off.cond_k, sw + c->off.cond_b, w.cond, B * frames, L,
-                                     c->cfg.cond_channels);
-  SRWN_LAUNCH_CHECK();
-  k_fold_bias<<<B * frames, 256, 0, st>>>(w.cond, sw + c->off.front_b, sw + c->off.res_b, w.cb, L);
+  k_cond_fold<<<(B * frames + kCondRows - 1) / kCondRows, 256, 0, st>>>(enc, sw + c->off.cond_k, sw + c->off.cond_b,
+                                                                        sw + c->off.front_b, sw + c->off.res_b, w.cb,
+                                                                        B * frames, L, c->cfg.cond_channels);
   SRWN_LAUNCH_CHECK();
   if (first) {
-    *part = make_partition(B, T, c->sum_dilation, c->sm_count);
-    SRWN_CUDA(cudaMemcpyAsync(w.segs, part->segs.data(), part->segs.size() * sizeof(Seg), cudaMemcpyHostToDevice, st));
-    SRWN_CUDA(cudaMemcpyAsync(w.nseg, part->nseg.data(), part->nseg.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    // the work partition depends on (B, T) only: built once, kept on the device next to the handle
+    if (!c->d_part || c->part_B != B || c->part_T != T) {
+      *part = make_partition(B, T, c->sum_dilation, c->sm_count);
+      const size_t seg_bytes = (size_t)c->sm_count * kMaxSeg * sizeof(Seg), n_bytes = (size_t)c->sm_count * sizeof(int);
+      if (!c->d_part) SRWN_CUDA(cudaMalloc(&c->d_part, seg_bytes + n_bytes));
+      std::vector<uint8_t> host(seg_bytes + n_bytes, 0);
+      memcpy(host.data(), part->segs.data(), std::min(seg_bytes, part->segs.size() * sizeof(Seg)));
+      memcpy(host.data() + seg_bytes, part->nseg.data(), std::min(n_bytes, part->nseg.size() * sizeof(int)));
+      SRWN_CUDA(cudaMemcpyAsync(c->d_part, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+      SRWN_CUDA(cudaStreamSynchronize(st));     // the staging vector is a host temporary
+      c->part_B = B; c->part_T = T; c->part_grid = part->grid;
+    }
+    part->grid = c->part_grid;
     SRWN_CUDA(cudaMemsetAsync(w.err, 0, 16, st));
-    SRWN_CUDA(cudaStreamSynchronize(st));     // the partition vectors are host temporaries
   }
   memset(p, 0, sizeof(*p));
   const size_t img = stack_image_bytes(c);
@@ -973,7 +1017,9 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   p->trace = getenv("SRWN_TRACE") ? w.trace : nullptr;
   p->trace_chunk = getenv("SRWN_TRACE") ? atoi(getenv("SRWN_TRACE")) : 0;
   p->dbg = getenv("SRWN_DBG") ? atoi(getenv("SRWN_DBG")) : 0;
-  p->cb = w.cb; p->rings = w.rings; p->segs = w.segs; p->nseg = w.nseg; p->err = w.err;
+  p->cb = w.cb; p->rings = w.rings; p->err = w.err;
+  p->segs = reinterpret_cast<const Seg*>(c->d_part);
+  p->nseg = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(c->d_part) + (size_t)c->sm_count * kMaxSeg * sizeof(Seg));
   p->T = T; p->L = L; p->P = P; p->frames = frames;
   p->O = 4 * c->cfg.num_mixtures; p->M = c->cfg.num_mixtures;
   p->ring_bytes_per_cta = c->sum_dilation * 64 + 256;
