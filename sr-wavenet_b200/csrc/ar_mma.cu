@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 #include <vector>
 #include <cstdio>
+#include <cstdlib>
 
 const float* srwn_host_weights(srwn_ctx* c);
 __global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
@@ -41,8 +42,8 @@ constexpr int kChainLayerBytes = 4096 + 2048 + 128;   // Wf fragments | Wr fragm
 constexpr int kItemBytes = 8192;              // one ring item: skip weights of a layer / a quarter of H1 / H2
 constexpr int kStages = 3;
 constexpr int kSlotBytes = 512;               // gate output of one layer: [lane][4 x b32]
-constexpr int kThreads = 11 * 32;
-constexpr int kChainWarp = 0, kProducerWarp = 4;      // SMSP 0 hosts only these two (and idle warp 8)
+constexpr int kThreads = 13 * 32;
+constexpr int kChainWarps = 4, kProducerWarp = 4;     // warps 0..3: chain (one per SMSP), 4: producer, 5..12: skip warps
 
 struct Smem {
   static constexpr int chain = 0;
@@ -56,7 +57,9 @@ struct Smem {
   static constexpr int bars = logits + 768;
   static constexpr int n_bars = 2 * kStages + kMaxL + 2;
   static constexpr int flags = bars + n_bars * 8 + 16;     // per-layer step counters: gate slot l holds step (flag - 1)
-  static constexpr int total = flags + kMaxL * 4;
+  static constexpr int xslot = flags + kMaxL * 4;           // x[t] of the 8 utterances, chain warp 0 -> chain warps 1..3
+  static constexpr int qofs = xslot + 64;                   // queue slot byte offsets of the step, [kMaxL] ints
+  static constexpr int total = qofs + kMaxL * 4;
 };
 static_assert(Smem::total <= 232448, "shared memory budget");
 
@@ -72,6 +75,7 @@ struct Params {
   float* logits_out;          // [B][T][4M] or null
   int* err;
   int B, T, L, P, frames, M, sum_d;
+  int dbg;                    // tuning experiments (SRWN_AR_DBG): wrong results, timing only
   int dil[kMaxL];
   int qoff[kMaxL];
 };
@@ -157,10 +161,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_WFULL + s)), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_WEMPTY + s)), "r"(8));
     }
-    for (int l = 0; l < kMaxL; l++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_CFULL + l)), "r"(32));
+    for (int l = 0; l < kMaxL; l++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_CFULL + l)), "r"(1));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_HID1)), "r"(256));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_HID2)), "r"(256));
     *abort_flag = 0;
+    for (int i = 0; i < 9; i++) reinterpret_cast<volatile float*>(smem + Smem::xslot)[i] = 0.f;
     for (int l = 0; l < kMaxL; l++) reinterpret_cast<volatile int*>(smem + Smem::flags)[l] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
 
   if (warp == kProducerWarp) {
     // ================= producer: skip / head weights, L2 -> shared ring ===========================
-    if (lane == 0) {
+    if (lane == 0 && !(p.dbg & 16)) {
       long long it = 0;
       for (int t = 0; t < p.T; t++) {
         for (int i = 0; i < n_items; i++, it++) {
@@ -196,22 +201,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     }
     return;
   }
-  if (warp == 8) return;
-
-  if (warp == kChainWarp) {
-    // ================= chain warp ==================================================================
+  if (warp < kChainWarps) {
+    // ================= chain warps: warp j owns channels 8j..8j+7 (n-tile j) of the filter conv and the gate;
+    // every warp then computes the whole residual conv and keeps the whole residual stream (no second exchange)
+    const int j = warp;
+    auto chain_sync = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
     const int bg = min(b0 + g, p.B - 1);               // utterance of fragment row g (clamped: padding rows repeat the last one)
     const float* cb_b = p.cb + (size_t)bg * p.frames * (L + 1) * 32;
     uint8_t* qbase = p.queues + (size_t)blockIdx.x * sum_d * kSlotBytes + lane * 16;
     const float* sf = reinterpret_cast<const float*>(smem + Smem::front);
+    volatile int* sq = reinterpret_cast<volatile int*>(smem + Smem::qofs);
+    volatile float* sx = reinterpret_cast<volatile float*>(smem + Smem::xslot);
     float xm1 = 0.f, xm2 = 0.f;                         // x[t-1], x[t-2] of utterance g
-    float h[4][2];                                      // residual stream: n-tile j, columns 8j+2q, 8j+2q+1 of row g
+    float h[4][2];                                      // residual stream: n-tile i, columns 8i+2q, 8i+2q+1 of row g
     uint32_t hA[4];                                     // its fp16 image as A fragments: kt0 (a0,a2), kt1 (a0,a2)
     long long it_base = 0;                              // ring item counter at the start of the step
-    const int ub = b0 + lane;                           // sampler lanes 0..7: utterance b0+lane
-    const bool samp = lane < kU && ub < p.B;
+    const int ub = b0 + lane;                           // sampler lanes 0..7 of warp 0: utterance b0+lane
+    const bool samp = j == 0 && lane < kU && ub < p.B;
+    bool ok = true;
+    long long tm_a = 0, tm_b = 0, tm_c = 0, tm_d = 0;
 
-    long long tm_a = 0, tm_b = 0, tm_c = 0, tl1 = 0, tl2 = 0, tl3 = 0;
     for (int t = 0; t < p.T; t++, it_base += n_items) {
       const long long c0 = clock64();
       const int frame = t / p.P;
@@ -224,185 +233,165 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         for (int m = 0; m < p.M; m++) u1v[m] = __ldg(p.u1 + ((size_t)ub * p.T + t) * p.M + m);
         u2v = __ldg(p.u2 + (size_t)ub * p.T + t);
       }
-      // queue slot of every layer at this step (byte offsets), computed by one lane per layer
-      {
-        int* sq = reinterpret_cast<int*>(smem + Smem::logits);          // the logits scratch is idle during the chain
-        if (lane < L) {
-          const int d = p.dil[lane];
-          sq[lane] = (p.qoff[lane] + (pow2 ? (t & (d - 1)) : (t % d))) * kSlotBytes;
-        }
-        __syncwarp();
+      // queue slot of every layer at this step (byte offsets), one lane per layer
+      if (j == 0 && lane < L) {
+        const int d = p.dil[lane];
+        sq[lane] = (p.qoff[lane] + (pow2 ? (t & (d - 1)) : (t % d))) * kSlotBytes;
       }
-      const volatile int* sq = reinterpret_cast<const volatile int*>(smem + Smem::logits);
-      // pops of layers 0 and 1; folded bias + conditioning of layers 0, 1, 2 (rotating registers, no arrays
-      // indexed by the layer: those would live in local memory)
+      chain_sync();
+      // pops of layers 0 and 1; folded bias + conditioning of layers 0, 1, 2 (rotating registers: arrays indexed by the
+      // layer would live in local memory)
       int ofs0 = sq[0], ofs1 = L > 1 ? sq[1] : 0, ofs2 = L > 2 ? sq[2] : 0;
       uint4 tap0 = *reinterpret_cast<const uint4*>(qbase + ofs0);
       uint4 tap1 = L > 1 ? *reinterpret_cast<const uint4*>(qbase + ofs1) : make_uint4(0, 0, 0, 0);
       float2 cb0[4], cbA[4], cbB[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        cb0[j] = *reinterpret_cast<const float2*>(cbf + 8 * j);
-        cbA[j] = *reinterpret_cast<const float2*>(cbf + 32 + 8 * j);
-        cbB[j] = L >= 2 ? *reinterpret_cast<const float2*>(cbf + 64 + 8 * j) : make_float2(0.f, 0.f);
+      for (int i = 0; i < 4; i++) {
+        cb0[i] = *reinterpret_cast<const float2*>(cbf + 8 * i);
+        cbA[i] = *reinterpret_cast<const float2*>(cbf + 32 + 8 * i);
+        cbB[i] = L >= 2 ? *reinterpret_cast<const float2*>(cbf + 64 + 8 * i) : make_float2(0.f, 0.f);
       }
       // front: RightShift + K=2 causal conv on one channel (model.py:172-173) + bias + conditioning of layer 0
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int c = 8 * j + 2 * q;
-        h[j][0] = fmaf(xm2, sf[c], fmaf(xm1, sf[32 + c], cb0[j].x));
-        h[j][1] = fmaf(xm2, sf[c + 1], fmaf(xm1, sf[32 + c + 1], cb0[j].y));
+      for (int i = 0; i < 4; i++) {
+        const int c = 8 * i + 2 * q;
+        h[i][0] = fmaf(xm2, sf[c], fmaf(xm1, sf[32 + c], cb0[i].x));
+        h[i][1] = fmaf(xm2, sf[c + 1], fmaf(xm1, sf[32 + c + 1], cb0[i].y));
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) hA[j] = pack_h2(h[j][0], h[j][1]);
-      uint4 wf[8];                                       // filter-conv B fragments of the current layer
-#pragma unroll
-      for (int i = 0; i < 8; i++) wf[i] = lds128_ro(sbase + Smem::chain + lane * 16 + i * 512);
+      for (int i = 0; i < 4; i++) hA[i] = pack_h2(h[i][0], h[i][1]);
+      // filter-conv B fragments of this warp's n-tile: [taps k-tiles 0,1 | current k-tiles 2,3]
+      uint4 wft = lds128_ro(sbase + Smem::chain + lane * 16 + (2 * j) * 512);
+      uint4 wfc = lds128_ro(sbase + Smem::chain + lane * 16 + (2 * j + 1) * 512);
 
       for (int l = 0; l < L; l++) {
         const uint32_t wl = sbase + Smem::chain + l * kChainLayerBytes + lane * 16;
-#ifdef SRWN_AR_TIMING
-        const long long s0 = clock64();
-#endif
         const uint4 tap = tap0;
         const int ofs = ofs0;
         tap0 = tap1; ofs0 = ofs1; ofs1 = ofs2;
-        if (l + 2 < L) tap1 = *reinterpret_cast<const uint4*>(qbase + ofs1);   // prefetch the pop two layers ahead
+        if (l + 2 < L && !(p.dbg & 1)) tap1 = *reinterpret_cast<const uint4*>(qbase + ofs1);   // prefetch the pop two layers ahead
         if (l + 3 < L) ofs2 = sq[l + 3];
         float2 cb_next[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          cb_next[j] = cbA[j];
-          cbA[j] = cbB[j];
-          if (l + 3 <= L) cbB[j] = *reinterpret_cast<const float2*>(cbf + (l + 3) * 32 + 8 * j);
+        for (int i = 0; i < 4; i++) {
+          cb_next[i] = cbA[i];
+          cbA[i] = cbB[i];
+          if (l + 3 <= L && !(p.dbg & 2)) cbB[i] = *reinterpret_cast<const float2*>(cbf + (l + 3) * 32 + 8 * i);
         }
-        // ---- filter conv (ops.py:6-10): taps (k-tiles 0,1: W[0] on h[t-d]) and current (k-tiles 2,3: W[1] on h[t]);
-        //      eight independent MMAs first, their eight dependants second
-        float acc[4][2], acc2[4][2];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          acc[j][0] = acc[j][1] = acc2[j][0] = acc2[j][1] = 0.f;
-          mma8(acc[j], tap.x, tap.y, wf[2 * j].x, wf[2 * j].y);
-          mma8(acc2[j], hA[0], hA[1], wf[2 * j + 1].x, wf[2 * j + 1].y);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          mma8(acc[j], tap.z, tap.w, wf[2 * j].z, wf[2 * j].w);
-          mma8(acc2[j], hA[2], hA[3], wf[2 * j + 1].z, wf[2 * j + 1].w);
-        }
+        // ---- filter conv (ops.py:6-10), n-tile j: taps (W[0] on h[t-d]) and current (W[1] on h[t]) as two
+        //      independent accumulation chains
+        float acc[2] = {0.f, 0.f}, acc2[2] = {0.f, 0.f};
+        mma8(acc, tap.x, tap.y, wft.x, wft.y);
+        mma8(acc2, hA[0], hA[1], wfc.x, wfc.y);
+        mma8(acc, tap.z, tap.w, wft.z, wft.w);
+        mma8(acc2, hA[2], hA[3], wfc.z, wfc.w);
         uint4 wr[4];                                     // residual B fragments: land while the gate runs
 #pragma unroll
-        for (int j = 0; j < 4; j++) wr[j] = lds128_ro(wl + 4096 + j * 512);
-        // push h[t] (the slot held h[t-d] until now)
-        *reinterpret_cast<uint4*>(qbase + ofs) = make_uint4(hA[0], hA[1], hA[2], hA[3]);
-        // ---- gate (ops.py:28,33,36) -> A fragments of the residual / skip convs
-        const float* bf = reinterpret_cast<const float*>(smem + Smem::chain + l * kChainLayerBytes + 6144) + 2 * q;
+        for (int i = 0; i < 4; i++) wr[i] = lds128_ro(wl + 4096 + i * 512);
+        // push h[t] (the slot held h[t-d] until now); every chain warp holds the same image
+        if (j == 0 && !(p.dbg & 4)) *reinterpret_cast<uint4*>(qbase + ofs) = make_uint4(hA[0], hA[1], hA[2], hA[3]);
+        // ---- gate (ops.py:28,33,36) of this warp's 8 channels -> one word of the A fragments of the residual / skip convs
+        {
+          const float2 b = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(smem + Smem::chain + l * kChainLayerBytes + 6144) + 8 * j + 2 * q);
+          const uint32_t cj = pack_h2(gate(acc[0] + acc2[0] + b.x), gate(acc[1] + acc2[1] + b.y));
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + Smem::cslots + l * kSlotBytes + j * 128 + lane * 4), "r"(cj) : "memory");
+        }
+        if (l + 1 < L) {                                 // next layer's filter-conv fragments
+          wft = lds128_ro(wl + kChainLayerBytes + (2 * j) * 512);
+          wfc = lds128_ro(wl + kChainLayerBytes + (2 * j + 1) * 512);
+        }
+        if (!(p.dbg & 8)) chain_sync();                  // the four words of every lane's slot are in place
+        if (j == 0 && lane == 0) mbar_arrive(bar(B_CFULL + l));      // release: the skip warps may read the slot
         uint32_t cA[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float2 b = *reinterpret_cast<const float2*>(bf + 8 * j);
-          cA[j] = pack_h2(gate(acc[j][0] + acc2[j][0] + b.x), gate(acc[j][1] + acc2[j][1] + b.y));
-        }
-#ifdef SRWN_AR_TIMING
-        const long long s1 = clock64() + (cA[0] & 0);
-#endif
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Smem::cslots + l * kSlotBytes + lane * 16),
-                     "r"(cA[0]), "r"(cA[1]), "r"(cA[2]), "r"(cA[3]) : "memory");
-        // publish the slot with a plain flag store: shared-memory accesses of one warp are performed in program
-        // order, so a reader that sees the flag sees the slot.  (An mbarrier arrive has release semantics and made
-        // the chain wait for the queue push -- a global store -- to be acknowledged: ~450 clocks per layer.)
-        if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sbase + Smem::flags + l * 4), "r"(t + 1) : "memory");
-#ifdef SRWN_AR_TIMING
-        const long long s2 = clock64();
-#endif
-        if (l + 1 < L) {                                 // next layer's filter-conv fragments
-#pragma unroll
-          for (int i = 0; i < 8; i++) wf[i] = lds128_ro(wl + kChainLayerBytes + i * 512);
-        }
+        for (int i = 0; i < 4; i++)
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cA[i]) : "r"(sbase + Smem::cslots + l * kSlotBytes + i * 128 + lane * 4) : "memory");
         // ---- residual 1x1 (ops.py:39) and dense = (inputs + residual) * sqrt(1/2) (ops.py:40); the folded
         //      term carries sqrt(1/2)*bias and the next layer's conditioning (model.py:183)
         float r[4][2];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { r[j][0] = r[j][1] = 0.f; mma8(r[j], cA[0], cA[1], wr[j].x, wr[j].y); }
+        for (int i = 0; i < 4; i++) { r[i][0] = r[i][1] = 0.f; mma8(r[i], cA[0], cA[1], wr[i].x, wr[i].y); }
 #pragma unroll
-        for (int j = 0; j < 4; j++) mma8(r[j], cA[2], cA[3], wr[j].z, wr[j].w);
+        for (int i = 0; i < 4; i++) mma8(r[i], cA[2], cA[3], wr[i].z, wr[i].w);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          h[j][0] = fmaf(h[j][0] + r[j][0], SRWN_SQRT_HALF, cb_next[j].x);
-          h[j][1] = fmaf(h[j][1] + r[j][1], SRWN_SQRT_HALF, cb_next[j].y);
+        for (int i = 0; i < 4; i++) {
+          h[i][0] = fmaf(h[i][0] + r[i][0], SRWN_SQRT_HALF, cb_next[i].x);
+          h[i][1] = fmaf(h[i][1] + r[i][1], SRWN_SQRT_HALF, cb_next[i].y);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) hA[j] = pack_h2(h[j][0], h[j][1]);
-#ifdef SRWN_AR_TIMING
-        const long long s3 = clock64() + (hA[0] & 0);
-        tl1 += s1 - s0; tl2 += s2 - s1; tl3 += s3 - s2;
-#endif
+        for (int i = 0; i < 4; i++) hA[i] = pack_h2(h[i][0], h[i][1]);
       }
-      __syncwarp();                                      // the slot offsets are dead: the scratch becomes logits again
 
-      // ---- head, last stage: relu(hidden) @ H2 -> logits (model.py:194-196) -------------------------
+      // ---- head, last stage (chain warp 0): relu(hidden) @ H2 -> logits (model.py:194-196), sampler -----------
+      float xs = 0.f;
       const long long c1 = clock64();
-      if (!mbar_wait(bar(B_HID2), (uint32_t)(t & 1), abort_flag)) break;
-      const long long c2 = clock64();
-      const long long it = it_base + L + 4;
-      const int st = (int)(it % kStages);
-      if (!mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag)) break;
-      float lg[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-      {
-        const uint32_t hb = sbase + Smem::cslots + (hid_slot + 8) * kSlotBytes + lane * 8;   // hid2 tiles
-        const uint32_t wb = sbase + Smem::ring + st * kItemBytes + lane * 16;
+      long long c2 = c1;
+      if (j == 0) {
+        ok = ok && ((p.dbg & 32) || mbar_wait(bar(B_HID2), (uint32_t)(t & 1), abort_flag));
+        c2 = clock64();
+        const long long it = it_base + L + 4;
+        const int st = (int)(it % kStages);
+        ok = ok && ((p.dbg & 16) || mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag));
+        float lg[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+        {
+          const uint32_t hb = sbase + Smem::cslots + (hid_slot + 8) * kSlotBytes + lane * 8;   // hid2 tiles
+          const uint32_t wb = sbase + Smem::ring + st * kItemBytes + lane * 16;
 #pragma unroll
-        for (int kp = 0; kp < 4; kp++) {
-          const uint2 a0 = lds64(hb + (2 * kp) * kSlotBytes), a1 = lds64(hb + (2 * kp + 1) * kSlotBytes);
+          for (int kp = 0; kp < 4; kp++) {
+            const uint2 a0 = lds64(hb + (2 * kp) * kSlotBytes), a1 = lds64(hb + (2 * kp + 1) * kSlotBytes);
 #pragma unroll
-          for (int j = 0; j < 3; j++) {
-            const uint4 w = lds128(wb + (j * 4 + kp) * 512);
-            mma8(lg[j], a0.x, a0.y, w.x, w.y);
-            mma8(lg[j], a1.x, a1.y, w.z, w.w);
+            for (int i = 0; i < 3; i++) {
+              const uint4 w = lds128(wb + (i * 4 + kp) * 512);
+              mma8(lg[i], a0.x, a0.y, w.x, w.y);
+              mma8(lg[i], a1.x, a1.y, w.z, w.w);
+            }
           }
         }
-      }
-      __syncwarp();
-      if (lane < 8) mbar_arrive(bar(B_WEMPTY + st));    // this item has one consumer warp: 8 lanes stand in for 8 warps
-      {
-        const float* b2 = reinterpret_cast<const float*>(smem + Smem::hbias) + 256;
-        float* sl = reinterpret_cast<float*>(smem + Smem::logits) + g * 24;
+        __syncwarp();
+        if (lane < 8) mbar_arrive(bar(B_WEMPTY + st));    // this item has one consumer warp: 8 lanes stand in for 8 warps
+        {
+          const float* b2 = reinterpret_cast<const float*>(smem + Smem::hbias) + 256;
+          float* sl = reinterpret_cast<float*>(smem + Smem::logits) + g * 24;
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          sl[8 * j + 2 * q] = lg[j][0] + b2[8 * j + 2 * q];
-          sl[8 * j + 2 * q + 1] = lg[j][1] + b2[8 * j + 2 * q + 1];
+          for (int i = 0; i < 3; i++) {
+            sl[8 * i + 2 * q] = lg[i][0] + b2[8 * i + 2 * q];
+            sl[8 * i + 2 * q + 1] = lg[i][1] + b2[8 * i + 2 * q + 1];
+          }
         }
-      }
-      __syncwarp();
-      float xs = 0.f;
-      if (samp) {
-        const float* sl = reinterpret_cast<const float*>(smem + Smem::logits) + lane * 24;
-        float lgv[24];
+        __syncwarp();
+        if (samp) {
+          const float* sl = reinterpret_cast<const float*>(smem + Smem::logits) + lane * 24;
+          float lgv[24];
 #pragma unroll
-        for (int j = 0; j < 24; j++) lgv[j] = sl[j];
-        int k;
-        xs = mol_sample_one(lgv, u1v, u2v, p.M, &k);    // ops.py:178-201
-        p.x_out[(size_t)ub * p.T + t] = xs;
-        if (p.logits_out) {
-          float* dst = p.logits_out + ((size_t)ub * p.T + t) * O;
-          for (int j = 0; j < O; j++) dst[j] = lgv[j];
+          for (int i = 0; i < 24; i++) lgv[i] = sl[i];
+          int k;
+          xs = mol_sample_one(lgv, u1v, u2v, p.M, &k);    // ops.py:178-201
+          p.x_out[(size_t)ub * p.T + t] = xs;
+          if (p.logits_out) {
+            float* dst = p.logits_out + ((size_t)ub * p.T + t) * O;
+            for (int i = 0; i < O; i++) dst[i] = lgv[i];
+          }
         }
+        if (lane < kU) sx[lane] = xs;
+        if (!ok) sx[8] = -1.f;                            // tells the other chain warps to stop
       }
-      __syncwarp();
-      xm2 = xm1;
-      xm1 = __shfl_sync(0xffffffffu, xs, g);
       const long long c3 = clock64();
-      tm_a += c1 - c0; tm_b += c2 - c1; tm_c += c3 - c2;
+      chain_sync();
+      xm2 = xm1;
+      xm1 = sx[g];
+      tm_a += c1 - c0; tm_b += c2 - c1; tm_c += c3 - c2; tm_d += clock64() - c3;
+      if (sx[8] < 0.f) break;
     }
 #ifdef SRWN_AR_TIMING
-    if (lane == 0 && blockIdx.x == 0) printf("chain: layers %lld clk/step, wait skip/head %lld, head+sampler %lld | per layer: conv+gate %lld, slot+arrive %lld, residual %lld\n", tm_a / p.T, tm_b / p.T, tm_c / p.T, tl1 / p.T / L, tl2 / p.T / L, tl3 / p.T / L);
+    if (lane == 0 && blockIdx.x == 0) printf("chain warp %d: layers %lld clk/step, wait hid2 %lld, head+sampler %lld, final sync %lld\n", j, tm_a / p.T, tm_b / p.T, tm_c / p.T, tm_d / p.T);
 #endif
-    if (lane == 0 && *abort_flag) atomicExch(p.err, 1);
+    if (j == 0 && lane == 0 && *abort_flag) atomicExch(p.err, 1);
     return;
   }
 
   // ================= skip warps: skip 1x1 summed over layers, then the S->S conv of the head =========
-  const int sw = warp < 4 ? warp - 1 : (warp < 8 ? warp - 2 : warp - 3);     // warps 1,2,3,5,6,7,9,10 -> 0..7
+  const int sw = warp - 5;                                // warps 5..12 -> 0..7
+  if (p.dbg & 32) return;
   const float* shb = reinterpret_cast<const float*>(smem + Smem::hbias);
   long long it = 0;
   for (int t = 0; t < p.T; t++) {
@@ -410,17 +399,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     bool ok = true;
     for (int l = 0; l < L && ok; l++, it++) {
       const int st = (int)(it % kStages);
-      ok = mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag);
-      if (ok) {                                          // gate slot of layer l written for step t?
-        const uint32_t fa = sbase + Smem::flags + l * 4;
-        int seen, spins = 0;
-        do {
-          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(fa) : "memory");
-          if (seen != t + 1 && (++spins & 1023) == 0 && *abort_flag) { ok = false; break; }
-        } while (seen != t + 1);
-      }
+      ok = ((p.dbg & 16) || mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag)) &&
+           mbar_wait(bar(B_CFULL + l), (uint32_t)(t & 1), abort_flag);      // suspended, not spinning: the chain warps share the SMSPs
       if (!ok) break;
-      const uint4 a = lds128(sbase + Smem::cslots + l * kSlotBytes + lane * 16);
+      uint4 a;                                           // gate output: word i = n-tile i of row g
+      {
+        const uint32_t ca = sbase + Smem::cslots + l * kSlotBytes + lane * 4;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a.x) : "r"(ca) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a.y) : "r"(ca + 128) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a.z) : "r"(ca + 256) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a.w) : "r"(ca + 384) : "memory");
+      }
       const uint32_t wb = sbase + Smem::ring + st * kItemBytes + sw * 1024 + lane * 16;
       const uint4 w0 = lds128(wb), w1 = lds128(wb + 512);
       mma8(acc[0], a.x, a.y, w0.x, w0.y);
@@ -443,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     float hd[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     for (int i = 0; i < 4 && ok; i++, it++) {           // H1 arrives as 4 items of two k-tiles each
       const int st = (int)(it % kStages);
-      ok = mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag);
+      ok = (p.dbg & 16) || mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag);
       if (!ok) break;
       const uint32_t wb = sbase + Smem::ring + st * kItemBytes + sw * 1024 + lane * 16;
       const uint4 w0 = lds128(wb), w1 = lds128(wb + 512);
@@ -590,6 +579,7 @@ int run_ar_mma(srwn_ctx* c, const float* enc, const float* u1, const float* u2, 
     if (c->dilations[l] & (c->dilations[l] - 1)) pow2 = false;
   }
   p.sum_d = pow2 ? -c->sum_dilation : c->sum_dilation;
+  p.dbg = getenv("SRWN_AR_DBG") ? atoi(getenv("SRWN_AR_DBG")) : 0;
   SRWN_CUDA(cudaFuncSetAttribute(armma::k_ar_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, armma::Smem::total));
   ProfScope prof(c, st, "k_ar_mma", 1);
   armma::k_ar_mma<<<w.grid, armma::kThreads, armma::Smem::total, st>>>(p);
