@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SRWN_ABI_VERSION 3
+#define SRWN_ABI_VERSION 4
 
 enum srwn_status {
   SRWN_OK = 0,
@@ -179,6 +179,44 @@ int srwn_mol_loss_grad(const float* x, const float* l, float* dx, float* nll_out
 int srwn_adam_step(srwn_handle_t h, const float* grads, float* m, float* v, float* scratch,
                    float clip_norm, float lr, float beta1, float beta2, float eps, int32_t step,
                    void* stream);
+
+/* ---- teacher encoder (model.py:137-155; SURVEY.md 8(f)-1, the row next to the hot path) ---------
+ * A separate handle: the encoder shares no variable with the decoder.  createEncoder stacks
+ * ResidualDilationLayerNC (ops.py:48-57): relu -> K=2 conv with SAME padding (looks one step AHEAD,
+ * `dilation_rate` is ignored) -> relu -> 1x1 "residual" (no skip connection) and 1x1 skip; the skips
+ * are summed, reduced to `latent_channels` by a 1x1 conv and average-pooled by `pool_stride`. */
+typedef struct srwn_encoder_config {
+  int32_t n_layers;           /* len(dilations): layers after nc_conv (model.py:144) */
+  int32_t filter_width;       /* kernels are built for 2 */
+  int32_t encoder_channels;   /* model.py:76 encoder_channels (128) */
+  int32_t skip_channels;      /* teacher.py:62 -> 128 */
+  int32_t latent_channels;    /* teacher.py:44 -> 32 */
+  int32_t pool_stride;        /* teacher.py:38 -> 128 */
+} srwn_encoder_config_t;
+typedef struct srwn_encoder* srwn_encoder_t;
+
+int srwn_encoder_create(const srwn_encoder_config_t* cfg, srwn_encoder_t* out);
+int srwn_encoder_destroy(srwn_encoder_t e);
+/* TF variable names under "WaveNetAutoEncoder/Encoder/": "<layer>_NC/conv1d/{kernel,bias}" with
+ * <layer> = nc_conv | dilated_conv_<i>, "conv1d[_<n>]/{kernel,bias}" with n = 2j residual / 2j+1
+ * skip of layer j (0 = nc_conv, whose skip is dead: model.py:141) and n = 2(n_layers+1) the latent
+ * conv.  HOST fp32, TF layout. */
+int srwn_encoder_set_weight(srwn_encoder_t e, const char* name, const float* data,
+                            const int64_t* shape, int32_t ndim);
+int srwn_encoder_commit(srwn_encoder_t e, void* stream);
+int srwn_encoder_supports(srwn_encoder_t e, int32_t precision);
+int srwn_encoder_workspace_bytes(srwn_encoder_t e, int32_t B, int32_t T, int32_t precision,
+                                 size_t* bytes);
+/* encode(inputs) (model.py:250-255): x [B,T] audio -> encoding [B, T/pool_stride, latent].
+ * SRWN_FP32: FFMA kernels (parity grade).  SRWN_FP16 / SRWN_BF16: tcgen05 kernels, one launch per
+ * layer, 16-bit activations between layers (needs encoder_channels = 128, T % 128 == 0,
+ * pool_stride % 128 == 0). */
+int srwn_teacher_encode(srwn_encoder_t e, const float* x, float* encoding, int32_t B, int32_t T,
+                        int32_t precision, void* workspace, size_t workspace_bytes, void* stream);
+int srwn_encoder_check_async_error(srwn_encoder_t e, int32_t B, int32_t T, int32_t precision,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+int srwn_encoder_set_profiling(srwn_encoder_t e, int32_t enable);
+int srwn_encoder_last_ms(srwn_encoder_t e, float* ms);
 
 /* ---- stateless ops (ops.py) ----------------------------------------------------- */
 /* _DilatedCausalConv1d / DilatedCausalConv1d (ops.py:6-20): x [B,T,Cin],

@@ -220,6 +220,59 @@ def teacher_decoder_logits(weights, truth, encoding, dilations, pool_stride,
         weights[prefix + 'conv1d_%d/bias' % (3 * n + 1)]                  # :196
 
 
+def residual_dilation_layer_nc(inputs, conv_kernel, conv_bias, res_kernel, res_bias,
+                               skip_kernel=None, skip_bias=None):
+    """ops.py:48-57  ResidualDilationLayerNC -> (residual, skip).
+
+    x = relu(inputs); x = relu(conv1d(x, k=K, padding='SAME')) -- NOT causal and NOT dilated (the
+    ``dilation_rate`` argument is never passed on, ops.py:51): for K=2 TF's SAME pads one zero on the
+    RIGHT, so out[t] = x[t] @ W[0] + x[t+1] @ W[1].  ``residual`` is the 1x1 conv alone (no skip
+    connection to ``inputs``, ops.py:54,57); ``skip`` the second 1x1 conv."""
+    x = np.maximum(inputs, 0)                                             # :49
+    K = conv_kernel.shape[0]
+    B, T, _ = x.shape
+    left = (K - 1) // 2                                                   # SAME: extra padding goes to the end
+    padded = np.concatenate([np.zeros((B, left, x.shape[2]), x.dtype), x,
+                             np.zeros((B, K - 1 - left, x.shape[2]), x.dtype)], axis=1)
+    conv = 0
+    for k in range(K):
+        conv = conv + padded[:, k:k + T, :] @ conv_kernel[k]
+    x = np.maximum(conv + conv_bias, 0)                                   # :51-52
+    residual = x @ res_kernel[0] + res_bias                               # :54
+    skip = None if skip_kernel is None else x @ skip_kernel[0] + skip_bias  # :55
+    return residual, skip
+
+
+def teacher_encoder(weights, inputs, n_layers, pool_stride, prefix='WaveNetAutoEncoder/Encoder/'):
+    """model.py:137-155  createEncoder: inputs [B,T] -> encoding [B, T/P, latent].
+
+    ``nc_conv`` (1 -> E channels, its skip discarded, :141-142) then ``n_layers`` =
+    len(dilations) layers of ResidualDilationLayerNC (:144-149), sum of skips (:151), 1x1 to the
+    latent channels (:152), average pooling window = stride = pool_stride, VALID (:154).
+    Variable names follow tf.layers' default numbering inside the ``Encoder`` scope: layer j
+    (0 = nc_conv, i+1 = dilated_conv_i) owns ``<name>_NC/conv1d`` (the K=2 conv), ``conv1d_{2j}``
+    (residual) and ``conv1d_{2j+1}`` (skip; ``conv1d`` without suffix for index 0); the latent conv is
+    ``conv1d_{2(n_layers+1)}``."""
+    W = lambda n: weights[prefix + n]
+    cname = lambda idx: 'conv1d' if idx == 0 else 'conv1d_%d' % idx
+    h = inputs[:, :, None]
+    h, _ = residual_dilation_layer_nc(h, W('nc_conv_NC/conv1d/kernel'), W('nc_conv_NC/conv1d/bias'),
+                                      W(cname(0) + '/kernel'), W(cname(0) + '/bias'))
+    total = None
+    for i in range(n_layers):
+        name = 'dilated_conv_%d_NC/conv1d' % i
+        j = i + 1
+        h, skip = residual_dilation_layer_nc(h, W(name + '/kernel'), W(name + '/bias'),
+                                             W(cname(2 * j) + '/kernel'), W(cname(2 * j) + '/bias'),
+                                             W(cname(2 * j + 1) + '/kernel'), W(cname(2 * j + 1) + '/bias'))
+        total = skip if total is None else total + skip                   # :151
+    lat = cname(2 * (n_layers + 1))
+    reduced = total @ W(lat + '/kernel')[0] + W(lat + '/bias')            # :152
+    B, T, C = reduced.shape
+    frames = T // pool_stride                                             # VALID pooling drops a ragged tail
+    return reduced[:, :frames * pool_stride].reshape(B, frames, pool_stride, C).mean(axis=2)   # :154
+
+
 def teacher_nll(weights, truth, encoding, dilations, pool_stride, sum_all=True):
     """model.py:114-115  loss_encoding = discretized_mix_logistic_loss(labels_truth, logits)."""
     logits = teacher_decoder_logits(weights, truth, encoding, dilations, pool_stride)

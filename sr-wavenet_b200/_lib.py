@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRWN_LIB") or os.path.join(_HERE, "libsrwn.so")   # SRWN_LIB: tuning builds (tools/exp_build.sh)
 
-ABI_VERSION = 3      # SRWN_ABI_VERSION in include/srwn.h
+ABI_VERSION = 4      # SRWN_ABI_VERSION in include/srwn.h
 OK, ERR_INVALID, ERR_CUDA, ERR_WEIGHTS, ERR_UNSUPPORTED, ERR_WORKSPACE = range(6)
 TEACHER, STUDENT = 0, 1
 FP32, BF16, FP16 = 0, 1, 2
@@ -28,6 +28,12 @@ class Config(ctypes.Structure):
                 ("dilation_channels", ctypes.c_int32), ("skip_channels", ctypes.c_int32),
                 ("cond_channels", ctypes.c_int32), ("pool_stride", ctypes.c_int32),
                 ("num_mixtures", ctypes.c_int32), ("num_flows", ctypes.c_int32)]
+
+
+class EncoderConfig(ctypes.Structure):
+    _fields_ = [("n_layers", ctypes.c_int32), ("filter_width", ctypes.c_int32),
+                ("encoder_channels", ctypes.c_int32), ("skip_channels", ctypes.c_int32),
+                ("latent_channels", ctypes.c_int32), ("pool_stride", ctypes.c_int32)]
 
 
 _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
@@ -60,6 +66,16 @@ SIGNATURES = {
     "srwn_mol_loss_grad": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp]),
     "srwn_adam_step": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_float, ctypes.c_float, _i32, _vp]),
+    "srwn_encoder_create": (ctypes.c_int, [ctypes.POINTER(EncoderConfig), ctypes.POINTER(_vp)]),
+    "srwn_encoder_destroy": (ctypes.c_int, [_vp]),
+    "srwn_encoder_set_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(_i64), _i32]),
+    "srwn_encoder_commit": (ctypes.c_int, [_vp, _vp]),
+    "srwn_encoder_supports": (ctypes.c_int, [_vp, _i32]),
+    "srwn_encoder_workspace_bytes": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(_sz)]),
+    "srwn_teacher_encode": (ctypes.c_int, [_vp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_encoder_check_async_error": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_encoder_set_profiling": (ctypes.c_int, [_vp, _i32]),
+    "srwn_encoder_last_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "srwn_dilated_causal_conv1d": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "srwn_residual_dilation_layer": (ctypes.c_int, [_fp] * 9 + [_i32] * 6 + [_vp]),
     "srwn_right_shift": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),

@@ -5,8 +5,8 @@ call into libsrwn.so (include/srwn.h).  Like the reference's ``feed_dict`` bound
 NumPy arrays (or torch tensors) and return NumPy arrays; CUDA tensors in -> CUDA tensors out,
 with no host copies (used for device-resident benchmarking).
 
-Outside the hot path: the teacher encoder (``encode`` / ``reconstruct``) and
-training (``train`` / ``train_fast``) raise NotImplementedError.
+The teacher encoder (``encode`` / ``reconstruct``) runs through its own handle
+(``srwn_encoder_*``); teacher training (``train``) raises NotImplementedError.
 """
 import ctypes
 import os
@@ -116,6 +116,69 @@ class _Engine(object):
         return buf.numpy().copy()
 
 
+class _EncoderEngine(object):
+    """Owns one libsrwn encoder handle (include/srwn.h, srwn_encoder_*) and its workspace."""
+
+    def __init__(self, n_layers, filter_width, encoder_channels, skip_channels, latent_channels, pool_stride):
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("the SR-WaveNet encoder needs a CUDA device (no CPU fallback)")
+        cfg = _lib.EncoderConfig(n_layers, filter_width, encoder_channels, skip_channels, latent_channels,
+                                 pool_stride)
+        h = ctypes.c_void_p()
+        _lib.check(lib.srwn_encoder_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self.lib, self.h = lib, h
+        self.latent_channels, self.pool_stride = latent_channels, pool_stride
+        self._ws = None
+        self.committed = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.srwn_encoder_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_weights(self, weights):
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+            _lib.check(self.lib.srwn_encoder_set_weight(self.h, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
+                                                        shape, a.ndim))
+        _lib.check(self.lib.srwn_encoder_commit(self.h, torch.cuda.current_stream().cuda_stream))
+        self.committed = True
+
+    def supports(self, prec):
+        return bool(self.lib.srwn_encoder_supports(self.h, prec))
+
+    def set_profiling(self, enable):
+        _lib.check(self.lib.srwn_encoder_set_profiling(self.h, int(bool(enable))))
+
+    def last_ms(self):
+        ms = ctypes.c_float()
+        _lib.check(self.lib.srwn_encoder_last_ms(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def workspace(self, B, T, prec):
+        n = ctypes.c_size_t()
+        _lib.check(self.lib.srwn_encoder_workspace_bytes(self.h, B, T, prec, ctypes.byref(n)))
+        if self._ws is None or self._ws.numel() < n.value:
+            self._ws = None
+            self._ws = torch.empty(max(n.value, 256), dtype=torch.uint8, device="cuda")
+        return self._ws.data_ptr(), self._ws.numel()
+
+    def encode(self, x, prec, check=True):
+        """x: CUDA fp32 [B,T] -> CUDA fp32 [B, T // P, latent]."""
+        B, T = x.shape
+        ws, wsn = self.workspace(B, T, prec)
+        out = torch.empty(B, T // self.pool_stride, self.latent_channels, dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.srwn_teacher_encode(self.h, x.data_ptr(), out.data_ptr(), B, T, prec, ws, wsn, _stream()))
+        if check and prec != _lib.FP32:
+            _lib.check(self.lib.srwn_encoder_check_async_error(self.h, B, T, prec, ws, wsn, _stream()))
+        return out
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -167,7 +230,7 @@ class _CheckpointMixin(object):
 
 
 class WaveNetAutoEncoder(_CheckpointMixin):
-    """model.py:75-285.  Decoder path only (the hot path); constructor signature kept verbatim."""
+    """model.py:75-285: decoder (the hot path) and encoder; constructor signature kept verbatim."""
 
     def __init__(self, input_size, condition_size, num_mixtures, dilations, filter_width=2,
                  encoder_channels=128, dilation_channels=32, skip_channels=256, latent_channels=16,
@@ -198,15 +261,21 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         w = synth.make_teacher_weights(self.dilations, self.filter_width, self.dilation_channels,
                                        self.skip_channels, self.latent_channels + self.condition_size,
                                        self.num_mixtures, seed=None, dead_vars=True)
-        for k in w:                      # TF initialises biases to zero (ops.py:18)
+        self._enc_eng = _EncoderEngine(len(self.dilations), self.filter_width, self.encoder_channels,
+                                       self.skip_channels, self.latent_channels, self.pool_stride)
+        we = synth.make_encoder_weights(len(self.dilations), self.filter_width, self.encoder_channels,
+                                        self.skip_channels, self.latent_channels, seed=None, gain=1.0)
+        w.update(we)
+        for k in w:                      # TF initialises biases to zero (ops.py:18, tf.layers default)
             if k.endswith('Bias') or k.endswith('/bias'):
                 w[k][...] = 0
         self._weights = {}
         self.set_weights(w)
 
-    def createEncoder(self, h, reuse=False):
-        raise NotImplementedError("the teacher encoder (model.py:137-155) is outside the hot path; "
-                                  "pass a precomputed `encoding`")
+    def createEncoder(self, h, reuse=False, precision=None):
+        """model.py:137-155 -> encoding [B, T/pool_stride, latent].  h [B,T,1] or [B,T]."""
+        h2 = h[..., 0] if getattr(h, "ndim", 2) == 3 else h
+        return self.encode(h2, precision=precision)
 
     def createDecoder(self, truth, encoding, conditions, reuse=False, u1=None, u2=None, precision=None):
         """model.py:158-200 -> (logits [B,T,4M], out [B,T]).  truth [B,T,1] or [B,T]."""
@@ -221,8 +290,14 @@ class WaveNetAutoEncoder(_CheckpointMixin):
 
     # -- weights -----------------------------------------------------------------------------
     def set_weights(self, weights):
-        """name -> ndarray with TF variable names (``WaveNetAutoEncoder/Decoder/...``)."""
-        self._eng.set_weights(weights)
+        """name -> ndarray with TF variable names (``WaveNetAutoEncoder/Decoder/...`` and
+        ``WaveNetAutoEncoder/Encoder/...``); either half may be given alone."""
+        dec = {k: v for k, v in weights.items() if '/Encoder/' not in k}
+        enc = {k: v for k, v in weights.items() if '/Encoder/' in k}
+        if dec:
+            self._eng.set_weights(dec)
+        if enc:
+            self._enc_eng.set_weights(enc)
         self._weights.update({k: np.array(v, dtype=np.float32) for k, v in weights.items()})
 
     def get_weights(self):
@@ -241,12 +316,24 @@ class WaveNetAutoEncoder(_CheckpointMixin):
     def train(self, inputs, conditions=None):
         raise NotImplementedError("teacher training (model.py:242-248) is outside the hot path")
 
-    def encode(self, inputs, conditions=None):
-        raise NotImplementedError("the teacher encoder (model.py:250-255) is outside the hot path")
+    def encode(self, inputs, conditions=None, precision=None):
+        """model.py:250-255 -> encoding [B, T/pool_stride, latent] (``conditions`` does not enter the
+        encoder graph, model.py:212).  A ragged tail T % pool_stride is dropped like the VALID pooling
+        of model.py:154 does.  The 16-bit tensor-core path needs T % 128 == 0; other lengths run fp32."""
+        eng = self._enc_eng
+        x, on_dev = self._eng.to_device(inputs, "x")
+        prec = self._prec(precision)
+        if prec != _lib.FP32 and (not eng.supports(prec) or x.shape[1] % 128 != 0):
+            prec = _lib.FP32
+        return self._eng.to_host(eng.encode(x, prec), on_dev)
 
-    def reconstruct(self, inputs, conditions=None):
-        raise NotImplementedError("reconstruct (model.py:257-262) needs the encoder; use "
-                                  "reconstruct_with_encoding(inputs, encoding)")
+    def reconstruct(self, inputs, conditions=None, u1=None, u2=None, precision=None):
+        """model.py:257-262 -> [B,T]: encoder, then the decoder teacher-forced on the same audio, then
+        parallel sampling from the logits (``self.out``)."""
+        x, on_dev = self._eng.to_device(inputs, "x")
+        enc = self.encode(x, precision=precision)
+        out = self.reconstruct_with_encoding(x, enc, conditions, u1=u1, u2=u2, precision=precision)
+        return out if on_dev else out.cpu().numpy()
 
     def _prec(self, precision):
         return _lib.PRECISIONS[precision or self.precision]
@@ -570,8 +657,16 @@ class ParallelWaveNet(_CheckpointMixin):
         loss's norm, which the reference takes per example there.  The batched graph is used."""
         return self.train_fast(sess, inputs, truth, encoding, conditions, **kw)
 
-    def encode(self, sess, inputs, conditions=None):
-        raise NotImplementedError("the teacher encoder (model.py:644-649) is outside the hot path")
+    def _need_teacher(self):
+        if not isinstance(self.teacher, WaveNetAutoEncoder):
+            raise RuntimeError("this call evaluates the imported teacher graph (model.py:326-334): construct "
+                               "ParallelWaveNet with teacher=<WaveNetAutoEncoder instance>")
+        return self.teacher
 
-    def reconstruct(self, sess, inputs, conditions=None):
-        raise NotImplementedError("reconstruct (model.py:651-656) needs the teacher encoder")
+    def encode(self, sess, inputs, conditions=None, precision=None):
+        """model.py:644-649: the imported teacher's ``Encoding_output`` on ``inputs``."""
+        return self._need_teacher().encode(inputs, conditions, precision=precision)
+
+    def reconstruct(self, sess, inputs, conditions=None, **kw):
+        """model.py:651-656: the imported teacher's ``Out_e`` (encoder + teacher-forced decoder + sampling)."""
+        return self._need_teacher().reconstruct(inputs, conditions, **kw)

@@ -85,6 +85,42 @@ def make_student_weights(dilations=DEFAULT_DILATIONS, num_flows=4, filter_width=
     return w
 
 
+ENCODER_PREFIX = 'WaveNetAutoEncoder/Encoder/'
+
+
+def encoder_conv_name(idx):
+    """idx-th tf.layers.conv1d created directly in the Encoder scope (ops.py:54-55, model.py:152)."""
+    return 'conv1d' if idx == 0 else 'conv1d_%d' % idx
+
+
+def make_encoder_weights(n_layers=len(DEFAULT_DILATIONS), filter_width=2, encoder_channels=128,
+                         skip_channels=128, latent_channels=32, seed=44, dtype=np.float32,
+                         dead_vars=True, gain=2.0):
+    """Teacher encoder variables (model.py:137-155, ops.py:48-57).  Layer j (0 = ``nc_conv``,
+    i+1 = ``dilated_conv_i``): ``<name>_NC/conv1d`` [K,Cin,E], ``conv1d_{2j}`` residual [1,E,E],
+    ``conv1d_{2j+1}`` skip [1,E,S] (dead for nc_conv: model.py:141 discards it); latent conv
+    ``conv1d_{2(n+1)}`` [1,S,latent].  The residual kernels are Glorot x ``gain``: the encoder has no
+    skip connection around its two relus per layer, so with plain Glorot the signal halves per layer
+    and the encoding would be bias noise, useless as a parity probe."""
+    rng = np.random.default_rng(seed)
+    p, E, S = ENCODER_PREFIX, encoder_channels, skip_channels
+    w = {}
+    for j in range(n_layers + 1):
+        name = 'nc_conv' if j == 0 else 'dilated_conv_%d' % (j - 1)
+        cin = 1 if j == 0 else E
+        w['%s%s_NC/conv1d/kernel' % (p, name)] = _glorot(rng, (filter_width, cin, E), dtype)
+        w['%s%s_NC/conv1d/bias' % (p, name)] = _bias(rng, (E,), dtype)
+        w[p + encoder_conv_name(2 * j) + '/kernel'] = (_glorot(rng, (1, E, E), dtype) * gain).astype(dtype)
+        w[p + encoder_conv_name(2 * j) + '/bias'] = _bias(rng, (E,), dtype)
+        if j > 0 or dead_vars:
+            w[p + encoder_conv_name(2 * j + 1) + '/kernel'] = _glorot(rng, (1, E, S), dtype)
+            w[p + encoder_conv_name(2 * j + 1) + '/bias'] = _bias(rng, (S,), dtype)
+    lat = p + encoder_conv_name(2 * (n_layers + 1))
+    w[lat + '/kernel'] = _glorot(rng, (1, S, latent_channels), dtype)
+    w[lat + '/bias'] = _bias(rng, (latent_channels,), dtype)
+    return w
+
+
 def synthetic_audio(batch, length, seed=1234, dtype=np.float32):
     """NSynth-shaped synthetic clips in the style of simple_audio.py:40-61: one of
     sine/square/saw/triangle at a random frequency + N(0, 0.05) noise, min-max

@@ -84,8 +84,24 @@ def default_cfg():
              s_tot=net["s_tot"].astype(np.float32), mu_tot=net["mu_tot"].astype(np.float32))
 
 
+def encoder():
+    """Teacher encoder (model.py:137-155): a tiny generic shape with a ragged tail (fp32 path only) and
+    the teacher.py:55-62 shape (128 channels, P=128, 30 layers), B=2, T=512."""
+    L, E, S, C, P, B, T = 3, 16, 8, 4, 8, 2, 43
+    w = synth.make_encoder_weights(L, 2, E, S, C, seed=21)
+    x = synth.synthetic_audio(B, T, seed=9)
+    enc = orc.teacher_encoder(f64(w), x.astype(np.float64), L, P)
+    np.savez(os.path.join(OUT, "encoder_small.npz"), L=L, E=E, S=S, C=C, P=P, seed=21, x=x, encoding=enc)
+    L, B, T, P = len(synth.DEFAULT_DILATIONS), 2, 512, 128
+    w = synth.make_encoder_weights(L, seed=44)
+    x = synth.synthetic_audio(B, T, seed=1234)
+    enc = orc.teacher_encoder(f64(w), x.astype(np.float64), L, P)
+    np.savez(os.path.join(OUT, "encoder_default.npz"), L=L, P=P, seed=44, B=B, T=T, encoding=enc)
+
+
 if __name__ == "__main__":
     conv_kat()
     small()
     default_cfg()
+    encoder()
     print("golden vectors written to", OUT)

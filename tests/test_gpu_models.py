@@ -150,7 +150,7 @@ def test_teacher_errors(srwn):
     with pytest.raises(RuntimeError):
         t._eng.set_weights({"WaveNetAutoEncoder/Decoder/conv1d_1/kernel": np.zeros((1, 32, 31), np.float32)})
     with pytest.raises(NotImplementedError):
-        t.encode(x)
+        t.train(x)
 
 
 def test_generate_golden_small(srwn, golden_small):

@@ -166,3 +166,23 @@ def test_torch_cpu_port_matches_numpy_oracle(golden_default):
     cpu = TeacherCPU(tw, dil, P, 5)
     assert np.abs(cpu.logits(x, enc).numpy() - g["logits"]).max() < 1e-4
     assert abs(cpu.nll(x, enc) - float(g["nll_sum"])) < 1e-4 * abs(float(g["nll_sum"]))
+
+
+def test_encoder_golden_and_same_padding():
+    """Teacher encoder restatement (model.py:137-155, ops.py:48-57) against the committed vectors, plus a
+    hand-checked case of the K=2 SAME-padding tap order: out[t] = relu(x)[t] W0 + relu(x)[t+1] W1, zero past the end."""
+    import os
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "encoder_small.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    L, E, S, C, P = (int(g[k]) for k in "LESCP")
+    w = synth.make_encoder_weights(L, 2, E, S, C, seed=int(g["seed"]))
+    enc = orc.teacher_encoder(f64(w), g["x"].astype(np.float64), L, P)
+    assert np.array_equal(enc, g["encoding"])
+    x = np.array([[[1.0], [-2.0], [3.0], [4.0]]])
+    ck = np.array([[[1.0]], [[10.0]]])                    # W0 = 1, W1 = 10
+    res, skip = orc.residual_dilation_layer_nc(x, ck, np.zeros(1), np.array([[[2.0]]]), np.array([0.5]),
+                                               np.array([[[1.0, -1.0]]]), np.zeros(2))
+    # relu(x) = [1,0,3,4]; conv = [1+0, 0+30, 3+40, 4+0] = [1,30,43,4]
+    assert np.array_equal(res[0, :, 0], np.array([2.5, 60.5, 86.5, 8.5]))
+    assert np.array_equal(skip[0], np.array([[1, -1], [30, -30], [43, -43], [4, -4]], dtype=np.float64))
