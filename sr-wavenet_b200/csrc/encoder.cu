@@ -65,6 +65,7 @@ struct LayerParams {
   float* pooled;             // [n_tiles][128] column sums of y (null: front layer)
   int* err;
   int n_tiles, tiles_per_utt, T;
+  int reverse;               // walk the tiles from the end: the tail of the previous layer's output is still in L2
 };
 
 template <bool FP16>
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_layer(const LayerParams p) 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_my = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto tile_of = [&](int k) { const int i = (int)blockIdx.x + k * (int)gridDim.x; return p.reverse ? p.n_tiles - 1 - i : i; };
   constexpr uint32_t idesc = make_idesc(FP16 ? 0 : 1, 128, 128);
   constexpr int w_bytes = FRONT ? kFrontImg : kLayerImg;
   constexpr int res_off = FRONT ? 0 : kConvImg;               // residual image inside the shared weight area
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_layer(const LayerParams p) 
       if (!FRONT) {
         for (int k = 0; k < n_my; k++) {
           const int s = k % kStages;
-          const int tile = blockIdx.x + k * gridDim.x;
+          const int tile = tile_of(k);
           if (!mbar_wait(bar(B_AE + s), ((k / kStages) & 1) ^ 1, abort_flag, 0x100 | s)) break;
           const uint32_t dst = sbase + Smem::a + s * kAStage;
           const uint8_t* src = p.in + (size_t)tile * kAStage;
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_layer(const LayerParams p) 
     uint8_t* yb = smem + Smem::y;
     for (int k = 0; k < n_my; k++) {
       const int d = k & 1;
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = tile_of(k);
       float a0 = 0.f, a1 = 0.f;
       if (FRONT) {
         const int b = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * kTile + row;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_layer(const LayerParams p) 
     const float* rbias = FRONT ? s_bias + 3 * kE : s_bias + kE;
     for (int k = 0; k < n_my; k++) {
       const int s = k & 1;
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = tile_of(k);
       ok = ok && mbar_wait(bar(B_YF), k & 1, abort_flag, 0x410);
       if (do_pool && ok) {
         // column sums of the tile's y (16-bit image in shared memory): thread = (k-chunk, row residue mod 8)
@@ -326,19 +328,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_layer(const LayerParams p) 
 }
 
 // encoding[b, f, c] = bias'[c] + (1/P) * sum_l sum_ch (sum over the window's tiles of pooled[l][tile][ch]) * Wf[l][ch][c]
-__global__ void k_enc_finish(const float* __restrict__ pooled, const float* __restrict__ wf, const float* __restrict__ bf,
-                             float* __restrict__ out, int L, size_t n_tiles, int tiles_per_utt, int frames, int tiles_per_win,
-                             int C, float inv_p) {
+// One block per pooling window: the window's L*128 column sums are staged in shared memory (coalesced rows of 128
+// floats), then 8 partial dot products per output channel.
+__global__ void __launch_bounds__(256) k_enc_finish(const float* __restrict__ pooled, const float* __restrict__ wf,
+                                                    const float* __restrict__ bf, float* __restrict__ out, int L, size_t n_tiles,
+                                                    int tiles_per_utt, int frames, int tiles_per_win, int C, float inv_p) {
+  extern __shared__ float sp[];                 // [L * 128]
   __shared__ float red[8][64];
   const int win = blockIdx.x, c0 = threadIdx.x & 31, part = threadIdx.x >> 5;
   const size_t tile0 = (size_t)(win / frames) * tiles_per_utt + (size_t)(win % frames) * tiles_per_win;
-  float acc0 = 0.f, acc1 = 0.f;
-  for (int k = part; k < L * kE; k += 8) {
+  for (int k = threadIdx.x; k < L * kE; k += 256) {
     const int l = k / kE, ch = k % kE;
     float s = 0.f;
-    for (int j = 0; j < tiles_per_win; j++) s += pooled[((size_t)l * n_tiles + tile0 + j) * kE + ch];
-    if (c0 < C) acc0 = fmaf(s, wf[(size_t)k * C + c0], acc0);
-    if (c0 + 32 < C) acc1 = fmaf(s, wf[(size_t)k * C + c0 + 32], acc1);
+    for (int j = 0; j < tiles_per_win; j++) s += __ldg(pooled + ((size_t)l * n_tiles + tile0 + j) * kE + ch);
+    sp[k] = s;
+  }
+  __syncthreads();
+  float acc0 = 0.f, acc1 = 0.f;
+  const bool two = c0 + 32 < C;
+  const int cc = c0 < C ? c0 : 0;
+#pragma unroll 4
+  for (int k = part; k < L * kE; k += 8) {
+    const float s = sp[k];
+    acc0 = fmaf(s, __ldg(wf + (size_t)k * C + cc), acc0);
+    if (two) acc1 = fmaf(s, __ldg(wf + (size_t)k * C + c0 + 32), acc1);
   }
   red[part][c0] = acc0; red[part][c0 + 32] = acc1;
   __syncthreads();
@@ -733,18 +746,21 @@ extern "C" int srwn_teacher_encode(srwn_encoder_t e, const float* x, float* enc_
     const uint8_t* img = e->d_img + (fp16 ? e->img_bytes : 0);
     enc::LayerParams p;
     p.err = err; p.n_tiles = (int)n_tiles; p.tiles_per_utt = T / enc::kTile; p.T = T;
-    p.img = img; p.in = nullptr; p.x = x; p.out = act0; p.pooled = nullptr;
+    p.img = img; p.in = nullptr; p.x = x; p.out = act0; p.pooled = nullptr; p.reverse = 0;
     int rc = fp16 ? launch_layer<true, true>(e, p, st) : launch_layer<true, false>(e, p, st);
     if (rc) return rc;
     uint8_t* cur = act0; uint8_t* nxt = act1;
     for (int l = 0; l < L; l++) {
       p.img = img + enc::kFrontImg + (size_t)l * enc::kLayerImg;
       p.in = cur; p.x = nullptr; p.out = l + 1 < L ? nxt : nullptr; p.pooled = pooled + (size_t)l * n_tiles * enc::kE;
+      p.reverse = (l & 1) ^ 1;
       rc = fp16 ? launch_layer<false, true>(e, p, st) : launch_layer<false, false>(e, p, st);
       if (rc) return rc;
       uint8_t* t = cur; cur = nxt; nxt = t;
     }
-    enc::k_enc_finish<<<B * frames, 256, 0, st>>>(pooled, W + e->o_wf, W + e->o_bf, enc_out, L, n_tiles, T / enc::kTile, frames, P / enc::kTile, C, 1.f / (float)P);
+    if ((size_t)L * enc::kE * sizeof(float) > 48 * 1024)
+      SRWN_CUDA(cudaFuncSetAttribute(enc::k_enc_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, L * enc::kE * (int)sizeof(float)));
+    enc::k_enc_finish<<<B * frames, 256, (size_t)L * enc::kE * sizeof(float), st>>>(pooled, W + e->o_wf, W + e->o_bf, enc_out, L, n_tiles, T / enc::kTile, frames, P / enc::kTile, C, 1.f / (float)P);
     SRWN_LAUNCH_CHECK();
   }
   if (e->profiling) cudaEventRecord(e->ev[1], st);
