@@ -29,6 +29,8 @@ BYTES_PER_SAMPLE_AR_F16 = 3844        # same with 16-bit queue state (2*30*32*2 
 # distillation backward (fp32, layer at a time): per (sample, layer, flow) the gate kernel reads x_l and g and writes
 # da (3 x 128 B), the conv kernel reads x_l, g, da and writes dx (4 x 128 B): 896 B; x 30 layers x 4 flows
 BYTES_PER_SAMPLE_BWD = 4 * 30 * 896
+BYTES_PER_SAMPLE_ENC_LAYER = 512      # encoder layer launch: 16-bit image of relu(h), 128 channels, read + write
+FLOP_PER_SAMPLE_ENC = 2949632         # GEMMs the encoder executes: 33280 (nc_conv) + 30*65536 (K=2 convs) + 29*32768 (1x1 residuals)
 METRIC = "audio samples/sec"
 UNIT = "samples/s"
 
@@ -139,7 +141,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="teacher_nll", choices=["teacher_nll", "student", "generate", "distill"])
+    ap.add_argument("--workload", default="teacher_nll", choices=["teacher_nll", "student", "generate", "distill", "encode"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config)")
     ap.add_argument("--length", type=int, default=0)
@@ -168,7 +170,7 @@ def main():
     P = 128
 
     defaults = {"teacher_nll": (32, 64000), "student": (64 // max(world, 1) if world > 1 else 8, 64000),
-                "generate": (256, 16000), "distill": (4, 64000)}
+                "generate": (256, 16000), "distill": (4, 64000), "encode": (32, 64000)}
     B, T = defaults[args.workload]
     if args.workload == "student":
         B = 8          # configs[2]: 64 x 64000 over 8 GPUs = 8 per GPU (weak scaling unit)
@@ -192,7 +194,10 @@ def main():
         flop_per_sample = FLOP_PER_SAMPLE_STUDENT / 4.0     # the dominant kernel is one flow (one launch per flow)
     else:
         model = srwn.WaveNetAutoEncoder(T, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=P)
-        model.set_weights(synth.make_teacher_weights(dil))
+        w = synth.make_teacher_weights(dil)
+        if args.workload == "encode":
+            w.update(synth.make_encoder_weights(len(dil)))
+        model.set_weights(w)
         x_h = synth.synthetic_audio(B, T, seed=1234 + g0)
         flop_per_sample = FLOP_PER_SAMPLE_TEACHER
     prec = args.precision
@@ -221,9 +226,13 @@ def main():
             return model.nll(x_d, enc_d, precision=prec)
         if args.workload == "student":
             return model.generate(None, x_d, enc_d, precision=prec)
+        if args.workload == "encode":
+            return model.encode(x_d, precision=prec)
         return model.generate(enc_d, u1=u1_d, u2=u2_d, precision=prec)
 
     def step_e2e():
+        if args.workload == "encode":
+            return model.encode(x_p, precision=prec)                # ndarray on the host
         if args.workload == "distill":
             return model.train_fast(None, x_p, truth_p, enc_p)      # (loss, power_loss) floats on the host
         if args.workload == "teacher_nll":
@@ -235,6 +244,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     model._eng.set_profiling(True)
+    if args.workload == "encode":
+        model._enc_eng.set_profiling(True)
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
@@ -251,10 +262,13 @@ def main():
         a.record()
         step_device()
         b.record()
-        km, kern_launches, kern_name = model._eng.last_kernel_ms()
+        if args.workload == "encode":
+            km, kern_launches, kern_name = model._enc_eng.last_ms(), len(dil) + 1, "enc::k_enc_layer"
+        else:
+            km, kern_launches, kern_name = model._eng.last_kernel_ms()
         kern_ms.append(km)
     torch.cuda.synchronize()
-    if prec != "fp32" and args.workload not in ("generate", "distill"):     # a fused launch that aborted on the device is not a measurement
+    if prec != "fp32" and args.workload not in ("generate", "distill", "encode"):     # a fused launch that aborted on the device is not a measurement
         model._eng.check_async(srwn._lib.OP_TEACHER_NLL if args.workload == "teacher_nll" else srwn._lib.OP_STUDENT_FORWARD,
                                B, T, srwn._lib.PRECISIONS[prec])
     launches = srwn._lib.launch_count() - launches0
@@ -280,7 +294,10 @@ def main():
     e2e_value = units / e2e_s_max
     h2d = x_h.nbytes + enc_h.nbytes + (u1_h.nbytes + u2_h.nbytes if args.workload == "generate" else 0) + \
         (truth_h.nbytes if truth_h is not None else 0)
-    d2h = 4 if args.workload == "teacher_nll" else 16 if args.workload == "distill" else B * T * 4
+    d2h = 4 if args.workload == "teacher_nll" else 16 if args.workload == "distill" else \
+        B * (T // P) * 32 * 4 if args.workload == "encode" else B * T * 4
+    if args.workload == "encode":
+        h2d = x_h.nbytes
 
     # roofline of the dominant kernel, from this run's CUDA-event bracket around its launches
     k_ms = sum(kern_ms) / len(kern_ms) / max(kern_launches, 1)
@@ -292,6 +309,12 @@ def main():
     if args.workload == "distill":
         ach = BYTES_PER_SAMPLE_BWD * B * T / (k_ms * kern_launches * 1e-3) / 1e9     # the bracket spans the whole backward
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s"}
+    elif args.workload == "encode":
+        # one launch per layer moves the 16-bit image of relu(h): 256 B read + 256 B written per sample (the front layer
+        # reads the audio, the last layer writes only pooled sums); the skip path is folded away
+        ach = BYTES_PER_SAMPLE_ENC_LAYER * B * T / (k_ms * 1e-3) / 1e9 * (len(dil) / (len(dil) + 1.0))
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                "tensor_tflops": FLOP_PER_SAMPLE_ENC * B * T / (k_ms * kern_launches * 1e-3) / 1e12}
     elif args.workload == "generate":
         # queue pop + push of 32 channels per layer + the sample: 7684 B with fp32 state, 3844 B with fp16 state
         ach = (BYTES_PER_SAMPLE_AR if prec == "fp32" else BYTES_PER_SAMPLE_AR_F16) * B * T / (k_ms * 1e-3) / 1e9
@@ -316,6 +339,7 @@ def main():
         names = {"teacher_nll": "teacher WaveNet teacher-forced log-likelihood (BASELINE.json configs[1])",
                  "student": "student IAF parallel synthesis, 4 flows (BASELINE.json configs[2])",
                  "generate": "teacher autoregressive fast generation, dilation queues (BASELINE.json configs[3])",
+                 "encode": "teacher encoder, 31 non-causal 128-channel layers + pooled latent (SURVEY.md 8(f)-1)",
                  "distill": "student distillation training step: teacher scores real audio, KL + power loss, "
                             "all-reduce + clip + Adam (BASELINE.json configs[4])"}
         line = {
