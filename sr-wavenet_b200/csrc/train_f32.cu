@@ -28,11 +28,32 @@ constexpr int kThreads = 256;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---- warp-level TF32 tensor-core helpers (mma.sync.m16n8k8, fp32 accumulate) ------------------------------
+// The backward GEMMs are tiny in N and K (32 / 64 channels) and HBM-bound once they leave the FFMA pipe; operands are
+// rounded to TF32 (cvt.rna, 10-bit mantissa) when they are staged in shared memory, products accumulate in fp32.
+// Fragment layouts (g = lane >> 2, q = lane & 3):  A 16x8 row-major: a0 (g, q) a1 (g+8, q) a2 (g, q+4) a3 (g+8, q+4);
+// B 8x8: b0 (k = q, n = g) b1 (k = q+4, n = g);  C 16x8: c0 (g, 2q) c1 (g, 2q+1) c2 (g+8, 2q) c3 (g+8, 2q+1).
+__device__ __forceinline__ float tf32r(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32r4(float4 v) { return make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w)); }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
+                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+constexpr int kWP = kR + 8;         // pitch of B operands read as (k = q, n = g): banks 8q + g
+
 // ---- gate backward ------------------------------------------------------------------------------------
 // g = dL/dx_{l+1}; recomputes a, f, c from x_l; writes da = dL/da; accumulates dWr [32][32], dbr [32].
+// Tile = 64 time steps, 8 warps.  Stages 1-2: warp (mt = warp & 3, nh = warp >> 2) owns rows 16 mt.. and channels
+// 16 nh..; stage 3 (dWr = c^T dres over the tile's rows): warp (mi = warp & 1, ni = warp >> 1) owns one 16x8 block.
 struct GateSmem {
   float a_tap[kTT][kAP], a_cur[kTT][kAP], c[kTT][kAP], g[kTT][kAP];
-  float wf[2 * kR][kR], wr[kR][kR + 1], bf[kR];
+  float wf[2 * kR][kWP], wr[kR][kAP], bf[kR];
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -42,13 +63,15 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
            int B, int T, int d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GateSmem& s = *reinterpret_cast<GateSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 2 * kR * kR; i += kThreads) (&s.wf[0][0])[i] = filt_k[i];
-  for (int i = tid; i < kR * kR; i += kThreads) s.wr[i / kR][i % kR] = res_k[i];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  for (int i = tid; i < 2 * kR * kR; i += kThreads) s.wf[i / kR][i % kR] = tf32r(filt_k[i]);
+  for (int i = tid; i < kR * kR; i += kThreads) s.wr[i / kR][i % kR] = tf32r(res_k[i]);
   if (tid < kR) s.bf[tid] = filt_b[tid];
   const int tiles_per_b = (T + kTT - 1) / kTT;
   const int n_tiles = B * tiles_per_b;
-  float gw[4] = {0.f, 0.f, 0.f, 0.f};      // dWr[warp*4 + i][lane]
+  const int mt = warp & 3, nh = warp >> 2, r0 = mt * 16;
+  const int mi = warp & 1, ni = warp >> 1;
+  float gw[4] = {0.f, 0.f, 0.f, 0.f};      // dWr block: rows (k) 16 mi + g (+8), columns (n) 8 ni + 2q (+1)
   float gb = 0.f;                          // dbr[lane] (warp 0)
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
@@ -56,75 +79,102 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
     const float* gbp = g_in + (size_t)b * T * kR;
     __syncthreads();
     for (int i = tid; i < kTT * (kR / 4); i += kThreads) {
-      const int row = i / (kR / 4), q = i % (kR / 4);
+      const int row = i / (kR / 4), c4 = i % (kR / 4);
       const int t = t0 + row;
       float4 cur = make_float4(0, 0, 0, 0), tap = cur, gg = cur;
       if (t < T) {
-        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + q * 4);
-        gg = *reinterpret_cast<const float4*>(gbp + (size_t)t * kR + q * 4);
-        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + q * 4);
+        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + c4 * 4);
+        gg = *reinterpret_cast<const float4*>(gbp + (size_t)t * kR + c4 * 4);
+        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + c4 * 4);
       }
       gg.x *= SRWN_SQRT_HALF; gg.y *= SRWN_SQRT_HALF; gg.z *= SRWN_SQRT_HALF; gg.w *= SRWN_SQRT_HALF;   // dres
-      *reinterpret_cast<float4*>(&s.a_cur[row][q * 4]) = cur;
-      *reinterpret_cast<float4*>(&s.a_tap[row][q * 4]) = tap;
-      *reinterpret_cast<float4*>(&s.g[row][q * 4]) = gg;
+      *reinterpret_cast<float4*>(&s.a_cur[row][c4 * 4]) = tf32r4(cur);
+      *reinterpret_cast<float4*>(&s.a_tap[row][c4 * 4]) = tf32r4(tap);
+      *reinterpret_cast<float4*>(&s.g[row][c4 * 4]) = tf32r4(gg);
     }
     __syncthreads();
-    const int r0 = warp * 8;               // rows r0..r0+7, lane = channel
-    float acc[8], fv[8];
+    // stage 1: a = [x[t-d] | x[t]] Wf + bf (ops.py:6-20), f = tanh(a), c = f sigmoid(f) (ops.py:28,33,36)
+    float acc[2][4], fv[2][4];
 #pragma unroll
-    for (int r = 0; r < 8; r++) acc[r] = s.bf[lane];
-#pragma unroll 4
-    for (int k = 0; k < kR; k++) {
-      const float w0 = s.wf[k][lane], w1 = s.wf[kR + k][lane];
-#pragma unroll
-      for (int r = 0; r < 8; r++) acc[r] = fmaf(s.a_tap[r0 + r][k], w0, fmaf(s.a_cur[r0 + r][k], w1, acc[r]));
+    for (int nt = 0; nt < 2; nt++) {
+      const int n0 = nh * 16 + nt * 8 + 2 * q;
+      acc[nt][0] = acc[nt][2] = s.bf[n0]; acc[nt][1] = acc[nt][3] = s.bf[n0 + 1];
     }
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      fv[r] = tanhf(acc[r]);
-      s.c[r0 + r][lane] = fv[r] * sigmoidf_(fv[r]);
-    }
-    // dc[k] = sum_n Wr[k][n] dres[n]   (lane = k)
-    float dc[8];
+    for (int ks = 0; ks < 8; ks++) {
+      const float (*X)[kAP] = ks < 4 ? s.a_tap : s.a_cur;
+      const int kc = (ks & 3) * 8;
+      const float a0 = X[r0 + g][kc + q], a1 = X[r0 + g + 8][kc + q], a2 = X[r0 + g][kc + q + 4], a3 = X[r0 + g + 8][kc + q + 4];
 #pragma unroll
-    for (int r = 0; r < 8; r++) dc[r] = 0.f;
-#pragma unroll 4
-    for (int n = 0; n < kR; n++) {
-      const float w = s.wr[lane][n];
-#pragma unroll
-      for (int r = 0; r < 8; r++) dc[r] = fmaf(s.g[r0 + r][n], w, dc[r]);
+      for (int nt = 0; nt < 2; nt++) {
+        const int n0 = nh * 16 + nt * 8;
+        mma_tf32(acc[nt], a0, a1, a2, a3, s.wf[ks * 8 + q][n0 + g], s.wf[ks * 8 + q + 4][n0 + g]);
+      }
     }
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int t = t0 + r0 + r;
-      const float f = fv[r], sg = sigmoidf_(f);
-      const float df = dc[r] * (sg + f * sg * (1.f - sg));        // d(f sigmoid(f))/df
-      const float da = df * (1.f - f * f);                        // tanh'
-      if (t < T) da_out[((size_t)b * T + t) * kR + lane] = da;
+    for (int nt = 0; nt < 2; nt++) {
+      const int n0 = nh * 16 + nt * 8 + 2 * q;
+#pragma unroll
+      for (int e = 0; e < 4; e++) fv[nt][e] = tanhf(acc[nt][e]);
+      *reinterpret_cast<float2*>(&s.c[r0 + g][n0]) = make_float2(tf32r(fv[nt][0] * sigmoidf_(fv[nt][0])), tf32r(fv[nt][1] * sigmoidf_(fv[nt][1])));
+      *reinterpret_cast<float2*>(&s.c[r0 + g + 8][n0]) = make_float2(tf32r(fv[nt][2] * sigmoidf_(fv[nt][2])), tf32r(fv[nt][3] * sigmoidf_(fv[nt][3])));
+    }
+    // stage 2: dc[t][k] = sum_n dres[t][n] Wr[k][n]  (same (row, channel) positions as a / f)
+    float dc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const int kc = ks * 8;
+      const float a0 = s.g[r0 + g][kc + q], a1 = s.g[r0 + g + 8][kc + q], a2 = s.g[r0 + g][kc + q + 4], a3 = s.g[r0 + g + 8][kc + q + 4];
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        const int k0 = nh * 16 + nt * 8;
+        mma_tf32(dc[nt], a0, a1, a2, a3, s.wr[k0 + g][kc + q], s.wr[k0 + g][kc + q + 4]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+      const int n0 = nh * 16 + nt * 8 + 2 * q;
+      float da[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float f = fv[nt][e], sg = sigmoidf_(f);
+        const float df = dc[nt][e] * (sg + f * sg * (1.f - sg));       // d(f sigmoid(f))/df
+        da[e] = df * (1.f - f * f);                                    // tanh'
+      }
+      const int ta = t0 + r0 + g, tb = ta + 8;
+      if (ta < T) *reinterpret_cast<float2*>(da_out + ((size_t)b * T + ta) * kR + n0) = make_float2(da[0], da[1]);
+      if (tb < T) *reinterpret_cast<float2*>(da_out + ((size_t)b * T + tb) * kR + n0) = make_float2(da[2], da[3]);
     }
     __syncthreads();
-    // dWr[k][n] += sum_t c[t][k] dres[t][n]; dbr[n] += sum_t dres[t][n]   (rows past T hold zeros in g)
-    for (int t = 0; t < kTT; t++) {
-      const float gn = s.g[t][lane];
+    // stage 3: dWr[k][n] += sum_t c[t][k] dres[t][n]; dbr[n] += sum_t dres[t][n]   (rows past T hold zeros in g)
 #pragma unroll
-      for (int i = 0; i < 4; i++) gw[i] = fmaf(s.c[t][warp * 4 + i], gn, gw[i]);
-      if (warp == 0) gb += gn;
+    for (int ks = 0; ks < 8; ks++) {
+      const int tq = ks * 8 + q, m0 = mi * 16 + g, n0 = ni * 8 + g;
+      mma_tf32(gw, s.c[tq][m0], s.c[tq][m0 + 8], s.c[tq + 4][m0], s.c[tq + 4][m0 + 8], s.g[tq][n0], s.g[tq + 4][n0]);
+    }
+    if (warp == 0) {
+#pragma unroll 8
+      for (int t = 0; t < kTT; t++) gb += s.g[t][lane];
     }
   }
   float* pp = partial + (size_t)blockIdx.x * (kR * kR + kR);
-#pragma unroll
-  for (int i = 0; i < 4; i++) pp[(warp * 4 + i) * kR + lane] = gw[i];
+  {
+    const int m0 = mi * 16 + g, n0 = ni * 8 + 2 * q;
+    *reinterpret_cast<float2*>(pp + m0 * kR + n0) = make_float2(gw[0], gw[1]);
+    *reinterpret_cast<float2*>(pp + (m0 + 8) * kR + n0) = make_float2(gw[2], gw[3]);
+  }
   if (warp == 0) pp[kR * kR + lane] = gb;
 }
 
 // ---- conv backward ------------------------------------------------------------------------------------
 // dx_l[t] = g[t] sqrt(1/2) + da[t] W1^T + da[t+d] W0^T;  dWf0 += x_l[t-d]^T da[t], dWf1 += x_l[t]^T da[t],
 // dbf += sum da;  dcond_l[b][t/P] += dx_l[t] (one tile lies inside one latent frame when P % 64 == 0, else atomics).
+// Stage 1: warp (mt, nh) as above; stage 2 (dWf = [x[t-d] | x[t]]^T da): warp (mi = warp & 3, nj = warp >> 2) owns
+// input rows 16 mi.. of the 64 stacked rows and output channels 16 nj...
 struct ConvSmem {
   float a_tap[kTT][kAP], a_cur[kTT][kAP], da[kTT][kAP], da_f[kTT][kAP];
-  float w0t[kR][kR + 1], w1t[kR][kR + 1];      // transposed: [n][k]
-  float red[8][kR];
+  float w0[kR][kAP], w1[kR][kAP];              // [cin][cout] as stored (read as (cin = g, cout = q))
+  float red[4][kR];
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -135,15 +185,16 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
            int B, int T, int d, int P, int frames) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   for (int i = tid; i < kR * kR; i += kThreads) {
-    const int k = i / kR, n = i % kR;
-    s.w0t[n][k] = filt_k[i];
-    s.w1t[n][k] = filt_k[kR * kR + i];
+    s.w0[i / kR][i % kR] = tf32r(filt_k[i]);
+    s.w1[i / kR][i % kR] = tf32r(filt_k[kR * kR + i]);
   }
   const int tiles_per_b = (T + kTT - 1) / kTT;
   const int n_tiles = B * tiles_per_b;
-  float gw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // dWf[warp*8 + i][lane] over the 64 stacked input rows
+  const int mt = warp & 3, nh = warp >> 2, r0 = mt * 16;
+  const int mi = warp & 3, nj = warp >> 2;
+  float gw[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // dWf block: rows 16 mi + g (+8), columns 16 nj + 8 nt + 2q (+1)
   float gb = 0.f;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
@@ -151,66 +202,94 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
     const float* db = da_in + (size_t)b * T * kR;
     __syncthreads();
     for (int i = tid; i < kTT * (kR / 4); i += kThreads) {
-      const int row = i / (kR / 4), q = i % (kR / 4);
+      const int row = i / (kR / 4), c4 = i % (kR / 4);
       const int t = t0 + row;
       float4 cur = make_float4(0, 0, 0, 0), tap = cur, a = cur, af = cur;
       if (t < T) {
-        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + q * 4);
-        a = *reinterpret_cast<const float4*>(db + (size_t)t * kR + q * 4);
-        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + q * 4);
-        if (t + d < T) af = *reinterpret_cast<const float4*>(db + (size_t)(t + d) * kR + q * 4);
+        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + c4 * 4);
+        a = *reinterpret_cast<const float4*>(db + (size_t)t * kR + c4 * 4);
+        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + c4 * 4);
+        if (t + d < T) af = *reinterpret_cast<const float4*>(db + (size_t)(t + d) * kR + c4 * 4);
       }
-      *reinterpret_cast<float4*>(&s.a_cur[row][q * 4]) = cur;
-      *reinterpret_cast<float4*>(&s.a_tap[row][q * 4]) = tap;
-      *reinterpret_cast<float4*>(&s.da[row][q * 4]) = a;
-      *reinterpret_cast<float4*>(&s.da_f[row][q * 4]) = af;
+      *reinterpret_cast<float4*>(&s.a_cur[row][c4 * 4]) = tf32r4(cur);
+      *reinterpret_cast<float4*>(&s.a_tap[row][c4 * 4]) = tf32r4(tap);
+      *reinterpret_cast<float4*>(&s.da[row][c4 * 4]) = tf32r4(a);
+      *reinterpret_cast<float4*>(&s.da_f[row][c4 * 4]) = tf32r4(af);
     }
     __syncthreads();
-    const int r0 = warp * 8;
-    float acc[8];
+    // stage 1: dx[t][k] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-    for (int r = 0; r < 8; r++) acc[r] = 0.f;
-    // dx[t][k = lane] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]
-#pragma unroll 4
-    for (int n = 0; n < kR; n++) {
-      const float w1 = s.w1t[n][lane], w0 = s.w0t[n][lane];
+    for (int ks = 0; ks < 8; ks++) {
+      const float (*A)[kAP] = ks < 4 ? s.da : s.da_f;
+      const float (*W)[kAP] = ks < 4 ? s.w1 : s.w0;
+      const int kc = (ks & 3) * 8;
+      const float a0 = A[r0 + g][kc + q], a1 = A[r0 + g + 8][kc + q], a2 = A[r0 + g][kc + q + 4], a3 = A[r0 + g + 8][kc + q + 4];
 #pragma unroll
-      for (int r = 0; r < 8; r++) acc[r] = fmaf(s.da[r0 + r][n], w1, fmaf(s.da_f[r0 + r][n], w0, acc[r]));
+      for (int nt = 0; nt < 2; nt++) {
+        const int k0 = nh * 16 + nt * 8;
+        mma_tf32(acc[nt], a0, a1, a2, a3, W[k0 + g][kc + q], W[k0 + g][kc + q + 4]);
+      }
     }
-    float csum = 0.f;
+    const int ta = t0 + r0 + g, tb = ta + 8;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int t = t0 + r0 + r;
-      if (t < T) {
-        const size_t at = ((size_t)b * T + t) * kR + lane;
-        const float v = fmaf(g_in[at], SRWN_SQRT_HALF, acc[r]);
-        dx_out[at] = v;
-        if (P % kTT == 0) csum += v;
-        else atomicAdd(dcond + ((size_t)b * frames + t / P) * kR + lane, v);
+    for (int nt = 0; nt < 2; nt++) {
+      const int n0 = nh * 16 + nt * 8 + 2 * q;
+      float2 va = make_float2(0.f, 0.f), vb = va;
+      if (ta < T) {
+        const size_t at = ((size_t)b * T + ta) * kR + n0;
+        const float2 gg = *reinterpret_cast<const float2*>(g_in + at);
+        va = make_float2(fmaf(gg.x, SRWN_SQRT_HALF, acc[nt][0]), fmaf(gg.y, SRWN_SQRT_HALF, acc[nt][1]));
+        *reinterpret_cast<float2*>(dx_out + at) = va;
+      }
+      if (tb < T) {
+        const size_t at = ((size_t)b * T + tb) * kR + n0;
+        const float2 gg = *reinterpret_cast<const float2*>(g_in + at);
+        vb = make_float2(fmaf(gg.x, SRWN_SQRT_HALF, acc[nt][2]), fmaf(gg.y, SRWN_SQRT_HALF, acc[nt][3]));
+        *reinterpret_cast<float2*>(dx_out + at) = vb;
+      }
+      if (P % kTT == 0) {                   // the tile lies inside one latent frame: sum its rows first
+        float sx = va.x + vb.x, sy = va.y + vb.y;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+        if (g == 0) { s.red[mt][n0] = sx; s.red[mt][n0 + 1] = sy; }
+      } else {
+        if (ta < T) { atomicAdd(dcond + ((size_t)b * frames + ta / P) * kR + n0, va.x); atomicAdd(dcond + ((size_t)b * frames + ta / P) * kR + n0 + 1, va.y); }
+        if (tb < T) { atomicAdd(dcond + ((size_t)b * frames + tb / P) * kR + n0, vb.x); atomicAdd(dcond + ((size_t)b * frames + tb / P) * kR + n0 + 1, vb.y); }
       }
     }
     if (P % kTT == 0) {
-      s.red[warp][lane] = csum;
       __syncthreads();
-      if (warp == 0 && t0 < T) {
-        float tot = 0.f;
+      if (warp == 0 && t0 < T)
+        atomicAdd(dcond + ((size_t)b * frames + t0 / P) * kR + lane, (s.red[0][lane] + s.red[1][lane]) + (s.red[2][lane] + s.red[3][lane]));
+    }
+    // stage 2: dWf[k][n] += sum_t A[t][k] da[t][n] with A = [tap | cur] (rows past T hold zeros in da)
+    {
+      const float (*X)[kAP] = mi < 2 ? s.a_tap : s.a_cur;
+      const int m0 = (mi & 1) * 16 + g;
 #pragma unroll
-        for (int w = 0; w < 8; w++) tot += s.red[w][lane];
-        atomicAdd(dcond + ((size_t)b * frames + t0 / P) * kR + lane, tot);
+      for (int ks = 0; ks < 8; ks++) {
+        const int tq = ks * 8 + q;
+        const float a0 = X[tq][m0], a1 = X[tq][m0 + 8], a2 = X[tq + 4][m0], a3 = X[tq + 4][m0 + 8];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          const int n0 = nj * 16 + nt * 8 + g;
+          mma_tf32(gw[nt], a0, a1, a2, a3, s.da[tq][n0], s.da[tq + 4][n0]);
+        }
       }
     }
-    // dWf[k][n] += sum_t A[t][k] da[t][n] with A = [tap | cur] (rows past T hold zeros in da)
-    for (int t = 0; t < kTT; t++) {
-      const float an = s.da[t][lane];
-      const float* arow = warp < 4 ? &s.a_tap[t][warp * 8] : &s.a_cur[t][(warp - 4) * 8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) gw[i] = fmaf(arow[i], an, gw[i]);
-      if (warp == 0) gb += an;
+    if (warp == 0) {
+#pragma unroll 8
+      for (int t = 0; t < kTT; t++) gb += s.da[t][lane];
     }
   }
   float* pp = partial + (size_t)blockIdx.x * (2 * kR * kR + kR);
 #pragma unroll
-  for (int i = 0; i < 8; i++) pp[(warp * 8 + i) * kR + lane] = gw[i];
+  for (int nt = 0; nt < 2; nt++) {
+    const int m0 = mi * 16 + g, n0 = nj * 16 + nt * 8 + 2 * q;
+    *reinterpret_cast<float2*>(pp + m0 * kR + n0) = make_float2(gw[nt][0], gw[nt][1]);
+    *reinterpret_cast<float2*>(pp + (m0 + 8) * kR + n0) = make_float2(gw[nt][2], gw[nt][3]);
+  }
   if (warp == 0) pp[2 * kR * kR + lane] = gb;
 }
 
