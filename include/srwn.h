@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SRWN_ABI_VERSION 4
+#define SRWN_ABI_VERSION 5
 
 enum srwn_status {
   SRWN_OK = 0,
@@ -179,6 +179,31 @@ int srwn_mol_loss_grad(const float* x, const float* l, float* dx, float* nll_out
 int srwn_adam_step(srwn_handle_t h, const float* grads, float* m, float* v, float* scratch,
                    float clip_norm, float lr, float beta1, float beta2, float eps, int32_t step,
                    void* stream);
+
+/* ---- spectral power loss and loss glue of the distillation step (model.py:356-379) ----
+ * srwn_stft_power: s(x) = mean over frames of |tf.contrib.signal.stft(x, frame_length, frame_step)|^2
+ *   (model.py:360-367: periodic Hann window, fft_length = frame_length (a power of two), no padding,
+ *   F = 1 + (T - frame_length) / frame_step frames); x [B,T] -> power [B, frame_length/2 + 1].
+ * srwn_stft_power_loss: loss[0] (device double) = gamma * sum (s(truth) - s(out))^2 (model.py:369-371) and,
+ *   when d_out != NULL, d_out [B,T] = dLoss/d out.  T < frame_length is an error (the reference's
+ *   mean over zero frames is NaN).  Workspace: srwn_stft_workspace_bytes.
+ * srwn_distill_loss_grad: the elementwise rest of model.py:356-379 / :535 for given per-sample
+ *   cross-entropy terms: d_pre = (beta * d_ce + d_pow) * [-1 <= z*s_tot + mu_tot <= 1] * inv_norm,
+ *   d_s = -alpha * inv_norm / s_tot, sums[0] = sum nll, sums[1] = sum(log s_tot + 2) (the entropy,
+ *   model.py:356).  `sums` is a device buffer of SRWN_DISTILL_SUMS_LEN doubles (partials after the
+ *   first two); nll and d_pow may be NULL.  All sums are taken in a fixed order. */
+#define SRWN_DISTILL_SUMS_LEN 1024
+int srwn_stft_workspace_bytes(int32_t B, int32_t T, int32_t frame_length, int32_t frame_step,
+                              size_t* bytes);
+int srwn_stft_power(const float* x, float* power, int32_t B, int32_t T, int32_t frame_length,
+                    int32_t frame_step, void* workspace, size_t workspace_bytes, void* stream);
+int srwn_stft_power_loss(const float* truth, const float* out, float gamma, double* loss,
+                         float* d_out, int32_t B, int32_t T, int32_t frame_length,
+                         int32_t frame_step, void* workspace, size_t workspace_bytes, void* stream);
+int srwn_distill_loss_grad(const float* z, const float* s_tot, const float* mu_tot,
+                           const float* nll, const float* d_ce, const float* d_pow, float alpha,
+                           float beta, float inv_norm, float* d_pre, float* d_s, double* sums,
+                           int32_t B, int32_t T, void* stream);
 
 /* ---- teacher encoder (model.py:137-155; SURVEY.md 8(f)-1, the row next to the hot path) ---------
  * A separate handle: the encoder shares no variable with the decoder.  createEncoder stacks

@@ -8,11 +8,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRWN_LIB") or os.path.join(_HERE, "libsrwn.so")   # SRWN_LIB: tuning builds (tools/exp_build.sh)
 
-ABI_VERSION = 4      # SRWN_ABI_VERSION in include/srwn.h
+ABI_VERSION = 5      # SRWN_ABI_VERSION in include/srwn.h
 OK, ERR_INVALID, ERR_CUDA, ERR_WEIGHTS, ERR_UNSUPPORTED, ERR_WORKSPACE = range(6)
 TEACHER, STUDENT = 0, 1
 FP32, BF16, FP16 = 0, 1, 2
 OP_TEACHER_LOGITS, OP_TEACHER_NLL, OP_TEACHER_GENERATE, OP_STUDENT_FORWARD, OP_STUDENT_TRAIN = range(5)
+DISTILL_SUMS_LEN = 1024   # SRWN_DISTILL_SUMS_LEN
 PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
 
 
@@ -66,6 +67,11 @@ SIGNATURES = {
     "srwn_mol_loss_grad": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp]),
     "srwn_adam_step": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_float, ctypes.c_float, _i32, _vp]),
+    "srwn_stft_workspace_bytes": (ctypes.c_int, [_i32, _i32, _i32, _i32, ctypes.POINTER(_sz)]),
+    "srwn_stft_power": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_stft_power_loss": (ctypes.c_int, [_fp, _fp, ctypes.c_float, _vp, _fp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_distill_loss_grad": (ctypes.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                              _fp, _fp, _vp, _i32, _i32, _vp]),
     "srwn_encoder_create": (ctypes.c_int, [ctypes.POINTER(EncoderConfig), ctypes.POINTER(_vp)]),
     "srwn_encoder_destroy": (ctypes.c_int, [_vp]),
     "srwn_encoder_set_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(_i64), _i32]),

@@ -569,6 +569,43 @@ extern "C" int srwn_mol_loss_grad(const float* x, const float* l, float* dx, flo
   return run_mol_nll_grad(x, l, dx, nll_out, B, T, M, (cudaStream_t)stream);
 }
 
+int run_stft_workspace_bytes(int B, int T, int N, int step, size_t* bytes);
+int run_stft_power(const float* x, float* power, int B, int T, int N, int step, void* ws, size_t cap, cudaStream_t st);
+int run_stft_power_loss(const float* truth, const float* out, float gamma, double* loss, float* d_out, int B, int T, int N,
+                        int step, void* ws, size_t cap, cudaStream_t st);
+int run_distill_loss_grad(const float* z, const float* s_tot, const float* mu_tot, const float* nll, const float* d_ce,
+                          const float* d_pow, float alpha, float beta, float inv_norm, float* d_pre, float* d_s, double* sums,
+                          int B, int T, cudaStream_t st);
+
+extern "C" int srwn_stft_workspace_bytes(int32_t B, int32_t T, int32_t frame_length, int32_t frame_step, size_t* bytes) {
+  if (!bytes) return srwn_fail(SRWN_ERR_INVALID, "srwn_stft_workspace_bytes: null argument");
+  return run_stft_workspace_bytes(B, T, frame_length, frame_step, bytes);
+}
+
+extern "C" int srwn_stft_power(const float* x, float* power, int32_t B, int32_t T, int32_t frame_length, int32_t frame_step,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !power || !workspace) return srwn_fail(SRWN_ERR_INVALID, "srwn_stft_power: null argument");
+  return run_stft_power(x, power, B, T, frame_length, frame_step, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int srwn_stft_power_loss(const float* truth, const float* out, float gamma, double* loss, float* d_out, int32_t B,
+                                    int32_t T, int32_t frame_length, int32_t frame_step, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!truth || !out || !loss || !workspace) return srwn_fail(SRWN_ERR_INVALID, "srwn_stft_power_loss: null argument");
+  return run_stft_power_loss(truth, out, gamma, loss, d_out, B, T, frame_length, frame_step, workspace, workspace_bytes,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int srwn_distill_loss_grad(const float* z, const float* s_tot, const float* mu_tot, const float* nll,
+                                      const float* d_ce, const float* d_pow, float alpha, float beta, float inv_norm,
+                                      float* d_pre, float* d_s, double* sums, int32_t B, int32_t T, void* stream) {
+  if (!z || !s_tot || !mu_tot || !d_ce || !d_pre || !d_s || !sums)
+    return srwn_fail(SRWN_ERR_INVALID, "srwn_distill_loss_grad: null argument");
+  if (B < 1 || T < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_distill_loss_grad: bad B/T");
+  return run_distill_loss_grad(z, s_tot, mu_tot, nll, d_ce, d_pow, alpha, beta, inv_norm, d_pre, d_s, sums, B, T,
+                               (cudaStream_t)stream);
+}
+
 extern "C" int srwn_adam_step(srwn_handle_t h, const float* grads, float* m, float* v, float* scratch, float clip_norm,
                               float lr, float beta1, float beta2, float eps, int32_t step, void* stream) {
   if (!h || !grads || !m || !v || !scratch) return srwn_fail(SRWN_ERR_INVALID, "srwn_adam_step: null argument");

@@ -570,16 +570,17 @@ class ParallelWaveNet(_CheckpointMixin):
         # cross-entropy against the teacher's mixture (model.py:374-375): value + d/d out
         d_ce, nll = torch.empty_like(out), torch.empty_like(out)
         _lib.check(eng.lib.srwn_mol_loss_grad(out.data_ptr(), tl.data_ptr(), d_ce.data_ptr(), nll.data_ptr(), B, T, M, _stream()))
-        # spectral power loss (model.py:360-371): torch.stft stands in for tf.contrib.signal.stft(x, 512, 256)
-        # (host-side glue, next in line for a fused kernel)
+        # spectral power loss (model.py:360-371) and its gradient: FFT kernels of csrc/stft_loss.cu
         power, d_pow = self._power_loss(x, out)
-        entropy = (torch.log(s_tot) + 2.0).sum()                                   # model.py:356
-        loss = (self.beta * nll.double().sum() - self.alpha * entropy.double() + power.double()) / norm
-        # d loss / d pre, pre = z*s_tot + mu_tot: tf.minimum/maximum pass the gradient inside [-1, 1] (model.py:535)
-        pre = z * s_tot + mu_tot
-        mask = ((pre >= -1.0) & (pre <= 1.0)).float()
-        d_pre = ((self.beta * d_ce + d_pow) * mask / norm).contiguous()
-        d_s = (-(self.alpha / norm) / s_tot).contiguous()                          # entropy term, model.py:377
+        # entropy (model.py:356), clip mask (model.py:535) and the loss gradients the backward pass starts from
+        d_pre, d_s = torch.empty_like(out), torch.empty_like(out)
+        sums = torch.empty(_lib.DISTILL_SUMS_LEN, dtype=torch.float64, device="cuda")
+        _lib.check(eng.lib.srwn_distill_loss_grad(z.data_ptr(), s_tot.data_ptr(), mu_tot.data_ptr(), nll.data_ptr(),
+                                                  d_ce.data_ptr(), d_pow.data_ptr(), float(self.alpha), float(self.beta),
+                                                  1.0 / norm, d_pre.data_ptr(), d_s.data_ptr(), sums.data_ptr(), B, T,
+                                                  _stream()))
+        entropy = sums[1]
+        loss = (self.beta * sums[0] - self.alpha * entropy + power) / norm          # model.py:374-379
         n = ctypes.c_int64()
         _lib.check(eng.lib.srwn_param_count(eng.h, ctypes.byref(n)))
         grads = torch.empty(n.value, dtype=torch.float32, device="cuda")
@@ -587,20 +588,21 @@ class ParallelWaveNet(_CheckpointMixin):
                                                  grads.data_ptr(), B, T, ws, wsn, _stream()))
         return loss, power, entropy, grads
 
-    def _power_loss(self, truth, out):
-        """gamma * || mean_t |STFT(truth)|^2 - mean_t |STFT(out)|^2 ||^2 (model.py:360-371) and d/d out."""
-        if not hasattr(self, "_hann") or self._hann.device != out.device:
-            self._hann = torch.hann_window(512, periodic=True, dtype=torch.float32, device=out.device)
-
-        def power(sig):
-            spec = torch.stft(sig, n_fft=512, hop_length=256, win_length=512, window=self._hann, center=False,
-                              return_complex=True)
-            return (spec.real ** 2 + spec.imag ** 2).mean(dim=2)
-        o = out.detach().clone().requires_grad_(True)
-        with torch.enable_grad():
-            p = ((power(truth) - power(o)) ** 2).sum() * self.gamma
-            g, = torch.autograd.grad(p, o)
-        return p.detach(), g
+    def _power_loss(self, truth, out, frame_length=512, frame_step=256):
+        """gamma * || mean_t |STFT(truth)|^2 - mean_t |STFT(out)|^2 ||^2 (model.py:360-371) and d/d out, on the device.
+        Returns (power_loss: 0-d float64 CUDA tensor, d_out [B,T] fp32)."""
+        eng = self._eng
+        B, T = out.shape
+        n = ctypes.c_size_t()
+        _lib.check(eng.lib.srwn_stft_workspace_bytes(B, T, frame_length, frame_step, ctypes.byref(n)))
+        if getattr(self, "_stft_ws", None) is None or self._stft_ws.numel() < n.value:
+            self._stft_ws = torch.empty(max(n.value, 256), dtype=torch.uint8, device="cuda")
+        p = torch.empty(1, dtype=torch.float64, device="cuda")
+        g = torch.empty_like(out)
+        _lib.check(eng.lib.srwn_stft_power_loss(truth.data_ptr(), out.data_ptr(), float(self.gamma), p.data_ptr(),
+                                                g.data_ptr(), B, T, frame_length, frame_step, self._stft_ws.data_ptr(),
+                                                self._stft_ws.numel(), _stream()))
+        return p[0], g
 
     def grad_of(self, flat_grads, name):
         """View of one variable's gradient inside ``flat_grads`` (TF variable name)."""

@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), "libsrwn.so does not export %s" % n
         assert n in _lib.SIGNATURES, "ctypes binding misses %s" % n
-    assert lib.srwn_abi_version() == 4
+    assert lib.srwn_abi_version() == 5
 
 
 def test_binding_has_no_undeclared_symbols(lib):
@@ -49,6 +49,10 @@ def test_argument_errors_need_no_gpu(lib):
     assert lib.srwn_create(ctypes.byref(unsupported), ctypes.byref(h)) == _lib.ERR_UNSUPPORTED
     assert lib.srwn_destroy(None) == _lib.OK
     assert lib.srwn_mol_loss(None, None, None, None, 1, 1, 5, None) == _lib.ERR_INVALID
+    n = ctypes.c_size_t()
+    assert lib.srwn_stft_workspace_bytes(4, 64000, 512, 256, ctypes.byref(n)) == _lib.OK and n.value > 0
+    assert lib.srwn_stft_workspace_bytes(4, 64000, 500, 256, ctypes.byref(n)) == _lib.ERR_INVALID     # not a power of two
+    assert lib.srwn_stft_workspace_bytes(4, 256, 512, 256, ctypes.byref(n)) == _lib.ERR_INVALID       # shorter than a frame
 
 
 def test_no_cpu_fallback_without_gpu(lib):

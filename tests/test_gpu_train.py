@@ -55,6 +55,81 @@ def test_mol_loss_grad_matches_autograd(srwn):
     assert np.abs(g - g_ref.numpy()).max() <= 2e-4 * scale
 
 
+def _stft_ws(srwn, lib, B, T, N, step):
+    import ctypes
+    n = ctypes.c_size_t()
+    srwn._lib.check(lib.srwn_stft_workspace_bytes(B, T, N, step, ctypes.byref(n)))
+    return torch.empty(n.value, dtype=torch.uint8, device="cuda")
+
+
+@pytest.mark.parametrize("B,T,N,step", [(2, 1280, 512, 256), (3, 1000, 512, 256), (1, 64000, 512, 256), (2, 700, 64, 48),
+                                         (1, 4096, 2048, 512)])
+def test_stft_power_and_loss_match_oracle(srwn, B, T, N, step):
+    """model.py:360-371 on the device vs the NumPy oracle (value) and torch float64 autograd (gradient)."""
+    from oracle import srwn_oracle as orc
+    lib = srwn._lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    truth = synth.synthetic_audio(B, T)
+    rng = np.random.default_rng(17)
+    out = np.clip(truth * 0.8 + rng.normal(0, 0.1, size=truth.shape), -1, 1).astype(np.float32)
+    ws = _stft_ws(srwn, lib, B, T, N, step)
+    xd, od = torch.from_numpy(truth).cuda(), torch.from_numpy(out).cuda()
+    K = N // 2 + 1
+    pw = torch.empty(B, K, dtype=torch.float32, device="cuda")
+    srwn._lib.check(lib.srwn_stft_power(xd.data_ptr(), pw.data_ptr(), B, T, N, step, ws.data_ptr(), ws.numel(), st))
+    ref = orc.stft_power(truth.astype(np.float64), N, step)
+    np.testing.assert_allclose(pw.cpu().numpy(), ref, rtol=2e-5, atol=2e-6 * ref.max())
+    gamma = 0.7
+    loss = torch.empty(1, dtype=torch.float64, device="cuda")
+    g = torch.empty_like(od)
+    srwn._lib.check(lib.srwn_stft_power_loss(xd.data_ptr(), od.data_ptr(), gamma, loss.data_ptr(), g.data_ptr(), B, T, N, step,
+                                             ws.data_ptr(), ws.numel(), st))
+    ot = torch.tensor(out.astype(np.float64), requires_grad=True)
+    win = torch.hann_window(N, periodic=True, dtype=torch.float64)
+
+    def power(sig):
+        spec = torch.stft(sig, n_fft=N, hop_length=step, win_length=N, window=win, center=False, return_complex=True)
+        return (spec.real ** 2 + spec.imag ** 2).mean(dim=2)
+    ref_loss = gamma * ((power(torch.tensor(truth.astype(np.float64))) - power(ot)) ** 2).sum()
+    g_ref, = torch.autograd.grad(ref_loss, ot)
+    np.testing.assert_allclose(float(ref_loss), gamma * np.sum((ref - orc.stft_power(out.astype(np.float64), N, step)) ** 2),
+                               rtol=1e-9)
+    np.testing.assert_allclose(loss.item(), float(ref_loss), rtol=2e-4)
+    scale = np.abs(g_ref.numpy()).max()
+    assert np.abs(g.cpu().numpy() - g_ref.numpy()).max() <= 2e-4 * scale
+    # samples past the last full frame do not enter the loss (pad_end=False)
+    F = 1 + (T - N) // step
+    assert not g[:, (F - 1) * step + N:].any()
+    # value-only call, and determinism
+    loss2 = torch.empty(1, dtype=torch.float64, device="cuda")
+    srwn._lib.check(lib.srwn_stft_power_loss(xd.data_ptr(), od.data_ptr(), gamma, loss2.data_ptr(), None, B, T, N, step,
+                                             ws.data_ptr(), ws.numel(), st))
+    assert loss2.item() == loss.item()
+
+
+def test_distill_loss_glue(srwn):
+    lib = srwn._lib.load()
+    rng = np.random.default_rng(23)
+    B, T = 3, 5000
+    z = rng.logistic(0, 1, size=(B, T)).astype(np.float32)
+    s = np.exp(rng.normal(-1, 0.5, size=(B, T))).astype(np.float32)
+    mu = rng.normal(0, 0.3, size=(B, T)).astype(np.float32)
+    nll, dce, dpow = (rng.normal(0, 1, size=(B, T)).astype(np.float32) for _ in range(3))
+    dev = [torch.from_numpy(a).cuda() for a in (z, s, mu, nll, dce, dpow)]
+    d_pre, d_s = torch.empty_like(dev[0]), torch.empty_like(dev[0])
+    sums = torch.empty(srwn._lib.DISTILL_SUMS_LEN, dtype=torch.float64, device="cuda")
+    alpha, beta, inv = 0.25, 1.5, 1.0 / 6
+    srwn._lib.check(lib.srwn_distill_loss_grad(*[t.data_ptr() for t in dev], alpha, beta, inv, d_pre.data_ptr(), d_s.data_ptr(),
+                                               sums.data_ptr(), B, T, torch.cuda.current_stream().cuda_stream))
+    pre = z * s + mu
+    mask = (pre >= -1) & (pre <= 1)
+    assert 0.05 < mask.mean() < 0.999
+    np.testing.assert_allclose(d_pre.cpu().numpy(), (beta * dce + dpow) * mask * np.float32(inv), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(d_s.cpu().numpy(), -(alpha * inv) / s, rtol=2e-6)
+    np.testing.assert_allclose(sums[0].item(), nll.astype(np.float64).sum(), rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(sums[1].item(), (np.log(s.astype(np.float64)) + 2).sum(), rtol=1e-6)
+
+
 @pytest.mark.parametrize("cfg", ["small", "default"])
 def test_gradients_match_oracle(srwn, cfg):
     if cfg == "small":

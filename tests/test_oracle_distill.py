@@ -70,3 +70,21 @@ def test_adam_reference_first_step_is_sign_step():
     np.testing.assert_allclose(w1, w[0] - 1e-3 * np.sign(g[0]), rtol=1e-6)
     (w2, _, _), = dt.adam_reference(w, [np.array([30.0, -40.0])], [np.zeros(2)], [np.zeros(2)], step=1, lr=1e-3)
     np.testing.assert_allclose(w2, w1, rtol=1e-6)               # clipped to norm 1: same direction, same first step
+
+
+def test_stft_power_known_answer():
+    """tf.contrib.signal.stft(x, 512, 256) semantics (model.py:360-367) on a closed-form case: a cosine on bin k0 under
+    the periodic Hann window has |X[k0]| = N/4 and |X[k0 +- 1]| = N/8 in every frame, nothing elsewhere; 1 + (T-N)//step
+    frames, the tail that does not fill a frame is dropped."""
+    N, step, k0, T = 512, 256, 37, 512 + 256 * 5 + 100
+    n = np.arange(T)
+    x = np.cos(2 * np.pi * k0 * n / N)[None, :]
+    p = orc.stft_power(x, N, step)
+    assert p.shape == (1, N // 2 + 1)
+    expect = np.zeros(N // 2 + 1)
+    expect[k0] = (N / 4) ** 2
+    expect[k0 - 1] = expect[k0 + 1] = (N / 8) ** 2
+    np.testing.assert_allclose(p[0], expect, atol=1e-6)
+    x2 = x.copy()
+    x2[:, 512 + 256 * 5:] = 7.0               # past the last full frame: ignored (pad_end=False)
+    np.testing.assert_allclose(orc.stft_power(x2, N, step), p, atol=0)
