@@ -58,8 +58,9 @@ struct Smem {
   static constexpr int n_bars = 2 * kStages + kMaxL + 2;
   static constexpr int flags = bars + n_bars * 8 + 16;     // per-layer step counters: gate slot l holds step (flag - 1)
   static constexpr int xslot = flags + kMaxL * 4;           // x[t] of the 8 utterances, chain warp 0 -> chain warps 1..3
-  static constexpr int qofs = xslot + 64;                   // queue slot byte offsets of the step, [kMaxL] ints
-  static constexpr int total = qofs + kMaxL * 4;
+  static constexpr int qofs = xslot + 64;                   // queue slot byte offsets, [2 step parities][kMaxL] ints
+  static constexpr int tmem = qofs + 2 * kMaxL * 4;         // TMEM base address (tcgen05.alloc)
+  static constexpr int total = tmem + 16;
 };
 static_assert(Smem::total <= 232448, "shared memory budget");
 
@@ -69,8 +70,8 @@ struct Params {
   const float* fixed;         // fk[64] | bsum[128] b1[128] b2[32]
   const float* cb;            // [B][frames][L+1][32] folded biases + conditioning (fused::k_fold_bias)
   uint8_t* queues;            // [grid][sum_d][kSlotBytes]
-  const float* u1;            // [B][T][M]
-  const float* u2;            // [B][T]
+  const float* g1;            // [B][T][M]  -log(-log(u1))           (k_sampler_noise)
+  const float* lg2;           // [B][T]     log(u2) - log(1 - u2)
   float* x_out;               // [B][T]
   float* logits_out;          // [B][T][4M] or null
   int* err;
@@ -141,6 +142,48 @@ __device__ __forceinline__ uint2 lds64(uint32_t a) {
   return v;
 }
 
+// Tensor memory as a per-lane scratchpad (mma.sync leaves it unused): each chain warp keeps the folded bias +
+// conditioning table of the current latent frame, 8 floats per lane and layer, in its own 32-lane quarter.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float2 (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y)
+               : "r"(taddr) : "memory");
+}
+// wait for the warp's tcgen05.ld; the operands tie the loaded registers to the wait so no use moves above it
+__device__ __forceinline__ void tmem_wait_ld(float2 (&v)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y), "+f"(v[3].x), "+f"(v[3].y)
+               :: "memory");
+}
+constexpr int kTmemCols = 256;                 // (kMaxL + 1) * 8 = 248 columns used
+
+#ifdef SRWN_AR_TIMING
+__device__ __forceinline__ long long clk_after(uint32_t dep) {      // clock read ordered after the value `dep` is ready
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+  return t;
+}
+#define AR_T(var, dep) const long long var = clk_after(dep)
+#define AR_ACC(acc, expr) acc += (expr)
+#else
+#define AR_T(var, dep)
+#define AR_ACC(acc, expr)
+#endif
+
+// The sampler's noise transforms (ops.py:187,197) do not depend on the logits: one elementwise pass ahead of the
+// sequential kernel takes ~12 logarithms per sample off the per-step dependency chain.  Same operations and order
+// as mol_sample_one (mol.cuh), so the samples are bit-identical to it.
+__global__ void k_sampler_noise(const float* __restrict__ u1, const float* __restrict__ u2, float* __restrict__ g1,
+                                float* __restrict__ lg2, int64_t n, int M) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * M) g1[i] = -logf(-logf(u1[i]));
+  if (i < n) { const float u = u2[i]; lg2[i] = logf(u) - logf(1.f - u); }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -178,7 +221,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     float* sh = reinterpret_cast<float*>(smem + Smem::hbias);
     for (int i = tid; i < 288; i += kThreads) sh[i] = p.fixed[64 + i];
   }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::tmem), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem);
 
   const int b0 = blockIdx.x * kU;
   const bool pow2 = p.sum_d < 0;      // host encodes "all dilations are powers of two" in the sign
@@ -207,10 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     const int j = warp;
     auto chain_sync = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
     const int bg = min(b0 + g, p.B - 1);               // utterance of fragment row g (clamped: padding rows repeat the last one)
-    const float* cb_b = p.cb + (size_t)bg * p.frames * (L + 1) * 32;
+    const float* cb_b = p.cb + (size_t)bg * p.frames * (L + 1) * 32 + 2 * q;
     uint8_t* qbase = p.queues + (size_t)blockIdx.x * sum_d * kSlotBytes + lane * 16;
     const float* sf = reinterpret_cast<const float*>(smem + Smem::front);
-    volatile int* sq = reinterpret_cast<volatile int*>(smem + Smem::qofs);
+    volatile int* sq = reinterpret_cast<volatile int*>(smem + Smem::qofs);      // [2][kMaxL]: queue slot byte offsets, by step parity
     volatile float* sx = reinterpret_cast<volatile float*>(smem + Smem::xslot);
     float xm1 = 0.f, xm2 = 0.f;                         // x[t-1], x[t-2] of utterance g
     float h[4][2];                                      // residual stream: n-tile i, columns 8i+2q, 8i+2q+1 of row g
@@ -220,38 +270,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     const bool samp = j == 0 && lane < kU && ub < p.B;
     bool ok = true;
     long long tm_a = 0, tm_b = 0, tm_c = 0, tm_d = 0;
+    long long tl_conv = 0, tl_gate = 0, tl_sync = 0, tl_res = 0, tl_top = 0;
+
+    // Queue pops (L2) run three layers ahead of their use, in three register sets that the layer loop (unrolled by
+    // three) addresses by name: nothing is rotated through register moves, and a set is reloaded right after its
+    // value is consumed, so whenever the warp waits for a pop every load in flight is at least a layer old (loads
+    // share scoreboards: waiting for an old one also waits for the newest).
+    // The folded bias + conditioning terms (8 floats per lane and layer) change once per latent frame: they live in
+    // tensor memory, one table per chain warp, and come back with tcgen05.ld a layer ahead of their use.
+    struct Pre { uint4 tap; int ofs; };
+    Pre S0, S1, S2;
+    float2 cb0[4];                                      // folded term of layer 0 (front bias + conditioning)
+    const uint32_t tm = tmem_base + ((uint32_t)(j * 32) << 16);
+    auto slot_of = [&](int l, int t) {
+      const int d = p.dil[l];
+      return (p.qoff[l] + (pow2 ? (t & (d - 1)) : (t % d))) * kSlotBytes;
+    };
+    auto prefetch = [&](Pre& S, int l, const volatile int* sqt) {      // pop of layer l: the slot holds h_l[t - d]
+      S.ofs = sqt[l];
+      S.tap = *reinterpret_cast<const uint4*>(qbase + S.ofs);
+    };
+    auto load_frame_table = [&](int frame) {            // cb [frame][0..L][32] of utterance g -> TMEM columns 8 li..8 li + 7
+      const float* cbf = cb_b + (size_t)frame * (L + 1) * 32;
+      for (int li = 0; li <= L; li++) {
+        float2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float2*>(cbf + li * 32 + 8 * i);
+        tmem_st8(tm + li * 8, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    };
+    if (j == 0 && lane < L) sq[lane] = slot_of(lane, 0);
+    chain_sync();
+    prefetch(S0, 0, sq);
+    prefetch(S1, 1, sq);
+    prefetch(S2, 2, sq);
 
     for (int t = 0; t < p.T; t++, it_base += n_items) {
       const long long c0 = clock64();
-      const int frame = t / p.P;
-      const float* cbf = cb_b + (size_t)frame * (L + 1) * 32 + 2 * q;
-      // sampler noise of this step (latency hidden behind the layer chain)
-      float u1v[8], u2v = 0.5f;
+      const volatile int* sqt = sq + (t & 1) * kMaxL;
+      if (t % p.P == 0) load_frame_table(t / p.P);
+      tmem_ld8(tm, cb0);
+      // sampler noise of this step, already transformed (k_sampler_noise); latency hidden behind the layer chain
+      float g1v[8], lg2v = 0.f;
 #pragma unroll
-      for (int m = 0; m < 8; m++) u1v[m] = 0.5f;
-      if (samp) {
-        for (int m = 0; m < p.M; m++) u1v[m] = __ldg(p.u1 + ((size_t)ub * p.T + t) * p.M + m);
-        u2v = __ldg(p.u2 + (size_t)ub * p.T + t);
-      }
-      // queue slot of every layer at this step (byte offsets), one lane per layer
-      if (j == 0 && lane < L) {
-        const int d = p.dil[lane];
-        sq[lane] = (p.qoff[lane] + (pow2 ? (t & (d - 1)) : (t % d))) * kSlotBytes;
-      }
-      chain_sync();
-      // pops of layers 0 and 1; folded bias + conditioning of layers 0, 1, 2 (rotating registers: arrays indexed by the
-      // layer would live in local memory)
-      int ofs0 = sq[0], ofs1 = L > 1 ? sq[1] : 0, ofs2 = L > 2 ? sq[2] : 0;
-      uint4 tap0 = *reinterpret_cast<const uint4*>(qbase + ofs0);
-      uint4 tap1 = L > 1 ? *reinterpret_cast<const uint4*>(qbase + ofs1) : make_uint4(0, 0, 0, 0);
-      float2 cb0[4], cbA[4], cbB[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        cb0[i] = *reinterpret_cast<const float2*>(cbf + 8 * i);
-        cbA[i] = *reinterpret_cast<const float2*>(cbf + 32 + 8 * i);
-        cbB[i] = L >= 2 ? *reinterpret_cast<const float2*>(cbf + 64 + 8 * i) : make_float2(0.f, 0.f);
-      }
+      for (int m = 0; m < 8; m++) g1v[m] = (samp && m < p.M) ? __ldg(p.g1 + ((size_t)ub * p.T + t) * p.M + m) : 0.f;
+      if (samp) lg2v = __ldg(p.lg2 + (size_t)ub * p.T + t);
+      // queue slots of the next step, one lane per layer (read after the barriers of this step)
+      if (j == 0 && lane < L) sq[((t + 1) & 1) * kMaxL + lane] = slot_of(lane, t + 1);
       // front: RightShift + K=2 causal conv on one channel (model.py:172-173) + bias + conditioning of layer 0
+      tmem_wait_ld(cb0);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int c = 8 * i + 2 * q;
@@ -264,43 +332,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
       uint4 wft = lds128_ro(sbase + Smem::chain + lane * 16 + (2 * j) * 512);
       uint4 wfc = lds128_ro(sbase + Smem::chain + lane * 16 + (2 * j + 1) * 512);
 
-      for (int l = 0; l < L; l++) {
+      auto layer = [&](const int l, Pre& S) {
         const uint32_t wl = sbase + Smem::chain + l * kChainLayerBytes + lane * 16;
-        const uint4 tap = tap0;
-        const int ofs = ofs0;
-        tap0 = tap1; ofs0 = ofs1; ofs1 = ofs2;
-        if (l + 2 < L && !(p.dbg & 1)) tap1 = *reinterpret_cast<const uint4*>(qbase + ofs1);   // prefetch the pop two layers ahead
-        if (l + 3 < L) ofs2 = sq[l + 3];
-        float2 cb_next[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          cb_next[i] = cbA[i];
-          cbA[i] = cbB[i];
-          if (l + 3 <= L && !(p.dbg & 2)) cbB[i] = *reinterpret_cast<const float2*>(cbf + (l + 3) * 32 + 8 * i);
-        }
+        AR_T(t_0, hA[0]);
+        float2 cbn[4];                                   // term added after this layer (index l + 1)
+        tmem_ld8(tm + (l + 1) * 8, cbn);
         // ---- filter conv (ops.py:6-10), n-tile j: taps (W[0] on h[t-d]) and current (W[1] on h[t]) as two
         //      independent accumulation chains
         float acc[2] = {0.f, 0.f}, acc2[2] = {0.f, 0.f};
-        mma8(acc, tap.x, tap.y, wft.x, wft.y);
         mma8(acc2, hA[0], hA[1], wfc.x, wfc.y);
-        mma8(acc, tap.z, tap.w, wft.z, wft.w);
+        mma8(acc, S.tap.x, S.tap.y, wft.x, wft.y);
         mma8(acc2, hA[2], hA[3], wfc.z, wfc.w);
+        mma8(acc, S.tap.z, S.tap.w, wft.z, wft.w);
+        AR_T(t_1, S.tap.x);
+        AR_T(t_2, __float_as_uint(acc[0] + acc2[0]));
         uint4 wr[4];                                     // residual B fragments: land while the gate runs
 #pragma unroll
         for (int i = 0; i < 4; i++) wr[i] = lds128_ro(wl + 4096 + i * 512);
         // push h[t] (the slot held h[t-d] until now); every chain warp holds the same image
-        if (j == 0 && !(p.dbg & 4)) *reinterpret_cast<uint4*>(qbase + ofs) = make_uint4(hA[0], hA[1], hA[2], hA[3]);
+        if (j == 0) *reinterpret_cast<uint4*>(qbase + S.ofs) = make_uint4(hA[0], hA[1], hA[2], hA[3]);
+        if (l + 3 < L) prefetch(S, l + 3, sqt);          // this set's next use: layer l + 3
         // ---- gate (ops.py:28,33,36) of this warp's 8 channels -> one word of the A fragments of the residual / skip convs
         {
           const float2 b = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(smem + Smem::chain + l * kChainLayerBytes + 6144) + 8 * j + 2 * q);
           const uint32_t cj = pack_h2(gate(acc[0] + acc2[0] + b.x), gate(acc[1] + acc2[1] + b.y));
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + Smem::cslots + l * kSlotBytes + j * 128 + lane * 4), "r"(cj) : "memory");
         }
+        AR_T(t_3, 0u);
         if (l + 1 < L) {                                 // next layer's filter-conv fragments
           wft = lds128_ro(wl + kChainLayerBytes + (2 * j) * 512);
           wfc = lds128_ro(wl + kChainLayerBytes + (2 * j + 1) * 512);
         }
-        if (!(p.dbg & 8)) chain_sync();                  // the four words of every lane's slot are in place
+        chain_sync();                                    // the four words of every lane's slot are in place
+        AR_T(t_4, 0u);
         if (j == 0 && lane == 0) mbar_arrive(bar(B_CFULL + l));      // release: the skip warps may read the slot
         uint32_t cA[4];
 #pragma unroll
@@ -313,13 +377,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         for (int i = 0; i < 4; i++) { r[i][0] = r[i][1] = 0.f; mma8(r[i], cA[0], cA[1], wr[i].x, wr[i].y); }
 #pragma unroll
         for (int i = 0; i < 4; i++) mma8(r[i], cA[2], cA[3], wr[i].z, wr[i].w);
+        tmem_wait_ld(cbn);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          h[i][0] = fmaf(h[i][0] + r[i][0], SRWN_SQRT_HALF, cb_next[i].x);
-          h[i][1] = fmaf(h[i][1] + r[i][1], SRWN_SQRT_HALF, cb_next[i].y);
+          h[i][0] = fmaf(h[i][0] + r[i][0], SRWN_SQRT_HALF, cbn[i].x);
+          h[i][1] = fmaf(h[i][1] + r[i][1], SRWN_SQRT_HALF, cbn[i].y);
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) hA[i] = pack_h2(h[i][0], h[i][1]);
+        AR_T(t_5, hA[0] ^ hA[3]);
+        AR_ACC(tl_top, t_1 - t_0); AR_ACC(tl_conv, t_2 - t_1); AR_ACC(tl_gate, t_3 - t_2); AR_ACC(tl_sync, t_4 - t_3); AR_ACC(tl_res, t_5 - t_4);
+      };
+      {
+        int l = 0;
+        for (; l + 3 <= L; l += 3) { layer(l, S0); layer(l + 1, S1); layer(l + 2, S2); }
+        if (l < L) { layer(l, S0); if (l + 1 < L) layer(l + 1, S1); }
+      }
+      // pops of the next step's first three layers: their latency hides behind the head
+      if (t + 1 < p.T) {
+        const volatile int* sqn = sq + ((t + 1) & 1) * kMaxL;
+        prefetch(S0, 0, sqn);
+        prefetch(S1, 1, sqn);
+        prefetch(S2, 2, sqn);
       }
 
       // ---- head, last stage (chain warp 0): relu(hidden) @ H2 -> logits (model.py:194-196), sampler -----------
@@ -360,16 +439,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         }
         __syncwarp();
         if (samp) {
+          // ops.py:178-201 on the transformed noise: Gumbel-argmax mixture pick, logistic inverse CDF, clip
           const float* sl = reinterpret_cast<const float*>(smem + Smem::logits) + lane * 24;
-          float lgv[24];
+          int k = 0;
+          float best = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 24; i++) lgv[i] = sl[i];
-          int k;
-          xs = mol_sample_one(lgv, u1v, u2v, p.M, &k);    // ops.py:178-201
+          for (int m = 0; m < 8; m++) {
+            if (m < p.M) {
+              const float v = sl[m] + g1v[m];                             // ops.py:187
+              if (v > best) { best = v; k = m; }
+            }
+          }
+          const float mean = sl[p.M + k];
+          const float ls = fmaxf(sl[2 * p.M + k], -7.f);                  // ops.py:192
+          xs = fminf(fmaxf(fmaf(expf(ls), lg2v, mean), -1.f), 1.f);       // ops.py:197-199
           p.x_out[(size_t)ub * p.T + t] = xs;
           if (p.logits_out) {
             float* dst = p.logits_out + ((size_t)ub * p.T + t) * O;
-            for (int i = 0; i < O; i++) dst[i] = lgv[i];
+            for (int i = 0; i < O; i++) dst[i] = sl[i];
           }
         }
         if (lane < kU) sx[lane] = xs;
@@ -383,9 +470,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
       if (sx[8] < 0.f) break;
     }
 #ifdef SRWN_AR_TIMING
-    if (lane == 0 && blockIdx.x == 0) printf("chain warp %d: layers %lld clk/step, wait hid2 %lld, head+sampler %lld, final sync %lld\n", j, tm_a / p.T, tm_b / p.T, tm_c / p.T, tm_d / p.T);
+    if (lane == 0 && blockIdx.x == 0) {
+      printf("chain warp %d: layers %lld clk/step, wait hid2 %lld, head+sampler %lld, final sync %lld\n", j, tm_a / p.T, tm_b / p.T, tm_c / p.T, tm_d / p.T);
+      const long long n = (long long)p.T * L;
+      printf("chain warp %d per layer: wait tap %lld, conv mma %lld, gate+store %lld, sync %lld, residual %lld\n", j, tl_top / n, tl_conv / n, tl_gate / n, tl_sync / n, tl_res / n);
+    }
 #endif
     if (j == 0 && lane == 0 && *abort_flag) atomicExch(p.err, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    chain_sync();
+    if (j == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
     return;
   }
 
@@ -480,7 +577,7 @@ static void pack_frag_pair(uint8_t* dst, const float* W, int ld, int K, int N, i
 }
 
 bool ar_mma_supported(const srwn_ctx* c) {
-  return c->cfg.kind == SRWN_TEACHER && c->cfg.n_layers <= armma::kMaxL && (c->cfg.n_layers <= armma::kMaxL - 16 || c->cfg.n_layers >= 20) && 4 * c->cfg.num_mixtures <= 24 &&
+  return c->cfg.kind == SRWN_TEACHER && c->cfg.n_layers >= 3 && c->cfg.n_layers <= armma::kMaxL && (c->cfg.n_layers <= armma::kMaxL - 16 || c->cfg.n_layers >= 20) && 4 * c->cfg.num_mixtures <= 24 &&
          c->cfg.num_mixtures <= 8;
 }
 
@@ -533,7 +630,7 @@ int ar_mma_pack_weights(srwn_ctx* c, cudaStream_t st) {
   return SRWN_OK;
 }
 
-struct ArMmaWs { uint8_t* queues; float *cond, *cb; int* err; size_t bytes; int grid; };
+struct ArMmaWs { uint8_t* queues; float *cond, *cb, *g1, *lg2; int* err; size_t bytes; int grid; };
 
 static ArMmaWs carve_ar_mma(const srwn_ctx* c, int B, int T, void* ws, size_t cap) {
   WsCarver w(ws, cap);
@@ -543,6 +640,8 @@ static ArMmaWs carve_ar_mma(const srwn_ctx* c, int B, int T, void* ws, size_t ca
   r.queues = w.take<uint8_t>((size_t)r.grid * c->sum_dilation * armma::kSlotBytes);
   r.cond = w.take<float>((size_t)B * frames * L * 32);
   r.cb = w.take<float>((size_t)B * frames * (L + 1) * 32);
+  r.g1 = w.take<float>((size_t)B * T * c->cfg.num_mixtures);
+  r.lg2 = w.take<float>((size_t)B * T);
   r.err = w.take<int>(4);
   r.bytes = w.used;
   return r;
@@ -564,13 +663,18 @@ int run_ar_mma(srwn_ctx* c, const float* enc, const float* u1, const float* u2, 
   SRWN_LAUNCH_CHECK();
   fused::k_fold_bias<<<B * frames, 256, 0, st>>>(w.cond, sw + c->off.front_b, sw + c->off.res_b, w.cb, L);
   SRWN_LAUNCH_CHECK();
+  {
+    const int64_t n = (int64_t)B * T, nm = n * c->cfg.num_mixtures;
+    armma::k_sampler_noise<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(u1, u2, w.g1, w.lg2, n, c->cfg.num_mixtures);
+    SRWN_LAUNCH_CHECK();
+  }
   armma::Params p;
   memset(&p, 0, sizeof(p));
   const uint8_t* img = reinterpret_cast<const uint8_t*>(c->d_ar_packed);
   p.chain_w = img;
   p.stream = img + (size_t)L * armma::kChainLayerBytes;
   p.fixed = reinterpret_cast<const float*>(p.stream + (size_t)(L + 5) * armma::kItemBytes);
-  p.cb = w.cb; p.queues = w.queues; p.u1 = u1; p.u2 = u2; p.x_out = x_out; p.logits_out = logits_out; p.err = w.err;
+  p.cb = w.cb; p.queues = w.queues; p.g1 = w.g1; p.lg2 = w.lg2; p.x_out = x_out; p.logits_out = logits_out; p.err = w.err;
   p.B = B; p.T = T; p.L = L; p.P = c->cfg.pool_stride; p.frames = frames; p.M = c->cfg.num_mixtures;
   bool pow2 = true;
   int off = 0;
