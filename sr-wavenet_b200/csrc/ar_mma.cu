@@ -112,6 +112,14 @@ __device__ __forceinline__ void mma8(float (&d)[2], uint32_t a0, uint32_t a2, ui
                : "+f"(d[0]), "+f"(d[1]), "+f"(z0), "+f"(z1)
                : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
+// Same instruction with all four A registers named by the caller.  Rows 8..15 of A only reach rows 8..15 of D, which
+// nobody reads, so a1 / a3 may hold anything: passing registers that already sit next to a0 / a2 (the neighbours
+// inside a 128-bit load, or a quad the caller keeps alive) saves the moves that zero padding would cost.
+__device__ __forceinline__ void mma8q(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -255,6 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     // ================= chain warps: warp j owns channels 8j..8j+7 (n-tile j) of the filter conv and the gate;
     // every warp then computes the whole residual conv and keeps the whole residual stream (no second exchange)
     const int j = warp;
+    const int cpos = (j == 1 ? 2 : j == 2 ? 1 : j) * 4;   // n-tile j's word inside a lane's 16 bytes of a gate slot: order {0, 2, 1, 3}
     auto chain_sync = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
     const int bg = min(b0 + g, p.B - 1);               // utterance of fragment row g (clamped: padding rows repeat the last one)
     const float* cb_b = p.cb + (size_t)bg * p.frames * (L + 1) * 32 + 2 * q;
@@ -264,7 +273,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     volatile float* sx = reinterpret_cast<volatile float*>(smem + Smem::xslot);
     float xm1 = 0.f, xm2 = 0.f;                         // x[t-1], x[t-2] of utterance g
     float h[4][2];                                      // residual stream: n-tile i, columns 8i+2q, 8i+2q+1 of row g
-    uint32_t hA[4];                                     // its fp16 image as A fragments: kt0 (a0,a2), kt1 (a0,a2)
+    uint32_t hA[4];                                     // its fp16 image, n-tile i = channels 8i+2q, 8i+2q+1 (A fragments: kt0 (0,1), kt1 (2,3))
+    uint32_t hB[2];                                     // second copy of hA[2], hA[3]: a0 / a2 of the k-tile 1 quad
+    uint32_t dm[6];                                     // don't-care registers that complete the k-tile 1 quads
+#pragma unroll
+    for (int i = 0; i < 6; i++) asm volatile("mov.u32 %0, %%laneid;" : "=r"(dm[i]));   // opaque to ptxas: a constant would be re-materialised per use
     long long it_base = 0;                              // ring item counter at the start of the step
     const int ub = b0 + lane;                           // sampler lanes 0..7 of warp 0: utterance b0+lane
     const bool samp = j == 0 && lane < kU && ub < p.B;
@@ -328,10 +341,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
       }
 #pragma unroll
       for (int i = 0; i < 4; i++) hA[i] = pack_h2(h[i][0], h[i][1]);
+      hB[0] = pack_h2(h[2][0], h[2][1]); hB[1] = pack_h2(h[3][0], h[3][1]);
       // filter-conv B fragments of this warp's n-tile: [taps k-tiles 0,1 | current k-tiles 2,3]
       uint4 wft = lds128_ro(sbase + Smem::chain + lane * 16 + (2 * j) * 512);
       uint4 wfc = lds128_ro(sbase + Smem::chain + lane * 16 + (2 * j + 1) * 512);
 
+      // Register quads of the A operands (a0, a1, a2, a3); a1 / a3 are don't-care (see mma8q).  The 16 bytes a lane
+      // keeps per queue slot / gate slot are ordered {k-tile 0: a0, k-tile 1: a0, k-tile 0: a2, k-tile 1: a2}, so the
+      // 128-bit value IS the quad of k-tile 0 and the quad of k-tile 1 is two moves.
       auto layer = [&](const int l, Pre& S) {
         const uint32_t wl = sbase + Smem::chain + l * kChainLayerBytes + lane * 16;
         AR_T(t_0, hA[0]);
@@ -339,24 +356,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         tmem_ld8(tm + (l + 1) * 8, cbn);
         // ---- filter conv (ops.py:6-10), n-tile j: taps (W[0] on h[t-d]) and current (W[1] on h[t]) as two
         //      independent accumulation chains
-        float acc[2] = {0.f, 0.f}, acc2[2] = {0.f, 0.f};
-        mma8(acc2, hA[0], hA[1], wfc.x, wfc.y);
-        mma8(acc, S.tap.x, S.tap.y, wft.x, wft.y);
-        mma8(acc2, hA[2], hA[3], wfc.z, wfc.w);
-        mma8(acc, S.tap.z, S.tap.w, wft.z, wft.w);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+        mma8q(acc2, hA[0], hA[2], hA[1], hA[3], wfc.x, wfc.y);
+        mma8q(acc, S.tap.x, S.tap.y, S.tap.z, S.tap.w, wft.x, wft.y);
+        mma8q(acc2, hB[0], dm[0], hB[1], dm[1], wfc.z, wfc.w);
+        mma8q(acc, S.tap.y, dm[2], S.tap.w, dm[3], wft.z, wft.w);
         AR_T(t_1, S.tap.x);
         AR_T(t_2, __float_as_uint(acc[0] + acc2[0]));
         uint4 wr[4];                                     // residual B fragments: land while the gate runs
 #pragma unroll
         for (int i = 0; i < 4; i++) wr[i] = lds128_ro(wl + 4096 + i * 512);
         // push h[t] (the slot held h[t-d] until now); every chain warp holds the same image
-        if (j == 0) *reinterpret_cast<uint4*>(qbase + S.ofs) = make_uint4(hA[0], hA[1], hA[2], hA[3]);
+        if (j == 0) *reinterpret_cast<uint4*>(qbase + S.ofs) = make_uint4(hA[0], hA[2], hA[1], hA[3]);
         if (l + 3 < L) prefetch(S, l + 3, sqt);          // this set's next use: layer l + 3
         // ---- gate (ops.py:28,33,36) of this warp's 8 channels -> one word of the A fragments of the residual / skip convs
         {
           const float2 b = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(smem + Smem::chain + l * kChainLayerBytes + 6144) + 8 * j + 2 * q);
           const uint32_t cj = pack_h2(gate(acc[0] + acc2[0] + b.x), gate(acc[1] + acc2[1] + b.y));
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + Smem::cslots + l * kSlotBytes + j * 128 + lane * 4), "r"(cj) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + Smem::cslots + l * kSlotBytes + lane * 16 + cpos), "r"(cj) : "memory");
         }
         AR_T(t_3, 0u);
         if (l + 1 < L) {                                 // next layer's filter-conv fragments
@@ -366,17 +383,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         chain_sync();                                    // the four words of every lane's slot are in place
         AR_T(t_4, 0u);
         if (j == 0 && lane == 0) mbar_arrive(bar(B_CFULL + l));      // release: the skip warps may read the slot
-        uint32_t cA[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cA[i]) : "r"(sbase + Smem::cslots + l * kSlotBytes + i * 128 + lane * 4) : "memory");
+        const uint4 cA = lds128(sbase + Smem::cslots + l * kSlotBytes + lane * 16);     // {c n-tile 0, 2, 1, 3}
         // ---- residual 1x1 (ops.py:39) and dense = (inputs + residual) * sqrt(1/2) (ops.py:40); the folded
         //      term carries sqrt(1/2)*bias and the next layer's conditioning (model.py:183)
-        float r[4][2];
+        float r[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { r[i][0] = r[i][1] = 0.f; mma8(r[i], cA[0], cA[1], wr[i].x, wr[i].y); }
+        for (int i = 0; i < 4; i++) { r[i][0] = r[i][1] = r[i][2] = r[i][3] = 0.f; mma8q(r[i], cA.x, cA.y, cA.z, cA.w, wr[i].x, wr[i].y); }
 #pragma unroll
-        for (int i = 0; i < 4; i++) mma8(r[i], cA[2], cA[3], wr[i].z, wr[i].w);
+        for (int i = 0; i < 4; i++) mma8q(r[i], cA.y, dm[4], cA.w, dm[5], wr[i].z, wr[i].w);
         tmem_wait_ld(cbn);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -385,6 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) hA[i] = pack_h2(h[i][0], h[i][1]);
+        hB[0] = pack_h2(h[2][0], h[2][1]); hB[1] = pack_h2(h[3][0], h[3][1]);
         AR_T(t_5, hA[0] ^ hA[3]);
         AR_ACC(tl_top, t_1 - t_0); AR_ACC(tl_conv, t_2 - t_1); AR_ACC(tl_gate, t_3 - t_2); AR_ACC(tl_sync, t_4 - t_3); AR_ACC(tl_res, t_5 - t_4);
       };
@@ -491,28 +506,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
   if (p.dbg & 32) return;
   const float* shb = reinterpret_cast<const float*>(smem + Smem::hbias);
   long long it = 0;
+  uint32_t sdm0, sdm1;                                   // don't-care registers of the k-tile 1 quad
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(sdm0));
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(sdm1));
   for (int t = 0; t < p.T; t++) {
-    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};        // skip sum, n-tiles 2sw, 2sw+1 (model.py:190)
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // skip sum, n-tiles 2sw, 2sw+1 (model.py:190); [2], [3]: unused rows
     bool ok = true;
     for (int l = 0; l < L && ok; l++, it++) {
       const int st = (int)(it % kStages);
       ok = ((p.dbg & 16) || mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag)) &&
            mbar_wait(bar(B_CFULL + l), (uint32_t)(t & 1), abort_flag);      // suspended, not spinning: the chain warps share the SMSPs
       if (!ok) break;
-      uint4 a;                                           // gate output: word i = n-tile i of row g
-      {
-        const uint32_t ca = sbase + Smem::cslots + l * kSlotBytes + lane * 4;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a.x) : "r"(ca) : "memory");
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a.y) : "r"(ca + 128) : "memory");
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a.z) : "r"(ca + 256) : "memory");
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a.w) : "r"(ca + 384) : "memory");
-      }
+      const uint4 a = lds128(sbase + Smem::cslots + l * kSlotBytes + lane * 16);   // gate output, n-tiles {0, 2, 1, 3}
       const uint32_t wb = sbase + Smem::ring + st * kItemBytes + sw * 1024 + lane * 16;
       const uint4 w0 = lds128(wb), w1 = lds128(wb + 512);
-      mma8(acc[0], a.x, a.y, w0.x, w0.y);
-      mma8(acc[1], a.x, a.y, w1.x, w1.y);
-      mma8(acc[0], a.z, a.w, w0.z, w0.w);
-      mma8(acc[1], a.z, a.w, w1.z, w1.w);
+      mma8q(acc[0], a.x, a.y, a.z, a.w, w0.x, w0.y);
+      mma8q(acc[1], a.x, a.y, a.z, a.w, w1.x, w1.y);
+      mma8q(acc[0], a.y, sdm0, a.w, sdm1, w0.z, w0.w);
+      mma8q(acc[1], a.y, sdm0, a.w, sdm1, w1.z, w1.w);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_WEMPTY + st));
     }
