@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;              // fragment row / column-pair index
   const int L = p.L, O = 4 * p.M;
-  const int n_items = L + 5;
+  const int n_items = L;                              // ring items per step: the skip weights of each layer
   // hidden-layer exchange tiles (16 x 256 B used): behind the gate slots when there is room, else on top of
   // slots 0..15, which every skip warp has left by then (the 3-stage ring keeps them within 3 layers of each other)
   const int hid_slot = (L + 16 <= kMaxL) ? L : 0;
@@ -293,6 +293,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     // tensor memory, one table per chain warp, and come back with tcgen05.ld a layer ahead of their use.
     struct Pre { uint4 tap; int ofs; };
     Pre S0, S1, S2;
+    uint4 h2w[4];                                       // H2 B fragments of logit n-tile j (warps 0..2), k-tile pairs 0..3
+#pragma unroll
+    for (int kp = 0; kp < 4; kp++)
+      h2w[kp] = j < 3 ? *reinterpret_cast<const uint4*>(p.stream + (size_t)(L + 4) * kItemBytes + ((j * 4 + kp) * 512) + lane * 16)
+                      : make_uint4(0u, 0u, 0u, 0u);
     float2 cb0[4];                                      // folded term of layer 0 (front bias + conditioning)
     const uint32_t tm = tmem_base + ((uint32_t)(j * 32) << 16);
     auto slot_of = [&](int l, int t) {
@@ -416,43 +421,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         prefetch(S2, 2, sqn);
       }
 
-      // ---- head, last stage (chain warp 0): relu(hidden) @ H2 -> logits (model.py:194-196), sampler -----------
+      // ---- head, last stage: relu(hidden) @ H2 -> logits (model.py:194-196), chain warp i < 3 owns logit n-tile i with
+      //      its H2 fragments resident in registers (nothing to fetch on the critical path); then the sampler ----------
       float xs = 0.f;
       const long long c1 = clock64();
       long long c2 = c1;
-      if (j == 0) {
+      if (j < 3) {
         ok = ok && ((p.dbg & 32) || mbar_wait(bar(B_HID2), (uint32_t)(t & 1), abort_flag));
         c2 = clock64();
-        const long long it = it_base + L + 4;
-        const int st = (int)(it % kStages);
-        ok = ok && ((p.dbg & 16) || mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag));
-        float lg[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-        {
-          const uint32_t hb = sbase + Smem::cslots + (hid_slot + 8) * kSlotBytes + lane * 8;   // hid2 tiles
-          const uint32_t wb = sbase + Smem::ring + st * kItemBytes + lane * 16;
+        float lgA[4] = {0.f, 0.f, 0.f, 0.f}, lgB[4] = {0.f, 0.f, 0.f, 0.f};      // two accumulation chains
+        const uint32_t hb = sbase + Smem::cslots + (hid_slot + 8) * kSlotBytes + lane * 8;   // hid2 tiles
 #pragma unroll
-          for (int kp = 0; kp < 4; kp++) {
-            const uint2 a0 = lds64(hb + (2 * kp) * kSlotBytes), a1 = lds64(hb + (2 * kp + 1) * kSlotBytes);
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              const uint4 w = lds128(wb + (i * 4 + kp) * 512);
-              mma8(lg[i], a0.x, a0.y, w.x, w.y);
-              mma8(lg[i], a1.x, a1.y, w.z, w.w);
-            }
+        for (int kp = 0; kp < 4; kp++) {
+          const uint2 a0 = lds64(hb + (2 * kp) * kSlotBytes), a1 = lds64(hb + (2 * kp + 1) * kSlotBytes);
+          if (kp & 1) {
+            mma8q(lgB, a0.x, dm[0], a0.y, dm[1], h2w[kp].x, h2w[kp].y);
+            mma8q(lgB, a1.x, dm[2], a1.y, dm[3], h2w[kp].z, h2w[kp].w);
+          } else {
+            mma8q(lgA, a0.x, dm[0], a0.y, dm[1], h2w[kp].x, h2w[kp].y);
+            mma8q(lgA, a1.x, dm[2], a1.y, dm[3], h2w[kp].z, h2w[kp].w);
           }
         }
-        __syncwarp();
-        if (lane < 8) mbar_arrive(bar(B_WEMPTY + st));    // this item has one consumer warp: 8 lanes stand in for 8 warps
-        {
-          const float* b2 = reinterpret_cast<const float*>(smem + Smem::hbias) + 256;
-          float* sl = reinterpret_cast<float*>(smem + Smem::logits) + g * 24;
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            sl[8 * i + 2 * q] = lg[i][0] + b2[8 * i + 2 * q];
-            sl[8 * i + 2 * q + 1] = lg[i][1] + b2[8 * i + 2 * q + 1];
-          }
-        }
-        __syncwarp();
+        const float* b2 = reinterpret_cast<const float*>(smem + Smem::hbias) + 256;
+        float* slw = reinterpret_cast<float*>(smem + Smem::logits) + g * 24 + 8 * j + 2 * q;
+        slw[0] = (lgA[0] + lgB[0]) + b2[8 * j + 2 * q];
+        slw[1] = (lgA[1] + lgB[1]) + b2[8 * j + 2 * q + 1];
+      }
+      chain_sync();                                       // the three logit n-tiles are in shared memory
+      if (j == 0) {
         if (samp) {
           // ops.py:178-201 on the transformed noise: Gumbel-argmax mixture pick, logistic inverse CDF, clip
           const float* sl = reinterpret_cast<const float*>(smem + Smem::logits) + lane * 24;
@@ -506,6 +502,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
   if (p.dbg & 32) return;
   const float* shb = reinterpret_cast<const float*>(smem + Smem::hbias);
   long long it = 0;
+  uint4 h1w[4][2];                                        // H1 B fragments of this warp's two n-tiles, resident: [k-tile pair][n-tile]
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int nl = 0; nl < 2; nl++)
+      h1w[i][nl] = *reinterpret_cast<const uint4*>(p.stream + (size_t)(L + i) * kItemBytes + sw * 1024 + nl * 512 + lane * 16);
   uint32_t sdm0, sdm1;                                   // don't-care registers of the k-tile 1 quad
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(sdm0));
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(sdm1));
@@ -537,24 +539,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
       mbar_arrive(bar(B_HID1));
     }
     if (!mbar_wait(bar(B_HID1), (uint32_t)(t & 1), abort_flag)) break;
-    float hd[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    for (int i = 0; i < 4 && ok; i++, it++) {           // H1 arrives as 4 items of two k-tiles each
-      const int st = (int)(it % kStages);
-      ok = (p.dbg & 16) || mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag);
-      if (!ok) break;
-      const uint32_t wb = sbase + Smem::ring + st * kItemBytes + sw * 1024 + lane * 16;
-      const uint4 w0 = lds128(wb), w1 = lds128(wb + 512);
+    float hd[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, he[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                       // S -> S conv of the head (model.py:193): two chains per n-tile
       const uint2 a0 = lds64(sbase + Smem::cslots + (hid_slot + 2 * i) * kSlotBytes + lane * 8);
       const uint2 a1 = lds64(sbase + Smem::cslots + (hid_slot + 2 * i + 1) * kSlotBytes + lane * 8);
-      mma8(hd[0], a0.x, a0.y, w0.x, w0.y);
-      mma8(hd[1], a0.x, a0.y, w1.x, w1.y);
-      mma8(hd[0], a1.x, a1.y, w0.z, w0.w);
-      mma8(hd[1], a1.x, a1.y, w1.z, w1.w);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_WEMPTY + st));
+      mma8q(hd[0], a0.x, sdm0, a0.y, sdm1, h1w[i][0].x, h1w[i][0].y);
+      mma8q(hd[1], a0.x, sdm0, a0.y, sdm1, h1w[i][1].x, h1w[i][1].y);
+      mma8q(he[0], a1.x, sdm0, a1.y, sdm1, h1w[i][0].z, h1w[i][0].w);
+      mma8q(he[1], a1.x, sdm0, a1.y, sdm1, h1w[i][1].z, h1w[i][1].w);
     }
-    if (!ok) break;
-    it++;                                               // the H2 item belongs to the chain warp
+#pragma unroll
+    for (int e = 0; e < 2; e++) { hd[0][e] += he[0][e]; hd[1][e] += he[1][e]; }
     {
       const int c = 16 * sw + 2 * q;
       const uint32_t a0 = pack_h2(fmaxf(hd[0][0] + shb[128 + c], 0.f), fmaxf(hd[0][1] + shb[128 + c + 1], 0.f));
