@@ -293,14 +293,28 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
   if (warp == 0) pp[2 * kR * kR + lane] = gb;
 }
 
-// sums `rows` partial rows (row pitch `pitch`) of width `w` into dst (+=), one thread per column, fixed order
-__global__ void k_reduce_partials(const float* __restrict__ partial, int rows, int pitch, int w, float* __restrict__ dst) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= w) return;
+// sums `rows` partial rows (row pitch `pitch`) of width w1 + w2 into dst1 [w1] and dst2 [w2] (+=) in a fixed order:
+// 32 columns per CTA, the rows split over the 8 warps (independent loads in flight), then a fixed-order sum of the 8 parts
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const float* __restrict__ partial, int rows, int pitch, int w1, float* __restrict__ dst1, int w2,
+                  float* __restrict__ dst2) {
+  __shared__ float red[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5, j = blockIdx.x * 32 + x, w = w1 + w2;
   float acc = 0.f;
-  for (int r = 0; r < rows; r++) acc += partial[(size_t)r * pitch + j];
-  dst[j] += acc;
+  if (j < w) {
+#pragma unroll 8
+    for (int r = y; r < rows; r += 8) acc += partial[(size_t)r * pitch + j];
+  }
+  red[y][x] = acc;
+  __syncthreads();
+  if (y == 0 && j < w) {
+    float t = red[0][x];
+#pragma unroll
+    for (int k = 1; k < 8; k++) t += red[k][x];
+    if (j < w1) dst1[j] += t; else dst2[j - w1] += t;
+  }
 }
+static inline unsigned reduce_grid(int w) { return (unsigned)((w + 31) / 32); }
 
 // ---- flow head backward (model.py:451-452, 479-482) ---------------------------------------------------
 // inputs per sample: d_scale, d_mean (from the composition), d_xout (from the next flow's front conv), x_prev, scale;
@@ -370,17 +384,30 @@ k_bwd_front(const float* __restrict__ x_in, const float* __restrict__ dh0, const
 }
 
 // conditioning 1x1 (model.py:431): cond[bf][l][r] = enc[bf][:] Wc_l[:, r] + bc_l[r]
-// dWc_l[c][r] += sum_bf enc[bf][c] dcond_l[bf][r];  dbc_l[r] += sum_bf dcond_l[bf][r].   grid = L, block = 256
-__global__ void k_bwd_cond(const float* __restrict__ enc, const float* __restrict__ dcond,   // dcond [L][BF][32]
-                           float* __restrict__ dWc, float* __restrict__ dbc, int BF, int C) {
-  const int l = blockIdx.x;
+// dWc_l[c][r] += sum_bf enc[bf][c] dcond_l[bf][r];  dbc_l[r] += sum_bf dcond_l[bf][r].   grid = (L, C + 1), block = 256:
+// CTA (l, c) owns the 32 outputs of input channel c (c == C: the bias); lane = r, the 8 warps split the frames, and
+// their parts are added in a fixed order
+__global__ void __launch_bounds__(256)
+k_bwd_cond(const float* __restrict__ enc, const float* __restrict__ dcond,   // dcond [L][BF][32]
+           float* __restrict__ dWc, float* __restrict__ dbc, int BF, int C) {
+  __shared__ float red[8][kR];
+  const int l = blockIdx.x, c = blockIdx.y, r = threadIdx.x & 31, y = threadIdx.x >> 5;
   const float* dl = dcond + (size_t)l * BF * kR;
-  for (int o = threadIdx.x; o < (C + 1) * kR; o += blockDim.x) {
-    const int c = o / kR, r = o % kR;
-    float acc = 0.f;
-    if (c < C) for (int bf = 0; bf < BF; bf++) acc = fmaf(enc[(size_t)bf * C + c], dl[(size_t)bf * kR + r], acc);
-    else for (int bf = 0; bf < BF; bf++) acc += dl[(size_t)bf * kR + r];
-    if (c < C) dWc[((size_t)l * C + c) * kR + r] += acc; else dbc[(size_t)l * kR + r] += acc;
+  float acc = 0.f;
+  if (c < C) {
+#pragma unroll 4
+    for (int bf = y; bf < BF; bf += 8) acc = fmaf(enc[(size_t)bf * C + c], dl[(size_t)bf * kR + r], acc);
+  } else {
+#pragma unroll 4
+    for (int bf = y; bf < BF; bf += 8) acc += dl[(size_t)bf * kR + r];
+  }
+  red[y][r] = acc;
+  __syncthreads();
+  if (y == 0) {
+    float t = red[0][r];
+#pragma unroll
+    for (int k = 1; k < 8; k++) t += red[k][r];
+    if (c < C) dWc[((size_t)l * C + c) * kR + r] += t; else dbc[(size_t)l * kR + r] += t;
   }
 }
 
@@ -472,13 +499,13 @@ __global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float
   w[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
-__global__ void k_sumsq(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
-  __shared__ double s_red[256];
+__global__ void __launch_bounds__(1024) k_sumsq(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+  __shared__ double s_red[1024];
   double acc = 0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)g[i] * g[i];
   s_red[threadIdx.x] = acc;
   __syncthreads();
-  for (int s = 128; s >= 1; s >>= 1) { if (threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s]; __syncthreads(); }
+  for (int s = 512; s >= 1; s >>= 1) { if (threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s]; __syncthreads(); }
   if (threadIdx.x == 0) *out = (float)s_red[0];
 }
 
@@ -494,7 +521,7 @@ static TrainWs carve_train(const srwn_ctx* c, int B, int T, void* ws, size_t cap
   WsCarver w(ws, cap);
   TrainWs r{};
   const size_t n = (size_t)B * T, L = c->cfg.n_layers, F = c->cfg.num_flows, frames = T / c->cfg.pool_stride;
-  r.grid = 2 * (c->sm_count > 0 ? c->sm_count : 148);
+  r.grid = 3 * (c->sm_count > 0 ? c->sm_count : 148);     // three CTAs of k_bwd_gate / k_bwd_conv fit one SM (registers, shared memory)
   r.acts = w.take<float>(F * (L + 1) * n * kR);
   r.cond = w.take<float>((size_t)B * frames * L * kR);
   r.scales = w.take<float>(F * n);
@@ -568,9 +595,7 @@ int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const fl
     k_bwd_flow_head<<<grid, 256, 0, st>>>(acts + (size_t)L * n * kR, x_prev, w.scales + (size_t)f * n, w.d_scales + (size_t)f * n,
                                           w.d_means + (size_t)f * n, dx_next, sw + o.head1_k, w.g0, dx_cur, w.partial, (int64_t)n);
     SRWN_LAUNCH_CHECK();
-    k_reduce_partials<<<1, 64, 0, st>>>(w.partial, grid, 66, 64, gs + o.head1_k);
-    SRWN_LAUNCH_CHECK();
-    k_reduce_partials<<<1, 32, 0, st>>>(w.partial + 64, grid, 66, 2, gs + o.head1_b);
+    k_reduce_partials<<<reduce_grid(66), 256, 0, st>>>(w.partial, grid, 66, 64, gs + o.head1_k, 2, gs + o.head1_b);
     SRWN_LAUNCH_CHECK();
     SRWN_CUDA(cudaMemsetAsync(w.dcond, 0, (size_t)L * BF * kR * sizeof(float), st));
     float* g = w.g0;
@@ -582,29 +607,25 @@ int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const fl
                                                            sw + o.filt_b + (size_t)l * kR, sw + o.res_k + (size_t)l * kR * kR,
                                                            w.partial, B, T, d);
       SRWN_LAUNCH_CHECK();
-      k_reduce_partials<<<(kR * kR + 255) / 256, 256, 0, st>>>(w.partial, grid, kR * kR + kR, kR * kR, gs + o.res_k + (size_t)l * kR * kR);
-      SRWN_LAUNCH_CHECK();
-      k_reduce_partials<<<1, 32, 0, st>>>(w.partial + kR * kR, grid, kR * kR + kR, kR, gs + o.res_b + (size_t)l * kR);
+      k_reduce_partials<<<reduce_grid(kR * kR + kR), 256, 0, st>>>(w.partial, grid, kR * kR + kR, kR * kR, gs + o.res_k + (size_t)l * kR * kR,
+                                                                  kR, gs + o.res_b + (size_t)l * kR);
       SRWN_LAUNCH_CHECK();
       // x_l carries cond_l (added before the block, model.py:183; for l = 0 by the front): dcond_l = sum over the frame of dx_l
       k_bwd_conv<<<grid, kThreads, sizeof(ConvSmem), st>>>(x_l, g, w.da, gn, sw + o.filt_k + (size_t)l * 2 * kR * kR, w.partial,
                                                            w.dcond + (size_t)l * BF * kR, B, T, d, P, frames);
       SRWN_LAUNCH_CHECK();
-      k_reduce_partials<<<(2 * kR * kR + 255) / 256, 256, 0, st>>>(w.partial, grid, 2 * kR * kR + kR, 2 * kR * kR, gs + o.filt_k + (size_t)l * 2 * kR * kR);
-      SRWN_LAUNCH_CHECK();
-      k_reduce_partials<<<1, 32, 0, st>>>(w.partial + 2 * kR * kR, grid, 2 * kR * kR + kR, kR, gs + o.filt_b + (size_t)l * kR);
+      k_reduce_partials<<<reduce_grid(2 * kR * kR + kR), 256, 0, st>>>(w.partial, grid, 2 * kR * kR + kR, 2 * kR * kR,
+                                                                      gs + o.filt_k + (size_t)l * 2 * kR * kR, kR, gs + o.filt_b + (size_t)l * kR);
       SRWN_LAUNCH_CHECK();
       float* tmp = g; g = gn; gn = tmp;
     }
     // g = dLoss/dx_0 (front output incl. cond_0)
     k_bwd_front<<<grid, 256, 0, st>>>(x_prev, g, sw + o.front_k, f > 0 ? dx_cur : nullptr, w.partial, B, T);
     SRWN_LAUNCH_CHECK();
-    k_reduce_partials<<<1, 64, 0, st>>>(w.partial, grid, 96, 64, gs + o.front_k);
-    SRWN_LAUNCH_CHECK();
-    k_reduce_partials<<<1, 32, 0, st>>>(w.partial + 64, grid, 96, 32, gs + o.front_b);
+    k_reduce_partials<<<reduce_grid(96), 256, 0, st>>>(w.partial, grid, 96, 64, gs + o.front_k, 32, gs + o.front_b);
     SRWN_LAUNCH_CHECK();
     // conditioning: every layer's dcond -> dWc, dbc
-    k_bwd_cond<<<L, 256, 0, st>>>(enc, w.dcond, gs + o.cond_k, gs + o.cond_b, BF, C);
+    k_bwd_cond<<<dim3(L, C + 1), 256, 0, st>>>(enc, w.dcond, gs + o.cond_k, gs + o.cond_b, BF, C);
     SRWN_LAUNCH_CHECK();
     dx_next = dx_cur;
     dx_cur = dx_cur == w.dxa ? w.dxb : w.dxa;
@@ -622,7 +643,7 @@ int run_mol_nll_grad(const float* x, const float* l, float* dx, float* nll, int 
 int run_adam(srwn_ctx* c, const float* grads, float* m, float* v, float* scratch1, float clip, float lr, float b1, float b2,
              float eps, int step, cudaStream_t st) {
   const int64_t n = (int64_t)c->n_stacks * c->stack_floats;
-  train::k_sumsq<<<1, 256, 0, st>>>(grads, n, scratch1);
+  train::k_sumsq<<<1, 1024, 0, st>>>(grads, n, scratch1);
   SRWN_LAUNCH_CHECK();
   const float lr_t = lr * sqrtf(1.f - powf(b2, (float)step)) / (1.f - powf(b1, (float)step));
   train::k_adam<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->d_weights, grads, m, v, scratch1, clip, lr_t, b1, b2, eps, n);

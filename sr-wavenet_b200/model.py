@@ -312,6 +312,27 @@ class WaveNetAutoEncoder(_CheckpointMixin):
     def save(self, logdir, global_step, force=False):
         return self._save(logdir, global_step, force)
 
+    @classmethod
+    def from_checkpoint(cls, logdir, dilations, latent_channels, pool_stride, condition_size=0, filter_width=2,
+                        dilation_channels=32, input_size=0):
+        """A teacher built from a checkpoint directory alone (what ParallelWaveNet(teacher=<dir>) needs,
+        model.py:323-334): mixtures, skip and encoder widths come from the stored variable shapes."""
+        state = os.path.join(logdir, 'checkpoint')
+        if not os.path.exists(state):
+            raise IOError("no teacher checkpoint under %s (expected the files WaveNetAutoEncoder.save writes)" % logdir)
+        with open(state) as f:
+            path = os.path.join(logdir, f.readline().split('"')[1] + '.npz')
+        L = len(dilations)
+        with np.load(path) as z:
+            head2 = z['%sconv1d_%d/kernel' % (synth.TEACHER_PREFIX, 3 * L + 1)]
+            enc0 = z['%snc_conv_NC/conv1d/kernel' % synth.ENCODER_PREFIX]
+        t = cls(input_size=input_size, condition_size=condition_size, num_mixtures=head2.shape[2] // 4, dilations=dilations,
+                filter_width=filter_width, encoder_channels=enc0.shape[2], dilation_channels=dilation_channels,
+                skip_channels=head2.shape[1], latent_channels=latent_channels, pool_stride=pool_stride)
+        if not t.load(logdir):
+            raise IOError("could not restore the teacher from %s" % logdir)
+        return t
+
     # -- sess.run wrappers -------------------------------------------------------------------
     def train(self, inputs, conditions=None):
         raise NotImplementedError("teacher training (model.py:242-248) is outside the hot path")
@@ -445,6 +466,14 @@ class ParallelWaveNet(_CheckpointMixin):
         self.condition_size = condition_size
         self.dilations = list(dilations)
         self.teacher = teacher
+        if isinstance(teacher, str):
+            # model.py:326-331 imports the teacher's meta-graph from this directory; here the checkpoint written by
+            # WaveNetAutoEncoder.save names every variable, and the constructor arguments the graph would carry
+            # (mixtures, skip / encoder channels) are read off the variable shapes
+            self.teacher = WaveNetAutoEncoder.from_checkpoint(teacher, dilations, latent_channels=latent_channels,
+                                                              pool_stride=pool_stride, condition_size=condition_size,
+                                                              filter_width=filter_width,
+                                                              dilation_channels=dilation_channels, input_size=input_size)
         self.num_flows = num_flows
         self.filter_width = filter_width
         self.dilation_channels = dilation_channels
@@ -483,6 +512,8 @@ class ParallelWaveNet(_CheckpointMixin):
         self._weights.update({k: np.array(v, dtype=np.float32) for k, v in weights.items()})
 
     def get_weights(self):
+        if getattr(self, "_packed_stale", False):        # trained on the device since the last read-back
+            self.sync_weights()
         return dict(self._weights)
 
     def available_precisions(self):
