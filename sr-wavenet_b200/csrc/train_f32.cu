@@ -47,6 +47,134 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], float a0, float a1, floa
 }
 constexpr int kWP = kR + 8;         // pitch of B operands read as (k = q, n = g): banks 8q + g
 
+// ---- forward layer of the training pass ---------------------------------------------------------------
+// x_{l+1} = (x_l + c Wr + br) sqrt(1/2) + cond_{l+1},  c = f sigmoid(f),  f = tanh([x_l[t-d] | x_l[t]] Wf + bf)   (ops.py:23-46)
+// Same tiling as the backward kernels (64 time steps, persistent CTAs, weights staged once).  The GEMMs run on the
+// tensor cores at fp32 grade: every operand is split into two TF32 numbers (x = hi + lo, |lo| <= 2^-11 |hi|) and a
+// product is three MMAs, lo*hi + hi*lo + hi*hi, small terms first (the dropped lo*lo term is 2^-22 relative).  The
+// stored activations are what the backward pass differentiates, so they stay within the fp32 path's 1e-4 of the oracle.
+struct FwdSmem {
+  float tap_h[kTT][kAP], tap_l[kTT][kAP], cur_h[kTT][kAP], cur_l[kTT][kAP], c_h[kTT][kAP], c_l[kTT][kAP];
+  float wf_h[2 * kR][kWP], wf_l[2 * kR][kWP], wr_h[kR][kWP], wr_l[kR][kWP], bf[kR], br[kR];
+};
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) { hi = tf32r(x); lo = tf32r(x - hi); }
+__device__ __forceinline__ void split_store4(float* h, float* l, float4 v) {
+  float4 vh, vl;
+  split_tf32(v.x, vh.x, vl.x); split_tf32(v.y, vh.y, vl.y); split_tf32(v.z, vh.z, vl.z); split_tf32(v.w, vh.w, vl.w);
+  *reinterpret_cast<float4*>(h) = vh;
+  *reinterpret_cast<float4*>(l) = vl;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const float* __restrict__ filt_k,
+            const float* __restrict__ filt_b, const float* __restrict__ res_k, const float* __restrict__ res_b,
+            const float* __restrict__ cond_next,     // cond + (l + 1) * R of layout [B][frames][L][R], or null after the last layer
+            int B, int T, int d, int P, int L, int frames) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdSmem& s = *reinterpret_cast<FwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  for (int i = tid; i < 2 * kR * kR; i += kThreads) split_tf32(filt_k[i], s.wf_h[i / kR][i % kR], s.wf_l[i / kR][i % kR]);
+  for (int i = tid; i < kR * kR; i += kThreads) split_tf32(res_k[i], s.wr_h[i / kR][i % kR], s.wr_l[i / kR][i % kR]);
+  if (tid < kR) { s.bf[tid] = filt_b[tid]; s.br[tid] = res_b[tid]; }
+  const int tiles_per_b = (T + kTT - 1) / kTT;
+  const int n_tiles = B * tiles_per_b;
+  const int mt = warp & 3, nh = warp >> 2, r0 = mt * 16;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
+    const float* xb = x_l + (size_t)b * T * kR;
+    __syncthreads();
+    for (int i = tid; i < kTT * (kR / 4); i += kThreads) {
+      const int row = i / (kR / 4), c4 = i % (kR / 4);
+      const int t = t0 + row;
+      float4 cur = make_float4(0, 0, 0, 0), tap = cur;
+      if (t < T) {
+        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + c4 * 4);
+        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + c4 * 4);
+      }
+      split_store4(&s.cur_h[row][c4 * 4], &s.cur_l[row][c4 * 4], cur);
+      split_store4(&s.tap_h[row][c4 * 4], &s.tap_l[row][c4 * 4], tap);
+    }
+    __syncthreads();
+    // filter conv (ops.py:6-20): W[0] pairs with x[t-d], W[1] with x[t]
+    float acc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+      const int n0 = nh * 16 + nt * 8 + 2 * q;
+      acc[nt][0] = acc[nt][2] = s.bf[n0]; acc[nt][1] = acc[nt][3] = s.bf[n0 + 1];
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+      const float (*XH)[kAP] = ks < 4 ? s.tap_h : s.cur_h;
+      const float (*XL)[kAP] = ks < 4 ? s.tap_l : s.cur_l;
+      const int kc = (ks & 3) * 8;
+      const float h0 = XH[r0 + g][kc + q], h1 = XH[r0 + g + 8][kc + q], h2 = XH[r0 + g][kc + q + 4], h3 = XH[r0 + g + 8][kc + q + 4];
+      const float l0 = XL[r0 + g][kc + q], l1 = XL[r0 + g + 8][kc + q], l2 = XL[r0 + g][kc + q + 4], l3 = XL[r0 + g + 8][kc + q + 4];
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        const int n0 = nh * 16 + nt * 8 + g;
+        const float bh0 = s.wf_h[ks * 8 + q][n0], bh1 = s.wf_h[ks * 8 + q + 4][n0];
+        const float bl0 = s.wf_l[ks * 8 + q][n0], bl1 = s.wf_l[ks * 8 + q + 4][n0];
+        mma_tf32(acc[nt], l0, l1, l2, l3, bh0, bh1);
+        mma_tf32(acc[nt], h0, h1, h2, h3, bl0, bl1);
+        mma_tf32(acc[nt], h0, h1, h2, h3, bh0, bh1);
+      }
+    }
+    // gate: tanh, sigmoid OF THE TANH, product (ops.py:28,33,36)
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+      const int n0 = nh * 16 + nt * 8 + 2 * q;
+      float cv[4], ch[4], cl[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float f = tanhf(acc[nt][e]); cv[e] = f * sigmoidf_(f); split_tf32(cv[e], ch[e], cl[e]); }
+      *reinterpret_cast<float2*>(&s.c_h[r0 + g][n0]) = make_float2(ch[0], ch[1]);
+      *reinterpret_cast<float2*>(&s.c_h[r0 + g + 8][n0]) = make_float2(ch[2], ch[3]);
+      *reinterpret_cast<float2*>(&s.c_l[r0 + g][n0]) = make_float2(cl[0], cl[1]);
+      *reinterpret_cast<float2*>(&s.c_l[r0 + g + 8][n0]) = make_float2(cl[2], cl[3]);
+    }
+    __syncthreads();
+    // residual 1x1 (ops.py:39), dense = (inputs + residual) * sqrt(1/2) (ops.py:40), next layer's conditioning (model.py:183)
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+      const int n0 = nh * 16 + nt * 8 + 2 * q;
+      acc[nt][0] = acc[nt][2] = s.br[n0]; acc[nt][1] = acc[nt][3] = s.br[n0 + 1];
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const int kc = ks * 8;
+      const float h0 = s.c_h[r0 + g][kc + q], h1 = s.c_h[r0 + g + 8][kc + q], h2 = s.c_h[r0 + g][kc + q + 4], h3 = s.c_h[r0 + g + 8][kc + q + 4];
+      const float l0 = s.c_l[r0 + g][kc + q], l1 = s.c_l[r0 + g + 8][kc + q], l2 = s.c_l[r0 + g][kc + q + 4], l3 = s.c_l[r0 + g + 8][kc + q + 4];
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        const int n0 = nh * 16 + nt * 8 + g;
+        const float bh0 = s.wr_h[kc + q][n0], bh1 = s.wr_h[kc + q + 4][n0];
+        const float bl0 = s.wr_l[kc + q][n0], bl1 = s.wr_l[kc + q + 4][n0];
+        mma_tf32(acc[nt], l0, l1, l2, l3, bh0, bh1);
+        mma_tf32(acc[nt], h0, h1, h2, h3, bl0, bl1);
+        mma_tf32(acc[nt], h0, h1, h2, h3, bh0, bh1);
+      }
+    }
+    const int ta = t0 + r0 + g, tb = ta + 8;
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+      const int n0 = nh * 16 + nt * 8 + 2 * q;
+      if (ta < T) {
+        const size_t at = ((size_t)b * T + ta) * kR + n0;
+        const float2 xv = *reinterpret_cast<const float2*>(x_l + at);
+        float2 v = make_float2((xv.x + acc[nt][0]) * SRWN_SQRT_HALF, (xv.y + acc[nt][1]) * SRWN_SQRT_HALF);
+        if (cond_next) { const float2 cn = *reinterpret_cast<const float2*>(cond_next + ((size_t)b * frames + ta / P) * L * kR + n0); v.x += cn.x; v.y += cn.y; }
+        *reinterpret_cast<float2*>(x_next + at) = v;
+      }
+      if (tb < T) {
+        const size_t at = ((size_t)b * T + tb) * kR + n0;
+        const float2 xv = *reinterpret_cast<const float2*>(x_l + at);
+        float2 v = make_float2((xv.x + acc[nt][2]) * SRWN_SQRT_HALF, (xv.y + acc[nt][3]) * SRWN_SQRT_HALF);
+        if (cond_next) { const float2 cn = *reinterpret_cast<const float2*>(cond_next + ((size_t)b * frames + tb / P) * L * kR + n0); v.x += cn.x; v.y += cn.y; }
+        *reinterpret_cast<float2*>(x_next + at) = v;
+      }
+    }
+  }
+}
+
 // ---- gate backward ------------------------------------------------------------------------------------
 // g = dL/dx_{l+1}; recomputes a, f, c from x_l; writes da = dL/da; accumulates dWr [32][32], dbr [32].
 // Tile = 64 time steps, 8 warps.  Stages 1-2: warp (mt = warp & 3, nh = warp >> 2) owns rows 16 mt.. and channels
@@ -543,6 +671,32 @@ static TrainWs carve_train(const srwn_ctx* c, int B, int T, void* ws, size_t cap
 size_t train_workspace_bytes(const srwn_ctx* c, int B, int T) { return carve_train(c, B, T, nullptr, 0).bytes; }
 
 // forward of all flows in fp32, keeping every layer input (model.py:489-535)
+// forward of one flow keeping every layer input: acts [L+1][B][T][R], acts[l] = block input of layer l, acts[L] = stack output
+static int run_stack_train_acts(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T, float* acts,
+                                float* cond, int grid, cudaStream_t st) {
+  const float* w = stack_w(c, stack);
+  const StackOffsets& o = c->off;
+  const int L = c->cfg.n_layers, P = c->cfg.pool_stride, C = c->cfg.cond_channels, frames = T / P;
+  const size_t n = (size_t)B * T;
+  k_cond<<<B * frames, 256, 0, st>>>(enc, w + o.cond_k, w + o.cond_b, cond, B * frames, L, C);
+  SRWN_LAUNCH_CHECK();
+  {
+    dim3 g((unsigned)(((int64_t)T * kR + 255) / 256), B);
+    k_front<<<g, 256, 0, st>>>(xin, w + o.front_k, w + o.front_b, cond, acts, T, P, L, frames);
+    SRWN_LAUNCH_CHECK();
+  }
+  SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmem)));
+  for (int l = 0; l < L; l++) {
+    const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
+    train::k_fwd_layer<<<grid, train::kThreads, sizeof(train::FwdSmem), st>>>(
+        acts + (size_t)l * n * kR, acts + (size_t)(l + 1) * n * kR, w + o.filt_k + (size_t)l * 2 * kR * kR,
+        w + o.filt_b + (size_t)l * kR, w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR, cond_next,
+        B, T, c->dilations[l], P, L, frames);
+    SRWN_LAUNCH_CHECK();
+  }
+  return SRWN_OK;
+}
+
 int run_student_forward_train(srwn_ctx* c, const float* z, const float* enc, float* out, float* s_tot,
                               float* mu_tot, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st) {
   TrainWs w = carve_train(c, B, T, ws, ws_bytes);
@@ -552,7 +706,7 @@ int run_student_forward_train(srwn_ctx* c, const float* z, const float* enc, flo
   const float* xin = z;
   for (int f = 0; f < F; f++) {
     float* acts = w.acts + (size_t)f * (L + 1) * n * kR;
-    int rc = run_stack_f32_acts(c, f, xin, enc, B, T, acts, w.cond, st);
+    int rc = run_stack_train_acts(c, f, xin, enc, B, T, acts, w.cond, 2 * (w.grid / 3), st);
     if (rc) return rc;
     rc = run_flow_head_f32(c, f, acts + (size_t)L * n * kR, xin, w.scales + (size_t)f * n, w.means + (size_t)f * n,
                            w.xs + (size_t)f * n, B, T, st);
