@@ -1,9 +1,10 @@
 """Host-side audio source for the drivers (teacher.py / student.py at the repo root).
 
 The reference reads NSynth TFRecords through a private tf.Session (nsynth.py:5-52: parse, shuffle, repeat, batch;
-``next()`` returns ``(audio[:, :num_samples], one_hot(pitch, 128))``).  TensorFlow is not part of this build, so the
-same ``next()`` contract is served from a directory of .wav files (int16 / 32767 like data.py:7-123) or from the
-synthetic waves of simple_audio.py:40-61.  Pure host I/O: nothing here touches the GPU path."""
+``next()`` returns ``(audio[:, :num_samples], one_hot(pitch, 128))``).  The same ``next()`` contract is served from a
+``*.tfrecord`` file (``nsynth.NsynthDataReader``, a TensorFlow-free reader of the same format), from a directory of
+.wav files (int16 / 32767 like data.py:7-123) or from the synthetic waves of simple_audio.py:40-61.  Pure host I/O:
+nothing here touches the GPU path."""
 import glob
 import os
 
@@ -13,12 +14,16 @@ from . import synth
 
 
 class AudioReader(object):
-    def __init__(self, source, batch_size, num_samples, seed=1234):
+    def __init__(self, source, batch_size, num_samples, seed=1234, audio_max_length=16000):
         self.batch_size, self.num_samples = batch_size, num_samples
         self._cursor = 0
         self._seed = seed
         self._files = None
-        if source not in (None, "synthetic"):
+        self._tfrecord = None
+        if source not in (None, "synthetic") and os.path.isfile(source):
+            from .nsynth import NsynthDataReader              # teacher.py:53: NsynthDataReader(path, batch, num_samples, audio_max_length=16000)
+            self._tfrecord = NsynthDataReader(source, batch_size, num_samples, audio_max_length=audio_max_length)
+        elif source not in (None, "synthetic"):
             self._files = sorted(glob.glob(os.path.join(source, "*.wav")))
             if not self._files:
                 raise ValueError("no .wav files under %s" % source)
@@ -35,6 +40,8 @@ class AudioReader(object):
     def next(self):
         """-> (audio [B, num_samples] float32 in [-1, 1], one-hot pitch [B, 128])."""
         B = self.batch_size
+        if self._tfrecord is not None:
+            return self._tfrecord.next()
         if self._files is None:
             x = synth.synthetic_audio(B, self.num_samples, seed=self._seed + self._cursor)
         else:

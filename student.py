@@ -2,8 +2,8 @@
 (student.py:89-160: encode -> logistic noise -> train_fast; every print_steps the entropy, a synthesis and a
 reconstruction) and ``--test`` the synthesis entry point (student.py:163-197), on the CUDA hot path.
 
-Host-side differences: audio comes from ``--data`` (a directory of .wav files) or synthetic waves instead of an NSynth
-TFRecord; results are written as .wav (no matplotlib windows); ``--steps`` bounds the training loop (the reference's
+Host-side differences: audio comes from ``--data``: an NSynth TFRecord (read without TensorFlow), a directory of .wav
+files, or synthetic waves; results are written as .wav (no matplotlib windows); ``--steps`` bounds the training loop (the reference's
 literal is 1000000).  ``--teacher`` is a checkpoint directory written by teacher.py / WaveNetAutoEncoder.save; without
 one a randomly initialised teacher is used and the driver says so."""
 import argparse
@@ -39,7 +39,8 @@ def build_parser():
     p.add_argument('--sample-rate', type=int, default=4000)
     p.add_argument('--steps', type=int, default=1000000, help='last training step (exclusive)')
     p.add_argument('--print-steps', type=int, default=25)
-    p.add_argument('--data', type=str, default='synthetic', help='"synthetic" or a directory of .wav files')
+    p.add_argument('--data', type=str, default='synthetic', help='"synthetic", an NSynth .tfrecord file (nsynth.py) or a directory of .wav files')
+    p.add_argument('--audio-max-length', type=int, default=16000, help='length of the audio feature in the TFRecord (nsynth.py:6)')
     p.add_argument('--out-dir', type=str, default='.')
     p.add_argument('--clips', type=int, default=20, help='--test: number of clips')
     p.add_argument('--precision', type=str, default='fp16', choices=['fp32', 'bf16', 'fp16'])
@@ -53,7 +54,7 @@ def main(argv=None):
     from sr_wavenet_b200.audio_data import AudioReader, write_wav
 
     num_samples, batch = args.num_samples, args.batch_size
-    audio_data = AudioReader(args.data, batch, num_samples)
+    audio_data = AudioReader(args.data, batch, num_samples, audio_max_length=args.audio_max_length)
     teacher = args.teacher
     if teacher is None or not os.path.exists(os.path.join(teacher, 'checkpoint')):
         print('no teacher checkpoint under %r: using a randomly initialised teacher' % (teacher,))

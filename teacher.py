@@ -2,8 +2,8 @@
 ``--test-fast`` (one teacher-forced pass + parallel sampling, teacher.py:117-138) and ``--test-slow`` (sample-by-sample
 generation, teacher.py:140-170) on the CUDA hot path.
 
-Differences, all host-side: audio comes from ``--data`` (a directory of .wav files) or synthetic waves instead of an
-NSynth TFRecord; results are written as .wav (no matplotlib windows); ``--test-slow`` runs the dilation-queue kernel
+Differences, all host-side: audio comes from ``--data``: an NSynth TFRecord (read without TensorFlow), a directory of
+.wav files, or synthetic waves; results are written as .wav (no matplotlib windows); ``--test-slow`` runs the dilation-queue kernel
 (one call, O(T)) and, with ``--check-naive N``, also the reference's literal loop (one full decoder pass per sample,
 teacher.py:153-170) on the first N samples with the same noise to show that both produce the same audio.
 ``--train`` is not offered: teacher training (model.py:242-248) is outside the hot path of this build."""
@@ -35,7 +35,8 @@ def build_parser():
     # additions (the reference hard-codes these: teacher.py:42-47)
     p.add_argument('--num-samples', type=int, default=4096)
     p.add_argument('--sample-rate', type=int, default=4000)
-    p.add_argument('--data', type=str, default='synthetic', help='"synthetic" or a directory of .wav files')
+    p.add_argument('--data', type=str, default='synthetic', help='"synthetic", an NSynth .tfrecord file (nsynth.py) or a directory of .wav files')
+    p.add_argument('--audio-max-length', type=int, default=16000, help='length of the audio feature in the TFRecord (nsynth.py:6)')
     p.add_argument('--out-dir', type=str, default='.')
     p.add_argument('--clips', type=int, default=None, help='number of clips (default: 10 for --test-fast, 1 for --test-slow)')
     p.add_argument('--precision', type=str, default='fp16', choices=['fp32', 'bf16', 'fp16'])
@@ -52,7 +53,7 @@ def main(argv=None):
     if args.train:
         raise SystemExit("teacher training (model.py:242-248) is outside the hot path of this build")
     num_samples, batch = args.num_samples, args.batch_size
-    audio_data = AudioReader(args.data, batch, num_samples)
+    audio_data = AudioReader(args.data, batch, num_samples, audio_max_length=args.audio_max_length)
     teacher = srwn.WaveNetAutoEncoder(input_size=num_samples, condition_size=0, num_mixtures=5, dilations=DILATIONS,
                                       latent_channels=args.latent_channels, skip_channels=128,
                                       pool_stride=args.pool_stride, learning_rate=1e-4)

@@ -56,5 +56,10 @@ def test_student_driver_train_and_test(srwn, tmp_path):
     assert isinstance(s2.teacher, srwn.WaveNetAutoEncoder) and s2.teacher.num_mixtures == 5
     np.testing.assert_array_equal(s2.teacher.get_weights()["WaveNetAutoEncoder/Decoder/causal_conv_Kernel"],
                                   t.get_weights()["WaveNetAutoEncoder/Decoder/causal_conv_Kernel"])
-    res = drv.main(common + ["--test", "--clips", "1"])
+    # --test reads an NSynth-style TFRecord through the TensorFlow-free reader (nsynth.py:5-52)
+    from sr_wavenet_b200 import nsynth, synth
+    rec = str(tmp_path / "clips.tfrecord")
+    clips = synth.synthetic_audio(4, 2048)
+    nsynth.write_tfrecord(rec, [{"audio": c, "pitch": np.array([60])} for c in clips])
+    res = drv.main(common + ["--test", "--clips", "1", "--data", rec, "--audio-max-length", "2048"])
     assert res["output_shape"] == (2, 1024, 1)
