@@ -74,6 +74,7 @@ struct Params {
   int ring_bytes_per_cta;
   int dil[kMaxLayers];
   int ring_off[kMaxLayers];   // byte offset of layer l's ring inside a CTA's ring block
+  int rsuf[kMaxLayers + 1];   // rsuf[l] = dil[l] + ... + dil[L-1]: how far back h_l is needed before the first output row
 };
 
 // ---- shared memory map ------------------------------------------------------------------
@@ -233,8 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
   const Seg* segs = p.segs + (size_t)blockIdx.x * kMaxSeg;
   const int nseg = p.nseg[blockIdx.x];
   uint8_t* ring = p.rings + (size_t)blockIdx.x * p.ring_bytes_per_cta;
-  const int uses0 = (L + 1) >> 1, uses1 = L >> 1;     // per-chunk phases of the parity-indexed barriers
-  int chunk_idx = 0;                                  // chunks processed so far (phase bookkeeping)
+  int u0e = 0, u0o = 0, lay_base = 0;                 // phases of the parity-indexed / per-layer barriers used so far
+  int chunk_idx = 0;                                  // chunks processed so far
   int head_idx = 0;                                   // chunks with a head phase so far
   double nll_acc = 0.0;
   const bool elected = elect_one();
@@ -244,13 +245,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
     for (int t0 = sg.t_start; t0 < sg.t_end; t0 += kChunk, chunk_idx++) {
       const bool warm = TEACHER ? (t0 + kChunk <= sg.t_out) : false;   // student chunks always need h (cheap)
       const bool do_head = TEACHER && !warm;
-      const int u0e = chunk_idx * uses0, u0o = chunk_idx * uses1;      // phase base of parity-indexed barriers
+      // A warm-up chunk only feeds the rings: layer l's output h_{l+1} is needed on the rsuf[l+1] rows before the first
+      // output row t_out (h_{l+1}[t] reads h_l[t] and h_l[t - d_l]), so a chunk that ends `dist` rows before t_out runs
+      // the layers with rsuf[l+1] > dist and nothing deeper; rows outside that cone hold garbage nobody reads.
+      int Lc = L;
+      if (t0 + kChunk <= sg.t_out) {
+        const int dist = sg.t_out - (t0 + kChunk);
+        Lc = 0;
+        while (Lc < L && p.rsuf[Lc + 1] > dist) Lc++;
+        if (Lc < 1) Lc = 1;
+      }
 #define U0(par) ((par) ? u0o : u0e)
       const bool tracing_chunk = p.trace != nullptr && blockIdx.x == 0 && chunk_idx == p.trace_chunk;
 
       if (warp == kLoadWarp) {
         // ================= loader: weights (bulk copy) + halo rows (cp.async) per layer ============
-        for (int l = 0; l < L; l++) {
+        for (int l = 0; l < Lc; l++) {
           const int s = l & 1;
           const int use = U0(s) + (l >> 1);                  // how many times stage s was used before
           const bool tracing = tracing_chunk && lane == 0;
@@ -366,9 +376,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           mbar_arrive(bar(BAR_HD + 2 * m + 0));
         }
 
-        for (int l = 0; l < L; l++) {
+        for (int l = 0; l < Lc; l++) {
           const int s = l & 1, sn = s ^ 1;
-          const uint32_t ph = (chunk_idx * L + l) & 1, phs = (U0(s) + (l >> 1)) & 1;
+          const uint32_t ph = (lay_base + l) & 1, phs = (U0(s) + (l >> 1)) & 1;
           TRACE(m, l, 0);
           // ---- filter-conv GEMM: K = 64, steps 0,1 = tap rows (W[0], d rows earlier), 2,3 = current rows (W[1])
           const uint32_t hb_lo = hb_lo0 + (uint32_t)(s * (SmemMap::hbuf_bytes >> 4));
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           //  - activation buffer sn is free once the filter-conv MMAs of layer l-1 retired (all tiles),
           //  - ring l+1 may be overwritten once this chunk's halo of layer l+1 was read
           bool next_ok = true;
-          if (l + 1 < L && !issuer) {
+          if (l + 1 < Lc && !issuer) {
             if (l >= 1) next_ok = mbar_poll(bar(BAR_G1 + sn), (U0(sn) + ((l - 1) >> 1)) & 1);
             next_ok = mbar_poll(bar(BAR_HALO + sn), (U0(sn) + ((l + 1) >> 1)) & 1) && next_ok;
           }
@@ -488,15 +498,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           if (l + 1 < L) {
 #pragma unroll
             for (int j = 0; j < 16; j++) { float a, b; upk(h2[j], a, b); w16[j] = pack2<FP16>(a, b); }
-            if (!next_ok) {                             // rare: the polls were too early
-              if (l >= 1) alive = mbar_wait(bar(BAR_G1 + sn), (U0(sn) + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l) && alive;
-              alive = mbar_wait(bar(BAR_HALO + sn), (U0(sn) + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l) && alive;
+            if (l + 1 < Lc) {
+              if (!next_ok) {                           // rare: the polls were too early
+                if (l >= 1) alive = mbar_wait(bar(BAR_G1 + sn), (U0(sn) + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l) && alive;
+                alive = mbar_wait(bar(BAR_HALO + sn), (U0(sn) + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l) && alive;
+              }
+              TRACE(m, l, 10);
+              store_row_packed(smem + SmemMap::hbuf + sn * SmemMap::hbuf_bytes, kRows, kHalo + rc, w16);
+              tc_fence_before();
+              LOOP_FENCE();
+              mbar_arrive(bar(BAR_HD + 2 * m + sn));
+            } else {
+              tc_fence_before();                        // last layer of a pruned warm-up chunk: only the ring rows below
             }
-            TRACE(m, l, 10);
-            store_row_packed(smem + SmemMap::hbuf + sn * SmemMap::hbuf_bytes, kRows, kHalo + rc, w16);
-            tc_fence_before();
-            LOOP_FENCE();
-            mbar_arrive(bar(BAR_HD + 2 * m + sn));
             // history for the next chunk (read by the loader after the chunk-end barrier)
             const int dn = p.dil[l + 1];
             if (!(SRWN_EXP & 4) && rc >= kChunk - dn) store_row_packed(ring + p.ring_off[l + 1], dn, t % dn, w16);
@@ -606,6 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         }
       }
       if (do_head) head_idx++;
+      u0e += (Lc + 1) >> 1; u0o += Lc >> 1; lay_base += Lc;
       tc_fence_before();
       asm volatile("fence.proxy.async;" ::: "memory");   // ring rows (generic stores) -> next chunk's bulk loads
       __syncthreads();          // chunk boundary: every role is quiescent, buffers and rings are consistent
@@ -788,7 +803,10 @@ int fused_pack_weights(srwn_ctx* c, cudaStream_t st) {
 // ---- work partition: equal-cost contiguous pieces of the (utterance, chunk) line -------------------
 struct Partition { std::vector<Seg> segs; std::vector<int> nseg; int grid; };
 
-static bool try_partition(int B, int T, int warm_chunks, int grid, double budget, Partition* out) {
+// warm_cost[k] = cost (in full chunks) of the k warm-up chunks nearest the first output row: a warm-up chunk skips the skip
+// GEMM and the head (x0.85) and runs only the layers inside the dependency cone (k_fused: rsuf[l+1] > dist)
+static bool try_partition(int B, int T, const std::vector<double>& warm_cost, int grid, double budget, Partition* out) {
+  const int warm_chunks = (int)warm_cost.size() - 1;
   const int NC = (T + kChunk - 1) / kChunk;
   std::vector<Seg> segs((size_t)grid * kMaxSeg);
   std::vector<int> nseg(grid, 0);
@@ -799,7 +817,7 @@ static bool try_partition(int B, int T, int warm_chunks, int grid, double budget
     while (c0 < NC) {
       if (cta >= grid) return false;
       const int warm = c0 == 0 ? 0 : std::min(warm_chunks, c0);
-      double room = budget - used - 0.85 * warm;
+      double room = budget - used - warm_cost[warm];
       int take = (int)room;
       if (take < 1 || nseg[cta] >= kMaxSeg) {
         if (used == 0 && nseg[cta] < kMaxSeg) take = 1; else { cta++; used = 0; continue; }
@@ -809,7 +827,7 @@ static bool try_partition(int B, int T, int warm_chunks, int grid, double budget
       s.b = b; s.t_start = (c0 - warm) * kChunk; s.t_out = c0 * kChunk;
       s.t_end = std::min(T, (c0 + take) * kChunk);
       segs[(size_t)cta * kMaxSeg + nseg[cta]++] = s;
-      used += take + 0.85 * warm;
+      used += take + warm_cost[warm];
       c0 += take;
     }
   }
@@ -817,18 +835,27 @@ static bool try_partition(int B, int T, int warm_chunks, int grid, double budget
   return true;
 }
 
-static Partition make_partition(int B, int T, int sum_d, int grid) {
+static Partition make_partition(int B, int T, const std::vector<int>& dilations, int grid) {
   const int NC = (T + kChunk - 1) / kChunk;
-  const int warm_chunks = (sum_d + kChunk - 1) / kChunk;
+  const int L = (int)dilations.size();
+  std::vector<int> rsuf(L + 1, 0);
+  for (int l = L - 1; l >= 0; l--) rsuf[l] = rsuf[l + 1] + dilations[l];
+  const int warm_chunks = (rsuf[0] + kChunk - 1) / kChunk;
+  std::vector<double> warm_cost(warm_chunks + 1, 0.0);
+  for (int k = 0; k < warm_chunks; k++) {                      // chunk k ends k * kChunk rows before the first output row
+    int lc = 0;
+    while (lc < L && rsuf[lc + 1] > k * kChunk) lc++;
+    warm_cost[k + 1] = warm_cost[k] + 0.85 * std::max(lc, 1) / (double)L;
+  }
   const long long total = (long long)B * NC;
   if (total < grid) grid = (int)total;
   double lo = (double)total / grid, hi = lo + warm_chunks + 2;
   Partition best;
-  while (!try_partition(B, T, warm_chunks, grid, hi, &best)) hi *= 1.5;
+  while (!try_partition(B, T, warm_cost, grid, hi, &best)) hi *= 1.5;
   for (int it = 0; it < 24; it++) {
     const double mid = 0.5 * (lo + hi);
     Partition cand;
-    if (try_partition(B, T, warm_chunks, grid, mid, &cand)) { hi = mid; best = cand; } else lo = mid;
+    if (try_partition(B, T, warm_cost, grid, mid, &cand)) { hi = mid; best = cand; } else lo = mid;
   }
   return best;
 }
@@ -886,7 +913,7 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   if (first) {
     // the work partition depends on (B, T) only: built once, kept on the device next to the handle
     if (!c->d_part || c->part_B != B || c->part_T != T) {
-      *part = make_partition(B, T, c->sum_dilation, c->sm_count);
+      *part = make_partition(B, T, c->dilations, c->sm_count);
       const size_t seg_bytes = (size_t)c->sm_count * kMaxSeg * sizeof(Seg), n_bytes = (size_t)c->sm_count * sizeof(int);
       if (!c->d_part) SRWN_CUDA(cudaMalloc(&c->d_part, seg_bytes + n_bytes));
       std::vector<uint8_t> host(seg_bytes + n_bytes, 0);
@@ -913,6 +940,8 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   p->ring_bytes_per_cta = c->sum_dilation * 64 + 256;
   int off = 0;
   for (int l = 0; l < L; l++) { p->dil[l] = c->dilations[l]; p->ring_off[l] = off; off += c->dilations[l] * 64; }
+  p->rsuf[L] = 0;
+  for (int l = L - 1; l >= 0; l--) p->rsuf[l] = p->rsuf[l + 1] + c->dilations[l];
   return SRWN_OK;
 }
 
