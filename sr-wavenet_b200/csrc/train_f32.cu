@@ -27,6 +27,8 @@ constexpr int kAP = kR + 4;         // padded pitch
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 // ---- warp-level TF32 tensor-core helpers (mma.sync.m16n8k8, fp32 accumulate) ------------------------------
 // The backward GEMMs are tiny in N and K (32 / 64 channels) and HBM-bound once they leave the FFMA pipe; operands are
@@ -222,7 +224,7 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
     }
     __syncthreads();
     // stage 1: a = [x[t-d] | x[t]] Wf + bf (ops.py:6-20), f = tanh(a), c = f sigmoid(f) (ops.py:28,33,36)
-    float acc[2][4], fv[2][4];
+    float acc[2][4], fv[2][4], sv[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; nt++) {
       const int n0 = nh * 16 + nt * 8 + 2 * q;
@@ -243,9 +245,11 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
     for (int nt = 0; nt < 2; nt++) {
       const int n0 = nh * 16 + nt * 8 + 2 * q;
 #pragma unroll
-      for (int e = 0; e < 4; e++) fv[nt][e] = tanhf(acc[nt][e]);
-      *reinterpret_cast<float2*>(&s.c[r0 + g][n0]) = make_float2(tf32r(fv[nt][0] * sigmoidf_(fv[nt][0])), tf32r(fv[nt][1] * sigmoidf_(fv[nt][1])));
-      *reinterpret_cast<float2*>(&s.c[r0 + g + 8][n0]) = make_float2(tf32r(fv[nt][2] * sigmoidf_(fv[nt][2])), tf32r(fv[nt][3] * sigmoidf_(fv[nt][3])));
+      // recomputed gate: the operands are TF32 already (2^-11), so the MUFU approximations (tanh.approx, ex2 / rcp) cost nothing
+      // in accuracy here; the forward pass that produced the stored activations uses the accurate functions
+      for (int e = 0; e < 4; e++) { fv[nt][e] = tanh_approx(acc[nt][e]); sv[nt][e] = sigmoid_fast(fv[nt][e]); }
+      *reinterpret_cast<float2*>(&s.c[r0 + g][n0]) = make_float2(tf32r(fv[nt][0] * sv[nt][0]), tf32r(fv[nt][1] * sv[nt][1]));
+      *reinterpret_cast<float2*>(&s.c[r0 + g + 8][n0]) = make_float2(tf32r(fv[nt][2] * sv[nt][2]), tf32r(fv[nt][3] * sv[nt][3]));
     }
     // stage 2: dc[t][k] = sum_n dres[t][n] Wr[k][n]  (same (row, channel) positions as a / f)
     float dc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -265,7 +269,7 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
       float da[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        const float f = fv[nt][e], sg = sigmoidf_(f);
+        const float f = fv[nt][e], sg = sv[nt][e];
         const float df = dc[nt][e] * (sg + f * sg * (1.f - sg));       // d(f sigmoid(f))/df
         da[e] = df * (1.f - f * f);                                    // tanh'
       }
