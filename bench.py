@@ -46,15 +46,52 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples the SM clock and the clock-event (throttle) reasons of this rank's GPU while the timed region runs:
+    NVML in-process every 2 ms (the timed region of the short workloads lasts ~15 ms, less than one nvidia-smi start-up);
+    `nvidia-smi -lms` is the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self._stop = None, None, threading.Event()
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        try:
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.rows.append((mhz, int(get(self.handle))))
+        except Exception:
+            pass
+
+    def _loop_nvml(self):
+        while not self._stop.is_set():
+            self._sample_nvml()
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -70,6 +107,16 @@ class ClockSampler(object):
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+            sm = sorted(r[0] for r in self.rows)
+            mask = 0
+            for r in self.rows:
+                mask |= r[1]
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(name for bit, name in self.NVML_REASONS if mask & bit), "samples": len(sm),
+                    "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +137,7 @@ class ClockSampler(object):
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_port_samples_per_s(B, T, repeats, warm=1):
