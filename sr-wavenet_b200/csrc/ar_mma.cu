@@ -42,8 +42,8 @@ constexpr int kChainLayerBytes = 4096 + 2048 + 128;   // Wf fragments | Wr fragm
 constexpr int kItemBytes = 8192;              // one ring item: skip weights of a layer / a quarter of H1 / H2
 constexpr int kStages = 3;
 constexpr int kSlotBytes = 512;               // gate output of one layer: [lane][4 x b32]
-constexpr int kThreads = 13 * 32;
-constexpr int kChainWarps = 4, kProducerWarp = 4;     // warps 0..3: chain (one per SMSP), 4: producer, 5..12: skip warps
+constexpr int kThreads = 9 * 32;
+constexpr int kChainWarps = 4, kProducerWarp = 4, kSkipWarps = 4;   // warps 0..3: chain (one per SMSP), 4: producer, 5..8: skip warps
 
 struct Smem {
   static constexpr int chain = 0;
@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_WFULL + s)), "r"(1));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_WEMPTY + s)), "r"(8));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_WEMPTY + s)), "r"(kSkipWarps));
     }
     for (int l = 0; l < kMaxL; l++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_CFULL + l)), "r"(1));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_HID1)), "r"(256));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_HID2)), "r"(256));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_HID1)), "r"(kSkipWarps * 32));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar(B_HID2)), "r"(kSkipWarps * 32));
     *abort_flag = 0;
     for (int i = 0; i < 9; i++) reinterpret_cast<volatile float*>(smem + Smem::xslot)[i] = 0.f;
     for (int l = 0; l < kMaxL; l++) reinterpret_cast<volatile int*>(smem + Smem::flags)[l] = 0;
@@ -498,64 +498,81 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
   }
 
   // ================= skip warps: skip 1x1 summed over layers, then the S->S conv of the head =========
-  const int sw = warp - 5;                                // warps 5..12 -> 0..7
+  // Transposed GEMMs: the WEIGHTS are the A operand (16 output channels x 16 inputs: every row of the tile is used) and the
+  // 8 utterances are the N dimension, so a warp owns 32 output channels with 2 MMAs per k-tile and no padded rows --
+  // half the tensor-pipe work of the row-major form, on pipes the chain warps share.  The B fragment of c^T is the same
+  // register pair as the A fragment of c (b0 = a0, b1 = a2), so the gate slot is read as it is.
+  const int sw = warp - 5;                                // warps 5..8 -> 0..3: skip / hidden channels 32 sw .. 32 sw + 31
   if (p.dbg & 32) return;
   const float* shb = reinterpret_cast<const float*>(smem + Smem::hbias);
   long long it = 0;
-  uint4 h1w[4][2];                                        // H1 B fragments of this warp's two n-tiles, resident: [k-tile pair][n-tile]
+  uint4 h1a[2][8];                                        // H1^T A fragments of this warp's two m-tiles, resident: [m-tile][k-tile]
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-    for (int nl = 0; nl < 2; nl++)
-      h1w[i][nl] = *reinterpret_cast<const uint4*>(p.stream + (size_t)(L + i) * kItemBytes + sw * 1024 + nl * 512 + lane * 16);
-  uint32_t sdm0, sdm1;                                   // don't-care registers of the k-tile 1 quad
-  asm volatile("mov.u32 %0, %%laneid;" : "=r"(sdm0));
-  asm volatile("mov.u32 %0, %%laneid;" : "=r"(sdm1));
+    for (int kt = 0; kt < 8; kt++)
+      h1a[mt][kt] = *reinterpret_cast<const uint4*>(p.stream + (size_t)L * kItemBytes + (size_t)(((sw * 2 + mt) * 8 + kt) * 512) + lane * 16);
+  // where a value (channel c = 16 kt + cc, utterance u) goes inside k-tile kt of a hidden-layer exchange tile so that lane
+  // (g', q') of a consumer finds {(k = 2q', 2q'+1; u = g'), (k = 2q'+8, 2q'+9; u = g')}: the B fragment of hidden^T and,
+  // equally, the (a0, a2) pair of the row-major A fragment the chain warps use for the last conv
+  auto hid_ofs = [&](int c, int u) { const int cc = c & 15; return (c >> 4) * kSlotBytes + (u * 4 + ((cc & 7) >> 1)) * 8 + (cc >> 3) * 4 + (cc & 1) * 2; };
   for (int t = 0; t < p.T; t++) {
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // skip sum, n-tiles 2sw, 2sw+1 (model.py:190); [2], [3]: unused rows
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // skip sum (model.py:190): [m-tile]{(ch g, utt 2q), (g, 2q+1), (g+8, 2q), (g+8, 2q+1)}
     bool ok = true;
     for (int l = 0; l < L && ok; l++, it++) {
       const int st = (int)(it % kStages);
       ok = ((p.dbg & 16) || mbar_wait(bar(B_WFULL + st), (uint32_t)((it / kStages) & 1), abort_flag)) &&
            mbar_wait(bar(B_CFULL + l), (uint32_t)(t & 1), abort_flag);      // suspended, not spinning: the chain warps share the SMSPs
       if (!ok) break;
-      const uint4 a = lds128(sbase + Smem::cslots + l * kSlotBytes + lane * 16);   // gate output, n-tiles {0, 2, 1, 3}
-      const uint32_t wb = sbase + Smem::ring + st * kItemBytes + sw * 1024 + lane * 16;
-      const uint4 w0 = lds128(wb), w1 = lds128(wb + 512);
-      mma8q(acc[0], a.x, a.y, a.z, a.w, w0.x, w0.y);
-      mma8q(acc[1], a.x, a.y, a.z, a.w, w1.x, w1.y);
-      mma8q(acc[0], a.y, sdm0, a.w, sdm1, w0.z, w0.w);
-      mma8q(acc[1], a.y, sdm0, a.w, sdm1, w1.z, w1.w);
+      const uint4 c = lds128(sbase + Smem::cslots + l * kSlotBytes + lane * 16);   // gate output, n-tiles {0, 2, 1, 3}
+      const uint32_t wb = sbase + Smem::ring + st * kItemBytes + sw * 2048 + lane * 16;   // [m-tile][k-tile][lane][16 B]
+      const uint4 w00 = lds128(wb), w01 = lds128(wb + 512), w10 = lds128(wb + 1024), w11 = lds128(wb + 1536);
+      mma8q(acc[0], w00.x, w00.y, w00.z, w00.w, c.x, c.z);
+      mma8q(acc[1], w10.x, w10.y, w10.z, w10.w, c.x, c.z);
+      mma8q(acc[0], w01.x, w01.y, w01.z, w01.w, c.y, c.w);
+      mma8q(acc[1], w11.x, w11.y, w11.z, w11.w, c.y, c.w);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_WEMPTY + st));
     }
     if (!ok) break;
-    // relu(sum of skips + summed skip biases) -> A k-tile `sw` of the S->S conv (model.py:190-193); slots 0..7
+    // relu(sum of skips + summed skip biases) -> hidden^T tiles of the S->S conv (model.py:190-193)
     {
-      const int c = 16 * sw + 2 * q;
-      const uint32_t a0 = pack_h2(fmaxf(acc[0][0] + shb[c], 0.f), fmaxf(acc[0][1] + shb[c + 1], 0.f));
-      const uint32_t a2 = pack_h2(fmaxf(acc[1][0] + shb[c + 8], 0.f), fmaxf(acc[1][1] + shb[c + 9], 0.f));
-      asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sbase + Smem::cslots + (hid_slot + sw) * kSlotBytes + lane * 8), "r"(a0), "r"(a2) : "memory");
+      uint8_t* hb1 = smem + Smem::cslots + hid_slot * kSlotBytes;
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        const int c0 = 32 * sw + 16 * mt + g;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int ch = c0 + (e >> 1) * 8, u = 2 * q + (e & 1);
+          *reinterpret_cast<__half*>(hb1 + hid_ofs(ch, u)) = __float2half_rn(fmaxf(acc[mt][e] + shb[ch], 0.f));
+        }
+      }
       mbar_arrive(bar(B_HID1));
     }
     if (!mbar_wait(bar(B_HID1), (uint32_t)(t & 1), abort_flag)) break;
     float hd[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, he[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-    for (int i = 0; i < 4; i++) {                       // S -> S conv of the head (model.py:193): two chains per n-tile
-      const uint2 a0 = lds64(sbase + Smem::cslots + (hid_slot + 2 * i) * kSlotBytes + lane * 8);
-      const uint2 a1 = lds64(sbase + Smem::cslots + (hid_slot + 2 * i + 1) * kSlotBytes + lane * 8);
-      mma8q(hd[0], a0.x, sdm0, a0.y, sdm1, h1w[i][0].x, h1w[i][0].y);
-      mma8q(hd[1], a0.x, sdm0, a0.y, sdm1, h1w[i][1].x, h1w[i][1].y);
-      mma8q(he[0], a1.x, sdm0, a1.y, sdm1, h1w[i][0].z, h1w[i][0].w);
-      mma8q(he[1], a1.x, sdm0, a1.y, sdm1, h1w[i][1].z, h1w[i][1].w);
+    for (int kt = 0; kt < 8; kt++) {                    // S -> S conv of the head (model.py:193): two chains per m-tile
+      const uint2 b = lds64(sbase + Smem::cslots + (hid_slot + kt) * kSlotBytes + lane * 8);
+      if (kt & 1) {
+        mma8q(he[0], h1a[0][kt].x, h1a[0][kt].y, h1a[0][kt].z, h1a[0][kt].w, b.x, b.y);
+        mma8q(he[1], h1a[1][kt].x, h1a[1][kt].y, h1a[1][kt].z, h1a[1][kt].w, b.x, b.y);
+      } else {
+        mma8q(hd[0], h1a[0][kt].x, h1a[0][kt].y, h1a[0][kt].z, h1a[0][kt].w, b.x, b.y);
+        mma8q(hd[1], h1a[1][kt].x, h1a[1][kt].y, h1a[1][kt].z, h1a[1][kt].w, b.x, b.y);
+      }
     }
-#pragma unroll
-    for (int e = 0; e < 2; e++) { hd[0][e] += he[0][e]; hd[1][e] += he[1][e]; }
     {
-      const int c = 16 * sw + 2 * q;
-      const uint32_t a0 = pack_h2(fmaxf(hd[0][0] + shb[128 + c], 0.f), fmaxf(hd[0][1] + shb[128 + c + 1], 0.f));
-      const uint32_t a2 = pack_h2(fmaxf(hd[1][0] + shb[128 + c + 8], 0.f), fmaxf(hd[1][1] + shb[128 + c + 9], 0.f));
-      asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sbase + Smem::cslots + (hid_slot + 8 + sw) * kSlotBytes + lane * 8), "r"(a0), "r"(a2) : "memory");
+      uint8_t* hb2 = smem + Smem::cslots + (hid_slot + 8) * kSlotBytes;
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        const int c0 = 32 * sw + 16 * mt + g;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int ch = c0 + (e >> 1) * 8, u = 2 * q + (e & 1);
+          *reinterpret_cast<__half*>(hb2 + hid_ofs(ch, u)) = __float2half_rn(fmaxf(hd[mt][e] + he[mt][e] + shb[128 + ch], 0.f));
+        }
+      }
       mbar_arrive(bar(B_HID2));
     }
   }
@@ -580,6 +597,19 @@ static void pack_frag_pair(uint8_t* dst, const float* W, int ld, int K, int N, i
         o[lane * 8 + half * 4 + e] = h16(v);
       }
     }
+  }
+}
+
+// A fragment of W^T for the transposed GEMMs (W is [K][N], row stride ld): m-tile = output channels ch0 .. ch0 + 15,
+// k-tile kt; the 16 bytes lane (g, q) loads are {a0, a1, a2, a3} = {(row g, k 2q..2q+1), (row g+8, same k),
+// (row g, k 2q+8..2q+9), (row g+8, same k)} with A[row][k] = W[16 kt + k][ch0 + row]
+static void pack_frag_a_t(uint8_t* dst, const float* W, int ld, int kt, int ch0) {
+  uint16_t* o = reinterpret_cast<uint16_t*>(dst);
+  for (int lane = 0; lane < 32; lane++) {
+    const int g = lane >> 2, q = lane & 3;
+    const int rows[4] = {g, g + 8, g, g + 8}, ks[4] = {2 * q, 2 * q, 2 * q + 8, 2 * q + 8};
+    for (int r = 0; r < 4; r++)
+      for (int e = 0; e < 2; e++) o[lane * 8 + r * 2 + e] = h16(W[(size_t)(16 * kt + ks[r] + e) * ld + ch0 + rows[r]]);
   }
 }
 
@@ -613,15 +643,17 @@ int ar_mma_pack_weights(srwn_ctx* c, cudaStream_t st) {
     const float* rk = w + o.res_k + (size_t)l * kR * kR;
     for (int j = 0; j < 4; j++) pack_frag_pair(cl + 4096 + j * 512, rk, kR, 32, 32, 0, j);
     memcpy(cl + 6144, w + o.filt_b + (size_t)l * kR, 32 * 4);
-    uint8_t* it = stream + (size_t)l * armma::kItemBytes;           // skip weights: [warp][n-tile local]
+    uint8_t* it = stream + (size_t)l * armma::kItemBytes;           // skip weights, transposed: [warp][m-tile][k-tile]
     const float* sk = w + o.skip_k + (size_t)l * kR * kS;
-    for (int sw = 0; sw < 8; sw++)
-      for (int nl = 0; nl < 2; nl++) pack_frag_pair(it + sw * 1024 + nl * 512, sk, kS, 32, 128, 0, 2 * sw + nl);
+    for (int sw = 0; sw < 4; sw++)
+      for (int mt = 0; mt < 2; mt++)
+        for (int kt = 0; kt < 2; kt++) pack_frag_a_t(it + ((sw * 2 + mt) * 2 + kt) * 512, sk, kS, kt, 32 * sw + 16 * mt);
   }
-  for (int i = 0; i < 4; i++) {                                      // H1: item i = k-tiles 2i, 2i+1
-    uint8_t* it = stream + (size_t)(L + i) * armma::kItemBytes;
-    for (int sw = 0; sw < 8; sw++)
-      for (int nl = 0; nl < 2; nl++) pack_frag_pair(it + sw * 1024 + nl * 512, w + o.head1_k, kS, 128, 128, 2 * i, 2 * sw + nl);
+  {                                                                  // H1, transposed: [warp][m-tile][k-tile], 32 KB = items L..L+3
+    uint8_t* it = stream + (size_t)L * armma::kItemBytes;
+    for (int sw = 0; sw < 4; sw++)
+      for (int mt = 0; mt < 2; mt++)
+        for (int kt = 0; kt < 8; kt++) pack_frag_a_t(it + ((sw * 2 + mt) * 8 + kt) * 512, w + o.head1_k, kS, kt, 32 * sw + 16 * mt);
   }
   {                                                                  // H2: [n-tile][k-tile pair]
     uint8_t* it = stream + (size_t)(L + 4) * armma::kItemBytes;
