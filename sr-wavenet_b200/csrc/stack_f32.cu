@@ -186,6 +186,10 @@ k_layer_f32(const float* __restrict__ hc_in, float* __restrict__ hc_out, float* 
   }
 }
 
+int run_layer_tf32x3(srwn_ctx* c, bool with_skip, const float* x_l, float* x_next, float* skip, const float* filt_k,
+                     const float* filt_b, const float* res_k, const float* res_b, const float* skip_k, const float* skip_b,
+                     const float* cond_next, int B, int T, int d, int P, int L, int frames, int skip_init, cudaStream_t st);
+
 int run_stack_f32(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T,
                   float* h0, float* h1, float* skip, float* cond, float** h_final,
                   cudaStream_t st) {
@@ -201,32 +205,16 @@ int run_stack_f32(srwn_ctx* c, int stack, const float* xin, const float* enc, in
     k_front<<<grid, 256, 0, st>>>(xin, w + o.front_k, w + o.front_b, cond, h0, T, P, L, frames);
     SRWN_LAUNCH_CHECK();
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    SRWN_CUDA(cudaFuncSetAttribute(k_layer_f32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(LayerSmem)));
-    SRWN_CUDA(cudaFuncSetAttribute(k_layer_f32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(LayerSmem)));
-    attr_done = true;
-  }
   float* cur = h0;
   float* nxt = h1;
-  dim3 grid((T + kTT - 1) / kTT, B);
-  ProfScope prof(c, st, with_skip ? "k_layer_f32<true>" : "k_layer_f32<false>", L);
+  ProfScope prof(c, st, with_skip ? "k_fwd_layer<skip> (3xTF32)" : "k_fwd_layer (3xTF32)", L);
   for (int l = 0; l < L; l++) {
     const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
-    if (with_skip)
-      k_layer_f32<true><<<grid, 256, sizeof(LayerSmem), st>>>(
-          cur, nxt, skip, w + o.filt_k + (size_t)l * 2 * kR * kR, w + o.filt_b + (size_t)l * kR,
-          w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR,
-          w + o.skip_k + (size_t)l * kR * kS, w + o.skip_b + (size_t)l * kS, cond_next, T,
-          c->dilations[l], P, L, frames, l == 0);
-    else
-      k_layer_f32<false><<<grid, 256, sizeof(LayerSmem), st>>>(
-          cur, nxt, nullptr, w + o.filt_k + (size_t)l * 2 * kR * kR, w + o.filt_b + (size_t)l * kR,
-          w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR, nullptr, nullptr,
-          cond_next, T, c->dilations[l], P, L, frames, 0);
-    SRWN_LAUNCH_CHECK();
+    int rc = run_layer_tf32x3(c, with_skip, cur, nxt, skip, w + o.filt_k + (size_t)l * 2 * kR * kR, w + o.filt_b + (size_t)l * kR,
+                              w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR,
+                              with_skip ? w + o.skip_k + (size_t)l * kR * kS : nullptr, with_skip ? w + o.skip_b + (size_t)l * kS : nullptr,
+                              cond_next, B, T, c->dilations[l], P, L, frames, l == 0, st);
+    if (rc) return rc;
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
   *h_final = cur;

@@ -10,6 +10,7 @@
 //                          row per CTA) and summed by a second kernel in a fixed order (deterministic).
 #include "common.cuh"
 #include "mol.cuh"
+#include <type_traits>
 
 __global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
                        const float* __restrict__ cond_b, float* __restrict__ cond,
@@ -55,9 +56,17 @@ constexpr int kWP = kR + 8;         // pitch of B operands read as (k = q, n = g
 // tensor cores at fp32 grade: every operand is split into two TF32 numbers (x = hi + lo, |lo| <= 2^-11 |hi|) and a
 // product is three MMAs, lo*hi + hi*lo + hi*hi, small terms first (the dropped lo*lo term is 2^-22 relative).  The
 // stored activations are what the backward pass differentiates, so they stay within the fp32 path's 1e-4 of the oracle.
+constexpr int kSP = kS + 8;         // pitch of the skip weights: banks 8q + g
 struct FwdSmem {
   float tap_h[kTT][kAP], tap_l[kTT][kAP], cur_h[kTT][kAP], cur_l[kTT][kAP], c_h[kTT][kAP], c_l[kTT][kAP];
   float wf_h[2 * kR][kWP], wf_l[2 * kR][kWP], wr_h[kR][kWP], wr_l[kR][kWP], bf[kR], br[kR];
+};
+// teacher layers (skip 1x1, ops.py:44): the skip weights join the resident set and the gate output c takes over the
+// tap rows, which are dead once the filter conv has run, so that two CTAs still fit one SM
+struct FwdSmemSkip {
+  float tap_h[kTT][kAP], tap_l[kTT][kAP], cur_h[kTT][kAP], cur_l[kTT][kAP];
+  float wf_h[2 * kR][kWP], wf_l[2 * kR][kWP], wr_h[kR][kWP], wr_l[kR][kWP], bf[kR], br[kR];
+  float ws_h[kR][kSP], ws_l[kR][kSP], bs[kS];
 };
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) { hi = tf32r(x); lo = tf32r(x - hi); }
 __device__ __forceinline__ void split_store4(float* h, float* l, float4 v) {
@@ -67,14 +76,24 @@ __device__ __forceinline__ void split_store4(float* h, float* l, float4 v) {
   *reinterpret_cast<float4*>(l) = vl;
 }
 
+template <bool SKIP>
 __global__ void __launch_bounds__(kThreads)
 k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const float* __restrict__ filt_k,
             const float* __restrict__ filt_b, const float* __restrict__ res_k, const float* __restrict__ res_b,
             const float* __restrict__ cond_next,     // cond + (l + 1) * R of layout [B][frames][L][R], or null after the last layer
-            int B, int T, int d, int P, int L, int frames) {
+            int B, int T, int d, int P, int L, int frames,
+            const float* __restrict__ skip_k, const float* __restrict__ skip_b, float* __restrict__ skip, int skip_init) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FwdSmem& s = *reinterpret_cast<FwdSmem*>(smem_raw);
+  typedef typename std::conditional<SKIP, FwdSmemSkip, FwdSmem>::type Smem;
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  float (*c_h)[kAP];
+  float (*c_l)[kAP];
+  if constexpr (SKIP) { c_h = s.tap_h; c_l = s.tap_l; } else { c_h = s.c_h; c_l = s.c_l; }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  if constexpr (SKIP) {
+    for (int i = tid; i < kR * kS; i += kThreads) split_tf32(skip_k[i], s.ws_h[i / kS][i % kS], s.ws_l[i / kS][i % kS]);
+    if (tid < kS) s.bs[tid] = skip_b[tid];
+  }
   for (int i = tid; i < 2 * kR * kR; i += kThreads) split_tf32(filt_k[i], s.wf_h[i / kR][i % kR], s.wf_l[i / kR][i % kR]);
   for (int i = tid; i < kR * kR; i += kThreads) split_tf32(res_k[i], s.wr_h[i / kR][i % kR], s.wr_l[i / kR][i % kR]);
   if (tid < kR) { s.bf[tid] = filt_b[tid]; s.br[tid] = res_b[tid]; }
@@ -121,6 +140,7 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
         mma_tf32(acc[nt], h0, h1, h2, h3, bh0, bh1);
       }
     }
+    if constexpr (SKIP) __syncthreads();               // every warp is done with the tap rows: c may take their place
     // gate: tanh, sigmoid OF THE TANH, product (ops.py:28,33,36)
 #pragma unroll
     for (int nt = 0; nt < 2; nt++) {
@@ -128,10 +148,10 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
       float cv[4], ch[4], cl[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) { const float f = tanhf(acc[nt][e]); cv[e] = f * sigmoidf_(f); split_tf32(cv[e], ch[e], cl[e]); }
-      *reinterpret_cast<float2*>(&s.c_h[r0 + g][n0]) = make_float2(ch[0], ch[1]);
-      *reinterpret_cast<float2*>(&s.c_h[r0 + g + 8][n0]) = make_float2(ch[2], ch[3]);
-      *reinterpret_cast<float2*>(&s.c_l[r0 + g][n0]) = make_float2(cl[0], cl[1]);
-      *reinterpret_cast<float2*>(&s.c_l[r0 + g + 8][n0]) = make_float2(cl[2], cl[3]);
+      *reinterpret_cast<float2*>(&c_h[r0 + g][n0]) = make_float2(ch[0], ch[1]);
+      *reinterpret_cast<float2*>(&c_h[r0 + g + 8][n0]) = make_float2(ch[2], ch[3]);
+      *reinterpret_cast<float2*>(&c_l[r0 + g][n0]) = make_float2(cl[0], cl[1]);
+      *reinterpret_cast<float2*>(&c_l[r0 + g + 8][n0]) = make_float2(cl[2], cl[3]);
     }
     __syncthreads();
     // residual 1x1 (ops.py:39), dense = (inputs + residual) * sqrt(1/2) (ops.py:40), next layer's conditioning (model.py:183)
@@ -143,8 +163,8 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       const int kc = ks * 8;
-      const float h0 = s.c_h[r0 + g][kc + q], h1 = s.c_h[r0 + g + 8][kc + q], h2 = s.c_h[r0 + g][kc + q + 4], h3 = s.c_h[r0 + g + 8][kc + q + 4];
-      const float l0 = s.c_l[r0 + g][kc + q], l1 = s.c_l[r0 + g + 8][kc + q], l2 = s.c_l[r0 + g][kc + q + 4], l3 = s.c_l[r0 + g + 8][kc + q + 4];
+      const float h0 = c_h[r0 + g][kc + q], h1 = c_h[r0 + g + 8][kc + q], h2 = c_h[r0 + g][kc + q + 4], h3 = c_h[r0 + g + 8][kc + q + 4];
+      const float l0 = c_l[r0 + g][kc + q], l1 = c_l[r0 + g + 8][kc + q], l2 = c_l[r0 + g][kc + q + 4], l3 = c_l[r0 + g + 8][kc + q + 4];
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) {
         const int n0 = nh * 16 + nt * 8 + g;
@@ -172,6 +192,46 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
         float2 v = make_float2((xv.x + acc[nt][2]) * SRWN_SQRT_HALF, (xv.y + acc[nt][3]) * SRWN_SQRT_HALF);
         if (cond_next) { const float2 cn = *reinterpret_cast<const float2*>(cond_next + ((size_t)b * frames + tb / P) * L * kR + n0); v.x += cn.x; v.y += cn.y; }
         *reinterpret_cast<float2*>(x_next + at) = v;
+      }
+    }
+    if constexpr (SKIP) {
+      // skip 1x1 (ops.py:44) accumulated over layers in global memory (model.py:190); warp (mt, nh): rows 16 mt.., channels 64 nh..
+      float sk[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        const int n0 = nh * 64 + nt * 8 + 2 * q;
+        sk[nt][0] = sk[nt][2] = s.bs[n0]; sk[nt][1] = sk[nt][3] = s.bs[n0 + 1];
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        const int kc = ks * 8;
+        const float h0 = c_h[r0 + g][kc + q], h1 = c_h[r0 + g + 8][kc + q], h2 = c_h[r0 + g][kc + q + 4], h3 = c_h[r0 + g + 8][kc + q + 4];
+        const float l0 = c_l[r0 + g][kc + q], l1 = c_l[r0 + g + 8][kc + q], l2 = c_l[r0 + g][kc + q + 4], l3 = c_l[r0 + g + 8][kc + q + 4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+          const int n0 = nh * 64 + nt * 8 + g;
+          const float bh0 = s.ws_h[kc + q][n0], bh1 = s.ws_h[kc + q + 4][n0];
+          const float bl0 = s.ws_l[kc + q][n0], bl1 = s.ws_l[kc + q + 4][n0];
+          mma_tf32(sk[nt], l0, l1, l2, l3, bh0, bh1);
+          mma_tf32(sk[nt], h0, h1, h2, h3, bl0, bl1);
+          mma_tf32(sk[nt], h0, h1, h2, h3, bh0, bh1);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        const int n0 = nh * 64 + nt * 8 + 2 * q;
+        if (ta < T) {
+          float2* dst = reinterpret_cast<float2*>(skip + ((size_t)b * T + ta) * kS + n0);
+          float2 v = make_float2(sk[nt][0], sk[nt][1]);
+          if (!skip_init) { const float2 pv = *dst; v.x += pv.x; v.y += pv.y; }
+          *dst = v;
+        }
+        if (tb < T) {
+          float2* dst = reinterpret_cast<float2*>(skip + ((size_t)b * T + tb) * kS + n0);
+          float2 v = make_float2(sk[nt][2], sk[nt][3]);
+          if (!skip_init) { const float2 pv = *dst; v.x += pv.x; v.y += pv.y; }
+          *dst = v;
+        }
       }
     }
   }
@@ -675,6 +735,24 @@ static TrainWs carve_train(const srwn_ctx* c, int B, int T, void* ws, size_t cap
 size_t train_workspace_bytes(const srwn_ctx* c, int B, int T) { return carve_train(c, B, T, nullptr, 0).bytes; }
 
 // forward of all flows in fp32, keeping every layer input (model.py:489-535)
+// one layer of the fp32-grade path (stack_f32.cu): x_l -> x_next, teacher layers also accumulate their skip output
+int run_layer_tf32x3(srwn_ctx* c, bool with_skip, const float* x_l, float* x_next, float* skip, const float* filt_k,
+                     const float* filt_b, const float* res_k, const float* res_b, const float* skip_k, const float* skip_b,
+                     const float* cond_next, int B, int T, int d, int P, int L, int frames, int skip_init, cudaStream_t st) {
+  const int grid = 2 * (c->sm_count > 0 ? c->sm_count : 148);
+  if (with_skip) {
+    SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmemSkip)));
+    train::k_fwd_layer<true><<<grid, train::kThreads, sizeof(train::FwdSmemSkip), st>>>(
+        x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, skip_k, skip_b, skip, skip_init);
+  } else {
+    SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmem)));
+    train::k_fwd_layer<false><<<grid, train::kThreads, sizeof(train::FwdSmem), st>>>(
+        x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, nullptr, nullptr, nullptr, 0);
+  }
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
 // forward of one flow keeping every layer input: acts [L+1][B][T][R], acts[l] = block input of layer l, acts[L] = stack output
 static int run_stack_train_acts(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T, float* acts,
                                 float* cond, int grid, cudaStream_t st) {
@@ -689,13 +767,13 @@ static int run_stack_train_acts(srwn_ctx* c, int stack, const float* xin, const 
     k_front<<<g, 256, 0, st>>>(xin, w + o.front_k, w + o.front_b, cond, acts, T, P, L, frames);
     SRWN_LAUNCH_CHECK();
   }
-  SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmem)));
+  SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmem)));
   for (int l = 0; l < L; l++) {
     const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
-    train::k_fwd_layer<<<grid, train::kThreads, sizeof(train::FwdSmem), st>>>(
+    train::k_fwd_layer<false><<<grid, train::kThreads, sizeof(train::FwdSmem), st>>>(
         acts + (size_t)l * n * kR, acts + (size_t)(l + 1) * n * kR, w + o.filt_k + (size_t)l * 2 * kR * kR,
         w + o.filt_b + (size_t)l * kR, w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR, cond_next,
-        B, T, c->dilations[l], P, L, frames);
+        B, T, c->dilations[l], P, L, frames, nullptr, nullptr, nullptr, 0);
     SRWN_LAUNCH_CHECK();
   }
   return SRWN_OK;
