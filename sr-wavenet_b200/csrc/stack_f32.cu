@@ -1,8 +1,9 @@
-// fp32 FFMA path of the residual stack (parity path, <= 1e-4 relative vs the oracle).
+// fp32-grade path of the residual stack (parity path, <= 1e-4 relative vs the oracle).
 //
-// One launch per layer; the residual stream round-trips through HBM as fp32.  This is the
-// reference-grade path and the GPU-side cross-check for the fused bf16 tcgen05 kernel
-// (fused_bf16.cu), which is the one the benchmark times.
+// One launch per layer; the residual stream (and the teacher's skip sum) round-trips through HBM as fp32.  The layer
+// GEMMs run on the tensor cores with split TF32 operands (train::k_fwd_layer, three MMAs per product), conditioning,
+// front conv and the output heads are FFMA kernels.  This is the reference-grade path and the GPU-side cross-check for
+// the fused 16-bit tcgen05 kernel (fused_bf16.cu), which is the one the benchmark times.
 //
 // Stored tensor convention: `hc_i` = the block input of layer i = h_i + upsampled
 // conditioning of layer i (model.py:183 adds it before ResidualDilationLayer, so it also
@@ -42,150 +43,7 @@ __global__ void k_front(const float* __restrict__ x, const float* __restrict__ f
   hc[((size_t)b * T + t) * kR + r] = v;
 }
 
-// One residual block (ops.py:23-46) on a tile of 64 time steps.
-constexpr int kTT = 64;       // time steps per CTA
-constexpr int kAP = kR + 4;   // padded row pitch (floats), keeps 16-byte alignment
-struct LayerSmem {
-  float a_tap[kTT][kAP];
-  float a_cur[kTT][kAP];
-  float c[kTT][kAP];
-  float wf[2 * kR][kR];
-  float wr[kR][kR];
-  float ws[kR][kS];
-  float bf[kR], br[kR], bs[kS];
-};
-
-template <bool SKIP>
-__global__ void __launch_bounds__(256)
-k_layer_f32(const float* __restrict__ hc_in, float* __restrict__ hc_out, float* __restrict__ skip,
-            const float* __restrict__ filt_k, const float* __restrict__ filt_b,
-            const float* __restrict__ res_k, const float* __restrict__ res_b,
-            const float* __restrict__ skip_k, const float* __restrict__ skip_b,
-            const float* __restrict__ cond_next,   // cond + (layer+1)*R, or nullptr for the last layer
-            int T, int d, int P, int L, int frames, int skip_init) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  LayerSmem& s = *reinterpret_cast<LayerSmem*>(smem_raw);
-  const int b = blockIdx.y, t0 = blockIdx.x * kTT;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* hb = hc_in + (size_t)b * T * kR;
-
-  // stage operands: current rows, rows d steps back (zero before the utterance start), weights
-  for (int i = tid; i < kTT * (kR / 4); i += 256) {
-    const int row = i / (kR / 4), q = i % (kR / 4);
-    const int t = t0 + row;
-    float4 cur = make_float4(0, 0, 0, 0), tap = cur;
-    if (t < T) {
-      cur = *reinterpret_cast<const float4*>(hb + (size_t)t * kR + q * 4);
-      if (t - d >= 0) tap = *reinterpret_cast<const float4*>(hb + (size_t)(t - d) * kR + q * 4);
-    }
-    *reinterpret_cast<float4*>(&s.a_cur[row][q * 4]) = cur;
-    *reinterpret_cast<float4*>(&s.a_tap[row][q * 4]) = tap;
-  }
-  for (int i = tid; i < 2 * kR * kR; i += 256) (&s.wf[0][0])[i] = filt_k[i];
-  for (int i = tid; i < kR * kR; i += 256) (&s.wr[0][0])[i] = res_k[i];
-  if (SKIP) for (int i = tid; i < kR * kS; i += 256) (&s.ws[0][0])[i] = skip_k[i];
-  if (tid < kR) { s.bf[tid] = filt_b[tid]; s.br[tid] = res_b[tid]; }
-  if (SKIP && tid < kS) s.bs[tid] = skip_b[tid];
-  __syncthreads();
-
-  const int r0 = warp * 8;     // this warp owns rows r0..r0+7; lane = output channel
-  float acc[8];
-#pragma unroll
-  for (int r = 0; r < 8; r++) acc[r] = s.bf[lane];
-  // filter conv: W[0] pairs with x[t-d], W[1] with x[t] (ops.py:6-10)
-#pragma unroll 4
-  for (int k4 = 0; k4 < kR / 4; k4++) {
-    const float w0 = s.wf[k4 * 4 + 0][lane], w1 = s.wf[k4 * 4 + 1][lane],
-                w2 = s.wf[k4 * 4 + 2][lane], w3 = s.wf[k4 * 4 + 3][lane];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const float4 a = *reinterpret_cast<const float4*>(&s.a_tap[r0 + r][k4 * 4]);
-      acc[r] = fmaf(a.x, w0, acc[r]); acc[r] = fmaf(a.y, w1, acc[r]);
-      acc[r] = fmaf(a.z, w2, acc[r]); acc[r] = fmaf(a.w, w3, acc[r]);
-    }
-  }
-#pragma unroll 4
-  for (int k4 = 0; k4 < kR / 4; k4++) {
-    const float w0 = s.wf[kR + k4 * 4 + 0][lane], w1 = s.wf[kR + k4 * 4 + 1][lane],
-                w2 = s.wf[kR + k4 * 4 + 2][lane], w3 = s.wf[kR + k4 * 4 + 3][lane];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const float4 a = *reinterpret_cast<const float4*>(&s.a_cur[r0 + r][k4 * 4]);
-      acc[r] = fmaf(a.x, w0, acc[r]); acc[r] = fmaf(a.y, w1, acc[r]);
-      acc[r] = fmaf(a.z, w2, acc[r]); acc[r] = fmaf(a.w, w3, acc[r]);
-    }
-  }
-  // gate: tanh, then sigmoid OF THE TANH (ops.py:28,33), product (ops.py:36)
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    const float f = tanhf(acc[r]);
-    const float g = 1.0f / (1.0f + expf(-f));
-    s.c[r0 + r][lane] = f * g;
-  }
-  __syncwarp();
-
-  // residual 1x1 (ops.py:39) and dense = (inputs + residual) * sqrt(1/2) (ops.py:40)
-#pragma unroll
-  for (int r = 0; r < 8; r++) acc[r] = s.br[lane];
-#pragma unroll 4
-  for (int k4 = 0; k4 < kR / 4; k4++) {
-    const float w0 = s.wr[k4 * 4 + 0][lane], w1 = s.wr[k4 * 4 + 1][lane],
-                w2 = s.wr[k4 * 4 + 2][lane], w3 = s.wr[k4 * 4 + 3][lane];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const float4 a = *reinterpret_cast<const float4*>(&s.c[r0 + r][k4 * 4]);
-      acc[r] = fmaf(a.x, w0, acc[r]); acc[r] = fmaf(a.y, w1, acc[r]);
-      acc[r] = fmaf(a.z, w2, acc[r]); acc[r] = fmaf(a.w, w3, acc[r]);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    const int t = t0 + r0 + r;
-    if (t < T) {
-      float v = (s.a_cur[r0 + r][lane] + acc[r]) * SRWN_SQRT_HALF;
-      if (cond_next) v += cond_next[((size_t)b * frames + t / P) * L * kR + lane];
-      hc_out[((size_t)b * T + t) * kR + lane] = v;
-    }
-  }
-
-  if (SKIP) {   // skip 1x1 (ops.py:44), accumulated over layers (model.py:190)
-    float sk[8][4];
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) sk[r][j] = s.bs[lane + 32 * j];
-#pragma unroll 2
-    for (int k4 = 0; k4 < kR / 4; k4++) {
-      float w[4][4];
-#pragma unroll
-      for (int kk = 0; kk < 4; kk++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) w[kk][j] = s.ws[k4 * 4 + kk][lane + 32 * j];
-#pragma unroll
-      for (int r = 0; r < 8; r++) {
-        const float4 a = *reinterpret_cast<const float4*>(&s.c[r0 + r][k4 * 4]);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          sk[r][j] = fmaf(a.x, w[0][j], sk[r][j]); sk[r][j] = fmaf(a.y, w[1][j], sk[r][j]);
-          sk[r][j] = fmaf(a.z, w[2][j], sk[r][j]); sk[r][j] = fmaf(a.w, w[3][j], sk[r][j]);
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int t = t0 + r0 + r;
-      if (t < T) {
-        float* dst = skip + ((size_t)b * T + t) * kS + lane;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float prev = skip_init ? 0.f : dst[32 * j];
-          dst[32 * j] = prev + sk[r][j];
-        }
-      }
-    }
-  }
-}
-
+// The residual blocks (ops.py:23-46) run in train::k_fwd_layer (train_f32.cu): 64-step tiles, 3xTF32 tensor-core GEMMs.
 int run_layer_tf32x3(srwn_ctx* c, bool with_skip, const float* x_l, float* x_next, float* skip, const float* filt_k,
                      const float* filt_b, const float* res_k, const float* res_b, const float* skip_k, const float* skip_b,
                      const float* cond_next, int B, int T, int d, int P, int L, int frames, int skip_init, cudaStream_t st);
@@ -218,35 +76,6 @@ int run_stack_f32(srwn_ctx* c, int stack, const float* xin, const float* enc, in
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
   *h_final = cur;
-  return SRWN_OK;
-}
-
-// Same stack (student: no skip conv), keeping every layer input for the backward pass (train_f32.cu):
-// acts [L+1][B][T][R], acts[l] = block input of layer l, acts[L] = stack output.
-int run_stack_f32_acts(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T,
-                       float* acts, float* cond, cudaStream_t st) {
-  const float* w = stack_w(c, stack);
-  const StackOffsets& o = c->off;
-  const int L = c->cfg.n_layers, P = c->cfg.pool_stride, C = c->cfg.cond_channels;
-  const int frames = T / P;
-  const size_t n = (size_t)B * T;
-  k_cond<<<B * frames, 256, 0, st>>>(enc, w + o.cond_k, w + o.cond_b, cond, B * frames, L, C);
-  SRWN_LAUNCH_CHECK();
-  {
-    dim3 grid((unsigned)(((int64_t)T * kR + 255) / 256), B);
-    k_front<<<grid, 256, 0, st>>>(xin, w + o.front_k, w + o.front_b, cond, acts, T, P, L, frames);
-    SRWN_LAUNCH_CHECK();
-  }
-  SRWN_CUDA(cudaFuncSetAttribute(k_layer_f32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LayerSmem)));
-  dim3 grid((T + kTT - 1) / kTT, B);
-  for (int l = 0; l < L; l++) {
-    const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
-    k_layer_f32<false><<<grid, 256, sizeof(LayerSmem), st>>>(
-        acts + (size_t)l * n * kR, acts + (size_t)(l + 1) * n * kR, nullptr, w + o.filt_k + (size_t)l * 2 * kR * kR,
-        w + o.filt_b + (size_t)l * kR, w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR, nullptr, nullptr,
-        cond_next, T, c->dilations[l], P, L, frames, 0);
-    SRWN_LAUNCH_CHECK();
-  }
   return SRWN_OK;
 }
 

@@ -18,8 +18,6 @@ __global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ 
 __global__ void k_front(const float* __restrict__ x, const float* __restrict__ fk,
                         const float* __restrict__ fb, const float* __restrict__ cond,
                         float* __restrict__ hc, int T, int P, int L, int frames);
-int run_stack_f32_acts(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T,
-                       float* acts, float* cond, cudaStream_t st);
 
 namespace train {
 
