@@ -74,3 +74,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/srwn.h must compile as C99 (no C++ or torch types), and a C program that
+    links only against libsrwn.so resolves every declared entry point."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    calls = "\n".join("  p[%d] = (fn_t)%s;" % (i, n) for i, n in enumerate(_declared_symbols()))
+    src.write_text('#include "srwn.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t p[%d];\n%s\n'
+                   '  printf("%%d %%d\\n", srwn_abi_version(), (int)(sizeof(p) / sizeof(p[0])));\n  return p[0] == 0;\n}\n'
+                   % (len(_declared_symbols()), calls))
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-l:libsrwn.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == _lib.ABI_VERSION and int(out[1]) == len(_declared_symbols())
