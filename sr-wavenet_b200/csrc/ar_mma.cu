@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
     const bool samp = j == 0 && lane < kU && ub < p.B;
     bool ok = true;
     long long tm_a = 0, tm_b = 0, tm_c = 0, tm_d = 0;
-    long long tl_conv = 0, tl_gate = 0, tl_sync = 0, tl_res = 0, tl_top = 0;
+    [[maybe_unused]] long long tl_conv = 0, tl_gate = 0, tl_sync = 0, tl_res = 0, tl_top = 0;
 
     // Queue pops (L2) run three layers ahead of their use, in three register sets that the layer loop (unrolled by
     // three) addresses by name: nothing is rotated through register moves, and a set is reloaded right after its

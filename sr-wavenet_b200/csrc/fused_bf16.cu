@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         for (int l = 0; l < Lc; l++) {
           const int s = l & 1;
           const int use = U0(s) + (l >> 1);                  // how many times stage s was used before
-          const bool tracing = tracing_chunk && lane == 0;
+          [[maybe_unused]] const bool tracing = tracing_chunk && lane == 0;
           TRACE(6, l, 0);
           // halo rows of layer l: inputs at t0-d .. t0-1 (zeros before the segment start).  The halo goes first:
           // its condition (filter-conv MMAs of layer l-2 retired) holds earlier than the weight stage's.
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         float v[32];
         uint32_t w16[16];
         bool alive = true;
-        const bool tracing = tracing_chunk && row == 0;
+        [[maybe_unused]] const bool tracing = tracing_chunk && row == 0;
         constexpr uint32_t fmt = FP16 ? 0u : 1u;
         constexpr uint32_t id32 = make_idesc(fmt, 128, 32), id128 = make_idesc(fmt, 128, 128), id160 = make_idesc(fmt, 128, 160); (void)id160;
         // descriptor low words that do not depend on the layer
