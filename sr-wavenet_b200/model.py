@@ -197,15 +197,25 @@ def _with_conditions(encoding, conditions, condition_size):
 
 
 class _CheckpointMixin(object):
-    """npz stand-in for tf.train.Saver (model.py:217-239): ``<logdir>/model.ckpt-<step>.npz`` plus a
-    ``checkpoint`` state file; ``save`` is throttled to once per 60 s unless ``force``."""
+    """Stand-in for tf.train.Saver (model.py:217-239).  ``save`` writes ``<logdir>/model.ckpt-<step>.npz`` (name-keyed,
+    TF variable names) plus the ``checkpoint`` state file, throttled to once per 60 s unless ``force``; with
+    ``checkpoint_format = "tf"`` it writes a TensorFlow tensor bundle (``.index`` + ``.data-00000-of-00001``) instead.
+    ``load`` restores whichever of the two the state file points to, so a checkpoint directory written by the
+    reference's Saver loads as it is (``tf_checkpoint.py``; optimizer slots and other variables the graph does not have
+    are ignored)."""
+
+    checkpoint_format = "npz"
 
     def _save(self, logdir, global_step, force):
         if force or time.time() - self.last_checkpoint_time > 60:
             if not os.path.isdir(logdir):
                 os.makedirs(logdir)
             path = os.path.join(logdir, 'model.ckpt-%d' % global_step)
-            np.savez(path + '.npz', **self.get_weights())
+            if self.checkpoint_format == "tf":
+                from . import tf_checkpoint
+                tf_checkpoint.write_checkpoint(path, self.get_weights())
+            else:
+                np.savez(path + '.npz', **self.get_weights())
             with open(os.path.join(logdir, 'checkpoint'), 'w') as f:
                 f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
             self.last_checkpoint_time = time.time()
@@ -218,12 +228,22 @@ class _CheckpointMixin(object):
             if os.path.exists(state):
                 with open(state) as f:
                     name = f.readline().split('"')[1]
-                path = os.path.join(logdir, name + '.npz')
-                if not os.path.exists(path):
+                path = name if os.path.isabs(name) else os.path.join(logdir, name)
+                if os.path.exists(path + '.npz'):
+                    with np.load(path + '.npz') as z:
+                        self.set_weights({k: z[k] for k in z.files})
+                elif os.path.exists(path + '.index'):
+                    from . import tf_checkpoint
+                    known = self.get_weights()
+                    found = {k: v for k, v in tf_checkpoint.read_checkpoint(path).items()
+                             if k in known and tuple(v.shape) == tuple(known[k].shape)}
+                    if not found:
+                        print('No variable of this graph in %s' % path)
+                        return False
+                    self.set_weights(found)
+                else:
                     print('Could not find checkpoint at %s' % path)
                     return False
-                with np.load(path) as z:
-                    self.set_weights({k: z[k] for k in z.files})
                 print('Restoring previous session')
                 return True
         return None

@@ -10,6 +10,8 @@ operands are the default 16-bit path: measured max |dlogits| ~3e-3, asserted <= 
 and the weights to 8 mantissa bits alone gives 2.45e-2 max-abs on 2 x 4096 samples in a NumPy
 emulation of exact arithmetic with bf16-rounded operands (tools/bf16_emulation.py), and the kernel
 reproduces that number; bf16 is therefore asserted at 4e-2 (documented in DESIGN.md)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -283,6 +285,35 @@ def test_checkpoint_roundtrip(srwn, tmp_path):
     np.testing.assert_array_equal(t2.get_logits(x, enc), a)
     k = synth.TEACHER_PREFIX + "conv1d_1/kernel"
     np.testing.assert_array_equal(t2._eng.get_weight(k, (1, 32, 32)), w[k])
+
+
+def test_tf_bundle_checkpoint_roundtrip(srwn, tmp_path):
+    """A checkpoint directory in TensorFlow's tensor-bundle format (what the reference's Saver writes, model.py:230-239)
+    restores into the model; optimizer slots and other variables the graph does not have are ignored."""
+    from sr_wavenet_b200 import tf_checkpoint as tfc
+    dil = [1, 2, 4]
+    t, w = _teacher(srwn, dil)
+    t.checkpoint_format = "tf"
+    assert t.save(str(tmp_path / "a"), 3, force=True) is True
+    assert os.path.exists(str(tmp_path / "a" / "model.ckpt-3.index"))
+    x, enc = synth.synthetic_audio(1, 256), synth.synthetic_encoding(1, 2)
+    a = t.get_logits(x, enc)
+    t2 = srwn.WaveNetAutoEncoder(256, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=128)
+    assert t2.load(str(tmp_path / "a")) is True
+    np.testing.assert_array_equal(t2.get_logits(x, enc), a)
+    # a Saver checkpoint also carries Adam slots, beta powers and the step counter
+    full = dict(t.get_weights())
+    k = synth.TEACHER_PREFIX + "conv1d_1/kernel"
+    full[k + "/Adam"] = np.zeros_like(full[k])
+    full[k + "/Adam_1"] = np.ones_like(full[k])
+    full["beta1_power"] = np.array(0.9, dtype=np.float32)
+    full["global_step"] = np.array(3, dtype=np.int64)
+    os.makedirs(str(tmp_path / "b"))
+    tfc.write_checkpoint(str(tmp_path / "b" / "model.ckpt-9"), full)
+    open(str(tmp_path / "b" / "checkpoint"), "w").write('model_checkpoint_path: "model.ckpt-9"\n')
+    t3 = srwn.WaveNetAutoEncoder(256, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=128)
+    assert t3.load(str(tmp_path / "b")) is True
+    np.testing.assert_array_equal(t3.get_logits(x, enc), a)
 
 
 def test_device_resident_path(srwn):
