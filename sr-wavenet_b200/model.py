@@ -341,14 +341,21 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         if not os.path.exists(state):
             raise IOError("no teacher checkpoint under %s (expected the files WaveNetAutoEncoder.save writes)" % logdir)
         with open(state) as f:
-            path = os.path.join(logdir, f.readline().split('"')[1] + '.npz')
+            name = f.readline().split('"')[1]
+        path = name if os.path.isabs(name) else os.path.join(logdir, name)
         L = len(dilations)
-        with np.load(path) as z:
-            head2 = z['%sconv1d_%d/kernel' % (synth.TEACHER_PREFIX, 3 * L + 1)]
-            enc0 = z['%snc_conv_NC/conv1d/kernel' % synth.ENCODER_PREFIX]
-        t = cls(input_size=input_size, condition_size=condition_size, num_mixtures=head2.shape[2] // 4, dilations=dilations,
-                filter_width=filter_width, encoder_channels=enc0.shape[2], dilation_channels=dilation_channels,
-                skip_channels=head2.shape[1], latent_channels=latent_channels, pool_stride=pool_stride)
+        k_head2 = '%sconv1d_%d/kernel' % (synth.TEACHER_PREFIX, 3 * L + 1)
+        k_enc0 = '%snc_conv_NC/conv1d/kernel' % synth.ENCODER_PREFIX
+        if os.path.exists(path + '.npz'):
+            with np.load(path + '.npz') as z:
+                head2, enc0 = z[k_head2].shape, z[k_enc0].shape
+        else:                                              # a tf.train.Saver checkpoint (tensor bundle)
+            from . import tf_checkpoint
+            shapes = {n: sh for n, sh, _ in tf_checkpoint.list_variables(path)}
+            head2, enc0 = shapes[k_head2], shapes[k_enc0]
+        t = cls(input_size=input_size, condition_size=condition_size, num_mixtures=head2[2] // 4, dilations=dilations,
+                filter_width=filter_width, encoder_channels=enc0[2], dilation_channels=dilation_channels,
+                skip_channels=head2[1], latent_channels=latent_channels, pool_stride=pool_stride)
         if not t.load(logdir):
             raise IOError("could not restore the teacher from %s" % logdir)
         return t

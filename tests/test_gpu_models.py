@@ -314,6 +314,10 @@ def test_tf_bundle_checkpoint_roundtrip(srwn, tmp_path):
     t3 = srwn.WaveNetAutoEncoder(256, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=128)
     assert t3.load(str(tmp_path / "b")) is True
     np.testing.assert_array_equal(t3.get_logits(x, enc), a)
+    # ParallelWaveNet(teacher=<directory>) (model.py:323-334) takes such a directory as it is
+    s = srwn.ParallelWaveNet(256, 0, dil, str(tmp_path / "b"), num_flows=2, skip_channels=128, latent_channels=32, pool_stride=128)
+    assert s.teacher.num_mixtures == 5 and s.teacher.skip_channels == 128
+    np.testing.assert_array_equal(s.teacher.get_logits(x, enc), a)
 
 
 def test_device_resident_path(srwn):
