@@ -487,9 +487,12 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
 // 32 columns per CTA, the rows split over the 8 warps (independent loads in flight), then a fixed-order sum of the 8 parts
 __global__ void __launch_bounds__(256)
 k_reduce_partials(const float* __restrict__ partial, int rows, int pitch, int w1, float* __restrict__ dst1, int w2,
-                  float* __restrict__ dst2) {
+                  float* __restrict__ dst2, size_t layer_stride = 0, int dst1_stride = 0, int dst2_stride = 0) {
   __shared__ float red[8][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5, j = blockIdx.x * 32 + x, w = w1 + w2;
+  partial += blockIdx.y * layer_stride;              // blockIdx.y = layer: every layer's partial rows are reduced by one launch
+  dst1 += (size_t)blockIdx.y * dst1_stride;
+  dst2 += (size_t)blockIdx.y * dst2_stride;
   float acc = 0.f;
   if (j < w) {
 #pragma unroll 8
@@ -703,7 +706,7 @@ __global__ void __launch_bounds__(1024) k_sumsq(const float* __restrict__ g, int
 
 // ---- host ----------------------------------------------------------------------------------------------
 struct TrainWs {
-  float *acts, *cond, *scales, *means, *xs, *g0, *g1, *da, *dcond, *d_scales, *d_means, *dxa, *dxb, *partial;
+  float *acts, *cond, *scales, *means, *xs, *g0, *g1, *da, *dcond, *d_scales, *d_means, *dxa, *dxb, *partial, *partial_gate, *partial_conv;
   size_t bytes; int grid;
 };
 
@@ -726,6 +729,8 @@ static TrainWs carve_train(const srwn_ctx* c, int B, int T, void* ws, size_t cap
   r.dxa = w.take<float>(n);
   r.dxb = w.take<float>(n);
   r.partial = w.take<float>((size_t)r.grid * (2 * kR * kR + kR));
+  r.partial_gate = w.take<float>(L * (size_t)r.grid * (kR * kR + kR));           // [L][grid][dWr | dbr]
+  r.partial_conv = w.take<float>(L * (size_t)r.grid * (2 * kR * kR + kR));       // [L][grid][dWf | dbf]
   r.bytes = w.used;
   return r;
 }
@@ -837,22 +842,26 @@ int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const fl
     for (int l = L - 1; l >= 0; l--) {
       const float* x_l = acts + (size_t)l * n * kR;
       const int d = c->dilations[l];
+      // per-CTA weight-gradient partials of every layer are kept ([L][grid][...]) and reduced by ONE launch per flow
+      float* pg = w.partial_gate + (size_t)l * grid * (kR * kR + kR);
+      float* pc = w.partial_conv + (size_t)l * grid * (2 * kR * kR + kR);
       k_bwd_gate<<<grid, kThreads, sizeof(GateSmem), st>>>(x_l, g, w.da, sw + o.filt_k + (size_t)l * 2 * kR * kR,
                                                            sw + o.filt_b + (size_t)l * kR, sw + o.res_k + (size_t)l * kR * kR,
-                                                           w.partial, B, T, d);
-      SRWN_LAUNCH_CHECK();
-      k_reduce_partials<<<reduce_grid(kR * kR + kR), 256, 0, st>>>(w.partial, grid, kR * kR + kR, kR * kR, gs + o.res_k + (size_t)l * kR * kR,
-                                                                  kR, gs + o.res_b + (size_t)l * kR);
+                                                           pg, B, T, d);
       SRWN_LAUNCH_CHECK();
       // x_l carries cond_l (added before the block, model.py:183; for l = 0 by the front): dcond_l = sum over the frame of dx_l
-      k_bwd_conv<<<grid, kThreads, sizeof(ConvSmem), st>>>(x_l, g, w.da, gn, sw + o.filt_k + (size_t)l * 2 * kR * kR, w.partial,
+      k_bwd_conv<<<grid, kThreads, sizeof(ConvSmem), st>>>(x_l, g, w.da, gn, sw + o.filt_k + (size_t)l * 2 * kR * kR, pc,
                                                            w.dcond + (size_t)l * BF * kR, B, T, d, P, frames);
-      SRWN_LAUNCH_CHECK();
-      k_reduce_partials<<<reduce_grid(2 * kR * kR + kR), 256, 0, st>>>(w.partial, grid, 2 * kR * kR + kR, 2 * kR * kR,
-                                                                      gs + o.filt_k + (size_t)l * 2 * kR * kR, kR, gs + o.filt_b + (size_t)l * kR);
       SRWN_LAUNCH_CHECK();
       float* tmp = g; g = gn; gn = tmp;
     }
+    k_reduce_partials<<<dim3(reduce_grid(kR * kR + kR), L), 256, 0, st>>>(w.partial_gate, grid, kR * kR + kR, kR * kR, gs + o.res_k, kR,
+                                                                         gs + o.res_b, (size_t)grid * (kR * kR + kR), kR * kR, kR);
+    SRWN_LAUNCH_CHECK();
+    k_reduce_partials<<<dim3(reduce_grid(2 * kR * kR + kR), L), 256, 0, st>>>(w.partial_conv, grid, 2 * kR * kR + kR, 2 * kR * kR,
+                                                                             gs + o.filt_k, kR, gs + o.filt_b,
+                                                                             (size_t)grid * (2 * kR * kR + kR), 2 * kR * kR, kR);
+    SRWN_LAUNCH_CHECK();
     // g = dLoss/dx_0 (front output incl. cond_0)
     k_bwd_front<<<grid, 256, 0, st>>>(x_prev, g, sw + o.front_k, f > 0 ? dx_cur : nullptr, w.partial, B, T);
     SRWN_LAUNCH_CHECK();
