@@ -26,6 +26,9 @@ constexpr int kAP = kR + 4;         // padded pitch
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Programmatic dependent launch: the layer kernels are launched so that a kernel's CTAs may start (and stage their weights) while
+// the previous layer's kernel drains; everything the previous launch wrote is visible after this wait (no-op in a plain launch).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
@@ -98,6 +101,7 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
   const int tiles_per_b = (T + kTT - 1) / kTT;
   const int n_tiles = B * tiles_per_b;
   const int mt = warp & 3, nh = warp >> 2, r0 = mt * 16;
+  grid_dependency_wait();                            // weights are staged; the activations come from the previous launch
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
     const float* xb = x_l + (size_t)b * T * kR;
@@ -261,6 +265,7 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
   const int mi = warp & 1, ni = warp >> 1;
   float gw[4] = {0.f, 0.f, 0.f, 0.f};      // dWr block: rows (k) 16 mi + g (+8), columns (n) 8 ni + 2q (+1)
   float gb = 0.f;                          // dbr[lane] (warp 0)
+  grid_dependency_wait();
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
     const float* xb = x_l + (size_t)b * T * kR;
@@ -386,6 +391,7 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
   const int mi = warp & 3, nj = warp >> 2;
   float gw[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // dWf block: rows 16 mi + g (+8), columns 16 nj + 8 nt + 2q (+1)
   float gb = 0.f;
+  grid_dependency_wait();
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
     const float* xb = x_l + (size_t)b * T * kR;
@@ -738,6 +744,17 @@ static TrainWs carve_train(const srwn_ctx* c, int B, int T, void* ws, size_t cap
 size_t train_workspace_bytes(const srwn_ctx* c, int B, int T) { return carve_train(c, B, T, nullptr, 0).bytes; }
 
 // forward of all flows in fp32, keeping every layer input (model.py:489-535)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // one layer of the fp32-grade path (stack_f32.cu): x_l -> x_next, teacher layers also accumulate their skip output
 int run_layer_tf32x3(srwn_ctx* c, bool with_skip, const float* x_l, float* x_next, float* skip, const float* filt_k,
                      const float* filt_b, const float* res_k, const float* res_b, const float* skip_k, const float* skip_b,
@@ -745,12 +762,12 @@ int run_layer_tf32x3(srwn_ctx* c, bool with_skip, const float* x_l, float* x_nex
   const int grid = 2 * (c->sm_count > 0 ? c->sm_count : 148);
   if (with_skip) {
     SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmemSkip)));
-    train::k_fwd_layer<true><<<grid, train::kThreads, sizeof(train::FwdSmemSkip), st>>>(
-        x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, skip_k, skip_b, skip, skip_init);
+    SRWN_CUDA(launch_dependent(train::k_fwd_layer<true>, grid, train::kThreads, sizeof(train::FwdSmemSkip), st,
+        x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, skip_k, skip_b, skip, skip_init));
   } else {
     SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmem)));
-    train::k_fwd_layer<false><<<grid, train::kThreads, sizeof(train::FwdSmem), st>>>(
-        x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, nullptr, nullptr, nullptr, 0);
+    SRWN_CUDA(launch_dependent(train::k_fwd_layer<false>, grid, train::kThreads, sizeof(train::FwdSmem), st,
+        x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, nullptr, nullptr, nullptr, 0));
   }
   SRWN_LAUNCH_CHECK();
   return SRWN_OK;
@@ -773,10 +790,10 @@ static int run_stack_train_acts(srwn_ctx* c, int stack, const float* xin, const 
   SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmem)));
   for (int l = 0; l < L; l++) {
     const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
-    train::k_fwd_layer<false><<<grid, train::kThreads, sizeof(train::FwdSmem), st>>>(
+    SRWN_CUDA(launch_dependent(train::k_fwd_layer<false>, grid, train::kThreads, sizeof(train::FwdSmem), st,
         acts + (size_t)l * n * kR, acts + (size_t)(l + 1) * n * kR, w + o.filt_k + (size_t)l * 2 * kR * kR,
         w + o.filt_b + (size_t)l * kR, w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR, cond_next,
-        B, T, c->dilations[l], P, L, frames, nullptr, nullptr, nullptr, 0);
+        B, T, c->dilations[l], P, L, frames, nullptr, nullptr, nullptr, 0));
     SRWN_LAUNCH_CHECK();
   }
   return SRWN_OK;
@@ -845,13 +862,13 @@ int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const fl
       // per-CTA weight-gradient partials of every layer are kept ([L][grid][...]) and reduced by ONE launch per flow
       float* pg = w.partial_gate + (size_t)l * grid * (kR * kR + kR);
       float* pc = w.partial_conv + (size_t)l * grid * (2 * kR * kR + kR);
-      k_bwd_gate<<<grid, kThreads, sizeof(GateSmem), st>>>(x_l, g, w.da, sw + o.filt_k + (size_t)l * 2 * kR * kR,
-                                                           sw + o.filt_b + (size_t)l * kR, sw + o.res_k + (size_t)l * kR * kR,
-                                                           pg, B, T, d);
+      SRWN_CUDA(launch_dependent(k_bwd_gate, grid, kThreads, sizeof(GateSmem), st, x_l, (const float*)g, w.da,
+                                 sw + o.filt_k + (size_t)l * 2 * kR * kR, sw + o.filt_b + (size_t)l * kR,
+                                 sw + o.res_k + (size_t)l * kR * kR, pg, B, T, d));
       SRWN_LAUNCH_CHECK();
       // x_l carries cond_l (added before the block, model.py:183; for l = 0 by the front): dcond_l = sum over the frame of dx_l
-      k_bwd_conv<<<grid, kThreads, sizeof(ConvSmem), st>>>(x_l, g, w.da, gn, sw + o.filt_k + (size_t)l * 2 * kR * kR, pc,
-                                                           w.dcond + (size_t)l * BF * kR, B, T, d, P, frames);
+      SRWN_CUDA(launch_dependent(k_bwd_conv, grid, kThreads, sizeof(ConvSmem), st, x_l, (const float*)g, (const float*)w.da, gn,
+                                 sw + o.filt_k + (size_t)l * 2 * kR * kR, pc, w.dcond + (size_t)l * BF * kR, B, T, d, P, frames));
       SRWN_LAUNCH_CHECK();
       float* tmp = g; g = gn; gn = tmp;
     }
