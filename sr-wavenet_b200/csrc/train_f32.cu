@@ -28,7 +28,12 @@ constexpr int kThreads = 256;
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 // Programmatic dependent launch: the layer kernels are launched so that a kernel's CTAs may start (and stage their weights) while
 // the previous layer's kernel drains; everything the previous launch wrote is visible after this wait (no-op in a plain launch).
-__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// The trigger right after it lets the NEXT launch's CTAs take the SM slots this grid frees as its CTAs exit (all of this grid's
+// CTAs are resident from the start, so nothing of it can be starved).
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
