@@ -55,6 +55,15 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], float a0, float a1, floa
                  "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 constexpr int kWP = kR + 8;         // pitch of B operands read as (k = q, n = g): banks 8q + g
+// A fragment (16 rows x 8 tf32) with one ldmatrix: a 8x8 b16 matrix is 8 rows of 16 bytes = 8 rows x 4 tf32 words, and thread
+// (g, q) receives row g, word q -- the m16n8k8 A layout.  Lane l passes the row address of matrix l >> 3:
+// {rows 0-7 | rows 8-15} x {words 0-3 | words 4-7} -> a0, a1, a2, a3.  Rows are 144 bytes apart: conflict-free.
+__device__ __forceinline__ void ldsm_a(float (&a)[4], const float* lane_row_ptr) {
+  uint32_t r0, r1, r2, r3;
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(lane_row_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+  a[0] = __uint_as_float(r0); a[1] = __uint_as_float(r1); a[2] = __uint_as_float(r2); a[3] = __uint_as_float(r3);
+}
 
 // ---- forward layer of the training pass ---------------------------------------------------------------
 // x_{l+1} = (x_l + c Wr + br) sqrt(1/2) + cond_{l+1},  c = f sigmoid(f),  f = tanh([x_l[t-d] | x_l[t]] Wf + bf)   (ops.py:23-46)
@@ -106,6 +115,7 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
   const int tiles_per_b = (T + kTT - 1) / kTT;
   const int n_tiles = B * tiles_per_b;
   const int mt = warp & 3, nh = warp >> 2, r0 = mt * 16;
+  const int lrow = r0 + (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 4;      // this lane's row address inside an ldmatrix A tile
   grid_dependency_wait();                            // weights are staged; the activations come from the previous launch
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
@@ -135,16 +145,17 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
       const float (*XH)[kAP] = ks < 4 ? s.tap_h : s.cur_h;
       const float (*XL)[kAP] = ks < 4 ? s.tap_l : s.cur_l;
       const int kc = (ks & 3) * 8;
-      const float h0 = XH[r0 + g][kc + q], h1 = XH[r0 + g + 8][kc + q], h2 = XH[r0 + g][kc + q + 4], h3 = XH[r0 + g + 8][kc + q + 4];
-      const float l0 = XL[r0 + g][kc + q], l1 = XL[r0 + g + 8][kc + q], l2 = XL[r0 + g][kc + q + 4], l3 = XL[r0 + g + 8][kc + q + 4];
+      float ah[4], al[4];
+      ldsm_a(ah, &XH[lrow][kc + lcol]);
+      ldsm_a(al, &XL[lrow][kc + lcol]);
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) {
         const int n0 = nh * 16 + nt * 8 + g;
         const float bh0 = s.wf_h[ks * 8 + q][n0], bh1 = s.wf_h[ks * 8 + q + 4][n0];
         const float bl0 = s.wf_l[ks * 8 + q][n0], bl1 = s.wf_l[ks * 8 + q + 4][n0];
-        mma_tf32(acc[nt], l0, l1, l2, l3, bh0, bh1);
-        mma_tf32(acc[nt], h0, h1, h2, h3, bl0, bl1);
-        mma_tf32(acc[nt], h0, h1, h2, h3, bh0, bh1);
+        mma_tf32(acc[nt], al[0], al[1], al[2], al[3], bh0, bh1);
+        mma_tf32(acc[nt], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+        mma_tf32(acc[nt], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
       }
     }
     if constexpr (SKIP) __syncthreads();               // every warp is done with the tap rows: c may take their place
@@ -170,8 +181,10 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       const int kc = ks * 8;
-      const float h0 = c_h[r0 + g][kc + q], h1 = c_h[r0 + g + 8][kc + q], h2 = c_h[r0 + g][kc + q + 4], h3 = c_h[r0 + g + 8][kc + q + 4];
-      const float l0 = c_l[r0 + g][kc + q], l1 = c_l[r0 + g + 8][kc + q], l2 = c_l[r0 + g][kc + q + 4], l3 = c_l[r0 + g + 8][kc + q + 4];
+      float ah[4], al[4];
+      ldsm_a(ah, &c_h[lrow][kc + lcol]);
+      ldsm_a(al, &c_l[lrow][kc + lcol]);
+      const float h0 = ah[0], h1 = ah[1], h2 = ah[2], h3 = ah[3], l0 = al[0], l1 = al[1], l2 = al[2], l3 = al[3];
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) {
         const int n0 = nh * 16 + nt * 8 + g;
@@ -212,8 +225,10 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
 #pragma unroll
       for (int ks = 0; ks < 4; ks++) {
         const int kc = ks * 8;
-        const float h0 = c_h[r0 + g][kc + q], h1 = c_h[r0 + g + 8][kc + q], h2 = c_h[r0 + g][kc + q + 4], h3 = c_h[r0 + g + 8][kc + q + 4];
-        const float l0 = c_l[r0 + g][kc + q], l1 = c_l[r0 + g + 8][kc + q], l2 = c_l[r0 + g][kc + q + 4], l3 = c_l[r0 + g + 8][kc + q + 4];
+      float ah[4], al[4];
+      ldsm_a(ah, &c_h[lrow][kc + lcol]);
+      ldsm_a(al, &c_l[lrow][kc + lcol]);
+      const float h0 = ah[0], h1 = ah[1], h2 = ah[2], h3 = ah[3], l0 = al[0], l1 = al[1], l2 = al[2], l3 = al[3];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
           const int n0 = nh * 64 + nt * 8 + g;
