@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="teacher_nll", choices=["teacher_nll", "student", "generate", "distill", "encode"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config)")
     ap.add_argument("--length", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -253,7 +253,7 @@ def main():
     if args.workload == "distill":
         prec = "fp32"                           # student forward/backward run in fp32; the teacher uses its fp16 path
     if args.workload == "generate":
-        if prec in ("auto", "fp16", "bf16"):     # tensor-core generation kernel (fp16 operands and queue state)
+        if prec in ("auto", "fp16"):     # tensor-core generation kernel (fp16 operands and queue state)
             prec = "fp16"
         u1_h, u2_h = synth.sampler_uniforms(B, T, seed=999 + rank)
 
@@ -366,7 +366,7 @@ def main():
         # queue pop + push of 32 channels per layer + the sample: 7684 B with fp32 state, 3844 B with fp16 state
         ach = (BYTES_PER_SAMPLE_AR if prec == "fp32" else BYTES_PER_SAMPLE_AR_F16) * B * T / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s"}
-    elif prec in ("bf16", "fp16"):
+    elif prec == "fp16":
         ach = flop_per_sample * B * T / (k_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s"}
     else:
@@ -392,7 +392,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[prec],
+            "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "fp32": "f32"}[prec],
             "data": "synthetic",
             "config": {"workload": names[args.workload], "batch_per_gpu": B, "global_batch": B * world,
                        "samples_per_utterance": T, "layers": len(dil), "parallelism": "batch-sharded x%d" % world,

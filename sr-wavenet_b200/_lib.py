@@ -14,7 +14,7 @@ TEACHER, STUDENT = 0, 1
 FP32, BF16, FP16 = 0, 1, 2
 OP_TEACHER_LOGITS, OP_TEACHER_NLL, OP_TEACHER_GENERATE, OP_STUDENT_FORWARD, OP_STUDENT_TRAIN = range(5)
 DISTILL_SUMS_LEN = 1024   # SRWN_DISTILL_SUMS_LEN
-PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
+PRECISIONS = {"fp32": FP32, "fp16": FP16}      # BF16 is refused by the library (include/srwn.h)
 
 
 class SrwnError(RuntimeError):

@@ -385,6 +385,13 @@ extern "C" int srwn_check_async_error(srwn_handle_t h, int32_t op, int32_t B, in
   return fused_check_error(workspace, workspace_bytes, h, B, T, (cudaStream_t)stream);
 }
 
+// bf16 MMA operands cannot meet the 2e-2 max-abs bound on logits for the 30-layer stack (exact arithmetic on bf16-rounded
+// operands already gives 2.45e-2, tools/bf16_emulation.py; the kernel measured 2.5e-2), so the 16-bit path is fp16
+// (same tensor rate, 8x finer mantissa, measured 3.6e-3) and SRWN_BF16 is refused rather than shipped with a looser bound.
+static int reject_bf16() {
+  return srwn_fail(SRWN_ERR_UNSUPPORTED, "SRWN_BF16 is not offered: bf16 operands miss the 2e-2 logit bound on this stack; use SRWN_FP16");
+}
+
 extern "C" int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision) {
   if (!h) return 0;
   const bool teacher_op = op == SRWN_OP_TEACHER_LOGITS || op == SRWN_OP_TEACHER_NLL || op == SRWN_OP_TEACHER_GENERATE;
@@ -392,8 +399,9 @@ extern "C" int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision) {
   if (teacher_op != (h->cfg.kind == SRWN_TEACHER) || op < 0 || op > SRWN_OP_STUDENT_FORWARD) return 0;
   if (precision == SRWN_FP32) return 1;
   if (op == SRWN_OP_TEACHER_GENERATE) return precision == SRWN_FP16 && ar_mma_supported(h) ? 1 : 0;
-  if (precision == SRWN_BF16 || precision == SRWN_FP16) return fused_supported(h) ? 1 : 0;
-  return 0;
+  if (precision == SRWN_FP16) return fused_supported(h) ? 1 : 0;
+  return 0;   // SRWN_BF16: see reject_bf16
+
 }
 
 extern "C" int srwn_workspace_bytes(srwn_handle_t h, int32_t op, int32_t B, int32_t T,
@@ -441,7 +449,8 @@ extern "C" int srwn_teacher_logits(srwn_handle_t h, const float* x, const float*
   if (h->cfg.kind != SRWN_TEACHER) return srwn_fail(SRWN_ERR_INVALID, "not a teacher handle");
   int rc = check_bt(h, B, T);
   if (rc) return rc;
-  if (precision == SRWN_BF16 || precision == SRWN_FP16)
+  if (precision == SRWN_BF16) return reject_bf16();
+  if (precision == SRWN_FP16)
     return run_teacher_fused_bf16(h, x, enc, nullptr, nullptr, nullptr, logits, B, T,
                                   precision == SRWN_FP16, workspace, workspace_bytes, (cudaStream_t)stream);
   if (precision != SRWN_FP32) return srwn_fail(SRWN_ERR_INVALID, "unknown precision %d", precision);
@@ -459,7 +468,8 @@ extern "C" int srwn_teacher_nll(srwn_handle_t h, const float* x_in, const float*
   if (h->cfg.kind != SRWN_TEACHER) return srwn_fail(SRWN_ERR_INVALID, "not a teacher handle");
   int rc = check_bt(h, B, T);
   if (rc) return rc;
-  if (precision == SRWN_BF16 || precision == SRWN_FP16)
+  if (precision == SRWN_BF16) return reject_bf16();
+  if (precision == SRWN_FP16)
     return run_teacher_fused_bf16(h, x_in, enc, x_scored, nll_out, nll_sum, logits_out, B, T,
                                   precision == SRWN_FP16, workspace, workspace_bytes, (cudaStream_t)stream);
   if (precision != SRWN_FP32) return srwn_fail(SRWN_ERR_INVALID, "unknown precision %d", precision);
@@ -498,7 +508,8 @@ extern "C" int srwn_student_forward(srwn_handle_t h, const float* z, const float
   int rc = check_bt(h, B, T);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == SRWN_BF16 || precision == SRWN_FP16)
+  if (precision == SRWN_BF16) return reject_bf16();
+  if (precision == SRWN_FP16)
     return run_student_fused_bf16(h, z, enc, out, s_tot, mu_tot, x_last, B, T, precision == SRWN_FP16,
                                   workspace, workspace_bytes, st);
   if (precision != SRWN_FP32) return srwn_fail(SRWN_ERR_INVALID, "unknown precision %d", precision);

@@ -71,7 +71,7 @@ struct LayerParams {
 template <bool FP16>
 __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
   uint32_t r;
-  if (FP16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (FP16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // saturating: no inf in an operand image
   else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
@@ -655,7 +655,7 @@ extern "C" int srwn_encoder_commit(srwn_encoder_t e, void* stream) {
 extern "C" int srwn_encoder_supports(srwn_encoder_t e, int32_t precision) {
   if (!e) return 0;
   if (precision == SRWN_FP32) return 1;
-  return (precision == SRWN_BF16 || precision == SRWN_FP16) && enc_tc_supported(e) ? 1 : 0;
+  return precision == SRWN_FP16 && enc_tc_supported(e) ? 1 : 0;   // bf16 operands are not offered (see srwn.h)
 }
 
 static size_t enc_ws_bytes(const srwn_encoder* e, int B, int T, int precision) {
@@ -736,7 +736,8 @@ extern "C" int srwn_teacher_encode(srwn_encoder_t e, const float* x, float* enc_
     enc::k_enc_latent_pool_f32<<<B * frames, 128, S * sizeof(float), st>>>(skip, W + e->o_lat_k, W + e->o_lat_b, enc_out, T, P, frames, S, C);
     SRWN_LAUNCH_CHECK();
   } else {
-    const bool fp16 = precision == SRWN_FP16;
+    if (precision != SRWN_FP16) return srwn_fail(SRWN_ERR_UNSUPPORTED, "the tensor-core encoder is built for fp16 operands only; use SRWN_FP16 or SRWN_FP32");
+    const bool fp16 = true;
     const size_t n_tiles = rows / enc::kTile;
     uint8_t* act0 = w.take<uint8_t>(n_tiles * enc::kAStage);
     uint8_t* act1 = w.take<uint8_t>(n_tiles * enc::kAStage);
@@ -747,14 +748,14 @@ extern "C" int srwn_teacher_encode(srwn_encoder_t e, const float* x, float* enc_
     enc::LayerParams p;
     p.err = err; p.n_tiles = (int)n_tiles; p.tiles_per_utt = T / enc::kTile; p.T = T;
     p.img = img; p.in = nullptr; p.x = x; p.out = act0; p.pooled = nullptr; p.reverse = 0;
-    int rc = fp16 ? launch_layer<true, true>(e, p, st) : launch_layer<true, false>(e, p, st);
+    int rc = launch_layer<true, true>(e, p, st);
     if (rc) return rc;
     uint8_t* cur = act0; uint8_t* nxt = act1;
     for (int l = 0; l < L; l++) {
       p.img = img + enc::kFrontImg + (size_t)l * enc::kLayerImg;
       p.in = cur; p.x = nullptr; p.out = l + 1 < L ? nxt : nullptr; p.pooled = pooled + (size_t)l * n_tiles * enc::kE;
       p.reverse = (l & 1) ^ 1;
-      rc = fp16 ? launch_layer<false, true>(e, p, st) : launch_layer<false, false>(e, p, st);
+      rc = launch_layer<false, true>(e, p, st);
       if (rc) return rc;
       uint8_t* t = cur; cur = nxt; nxt = t;
     }

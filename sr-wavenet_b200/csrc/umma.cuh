@@ -98,7 +98,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
 
 template <bool FP16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if (FP16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  if (FP16) {   // saturating: a value beyond +-65504 becomes the largest finite half, not an inf that would poison every later layer
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }

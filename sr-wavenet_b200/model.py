@@ -324,7 +324,7 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         return dict(self._weights)
 
     def available_precisions(self):
-        return ["fp32", "bf16", "fp16"] if _fused_available(self._eng) else ["fp32"]
+        return ["fp32", "fp16"] if _fused_available(self._eng) else ["fp32"]
 
     def load(self, logdir):
         return self._load(logdir)
@@ -478,7 +478,7 @@ class WaveNetAutoEncoder(_CheckpointMixin):
 
 def _fused_available(eng):
     op = _lib.OP_TEACHER_LOGITS if eng.kind == _lib.TEACHER else _lib.OP_STUDENT_FORWARD
-    return bool(eng.lib.srwn_supports(eng.h, op, _lib.BF16))
+    return bool(eng.lib.srwn_supports(eng.h, op, _lib.FP16))
 
 
 class ParallelWaveNet(_CheckpointMixin):
@@ -544,7 +544,7 @@ class ParallelWaveNet(_CheckpointMixin):
         return dict(self._weights)
 
     def available_precisions(self):
-        return ["fp32", "bf16", "fp16"] if _fused_available(self._eng) else ["fp32"]
+        return ["fp32", "fp16"] if _fused_available(self._eng) else ["fp32"]
 
     def load(self, sess, logdir):
         if isinstance(self.teacher, str):

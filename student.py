@@ -43,7 +43,7 @@ def build_parser():
     p.add_argument('--audio-max-length', type=int, default=16000, help='length of the audio feature in the TFRecord (nsynth.py:6)')
     p.add_argument('--out-dir', type=str, default='.')
     p.add_argument('--clips', type=int, default=20, help='--test: number of clips')
-    p.add_argument('--precision', type=str, default='fp16', choices=['fp32', 'bf16', 'fp16'])
+    p.add_argument('--precision', type=str, default='fp16', choices=['fp32', 'fp16'])
     p.add_argument('--seed', type=int, default=None, help='seed of the host-side logistic noise (student.py:104 leaves it unseeded)')
     return p
 

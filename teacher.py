@@ -39,7 +39,7 @@ def build_parser():
     p.add_argument('--audio-max-length', type=int, default=16000, help='length of the audio feature in the TFRecord (nsynth.py:6)')
     p.add_argument('--out-dir', type=str, default='.')
     p.add_argument('--clips', type=int, default=None, help='number of clips (default: 10 for --test-fast, 1 for --test-slow)')
-    p.add_argument('--precision', type=str, default='fp16', choices=['fp32', 'bf16', 'fp16'])
+    p.add_argument('--precision', type=str, default='fp16', choices=['fp32', 'fp16'])
     p.add_argument('--check-naive', type=int, default=0, help='--test-slow: also run the per-sample loop on the first N samples')
     return p
 

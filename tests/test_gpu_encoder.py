@@ -3,7 +3,7 @@ NumPy oracle and the committed golden vectors.
 
 Tolerances: fp32 path <= 1e-4 relative (BASELINE.json north_star).  The tensor-core path rounds the
 activations of 31 relu layers to 16 bits; measured max |d encoding| vs the float64 oracle is ~1e-3
-(fp16) / ~8e-3 (bf16) for encodings of scale ~0.3, asserted at 5e-3 / 3e-2."""
+(fp16) for encodings of scale ~0.3, asserted at 5e-3 (bf16 operands are not offered, see include/srwn.h)."""
 import numpy as np
 import pytest
 import torch
@@ -14,7 +14,7 @@ from sr_wavenet_b200 import synth, _lib
 
 pytestmark = pytest.mark.gpu
 
-TOL16 = {"fp16": 5e-3, "bf16": 3e-2}
+TOL16 = {"fp16": 5e-3}
 L30 = len(synth.DEFAULT_DILATIONS)
 
 
@@ -54,7 +54,7 @@ def test_encoder_golden_small_generic_shape(srwn):
         eng.encode(torch.from_numpy(g["x"]).cuda(), _lib.FP16)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
 def test_encoder_golden_default(teacher, prec):
     t, _ = teacher
     g = _load("encoder_default.npz")

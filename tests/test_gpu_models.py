@@ -4,12 +4,10 @@ the C ABI vs the NumPy oracle and the committed golden vectors.
 Tolerances (BASELINE.json north_star): fp32 path <= 1e-4 relative; 16-bit tensor-core path <= 2e-2
 max-abs on logits / per-sample log-likelihood, identical mixture argmax under teacher forcing.
 
-The fused kernel runs with fp16 or bf16 MMA operands (fp32 accumulate and residual stream).  fp16
-operands are the default 16-bit path: measured max |dlogits| ~3e-3, asserted <= 1e-2 (inside the
-2e-2 bound).  With bf16 operands the bound cannot hold for the 30-layer stack: rounding h, the gate
-and the weights to 8 mantissa bits alone gives 2.45e-2 max-abs on 2 x 4096 samples in a NumPy
-emulation of exact arithmetic with bf16-rounded operands (tools/bf16_emulation.py), and the kernel
-reproduces that number; bf16 is therefore asserted at 4e-2 (documented in DESIGN.md)."""
+The 16-bit path is fp16 operands (fp32 accumulate and residual stream): measured max |dlogits| ~3e-3,
+asserted <= 1e-2 (inside the 2e-2 bound).  bf16 operands are not offered: the bound cannot hold for the
+30-layer stack (exact arithmetic on bf16-rounded operands already gives 2.45e-2, tools/bf16_emulation.py),
+so the library refuses SRWN_BF16 instead of shipping a looser tolerance (test_bf16_is_refused)."""
 import os
 
 import numpy as np
@@ -23,8 +21,7 @@ from sr_wavenet_b200 import synth
 pytestmark = pytest.mark.gpu
 
 REL = 1e-4
-TOL16 = {"fp16": 1e-2, "bf16": 4e-2}
-BF16_ABS = 2e-2
+TOL16 = {"fp16": 1e-2}
 
 
 def _teacher(srwn, dil, C=32, M=5, P=128, seed=42, T=4096):
@@ -36,7 +33,7 @@ def _teacher(srwn, dil, C=32, M=5, P=128, seed=42, T=4096):
 
 
 # student: 4 chained flows x 30 layers and an exp() amplify operand rounding; out is clipped to [-1,1]
-STUDENT_TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 1.5e-1}
+STUDENT_TOL = {"fp32": 1e-4, "fp16": 2e-2}
 
 
 def _student(srwn, dil, F, C=32, P=128, seed=43, T=4096):
@@ -85,7 +82,7 @@ def test_teacher_golden_default_cfg(srwn, golden_default):
         assert np.abs(logits - g["logits"]).max() <= _tol(g["logits"], prec), prec
         tot = t.nll(x, enc, precision=prec)
         assert abs(tot - float(g["nll_sum"])) <= (1e-3 if prec in TOL16 else REL) * abs(float(g["nll_sum"]))
-        t._eng.check_async(1, B, T, {"fp32": 0, "bf16": 1, "fp16": 2}[prec])
+        t._eng.check_async(1, B, T, {"fp32": 0, "fp16": 2}[prec])
 
 
 @pytest.mark.parametrize("B,T", [(1, 128), (3, 3072), (2, 8192), (2, 13440)])
@@ -98,18 +95,60 @@ def test_teacher_vs_oracle_shapes(srwn, B, T):
     for prec in t.available_precisions():
         logits = t.get_logits(x, enc, precision=prec)
         assert np.abs(logits - ref).max() <= _tol(ref, prec), prec
-        if prec in TOL16:      # identical Gumbel-argmax mixture indices under teacher forcing
+        if prec in TOL16:      # identical Gumbel-argmax mixture indices under teacher forcing (ops.py:187)
             u1, u2 = synth.sampler_uniforms(B, T)
-            _, k_ref = orc.sample_from_discretized_mix_logistic(ref, 5, u1.astype(np.float64),
-                                                                u2.astype(np.float64)[:, :, None], True)
-            _, k = srwn.ops.sample_from_discretized_mix_logistic(logits, 5, u1, u2, return_index=True)
-            k = k.cpu().numpy()
-            # a flip is only legitimate where the top two perturbed logits are closer than the bf16 tolerance
-            pert = ref[:, :, :5] - np.log(-np.log(u1.astype(np.float64)))
-            srt = np.sort(pert, axis=2)
-            ambiguous = (srt[:, :, -1] - srt[:, :, -2]) < 2 * TOL16[prec]
-            assert ambiguous.mean() < 0.15
-            assert np.array_equal(k[~ambiguous], k_ref[~ambiguous])
+            flips, could = mixture_flips(srwn, ref, logits, u1, u2)
+            print("teacher %s %dx%d: %d mixture-index flips of %d positions (%d within reach of the measured error)"
+                  % (prec, B, T, flips, B * T, could))
+
+
+def mixture_flips(srwn, ref_logits, logits, u1, u2, M=5):
+    """Exact count of positions where the Gumbel-argmax mixture index (ops.py:187) of the 16-bit logits differs from the
+    oracle's, given the same uniforms.  A flip is legitimate only where the oracle's own top-two perturbed logits are
+    closer than twice the MEASURED max error of the mixture logits (an adversarial perturbation of that size flips the
+    oracle there too); every flip must lie in that set.  Returns (flips, positions within reach)."""
+    _, k_ref = orc.sample_from_discretized_mix_logistic(ref_logits, M, u1.astype(np.float64),
+                                                        u2.astype(np.float64)[:, :, None], True)
+    _, k = srwn.ops.sample_from_discretized_mix_logistic(logits, M, u1, u2, return_index=True)
+    k = k.cpu().numpy() if hasattr(k, "cpu") else np.asarray(k)
+    eps = float(np.abs(np.asarray(logits, np.float64)[:, :, :M] - ref_logits[:, :, :M]).max())
+    pert = ref_logits[:, :, :M] - np.log(-np.log(u1.astype(np.float64)))
+    srt = np.sort(pert, axis=2)
+    reach = (srt[:, :, -1] - srt[:, :, -2]) <= 2 * eps
+    flipped = k != k_ref
+    assert not (flipped & ~reach).any(), "a mixture index flipped where the logits differ by more than the gap allows"
+    assert flipped.sum() <= reach.sum()
+    return int(flipped.sum()), int(reach.sum())
+
+
+def test_bf16_is_refused(srwn):
+    t, _ = _teacher(srwn, synth.DEFAULT_DILATIONS)
+    assert "bf16" not in t.available_precisions()
+    lib = srwn._lib.load()
+    assert lib.srwn_supports(t._eng.h, srwn._lib.OP_TEACHER_LOGITS, srwn._lib.BF16) == 0
+    x = torch.zeros(1, 128, device="cuda")
+    enc = torch.zeros(1, 1, 32, device="cuda")
+    out = torch.zeros(1, 128, 20, device="cuda")
+    ws, wsn = t._eng.workspace(srwn._lib.OP_TEACHER_LOGITS, 1, 128, srwn._lib.FP16)
+    rc = lib.srwn_teacher_logits(t._eng.h, x.data_ptr(), enc.data_ptr(), out.data_ptr(), 1, 128, srwn._lib.BF16, ws, wsn, 0)
+    assert rc == srwn._lib.ERR_UNSUPPORTED
+
+
+def test_fp16_operands_saturate_instead_of_overflowing(srwn):
+    """Encodings scaled until the conditioning pushes |h| past the fp16 range (65504): the 16-bit operand image
+    saturates (cvt.rn.satfinite), so logits stay finite instead of turning into inf/NaN for every later layer; below
+    the range the usual bound holds relative to the size of the activations."""
+    dil = synth.DEFAULT_DILATIONS
+    t, w = _teacher(srwn, dil)
+    B, T = 1, 1024
+    x = synth.synthetic_audio(B, T, seed=3)
+    enc100 = synth.synthetic_encoding(B, T // 128, seed=4) * 100.0
+    ref = orc.teacher_decoder_logits(f64(w), x.astype(np.float64), enc100.astype(np.float64), dil, 128)
+    lg = t.get_logits(x, enc100, precision="fp16")
+    assert np.isfinite(lg).all()
+    assert np.abs(lg - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max())
+    huge = t.get_logits(x, enc100 * 3000.0, precision="fp16")          # |h| ~ 1e6 > 65504
+    assert np.isfinite(huge).all()
 
 
 def test_teacher_pool_stride_and_conditions(srwn):
@@ -263,7 +302,7 @@ def test_student_golden_default_cfg(srwn, golden_default):
         tol = STUDENT_TOL[prec]
         assert np.abs(r["out"] - g["student_out"][:, :, 0]).max() <= tol
         assert np.abs(r["s_tot"] / g["s_tot"][:, :, 0] - 1).max() <= 2 * tol
-        s._eng.check_async(3, B, T, {"fp32": 0, "bf16": 1, "fp16": 2}[prec])
+        s._eng.check_async(3, B, T, {"fp32": 0, "fp16": 2}[prec])
     ent = s.getEntropy_fast(None, z, enc)
     ref_ent = float(np.sum(np.log(g["s_tot"].astype(np.float64)) + 2.0))      # model.py:356
     assert abs(ent - ref_ent) <= 1e-3 * abs(ref_ent)

@@ -1,9 +1,11 @@
 """Oracle vs the committed golden vectors, plus the size-independent properties the domain
 offers (causality, receptive field, queue-AR == naive loop, flow composition identity)."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import f64
+from conftest import f64, GOLDEN
 from oracle import srwn_oracle as orc
 import sr_wavenet_b200.synth as synth
 
@@ -186,3 +188,32 @@ def test_encoder_golden_and_same_padding():
     # relu(x) = [1,0,3,4]; conv = [1+0, 0+30, 3+40, 4+0] = [1,30,43,4]
     assert np.array_equal(res[0, :, 0], np.array([2.5, 60.5, 86.5, 8.5]))
     assert np.array_equal(skip[0], np.array([[1, -1], [30, -30], [43, -43], [4, -4]], dtype=np.float64))
+
+
+@pytest.mark.parametrize("tag", ["small", "default"])
+def test_oracle_matches_reference_fixtures(tag):
+    """The oracle against outputs of the reference's own code (tests/golden/reference_*.npz, produced by running
+    /root/reference/ops.py + model.py through tests/tf_shim; see tests/test_reference_shim.py for the live comparison).
+    This copy of the pin travels to machines without the reference tree."""
+    with np.load(os.path.join(GOLDEN, "reference_%s.npz" % tag)) as z:
+        g = {k: z[k] for k in z.files}
+    dil, P, C, F, M = [int(d) for d in g["dilations"]], int(g["P"]), int(g["C"]), int(g["F"]), int(g["M"])
+    tw = synth.make_teacher_weights(dil, latent_channels=C, num_mixtures=M, seed=int(g["teacher_seed"]))
+    tw.update(synth.make_encoder_weights(len(dil), 2, 128, 128, C, seed=int(g["teacher_seed"]) + 2))
+    tw, sw = f64(tw), f64(synth.make_student_weights(dil, num_flows=F, latent_channels=C, seed=int(g["student_seed"])))
+    x, enc, z_ = (g[k].astype(np.float64) for k in ("x", "enc", "z"))
+    u1, u2 = g["u1"].astype(np.float64), g["u2"].astype(np.float64)
+    tol = dict(rtol=1e-10, atol=1e-11)
+    logits = orc.teacher_decoder_logits(tw, x, enc, dil, P)
+    np.testing.assert_allclose(logits, g["logits"], **tol)
+    np.testing.assert_allclose(orc.discretized_mix_logistic_loss(x[:, :, None], logits, False), g["nll"], **tol)
+    np.testing.assert_allclose(orc.sample_from_discretized_mix_logistic(logits, M, u1, u2[:, :, None])[:, :, 0], g["sample"], **tol)
+    np.testing.assert_allclose(orc.teacher_encoder(tw, x, len(dil), P), g["encoding"], **tol)
+    net = orc.student_network(sw, z_, enc, dil, P, F)
+    for k, ref in (("out", "student_out"), ("s_tot", "s_tot"), ("mu_tot", "mu_tot")):
+        np.testing.assert_allclose(net[k], g[ref], **tol)
+    loss, power, entropy = orc.distillation_loss(sw, tw, z_, x, enc, dil, P, F, alpha=0.25, beta=1.0, gamma=1.0)
+    np.testing.assert_allclose([loss, power, entropy], [g["loss"], g["power_loss"], g["entropy"]], rtol=1e-10)
+    if "ar_x" in g:
+        n = g["ar_x"].shape[1]
+        np.testing.assert_allclose(orc.queue_ar(tw, enc[:, :n // P], dil, P, M, u1[:, :n], u2[:, :n], n), g["ar_x"], rtol=1e-9, atol=1e-10)
