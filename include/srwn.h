@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SRWN_ABI_VERSION 5
+#define SRWN_ABI_VERSION 6
 
 enum srwn_status {
   SRWN_OK = 0,
@@ -110,6 +110,15 @@ int srwn_commit_weights(srwn_handle_t h, void* stream);
  * aborted (a bounded on-device pipeline wait expired; outputs are then invalid). */
 int srwn_check_async_error(srwn_handle_t h, int32_t op, int32_t B, int32_t T, int32_t precision,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* Synchronises `stream` and reports (then clears) the abort words of the fused-kernel calls issued on this handle so far
+ * (a bounded on-device pipeline wait expired; the outputs of that call are invalid).  The words live in pinned host
+ * memory: once a launch has aborted, every later call on the handle is refused with SRWN_ERR_CUDA until this function
+ * has been called, so a caller that keeps its results on the device cannot consume them unnoticed for long. */
+/* Fused tensor-core kernel: CTAs per team (teams walk contiguous pieces of the (utterance, chunk) line as a wavefront
+ * over chunks and layers, handing the per-layer history rings from CTA to CTA).  0 (default) = chosen per (B, T).
+ * Results do not depend on it.  srwn_last_partition reports the choice of the last fused call. */
+int srwn_set_team_size(srwn_handle_t h, int32_t ctas_per_team);
+int srwn_last_partition(srwn_handle_t h, int32_t* teams, int32_t* ctas_per_team);
 /* 1 if `op` (enum srwn_op) is built for `precision` with this handle's configuration, else 0. */
 int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision);
 int srwn_workspace_bytes(srwn_handle_t h, int32_t op, int32_t B, int32_t T,

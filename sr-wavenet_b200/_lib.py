@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRWN_LIB") or os.path.join(_HERE, "libsrwn.so")   # SRWN_LIB: tuning builds (tools/exp_build.sh)
 
-ABI_VERSION = 5      # SRWN_ABI_VERSION in include/srwn.h
+ABI_VERSION = 6      # SRWN_ABI_VERSION in include/srwn.h
 OK, ERR_INVALID, ERR_CUDA, ERR_WEIGHTS, ERR_UNSUPPORTED, ERR_WORKSPACE = range(6)
 TEACHER, STUDENT = 0, 1
 FP32, BF16, FP16 = 0, 1, 2
@@ -51,6 +51,8 @@ SIGNATURES = {
     "srwn_get_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, _i64]),
     "srwn_commit_weights": (ctypes.c_int, [_vp, _vp]),
     "srwn_set_profiling": (ctypes.c_int, [_vp, _i32]),
+    "srwn_set_team_size": (ctypes.c_int, [_vp, _i32]),
+    "srwn_last_partition": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "srwn_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32),
                                            ctypes.POINTER(ctypes.c_char_p)]),
     "srwn_check_async_error": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),

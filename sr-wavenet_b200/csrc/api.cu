@@ -184,7 +184,8 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
   c->committed = false; c->device_dirty = false;
   c->d_weights = nullptr; c->d_dilations = nullptr; c->d_queue_off = nullptr;
   c->d_packed = nullptr; c->packed_bytes = 0; c->d_ar_packed = nullptr;
-  c->d_part = nullptr; c->part_B = c->part_T = c->part_grid = 0;
+  c->d_part = nullptr; c->part_B = c->part_T = c->part_teams = c->part_G = 0; c->part_team_req = -1;
+  c->team_size = 0; c->h_err = nullptr;
   c->profiling = 0; c->prof_launches = 0; c->prof_name = "";
   c->prof_ev[0] = c->prof_ev[1] = nullptr;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -221,6 +222,9 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
   if (e == cudaSuccess) {
     c->packed_bytes = fused_packed_bytes(c);
     if (c->packed_bytes) e = cudaMalloc(&c->d_packed, c->packed_bytes);
+    if (e == cudaSuccess && c->packed_bytes) e = cudaMalloc(&c->d_part, fused_partition_bytes(c));
+    if (e == cudaSuccess && c->packed_bytes) e = cudaHostAlloc((void**)&c->h_err, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess && c->h_err) memset(c->h_err, 0, 64);
   }
   if (e != cudaSuccess) {
     int rc = srwn_fail(SRWN_ERR_CUDA, "srwn_create: %s", cudaGetErrorString(e));
@@ -235,6 +239,7 @@ extern "C" int srwn_destroy(srwn_handle_t h) {
   if (!h) return SRWN_OK;
   if (h->prof_ev[0]) { cudaEventDestroy(h->prof_ev[0]); cudaEventDestroy(h->prof_ev[1]); }
   cudaFree(h->d_ar_packed); cudaFree(h->d_part);
+  if (h->h_err) cudaFreeHost(h->h_err);
   cudaFree(h->d_weights); cudaFree(h->d_dilations); cudaFree(h->d_queue_off); cudaFree(h->d_packed);
   delete reinterpret_cast<CtxBox*>(h);
   return SRWN_OK;
@@ -349,6 +354,21 @@ static int check_bt(const srwn_ctx* c, int B, int T) {
     return srwn_fail(SRWN_ERR_INVALID, "T=%d must be a multiple of pool_stride=%d (model.py:183)", T,
                      c->cfg.pool_stride);
   if (!c->committed) return srwn_fail(SRWN_ERR_WEIGHTS, "weights not committed (srwn_commit_weights)");
+  return SRWN_OK;
+}
+
+extern "C" int srwn_set_team_size(srwn_handle_t h, int32_t ctas_per_team) {
+  if (!h) return srwn_fail(SRWN_ERR_INVALID, "srwn_set_team_size: null handle");
+  if (ctas_per_team < 0 || ctas_per_team > 64) return srwn_fail(SRWN_ERR_INVALID, "team size must be 0 (automatic) .. 64");
+  h->team_size = ctas_per_team;
+  return SRWN_OK;
+}
+
+extern "C" int srwn_last_partition(srwn_handle_t h, int32_t* teams, int32_t* ctas_per_team) {
+  if (!h || !teams || !ctas_per_team) return srwn_fail(SRWN_ERR_INVALID, "srwn_last_partition: null argument");
+  int t = 0, g = 0;
+  fused_last_partition(h, &t, &g);
+  *teams = t; *ctas_per_team = g;
   return SRWN_OK;
 }
 

@@ -71,8 +71,11 @@ struct srwn_ctx {
   // packed bf16 operand images for the tcgen05 path (built at commit)
   void* d_packed;
   size_t packed_bytes;
-  void* d_part;                       // cached work partition of the fused kernel for (part_B, part_T): segs | nseg
-  int part_B, part_T, part_grid;
+  void* d_part;                       // work partition of the fused kernel for (part_B, part_T, team size): segs | nseg (allocated at create)
+  int part_B, part_T, part_team_req, part_teams, part_G;
+  std::vector<uint8_t> part_host;     // host staging of d_part
+  int team_size;                      // srwn_set_team_size: CTAs per team of the fused kernel, 0 = chosen per (B, T)
+  int* h_err;                         // pinned, mapped: abort words of the fused kernel [flag, code, chunk, cta]
   void* d_ar_packed;                  // fragment-ordered fp16 weights of the tensor-core generation kernel (built at commit)
   // optional timing of the dominant kernel(s) of the last call (srwn_set_profiling)
   int profiling;
@@ -156,3 +159,5 @@ int run_student_fused_bf16(srwn_ctx* c, const float* z, const float* enc, float*
                            float* s_tot, float* mu_tot, float* x_last, int B, int T, int fp16,
                            void* ws, size_t ws_bytes, cudaStream_t st);
 int fused_check_error(void* ws, size_t ws_bytes, const srwn_ctx* c, int B, int T, cudaStream_t st);
+size_t fused_partition_bytes(const srwn_ctx* c);
+void fused_last_partition(const srwn_ctx* c, int* teams, int* G);

@@ -15,9 +15,14 @@
 // Warp roles: warps 0-11 = three epilogue warpgroups (one per tile; tcgen05.ld -> gate math ->
 // 16-bit operand stores), warp 12 = MMA issuer (event driven, one elected thread) + TMEM owner,
 // warp 13 = loader (cp.async.bulk weights per layer, cp.async ring -> halo rows).
-// A piece that starts mid-utterance first recomputes the receptive field (sum of dilations,
-// rounded up to whole chunks) with outputs discarded, so pieces are independent (no inter-CTA
-// synchronisation) and results do not depend on the partition.
+// Work decomposition: the (utterance, chunk) line is cut into contiguous pieces, one per TEAM of G CTAs; the members
+// of a team take the piece's chunks round-robin (member j: chunks j, j+G, ...).  Chunk n+1 needs, per layer, the last
+// d_l input rows of chunk n (the history ring): the team shares one ring block in global memory (L2 resident) and chunk
+// n's CTA publishes "ring l of chunk n is written" through a per-(team, layer) flag, so chunk n+1's CTA runs the same
+// layers about one layer behind -- a wavefront over (chunk, layer) with no recomputation inside a piece.  Only a piece
+// that starts mid-utterance recomputes the receptive field (sum of dilations, rounded up to whole chunks, pruned to the
+// dependency cone) with outputs discarded; that cost is shared by the G members.  Results do not depend on the
+// partition or on G (tests: bit-exact under batch permutation, oracle comparisons at several B x T).
 //
 // Reference semantics: ops.py:6-46 (block, gate = sigmoid(tanh(.)) per ops.py:33),
 // model.py:172-196 (decoder), model.py:423-452 + 479-482 (student flow), ops.py:124-175 (NLL).
@@ -57,21 +62,24 @@ struct Params {
   const float* x_in;          // [B][T] stack input (audio / noise / previous flow output)
   const float* x_scored;      // teacher: audio whose likelihood is taken (may be null)
   const float* cb;            // [B][frames][L+1][32] fp32: folded biases + conditioning
-  uint8_t* rings;             // per-CTA history rings
-  const Seg* segs;            // [grid][kMaxSeg]
-  const int* nseg;            // [grid]
+  uint8_t* rings;             // per-team history rings
+  const Seg* segs;            // [teams][kMaxSeg]
+  const int* nseg;            // [teams]
+  uint32_t* flags;            // [teams][kMaxLayers]: flags[l] = number of chunks of the piece whose ring l is published
+  int G;                      // CTAs per team
   float* logits_out;          // teacher, optional [B][T][O]
   float* nll_out;             // teacher, optional [B][T]
   double* nll_partial;        // teacher, optional [grid]
   float* scale_out;           // student [B][T]
   float* mean_out;            // student [B][T]
   float* x_out;               // student [B][T]
-  int* err;                   // device error flag
+  int* err;                   // error words (pinned host memory, mapped): [0] flag [1] code [2] chunk [3] cta
+#ifdef SRWN_TUNING
   long long* trace;           // optional [7 roles][kMaxLayers][12] clock64 stamps of CTA 0 (tuning aid)
   int trace_chunk;
-  int dbg;                    // tuning experiments (SRWN_DBG): wrong results, timing only
+#endif
   int T, L, P, frames, O, M;
-  int ring_bytes_per_cta;
+  int ring_bytes_per_team;
   int dil[kMaxLayers];
   int ring_off[kMaxLayers];   // byte offset of layer l's ring inside a CTA's ring block
   int rsuf[kMaxLayers + 1];   // rsuf[l] = dil[l] + ... + dil[L-1]: how far back h_l is needed before the first output row
@@ -92,7 +100,7 @@ struct SmemMap {
   static constexpr int cbs = front + 64 * 4;                      // [3 tiles][kMaxLayers+1][32] folded bias + conditioning of the chunk
   static constexpr int bars = cbs + kTiles * (kMaxLayers + 1) * 32 * 4;
   static constexpr int n_bars = 32;
-  static constexpr int misc = bars + n_bars * 8;                  // tmem ptr, abort flag
+  static constexpr int misc = bars + n_bars * 8;                  // [0] tmem ptr, [8] abort flag + code, [16..28) ring-row counters
   static constexpr int total = misc + 64;
 };
 static_assert(SmemMap::total <= 232448, "shared memory budget");
@@ -108,6 +116,7 @@ enum Bar {
   BAR_HALO = 16,   // [2] loader -> tile groups: halo rows of the layer landed
   BAR_G1 = 18,     // [2] MMA -> loader/tile groups: all filter-conv MMAs of the layer retired (3 commits)
   BAR_HDD = 20,    // [3] MMA -> tile group: head accumulator ready
+  BAR_TAIL = 23,   // loader -> tile groups: a pruned warm-up chunk may write the ring behind its last layer
 };
 
 using namespace umma;
@@ -154,7 +163,7 @@ __device__ __forceinline__ void store_row_packed(uint8_t* buf, int rows_per_kc, 
 #ifndef SRWN_EXP
 #define SRWN_EXP 0      // tuning experiments (compile-time; non-zero values give wrong results, timing only)
 #endif
-#if !(SRWN_EXP & 16)      // production builds carry no trace code (it costs ~10 % even when disabled at run time)
+#if !defined(SRWN_TUNING) || !(SRWN_EXP & 16)      // production builds carry no trace code (it costs ~10 % even when disabled at run time)
 #define TRACE(role, layer, slot) do {} while (0)
 #else
 #define TRACE(role, layer, slot)                                                            \
@@ -170,12 +179,54 @@ __device__ __forceinline__ void store_row_packed(uint8_t* buf, int rows_per_kc, 
 #endif
 
 // ---- the kernel --------------------------------------------------------------------------
-// 13 warps: warp 0 = loader + TMEM owner, warps 1..12 = three tile groups of four warps, one warp per
-// SMSP (row = TMEM lane = 32*(warp&3) + lane).  Warp w sits on SMSP q = w&3 at level j = (w-1)/4 and
+// 14 warps: warp 0 = loader + TMEM owner, warps 1..12 = three tile groups of four warps, one warp per
+// SMSP (row = TMEM lane = 32*(warp&3) + lane), warp 13 = publisher of the ring flags (off the layer chain).  Warp w sits on SMSP q = w&3 at level j = (w-1)/4 and
 // belongs to tile (j+q+1)%3, so that tile m's MMA-issuing warp is the highest warp id of SMSP m (the
 // arbiter prefers high warp ids, and tcgen05 issue from a busy SMSP is what the layer chain waits on).
-constexpr int kThreads = 13 * 32;
+constexpr int kThreads = 14 * 32;
 constexpr int kLoadWarp = 0;
+constexpr int kPubWarp = 13;
+constexpr long long kWaitLimit = 1000000000LL;       // clocks before a stuck wait raises the abort flag
+
+// ---- cross-CTA ring hand-off ------------------------------------------------------------------------
+// consumer: chunk n waits until flags[l] >= n (rings of chunks 0..n-1 published), then orders its bulk loads (async proxy)
+// after the acquire
+__device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, volatile int* abort_flag, const int* gerr, int code) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  if (v < need) {
+    const long long t0 = clock64();
+    int spins = 0;
+    while (true) {
+      __nanosleep(32);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v >= need) break;
+      if (*abort_flag) return false;
+      if (((++spins) & 1023) == 0 && *reinterpret_cast<const volatile int*>(gerr)) return false;   // another CTA aborted (host memory: polled rarely)
+      if (clock64() - t0 > kWaitLimit) {
+        if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = code;
+        return false;
+      }
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  return true;
+}
+// producer, tile-group thread: after its ring rows (generic stores): make them visible to the async proxy, then count
+// the row in the group's shared-memory counter (release at CTA scope: the publisher's acquire sees the rows)
+__device__ __forceinline__ void ring_row_done(uint32_t counter_addr) {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(counter_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// producer, publisher lane: flags[l] = max(flags[l], chunks) with release at GPU scope (cumulative over the rows it acquired)
+__device__ __forceinline__ void flag_publish(uint32_t* f, uint32_t chunks) {
+  asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(f), "r"(chunks) : "memory");
+}
 
 template <bool TEACHER, bool FP16>
 __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
@@ -200,7 +251,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
       mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), kTiles);
       mbar_init(bar(BAR_HALO + i), 1); mbar_init(bar(BAR_G1 + i), kTiles);
     }
+    mbar_init(bar(BAR_TAIL), 1);
     abort_flag[0] = 0; abort_flag[1] = 0;
+    for (int i = 0; i < 3; i++) reinterpret_cast<volatile uint32_t*>(smem + SmemMap::misc + 16)[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {  // resident constants: biases, front conv, head weights (plain loads; made visible below)
@@ -231,18 +284,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const Seg* segs = p.segs + (size_t)blockIdx.x * kMaxSeg;
-  const int nseg = p.nseg[blockIdx.x];
-  uint8_t* ring = p.rings + (size_t)blockIdx.x * p.ring_bytes_per_cta;
+  const int G = p.G, team = (int)blockIdx.x / G, member = (int)blockIdx.x % G;
+  const Seg* segs = p.segs + (size_t)team * kMaxSeg;
+  const int nseg = p.nseg[team];
+  uint8_t* ring = p.rings + (size_t)team * p.ring_bytes_per_team;
+  uint32_t* flags = p.flags + (size_t)team * kMaxLayers;
+  const uint32_t ringcnt = sbase + SmemMap::misc + 16;   // [3] ring rows written so far by tile group m (monotonic)
+  uint32_t pub_expect = 0;                              // publisher lane m: rows group m has to have written
+  int seq = 0;                                          // chunk sequence number inside the piece
   int u0e = 0, u0o = 0, lay_base = 0;                 // phases of the parity-indexed / per-layer barriers used so far
   int chunk_idx = 0;                                  // chunks processed so far
   int head_idx = 0;                                   // chunks with a head phase so far
+  int tail_idx = 0;                                   // pruned warm-up chunks (Lc < L) so far
   double nll_acc = 0.0;
   const bool elected = elect_one();
 
   for (int si = 0; si < nseg; si++) {
     const Seg sg = segs[si];
-    for (int t0 = sg.t_start; t0 < sg.t_end; t0 += kChunk, chunk_idx++) {
+    for (int t0 = sg.t_start; t0 < sg.t_end; t0 += kChunk) {
+      const int n = seq++;
+      if (n % G != member) continue;                    // another member of the team runs this chunk
       const bool warm = TEACHER ? (t0 + kChunk <= sg.t_out) : false;   // student chunks always need h (cheap)
       const bool do_head = TEACHER && !warm;
       // A warm-up chunk only feeds the rings: layer l's output h_{l+1} is needed on the rsuf[l+1] rows before the first
@@ -256,7 +317,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         if (Lc < 1) Lc = 1;
       }
 #define U0(par) ((par) ? u0o : u0e)
+#if defined(SRWN_TUNING) && (SRWN_EXP & 16)
       const bool tracing_chunk = p.trace != nullptr && blockIdx.x == 0 && chunk_idx == p.trace_chunk;
+#else
+      constexpr bool tracing_chunk = false; (void)tracing_chunk;
+#endif
 
       if (warp == kLoadWarp) {
         // ================= loader: weights (bulk copy) + halo rows (cp.async) per layer ============
@@ -269,6 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           // its condition (filter-conv MMAs of layer l-2 retired) holds earlier than the weight stage's.
           if (l >= 2 && !mbar_wait(bar(BAR_G1 + s), (use - 1) & 1, abort_flag, 0x1100000 | l)) break;   // G1 of layer l-2 retired
           TRACE(6, l, 2);
+          // ring l of the previous chunk of the piece (written by another member of the team unless G == 1); also taken
+          // at an utterance start, where the rows are not read: this chunk may overwrite the ring only after chunk n-1
+          // has read it, which its publication implies
+          if (n > 0 && !flag_wait(flags + l, (uint32_t)n, abort_flag, p.err, 0x1200000 | l)) break;
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
@@ -319,6 +388,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           TRACE(6, l, 1);
           TRACE(6, l, 3);
         }
+        // a pruned warm-up chunk writes ring Lc behind its last layer without reading it: the write has to come after
+        // chunk n-1's rows of the same ring
+        if (Lc < L && !*abort_flag) {
+          const bool ok = n == 0 || flag_wait(flags + Lc, (uint32_t)n, abort_flag, p.err, 0x1300000 | Lc);
+          if (ok && lane == 0) mbar_arrive(bar(BAR_TAIL));
+        }
+      } else if (warp == kPubWarp) {
+        // ================= publisher: ring l of this chunk is complete -> flags[l] = n + 1 ========================
+        // Rings written by this chunk: 0 (front conv) and l+1 by the residual epilogue of layer l < Lc (l+1 < L).  Lane m
+        // follows tile group m: ring r is written by the rows rc >= kChunk - d_r, i.e. a known number of rows per group.
+        const int last = Lc < L - 1 ? Lc : L - 1;
+        bool ok = true;
+        for (int r = 0; r <= last && ok; r++) {
+          if (lane < kTiles) {
+            const int lo = max(kChunk - p.dil[r], lane * kTile), hi = (lane + 1) * kTile;
+            if (hi > lo) {
+              pub_expect += (uint32_t)(hi - lo);
+              if ((int32_t)(ld_acquire_cta_shared(ringcnt + 4 * lane) - pub_expect) < 0) {
+                const long long t0 = clock64();
+                while ((int32_t)(ld_acquire_cta_shared(ringcnt + 4 * lane) - pub_expect) < 0) {
+                  if (*abort_flag) { ok = false; break; }
+                  if (clock64() - t0 > kWaitLimit) {
+                    if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = 0x4000000 | (lane << 8) | r;
+                    ok = false; break;
+                  }
+                }
+              }
+            }
+          }
+          ok = __all_sync(0xffffffffu, ok);
+          if (ok && lane == 0) flag_publish(flags + r, (uint32_t)n + 1);
+        }
+        // rings this (warm-up) chunk did not write hold rows nobody reads: release them right away
+        if (ok && lane == 0)
+          for (int r = last + 1; r < L; r++) flag_publish(flags + r, (uint32_t)n + 1);
       } else {
         // ================= tile group m: MMA issue + epilogues; row = TMEM lane ====================
         // Per layer: [rows of the layer input stored] -> group barrier -> filter-conv GEMM (4 MMAs) ->
@@ -371,9 +475,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           alive = mbar_wait(bar(BAR_HALO + 0), U0(0) & 1, abort_flag, 0x2000000 | (m << 8));      // ring 0 was read for this chunk
           store_row_packed(smem + SmemMap::hbuf, kRows, kHalo + rc, w16);
           const int d0 = p.dil[0];
-          if (rc >= kChunk - d0) store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);
           fence_async_smem();
           mbar_arrive(bar(BAR_HD + 2 * m + 0));
+          if (rc >= kChunk - d0) {
+            store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);
+            ring_row_done(ringcnt + 4 * m);
+          }
         }
 
         for (int l = 0; l < Lc; l++) {
@@ -510,10 +617,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
               mbar_arrive(bar(BAR_HD + 2 * m + sn));
             } else {
               tc_fence_before();                        // last layer of a pruned warm-up chunk: only the ring rows below
+              alive = mbar_wait(bar(BAR_TAIL), tail_idx & 1, abort_flag, 0x2700000 | (m << 8) | l) && alive;
             }
             // history for the next chunk (read by the loader after the chunk-end barrier)
             const int dn = p.dil[l + 1];
-            if (!(SRWN_EXP & 4) && rc >= kChunk - dn) store_row_packed(ring + p.ring_off[l + 1], dn, t % dn, w16);
+            if (rc >= kChunk - dn) {
+              store_row_packed(ring + p.ring_off[l + 1], dn, t % dn, w16);
+              ring_row_done(ringcnt + 4 * m);
+            }
             TRACE(m, l, 11);
           } else {
             tc_fence_before();
@@ -620,6 +731,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         }
       }
       if (do_head) head_idx++;
+      if (Lc < L) tail_idx++;
+      chunk_idx++;
       u0e += (Lc + 1) >> 1; u0o += Lc >> 1; lay_base += Lc;
       tc_fence_before();
       asm volatile("fence.proxy.async;" ::: "memory");   // ring rows (generic stores) -> next chunk's bulk loads
@@ -642,8 +755,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
       p.nll_partial[blockIdx.x] = tot;
     }
   }
-  if (tid == 0 && *abort_flag && atomicCAS(p.err, 0, 1) == 0) {
-    p.err[1] = abort_flag[1]; p.err[2] = chunk_idx; p.err[3] = blockIdx.x;
+  if (tid == 0 && *abort_flag) {     // pinned host memory, read by the next API call (no atomics over the bus: any aborting CTA may win)
+    volatile int* e = p.err;
+    e[1] = abort_flag[1]; e[2] = chunk_idx; e[3] = blockIdx.x;
+    __threadfence_system();
+    e[0] = 1;
   }
   tc_fence_before();
   __syncthreads();
@@ -800,43 +916,64 @@ int fused_pack_weights(srwn_ctx* c, cudaStream_t st) {
   return SRWN_OK;
 }
 
-// ---- work partition: equal-cost contiguous pieces of the (utterance, chunk) line -------------------
-struct Partition { std::vector<Seg> segs; std::vector<int> nseg; int grid; };
+// ---- work partition: equal-cost contiguous pieces of the (utterance, chunk) line, one per team of G CTAs ---------
+struct Partition { std::vector<Seg> segs; std::vector<int> nseg; int teams, G; double cost; };
 
 // warm_cost[k] = cost (in full chunks) of the k warm-up chunks nearest the first output row: a warm-up chunk skips the skip
 // GEMM and the head and runs only the layers inside the dependency cone (k_fused: rsuf[l+1] > dist); a fixed part per chunk
 // (front conv, conditioning loads, chunk barrier) plus a part proportional to the layers it runs
-static bool try_partition(int B, int T, const std::vector<double>& warm_cost, int grid, double budget, Partition* out) {
+static bool try_partition(int B, int T, const std::vector<double>& warm_cost, int teams, double budget, Partition* out) {
   const int warm_chunks = (int)warm_cost.size() - 1;
   const int NC = (T + kChunk - 1) / kChunk;
-  std::vector<Seg> segs((size_t)grid * kMaxSeg);
-  std::vector<int> nseg(grid, 0);
-  int cta = 0;
+  std::vector<Seg> segs((size_t)teams * kMaxSeg);
+  std::vector<int> nseg(teams, 0);
+  int tm = 0;
   double used = 0;
   for (int b = 0; b < B; b++) {
     int c0 = 0;
     while (c0 < NC) {
-      if (cta >= grid) return false;
+      if (tm >= teams) return false;
       const int warm = c0 == 0 ? 0 : std::min(warm_chunks, c0);
       double room = budget - used - warm_cost[warm];
       int take = (int)room;
-      if (take < 1 || nseg[cta] >= kMaxSeg) {
-        if (used == 0 && nseg[cta] < kMaxSeg) take = 1; else { cta++; used = 0; continue; }
+      if (take < 1 || nseg[tm] >= kMaxSeg) {
+        if (used == 0 && nseg[tm] < kMaxSeg) take = 1; else { tm++; used = 0; continue; }
       }
       take = std::min(take, NC - c0);
       Seg s;
       s.b = b; s.t_start = (c0 - warm) * kChunk; s.t_out = c0 * kChunk;
       s.t_end = std::min(T, (c0 + take) * kChunk);
-      segs[(size_t)cta * kMaxSeg + nseg[cta]++] = s;
+      segs[(size_t)tm * kMaxSeg + nseg[tm]++] = s;
       used += take + warm_cost[warm];
       c0 += take;
     }
   }
-  if (out) { out->segs.swap(segs); out->nseg.swap(nseg); out->grid = grid; }
+  if (out) { out->segs.swap(segs); out->nseg.swap(nseg); out->teams = teams; }
   return true;
 }
 
-static Partition make_partition(int B, int T, const std::vector<int>& dilations, int grid) {
+static Partition partition_for(int B, int T, const std::vector<double>& warm_cost, int teams) {
+  const int warm_chunks = (int)warm_cost.size() - 1;
+  const long long total = (long long)B * ((T + kChunk - 1) / kChunk);
+  double lo = (double)total / teams, hi = lo + warm_chunks + 2;
+  Partition best;
+  while (!try_partition(B, T, warm_cost, teams, hi, &best)) hi *= 1.5;
+  for (int it = 0; it < 24; it++) {
+    const double mid = 0.5 * (lo + hi);
+    Partition cand;
+    if (try_partition(B, T, warm_cost, teams, mid, &cand)) { hi = mid; best = cand; } else lo = mid;
+  }
+  best.cost = hi;
+  return best;
+}
+
+// Team size: a team of G CTAs walks its piece as a wavefront, member j+1 about `kLagLayers` layers behind member j, so
+// (a) a piece costs (chunks + warm-up) / G per member, (b) the wavefront fills and drains over (G-1) lags, (c) member 0
+// can only start its next chunk when member G-1 is through the same layer of the previous one: a chunk period is at
+// least G lags.  Larger G shares the mid-utterance warm-up between more CTAs; `force_G` > 0 overrides the choice.
+constexpr double kLagLayers = 1.5;
+constexpr int kMaxTeam = 18;
+static Partition make_partition(int B, int T, const std::vector<int>& dilations, int grid, int force_G) {
   const int NC = (T + kChunk - 1) / kChunk;
   const int L = (int)dilations.size();
   std::vector<int> rsuf(L + 1, 0);
@@ -849,20 +986,27 @@ static Partition make_partition(int B, int T, const std::vector<int>& dilations,
     warm_cost[k + 1] = warm_cost[k] + 0.1 + 0.9 * std::max(lc, 1) / (double)L;    // measured: flat optimum around (0.1, 0.9) .. (0, 1)
   }
   const long long total = (long long)B * NC;
-  if (total < grid) grid = (int)total;
-  double lo = (double)total / grid, hi = lo + warm_chunks + 2;
   Partition best;
-  while (!try_partition(B, T, warm_cost, grid, hi, &best)) hi *= 1.5;
-  for (int it = 0; it < 24; it++) {
-    const double mid = 0.5 * (lo + hi);
-    Partition cand;
-    if (try_partition(B, T, warm_cost, grid, mid, &cand)) { hi = mid; best = cand; } else lo = mid;
+  double best_time = 1e300;
+  for (int G = 1; G <= std::min(kMaxTeam, grid); G++) {
+    if (force_G > 0 && G != std::min(force_G, std::min(kMaxTeam, grid))) continue;
+    int teams = grid / G;
+    if ((long long)teams > total) teams = (int)total;
+    if (teams < 1) continue;
+    Partition cand = partition_for(B, T, warm_cost, teams);
+    const double lag = kLagLayers / L;
+    const double period = std::max(1.0, G * lag);
+    const double time = (cand.cost / G + (G > 1 ? 0.5 : 0.0)) * period + (G - 1) * lag;
+    if (time < best_time) { best_time = time; best = cand; best.G = G; }
   }
   return best;
 }
 
 struct FusedWs {
-  float *cond, *cb; uint8_t* rings; Seg* segs; int* nseg; double* partial; int* err; long long* trace;
+  float *cond, *cb; uint8_t* rings; uint32_t* flags; double* partial;
+#ifdef SRWN_TUNING
+  long long* trace;
+#endif
   float *scales, *means, *xa, *xb;
   size_t bytes;
 };
@@ -874,12 +1018,12 @@ static FusedWs carve_fused(const srwn_ctx* c, int B, int T, void* ws, size_t cap
   const int grid = c->sm_count > 0 ? c->sm_count : 148;
   r.cond = w.take<float>((size_t)B * frames * L * 32);
   r.cb = w.take<float>((size_t)B * frames * (L + 1) * 32);
-  r.rings = w.take<uint8_t>((size_t)grid * ((size_t)c->sum_dilation * 64 + 256));
-  r.segs = w.take<Seg>((size_t)grid * kMaxSeg);
-  r.nseg = w.take<int>(grid);
+  r.rings = w.take<uint8_t>((size_t)grid * ((size_t)c->sum_dilation * 64 + 256));     // one block per team, at most `grid` teams
+  r.flags = w.take<uint32_t>((size_t)grid * kMaxLayers);
   r.partial = w.take<double>(grid);
-  r.err = w.take<int>(4);
+#ifdef SRWN_TUNING
   r.trace = w.take<long long>(7 * kMaxLayers * 12);
+#endif
   if (c->cfg.kind == SRWN_STUDENT) {
     r.scales = w.take<float>(n * c->cfg.num_flows);
     r.means = w.take<float>(n * c->cfg.num_flows);
@@ -888,6 +1032,12 @@ static FusedWs carve_fused(const srwn_ctx* c, int B, int T, void* ws, size_t cap
   }
   r.bytes = w.used;
   return r;
+}
+
+// device copy of the partition: segs [grid][kMaxSeg] | nseg [grid]  (allocated at srwn_create)
+size_t fused_partition_bytes(const srwn_ctx* c) {
+  const size_t grid = c->sm_count > 0 ? c->sm_count : 148;
+  return grid * kMaxSeg * sizeof(Seg) + grid * sizeof(int);
 }
 
 size_t fused_workspace_bytes(const srwn_ctx* c, int op, int B, int T) {
@@ -899,51 +1049,66 @@ static int launch_fused(srwn_ctx* c, const Params& p, int grid, int fp16, cudaSt
   if (!fp16) return srwn_fail(SRWN_ERR_UNSUPPORTED, "the fused kernel is built for fp16 operands only (bf16 misses the 2e-2 logit bound)");
   auto kern = k_fused<TEACHER, true>;
   SRWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemMap::total));
-  kern<<<grid, kThreads, SmemMap::total, st>>>(p);
+  // the members of a team wait on one another's ring flags: the launch must be co-resident (grid <= SM count, one CTA
+  // per SM), which a cooperative launch guarantees or refuses
+  Params pl = p;
+  void* args[] = {&pl};
+  SRWN_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), args, SmemMap::total, st));
   SRWN_LAUNCH_CHECK();
   return SRWN_OK;
 }
 
+// a fused launch that aborted (a bounded wait expired) leaves its error words in pinned host memory; every later call on
+// the handle is refused until srwn_check_async_error has reported it
+static int sticky_error(const srwn_ctx* c) {
+  const volatile int* e = c->h_err;
+  if (e && e[0])
+    return srwn_fail(SRWN_ERR_CUDA, "an earlier fused launch aborted: pipeline wait timed out (code 0x%x, chunk %d, cta %d); "
+                     "results of that call are invalid", e[1], e[2], e[3]);
+  return SRWN_OK;
+}
+
 static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const FusedWs& w, Params* p,
-                   Partition* part, bool first, int fp16, cudaStream_t st) {
+                   int* grid, bool first, int fp16, cudaStream_t st) {
   const int L = c->cfg.n_layers, P = c->cfg.pool_stride, frames = T / P;
   const float* sw = stack_w(c, stack);
+  int rc = sticky_error(c);
+  if (rc) return rc;
   k_cond_fold<<<(B * frames + kCondRows - 1) / kCondRows, 256, 0, st>>>(enc, sw + c->off.cond_k, sw + c->off.cond_b,
                                                                         sw + c->off.front_b, sw + c->off.res_b, w.cb,
                                                                         B * frames, L, c->cfg.cond_channels);
   SRWN_LAUNCH_CHECK();
-  if (first) {
-    // the work partition depends on (B, T) only: built once, kept on the device next to the handle
-    if (!c->d_part || c->part_B != B || c->part_T != T) {
-      *part = make_partition(B, T, c->dilations, c->sm_count);
-      const size_t seg_bytes = (size_t)c->sm_count * kMaxSeg * sizeof(Seg), n_bytes = (size_t)c->sm_count * sizeof(int);
-      if (!c->d_part) SRWN_CUDA(cudaMalloc(&c->d_part, seg_bytes + n_bytes));
-      std::vector<uint8_t> host(seg_bytes + n_bytes, 0);
-      memcpy(host.data(), part->segs.data(), std::min(seg_bytes, part->segs.size() * sizeof(Seg)));
-      memcpy(host.data() + seg_bytes, part->nseg.data(), std::min(n_bytes, part->nseg.size() * sizeof(int)));
-      SRWN_CUDA(cudaMemcpyAsync(c->d_part, host.data(), host.size(), cudaMemcpyHostToDevice, st));
-      SRWN_CUDA(cudaStreamSynchronize(st));     // the staging vector is a host temporary
-      c->part_B = B; c->part_T = T; c->part_grid = part->grid;
-    }
-    part->grid = c->part_grid;
-    SRWN_CUDA(cudaMemsetAsync(w.err, 0, 16, st));
+  const size_t seg_bytes = (size_t)c->sm_count * kMaxSeg * sizeof(Seg), n_bytes = (size_t)c->sm_count * sizeof(int);
+  if (first && (c->part_B != B || c->part_T != T || c->part_team_req != c->team_size)) {
+    // the work partition depends on (B, T) and the team size only: built once, kept on the device next to the handle.
+    // The staging vector belongs to the handle (a copy from pageable memory returns once the bytes are staged).
+    Partition part = make_partition(B, T, c->dilations, c->sm_count, c->team_size);
+    c->part_host.assign(seg_bytes + n_bytes, 0);
+    memcpy(c->part_host.data(), part.segs.data(), std::min(seg_bytes, part.segs.size() * sizeof(Seg)));
+    memcpy(c->part_host.data() + seg_bytes, part.nseg.data(), std::min(n_bytes, part.nseg.size() * sizeof(int)));
+    SRWN_CUDA(cudaMemcpyAsync(c->d_part, c->part_host.data(), c->part_host.size(), cudaMemcpyHostToDevice, st));
+    c->part_B = B; c->part_T = T; c->part_team_req = c->team_size;
+    c->part_teams = part.teams; c->part_G = part.G;
   }
+  *grid = c->part_teams * c->part_G;
+  SRWN_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)c->sm_count * kMaxLayers * sizeof(uint32_t), st));
   memset(p, 0, sizeof(*p));
   const size_t img = stack_image_bytes(c);
   p->packed = (const uint8_t*)c->d_packed + ((size_t)(fp16 ? 1 : 0) * c->n_stacks + stack) * img;
-  p->trace = getenv("SRWN_TRACE") ? w.trace : nullptr;
-  p->trace_chunk = getenv("SRWN_TRACE") ? atoi(getenv("SRWN_TRACE")) : 0;
-  p->dbg = getenv("SRWN_DBG") ? atoi(getenv("SRWN_DBG")) : 0;
-  p->cb = w.cb; p->rings = w.rings; p->err = w.err;
+  p->cb = w.cb; p->rings = w.rings; p->flags = w.flags; p->err = c->h_err; p->G = c->part_G;
   p->segs = reinterpret_cast<const Seg*>(c->d_part);
-  p->nseg = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(c->d_part) + (size_t)c->sm_count * kMaxSeg * sizeof(Seg));
+  p->nseg = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(c->d_part) + seg_bytes);
   p->T = T; p->L = L; p->P = P; p->frames = frames;
   p->O = 4 * c->cfg.num_mixtures; p->M = c->cfg.num_mixtures;
-  p->ring_bytes_per_cta = c->sum_dilation * 64 + 256;
+  p->ring_bytes_per_team = c->sum_dilation * 64 + 256;
   int off = 0;
   for (int l = 0; l < L; l++) { p->dil[l] = c->dilations[l]; p->ring_off[l] = off; off += c->dilations[l] * 64; }
   p->rsuf[L] = 0;
   for (int l = L - 1; l >= 0; l--) p->rsuf[l] = p->rsuf[l + 1] + c->dilations[l];
+#ifdef SRWN_TUNING
+  p->trace = getenv("SRWN_TRACE") ? w.trace : nullptr;
+  p->trace_chunk = getenv("SRWN_TRACE") ? atoi(getenv("SRWN_TRACE")) : 0;
+#endif
   return SRWN_OK;
 }
 
@@ -954,18 +1119,18 @@ int run_teacher_fused_bf16(srwn_ctx* c, const float* x_in, const float* enc, con
   FusedWs w = carve_fused(c, B, T, ws, ws_bytes);
   if (!ws || w.bytes > ws_bytes) return srwn_fail(SRWN_ERR_WORKSPACE, "workspace too small: need %zu bytes", w.bytes);
   Params p;
-  Partition part;
-  int rc = prepare(c, 0, enc, B, T, w, &p, &part, true, fp16, st);
+  int grid = 0;
+  int rc = prepare(c, 0, enc, B, T, w, &p, &grid, true, fp16, st);
   if (rc) return rc;
   p.x_in = x_in; p.x_scored = x_scored; p.logits_out = logits_out; p.nll_out = nll_out;
   p.nll_partial = (x_scored && nll_sum) ? w.partial : nullptr;
   {
-    ProfScope prof(c, st, fp16 ? "k_fused<teacher,fp16>" : "k_fused<teacher,bf16>", 1);
-    rc = launch_fused<true>(c, p, part.grid, fp16, st);
+    ProfScope prof(c, st, "k_fused<teacher,fp16>", 1);
+    rc = launch_fused<true>(c, p, grid, fp16, st);
     if (rc) return rc;
   }
   if (p.nll_partial) {
-    k_sum_partials<<<1, 32, 0, st>>>(w.partial, part.grid, nll_sum);
+    k_sum_partials<<<1, 32, 0, st>>>(w.partial, grid, nll_sum);
     SRWN_LAUNCH_CHECK();
   }
   return SRWN_OK;
@@ -980,36 +1145,38 @@ int run_student_fused_bf16(srwn_ctx* c, const float* z, const float* enc, float*
   const size_t n = (size_t)B * T;
   const int F = c->cfg.num_flows;
   const float* xin = z;
-  Partition part;
+  int grid = 0;
   for (int f = 0; f < F; f++) {                     // model.py:509-513: flows are strictly sequential
     Params p;
-    int rc = prepare(c, f, enc, B, T, w, &p, &part, f == 0, fp16, st);
+    int rc = prepare(c, f, enc, B, T, w, &p, &grid, f == 0, fp16, st);
     if (rc) return rc;
     float* xout = (f == F - 1 && x_last) ? x_last : ((f & 1) ? w.xb : w.xa);
     p.x_in = xin; p.scale_out = w.scales + (size_t)f * n; p.mean_out = w.means + (size_t)f * n; p.x_out = xout;
-    ProfScope prof(c, st, fp16 ? "k_fused<student,fp16>" : "k_fused<student,bf16>", 1);
-    rc = launch_fused<false>(c, p, part.grid, fp16, st);
+    ProfScope prof(c, st, "k_fused<student,fp16>", 1);
+    rc = launch_fused<false>(c, p, grid, fp16, st);
     if (rc) return rc;
     xin = xout;
   }
   return run_flow_compose(z, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
 }
 
-// reads the device-side abort flag of the last fused launch (synchronises the stream)
+// reads (and clears) the abort words of the fused launches issued so far; synchronises the stream
 int fused_check_error(void* ws, size_t ws_bytes, const srwn_ctx* c, int B, int T, cudaStream_t st) {
-  FusedWs w = carve_fused(c, B, T, ws, ws_bytes);
-  int flag = 0;
+  (void)ws; (void)ws_bytes; (void)B; (void)T;
   SRWN_CUDA(cudaStreamSynchronize(st));
-  SRWN_CUDA(cudaMemcpy(&flag, w.err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) {
-    int info[4] = {0, 0, 0, 0};
-    cudaMemcpy(info, w.err, sizeof(info), cudaMemcpyDeviceToHost);
-    return srwn_fail(SRWN_ERR_CUDA, "fused kernel aborted: pipeline wait timed out (code 0x%x, chunk %d, cta %d)",
-                     info[1], info[2], info[3]);
+  volatile int* e = c->h_err;
+  if (e && e[0]) {
+    const int code = e[1], chunk = e[2], cta = e[3];
+    e[0] = 0; e[1] = 0; e[2] = 0; e[3] = 0;
+    return srwn_fail(SRWN_ERR_CUDA, "fused kernel aborted: pipeline wait timed out (code 0x%x, chunk %d, cta %d)", code, chunk, cta);
   }
   return SRWN_OK;
 }
 
+// partition chosen for the last fused call (tests, bench records): teams x CTAs per team
+void fused_last_partition(const srwn_ctx* c, int* teams, int* G) { *teams = c->part_teams; *G = c->part_G; }
+
+#ifdef SRWN_TUNING
 // tuning aid: copies the clock64 trace of CTA 0 (see SRWN_TRACE) to the host
 extern "C" int srwn_debug_read_trace(srwn_handle_t h, int32_t B, int32_t T, void* ws, size_t ws_bytes,
                                      long long* out, int32_t count) {
@@ -1111,3 +1278,4 @@ extern "C" int srwn_debug_mma_bench(long long* host_out24) {
   cudaFree(d);
   return SRWN_OK;
 }
+#endif  // SRWN_TUNING

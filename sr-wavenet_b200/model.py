@@ -74,6 +74,16 @@ class _Engine(object):
         _lib.check(self.lib.srwn_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(name)))
         return ms.value, n.value, name.value.decode()
 
+    def set_team_size(self, ctas_per_team):
+        """CTAs per team of the fused kernel (0 = chosen per (B, T)); results do not depend on it."""
+        _lib.check(self.lib.srwn_set_team_size(self.h, int(ctas_per_team)))
+
+    def last_partition(self):
+        """(teams, CTAs per team) of the last fused call."""
+        t, g = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(self.lib.srwn_last_partition(self.h, ctypes.byref(t), ctypes.byref(g)))
+        return t.value, g.value
+
     def check_async(self, op, B, T, precision):
         """Synchronises and raises if the last fused launch aborted on the device."""
         ws, wsn = self.workspace(op, B, T, precision)

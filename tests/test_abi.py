@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), "libsrwn.so does not export %s" % n
         assert n in _lib.SIGNATURES, "ctypes binding misses %s" % n
-    assert lib.srwn_abi_version() == 5
+    assert lib.srwn_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_binding_has_no_undeclared_symbols(lib):
@@ -94,3 +94,11 @@ def test_header_is_plain_c(tmp_path):
                     str(src), "-o", str(exe), "-L", libdir, "-l:libsrwn.so", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == _lib.ABI_VERSION and int(out[1]) == len(_declared_symbols())
+
+
+def test_product_library_exports_only_the_header(lib):
+    """No tuning / debug entry point ships in the product library (those build only with -DSRWN_TUNING)."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r"\bT (srwn_[a-z0-9_]+)$", out, flags=re.M)))
+    assert exported == _declared_symbols()
