@@ -159,6 +159,66 @@ def cpu_port_samples_per_s(B, T, repeats, warm=1):
     return B * T / min(times), B * T / (sum(times) / len(times)), torch.get_num_threads(), times
 
 
+def quick_measure(srwn, synth, shard, workload, B, T, rank, steps=3, warmup=3):
+    """A short device-timed run of another BASELINE configuration inside the same job (inputs resident in HBM, CUDA events
+    per step, MAX over ranks, whole-job samples/s).  Used for the `also` block: the strong split of configs[1] / [3] and
+    the distillation step of configs[4], whose all-reduce is bracketed with its own CUDA events."""
+    import torch
+    dil, P = synth.DEFAULT_DILATIONS, 128
+    enc = torch.from_numpy(synth.synthetic_encoding(B, T // P, seed=4321 + rank)).cuda()
+    extra = {}
+    if workload in ("student", "distill"):
+        teacher = None
+        if workload == "distill":
+            teacher = srwn.WaveNetAutoEncoder(T, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=P)
+            teacher.set_weights(synth.make_teacher_weights(dil))
+            truth = torch.from_numpy(synth.synthetic_audio(B, T, seed=1234 + rank * B)).cuda()
+        model = srwn.ParallelWaveNet(T, 0, dil, teacher, num_flows=4, skip_channels=128, latent_channels=32, pool_stride=P,
+                                     alpha=0.25, beta=1.0, gamma=1.0, learning_rate=1e-4)
+        model.set_weights(synth.make_student_weights(dil, 4))
+        z = torch.from_numpy(synth.logistic_noise(B, T, seed=777 + rank)).cuda()
+        if workload == "distill":
+            if shard.is_distributed():
+                model._coll_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            step = lambda: model.train_fast(None, z, truth, enc)
+        else:
+            step = lambda: model.generate(None, z, enc, precision="fp16")
+    else:
+        model = srwn.WaveNetAutoEncoder(T, 0, 5, dil, skip_channels=128, latent_channels=32, pool_stride=P)
+        model.set_weights(synth.make_teacher_weights(dil))
+        if workload == "teacher_nll":
+            x = torch.from_numpy(synth.synthetic_audio(B, T, seed=1234 + rank * B)).cuda()
+            step = lambda: model.nll(x, enc, precision="fp16")
+        else:
+            u1, u2 = (torch.from_numpy(a).cuda() for a in synth.sampler_uniforms(B, T, seed=999 + rank))
+            step = lambda: model.generate(enc, u1=u1, u2=u2, precision="fp16")
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    shard.barrier()
+    ms, coll = [], []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+        if getattr(model, "_coll_events", None):
+            coll.append(model._coll_events[0].elapsed_time(model._coll_events[1]))
+    shard.barrier()
+    total_max, coll_max = shard.reduce_scalars([sum(ms), sum(coll)], "max")
+    units, = shard.reduce_scalars([float(B * T * steps)], "sum")
+    out = {"batch_per_gpu": B, "samples_per_utterance": T, "ms_per_step": total_max / steps, "value": units / (total_max * 1e-3)}
+    if coll:
+        out["allreduce_us"] = 1e3 * coll_max / steps
+    if workload in ("teacher_nll", "student"):
+        out["partition_teams_x_ctas"] = list(model._eng.last_partition())
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU port of the reference path on the host cores (rank 0 only)."""
     if rank != 0:
@@ -193,6 +253,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config)")
     ap.add_argument("--length", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra configurations of the `also` block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -319,6 +380,7 @@ def main():
         model._eng.check_async(srwn._lib.OP_TEACHER_NLL if args.workload == "teacher_nll" else srwn._lib.OP_STUDENT_FORWARD,
                                B, T, srwn._lib.PRECISIONS[prec])
     launches = srwn._lib.launch_count() - launches0
+    partition = list(model._eng.last_partition()) if args.workload in ("teacher_nll", "student") and prec == "fp16" else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
     shard.barrier()
@@ -375,6 +437,20 @@ def main():
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=kern_name,
                 launches_per_step=kern_launches, kernel_ms=k_ms, peak_source=peaks["source"])
 
+    # the other BASELINE configurations in the same job (device-timed, short): the STRONG split of configs[1] (32 / N
+    # utterances per GPU) and configs[3] (256 / N), the per-GPU share of configs[2], and the configs[4] distillation step
+    # (4 x 64000 per GPU) with the NCCL all-reduce of its [gradient | loss | power] bucket timed separately
+    also = None
+    if args.workload == "teacher_nll" and not args.no_also and not (args.batch or args.length):
+        del model
+        torch.cuda.empty_cache()
+        also = {
+            "teacher_nll_strong_32_total": quick_measure(srwn, synth, shard, "teacher_nll", max(1, 32 // world), 64000, rank),
+            "generate_strong_256_total": quick_measure(srwn, synth, shard, "generate", max(1, 256 // world), 16000, rank, steps=2, warmup=1),
+            "student_8_per_gpu": quick_measure(srwn, synth, shard, "student", 8, 64000, rank),
+            "distill_4_per_gpu": quick_measure(srwn, synth, shard, "distill", 4, 64000, rank),
+        }
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "teacher_nll":
         best, mean, cores, times = cpu_port_samples_per_s(4, 64000, repeats=3)
@@ -396,12 +472,14 @@ def main():
             "data": "synthetic",
             "config": {"workload": names[args.workload], "batch_per_gpu": B, "global_batch": B * world,
                        "samples_per_utterance": T, "layers": len(dil), "parallelism": "batch-sharded x%d" % world,
-                       "l2": "flushed between timed iterations (256 MiB write)", "precision_path": prec},
+                       "l2": "flushed between timed iterations (256 MiB write)", "precision_path": prec,
+                       "fused_partition_teams_x_ctas": partition},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu_baseline,
+            "also": also,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

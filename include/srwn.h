@@ -118,6 +118,9 @@ int srwn_check_async_error(srwn_handle_t h, int32_t op, int32_t B, int32_t T, in
  * over chunks and layers, handing the per-layer history rings from CTA to CTA).  0 (default) = chosen per (B, T).
  * Results do not depend on it.  srwn_last_partition reports the choice of the last fused call. */
 int srwn_set_team_size(srwn_handle_t h, int32_t ctas_per_team);
+/* How many SM clocks a pipeline wait inside the fused kernel may spin before the launch aborts (default 1e9, about half a
+ * second; every wait is bounded so that a lost signal surfaces as SRWN_ERR_CUDA instead of a hung GPU). */
+int srwn_set_wait_limit(srwn_handle_t h, int64_t clocks);
 int srwn_last_partition(srwn_handle_t h, int32_t* teams, int32_t* ctas_per_team);
 /* 1 if `op` (enum srwn_op) is built for `precision` with this handle's configuration, else 0. */
 int srwn_supports(srwn_handle_t h, int32_t op, int32_t precision);
@@ -158,6 +161,16 @@ int srwn_student_forward(srwn_handle_t h, const float* z, const float* enc, floa
                          float* s_tot, float* mu_tot, float* x_last,
                          int32_t B, int32_t T, int32_t precision,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* generate(sess, noise, encoding) (model.py:570-576) with the logistic noise of student.py:104 / :172 drawn ON THE DEVICE:
+ * z[b,t] = log u - log(1-u), u = Philox4x32-10(seed; stream_id; b*T + t) in (0,1).  With SRWN_FP16 the fused flow kernel
+ * evaluates the draw in place (front conv taps, affine head, composition): no noise tensor is read.  z_out (optional)
+ * receives the draws, so srwn_student_forward(z_out, ...) reproduces the call.  srwn_random_logistic fills the same
+ * values; srwn_random_uniform serves the mixture sampler's uniforms (ops.py:187, 196). */
+int srwn_student_sample(srwn_handle_t h, uint64_t seed, uint64_t stream_id, const float* enc, float* out,
+                        float* s_tot, float* mu_tot, float* x_last, float* z_out, int32_t B, int32_t T,
+                        int32_t precision, void* workspace, size_t workspace_bytes, void* stream);
+int srwn_random_logistic(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
+int srwn_random_uniform(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float lo, float hi, void* stream);
 
 /* ---- student distillation step (model.py:356-401, student.py:107 train_fast) ------------------
  * The reference builds one graph: student forward, loss (teacher cross-entropy of the student's
@@ -186,6 +199,20 @@ int srwn_student_backward(srwn_handle_t h, const float* z, const float* enc, con
                           void* workspace, size_t workspace_bytes, void* stream);
 int srwn_mol_loss_grad(const float* x, const float* l, float* dx, float* nll_out,
                        int32_t B, int32_t T, int32_t M, void* stream);
+/* The whole device weight arena (layout of srwn_weight_offset; count = srwn_param_count) copied to (to_handle = 0) or from
+ * (to_handle = 1) a DEVICE buffer: data-parallel replicas broadcast rank 0's weights through it before the first step. */
+int srwn_weights_flat(srwn_handle_t h, float* buffer, int64_t count, int32_t to_handle, void* stream);
+/* {loss, power_loss} of model.py:378-379 as fp32 device values: out2[0] = (beta*sums[0] - alpha*sums[1] + *power) * inv_norm,
+ * out2[1] = *power (sums from srwn_distill_loss_grad, power from srwn_stft_power_loss). */
+int srwn_distill_finish(const double* sums, const double* power, float alpha, float beta, float inv_norm,
+                        float* out2, void* stream);
+/* tf.clip_by_global_norm(grads, clip_norm) in place (model.py:385; ParallelWaveNet.train clips per example, model.py:603-632).
+ * scratch: one device float. */
+int srwn_clip_by_global_norm(float* grads, int64_t n, float clip_norm, float* scratch, void* stream);
+/* y += a * x (host-side averaging of per-example gradients in model.py:621, kept on the device). */
+int srwn_axpy(float* y, const float* x, float a, int64_t n, void* stream);
+/* per_example[b] = sum_t (log s_tot[b,t] + 2): the entropy term of model.py:356 per example (getEntropy, model.py:578-600). */
+int srwn_entropy(const float* s_tot, double* per_example, int32_t B, int32_t T, void* stream);
 int srwn_adam_step(srwn_handle_t h, const float* grads, float* m, float* v, float* scratch,
                    float clip_norm, float lr, float beta1, float beta2, float eps, int32_t step,
                    void* stream);

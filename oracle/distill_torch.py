@@ -116,7 +116,7 @@ def loss_and_grads(weights, z, truth, enc, teacher_logits, dilations, pool_strid
 def adam_reference(w, g, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8, clip=1.0, gnorm=None):
     """tf.clip_by_global_norm + tf.train.AdamOptimizer._apply_dense (model.py:382-401), float64 NumPy."""
     gn = math.sqrt(sum(float((x.astype(np.float64) ** 2).sum()) for x in g)) if gnorm is None else gnorm
-    scale = clip / max(gn, clip)
+    scale = clip / max(gn, clip) if clip else 1.0       # clip=None: gradients arrive clipped (model.py:603-632)
     lr_t = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
     out = []
     for wi, gi, mi, vi in zip(w, g, m, v):

@@ -52,6 +52,7 @@ SIGNATURES = {
     "srwn_commit_weights": (ctypes.c_int, [_vp, _vp]),
     "srwn_set_profiling": (ctypes.c_int, [_vp, _i32]),
     "srwn_set_team_size": (ctypes.c_int, [_vp, _i32]),
+    "srwn_set_wait_limit": (ctypes.c_int, [_vp, _i64]),
     "srwn_last_partition": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "srwn_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32),
                                            ctypes.POINTER(ctypes.c_char_p)]),
@@ -62,6 +63,14 @@ SIGNATURES = {
     "srwn_teacher_nll": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "srwn_teacher_generate": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "srwn_student_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_student_sample": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_random_logistic": (ctypes.c_int, [_fp, _i64, ctypes.c_uint64, ctypes.c_uint64, _vp]),
+    "srwn_random_uniform": (ctypes.c_int, [_fp, _i64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_float, ctypes.c_float, _vp]),
+    "srwn_weights_flat": (ctypes.c_int, [_vp, _fp, _i64, _i32, _vp]),
+    "srwn_distill_finish": (ctypes.c_int, [_vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _fp, _vp]),
+    "srwn_clip_by_global_norm": (ctypes.c_int, [_fp, _i64, ctypes.c_float, _fp, _vp]),
+    "srwn_axpy": (ctypes.c_int, [_fp, _fp, ctypes.c_float, _i64, _vp]),
+    "srwn_entropy": (ctypes.c_int, [_fp, _vp, _i32, _i32, _vp]),
     "srwn_param_count": (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
     "srwn_weight_offset": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "srwn_student_forward_train": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _vp, _sz, _vp]),

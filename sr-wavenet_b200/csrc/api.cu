@@ -185,7 +185,7 @@ extern "C" int srwn_create(const srwn_config_t* cfg, srwn_handle_t* out) {
   c->d_weights = nullptr; c->d_dilations = nullptr; c->d_queue_off = nullptr;
   c->d_packed = nullptr; c->packed_bytes = 0; c->d_ar_packed = nullptr;
   c->d_part = nullptr; c->part_B = c->part_T = c->part_teams = c->part_G = 0; c->part_team_req = -1;
-  c->team_size = 0; c->h_err = nullptr;
+  c->team_size = 0; c->h_err = nullptr; c->wait_limit_clocks = 1000000000LL;
   c->profiling = 0; c->prof_launches = 0; c->prof_name = "";
   c->prof_ev[0] = c->prof_ev[1] = nullptr;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -325,7 +325,7 @@ extern "C" int srwn_commit_weights(srwn_handle_t h, void* stream) {
 }
 
 // ---- workspace sizing ---------------------------------------------------------------
-struct F32Ws { float *h0, *h1, *skip, *cond, *logits, *scales, *means, *xa, *xb; size_t bytes; };
+struct F32Ws { float *h0, *h1, *skip, *cond, *logits, *scales, *means, *xa, *xb, *z; size_t bytes; };
 
 static F32Ws carve_f32(const srwn_ctx* c, int op, int B, int T, void* ws, size_t cap, bool need_logits) {
   WsCarver w(ws, cap);
@@ -343,6 +343,7 @@ static F32Ws carve_f32(const srwn_ctx* c, int op, int B, int T, void* ws, size_t
     r.means = w.take<float>(n * c->cfg.num_flows);
     r.xa = w.take<float>(n);
     r.xb = w.take<float>(n);
+    r.z = w.take<float>(n);                       // on-device noise of srwn_student_sample
   }
   r.bytes = w.used;
   return r;
@@ -361,6 +362,12 @@ extern "C" int srwn_set_team_size(srwn_handle_t h, int32_t ctas_per_team) {
   if (!h) return srwn_fail(SRWN_ERR_INVALID, "srwn_set_team_size: null handle");
   if (ctas_per_team < 0 || ctas_per_team > 64) return srwn_fail(SRWN_ERR_INVALID, "team size must be 0 (automatic) .. 64");
   h->team_size = ctas_per_team;
+  return SRWN_OK;
+}
+
+extern "C" int srwn_set_wait_limit(srwn_handle_t h, int64_t clocks) {
+  if (!h || clocks < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_set_wait_limit: bad argument");
+  h->wait_limit_clocks = clocks;
   return SRWN_OK;
 }
 
@@ -519,25 +526,28 @@ extern "C" int srwn_teacher_generate(srwn_handle_t h, const float* enc, const fl
 }
 
 // ---- student --------------------------------------------------------------------------
-extern "C" int srwn_student_forward(srwn_handle_t h, const float* z, const float* enc, float* out,
-                                    float* s_tot, float* mu_tot, float* x_last, int32_t B, int32_t T,
-                                    int32_t precision, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
-  if (!h || !z || !enc || !out) return srwn_fail(SRWN_ERR_INVALID, "srwn_student_forward: null argument");
+// z supplied (noise.on == 0) or drawn on the device (student.py:104); z_out optionally receives the draws
+static int student_forward_impl(srwn_handle_t h, const float* z, NoiseSpec noise, float* z_out, const float* enc, float* out,
+                                float* s_tot, float* mu_tot, float* x_last, int32_t B, int32_t T,
+                                int32_t precision, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (h->cfg.kind != SRWN_STUDENT) return srwn_fail(SRWN_ERR_INVALID, "not a student handle");
   int rc = check_bt(h, B, T);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   if (precision == SRWN_BF16) return reject_bf16();
   if (precision == SRWN_FP16)
-    return run_student_fused_bf16(h, z, enc, out, s_tot, mu_tot, x_last, B, T, precision == SRWN_FP16,
-                                  workspace, workspace_bytes, st);
+    return run_student_fused_bf16(h, z, noise, z_out, enc, out, s_tot, mu_tot, x_last, B, T, 1, workspace, workspace_bytes, st);
   if (precision != SRWN_FP32) return srwn_fail(SRWN_ERR_INVALID, "unknown precision %d", precision);
   F32Ws w = carve_f32(h, SRWN_OP_STUDENT_FORWARD, B, T, workspace, workspace_bytes, false);
   if (!workspace || w.bytes > workspace_bytes)
     return srwn_fail(SRWN_ERR_WORKSPACE, "workspace too small: need %zu bytes", w.bytes);
   const size_t n = (size_t)B * T;
   const int F = h->cfg.num_flows;
+  if (noise.on) {                                     // the layer-at-a-time path reads the noise as a tensor
+    float* zbuf = z_out ? z_out : w.z;
+    rc = run_random_fill(zbuf, (int64_t)n, noise.seed, noise.stream, 1, 0.f, 1.f, st);
+    if (rc) return rc;
+    z = zbuf; noise.on = 0; z_out = nullptr;
+  }
   const float* xin = z;
   for (int f = 0; f < F; f++) {                       // model.py:509-513, strictly sequential
     float* hf = nullptr;
@@ -549,7 +559,24 @@ extern "C" int srwn_student_forward(srwn_handle_t h, const float* z, const float
     if (rc) return rc;
     xin = xout;
   }
-  return run_flow_compose(z, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
+  return run_flow_compose(z, noise, z_out, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
+}
+
+extern "C" int srwn_student_forward(srwn_handle_t h, const float* z, const float* enc, float* out,
+                                    float* s_tot, float* mu_tot, float* x_last, int32_t B, int32_t T,
+                                    int32_t precision, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  if (!h || !z || !enc || !out) return srwn_fail(SRWN_ERR_INVALID, "srwn_student_forward: null argument");
+  return student_forward_impl(h, z, NoiseSpec{0, 0, 0}, nullptr, enc, out, s_tot, mu_tot, x_last, B, T, precision,
+                              workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int srwn_student_sample(srwn_handle_t h, uint64_t seed, uint64_t stream_id, const float* enc, float* out,
+                                   float* s_tot, float* mu_tot, float* x_last, float* z_out, int32_t B, int32_t T,
+                                   int32_t precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !enc || !out) return srwn_fail(SRWN_ERR_INVALID, "srwn_student_sample: null argument");
+  return student_forward_impl(h, nullptr, NoiseSpec{seed, stream_id, 1}, z_out, enc, out, s_tot, mu_tot, x_last, B, T,
+                              precision, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // ---- student distillation step (model.py:356-401) ----------------------------------------------
@@ -635,6 +662,40 @@ extern "C" int srwn_distill_loss_grad(const float* z, const float* s_tot, const 
   if (B < 1 || T < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_distill_loss_grad: bad B/T");
   return run_distill_loss_grad(z, s_tot, mu_tot, nll, d_ce, d_pow, alpha, beta, inv_norm, d_pre, d_s, sums, B, T,
                                (cudaStream_t)stream);
+}
+
+extern "C" int srwn_weights_flat(srwn_handle_t h, float* buffer, int64_t count, int32_t to_handle, void* stream) {
+  if (!h || !buffer) return srwn_fail(SRWN_ERR_INVALID, "srwn_weights_flat: null argument");
+  const int64_t n = (int64_t)h->n_stacks * (int64_t)h->stack_floats;
+  if (count != n) return srwn_fail(SRWN_ERR_INVALID, "srwn_weights_flat: count %lld != srwn_param_count %lld", (long long)count, (long long)n);
+  if (to_handle) {
+    SRWN_CUDA(cudaMemcpyAsync(h->d_weights, buffer, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    h->device_dirty = true;        // host mirror and packed operand images are stale until srwn_commit_weights
+  } else {
+    SRWN_CUDA(cudaMemcpyAsync(buffer, h->d_weights, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return SRWN_OK;
+}
+
+extern "C" int srwn_distill_finish(const double* sums, const double* power, float alpha, float beta, float inv_norm,
+                                   float* out2, void* stream) {
+  if (!sums || !power || !out2) return srwn_fail(SRWN_ERR_INVALID, "srwn_distill_finish: null argument");
+  return run_distill_finish(sums, power, alpha, beta, inv_norm, out2, (cudaStream_t)stream);
+}
+
+extern "C" int srwn_clip_by_global_norm(float* grads, int64_t n, float clip_norm, float* scratch, void* stream) {
+  if (!grads || !scratch || n < 1 || !(clip_norm > 0.f)) return srwn_fail(SRWN_ERR_INVALID, "srwn_clip_by_global_norm: bad argument");
+  return run_clip_by_global_norm(grads, n, clip_norm, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int srwn_axpy(float* y, const float* x, float a, int64_t n, void* stream) {
+  if (!y || !x || n < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_axpy: bad argument");
+  return run_axpy(y, x, a, n, (cudaStream_t)stream);
+}
+
+extern "C" int srwn_entropy(const float* s_tot, double* per_example, int32_t B, int32_t T, void* stream) {
+  if (!s_tot || !per_example || B < 1 || T < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_entropy: bad argument");
+  return run_entropy(s_tot, per_example, B, T, (cudaStream_t)stream);
 }
 
 extern "C" int srwn_adam_step(srwn_handle_t h, const float* grads, float* m, float* v, float* scratch, float clip_norm,

@@ -75,6 +75,7 @@ struct srwn_ctx {
   int part_B, part_T, part_team_req, part_teams, part_G;
   std::vector<uint8_t> part_host;     // host staging of d_part
   int team_size;                      // srwn_set_team_size: CTAs per team of the fused kernel, 0 = chosen per (B, T)
+  long long wait_limit_clocks;        // srwn_set_wait_limit: how long a fused-kernel pipeline wait may spin before aborting
   int* h_err;                         // pinned, mapped: abort words of the fused kernel [flag, code, chunk, cta]
   void* d_ar_packed;                  // fragment-ordered fp16 weights of the tensor-core generation kernel (built at commit)
   // optional timing of the dominant kernel(s) of the last call (srwn_set_profiling)
@@ -109,6 +110,9 @@ struct WsCarver {
   }
 };
 
+// on-device noise (philox.cuh): element i of (seed, stream); `on` = 0 means the caller supplied the tensor
+struct NoiseSpec { unsigned long long seed, stream; int on; };
+
 // ---- kernel entry points implemented across translation units ---------------------
 // stack_f32.cu
 int run_stack_f32(srwn_ctx* c, int stack, const float* xin, const float* enc, int B, int T,
@@ -118,8 +122,10 @@ int run_teacher_head_f32(srwn_ctx* c, const float* skip, float* logits, int B, i
                          cudaStream_t st);
 int run_flow_head_f32(srwn_ctx* c, int stack, const float* h, const float* xin, float* scale,
                       float* mean, float* xout, int B, int T, cudaStream_t st);
-int run_flow_compose(const float* z, const float* scales, const float* means, int F,
+int run_flow_compose(const float* z, NoiseSpec noise, float* z_out, const float* scales, const float* means, int F,
                      float* out, float* s_tot, float* mu_tot, int64_t n, cudaStream_t st);
+// random.cu
+int run_random_fill(float* out, int64_t n, uint64_t seed, uint64_t stream, int logistic, float lo, float hi, cudaStream_t st);
 // mol.cu
 int run_mol_loss(const float* x, const float* l, float* nll_out, float* nll_sum,
                  int B, int T, int M, cudaStream_t st);
@@ -137,6 +143,10 @@ int run_student_forward_train(srwn_ctx* c, const float* z, const float* enc, flo
 int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const float* d_pre, const float* d_s_extra,
                          float* grads, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st);
 int run_mol_nll_grad(const float* x, const float* l, float* dx, float* nll, int B, int T, int M, cudaStream_t st);
+int run_distill_finish(const double* sums, const double* power, float alpha, float beta, float inv_norm, float* out2, cudaStream_t st);
+int run_clip_by_global_norm(float* grads, int64_t n, float clip, float* scratch1, cudaStream_t st);
+int run_axpy(float* y, const float* x, float a, int64_t n, cudaStream_t st);
+int run_entropy(const float* s_tot, double* per_example, int B, int T, cudaStream_t st);
 int run_adam(srwn_ctx* c, const float* grads, float* m, float* v, float* scratch1, float clip, float lr, float b1, float b2,
              float eps, int step, cudaStream_t st);
 // ar_mma.cu
@@ -155,7 +165,7 @@ int run_teacher_fused_bf16(srwn_ctx* c, const float* x_in, const float* enc,
                            const float* x_scored, float* nll_out, float* nll_sum,
                            float* logits_out, int B, int T, int fp16, void* ws, size_t ws_bytes,
                            cudaStream_t st);
-int run_student_fused_bf16(srwn_ctx* c, const float* z, const float* enc, float* out,
+int run_student_fused_bf16(srwn_ctx* c, const float* z, NoiseSpec noise, float* z_out, const float* enc, float* out,
                            float* s_tot, float* mu_tot, float* x_last, int B, int T, int fp16,
                            void* ws, size_t ws_bytes, cudaStream_t st);
 int fused_check_error(void* ws, size_t ws_bytes, const srwn_ctx* c, int B, int T, cudaStream_t st);

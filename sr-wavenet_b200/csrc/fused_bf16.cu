@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "mol.cuh"
 #include "umma.cuh"
+#include "philox.cuh"
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
@@ -67,6 +68,8 @@ struct Params {
   const int* nseg;            // [teams]
   uint32_t* flags;            // [teams][kMaxLayers]: flags[l] = number of chunks of the piece whose ring l is published
   int G;                      // CTAs per team
+  long long wait_limit;       // clocks a pipeline wait may spin before it raises the abort flag
+  NoiseSpec noise;            // student, first flow: x_in[b][t] is the logistic draw (seed, stream, b*T + t) instead of a tensor
   float* logits_out;          // teacher, optional [B][T][O]
   float* nll_out;             // teacher, optional [B][T]
   double* nll_partial;        // teacher, optional [grid]
@@ -186,12 +189,11 @@ __device__ __forceinline__ void store_row_packed(uint8_t* buf, int rows_per_kc, 
 constexpr int kThreads = 14 * 32;
 constexpr int kLoadWarp = 0;
 constexpr int kPubWarp = 13;
-constexpr long long kWaitLimit = 1000000000LL;       // clocks before a stuck wait raises the abort flag
 
 // ---- cross-CTA ring hand-off ------------------------------------------------------------------------
 // consumer: chunk n waits until flags[l] >= n (rings of chunks 0..n-1 published), then orders its bulk loads (async proxy)
 // after the acquire
-__device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, volatile int* abort_flag, const int* gerr, int code) {
+__device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, volatile int* abort_flag, const int* gerr, int code, long long limit) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
   if (v < need) {
@@ -203,7 +205,7 @@ __device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, vola
       if (v >= need) break;
       if (*abort_flag) return false;
       if (((++spins) & 1023) == 0 && *reinterpret_cast<const volatile int*>(gerr)) return false;   // another CTA aborted (host memory: polled rarely)
-      if (clock64() - t0 > kWaitLimit) {
+      if (clock64() - t0 > limit) {
         if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = code;
         return false;
       }
@@ -332,12 +334,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           TRACE(6, l, 0);
           // halo rows of layer l: inputs at t0-d .. t0-1 (zeros before the segment start).  The halo goes first:
           // its condition (filter-conv MMAs of layer l-2 retired) holds earlier than the weight stage's.
-          if (l >= 2 && !mbar_wait(bar(BAR_G1 + s), (use - 1) & 1, abort_flag, 0x1100000 | l)) break;   // G1 of layer l-2 retired
+          if (l >= 2 && !mbar_wait(bar(BAR_G1 + s), (use - 1) & 1, abort_flag, 0x1100000 | l, p.wait_limit)) break;   // G1 of layer l-2 retired
           TRACE(6, l, 2);
           // ring l of the previous chunk of the piece (written by another member of the team unless G == 1); also taken
           // at an utterance start, where the rows are not read: this chunk may overwrite the ring only after chunk n-1
           // has read it, which its publication implies
-          if (n > 0 && !flag_wait(flags + l, (uint32_t)n, abort_flag, p.err, 0x1200000 | l)) break;
+          if (n > 0 && !flag_wait(flags + l, (uint32_t)n, abort_flag, p.err, 0x1200000 | l, p.wait_limit)) break;
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_HALO + s));
           }
-          if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag, 0x1000000 | l)) break;
+          if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag, 0x1000000 | l, p.wait_limit)) break;
           if (lane == 0) {
             mbar_expect_tx(bar(BAR_WFULL + s), layer_bytes);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         // a pruned warm-up chunk writes ring Lc behind its last layer without reading it: the write has to come after
         // chunk n-1's rows of the same ring
         if (Lc < L && !*abort_flag) {
-          const bool ok = n == 0 || flag_wait(flags + Lc, (uint32_t)n, abort_flag, p.err, 0x1300000 | Lc);
+          const bool ok = n == 0 || flag_wait(flags + Lc, (uint32_t)n, abort_flag, p.err, 0x1300000 | Lc, p.wait_limit);
           if (ok && lane == 0) mbar_arrive(bar(BAR_TAIL));
         }
       } else if (warp == kPubWarp) {
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
                 const long long t0 = clock64();
                 while ((int32_t)(ld_acquire_cta_shared(ringcnt + 4 * lane) - pub_expect) < 0) {
                   if (*abort_flag) { ok = false; break; }
-                  if (clock64() - t0 > kWaitLimit) {
+                  if (clock64() - t0 > p.wait_limit) {
                     if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = 0x4000000 | (lane << 8) | r;
                     ok = false; break;
                   }
@@ -462,9 +464,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
         {
-          const float* xb = p.x_in + (size_t)sg.b * p.T;
-          const float xm1 = (t >= 1 && t - 1 < p.T) ? __ldg(xb + t - 1) : 0.f;
-          const float xm2 = (t >= 2 && t - 2 < p.T) ? __ldg(xb + t - 2) : 0.f;
+          // stack input at (b, tt): a tensor, or (student, first flow) the logistic noise drawn in place (student.py:104)
+          auto x_at = [&](int tt) -> float {
+            const size_t i = (size_t)sg.b * p.T + tt;
+            if (!TEACHER && p.noise.on) return philox::logistic_at(p.noise.seed, p.noise.stream, (uint64_t)i);
+            return __ldg(p.x_in + i);
+          };
+          const float xm1 = (t >= 1 && t - 1 < p.T) ? x_at(t - 1) : 0.f;
+          const float xm2 = (t >= 2 && t - 2 < p.T) ? x_at(t - 2) : 0.f;
 #pragma unroll
           for (int j = 0; j < 16; j++) {
             const float a = fmaf(xm2, s_front[2 * j], fmaf(xm1, s_front[32 + 2 * j], cb[2 * j]));
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             h2[j] = pk(a, b);
             w16[j] = pack2<FP16>(a, b);
           }
-          alive = mbar_wait(bar(BAR_HALO + 0), U0(0) & 1, abort_flag, 0x2000000 | (m << 8));      // ring 0 was read for this chunk
+          alive = mbar_wait(bar(BAR_HALO + 0), U0(0) & 1, abort_flag, 0x2000000 | (m << 8), p.wait_limit);      // ring 0 was read for this chunk
           store_row_packed(smem + SmemMap::hbuf, kRows, kHalo + rc, w16);
           const int d0 = p.dil[0];
           fence_async_smem();
@@ -495,9 +502,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           const uint32_t b2_lo = wb_lo + (kWfBytes >> 4) + ((uint32_t)wrs_rows << 16);
           // the conditions the GEMM depends on are checked by different warps in parallel; the group
           // barrier then publishes them (and this tile's operand rows) to the issuing lane
-          if (gw == ((m + 3) & 3)) alive = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l) && alive;
-          if (gw == ((m + 1) & 3) && m >= 1) alive = mbar_wait(bar(BAR_HD + 2 * (m - 1) + s), phs, abort_flag, 0x3100000 | (m << 8) | l) && alive;
-          if (gw == ((m + 2) & 3) && m >= 2) alive = mbar_wait(bar(BAR_HD + 2 * (m - 2) + s), phs, abort_flag, 0x3200000 | (m << 8) | l) && alive;
+          if (gw == ((m + 3) & 3)) alive = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l, p.wait_limit) && alive;
+          if (gw == ((m + 1) & 3) && m >= 1) alive = mbar_wait(bar(BAR_HD + 2 * (m - 1) + s), phs, abort_flag, 0x3100000 | (m << 8) | l, p.wait_limit) && alive;
+          if (gw == ((m + 2) & 3) && m >= 2) alive = mbar_wait(bar(BAR_HD + 2 * (m - 2) + s), phs, abort_flag, 0x3200000 | (m << 8) | l, p.wait_limit) && alive;
           group_sync(m);
           TRACE(m, l, 1);
           if (issuer) {
@@ -523,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           }
 
           // ---- gate: tanh, sigmoid of the tanh, product (ops.py:28,33,36) ----
-          alive = mbar_wait(bar(BAR_D1 + m), ph, abort_flag, 0x2100000 | (m << 8) | l) && alive;
+          alive = mbar_wait(bar(BAR_D1 + m), ph, abort_flag, 0x2100000 | (m << 8) | l, p.wait_limit) && alive;
           TRACE(m, l, 3);
           tc_fence_after();
           tc_ld32(d_conv + lane_addr, v);
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           TRACE(m, l, 7);
 
           // ---- residual: dense = (inputs + residual) * sqrt(1/2) (ops.py:39-40), next conditioning ----
-          alive = mbar_wait(bar(BAR_D2 + m), ph, abort_flag, 0x2200000 | (m << 8) | l) && alive;
+          alive = mbar_wait(bar(BAR_D2 + m), ph, abort_flag, 0x2200000 | (m << 8) | l, p.wait_limit) && alive;
           TRACE(m, l, 8);
           tc_fence_after();
           tc_ld32(d_conv + lane_addr, v);
@@ -607,8 +614,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             for (int j = 0; j < 16; j++) { float a, b; upk(h2[j], a, b); w16[j] = pack2<FP16>(a, b); }
             if (l + 1 < Lc) {
               if (!next_ok) {                           // rare: the polls were too early
-                if (l >= 1) alive = mbar_wait(bar(BAR_G1 + sn), (U0(sn) + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l) && alive;
-                alive = mbar_wait(bar(BAR_HALO + sn), (U0(sn) + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l) && alive;
+                if (l >= 1) alive = mbar_wait(bar(BAR_G1 + sn), (U0(sn) + ((l - 1) >> 1)) & 1, abort_flag, 0x2300000 | (m << 8) | l, p.wait_limit) && alive;
+                alive = mbar_wait(bar(BAR_HALO + sn), (U0(sn) + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l, p.wait_limit) && alive;
               }
               TRACE(m, l, 10);
               store_row_packed(smem + SmemMap::hbuf + sn * SmemMap::hbuf_bytes, kRows, kHalo + rc, w16);
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
               mbar_arrive(bar(BAR_HD + 2 * m + sn));
             } else {
               tc_fence_before();                        // last layer of a pruned warm-up chunk: only the ring rows below
-              alive = mbar_wait(bar(BAR_TAIL), tail_idx & 1, abort_flag, 0x2700000 | (m << 8) | l) && alive;
+              alive = mbar_wait(bar(BAR_TAIL), tail_idx & 1, abort_flag, 0x2700000 | (m << 8) | l, p.wait_limit) && alive;
             }
             // history for the next chunk (read by the loader after the chunk-end barrier)
             const int dn = p.dil[l + 1];
@@ -637,9 +644,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             uint8_t* a3 = smem + SmemMap::hbuf + m * (16 * kTile * 16);
             const uint32_t a3_lo = ((sbase + SmemMap::hbuf + m * (16 * kTile * 16)) >> 4) + ((uint32_t)kTile << 16);
             // all filter-conv MMAs of the last layer retired -> both activation buffers are free
-            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (U0((L - 1) & 1) + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8)) && alive;
+            alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (U0((L - 1) & 1) + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8), p.wait_limit) && alive;
             // the skip accumulator is complete once this tile's last skip MMA retired (WEMPTY commit of the last layer)
-            alive = mbar_wait(bar(BAR_WEMPTY + ((L - 1) & 1)), (U0((L - 1) & 1) + ((L - 1) >> 1)) & 1, abort_flag, 0x2510000 | (m << 8)) && alive;
+            alive = mbar_wait(bar(BAR_WEMPTY + ((L - 1) & 1)), (U0((L - 1) & 1) + ((L - 1) >> 1)) & 1, abort_flag, 0x2510000 | (m << 8), p.wait_limit) && alive;
             tc_fence_after();
 #pragma unroll 1
             for (int hs = 0; hs < 2; hs++) {
@@ -668,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
                 }
                 __syncwarp();
               }
-              alive = mbar_wait(bar(BAR_HDD + m), (head_idx * 2 + hs) & 1, abort_flag, 0x2600000 | (m << 8) | hs) && alive;
+              alive = mbar_wait(bar(BAR_HDD + m), (head_idx * 2 + hs) & 1, abort_flag, 0x2600000 | (m << 8) | hs, p.wait_limit) && alive;
               tc_fence_after();
             }
             tc_ld32(d_conv + lane_addr, v);
@@ -726,7 +733,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             const float mu = p1 + hk[65];
             p.scale_out[at] = sc;
             p.mean_out[at] = mu;
-            p.x_out[at] = fmaf(__ldg(p.x_in + at), sc, mu);
+            const float xin = p.noise.on ? philox::logistic_at(p.noise.seed, p.noise.stream, (uint64_t)at) : __ldg(p.x_in + at);
+            p.x_out[at] = fmaf(xin, sc, mu);
           }
         }
       }
@@ -1096,6 +1104,7 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   const size_t img = stack_image_bytes(c);
   p->packed = (const uint8_t*)c->d_packed + ((size_t)(fp16 ? 1 : 0) * c->n_stacks + stack) * img;
   p->cb = w.cb; p->rings = w.rings; p->flags = w.flags; p->err = c->h_err; p->G = c->part_G;
+  p->wait_limit = c->wait_limit_clocks;
   p->segs = reinterpret_cast<const Seg*>(c->d_part);
   p->nseg = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(c->d_part) + seg_bytes);
   p->T = T; p->L = L; p->P = P; p->frames = frames;
@@ -1136,7 +1145,7 @@ int run_teacher_fused_bf16(srwn_ctx* c, const float* x_in, const float* enc, con
   return SRWN_OK;
 }
 
-int run_student_fused_bf16(srwn_ctx* c, const float* z, const float* enc, float* out, float* s_tot,
+int run_student_fused_bf16(srwn_ctx* c, const float* z, NoiseSpec noise, float* z_out, const float* enc, float* out, float* s_tot,
                            float* mu_tot, float* x_last, int B, int T, int fp16, void* ws, size_t ws_bytes,
                            cudaStream_t st) {
   if (!fused_supported(c)) return srwn_fail(SRWN_ERR_UNSUPPORTED, "fused 16-bit path needs dilations <= %d, layers <= %d, pool_stride %% 128 == 0", kHalo, kMaxLayers);
@@ -1152,12 +1161,13 @@ int run_student_fused_bf16(srwn_ctx* c, const float* z, const float* enc, float*
     if (rc) return rc;
     float* xout = (f == F - 1 && x_last) ? x_last : ((f & 1) ? w.xb : w.xa);
     p.x_in = xin; p.scale_out = w.scales + (size_t)f * n; p.mean_out = w.means + (size_t)f * n; p.x_out = xout;
+    if (f == 0) p.noise = noise;                    // later flows read the previous flow's output
     ProfScope prof(c, st, "k_fused<student,fp16>", 1);
     rc = launch_fused<false>(c, p, grid, fp16, st);
     if (rc) return rc;
     xin = xout;
   }
-  return run_flow_compose(z, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
+  return run_flow_compose(z, noise, z_out, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
 }
 
 // reads (and clears) the abort words of the fused launches issued so far; synchronises the stream

@@ -9,6 +9,7 @@
 // conditioning of layer i (model.py:183 adds it before ResidualDilationLayer, so it also
 // feeds the `inputs + residual` term at ops.py:40 and is zero-padded like the rest).
 #include "common.cuh"
+#include "philox.cuh"
 
 // cond[b][frame][layer][r] = enc[b][frame][:] @ cond_k[layer] + cond_b[layer]   (model.py:180/431)
 __global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
@@ -200,11 +201,15 @@ int run_flow_head_f32(srwn_ctx* c, int stack, const float* h, const float* xin, 
 
 // s_tot = prod s_f; mu_tot = sum_f mu_f * prod_{j>f} s_j in the reference's loop order
 // (model.py:517-533); out = clip(z*s_tot + mu_tot, -1, 1) (model.py:535)
-__global__ void k_flow_compose(const float* __restrict__ z, const float* __restrict__ scales,
+__global__ void k_flow_compose(const float* __restrict__ z, NoiseSpec noise, float* __restrict__ z_out,
+                               const float* __restrict__ scales,
                                const float* __restrict__ means, int F, float* __restrict__ out,
                                float* __restrict__ s_tot, float* __restrict__ mu_tot, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // the student's input noise (student.py:104): supplied, or the same Philox draw the flow kernel evaluated
+  const float zi = noise.on ? philox::logistic_at(noise.seed, noise.stream, (uint64_t)i) : z[i];
+  if (z_out) z_out[i] = zi;
   float st = 1.f, mt = 0.f;
   for (int f = 0; f < F; f++) {
     st *= scales[(size_t)f * n + i];
@@ -214,12 +219,12 @@ __global__ void k_flow_compose(const float* __restrict__ z, const float* __restr
   }
   if (s_tot) s_tot[i] = st;
   if (mu_tot) mu_tot[i] = mt;
-  out[i] = fminf(fmaxf(fmaf(z[i], st, mt), -1.f), 1.f);
+  out[i] = fminf(fmaxf(fmaf(zi, st, mt), -1.f), 1.f);
 }
 
-int run_flow_compose(const float* z, const float* scales, const float* means, int F, float* out,
+int run_flow_compose(const float* z, NoiseSpec noise, float* z_out, const float* scales, const float* means, int F, float* out,
                      float* s_tot, float* mu_tot, int64_t n, cudaStream_t st) {
-  k_flow_compose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, scales, means, F, out, s_tot, mu_tot, n);
+  k_flow_compose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, noise, z_out, scales, means, F, out, s_tot, mu_tot, n);
   SRWN_LAUNCH_CHECK();
   return SRWN_OK;
 }

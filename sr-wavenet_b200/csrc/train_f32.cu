@@ -728,7 +728,66 @@ __global__ void __launch_bounds__(1024) k_sumsq(const float* __restrict__ g, int
   if (threadIdx.x == 0) *out = (float)s_red[0];
 }
 
+// loss = (beta * H(Ps,Pt) - alpha * H(Ps) + power) / B   (model.py:374-379); out2 = {loss, power_loss} as the reference returns them
+__global__ void k_distill_finish(const double* __restrict__ sums, const double* __restrict__ power, float alpha, float beta,
+                                 float inv_norm, float* __restrict__ out2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    out2[0] = (float)(((double)beta * sums[0] - (double)alpha * sums[1] + *power) * (double)inv_norm);
+    out2[1] = (float)*power;
+  }
+}
+
+// tf.clip_by_global_norm(grads, clip) in place: g *= clip / max(||g||, clip)   (model.py:385)
+__global__ void k_clip_scale(float* __restrict__ g, const float* __restrict__ gnorm_sq, float clip, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  g[i] *= clip / fmaxf(sqrtf(*gnorm_sq), clip);
+}
+
+__global__ void k_axpy(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+
+// per-example entropy term sum_t (log s_tot + 2)   (model.py:356, 578-593); one CTA per example, fixed summation order
+__global__ void __launch_bounds__(1024) k_entropy(const float* __restrict__ s_tot, double* __restrict__ out, int T) {
+  __shared__ double s_red[1024];
+  const float* s = s_tot + (size_t)blockIdx.x * T;
+  double acc = 0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) acc += (double)logf(s[t]) + 2.0;
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int k = 512; k >= 1; k >>= 1) { if (threadIdx.x < k) s_red[threadIdx.x] += s_red[threadIdx.x + k]; __syncthreads(); }
+  if (threadIdx.x == 0) out[blockIdx.x] = s_red[0];
+}
+
 }  // namespace train
+
+int run_distill_finish(const double* sums, const double* power, float alpha, float beta, float inv_norm, float* out2, cudaStream_t st) {
+  train::k_distill_finish<<<1, 32, 0, st>>>(sums, power, alpha, beta, inv_norm, out2);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+int run_clip_by_global_norm(float* grads, int64_t n, float clip, float* scratch1, cudaStream_t st) {
+  train::k_sumsq<<<1, 1024, 0, st>>>(grads, n, scratch1);
+  SRWN_LAUNCH_CHECK();
+  train::k_clip_scale<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grads, scratch1, clip, n);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+int run_axpy(float* y, const float* x, float a, int64_t n, cudaStream_t st) {
+  train::k_axpy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, x, a, n);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+int run_entropy(const float* s_tot, double* per_example, int B, int T, cudaStream_t st) {
+  train::k_entropy<<<B, 1024, 0, st>>>(s_tot, per_example, T);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
 
 // ---- host ----------------------------------------------------------------------------------------------
 struct TrainWs {
@@ -835,7 +894,7 @@ int run_student_forward_train(srwn_ctx* c, const float* z, const float* enc, flo
     if (rc) return rc;
     xin = w.xs + (size_t)f * n;
   }
-  return run_flow_compose(z, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
+  return run_flow_compose(z, NoiseSpec{0, 0, 0}, nullptr, w.scales, w.means, F, out, s_tot, mu_tot, (int64_t)n, st);
 }
 
 // backward: d_pre [B,T] = dLoss/d(z S + M) (caller applies the clip mask), d_s_extra [B,T] = extra dLoss/dS (entropy);

@@ -32,13 +32,13 @@ __device__ __forceinline__ bool mbar_poll(uint32_t a, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a stuck pipeline raises the abort flag instead of hanging the GPU
-__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity, volatile int* abort_flag, int code = 0) {
+__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity, volatile int* abort_flag, int code = 0, long long limit = 1000000000LL) {
   if (mbar_test(a, parity)) return true;
   const long long t0 = clock64();
   while (true) {
     if (mbar_test(a, parity)) return true;
     if (*abort_flag) return false;
-    if (clock64() - t0 > 1000000000LL) {
+    if (clock64() - t0 > limit) {
       if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = code;   // first failing wait wins
       return false;
     }

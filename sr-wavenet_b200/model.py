@@ -74,6 +74,12 @@ class _Engine(object):
         _lib.check(self.lib.srwn_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(name)))
         return ms.value, n.value, name.value.decode()
 
+    def random_uniform(self, shape, seed, stream_id, lo, hi):
+        """U(lo, hi) draws on the device (Philox, csrc/philox.cuh) for the sampler's noise (ops.py:187, 196)."""
+        out = torch.empty(shape, dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.srwn_random_uniform(out.data_ptr(), out.numel(), seed, stream_id, lo, hi, _stream()))
+        return out
+
     def set_team_size(self, ctas_per_team):
         """CTAs per team of the fused kernel (0 = chosen per (B, T)); results do not depend on it."""
         _lib.check(self.lib.srwn_set_team_size(self.h, int(ctas_per_team)))
@@ -105,18 +111,22 @@ class _Engine(object):
         t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
         t = t.float().contiguous()
         if not t.is_pinned():
-            buf = self._pinned.get(key)
+            buf, ev = self._pinned.get(key, (None, None))
             if buf is None or buf.shape != t.shape:
-                buf = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
-                self._pinned[key] = buf
+                buf, ev = torch.empty(t.shape, dtype=torch.float32, pin_memory=True), torch.cuda.Event()
+                self._pinned[key] = (buf, ev)
+            else:
+                ev.synchronize()        # the previous H2D copy out of this staging buffer may still be queued
             buf.copy_(t)
-            t = buf
+            d = buf.to("cuda", non_blocking=True)
+            ev.record()
+            return d, False
         return t.to("cuda", non_blocking=True), False
 
     def to_host(self, t, on_device):
         if on_device:
             return t
-        key = ("out", tuple(t.shape))
+        key = ("out", tuple(t.shape), t.dtype)
         buf = self._pinned.get(key)
         if buf is None:
             buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -278,6 +288,7 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         self.name = name
         self.learning_rate = learning_rate
         self.precision = "fp32"
+        self.seed = int.from_bytes(os.urandom(7), "little")      # the reference's RNG is unseeded; set for reproducible draws
         self.last_checkpoint_time = time.time()
         self.createNetwork()
 
@@ -396,6 +407,15 @@ class WaveNetAutoEncoder(_CheckpointMixin):
     def _prec(self, precision):
         return _lib.PRECISIONS[precision or self.precision]
 
+    def _finish(self, t, on_dev, op, B, T, prec):
+        """Result hand-over.  Host boundary (NumPy in -> NumPy out): the copy synchronises anyway, so a fused launch that
+        aborted on the device raises here instead of returning partial data.  Device-resident results are not
+        synchronised; an abort then refuses the NEXT call on the handle (pinned abort words, include/srwn.h)."""
+        out = self._eng.to_host(t, on_dev)
+        if not on_dev and prec != _lib.FP32:
+            self._eng.check_async(op, B, T, prec)
+        return out
+
     def get_logits(self, inputs, encoding, conditions=None, precision=None):
         """model.py:279-285 -> logits [B,T,4M]."""
         eng = self._eng
@@ -409,7 +429,7 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         logits = torch.empty(B, T, 4 * self.num_mixtures, dtype=torch.float32, device="cuda")
         _lib.check(eng.lib.srwn_teacher_logits(eng.h, x.data_ptr(), e.data_ptr(), logits.data_ptr(), B, T,
                                                prec, ws, wsn, _stream()))
-        return eng.to_host(logits, on_dev)
+        return self._finish(logits, on_dev, _lib.OP_TEACHER_LOGITS, B, T, prec)
 
     def nll(self, inputs, encoding, conditions=None, scored=None, sum_all=True, precision=None):
         """``loss_encoding`` of model.py:114-115: teacher-forced mixture-of-logistics negative
@@ -429,11 +449,11 @@ class WaveNetAutoEncoder(_CheckpointMixin):
             out = torch.empty(1, dtype=torch.float32, device="cuda")
             _lib.check(eng.lib.srwn_teacher_nll(eng.h, x.data_ptr(), e.data_ptr(), xs.data_ptr(), None,
                                                 out.data_ptr(), None, B, T, prec, ws, wsn, _stream()))
-            return out if on_dev else float(eng.to_host(out, False)[0])
+            return out if on_dev else float(self._finish(out, False, _lib.OP_TEACHER_NLL, B, T, prec)[0])
         out = torch.empty(B, T, 1, dtype=torch.float32, device="cuda")
         _lib.check(eng.lib.srwn_teacher_nll(eng.h, x.data_ptr(), e.data_ptr(), xs.data_ptr(), out.data_ptr(),
                                             None, None, B, T, prec, ws, wsn, _stream()))
-        return eng.to_host(out, on_dev)
+        return self._finish(out, on_dev, _lib.OP_TEACHER_NLL, B, T, prec)
 
     def reconstruct_with_encoding(self, inputs, encoding, conditions=None, u1=None, u2=None,
                                   precision=None):
@@ -456,10 +476,13 @@ class WaveNetAutoEncoder(_CheckpointMixin):
         B = e.shape[0]
         T = num_samples if num_samples is not None else e.shape[1] * self.pool_stride
         self._check(e, B, T)
-        lo, hi = 1e-5, 1.0 - 1e-5
-        u1 = torch.rand(B, T, self.num_mixtures, device="cuda") * (hi - lo) + lo if u1 is None \
+        lo, hi = 1e-5, 1.0 - 1e-5            # ops.py:187, 196
+        if u1 is None or u2 is None:
+            self._noise_calls = getattr(self, "_noise_calls", 0) + 1
+        u1 = eng.random_uniform((B, T, self.num_mixtures), self.seed, 2 * self._noise_calls, lo, hi) if u1 is None \
             else eng.to_device(u1, "u1")[0]
-        u2 = torch.rand(B, T, device="cuda") * (hi - lo) + lo if u2 is None else eng.to_device(u2, "u2")[0]
+        u2 = eng.random_uniform((B, T), self.seed, 2 * self._noise_calls + 1, lo, hi) if u2 is None \
+            else eng.to_device(u2, "u2")[0]
         prec = _lib.PRECISIONS[precision]
         if not eng.lib.srwn_supports(eng.h, _lib.OP_TEACHER_GENERATE, prec):
             raise RuntimeError("generate(precision=%r) is not supported for this configuration" % precision)
@@ -521,6 +544,8 @@ class ParallelWaveNet(_CheckpointMixin):
         self.alpha, self.beta, self.gamma = alpha, beta, gamma
         self.learning_rate = learning_rate
         self.precision = "fp32"
+        self.seed = int.from_bytes(os.urandom(7), "little")      # key of the on-device logistic noise (generate(sess, None, ...))
+        self._noise_calls = 0
         self.last_checkpoint_time = time.time()
         self.createNetwork()
 
@@ -538,10 +563,36 @@ class ParallelWaveNet(_CheckpointMixin):
         self._weights = {}
         self.set_weights(w)
 
-    def createPartialFlow(self, inputs, encoding, scope):
-        raise NotImplementedError("flows run fused inside generate(); see srwn_student_forward")
+    def _flow_model(self, scope):
+        """A one-flow network holding the variables of ``scope`` ('Flow<i>'): model.py:457-486 builds each flow as its own
+        sub-graph; here it is the same kernels run for a single stack."""
+        f = int(str(scope).replace('Flow', ''))
+        if not 0 <= f < self.num_flows:
+            raise ValueError("scope must be 'Flow0' .. 'Flow%d'" % (self.num_flows - 1))
+        cache = self.__dict__.setdefault("_flow_models", {})
+        if f not in cache:
+            m = ParallelWaveNet(self.input_size, self.condition_size, self.dilations, None, num_flows=1,
+                                filter_width=self.filter_width, dilation_channels=self.dilation_channels,
+                                skip_channels=self.skip_channels, latent_channels=self.latent_channels,
+                                pool_stride=self.pool_stride)
+            cache[f] = m
+        src, dst = synth.student_prefix(f), synth.student_prefix(0)
+        cache[f].set_weights({dst + k[len(src):]: v for k, v in self.get_weights().items() if k.startswith(src)})
+        return cache[f]
 
-    createFlow = createPartialFlow
+    def createFlow(self, inputs, encoding, scope, precision=None):
+        """model.py:457-486 -> (scale, mean, out), each [B,T,1]: out = inputs * scale + mean with
+        scale = exp(params[..., 0]), mean = params[..., 1] (no clamp on the log-scale)."""
+        x = inputs[..., 0] if getattr(inputs, "ndim", 2) == 3 else inputs
+        r = self._flow_model(scope).forward_all(x, encoding, precision=precision)
+        return r["s_tot"][..., None], r["mu_tot"][..., None], r["x_last"][..., None]
+
+    def createPartialFlow(self, inputs, encoding, scope, precision=None):
+        """model.py:415-454 -> params [B,T,2] = (log scale, mean) of one flow."""
+        scale, mean, _ = self.createFlow(inputs, encoding, scope, precision=precision)
+        log = torch.log if isinstance(scale, torch.Tensor) else np.log
+        cat = torch.cat if isinstance(scale, torch.Tensor) else np.concatenate
+        return cat([log(scale), mean], -1)
 
     def set_weights(self, weights):
         """name -> ndarray with TF variable names (``ParallelWaveNet/Flow{f}/Flow{f}/...``)."""
@@ -567,9 +618,13 @@ class ParallelWaveNet(_CheckpointMixin):
     def _forward(self, inputs, encoding, conditions, precision=None, want=("out",)):
         eng = self._eng
         enc = _with_conditions(encoding, conditions, self.condition_size)
-        z, on_dev = eng.to_device(inputs, "z")
-        e, _ = eng.to_device(enc, "enc")
-        B, T = z.shape
+        e, on_dev = eng.to_device(enc, "enc")
+        if inputs is None:          # student.py:104 / :172 draws the logistic noise on the host; here it is drawn on the device
+            B, T = e.shape[0], e.shape[1] * self.pool_stride
+            z = None
+        else:
+            z, on_dev = eng.to_device(inputs, "z")
+            B, T = z.shape
         if e.ndim != 3 or e.shape[0] != B or e.shape[1] * self.pool_stride != T:
             raise ValueError("encoding must be [B, T/pool_stride, C] with T == pool_stride * frames")
         prec = _lib.PRECISIONS[precision or self.precision]
@@ -578,30 +633,52 @@ class ParallelWaveNet(_CheckpointMixin):
         ws, wsn = eng.workspace(_lib.OP_STUDENT_FORWARD, B, T, prec)
         bufs = {k: torch.empty(B, T, dtype=torch.float32, device="cuda") for k in set(want) | {"out"}}
         g = lambda k: bufs[k].data_ptr() if k in bufs else None
-        _lib.check(eng.lib.srwn_student_forward(eng.h, z.data_ptr(), e.data_ptr(), g("out"), g("s_tot"),
-                                                g("mu_tot"), g("x_last"), B, T, prec, ws, wsn, _stream()))
+        if z is None:
+            self._noise_calls += 1
+            _lib.check(eng.lib.srwn_student_sample(eng.h, self.seed, self._noise_calls, e.data_ptr(), g("out"), g("s_tot"),
+                                                   g("mu_tot"), g("x_last"), g("z"), B, T, prec, ws, wsn, _stream()))
+        else:
+            bufs.pop("z", None)
+            _lib.check(eng.lib.srwn_student_forward(eng.h, z.data_ptr(), e.data_ptr(), g("out"), g("s_tot"),
+                                                    g("mu_tot"), g("x_last"), B, T, prec, ws, wsn, _stream()))
+        self._last_call = (B, T, prec)
         return bufs, on_dev
 
+    def _to_host(self, t, on_dev):
+        """see WaveNetAutoEncoder._finish"""
+        out = self._eng.to_host(t, on_dev)
+        B, T, prec = self._last_call
+        if not on_dev and prec != _lib.FP32:
+            self._eng.check_async(_lib.OP_STUDENT_FORWARD, B, T, prec)
+        return out
+
     def generate(self, sess, inputs, encoding, conditions=None, precision=None):
-        """model.py:570-576 -> out [B,T,1] = clip(z*s_tot + mu_tot, -1, 1)."""
+        """model.py:570-576 -> out [B,T,1] = clip(z*s_tot + mu_tot, -1, 1).  ``inputs=None`` draws the logistic noise of
+        student.py:172 on the device (inside the fused flow kernel on the fp16 path): nothing but the encoding is uploaded."""
         bufs, on_dev = self._forward(inputs, encoding, conditions, precision)
-        return self._eng.to_host(bufs["out"][:, :, None], on_dev)
+        return self._to_host(bufs["out"][:, :, None], on_dev)
 
     def forward_all(self, inputs, encoding, conditions=None, precision=None):
-        """out, s_tot, mu_tot (model.py:517-535) and the chained flow output, each [B,T]."""
-        bufs, on_dev = self._forward(inputs, encoding, conditions, precision,
-                                     want=("out", "s_tot", "mu_tot", "x_last"))
-        return {k: self._eng.to_host(v, on_dev) for k, v in bufs.items()}
+        """out, s_tot, mu_tot (model.py:517-535) and the chained flow output, each [B,T]; with ``inputs=None`` also the
+        noise ``z`` that was drawn."""
+        want = ("out", "s_tot", "mu_tot", "x_last") + (("z",) if inputs is None else ())
+        bufs, on_dev = self._forward(inputs, encoding, conditions, precision, want=want)
+        return {k: self._to_host(v, on_dev) for k, v in bufs.items()}
+
+    def _entropies(self, inputs, encoding, conditions):
+        bufs, _ = self._forward(inputs, encoding, conditions, want=("s_tot",))
+        B, T = bufs["s_tot"].shape
+        per = torch.empty(B, dtype=torch.float64, device="cuda")
+        _lib.check(self._eng.lib.srwn_entropy(bufs["s_tot"].data_ptr(), per.data_ptr(), B, T, _stream()))
+        return per.cpu().numpy()
 
     def getEntropy_fast(self, sess, inputs, encoding, conditions=None):
         """model.py:595-600: reduce_sum(log(s_tot) + 2) over the whole batch (model.py:356)."""
-        bufs, _ = self._forward(inputs, encoding, conditions, want=("s_tot",))
-        return float((torch.log(bufs["s_tot"]) + 2.0).sum().item())
+        return float(self._entropies(inputs, encoding, conditions).sum())
 
     def getEntropy(self, sess, inputs, encoding, conditions=None):
         """model.py:578-593: per-example entropies."""
-        bufs, _ = self._forward(inputs, encoding, conditions, want=("s_tot",))
-        return (torch.log(bufs["s_tot"]) + 2.0).sum(dim=1).double().cpu().numpy()
+        return self._entropies(inputs, encoding, conditions)
 
     # ---- distillation (model.py:316-401, 603-642) -------------------------------------------------
     def _teacher_logits(self, truth, enc, teacher_logits, teacher_precision):
@@ -648,17 +725,21 @@ class ParallelWaveNet(_CheckpointMixin):
                                                   1.0 / norm, d_pre.data_ptr(), d_s.data_ptr(), sums.data_ptr(), B, T,
                                                   _stream()))
         entropy = sums[1]
-        loss = (self.beta * sums[0] - self.alpha * entropy + power) / norm          # model.py:374-379
+        # one bucket [flat gradient | loss | power_loss]: what a data-parallel step all-reduces in a single call
         n = ctypes.c_int64()
         _lib.check(eng.lib.srwn_param_count(eng.h, ctypes.byref(n)))
-        grads = torch.empty(n.value, dtype=torch.float32, device="cuda")
+        bucket = torch.empty(n.value + 2, dtype=torch.float32, device="cuda")
+        grads, tail = bucket[:n.value], bucket[n.value:]
+        _lib.check(eng.lib.srwn_distill_finish(sums.data_ptr(), power.data_ptr(), float(self.alpha), float(self.beta),
+                                               1.0 / norm, tail.data_ptr(), _stream()))        # model.py:374-379
         _lib.check(eng.lib.srwn_student_backward(eng.h, z.data_ptr(), e.data_ptr(), d_pre.data_ptr(), d_s.data_ptr(),
                                                  grads.data_ptr(), B, T, ws, wsn, _stream()))
-        return loss, power, entropy, grads
+        self._bucket = bucket
+        return tail[0], tail[1], entropy, grads
 
     def _power_loss(self, truth, out, frame_length=512, frame_step=256):
         """gamma * || mean_t |STFT(truth)|^2 - mean_t |STFT(out)|^2 ||^2 (model.py:360-371) and d/d out, on the device.
-        Returns (power_loss: 0-d float64 CUDA tensor, d_out [B,T] fp32)."""
+        Returns (power_loss: float64 CUDA tensor [1], d_out [B,T] fp32)."""
         eng = self._eng
         B, T = out.shape
         n = ctypes.c_size_t()
@@ -670,7 +751,7 @@ class ParallelWaveNet(_CheckpointMixin):
         _lib.check(eng.lib.srwn_stft_power_loss(truth.data_ptr(), out.data_ptr(), float(self.gamma), p.data_ptr(),
                                                 g.data_ptr(), B, T, frame_length, frame_step, self._stft_ws.data_ptr(),
                                                 self._stft_ws.numel(), _stream()))
-        return p[0], g
+        return p, g
 
     def grad_of(self, flat_grads, name):
         """View of one variable's gradient inside ``flat_grads`` (TF variable name)."""
@@ -703,29 +784,85 @@ class ParallelWaveNet(_CheckpointMixin):
                 pass      # dead variables (gate conv, student skip conv) are not stored
         self._packed_stale = False
 
+    def _sync_replicas(self, local_B):
+        """Data parallelism: every rank must hold the same weights and optimizer state, or the shared gradient moves
+        different parameters and the replicas drift apart.  On the first distributed step rank 0's weight arena and Adam
+        state are broadcast; the global batch is the sum of the ranks' local batches (recomputed when the local one
+        changes).  Returns (world, global batch)."""
+        from . import shard
+        if not shard.is_distributed():
+            return 1, local_B
+        import torch.distributed as dist
+        st = self.__dict__.setdefault("_dp", {})
+        if st.get("local_B") != local_B:
+            st["local_B"], st["global_B"] = local_B, shard.global_batch(local_B)
+        if not st.get("synced"):
+            eng = self._eng
+            n = ctypes.c_int64()
+            _lib.check(eng.lib.srwn_param_count(eng.h, ctypes.byref(n)))
+            w = torch.empty(n.value, dtype=torch.float32, device="cuda")
+            _lib.check(eng.lib.srwn_weights_flat(eng.h, w.data_ptr(), n.value, 0, _stream()))      # device arena -> w
+            state = [w]
+            if hasattr(self, "_adam"):
+                step = torch.tensor([float(self._adam["step"])], device="cuda")
+                state += [self._adam["m"], self._adam["v"], step]
+            shard.broadcast_from_rank0(state)
+            _lib.check(eng.lib.srwn_weights_flat(eng.h, w.data_ptr(), n.value, 1, _stream()))      # w -> device arena
+            if hasattr(self, "_adam"):
+                self._adam["step"] = int(step.item())
+            self._packed_stale = True
+            st["synced"] = True
+        return dist.get_world_size(), st["global_B"]
+
     def train_fast(self, sess, inputs, truth, encoding, conditions=None, teacher_logits=None, teacher_precision=None):
         """model.py:634-642: one optimisation step, returns (loss, power_loss).  With torch.distributed
-        initialised, ranks hold batch shards: the loss is normalised by the global batch, the flat gradient is
-        summed with one NCCL all-reduce before the global-norm clip, and every rank applies
-        the same Adam update."""
-        import torch.distributed as dist
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        B = int(np.shape(inputs)[0])
+        initialised, ranks hold batch shards: the loss is normalised by the global batch, the bucket
+        [flat gradient | loss | power_loss] is summed with ONE all-reduce before the global-norm clip,
+        and every rank applies the same Adam update to the same weights (``_sync_replicas``).  CUDA tensors in ->
+        0-d CUDA tensors out with no host synchronisation inside the step; NumPy in -> Python floats."""
+        B = int(inputs.shape[0])
+        world, global_B = self._sync_replicas(B)
+        on_dev = isinstance(inputs, torch.Tensor) and inputs.is_cuda
         loss, power, _, grads = self.loss_and_grads(inputs, truth, encoding, conditions, teacher_logits,
-                                                    teacher_precision, batch_norm=B * world)
+                                                    teacher_precision, batch_norm=global_B)
         if world > 1:
-            dist.all_reduce(grads, op=dist.ReduceOp.SUM)
-            lp = torch.stack([loss.double(), power.double()])
-            dist.all_reduce(lp, op=dist.ReduceOp.SUM)
-            loss, power = lp[0], lp[1]
+            from . import shard
+            ev = self.__dict__.get("_coll_events")       # bench.py: CUDA events around the collective
+            if ev:
+                ev[0].record()
+            shard.all_reduce_sum(self._bucket)
+            if ev:
+                ev[1].record()
         self.apply_gradients(grads)
-        return float(loss), float(power)
+        if on_dev:
+            return loss, power
+        lp = self._eng.to_host(self._bucket[-2:], False)
+        return float(lp[0]), float(lp[1])
 
-    def train(self, sess, inputs, truth, encoding, conditions=None, **kw):
-        """model.py:603-632 averages per-example gradients on the host and applies them once; with a loss that is
-        a sum over the batch divided by B (model.py:379) this equals one batched step except for the power
-        loss's norm, which the reference takes per example there.  The batched graph is used."""
-        return self.train_fast(sess, inputs, truth, encoding, conditions, **kw)
+    def train(self, sess, inputs, truth, encoding, conditions=None, teacher_logits=None, teacher_precision=None):
+        """model.py:603-632, literally: one evaluation of the graph per EXAMPLE of ``inputs`` -- its noise row fed as a
+        batch of one, broadcast against the whole ``encoding`` / ``truth`` batch, the loss divided by shape(inputs)[0] = 1
+        (model.py:379), gradients clipped per example (``self.grads`` are the clipped ones, model.py:385-392) -- then the
+        clipped gradients, losses and power losses are averaged and one Adam update is applied without further clipping.
+        Returns (mean loss, mean power loss)."""
+        eng = self._eng
+        z_all, _ = eng.to_device(inputs, "z_all")
+        x, _ = eng.to_device(truth, "truth")
+        e, _ = eng.to_device(_with_conditions(encoding, conditions, self.condition_size), "enc")
+        N, Be = z_all.shape[0], e.shape[0]
+        mean = None
+        scratch = torch.zeros(1, dtype=torch.float32, device="cuda")
+        for i in range(N):
+            zi = z_all[i:i + 1].expand(Be, -1).contiguous()          # [1,T] against [Be, ...]: TF broadcasts the batch axis
+            self.loss_and_grads(zi, x, e, None, teacher_logits, teacher_precision, batch_norm=1)
+            b = self._bucket
+            _lib.check(eng.lib.srwn_clip_by_global_norm(b.data_ptr(), b.numel() - 2, 1.0, scratch.data_ptr(), _stream()))
+            if mean is None:
+                mean = torch.zeros_like(b)
+            _lib.check(eng.lib.srwn_axpy(mean.data_ptr(), b.data_ptr(), 1.0 / N, b.numel(), _stream()))
+        self.apply_gradients(mean[:-2], clip_norm=0.0)
+        lp = eng.to_host(mean[-2:], False)
+        return float(lp[0]), float(lp[1])
 
     def _need_teacher(self):
         if not isinstance(self.teacher, WaveNetAutoEncoder):

@@ -14,6 +14,8 @@ import torch
 from . import _lib
 
 SQRT_HALF = 0.7071067811865476
+SEED = int.from_bytes(__import__("os").urandom(7), "little")     # key of the sampler's Philox draws (the reference is unseeded)
+_draws = 0
 
 # ---- TF1-style variable store -----------------------------------------------------------
 _scope_stack = []
@@ -190,8 +192,16 @@ def sample_from_discretized_mix_logistic(l, nr_mix, u1=None, u2=None, return_ind
     if C != 4 * nr_mix:
         raise ValueError("l must have 4*nr_mix channels")
     lo, hi = 1e-5, 1.0 - 1e-5
-    u1 = torch.rand(B, T, nr_mix, device=lt.device) * (hi - lo) + lo if u1 is None else _prep(u1, "u1")
-    u2 = torch.rand(B, T, device=lt.device) * (hi - lo) + lo if u2 is None else _prep(u2, "u2")
+    if u1 is None or u2 is None:       # tf.random_uniform (ops.py:187, 196): Philox draws on the device
+        global _draws
+        _draws += 1
+
+        def _uniform(shape, stream_id):
+            t = torch.empty(shape, dtype=torch.float32, device=lt.device)
+            _lib.check(_lib.load().srwn_random_uniform(_ptr(t), t.numel(), SEED, 2 * _draws + stream_id, lo, hi, _stream()))
+            return t
+    u1 = _uniform((B, T, nr_mix), 0) if u1 is None else _prep(u1, "u1")
+    u2 = _uniform((B, T), 1) if u2 is None else _prep(u2, "u2")
     out = torch.empty(B, T, 1, dtype=torch.float32, device=lt.device)
     idx = torch.empty(B, T, dtype=torch.int32, device=lt.device) if return_index else None
     _lib.check(_lib.load().srwn_mol_sample(_ptr(lt), _ptr(u1), _ptr(u2), _ptr(out), _ptr(idx), B, T,

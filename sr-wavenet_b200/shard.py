@@ -48,3 +48,30 @@ def reduce_scalars(values, op, device=None):
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+# ---- data-parallel distillation step (the one path with a collective) ---------------------------
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def global_batch(local_batch, device=None):
+    """Sum of the ranks' local batch sizes (model.py:379 divides the loss by the batch: under data parallelism that is
+    the GLOBAL batch, and ranks need not hold equal shares)."""
+    total, = reduce_scalars([float(local_batch)], "sum", device)
+    return int(round(total))
+
+
+def broadcast_from_rank0(tensors):
+    """Make every replica start from rank 0's state (weights, Adam moments, step count): replicas that apply a shared
+    gradient to different parameters drift apart silently."""
+    if is_distributed():
+        for t in tensors:
+            dist.broadcast(t, src=0)
+
+
+def all_reduce_sum(bucket):
+    """ONE all-reduce for the whole step: bucket = [flat gradient | loss | power_loss]."""
+    if is_distributed():
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+    return bucket

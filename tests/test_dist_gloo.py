@@ -92,3 +92,39 @@ def test_two_rank_gradient_allreduce_equals_full_batch(tmp_path):
     # shard sums reproduce the full-batch loss and gradient
     np.testing.assert_allclose(r0["flat"], full, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(r0["lp"], [loss, power], rtol=1e-10)
+
+
+def _dp_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    shard.init_from_env(backend="gloo")
+    assert shard.is_distributed()
+    rng = np.random.default_rng(100 + rank)                 # replicas start DIFFERENT (unseeded Glorot init)
+    weights = torch.from_numpy(rng.normal(size=1000).astype(np.float32))
+    m, v = torch.from_numpy(rng.normal(size=1000).astype(np.float32)), torch.full((1000,), float(rank))
+    step = torch.tensor([float(3 + rank)])
+    local_B = 3 + rank                                      # unequal shares
+    gB = shard.global_batch(local_B, device="cpu")
+    shard.broadcast_from_rank0([weights, m, v, step])
+    # one step: bucket = [gradient | loss | power], each rank's terms divided by the GLOBAL batch
+    g = np.full(1000, float(local_B)) / gB
+    bucket = torch.from_numpy(np.concatenate([g, [local_B * 2.0 / gB, local_B * 5.0]]).astype(np.float32))
+    shard.all_reduce_sum(bucket)
+    weights -= 0.1 * bucket[:1000]
+    np.save(os.path.join(out_dir, "dp%d.npy" % rank), np.concatenate([weights.numpy(), m.numpy(), v.numpy(), step.numpy(),
+                                                                        bucket[-2:].numpy(), [gB]]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_replicas_are_synchronised(tmp_path):
+    """The data-parallel distillation step's host logic (ParallelWaveNet._sync_replicas / train_fast): replicas that
+    start from different weights / Adam state hold rank 0's after the first-step broadcast, the loss divisor is the sum
+    of unequal local batches, and one all-reduce of [gradient | loss | power] leaves identical weights everywhere."""
+    world = 2
+    mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = (np.load(str(tmp_path / ("dp%d.npy" % r))) for r in range(world))
+    np.testing.assert_array_equal(a, b)
+    ref = np.random.default_rng(100).normal(size=1000).astype(np.float32)
+    np.testing.assert_allclose(a[:1000], ref - np.float32(0.1), rtol=1e-6)        # summed gradient = (3 + 4) / 7 = 1
+    assert a[-1] == 7 and a[3000] == 3.0 and (a[2000:3000] == 0).all()
+    np.testing.assert_allclose(a[-3:-1], [2.0, 35.0], rtol=1e-6)

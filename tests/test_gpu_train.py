@@ -7,6 +7,7 @@ from oracle import distill_torch as dt
 from sr_wavenet_b200 import synth
 
 pytestmark = pytest.mark.gpu
+GRAD_TOL = 2e-3      # tightened to the measured error below
 
 
 @pytest.fixture(scope="module")
@@ -141,18 +142,23 @@ def test_gradients_match_oracle(srwn, cfg):
     loss, power, ent, flat = s.loss_and_grads(z, truth, enc, teacher_logits=tl)
     rl, rp, re, rg = dt.loss_and_grads({k: v.astype(np.float64) for k, v in w.items()}, z, truth, enc, tl, dil, P, F,
                                        alpha=0.25, beta=1.0, gamma=1.0)
+    print("distill %s: rel err entropy %.2e  power %.2e  loss %.2e" % (cfg, abs(float(ent) / re - 1), abs(float(power) / rp - 1),
+                                                                     abs(float(loss) / rl - 1)))
     np.testing.assert_allclose(float(ent), re, rtol=1e-4)
-    np.testing.assert_allclose(float(power), rp, rtol=2e-3)
-    np.testing.assert_allclose(float(loss), rl, rtol=1e-3)
+    np.testing.assert_allclose(float(power), rp, rtol=1e-4)
+    np.testing.assert_allclose(float(loss), rl, rtol=1e-4)
     gmax = max(np.abs(v).max() for v in rg.values())
-    checked = 0
+    checked, worst = 0, (0.0, "")
     for name, ref in rg.items():
         if "_gate/" in name or not np.any(ref):
             continue                                             # dead variables are not stored
         got = s.grad_of(flat, name).cpu().numpy().reshape(ref.shape)
-        tol = 2e-3 * max(np.abs(ref).max(), 1e-3 * gmax)         # fp32 kernels + fp32 loss gradients vs float64
-        assert np.abs(got - ref).max() <= tol, (name, np.abs(got - ref).max(), np.abs(ref).max())
+        rel = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-3 * gmax)
+        worst = max(worst, (float(rel), name))
         checked += 1
+    print("distill %s: worst gradient error relative to the variable's scale %.2e (%s), %d variables" % (cfg, worst[0], worst[1], checked))
+    # fp32 kernels (3xTF32 GEMMs, fp32 loss gradients, fp32 sums over B*T positions) against float64 autograd
+    assert worst[0] <= GRAD_TOL, worst
     assert checked == F * (2 + 6 * len(dil) + 2)
 
 
@@ -182,3 +188,51 @@ def test_adam_step_and_training_reduces_loss(srwn):
     if "fp16" in s.available_precisions():
         out16 = s.generate(None, z, enc, precision="fp16")
         assert np.abs(out16 - out32).max() <= 2e-2
+
+
+def test_per_example_train_matches_reference_semantics(srwn):
+    """ParallelWaveNet.train (model.py:603-632): per example a batch-of-one noise row against the whole encoding / truth
+    batch, loss / 1, gradients clipped per example, then averaged and applied without further clipping."""
+    dil, F, C, P, M, B, T = [1, 2, 4, 8], 2, 8, 128, 3, 2, 1024
+    s, w = _student(srwn, dil, F, C, P, lr=1e-3, alpha=0.25, beta=1.0, gamma=1.0)
+    z, truth, enc, tl = _inputs(B, T, P, C, M)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    names = [k for k in w if "_gate/" not in k and not any(k.endswith("conv1d_%d/%s" % (3 * i + 2, t)) for i in range(len(dil)) for t in ("kernel", "bias"))]
+    mean_g, losses, powers = None, [], []
+    for i in range(B):
+        zi = np.repeat(z[i:i + 1], B, axis=0)
+        rl, rp, _, rg = dt.loss_and_grads(w64, zi, truth, enc, tl, dil, P, F, alpha=0.25, beta=1.0, gamma=1.0, batch_norm=1)
+        g = [rg[k] for k in names]
+        gn = np.sqrt(sum((x ** 2).sum() for x in g))
+        g = [x * (1.0 / max(gn, 1.0)) for x in g]                                  # tf.clip_by_global_norm(., 1.0)
+        mean_g = g if mean_g is None else [a + b for a, b in zip(mean_g, g)]
+        losses.append(rl); powers.append(rp)
+    mean_g = [x / B for x in mean_g]
+    ref = dt.adam_reference([w64[k] for k in names], mean_g, [np.zeros_like(x) for x in mean_g], [np.zeros_like(x) for x in mean_g],
+                            step=1, lr=1e-3, clip=None)
+    loss, power = s.train(None, z, truth, enc, teacher_logits=tl)
+    np.testing.assert_allclose(loss, np.mean(losses), rtol=1e-4)
+    np.testing.assert_allclose(power, np.mean(powers), rtol=1e-4)
+    s.sync_weights()
+    new = s.get_weights()
+    for k, (wr, _, _) in zip(names, ref):
+        np.testing.assert_allclose(new[k], wr, rtol=0, atol=5e-6)
+
+
+def test_create_flow_matches_oracle(srwn):
+    """createFlow / createPartialFlow (model.py:415-486) for one flow of the network."""
+    from conftest import f64
+    from oracle import srwn_oracle as orc
+    dil, F, C, P, B, T = synth.DEFAULT_DILATIONS, 3, 32, 128, 2, 1024
+    s, w = _student(srwn, dil, F, C, P)
+    x = synth.logistic_noise(B, T, seed=3)
+    enc = synth.synthetic_encoding(B, T // P, C, seed=4)
+    for f in (0, 2):
+        scale, mean, out = s.createFlow(x[:, :, None], enc, 'Flow%d' % f)
+        rs, rm, ro = orc.student_flow(f64(w), x.astype(np.float64)[:, :, None], enc.astype(np.float64), dil, P, f)
+        assert scale.shape == (B, T, 1)
+        np.testing.assert_allclose(scale, rs, rtol=1e-4)
+        np.testing.assert_allclose(mean, rm, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(out, ro, rtol=1e-4, atol=1e-5)
+        params = s.createPartialFlow(x[:, :, None], enc, 'Flow%d' % f)
+        np.testing.assert_allclose(params[..., 0:1], np.log(rs), rtol=1e-4, atol=1e-5)
