@@ -4,9 +4,11 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this package.  The product
 (``sr-wavenet_b200/``) never imports it and has no CPU fallback.
 
-Parity status: the dilated-conv restatement is pinned by the reference's own
-known-answer prints (``ops.py:243-254``).  Everything else (gated block,
-decoder, flows, MoL loss / sampler) is **parity unpinned**: the reference is
-TensorFlow 1.x, which cannot be installed or run here, and it holds no golden
-vectors for those functions.  See DESIGN.md section "Oracle".
+Parity status: **pinned by executing the reference's own source** -- ``/root/reference/ops.py`` and
+``model.py`` are imported unmodified on top of a NumPy stand-in for TensorFlow 1.x (``tests/tf_shim``)
+and every function of ``srwn_oracle.py`` is compared with them at 1e-11
+(``tests/test_reference_shim.py``); the reference's printed known answers (``ops.py:243-254``) and the
+fixtures written from that code path (``tests/golden/reference_*.npz``) hold the oracle on machines
+without the reference tree.  TensorFlow itself cannot be installed here: the semantics of single
+``tf.*`` operations are the stand-in's restatement.  See DESIGN.md section "Oracle".
 """
