@@ -214,11 +214,17 @@ __device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, vola
   asm volatile("fence.proxy.async;" ::: "memory");
   return true;
 }
-// producer, tile-group thread: after its ring rows (generic stores): make them visible to the async proxy, then count
-// the row in the group's shared-memory counter (release at CTA scope: the publisher's acquire sees the rows)
-__device__ __forceinline__ void ring_row_done(uint32_t counter_addr) {
-  asm volatile("fence.proxy.async.global;" ::: "memory");
-  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(counter_addr) : "memory");
+// producer, one thread per tile group, after the group barrier that follows the group's ring stores (generic st.global by
+// up to 128 threads; the barrier orders them before this thread): count the rows in the group's shared-memory counter
+// with release at CTA scope, so that the publisher's acquire -- and, through its GPU-scope release, the consumer CTA --
+// observes them.  No per-thread fence or atomic sits on the layer chain.
+__device__ __forceinline__ void ring_rows_done(uint32_t counter_addr, uint32_t rows) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(counter_addr), "r"(rows) : "memory");
+}
+// rows of ring r (dilation d) that tile group m writes: chunk rows rc in [kChunk - d, kChunk) that fall into tile m
+__device__ __forceinline__ int ring_rows_of(int d, int m) {
+  const int lo = max(kChunk - d, m * kTile), hi = (m + 1) * kTile;
+  return hi > lo ? hi - lo : 0;
 }
 __device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
   uint32_t v;
@@ -404,12 +410,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         bool ok = true;
         for (int r = 0; r <= last && ok; r++) {
           if (lane < kTiles) {
-            const int lo = max(kChunk - p.dil[r], lane * kTile), hi = (lane + 1) * kTile;
-            if (hi > lo) {
-              pub_expect += (uint32_t)(hi - lo);
+            const int rows = ring_rows_of(p.dil[r], lane);
+            if (rows) {
+              pub_expect += (uint32_t)rows;
               if ((int32_t)(ld_acquire_cta_shared(ringcnt + 4 * lane) - pub_expect) < 0) {
                 const long long t0 = clock64();
                 while ((int32_t)(ld_acquire_cta_shared(ringcnt + 4 * lane) - pub_expect) < 0) {
+                  __nanosleep(128);            // this warp has the highest id of its scheduler: a busy spin would starve the tile warps there
                   if (*abort_flag) { ok = false; break; }
                   if (clock64() - t0 > p.wait_limit) {
                     if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = 0x4000000 | (lane << 8) | r;
@@ -484,10 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           const int d0 = p.dil[0];
           fence_async_smem();
           mbar_arrive(bar(BAR_HD + 2 * m + 0));
-          if (rc >= kChunk - d0) {
-            store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);
-            ring_row_done(ringcnt + 4 * m);
-          }
+          if (rc >= kChunk - d0) store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);     // published at the top of layer 0
         }
 
         for (int l = 0; l < Lc; l++) {
@@ -507,6 +511,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           if (gw == ((m + 2) & 3) && m >= 2) alive = mbar_wait(bar(BAR_HD + 2 * (m - 2) + s), phs, abort_flag, 0x3200000 | (m << 8) | l, p.wait_limit) && alive;
           group_sync(m);
           TRACE(m, l, 1);
+          // ring l of this chunk (front conv / residual epilogue of layer l-1) is complete for this group: tell the publisher
+          if (gw == ((m + 3) & 3) && lane == 0) {
+            const int rows = ring_rows_of((int)dl, m);
+            if (rows) ring_rows_done(ringcnt + 4 * m, (uint32_t)rows);
+          }
           if (issuer) {
             tc_fence_after();
             if (leader) {
@@ -628,10 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             }
             // history for the next chunk (read by the loader after the chunk-end barrier)
             const int dn = p.dil[l + 1];
-            if (rc >= kChunk - dn) {
-              store_row_packed(ring + p.ring_off[l + 1], dn, t % dn, w16);
-              ring_row_done(ringcnt + 4 * m);
-            }
+            if (rc >= kChunk - dn) store_row_packed(ring + p.ring_off[l + 1], dn, t % dn, w16);   // published at the top of layer l+1
             TRACE(m, l, 11);
           } else {
             tc_fence_before();
@@ -736,6 +742,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
             const float xin = p.noise.on ? philox::logistic_at(p.noise.seed, p.noise.stream, (uint64_t)at) : __ldg(p.x_in + at);
             p.x_out[at] = fmaf(xin, sc, mu);
           }
+        }
+      }
+      if (Lc < L && warp != kLoadWarp && warp != kPubWarp) {        // pruned warm-up chunk: ring Lc was written behind the last layer
+        const int gw = warp & 3, m = (((warp - 1) >> 2) + gw + 1) % 3;
+        group_sync(m);
+        if (gw == ((m + 3) & 3) && lane == 0) {
+          const int rows = ring_rows_of(p.dil[Lc], m);
+          if (rows) ring_rows_done(ringcnt + 4 * m, (uint32_t)rows);
         }
       }
       if (do_head) head_idx++;
