@@ -193,26 +193,34 @@ constexpr int kPubWarp = 13;
 // ---- cross-CTA ring hand-off ------------------------------------------------------------------------
 // consumer: chunk n waits until flags[l] >= n (rings of chunks 0..n-1 published), then orders its bulk loads (async proxy)
 // after the acquire
-__device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, volatile int* abort_flag, const int* gerr, int code, long long limit) {
+// Returns the last ring index whose flag was seen >= need (>= l on success, -1 on abort): the producer is usually a layer
+// or two ahead, so one acquire fence covers several rings.
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* f) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-  if (v < need) {
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  return v;
+}
+__device__ __forceinline__ int flag_wait(const uint32_t* flags, int l, int l_end, uint32_t need, volatile int* abort_flag, const int* gerr,
+                                         int code, long long limit) {
+  if (ld_relaxed_gpu(flags + l) < need) {
     const long long t0 = clock64();
     int spins = 0;
     while (true) {
       __nanosleep(32);
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (v >= need) break;
-      if (*abort_flag) return false;
-      if (((++spins) & 1023) == 0 && *reinterpret_cast<const volatile int*>(gerr)) return false;   // another CTA aborted (host memory: polled rarely)
+      if (ld_relaxed_gpu(flags + l) >= need) break;
+      if (*abort_flag) return -1;
+      if (((++spins) & 1023) == 0 && *reinterpret_cast<const volatile int*>(gerr)) return -1;   // another CTA aborted (host memory: polled rarely)
       if (clock64() - t0 > limit) {
         if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = code;
-        return false;
+        return -1;
       }
     }
   }
-  asm volatile("fence.proxy.async;" ::: "memory");
-  return true;
+  int upto = l;
+  while (upto + 1 < l_end && ld_relaxed_gpu(flags + upto + 1) >= need) upto++;
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");       // pairs with the publisher's release: the ring rows are visible
+  asm volatile("fence.proxy.async;" ::: "memory");       // ... and ordered before this thread's bulk loads (async proxy)
+  return upto;
 }
 // producer, one thread per tile group, after the group barrier that follows the group's ring stores (generic st.global by
 // up to 128 threads; the barrier orders them before this thread): count the rows in the group's shared-memory counter
@@ -300,6 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
   const uint32_t ringcnt = sbase + SmemMap::misc + 16;   // [3] ring rows written so far by tile group m (monotonic)
   uint32_t pub_expect = 0;                              // publisher lane m: rows group m has to have written
   int seq = 0;                                          // chunk sequence number inside the piece
+#ifndef SRWN_VAR
+#define SRWN_VAR 0          // timing-only variants of the hand-off (tools/exp_build.sh); non-zero values give wrong results
+#endif
+  const bool handoff = G > 1;                           // G == 1: the CTA hands its rings to itself across the chunk-end barrier
   int u0e = 0, u0o = 0, lay_base = 0;                 // phases of the parity-indexed / per-layer barriers used so far
   int chunk_idx = 0;                                  // chunks processed so far
   int head_idx = 0;                                   // chunks with a head phase so far
@@ -333,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
 
       if (warp == kLoadWarp) {
         // ================= loader: weights (bulk copy) + halo rows (cp.async) per layer ============
+        int acquired = -1;                                     // rings of chunk n-1 known to be published and acquired
         for (int l = 0; l < Lc; l++) {
           const int s = l & 1;
           const int use = U0(s) + (l >> 1);                  // how many times stage s was used before
@@ -345,7 +358,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           // ring l of the previous chunk of the piece (written by another member of the team unless G == 1); also taken
           // at an utterance start, where the rows are not read: this chunk may overwrite the ring only after chunk n-1
           // has read it, which its publication implies
-          if (n > 0 && !flag_wait(flags + l, (uint32_t)n, abort_flag, p.err, 0x1200000 | l, p.wait_limit)) break;
+          if (handoff && !(SRWN_VAR & 2) && n > 0 && l > acquired) {
+            acquired = flag_wait(flags, l, L, (uint32_t)n, abort_flag, p.err, 0x1200000 | l, p.wait_limit);
+            if (acquired < 0) break;
+          }
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
@@ -399,7 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         // a pruned warm-up chunk writes ring Lc behind its last layer without reading it: the write has to come after
         // chunk n-1's rows of the same ring
         if (Lc < L && !*abort_flag) {
-          const bool ok = n == 0 || flag_wait(flags + Lc, (uint32_t)n, abort_flag, p.err, 0x1300000 | Lc, p.wait_limit);
+          const bool ok = n == 0 || !handoff || (SRWN_VAR & 2) || Lc <= acquired ||
+                          flag_wait(flags, Lc, L, (uint32_t)n, abort_flag, p.err, 0x1300000 | Lc, p.wait_limit) >= 0;
           if (ok && lane == 0) mbar_arrive(bar(BAR_TAIL));
         }
       } else if (warp == kPubWarp) {
@@ -407,9 +424,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         // Rings written by this chunk: 0 (front conv) and l+1 by the residual epilogue of layer l < Lc (l+1 < L).  Lane m
         // follows tile group m: ring r is written by the rows rc >= kChunk - d_r, i.e. a known number of rows per group.
         const int last = Lc < L - 1 ? Lc : L - 1;
-        bool ok = true;
+        bool ok = handoff && !(SRWN_VAR & 4);
         for (int r = 0; r <= last && ok; r++) {
-          if (lane < kTiles) {
+          if (lane < kTiles && !(SRWN_VAR & 1)) {
             const int rows = ring_rows_of(p.dil[r], lane);
             if (rows) {
               pub_expect += (uint32_t)rows;
@@ -512,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           group_sync(m);
           TRACE(m, l, 1);
           // ring l of this chunk (front conv / residual epilogue of layer l-1) is complete for this group: tell the publisher
-          if (gw == ((m + 3) & 3) && lane == 0) {
+          if (handoff && !(SRWN_VAR & 1) && gw == ((m + 3) & 3) && lane == 0) {
             const int rows = ring_rows_of((int)dl, m);
             if (rows) ring_rows_done(ringcnt + 4 * m, (uint32_t)rows);
           }
@@ -744,7 +761,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           }
         }
       }
-      if (Lc < L && warp != kLoadWarp && warp != kPubWarp) {        // pruned warm-up chunk: ring Lc was written behind the last layer
+      if (handoff && !(SRWN_VAR & 1) && Lc < L && warp != kLoadWarp && warp != kPubWarp) {        // pruned warm-up chunk: ring Lc was written behind the last layer
         const int gw = warp & 3, m = (((warp - 1) >> 2) + gw + 1) % 3;
         group_sync(m);
         if (gw == ((m + 3) & 3) && lane == 0) {

@@ -215,8 +215,11 @@ def test_per_example_train_matches_reference_semantics(srwn):
     np.testing.assert_allclose(power, np.mean(powers), rtol=1e-4)
     s.sync_weights()
     new = s.get_weights()
+    # first Adam step: |update| = lr * |g| / (|g| + eps) -- for the few entries whose averaged gradient is as small as eps
+    # the fp32 gradient's relative error shows up in full, so the bound is a few percent of one step (lr = 1e-3)
     for k, (wr, _, _) in zip(names, ref):
-        np.testing.assert_allclose(new[k], wr, rtol=0, atol=5e-6)
+        np.testing.assert_allclose(new[k], wr, rtol=0, atol=5e-5)
+        assert np.mean(np.abs(new[k] - wr) > 5e-6) < 0.05
 
 
 def test_create_flow_matches_oracle(srwn):
