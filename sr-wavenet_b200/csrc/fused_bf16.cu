@@ -193,34 +193,31 @@ constexpr int kPubWarp = 13;
 // ---- cross-CTA ring hand-off ------------------------------------------------------------------------
 // consumer: chunk n waits until flags[l] >= n (rings of chunks 0..n-1 published), then orders its bulk loads (async proxy)
 // after the acquire
-// Returns the last ring index whose flag was seen >= need (>= l on success, -1 on abort): the producer is usually a layer
-// or two ahead, so one acquire fence covers several rings.
-__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* f) {
+// One acquire load per ring: measured faster than polling relaxed and fencing once for several rings (2.29 vs 2.56 ms
+// at 32x64000, G = 7; profiles/r02d_handoff_variants.log).  The spin lives out of line: the loop bodies of three different
+// warp roles share the instruction cache.
+__device__ __noinline__ bool flag_spin(const uint32_t* f, uint32_t need, volatile int* abort_flag, const int* gerr, int code, long long limit) {
+  const long long t0 = clock64();
+  int spins = 0;
   uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-  return v;
-}
-__device__ __forceinline__ int flag_wait(const uint32_t* flags, int l, int l_end, uint32_t need, volatile int* abort_flag, const int* gerr,
-                                         int code, long long limit) {
-  if (ld_relaxed_gpu(flags + l) < need) {
-    const long long t0 = clock64();
-    int spins = 0;
-    while (true) {
-      __nanosleep(32);
-      if (ld_relaxed_gpu(flags + l) >= need) break;
-      if (*abort_flag) return -1;
-      if (((++spins) & 1023) == 0 && *reinterpret_cast<const volatile int*>(gerr)) return -1;   // another CTA aborted (host memory: polled rarely)
-      if (clock64() - t0 > limit) {
-        if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = code;
-        return -1;
-      }
+  while (true) {
+    __nanosleep(32);
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v >= need) return true;
+    if (*abort_flag) return false;
+    if (((++spins) & 1023) == 0 && *reinterpret_cast<const volatile int*>(gerr)) return false;   // another CTA aborted (host memory: polled rarely)
+    if (clock64() - t0 > limit) {
+      if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = code;
+      return false;
     }
   }
-  int upto = l;
-  while (upto + 1 < l_end && ld_relaxed_gpu(flags + upto + 1) >= need) upto++;
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");       // pairs with the publisher's release: the ring rows are visible
-  asm volatile("fence.proxy.async;" ::: "memory");       // ... and ordered before this thread's bulk loads (async proxy)
-  return upto;
+}
+__device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, volatile int* abort_flag, const int* gerr, int code, long long limit) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  if (v < need && !flag_spin(f, need, abort_flag, gerr, code, limit)) return false;
+  asm volatile("fence.proxy.async;" ::: "memory");       // the ring rows are read by bulk copies (async proxy)
+  return true;
 }
 // producer, one thread per tile group, after the group barrier that follows the group's ring stores (generic st.global by
 // up to 128 threads; the barrier orders them before this thread): count the rows in the group's shared-memory counter
@@ -345,7 +342,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
 
       if (warp == kLoadWarp) {
         // ================= loader: weights (bulk copy) + halo rows (cp.async) per layer ============
-        int acquired = -1;                                     // rings of chunk n-1 known to be published and acquired
         for (int l = 0; l < Lc; l++) {
           const int s = l & 1;
           const int use = U0(s) + (l >> 1);                  // how many times stage s was used before
@@ -358,10 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           // ring l of the previous chunk of the piece (written by another member of the team unless G == 1); also taken
           // at an utterance start, where the rows are not read: this chunk may overwrite the ring only after chunk n-1
           // has read it, which its publication implies
-          if (handoff && !(SRWN_VAR & 2) && n > 0 && l > acquired) {
-            acquired = flag_wait(flags, l, L, (uint32_t)n, abort_flag, p.err, 0x1200000 | l, p.wait_limit);
-            if (acquired < 0) break;
-          }
+          if (handoff && !(SRWN_VAR & 2) && n > 0 && !flag_wait(flags + l, (uint32_t)n, abort_flag, p.err, 0x1200000 | l, p.wait_limit)) break;
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
@@ -415,8 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
         // a pruned warm-up chunk writes ring Lc behind its last layer without reading it: the write has to come after
         // chunk n-1's rows of the same ring
         if (Lc < L && !*abort_flag) {
-          const bool ok = n == 0 || !handoff || (SRWN_VAR & 2) || Lc <= acquired ||
-                          flag_wait(flags, Lc, L, (uint32_t)n, abort_flag, p.err, 0x1300000 | Lc, p.wait_limit) >= 0;
+          const bool ok = n == 0 || !handoff || (SRWN_VAR & 2) || flag_wait(flags + Lc, (uint32_t)n, abort_flag, p.err, 0x1300000 | Lc, p.wait_limit);
           if (ok && lane == 0) mbar_arrive(bar(BAR_TAIL));
         }
       } else if (warp == kPubWarp) {
@@ -529,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
           group_sync(m);
           TRACE(m, l, 1);
           // ring l of this chunk (front conv / residual epilogue of layer l-1) is complete for this group: tell the publisher
-          if (handoff && !(SRWN_VAR & 1) && gw == ((m + 3) & 3) && lane == 0) {
+          if (handoff && !(SRWN_VAR & 1) && gw == (m == 0 ? 1 : 0) && lane == 0) {       // a low row of the tile: it writes ring rows only for the largest dilations, so the release rarely waits for stores of its own
             const int rows = ring_rows_of((int)dl, m);
             if (rows) ring_rows_done(ringcnt + 4 * m, (uint32_t)rows);
           }
@@ -764,7 +756,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_fused(const Params p) {
       if (handoff && !(SRWN_VAR & 1) && Lc < L && warp != kLoadWarp && warp != kPubWarp) {        // pruned warm-up chunk: ring Lc was written behind the last layer
         const int gw = warp & 3, m = (((warp - 1) >> 2) + gw + 1) % 3;
         group_sync(m);
-        if (gw == ((m + 3) & 3) && lane == 0) {
+        if (gw == (m == 0 ? 1 : 0) && lane == 0) {
           const int rows = ring_rows_of(p.dil[Lc], m);
           if (rows) ring_rows_done(ringcnt + 4 * m, (uint32_t)rows);
         }
@@ -1035,7 +1027,8 @@ static Partition make_partition(int B, int T, const std::vector<int>& dilations,
     Partition cand = partition_for(B, T, warm_cost, teams);
     const double lag = kLagLayers / L;
     const double period = std::max(1.0, G * lag);
-    const double time = (cand.cost / G + (G > 1 ? 0.5 : 0.0)) * period + (G - 1) * lag;
+    // measured (profiles/r02d_handoff_variants.log): a chunk costs about 8 % more with the hand-off than without
+    const double time = (cand.cost / G + (G > 1 ? 0.5 : 0.0)) * period * (G > 1 ? 1.08 : 1.0) + (G - 1) * lag;
     if (time < best_time) { best_time = time; best = cand; best.G = G; }
   }
   return best;
