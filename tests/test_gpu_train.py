@@ -7,7 +7,7 @@ from oracle import distill_torch as dt
 from sr_wavenet_b200 import synth
 
 pytestmark = pytest.mark.gpu
-GRAD_TOL = 2e-3      # tightened to the measured error below
+GRAD_TOL = 1e-4      # fp32-grade backward (3xTF32 GEMMs, ex2-based gate recompute): the north star's bound for the fp32 path
 
 
 @pytest.fixture(scope="module")
