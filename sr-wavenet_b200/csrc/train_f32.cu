@@ -91,6 +91,31 @@ __device__ __forceinline__ void split_store4(float* h, float* l, float4 v) {
   *reinterpret_cast<float4*>(l) = vl;
 }
 
+// The backward kernels keep their operands in shared memory as plain fp32 and split them in registers when a fragment is
+// loaded: d += a b at fp32 grade = lo*hi + hi*lo + hi*hi (small terms first).  Round 1 rounded the operands to ONE TF32
+// number (2^-11) and recomputed the gate with tanh.approx: the gradients came out 1.4e-3 of each variable's scale off the
+// float64 oracle, above the 1e-4 the fp32 path promises.
+__device__ __forceinline__ void split4(const float (&a)[4], float (&h)[4], float (&l)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) split_tf32(a[i], h[i], l[i]);
+}
+__device__ __forceinline__ void mma_x3(float (&d)[4], const float (&ah)[4], const float (&al)[4], float b0h, float b1h, float b0l, float b1l) {
+  mma_tf32(d, al[0], al[1], al[2], al[3], b0h, b1h);
+  mma_tf32(d, ah[0], ah[1], ah[2], ah[3], b0l, b1l);
+  mma_tf32(d, ah[0], ah[1], ah[2], ah[3], b0h, b1h);
+}
+__device__ __forceinline__ void mma_x3_raw(float (&d)[4], const float (&ah)[4], const float (&al)[4], float b0, float b1) {
+  float b0h, b0l, b1h, b1l;
+  split_tf32(b0, b0h, b0l); split_tf32(b1, b1h, b1l);
+  mma_x3(d, ah, al, b0h, b1h, b0l, b1l);
+}
+// tanh / sigmoid for the recomputed gate: ex2.approx + rcp.approx are good to ~2 ulp, i.e. ~2e-7 absolute on outputs in
+// [-1, 1] (tanh.approx alone is 5e-4)
+__device__ __forceinline__ float tanh_ex2(float x) {
+  const float e = __expf(2.0f * fminf(fmaxf(x, -15.f), 15.f));
+  return 1.0f - 2.0f * __frcp_rn(e + 1.0f);
+}
+
 template <bool SKIP>
 __global__ void __launch_bounds__(kThreads)
 k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const float* __restrict__ filt_k,
@@ -264,11 +289,11 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
 // Tile = 64 time steps, 8 warps.  Stages 1-2: warp (mt = warp & 3, nh = warp >> 2) owns rows 16 mt.. and channels
 // 16 nh..; stage 3 (dWr = c^T dres over the tile's rows): warp (mi = warp & 1, ni = warp >> 1) owns one 16x8 block.
 struct GateSmem {
-  float a_tap[kTT][kAP], a_cur[kTT][kAP], c[kTT][kAP], g[kTT][kAP];
-  float wf[2 * kR][kWP], wr[kR][kAP], bf[kR];
+  float a_tap[kTT][kAP], a_cur[kTT][kAP], c[kTT][kAP], g[kTT][kAP];      // fp32 as loaded / computed (split at fragment load)
+  float wf_h[2 * kR][kWP], wf_l[2 * kR][kWP], wr_h[kR][kAP], wr_l[kR][kAP], bf[kR];
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float* __restrict__ da_out,
            const float* __restrict__ filt_k, const float* __restrict__ filt_b, const float* __restrict__ res_k,
            float* __restrict__ partial,            // [gridDim.x][kR*kR + kR]: dWr | dbr
@@ -276,8 +301,8 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GateSmem& s = *reinterpret_cast<GateSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  for (int i = tid; i < 2 * kR * kR; i += kThreads) s.wf[i / kR][i % kR] = tf32r(filt_k[i]);
-  for (int i = tid; i < kR * kR; i += kThreads) s.wr[i / kR][i % kR] = tf32r(res_k[i]);
+  for (int i = tid; i < 2 * kR * kR; i += kThreads) split_tf32(filt_k[i], s.wf_h[i / kR][i % kR], s.wf_l[i / kR][i % kR]);
+  for (int i = tid; i < kR * kR; i += kThreads) split_tf32(res_k[i], s.wr_h[i / kR][i % kR], s.wr_l[i / kR][i % kR]);
   if (tid < kR) s.bf[tid] = filt_b[tid];
   const int tiles_per_b = (T + kTT - 1) / kTT;
   const int n_tiles = B * tiles_per_b;
@@ -301,9 +326,9 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
         if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + c4 * 4);
       }
       gg.x *= SRWN_SQRT_HALF; gg.y *= SRWN_SQRT_HALF; gg.z *= SRWN_SQRT_HALF; gg.w *= SRWN_SQRT_HALF;   // dres
-      *reinterpret_cast<float4*>(&s.a_cur[row][c4 * 4]) = tf32r4(cur);
-      *reinterpret_cast<float4*>(&s.a_tap[row][c4 * 4]) = tf32r4(tap);
-      *reinterpret_cast<float4*>(&s.g[row][c4 * 4]) = tf32r4(gg);
+      *reinterpret_cast<float4*>(&s.a_cur[row][c4 * 4]) = cur;
+      *reinterpret_cast<float4*>(&s.a_tap[row][c4 * 4]) = tap;
+      *reinterpret_cast<float4*>(&s.g[row][c4 * 4]) = gg;
     }
     __syncthreads();
     // stage 1: a = [x[t-d] | x[t]] Wf + bf (ops.py:6-20), f = tanh(a), c = f sigmoid(f) (ops.py:28,33,36)
@@ -317,33 +342,36 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
     for (int ks = 0; ks < 8; ks++) {
       const float (*X)[kAP] = ks < 4 ? s.a_tap : s.a_cur;
       const int kc = (ks & 3) * 8;
-      const float a0 = X[r0 + g][kc + q], a1 = X[r0 + g + 8][kc + q], a2 = X[r0 + g][kc + q + 4], a3 = X[r0 + g + 8][kc + q + 4];
+      const float a[4] = {X[r0 + g][kc + q], X[r0 + g + 8][kc + q], X[r0 + g][kc + q + 4], X[r0 + g + 8][kc + q + 4]};
+      float ah[4], al[4];
+      split4(a, ah, al);
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) {
         const int n0 = nh * 16 + nt * 8;
-        mma_tf32(acc[nt], a0, a1, a2, a3, s.wf[ks * 8 + q][n0 + g], s.wf[ks * 8 + q + 4][n0 + g]);
+        mma_x3(acc[nt], ah, al, s.wf_h[ks * 8 + q][n0 + g], s.wf_h[ks * 8 + q + 4][n0 + g], s.wf_l[ks * 8 + q][n0 + g], s.wf_l[ks * 8 + q + 4][n0 + g]);
       }
     }
 #pragma unroll
     for (int nt = 0; nt < 2; nt++) {
       const int n0 = nh * 16 + nt * 8 + 2 * q;
 #pragma unroll
-      // recomputed gate: the operands are TF32 already (2^-11), so the MUFU approximations (tanh.approx, ex2 / rcp) cost nothing
-      // in accuracy here; the forward pass that produced the stored activations uses the accurate functions
-      for (int e = 0; e < 4; e++) { fv[nt][e] = tanh_approx(acc[nt][e]); sv[nt][e] = sigmoid_fast(fv[nt][e]); }
-      *reinterpret_cast<float2*>(&s.c[r0 + g][n0]) = make_float2(tf32r(fv[nt][0] * sv[nt][0]), tf32r(fv[nt][1] * sv[nt][1]));
-      *reinterpret_cast<float2*>(&s.c[r0 + g + 8][n0]) = make_float2(tf32r(fv[nt][2] * sv[nt][2]), tf32r(fv[nt][3] * sv[nt][3]));
+      // recomputed gate (ex2 / rcp based: ~2e-7 absolute, see tanh_ex2)
+      for (int e = 0; e < 4; e++) { fv[nt][e] = tanh_ex2(acc[nt][e]); sv[nt][e] = sigmoid_fast(fv[nt][e]); }
+      *reinterpret_cast<float2*>(&s.c[r0 + g][n0]) = make_float2(fv[nt][0] * sv[nt][0], fv[nt][1] * sv[nt][1]);
+      *reinterpret_cast<float2*>(&s.c[r0 + g + 8][n0]) = make_float2(fv[nt][2] * sv[nt][2], fv[nt][3] * sv[nt][3]);
     }
     // stage 2: dc[t][k] = sum_n dres[t][n] Wr[k][n]  (same (row, channel) positions as a / f)
     float dc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       const int kc = ks * 8;
-      const float a0 = s.g[r0 + g][kc + q], a1 = s.g[r0 + g + 8][kc + q], a2 = s.g[r0 + g][kc + q + 4], a3 = s.g[r0 + g + 8][kc + q + 4];
+      const float a[4] = {s.g[r0 + g][kc + q], s.g[r0 + g + 8][kc + q], s.g[r0 + g][kc + q + 4], s.g[r0 + g + 8][kc + q + 4]};
+      float ah[4], al[4];
+      split4(a, ah, al);
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) {
         const int k0 = nh * 16 + nt * 8;
-        mma_tf32(dc[nt], a0, a1, a2, a3, s.wr[k0 + g][kc + q], s.wr[k0 + g][kc + q + 4]);
+        mma_x3(dc[nt], ah, al, s.wr_h[k0 + g][kc + q], s.wr_h[k0 + g][kc + q + 4], s.wr_l[k0 + g][kc + q], s.wr_l[k0 + g][kc + q + 4]);
       }
     }
 #pragma unroll
@@ -365,7 +393,10 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
 #pragma unroll
     for (int ks = 0; ks < 8; ks++) {
       const int tq = ks * 8 + q, m0 = mi * 16 + g, n0 = ni * 8 + g;
-      mma_tf32(gw, s.c[tq][m0], s.c[tq][m0 + 8], s.c[tq + 4][m0], s.c[tq + 4][m0 + 8], s.g[tq][n0], s.g[tq + 4][n0]);
+      const float a[4] = {s.c[tq][m0], s.c[tq][m0 + 8], s.c[tq + 4][m0], s.c[tq + 4][m0 + 8]};
+      float ah[4], al[4];
+      split4(a, ah, al);
+      mma_x3_raw(gw, ah, al, s.g[tq][n0], s.g[tq + 4][n0]);
     }
     if (warp == 0) {
 #pragma unroll 8
@@ -388,7 +419,7 @@ k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float*
 // input rows 16 mi.. of the 64 stacked rows and output channels 16 nj...
 struct ConvSmem {
   float a_tap[kTT][kAP], a_cur[kTT][kAP], da[kTT][kAP], da_f[kTT][kAP];
-  float w0[kR][kAP], w1[kR][kAP];              // [cin][cout] as stored (read as (cin = g, cout = q))
+  float w0_h[kR][kAP], w0_l[kR][kAP], w1_h[kR][kAP], w1_l[kR][kAP];   // [cin][cout] as stored (read as (cin = g, cout = q)), split
   float red[4][kR];
 };
 
@@ -402,8 +433,8 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
   ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   for (int i = tid; i < kR * kR; i += kThreads) {
-    s.w0[i / kR][i % kR] = tf32r(filt_k[i]);
-    s.w1[i / kR][i % kR] = tf32r(filt_k[kR * kR + i]);
+    split_tf32(filt_k[i], s.w0_h[i / kR][i % kR], s.w0_l[i / kR][i % kR]);
+    split_tf32(filt_k[kR * kR + i], s.w1_h[i / kR][i % kR], s.w1_l[i / kR][i % kR]);
   }
   const int tiles_per_b = (T + kTT - 1) / kTT;
   const int n_tiles = B * tiles_per_b;
@@ -427,10 +458,10 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
         if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + c4 * 4);
         if (t + d < T) af = *reinterpret_cast<const float4*>(db + (size_t)(t + d) * kR + c4 * 4);
       }
-      *reinterpret_cast<float4*>(&s.a_cur[row][c4 * 4]) = tf32r4(cur);
-      *reinterpret_cast<float4*>(&s.a_tap[row][c4 * 4]) = tf32r4(tap);
-      *reinterpret_cast<float4*>(&s.da[row][c4 * 4]) = tf32r4(a);
-      *reinterpret_cast<float4*>(&s.da_f[row][c4 * 4]) = tf32r4(af);
+      *reinterpret_cast<float4*>(&s.a_cur[row][c4 * 4]) = cur;
+      *reinterpret_cast<float4*>(&s.a_tap[row][c4 * 4]) = tap;
+      *reinterpret_cast<float4*>(&s.da[row][c4 * 4]) = a;
+      *reinterpret_cast<float4*>(&s.da_f[row][c4 * 4]) = af;
     }
     __syncthreads();
     // stage 1: dx[t][k] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]
@@ -438,13 +469,16 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
 #pragma unroll
     for (int ks = 0; ks < 8; ks++) {
       const float (*A)[kAP] = ks < 4 ? s.da : s.da_f;
-      const float (*W)[kAP] = ks < 4 ? s.w1 : s.w0;
+      const float (*Wh)[kAP] = ks < 4 ? s.w1_h : s.w0_h;
+      const float (*Wl)[kAP] = ks < 4 ? s.w1_l : s.w0_l;
       const int kc = (ks & 3) * 8;
-      const float a0 = A[r0 + g][kc + q], a1 = A[r0 + g + 8][kc + q], a2 = A[r0 + g][kc + q + 4], a3 = A[r0 + g + 8][kc + q + 4];
+      const float a[4] = {A[r0 + g][kc + q], A[r0 + g + 8][kc + q], A[r0 + g][kc + q + 4], A[r0 + g + 8][kc + q + 4]};
+      float ah[4], al[4];
+      split4(a, ah, al);
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) {
         const int k0 = nh * 16 + nt * 8;
-        mma_tf32(acc[nt], a0, a1, a2, a3, W[k0 + g][kc + q], W[k0 + g][kc + q + 4]);
+        mma_x3(acc[nt], ah, al, Wh[k0 + g][kc + q], Wh[k0 + g][kc + q + 4], Wl[k0 + g][kc + q], Wl[k0 + g][kc + q + 4]);
       }
     }
     const int ta = t0 + r0 + g, tb = ta + 8;
@@ -486,11 +520,13 @@ k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const 
 #pragma unroll
       for (int ks = 0; ks < 8; ks++) {
         const int tq = ks * 8 + q;
-        const float a0 = X[tq][m0], a1 = X[tq][m0 + 8], a2 = X[tq + 4][m0], a3 = X[tq + 4][m0 + 8];
+        const float a[4] = {X[tq][m0], X[tq][m0 + 8], X[tq + 4][m0], X[tq + 4][m0 + 8]};
+        float ah[4], al[4];
+        split4(a, ah, al);
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           const int n0 = nj * 16 + nt * 8 + g;
-          mma_tf32(gw[nt], a0, a1, a2, a3, s.da[tq][n0], s.da[tq + 4][n0]);
+          mma_x3_raw(gw[nt], ah, al, s.da[tq][n0], s.da[tq + 4][n0]);
         }
       }
     }

@@ -7,7 +7,7 @@ from oracle import distill_torch as dt
 from sr_wavenet_b200 import synth
 
 pytestmark = pytest.mark.gpu
-GRAD_TOL = 2e-3      # tightened to the measured error below
+GRAD_TOL = 1e-4      # fp32-grade backward (3xTF32 GEMMs, ex2-based gate recompute): the north star's bound for the fp32 path
 
 
 @pytest.fixture(scope="module")
@@ -215,12 +215,17 @@ def test_per_example_train_matches_reference_semantics(srwn):
     np.testing.assert_allclose(power, np.mean(powers), rtol=1e-4)
     s.sync_weights()
     new = s.get_weights()
-    # first Adam step: |update| = lr * |g| / (|g| + eps) -- for the few entries whose averaged gradient is as small as eps
-    # the gradient's relative error (TF32 backward GEMMs, ~1e-3) shows up in full: a fraction of one step (lr = 1e-3) for
-    # under 5 % of the entries, 5e-6 for the rest
+    # first Adam step: update = lr * g / (|g| + eps), i.e. +-lr for every entry whose gradient is well above eps = 1e-8.  An
+    # entry whose per-example gradients cancel in the average (|g| ~ eps) can land anywhere in [-lr, lr] for a relative
+    # gradient error of 1e-5, so a fraction of a percent of the entries may differ by up to 2 lr; all others agree to 5e-6.
+    n_bad = n_all = 0
     for k, (wr, _, _) in zip(names, ref):
-        np.testing.assert_allclose(new[k], wr, rtol=0, atol=2e-4)
-        assert np.mean(np.abs(new[k] - wr) > 5e-6) < 0.05
+        diff = np.abs(new[k] - wr)
+        assert diff.max() <= 2.1e-3, (k, diff.max())
+        n_bad += int((diff > 5e-6).sum())
+        n_all += diff.size
+    print("per-example train: %d of %d weights differ by more than 5e-6 after one Adam step" % (n_bad, n_all))
+    assert n_bad <= 0.005 * n_all
 
 
 def test_create_flow_matches_oracle(srwn):
