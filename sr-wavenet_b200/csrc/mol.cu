@@ -2,14 +2,14 @@
 #include "common.cuh"
 #include "mol.cuh"
 
-// deterministic two-level reduction scratch (a handle is not thread-safe; one stream at a time)
+// Deterministic two-level reduction: per-block partial sums go to a scratch array that belongs to THIS call (stream-ordered
+// allocation), a second one-thread kernel adds them in a fixed order.  (Round 1 kept the partials in process-global device
+// variables: two handles or streams calling srwn_mol_loss concurrently corrupted each other's sums -- ADVICE r1.)
 constexpr int kMaxRedBlocks = 2048;
-__device__ double g_red_partials[kMaxRedBlocks];
-__device__ unsigned int g_red_counter = 0;
 
 __global__ void __launch_bounds__(256)
 k_mol_loss(const float* __restrict__ x, const float* __restrict__ l, float* __restrict__ nll_out,
-           float* __restrict__ nll_sum, int64_t n, int M) {
+           double* __restrict__ partial, int64_t n, int M) {
   double local = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -20,27 +20,23 @@ k_mol_loss(const float* __restrict__ x, const float* __restrict__ l, float* __re
     if (nll_out) nll_out[i] = v;
     local += (double)v;
   }
-  if (!nll_sum) return;
+  if (!partial) return;
   __shared__ double s_part[8];
   for (int s = 16; s >= 1; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
   __syncthreads();
-  __shared__ bool s_last;
   if (threadIdx.x == 0) {
     double b = 0;
     for (int w = 0; w < 8; w++) b += s_part[w];
-    g_red_partials[blockIdx.x] = b;
-    __threadfence();
-    const unsigned int done = atomicAdd(&g_red_counter, 1u);
-    s_last = done == gridDim.x - 1;
+    partial[blockIdx.x] = b;
   }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
+}
+
+__global__ void k_mol_loss_sum(const double* __restrict__ partial, int n, float* __restrict__ nll_sum) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
     double tot = 0;
-    for (unsigned int bI = 0; bI < gridDim.x; bI++) tot += ((volatile double*)g_red_partials)[bI];
+    for (int i = 0; i < n; i++) tot += partial[i];
     *nll_sum = (float)tot;            // ops.py:172  -reduce_sum(log_sum_exp(...))
-    g_red_counter = 0;
   }
 }
 
@@ -50,8 +46,15 @@ int run_mol_loss(const float* x, const float* l, float* nll_out, float* nll_sum,
   const int64_t n = (int64_t)B * T;
   int64_t blocks = (n + 255) / 256;
   if (blocks > kMaxRedBlocks) blocks = kMaxRedBlocks;
-  k_mol_loss<<<(unsigned)blocks, 256, 0, st>>>(x, l, nll_out, nll_sum, n, M);
+  double* partial = nullptr;
+  if (nll_sum) SRWN_CUDA(cudaMallocAsync((void**)&partial, (size_t)blocks * sizeof(double), st));
+  k_mol_loss<<<(unsigned)blocks, 256, 0, st>>>(x, l, nll_out, partial, n, M);
   SRWN_LAUNCH_CHECK();
+  if (nll_sum) {
+    k_mol_loss_sum<<<1, 32, 0, st>>>(partial, (int)blocks, nll_sum);
+    SRWN_LAUNCH_CHECK();
+    SRWN_CUDA(cudaFreeAsync(partial, st));
+  }
   return SRWN_OK;
 }
 
