@@ -236,6 +236,9 @@ class _CheckpointMixin(object):
                 tf_checkpoint.write_checkpoint(path, self.get_weights())
             else:
                 np.savez(path + '.npz', **self.get_weights())
+            if isinstance(self, WaveNetAutoEncoder):      # tf.train.Saver.save also exports the meta-graph the student imports
+                from . import tf_meta
+                tf_meta.write_meta(path + '.meta', *tf_meta.teacher_meta_skeleton(self.name))
             with open(os.path.join(logdir, 'checkpoint'), 'w') as f:
                 f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
             self.last_checkpoint_time = time.time()
@@ -379,6 +382,11 @@ class WaveNetAutoEncoder(_CheckpointMixin):
                 skip_channels=head2[1], latent_channels=latent_channels, pool_stride=pool_stride)
         if not t.load(logdir):
             raise IOError("could not restore the teacher from %s" % logdir)
+        if os.path.exists(path + '.meta'):
+            # the part of tf.train.import_meta_graph(..., input_map=...) + get_collection(...)[0] (model.py:326-341) that can
+            # fail: the placeholders the student re-wires and the collections it reads must exist in the teacher's graph
+            from . import tf_meta
+            t.meta_collections = tf_meta.check_teacher_contract(tf_meta.read_meta(path + '.meta'), t.name)
         return t
 
     # -- sess.run wrappers -------------------------------------------------------------------
