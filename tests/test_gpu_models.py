@@ -357,6 +357,17 @@ def test_tf_bundle_checkpoint_roundtrip(srwn, tmp_path):
     s = srwn.ParallelWaveNet(256, 0, dil, str(tmp_path / "b"), num_flows=2, skip_channels=128, latent_channels=32, pool_stride=128)
     assert s.teacher.num_mixtures == 5 and s.teacher.skip_channels == 128
     np.testing.assert_array_equal(s.teacher.get_logits(x, enc), a)
+    # a directory written by WaveNetAutoEncoder.save also carries the .meta skeleton; the student checks the placeholders of
+    # its input_map and the collections it reads (model.py:326-341)
+    assert os.path.exists(str(tmp_path / "a" / "model.ckpt-3.meta"))
+    s2 = srwn.ParallelWaveNet(256, 0, dil, str(tmp_path / "a"), num_flows=2, skip_channels=128, latent_channels=32, pool_stride=128)
+    assert set(s2.teacher.meta_collections) == {"Logits_d", "Encoding_output", "Inputs_e", "Out_e", "Out_d"}
+    from sr_wavenet_b200 import tf_meta
+    nodes, cols = tf_meta.teacher_meta_skeleton()
+    del cols["Out_d"]
+    tf_meta.write_meta(str(tmp_path / "a" / "model.ckpt-3.meta"), nodes, cols)
+    with pytest.raises(IndexError):
+        srwn.ParallelWaveNet(256, 0, dil, str(tmp_path / "a"), num_flows=2, skip_channels=128, latent_channels=32, pool_stride=128)
 
 
 def test_device_resident_path(srwn):
