@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
   const int nseg = p.nseg[team];
   uint8_t* ring = p.rings + (size_t)team * p.ring_bytes_per_team;
   uint32_t* flags = p.flags + (size_t)team * kMaxLayers;
-  const uint32_t acq_addr = sbase + SmemMap::misc + 16; // rings of predecessor chunks the watcher warp has acquired so far (monotonic)
-  uint32_t acq_need = 0;                                // loader / watcher: position in that sequence
+  const uint32_t acq_addr = sbase + SmemMap::misc + 16; // [2 ring parities] rings of predecessor chunks the watcher warp has acquired so far (monotonic)
+  uint32_t acq_e = 0, acq_o = 0;                        // loader / watcher: position in those two sequences
   int seq = 0;                                          // chunk sequence number inside the piece
   constexpr bool handoff = HANDOFF;
   int u0e = 0, u0o = 0, lay_base = 0;                 // phases of the parity-indexed / per-layer barriers used so far
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
           // ring l of the previous chunk of the piece (written by another member of the team unless G == 1); also taken
           // at an utterance start, where the rows are not read: this chunk may overwrite the ring only after chunk n-1
           // has read it, which its publication implies
-          if (handoff && n > 0 && !acq_wait(acq_addr, ++acq_need, abort_flag, 0x1200000 | l, p.wait_limit)) break;
+          if (handoff && n > 0 && !acq_wait(acq_addr + 4 * s, s ? ++acq_o : ++acq_e, abort_flag, 0x1200000 | l, p.wait_limit)) break;
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
@@ -433,57 +433,56 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
         // a pruned warm-up chunk writes ring Lc behind its last layer without reading it: the write has to come after
         // chunk n-1's rows of the same ring
         if (Lc < L && !*abort_flag) {
-          const bool ok = n == 0 || !handoff || acq_wait(acq_addr, ++acq_need, abort_flag, 0x1300000 | Lc, p.wait_limit);
+          const bool ok = n == 0 || !handoff || acq_wait(acq_addr + 4 * (Lc & 1), (Lc & 1) ? ++acq_o : ++acq_e, abort_flag, 0x1300000 | Lc, p.wait_limit);
           if (ok && lane == 0) mbar_arrive(bar(BAR_TAIL));
         }
       } else if (HANDOFF && warp == kWatchWarp) {
         // ================= watcher: acquires the predecessor chunk's ring flags ahead of the loader ================
         // The GPU-scope acquire (an L2 round trip plus a fence) happens here, off every critical path; the loader then only
-        // reads a shared-memory counter.  Same sequence of (chunk, ring) as the loader's waits.
-        if (n > 0) {
+        // reads a shared-memory counter.  Lane s follows the rings of parity s (two independent sequences: an acquire takes
+        // about as long as a layer), in the same order as the loader's waits.
+        if (n > 0 && lane < 2) {
           const int n_wait = Lc + (Lc < L ? 1 : 0);
-          for (int r = 0; r < n_wait; r++) {
+          for (int r = lane; r < n_wait; r += 2) {
             bool ok = true;
-            if (lane == 0) {
-              if (ld_relaxed_gpu(flags + r) < (uint32_t)n) {
-                const long long t0 = clock64();
-                int spins = 0;
-                while (ld_relaxed_gpu(flags + r) < (uint32_t)n) {
-                  __nanosleep(64);
-                  if (*abort_flag) { ok = false; break; }
-                  if (((++spins) & 1023) == 0 && *reinterpret_cast<const volatile int*>(p.err)) { ok = false; break; }
-                  if (clock64() - t0 > p.wait_limit) {
-                    if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = 0x5000000 | r;
-                    ok = false; break;
-                  }
+            if (ld_relaxed_gpu(flags + r) < (uint32_t)n) {
+              const long long t0 = clock64();
+              int spins = 0;
+              while (ld_relaxed_gpu(flags + r) < (uint32_t)n) {
+                __nanosleep(64);
+                if (*abort_flag) { ok = false; break; }
+                if (((++spins) & 1023) == 0 && *reinterpret_cast<const volatile int*>(p.err)) { ok = false; break; }
+                if (clock64() - t0 > p.wait_limit) {
+                  if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = 0x5000000 | r;
+                  ok = false; break;
                 }
               }
-              if (ok) {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");        // pairs with the publisher's release: the ring rows are visible
-                st_release_cta_shared(acq_addr, ++acq_need);
-              }
             }
-            if (!__shfl_sync(0xffffffffu, (int)ok, 0)) break;
+            if (!ok) break;
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");          // pairs with the publisher's release: the ring rows are visible
+            st_release_cta_shared(acq_addr + 4 * lane, lane ? ++acq_o : ++acq_e);
           }
         }
+        __syncwarp();
       } else if (HANDOFF && warp == kPubWarp) {
         // ================= publisher: copies ring r of this chunk to the team's ring block, then flags[r] = n + 1 ==========
         // The rows of ring r are the last min(d_r, kChunk) chunk rows of the activation buffer of parity r & 1 (front conv for
         // r = 0, residual epilogue of layer r-1 otherwise): the tile groups only signal that their rows are in shared memory
-        // (the HD barriers the higher tiles wait on anyway); ONE lane moves them with bulk copies shared -> global and
-        // publishes the flag once they have completed.  Nothing of the hand-off runs on the layer chain.
+        // (the HD barriers the higher tiles wait on anyway); a publisher lane moves them with bulk copies shared -> global and
+        // raises the flag once they have completed.  Nothing of the hand-off runs on the layer chain.  Copy + completion +
+        // GPU-scope release take about two layer times, so lane s serves the rings of parity s, independently of the other.
         const int last = Lc < L - 1 ? Lc : L - 1;
-        bool ok = true;
-        for (int r = 0; r <= last && ok; r++) {
-          const int s = r & 1, d = p.dil[r];
-          const bool tail = r == Lc;                                  // pruned warm-up chunk: rows behind its last layer
-          for (int m = 0; m < kTiles && ok; m++) {
-            if (ring_rows_of(d, m) == 0) continue;
-            ok = tail ? mbar_wait(bar(BAR_TAILHD + m), tail_idx & 1, abort_flag, 0x4100000 | (m << 8) | r, p.wait_limit)
-                      : mbar_wait(bar(BAR_HD + 2 * m + s), (U0(s) + (r >> 1)) & 1, abort_flag, 0x4000000 | (m << 8) | r, p.wait_limit);
-          }
-          if (!ok) break;
-          if (lane == 0) {
+        if (lane < 2) {
+          for (int r = lane; r <= last; r += 2) {
+            const int s = lane, d = p.dil[r];
+            const bool tail = r == Lc;                                // pruned warm-up chunk: rows behind its last layer
+            bool ok = true;
+            for (int m = 0; m < kTiles && ok; m++) {
+              if (ring_rows_of(d, m) == 0) continue;
+              ok = tail ? mbar_wait(bar(BAR_TAILHD + m), tail_idx & 1, abort_flag, 0x4100000 | (m << 8) | r, p.wait_limit)
+                        : mbar_wait(bar(BAR_HD + 2 * m + s), (U0(s) + (r >> 1)) & 1, abort_flag, 0x4000000 | (m << 8) | r, p.wait_limit);
+            }
+            if (!ok) break;
             const int cnt = d < kChunk ? d : kChunk;                  // new rows: the chunk's last cnt rows
             const int slot0 = (int)((unsigned)(t0 + kChunk - cnt) % (unsigned)d);
             const int n1 = cnt < d - slot0 ? cnt : d - slot0;
@@ -501,10 +500,10 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             asm volatile("fence.proxy.async.global;" ::: "memory");             // ... and ordered before the generic-proxy release below
             flag_publish(flags + r, (uint32_t)n + 1);
           }
-          __syncwarp();
         }
+        __syncwarp();
         // rings this (warm-up) chunk did not write hold rows nobody reads: release them right away
-        if (ok && lane == 0)
+        if (lane == 0 && !*abort_flag)
           for (int r = last + 1; r < L; r++) flag_publish(flags + r, (uint32_t)n + 1);
       } else {
         // ================= tile group m: MMA issue + epilogues; row = TMEM lane ====================

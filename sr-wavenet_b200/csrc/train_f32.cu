@@ -83,7 +83,13 @@ struct FwdSmemSkip {
   float wf_h[2 * kR][kWP], wf_l[2 * kR][kWP], wr_h[kR][kWP], wr_l[kR][kWP], bf[kR], br[kR];
   float ws_h[kR][kSP], ws_l[kR][kSP], bs[kS];
 };
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) { hi = tf32r(x); lo = tf32r(x - hi); }
+// x = hi + lo with both parts valid TF32 numbers (low 13 mantissa bits clear).  Truncation instead of cvt.rna: hi is off by
+// up to 2^-10 |x| but x - hi is exact, and truncating lo costs 2^-10 |lo| <= 2^-20 |x|; two LOP3 + one FADD, where
+// cvt.rna.tf32.f32 expands to ~5 instructions each on sm_100a (FSETP / VIADD / SEL / LOP3: half of k_bwd_gate's ALU work).
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void split_store4(float* h, float* l, float4 v) {
   float4 vh, vl;
   split_tf32(v.x, vh.x, vl.x); split_tf32(v.y, vh.y, vl.y); split_tf32(v.z, vh.z, vl.z); split_tf32(v.w, vh.w, vl.w);
