@@ -212,6 +212,14 @@ __device__ __noinline__ bool flag_spin(const uint32_t* f, uint32_t need, volatil
     }
   }
 }
+// one acquire load, no spin: used to take the NEXT ring's flag while the loader would otherwise idle
+__device__ __forceinline__ bool flag_try(const uint32_t* f, uint32_t need) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  if (v < need) return false;
+  asm volatile("fence.proxy.async;" ::: "memory");
+  return true;
+}
 __device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, volatile int* abort_flag, const int* gerr, int code, long long limit) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
@@ -345,6 +353,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
 
       if (warp == kLoadWarp) {
         // ================= loader: weights (bulk copy) + halo rows (cp.async) per layer ============
+        bool have_next = false;                                // the flag of ring l was acquired during the previous iteration
         for (int l = 0; l < Lc; l++) {
           const int s = l & 1;
           const int use = U0(s) + (l >> 1);                  // how many times stage s was used before
@@ -357,7 +366,9 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
           // ring l of the previous chunk of the piece (written by another member of the team unless G == 1); also taken
           // at an utterance start, where the rows are not read: this chunk may overwrite the ring only after chunk n-1
           // has read it, which its publication implies
-          if (handoff && !(SRWN_VAR & 2) && n > 0 && !flag_wait(flags + l, (uint32_t)n, abort_flag, p.err, 0x1200000 | l, p.wait_limit)) break;
+          if (handoff && !(SRWN_VAR & 2) && n > 0 && !have_next &&
+              !flag_wait(flags + l, (uint32_t)n, abort_flag, p.err, 0x1200000 | l, p.wait_limit)) break;
+          have_next = false;
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
           const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
@@ -398,6 +409,9 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_HALO + s));
           }
+          // the acquire of the next ring's flag (an L2 round trip and a fence, about a microsecond) goes here, where the loader
+          // would wait for the weight stage anyway, instead of between "buffer free" and the halo copy of the next layer
+          if (handoff && !(SRWN_VAR & 2) && n > 0 && l + 1 < Lc) have_next = flag_try(flags + l + 1, (uint32_t)n);
           if (!mbar_wait(bar(BAR_WEMPTY + s), (use & 1) ^ 1, abort_flag, 0x1000000 | l, p.wait_limit)) break;
           if (lane == 0) {
             mbar_expect_tx(bar(BAR_WFULL + s), layer_bytes);
