@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
               if ((int32_t)(ld_acquire_cta_shared(ringcnt + 4 * lane) - pub_expect) < 0) {
                 const long long t0 = clock64();
                 while ((int32_t)(ld_acquire_cta_shared(ringcnt + 4 * lane) - pub_expect) < 0) {
-                  __nanosleep(128);            // this warp has the highest id of its scheduler: a busy spin would starve the tile warps there
+                  __nanosleep((SRWN_VAR & 8) ? 1000 : 128);            // this warp has the highest id of its scheduler: a busy spin would starve the tile warps there
                   if (*abort_flag) { ok = false; break; }
                   if (clock64() - t0 > p.wait_limit) {
                     if (atomicCAS((int*)abort_flag, 0, 1) == 0) ((int*)abort_flag)[1] = 0x4000000 | (lane << 8) | r;
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             }
           }
           ok = __all_sync(0xffffffffu, ok);
-          if (ok && lane == 0) flag_publish(flags + r, (uint32_t)n + 1);
+          if (ok && lane == 0 && !(SRWN_VAR & 16)) flag_publish(flags + r, (uint32_t)n + 1);
         }
         // rings this (warm-up) chunk did not write hold rows nobody reads: release them right away
         if (ok && lane == 0)
