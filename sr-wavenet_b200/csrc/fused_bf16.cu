@@ -839,11 +839,15 @@ __global__ void k_fold_bias(const float* __restrict__ cond, const float* __restr
 }
 
 
-// conditioning 1x1 (model.py:180/431) and the bias folding above in one pass, 8 latent frames per CTA so that the
-// conditioning weights are read once per 8 frames:
+// conditioning 1x1 (model.py:180/431) and the bias folding above in one pass, kCondRows latent frames per CTA so that the
+// conditioning weights are read once per kCondRows frames:
 // cb[bf][l] = enc[bf] @ Wc_l + bc_l + (l == 0 ? front_b : sqrt(1/2) res_b[l-1]);  cb[bf][L] = sqrt(1/2) res_b[L-1]
-constexpr int kCondRows = 8;
-__global__ void __launch_bounds__(256)
+#ifndef SRWN_COND_ROWS
+#define SRWN_COND_ROWS 32
+#endif
+// 8 rows per CTA re-read the 127 KB of conditioning weights from L2 2000 times at 32x64000 (61 us); 32 rows: 4x less
+constexpr int kCondRows = SRWN_COND_ROWS;
+__global__ void __launch_bounds__(256, 2)
 k_cond_fold(const float* __restrict__ enc, const float* __restrict__ cond_k, const float* __restrict__ cond_b,
             const float* __restrict__ front_b, const float* __restrict__ res_b, float* __restrict__ cb,
             int BF, int L, int C) {
@@ -862,6 +866,7 @@ k_cond_fold(const float* __restrict__ enc, const float* __restrict__ cond_k, con
     for (int r = 0; r < kCondRows; r++) acc[r] = base;
     if (l < L) {
       const float* wk = cond_k + (size_t)l * C * 32 + j;
+#pragma unroll 2
       for (int c = 0; c < C; c++) {
         const float w = __ldg(wk + (size_t)c * 32);
 #pragma unroll
