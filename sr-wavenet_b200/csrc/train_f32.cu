@@ -10,6 +10,7 @@
 //                          row per CTA) and summed by a second kernel in a fixed order (deterministic).
 #include "common.cuh"
 #include "mol.cuh"
+#include "train_tc.cuh"
 #include <type_traits>
 
 __global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ cond_k,
@@ -834,14 +835,15 @@ int run_entropy(const float* s_tot, double* per_example, int B, int T, cudaStrea
 // ---- host ----------------------------------------------------------------------------------------------
 struct TrainWs {
   float *acts, *cond, *scales, *means, *xs, *g0, *g1, *da, *dcond, *d_scales, *d_means, *dxa, *dxb, *partial, *partial_gate, *partial_conv;
-  size_t bytes; int grid;
+  size_t bytes; int grid, grid_tc;
 };
 
 static TrainWs carve_train(const srwn_ctx* c, int B, int T, void* ws, size_t cap) {
   WsCarver w(ws, cap);
   TrainWs r{};
   const size_t n = (size_t)B * T, L = c->cfg.n_layers, F = c->cfg.num_flows, frames = T / c->cfg.pool_stride;
-  r.grid = 3 * (c->sm_count > 0 ? c->sm_count : 148);     // three CTAs of k_bwd_gate / k_bwd_conv fit one SM (registers, shared memory)
+  r.grid = 3 * (c->sm_count > 0 ? c->sm_count : 148);     // elementwise kernels of the step (heads, front)
+  r.grid_tc = c->sm_count > 0 ? c->sm_count : 148;         // tensor-core layer kernels: one persistent CTA per SM (shared memory)
   r.acts = w.take<float>(F * (L + 1) * n * kR);
   r.cond = w.take<float>((size_t)B * frames * L * kR);
   r.scales = w.take<float>(F * n);
@@ -886,9 +888,9 @@ int run_layer_tf32x3(srwn_ctx* c, bool with_skip, const float* x_l, float* x_nex
     SRWN_CUDA(launch_dependent(train::k_fwd_layer<true>, grid, train::kThreads, sizeof(train::FwdSmemSkip), st,
         x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, skip_k, skip_b, skip, skip_init));
   } else {
-    SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmem)));
-    SRWN_CUDA(launch_dependent(train::k_fwd_layer<false>, grid, train::kThreads, sizeof(train::FwdSmem), st,
-        x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, nullptr, nullptr, nullptr, 0));
+    SRWN_CUDA(cudaFuncSetAttribute(traintc::k_fwd_layer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, traintc::fwd_smem_bytes()));
+    SRWN_CUDA(launch_dependent(traintc::k_fwd_layer_tc, grid, traintc::kThreads, (size_t)traintc::fwd_smem_bytes(), st,
+        x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames));
   }
   SRWN_LAUNCH_CHECK();
   return SRWN_OK;
@@ -908,13 +910,13 @@ static int run_stack_train_acts(srwn_ctx* c, int stack, const float* xin, const 
     k_front<<<g, 256, 0, st>>>(xin, w + o.front_k, w + o.front_b, cond, acts, T, P, L, frames);
     SRWN_LAUNCH_CHECK();
   }
-  SRWN_CUDA(cudaFuncSetAttribute(train::k_fwd_layer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(train::FwdSmem)));
+  SRWN_CUDA(cudaFuncSetAttribute(traintc::k_fwd_layer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, traintc::fwd_smem_bytes()));
   for (int l = 0; l < L; l++) {
     const float* cond_next = l + 1 < L ? cond + (size_t)(l + 1) * kR : nullptr;
-    SRWN_CUDA(launch_dependent(train::k_fwd_layer<false>, grid, train::kThreads, sizeof(train::FwdSmem), st,
+    SRWN_CUDA(launch_dependent(traintc::k_fwd_layer_tc, grid, traintc::kThreads, (size_t)traintc::fwd_smem_bytes(), st,
         acts + (size_t)l * n * kR, acts + (size_t)(l + 1) * n * kR, w + o.filt_k + (size_t)l * 2 * kR * kR,
         w + o.filt_b + (size_t)l * kR, w + o.res_k + (size_t)l * kR * kR, w + o.res_b + (size_t)l * kR, cond_next,
-        B, T, c->dilations[l], P, L, frames, nullptr, nullptr, nullptr, 0));
+        B, T, c->dilations[l], P, L, frames));
     SRWN_LAUNCH_CHECK();
   }
   return SRWN_OK;
@@ -929,7 +931,7 @@ int run_student_forward_train(srwn_ctx* c, const float* z, const float* enc, flo
   const float* xin = z;
   for (int f = 0; f < F; f++) {
     float* acts = w.acts + (size_t)f * (L + 1) * n * kR;
-    int rc = run_stack_train_acts(c, f, xin, enc, B, T, acts, w.cond, 2 * (w.grid / 3), st);
+    int rc = run_stack_train_acts(c, f, xin, enc, B, T, acts, w.cond, 2 * w.grid_tc, st);
     if (rc) return rc;
     rc = run_flow_head_f32(c, f, acts + (size_t)L * n * kR, xin, w.scales + (size_t)f * n, w.means + (size_t)f * n,
                            w.xs + (size_t)f * n, B, T, st);
@@ -952,15 +954,15 @@ int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const fl
   const StackOffsets& o = c->off;
   static bool attr_done = false;
   if (!attr_done) {
-    SRWN_CUDA(cudaFuncSetAttribute(k_bwd_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GateSmem)));
-    SRWN_CUDA(cudaFuncSetAttribute(k_bwd_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
+    SRWN_CUDA(cudaFuncSetAttribute(traintc::k_bwd_gate_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, traintc::gate_smem_bytes()));
+    SRWN_CUDA(cudaFuncSetAttribute(traintc::k_bwd_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, traintc::conv_smem_bytes()));
     attr_done = true;
   }
   SRWN_CUDA(cudaMemsetAsync(grads, 0, (size_t)c->n_stacks * c->stack_floats * sizeof(float), st));
   k_bwd_compose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, w.scales, w.means, d_pre, d_s_extra, F, w.d_scales, w.d_means, (int64_t)n);
   SRWN_LAUNCH_CHECK();
-  const int grid = w.grid;
-  ProfScope prof(c, st, "k_bwd_gate+k_bwd_conv (student backward)", F * L * 2);
+  const int grid = w.grid, gtc = w.grid_tc;
+  ProfScope prof(c, st, "k_bwd_gate_tc+k_bwd_conv_tc (student backward)", F * L * 2);
   float* dx_next = nullptr;                  // dLoss/dx_f arriving from flow f+1's front conv (null for the last flow)
   float* dx_cur = w.dxa;
   for (int f = F - 1; f >= 0; f--) {
@@ -981,24 +983,24 @@ int run_student_backward(srwn_ctx* c, const float* z, const float* enc, const fl
       const float* x_l = acts + (size_t)l * n * kR;
       const int d = c->dilations[l];
       // per-CTA weight-gradient partials of every layer are kept ([L][grid][...]) and reduced by ONE launch per flow
-      float* pg = w.partial_gate + (size_t)l * grid * (kR * kR + kR);
-      float* pc = w.partial_conv + (size_t)l * grid * (2 * kR * kR + kR);
-      SRWN_CUDA(launch_dependent(k_bwd_gate, grid, kThreads, sizeof(GateSmem), st, x_l, (const float*)g, w.da,
+      float* pg = w.partial_gate + (size_t)l * gtc * (kR * kR + kR);
+      float* pc = w.partial_conv + (size_t)l * gtc * (2 * kR * kR + kR);
+      SRWN_CUDA(launch_dependent(traintc::k_bwd_gate_tc, gtc, traintc::kThreads, (size_t)traintc::gate_smem_bytes(), st, x_l, (const float*)g, w.da,
                                  sw + o.filt_k + (size_t)l * 2 * kR * kR, sw + o.filt_b + (size_t)l * kR,
                                  sw + o.res_k + (size_t)l * kR * kR, pg, B, T, d));
       SRWN_LAUNCH_CHECK();
       // x_l carries cond_l (added before the block, model.py:183; for l = 0 by the front): dcond_l = sum over the frame of dx_l
-      SRWN_CUDA(launch_dependent(k_bwd_conv, grid, kThreads, sizeof(ConvSmem), st, x_l, (const float*)g, (const float*)w.da, gn,
+      SRWN_CUDA(launch_dependent(traintc::k_bwd_conv_tc, gtc, traintc::kThreads, (size_t)traintc::conv_smem_bytes(), st, x_l, (const float*)g, (const float*)w.da, gn,
                                  sw + o.filt_k + (size_t)l * 2 * kR * kR, pc, w.dcond + (size_t)l * BF * kR, B, T, d, P, frames));
       SRWN_LAUNCH_CHECK();
       float* tmp = g; g = gn; gn = tmp;
     }
-    k_reduce_partials<<<dim3(reduce_grid(kR * kR + kR), L), 256, 0, st>>>(w.partial_gate, grid, kR * kR + kR, kR * kR, gs + o.res_k, kR,
-                                                                         gs + o.res_b, (size_t)grid * (kR * kR + kR), kR * kR, kR);
+    k_reduce_partials<<<dim3(reduce_grid(kR * kR + kR), L), 256, 0, st>>>(w.partial_gate, gtc, kR * kR + kR, kR * kR, gs + o.res_k, kR,
+                                                                         gs + o.res_b, (size_t)gtc * (kR * kR + kR), kR * kR, kR);
     SRWN_LAUNCH_CHECK();
-    k_reduce_partials<<<dim3(reduce_grid(2 * kR * kR + kR), L), 256, 0, st>>>(w.partial_conv, grid, 2 * kR * kR + kR, 2 * kR * kR,
+    k_reduce_partials<<<dim3(reduce_grid(2 * kR * kR + kR), L), 256, 0, st>>>(w.partial_conv, gtc, 2 * kR * kR + kR, 2 * kR * kR,
                                                                              gs + o.filt_k, kR, gs + o.filt_b,
-                                                                             (size_t)grid * (2 * kR * kR + kR), 2 * kR * kR, kR);
+                                                                             (size_t)gtc * (2 * kR * kR + kR), 2 * kR * kR, kR);
     SRWN_LAUNCH_CHECK();
     // g = dLoss/dx_0 (front output incl. cond_0)
     k_bwd_front<<<grid, 256, 0, st>>>(x_prev, g, sw + o.front_k, f > 0 ? dx_cur : nullptr, w.partial, B, T);

@@ -1,0 +1,591 @@
+// Student training pass, layer kernels on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+// The three per-layer kernels of the distillation step (model.py:356-401 differentiates model.py:415-535; block = ops.py:23-46):
+//   k_fwd_layer_tc   x_{l+1} = (x_l + c Wr + br) sqrt(1/2) + cond_{l+1},  c = f sigmoid(f),  f = tanh([x_l[t-d] | x_l[t]] Wf + bf)
+//   k_bwd_gate_tc    da = dL/da (a = pre-activation of the filter conv), dWr, dbr        (recomputes a, f, c from x_l)
+//   k_bwd_conv_tc    dx_l = g sqrt(1/2) + da W1^T + da[t+d] W0^T, dWf, dbf, dcond_l
+//
+// Tile = 128 time steps = the M of one MMA, 256 threads (thread = (row, half of the 32 channels)), persistent CTAs.
+// fp32 grade on TF32 tensor cores: every operand is split x = hi + lo into two TF32 numbers by truncation (x - hi is exact)
+// and a product is hi*hi + hi*lo + lo*hi.  The two terms that share the A operand come out of ONE instruction by stacking
+// [W_hi ; W_lo] along N (N = 64), so a GEMM costs two instruction chains instead of three:
+//     D[:, 0:32] = A_hi W_hi    D[:, 32:64] = A_hi W_lo    D[:, 64:96] = A_lo W_hi      (summed by the epilogue)
+// The chains are issued by different warps (an instruction costs its issuing thread ~60-120 clk, the pipe ~47-57 clk:
+// tools/umma_tf32_probe.cu) into separate accumulator columns, because instructions of different threads are not ordered.
+// Weight gradients contract over TIME: both operands are needed transposed, [channel][time].  MN-major TF32 operands only
+// exist for the 128B_BASE32B swizzle (the probe's no-swizzle MN-major descriptors return zeros), so the threads write
+// transposed copies themselves: thread = row, the 32 lanes of a warp hit 32 different banks with a chunk stride of
+// 16 * rows + 16 bytes.  [c_hi ; c_lo]^T (M) x [g_hi ; g_lo]^T (N = 64) is again one instruction per 8 time steps for all
+// four partial products, accumulated in TMEM over every tile of the CTA and read once at the end.
+//
+// Operand layouts (no swizzle, K-major, 8 x 16-byte core matrices; cute::UMMA canonical INTERLEAVE layout):
+//   activation operand (rows = time):    (row, ch)  at (ch / 4) * kCHS + row * 16 + (ch % 4) * 4      LBO = kCHS,  SBO = 128
+//   weight operand (rows = out channel): (n, k)     at (k / 4) * kWCH + n * 16 + (k % 4) * 4          LBO = kWCH,  SBO = 128
+//   transposed operand (rows = channel): (ch, t)    at (t / 4) * kTC* + ch * 16 + (t % 4) * 4         LBO = kTC*,  SBO = 128
+#include "common.cuh"
+#include "umma.cuh"
+#include "train_tc.cuh"
+
+namespace traintc {
+using namespace umma;
+
+constexpr int kRows = 128;
+constexpr int kCHS = kRows * 16 + 16;        // 2064
+constexpr int kTC64 = 64 * 16 + 16;          // 1040
+constexpr int kTC128 = 128 * 16 + 16;        // 2064
+constexpr int kWCH = 64 * 16;                // 1024
+constexpr uint32_t kTmemCols = 256;
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  // cute::UMMA::InstrDescriptor: c = F32 (bit 4), a / b format TF32 = 2 (bits 7, 10), K-major, N >> 3 at 17, M >> 4 at 24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+// x = hi + lo, both valid TF32 numbers (low 13 mantissa bits clear); x - hi is exact, truncating lo costs 2^-20 |x|
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void split4(float4 v, float4& h, float4& l) {
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+}
+__device__ __forceinline__ void split_store4(unsigned char* hi, unsigned char* lo, float4 v) {
+  float4 h, l;
+  split4(v, h, l);
+  *reinterpret_cast<float4*>(hi) = h;
+  *reinterpret_cast<float4*>(lo) = l;
+}
+// ex2.approx + rcp: ~2e-7 absolute on outputs in [-1, 1] (tanh.approx alone is 5e-4)
+__device__ __forceinline__ float tanh_ex2(float x) {
+  const float e = __expf(2.0f * fminf(fmaxf(x, -15.f), 15.f));
+  return 1.0f - 2.0f * __frcp_rn(e + 1.0f);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float& f4at(float4& v, int e) { return reinterpret_cast<float*>(&v)[e]; }
+
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// a pipeline wait that never completes is a bug in this file, not a data condition: stop the kernel instead of hanging the GPU
+__device__ __forceinline__ void wait_or_trap(uint32_t bar, uint32_t parity, volatile int* abort_words) {
+  if (!mbar_wait(bar, parity, abort_words, 1, 4000000000LL)) __trap();
+}
+
+struct Ctl {                 // barriers and bookkeeping at the end of dynamic shared memory
+  uint64_t bar_main, bar_wgrad;
+  uint32_t tmem_slot;
+  int abort_words[2];
+};
+
+__device__ __forceinline__ uint32_t cta_setup(Ctl* ctl, int main_arrivals) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(smem_u32(&ctl->bar_main), main_arrivals);
+    mbar_init(smem_u32(&ctl->bar_wgrad), 1);
+    ctl->abort_words[0] = ctl->abort_words[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return ctl->tmem_slot;
+}
+__device__ __forceinline__ void cta_teardown(uint32_t tmem) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+  }
+}
+
+// one instruction chain: nk K-steps of 8, A and B descriptors advancing by a_adv / b_adv bytes
+__device__ __forceinline__ void issue_chain(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_adv, uint32_t b_addr,
+                                            uint32_t b_lbo, uint32_t b_adv, int nk, uint32_t idesc, uint32_t acc_first) {
+  const uint64_t da = make_desc(a_addr, a_lbo, 128), db = make_desc(b_addr, b_lbo, 128);
+  const uint64_t as = (uint64_t)(a_adv >> 4), bs = (uint64_t)(b_adv >> 4);
+#pragma unroll 4
+  for (int k = 0; k < nk; k++) mma_tf32(d_tmem, da + k * as, db + k * bs, idesc, k > 0 ? 1u : acc_first);
+}
+
+// weight operand with the hi part in rows 0..31 and the lo part in rows 32..63: value(n, k) for n, k < 32 / K
+template <typename F>
+__device__ __forceinline__ void stage_weight(unsigned char* dst, int K, F value) {
+  for (int i = threadIdx.x; i < K * 32; i += kThreads) {
+    const int k = i >> 5, n = i & 31;
+    float h, l;
+    split_tf32(value(n, k), h, l);
+    unsigned char* p = dst + (k >> 2) * kWCH + n * 16 + (k & 3) * 4;
+    *reinterpret_cast<float*>(p) = h;
+    *reinterpret_cast<float*>(p + 32 * 16) = l;
+  }
+}
+
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+constexpr int kFwdX = 16 * kCHS;                                   // one of X_hi / X_lo: 8 tap chunks | 8 current chunks
+constexpr int kFwdSmem = 2 * kFwdX + 16 * kWCH + 8 * kWCH + 2 * 32 * 4 + (int)sizeof(Ctl);
+int fwd_smem_bytes() { return kFwdSmem; }
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const float* __restrict__ filt_k,
+               const float* __restrict__ filt_b, const float* __restrict__ res_k, const float* __restrict__ res_b,
+               const float* __restrict__ cond_next, int B, int T, int d, int P, int L, int frames) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* X_hi = smem;
+  unsigned char* X_lo = X_hi + kFwdX;
+  unsigned char* WfB = X_lo + kFwdX;
+  unsigned char* WrB = WfB + 16 * kWCH;
+  float* s_bf = reinterpret_cast<float*>(WrB + 8 * kWCH);
+  float* s_br = s_bf + 32;
+  Ctl* ctl = reinterpret_cast<Ctl*>(s_br + 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 16;        // epilogue: this thread's row (TMEM lane) and channel base
+  // a[t][n] = sum_kk [tap | cur][t][kk] Wf[kk][n]: B(n, kk) = filt_k[kk * 32 + n]  (filt_k = [tap][cin][cout], tap 0 pairs with x[t-d])
+  stage_weight(WfB, 64, [&](int n, int k) { return filt_k[k * kR + n]; });
+  stage_weight(WrB, 32, [&](int n, int k) { return res_k[k * kR + n]; });
+  if (tid < kR) { s_bf[tid] = filt_b[tid]; s_br[tid] = res_b[tid]; }
+  const uint32_t tmem = cta_setup(ctl, 2);
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t bar = smem_u32(&ctl->bar_main);
+  uint32_t phase = 0;
+  const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
+  constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
+  grid_dependency_wait();
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
+    const float* xb = x_l + (size_t)b * T * kR;
+    for (int i = 0; i < 4; i++) {
+      const int idx = tid + i * kThreads, r = idx >> 3, c4 = idx & 7, t = t0 + r;
+      float4 cur = make_float4(0, 0, 0, 0), tap = cur;
+      if (t < T) {
+        cur = ldg4(xb + (size_t)t * kR + c4 * 4);
+        if (t - d >= 0) tap = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
+      }
+      split_store4(X_hi + c4 * kCHS + r * 16, X_lo + c4 * kCHS + r * 16, tap);
+      split_store4(X_hi + (8 + c4) * kCHS + r * 16, X_lo + (8 + c4) * kCHS + r * 16, cur);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_chain(tmem, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI64, 0);
+      tc_commit(bar);
+    } else if (tid == 32) {
+      tc_fence_after();
+      issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
+      tc_commit(bar);
+    }
+    // this thread's row of x_l and of the next layer's conditioning, for the second epilogue (in flight during the GEMMs)
+    const int t = t0 + row;
+    float4 xv[4], cn[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      xv[j] = make_float4(0, 0, 0, 0); cn[j] = xv[j];
+      if (t < T) {
+        xv[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
+        if (cond_next) cn[j] = ldg4(cond_next + ((size_t)b * frames + t / P) * L * kR + cb + 4 * j);
+      }
+    }
+    wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
+    tc_fence_after();
+    {
+      float a0[16], a1[16], a2[16];
+      tc_ld16(lane_base + cb, a0); tc_ld16(lane_base + 32 + cb, a1); tc_ld16(lane_base + 64 + cb, a2);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float4 c;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int i = 4 * j + e;
+          const float f = tanh_ex2((a2[i] + a1[i]) + a0[i] + s_bf[cb + i]);     // gate: tanh, sigmoid OF THE TANH, product (ops.py:28,33,36)
+          f4at(c, e) = f * sigmoid_fast(f);
+        }
+        const int chunk = (cb >> 2) + j;                                         // c takes over the tap rows (dead after the filter conv)
+        split_store4(X_hi + chunk * kCHS + row * 16, X_lo + chunk * kCHS + row * 16, c);
+      }
+    }
+    tc_fence_before();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_chain(tmem + 128, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI64, 0);
+      tc_commit(bar);
+    } else if (tid == 32) {
+      tc_fence_after();
+      issue_chain(tmem + 192, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI32, 0);
+      tc_commit(bar);
+    }
+    wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
+    tc_fence_after();
+    {
+      float r0[16], r1[16], r2[16];
+      tc_ld16(lane_base + 128 + cb, r0); tc_ld16(lane_base + 160 + cb, r1); tc_ld16(lane_base + 192 + cb, r2);
+      tc_wait_ld();
+      if (t < T) {
+        float* dst = x_next + ((size_t)b * T + t) * kR + cb;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float4 v;
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int i = 4 * j + e;
+            const float res = (r2[i] + r1[i]) + r0[i] + s_br[cb + i];           // residual 1x1 (ops.py:39)
+            f4at(v, e) = (f4at(xv[j], e) + res) * SRWN_SQRT_HALF + f4at(cn[j], e);   // ops.py:40, next layer's conditioning (model.py:183)
+          }
+          *reinterpret_cast<float4*>(dst + 4 * j) = v;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  cta_teardown(tmem);
+}
+
+// =====================================================================================================================
+// gate backward
+// =====================================================================================================================
+constexpr int kGateX = 2 * 16 * kCHS;                       // X_hi | X_lo; [c_hi ; c_lo]^T takes the region over once a is computed
+constexpr int kGateG = 8 * kCHS;                            // one of G_hi / G_lo
+constexpr int kGateGT = 32 * kTC64;                         // [g_hi ; g_lo]^T
+constexpr int kGateSmem = kGateX + 2 * kGateG + kGateGT + 16 * kWCH + 8 * kWCH + 32 * 4 + (int)sizeof(Ctl);
+int gate_smem_bytes() { return kGateSmem; }
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, float* __restrict__ da_out,
+              const float* __restrict__ filt_k, const float* __restrict__ filt_b, const float* __restrict__ res_k,
+              float* __restrict__ partial, int B, int T, int d) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* X_hi = smem;
+  unsigned char* X_lo = X_hi + 16 * kCHS;
+  unsigned char* CT = smem;                                 // 32 time chunks of 64 rows; the M = 128 instruction reads 1 KB past it (inside X)
+  unsigned char* G_hi = smem + kGateX;
+  unsigned char* G_lo = G_hi + kGateG;
+  unsigned char* GT = G_lo + kGateG;
+  unsigned char* WfB = GT + kGateGT;
+  unsigned char* WrT = WfB + 16 * kWCH;
+  float* s_bf = reinterpret_cast<float*>(WrT + 8 * kWCH);
+  Ctl* ctl = reinterpret_cast<Ctl*>(s_bf + 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 16;
+  stage_weight(WfB, 64, [&](int n, int k) { return filt_k[k * kR + n]; });
+  // dc[t][k] = sum_n dres[t][n] Wr[k][n]: B(row = k, K index = n) = res_k[k * 32 + n]
+  stage_weight(WrT, 32, [&](int krow, int n) { return res_k[krow * kR + n]; });
+  if (tid < kR) s_bf[tid] = filt_b[tid];
+  const uint32_t tmem = cta_setup(ctl, 3);
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t bar = smem_u32(&ctl->bar_main), bar_w = smem_u32(&ctl->bar_wgrad);
+  uint32_t phase = 0, phase_w = 0;
+  const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
+  constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
+  float gsum[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) gsum[i] = 0.f;
+  float4 xc[4], xt[4], gg[4];
+  auto load_tile = [&](int tile) {
+    const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
+    const float* xb = x_l + (size_t)b * T * kR;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      xc[j] = make_float4(0, 0, 0, 0); xt[j] = xc[j]; gg[j] = xc[j];
+      if (t < T) {
+        xc[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
+        gg[j] = ldg4(g_in + ((size_t)b * T + t) * kR + cb + 4 * j);
+        if (t - d >= 0) xt[j] = ldg4(xb + (size_t)(t - d) * kR + cb + 4 * j);
+      }
+    }
+  };
+  grid_dependency_wait();
+  int n_done = 0;
+  if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n_done++) {
+    const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
+    if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWr has read CT / GT
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int chunk = (cb >> 2) + j;
+      split_store4(X_hi + chunk * kCHS + row * 16, X_lo + chunk * kCHS + row * 16, xt[j]);
+      split_store4(X_hi + (8 + chunk) * kCHS + row * 16, X_lo + (8 + chunk) * kCHS + row * 16, xc[j]);
+      float4 gs = make_float4(gg[j].x * SRWN_SQRT_HALF, gg[j].y * SRWN_SQRT_HALF, gg[j].z * SRWN_SQRT_HALF, gg[j].w * SRWN_SQRT_HALF);   // dres
+      float4 h, l;
+      split4(gs, h, l);
+      *reinterpret_cast<float4*>(G_hi + chunk * kCHS + row * 16) = h;
+      *reinterpret_cast<float4*>(G_lo + chunk * kCHS + row * 16) = l;
+      unsigned char* gt = GT + (row >> 2) * kTC64 + (row & 3) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int n = cb + 4 * j + e;
+        *reinterpret_cast<float*>(gt + n * 16) = f4at(h, e);
+        *reinterpret_cast<float*>(gt + (32 + n) * 16) = f4at(l, e);
+        gsum[4 * j + e] += f4at(gs, e);
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_chain(tmem, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI64, 0);
+      tc_commit(bar);
+    } else if (tid == 32) {
+      tc_fence_after();
+      issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
+      tc_commit(bar);
+    } else if (tid == 64) {
+      tc_fence_after();
+      issue_chain(tmem + 96, smem_u32(G_hi), kCHS, 2 * kCHS, smem_u32(WrT), kWCH, 2 * kWCH, 4, kI64, 0);
+      issue_chain(tmem + 160, smem_u32(G_lo), kCHS, 2 * kCHS, smem_u32(WrT), kWCH, 2 * kWCH, 4, kI32, 0);
+      tc_commit(bar);
+    }
+    if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);        // next tile's rows, in flight during the GEMMs
+    wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
+    tc_fence_after();
+    float da[16];
+    {
+      float a0[16], a1[16], a2[16], d0[16], d1[16], d2[16];
+      tc_ld16(lane_base + cb, a0); tc_ld16(lane_base + 32 + cb, a1); tc_ld16(lane_base + 64 + cb, a2);
+      tc_ld16(lane_base + 96 + cb, d0); tc_ld16(lane_base + 128 + cb, d1); tc_ld16(lane_base + 160 + cb, d2);
+      tc_wait_ld();
+      unsigned char* ct = CT + (row >> 2) * kTC64 + (row & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const float f = tanh_ex2((a2[i] + a1[i]) + a0[i] + s_bf[cb + i]);       // recomputed gate (ops.py:28,33,36)
+        const float sg = sigmoid_fast(f);
+        const float dc = (d2[i] + d1[i]) + d0[i];
+        const float df = dc * (sg + f * sg * (1.f - sg));                        // d(f sigmoid(f)) / df
+        da[i] = df * (1.f - f * f);                                              // tanh'
+        float h, l;
+        split_tf32(f * sg, h, l);
+        *reinterpret_cast<float*>(ct + (cb + i) * 16) = h;
+        *reinterpret_cast<float*>(ct + (32 + cb + i) * 16) = l;
+      }
+    }
+    tc_fence_before();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      // dWr[k][n] += sum_t c[t][k] dres[t][n]: [c_hi ; c_lo]^T x [g_hi ; g_lo]^T, 16 steps of 8 time steps
+      tc_fence_after();
+      issue_chain(tmem + 192, smem_u32(CT), kTC64, 2 * kTC64, smem_u32(GT), kTC64, 2 * kTC64, 16, kI64, n_done > 0 ? 1u : 0u);
+      tc_commit(bar_w);
+    }
+    if (t < T) {
+      float* dst = da_out + ((size_t)b * T + t) * kR + cb;
+#pragma unroll
+      for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
+    }
+  }
+  // ---- per-CTA partial sums: dWr | dbr ----
+  float* pp = partial + (size_t)blockIdx.x * (kR * kR + kR);
+  float* red = reinterpret_cast<float*>(G_hi);               // [64][33] floats + [8][16]
+  if (n_done > 0) {
+    wait_or_trap(bar_w, phase_w, ctl->abort_words);
+    tc_fence_after();
+    float v0[16], v1[16];
+    tc_ld16(lane_base + 192 + cb, v0); tc_ld16(lane_base + 224 + cb, v1);
+    tc_wait_ld();
+    if (row < 64) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) red[row * 33 + cb + i] = v0[i] + (row < 32 ? v1[i] : 0.f);     // hi row: hi*hi + hi*lo; lo row: lo*hi
+    }
+  }
+  float* red2 = red + 64 * 33;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    float v = gsum[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red2[warp * 16 + i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < kR * kR; i += kThreads) pp[i] = n_done > 0 ? red[(i >> 5) * 33 + (i & 31)] + red[(32 + (i >> 5)) * 33 + (i & 31)] : 0.f;
+  if (tid < kR) {
+    const int h = tid >> 4, e = tid & 15;
+    pp[kR * kR + tid] = (red2[(4 * h) * 16 + e] + red2[(4 * h + 1) * 16 + e]) + (red2[(4 * h + 2) * 16 + e] + red2[(4 * h + 3) * 16 + e]);
+  }
+  cta_teardown(tmem);
+}
+
+// =====================================================================================================================
+// conv backward
+// =====================================================================================================================
+constexpr int kConvDA = 2 * 16 * kCHS;                      // DA_hi | DA_lo: 8 chunks da[t] | 8 chunks da[t+d]
+constexpr int kConvDAT = 32 * kTC64;                        // [da_hi ; da_lo]^T
+constexpr int kConvXT = 32 * kTC128;                        // [tap_hi ; cur_hi ; tap_lo ; cur_lo]^T
+constexpr int kConvSmem = kConvDA + kConvDAT + kConvXT + 16 * kWCH + (int)sizeof(Ctl);
+int conv_smem_bytes() { return kConvSmem; }
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, const float* __restrict__ da_in,
+              float* __restrict__ dx_out, const float* __restrict__ filt_k, float* __restrict__ partial,
+              float* __restrict__ dcond, int B, int T, int d, int P, int frames) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* DA_hi = smem;
+  unsigned char* DA_lo = DA_hi + 16 * kCHS;
+  unsigned char* DAT = smem + kConvDA;
+  unsigned char* XT = DAT + kConvDAT;
+  unsigned char* WB = XT + kConvXT;
+  Ctl* ctl = reinterpret_cast<Ctl*>(WB + 16 * kWCH);
+  float* red = reinterpret_cast<float*>(DA_hi);             // [128][33] floats once the dx GEMM has read DA
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 16;
+  // dx[t][k] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]: B(row = k, K index j) = j < 32 ? W1[k][j] : W0[k][j - 32]
+  stage_weight(WB, 64, [&](int krow, int j) { return j < 32 ? filt_k[kR * kR + krow * kR + j] : filt_k[krow * kR + (j - 32)]; });
+  const uint32_t tmem = cta_setup(ctl, 2);
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t bar = smem_u32(&ctl->bar_main), bar_w = smem_u32(&ctl->bar_wgrad);
+  uint32_t phase = 0, phase_w = 0;
+  const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
+  constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
+  float dsum[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) dsum[i] = 0.f;
+  float4 xc[4], xt[4], dac[4], daf[4];
+  auto load_tile = [&](int tile) {
+    const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
+    const float* xb = x_l + (size_t)b * T * kR;
+    const float* db = da_in + (size_t)b * T * kR;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      xc[j] = make_float4(0, 0, 0, 0); xt[j] = xc[j]; dac[j] = xc[j]; daf[j] = xc[j];
+      if (t < T) {
+        xc[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
+        dac[j] = ldg4(db + (size_t)t * kR + cb + 4 * j);
+        if (t - d >= 0) xt[j] = ldg4(xb + (size_t)(t - d) * kR + cb + 4 * j);
+        if (t + d < T) daf[j] = ldg4(db + (size_t)(t + d) * kR + cb + 4 * j);
+      }
+    }
+  };
+  grid_dependency_wait();
+  int n_done = 0;
+  if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n_done++) {
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows, t = t0 + row;
+    if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWf has read DAT / XT
+    __syncthreads();                                                                       // and every thread is done with `red`
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int chunk = (cb >> 2) + j;
+      float4 h, l, xth, xtl, xch, xcl;
+      split4(dac[j], h, l);
+      *reinterpret_cast<float4*>(DA_hi + chunk * kCHS + row * 16) = h;
+      *reinterpret_cast<float4*>(DA_lo + chunk * kCHS + row * 16) = l;
+      split_store4(DA_hi + (8 + chunk) * kCHS + row * 16, DA_lo + (8 + chunk) * kCHS + row * 16, daf[j]);
+      split4(xt[j], xth, xtl);
+      split4(xc[j], xch, xcl);
+      unsigned char* dt = DAT + (row >> 2) * kTC64 + (row & 3) * 4;
+      unsigned char* xq = XT + (row >> 2) * kTC128 + (row & 3) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int n = cb + 4 * j + e;
+        *reinterpret_cast<float*>(dt + n * 16) = f4at(h, e);
+        *reinterpret_cast<float*>(dt + (32 + n) * 16) = f4at(l, e);
+        *reinterpret_cast<float*>(xq + n * 16) = f4at(xth, e);
+        *reinterpret_cast<float*>(xq + (32 + n) * 16) = f4at(xch, e);
+        *reinterpret_cast<float*>(xq + (64 + n) * 16) = f4at(xtl, e);
+        *reinterpret_cast<float*>(xq + (96 + n) * 16) = f4at(xcl, e);
+        dsum[4 * j + e] += f4at(dac[j], e);
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_chain(tmem, smem_u32(DA_hi), kCHS, 2 * kCHS, smem_u32(WB), kWCH, 2 * kWCH, 8, kI64, 0);
+      tc_commit(bar);
+    } else if (tid == 32) {
+      tc_fence_after();
+      issue_chain(tmem + 64, smem_u32(DA_lo), kCHS, 2 * kCHS, smem_u32(WB), kWCH, 2 * kWCH, 8, kI32, 0);
+      tc_commit(bar);
+    } else if (tid == 64) {
+      // dWf[kk][n] += sum_t [tap | cur][t][kk] da[t][n]: [x_hi ; x_lo]^T (M = 128) x [da_hi ; da_lo]^T (N = 64)
+      tc_fence_after();
+      issue_chain(tmem + 128, smem_u32(XT), kTC128, 2 * kTC128, smem_u32(DAT), kTC64, 2 * kTC64, 16, kI64, n_done > 0 ? 1u : 0u);
+      tc_commit(bar_w);
+    }
+    float4 gv[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) gv[j] = t < T ? ldg4(g_in + ((size_t)b * T + t) * kR + cb + 4 * j) : make_float4(0, 0, 0, 0);
+    if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
+    wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
+    tc_fence_after();
+    float dx[16];
+    {
+      float a0[16], a1[16], a2[16];
+      tc_ld16(lane_base + cb, a0); tc_ld16(lane_base + 32 + cb, a1); tc_ld16(lane_base + 64 + cb, a2);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; i++) dx[i] = t < T ? fmaf(f4at(gv[i >> 2], i & 3), SRWN_SQRT_HALF, (a2[i] + a1[i]) + a0[i]) : 0.f;
+    }
+    tc_fence_before();
+    if (t < T) {
+      float* dst = dx_out + ((size_t)b * T + t) * kR + cb;
+#pragma unroll
+      for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(dx[4 * j], dx[4 * j + 1], dx[4 * j + 2], dx[4 * j + 3]);
+    }
+    // x_l carries cond_l (model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l
+    if (P % 16 == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) red[row * 33 + cb + i] = dx[i];
+      __syncthreads();
+      const int ch = tid & 31, part = tid >> 5, tp = t0 + 16 * part;
+      if (tp < T) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) s += red[(16 * part + i) * 33 + ch];
+        atomicAdd(dcond + ((size_t)b * frames + tp / P) * kR + ch, s);
+      }
+    } else if (t < T) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) atomicAdd(dcond + ((size_t)b * frames + t / P) * kR + cb + i, dx[i]);
+    }
+  }
+  // ---- per-CTA partial sums: dWf | dbf ----
+  float* pp = partial + (size_t)blockIdx.x * (2 * kR * kR + kR);
+  __syncthreads();
+  float* red2 = reinterpret_cast<float*>(DAT);               // [8][16]
+  if (n_done > 0) {
+    wait_or_trap(bar_w, phase_w, ctl->abort_words);
+    tc_fence_after();
+    float v0[16], v1[16];
+    tc_ld16(lane_base + 128 + cb, v0); tc_ld16(lane_base + 160 + cb, v1);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; i++) red[row * 33 + cb + i] = v0[i] + (row < 64 ? v1[i] : 0.f);      // hi rows: hi*hi + hi*lo; lo rows: lo*hi
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    float v = dsum[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red2[warp * 16 + i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * kR * kR; i += kThreads) pp[i] = n_done > 0 ? red[(i >> 5) * 33 + (i & 31)] + red[(64 + (i >> 5)) * 33 + (i & 31)] : 0.f;
+  if (tid < kR) {
+    const int h = tid >> 4, e = tid & 15;
+    pp[2 * kR * kR + tid] = (red2[(4 * h) * 16 + e] + red2[(4 * h + 1) * 16 + e]) + (red2[(4 * h + 2) * 16 + e] + red2[(4 * h + 3) * 16 + e]);
+  }
+  cta_teardown(tmem);
+}
+
+}  // namespace traintc
