@@ -889,7 +889,7 @@ int run_layer_tf32x3(srwn_ctx* c, bool with_skip, const float* x_l, float* x_nex
         x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames, skip_k, skip_b, skip, skip_init));
   } else {
     SRWN_CUDA(cudaFuncSetAttribute(traintc::k_fwd_layer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, traintc::fwd_smem_bytes()));
-    SRWN_CUDA(launch_dependent(traintc::k_fwd_layer_tc, grid, traintc::kThreads, (size_t)traintc::fwd_smem_bytes(), st,
+    SRWN_CUDA(launch_dependent(traintc::k_fwd_layer_tc, grid / 2, traintc::kThreads, (size_t)traintc::fwd_smem_bytes(), st,
         x_l, x_next, filt_k, filt_b, res_k, res_b, cond_next, B, T, d, P, L, frames));
   }
   SRWN_LAUNCH_CHECK();
@@ -931,7 +931,7 @@ int run_student_forward_train(srwn_ctx* c, const float* z, const float* enc, flo
   const float* xin = z;
   for (int f = 0; f < F; f++) {
     float* acts = w.acts + (size_t)f * (L + 1) * n * kR;
-    int rc = run_stack_train_acts(c, f, xin, enc, B, T, acts, w.cond, 2 * w.grid_tc, st);
+    int rc = run_stack_train_acts(c, f, xin, enc, B, T, acts, w.cond, w.grid_tc, st);
     if (rc) return rc;
     rc = run_flow_head_f32(c, f, acts + (size_t)L * n * kR, xin, w.scales + (size_t)f * n, w.means + (size_t)f * n,
                            w.xs + (size_t)f * n, B, T, st);

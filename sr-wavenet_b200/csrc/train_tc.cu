@@ -5,7 +5,8 @@
 //   k_bwd_gate_tc    da = dL/da (a = pre-activation of the filter conv), dWr, dbr        (recomputes a, f, c from x_l)
 //   k_bwd_conv_tc    dx_l = g sqrt(1/2) + da W1^T + da[t+d] W0^T, dWf, dbf, dcond_l
 //
-// Tile = 128 time steps = the M of one MMA, 256 threads (thread = (row, half of the 32 channels)), persistent CTAs.
+// Tile = 128 time steps = the M of one MMA, 512 threads (thread = (row, quarter of the 32 channels): four warps per
+// scheduler hide the latencies of the epilogue math), one persistent CTA per SM.
 // fp32 grade on TF32 tensor cores: every operand is split x = hi + lo into two TF32 numbers by truncation (x - hi is exact)
 // and a product is hi*hi + hi*lo + lo*hi.  The two terms that share the A operand come out of ONE instruction by stacking
 // [W_hi ; W_lo] along N (N = 64), so a GEMM costs two instruction chains instead of three:
@@ -44,11 +45,10 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
 // x = hi + lo, both valid TF32 numbers (low 13 mantissa bits clear); x - hi is exact, truncating lo costs 2^-20 |x|
@@ -65,12 +65,12 @@ __device__ __forceinline__ void split_store4(unsigned char* hi, unsigned char* l
   *reinterpret_cast<float4*>(hi) = h;
   *reinterpret_cast<float4*>(lo) = l;
 }
-// ex2.approx + rcp: ~2e-7 absolute on outputs in [-1, 1] (tanh.approx alone is 5e-4)
-__device__ __forceinline__ float tanh_ex2(float x) {
-  const float e = __expf(2.0f * fminf(fmaxf(x, -15.f), 15.f));
-  return 1.0f - 2.0f * __frcp_rn(e + 1.0f);
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+// ex2.approx + rcp.approx (one MUFU each, ~1 ulp): ~2e-7 absolute on outputs in [-1, 1] (tanh.approx alone is 5e-4).
+// No clamp: e = inf gives rcp = 0 and tanh = 1, e = 0 gives tanh = -1.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tanh_ex2(float x) { return fmaf(-2.0f, rcp_approx(ex2_approx(x * 2.885390081777927f) + 1.0f), 1.0f); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float& f4at(float4& v, int e) { return reinterpret_cast<float*>(&v)[e]; }
 
@@ -125,12 +125,16 @@ __device__ __forceinline__ void issue_chain(uint32_t d_tmem, uint32_t a_addr, ui
 }
 
 // weight operand with the hi part in rows 0..31 and the lo part in rows 32..63: value(n, k) for n, k < 32 / K
-template <typename F>
-__device__ __forceinline__ void stage_weight(unsigned char* dst, int K, F value) {
-  for (int i = threadIdx.x; i < K * 32; i += kThreads) {
-    const int k = i >> 5, n = i & 31;
+template <int K, typename F>
+__device__ __forceinline__ void stage_weight(unsigned char* dst, F value) {
+  float v[K * 32 / kThreads];
+#pragma unroll
+  for (int u = 0; u < K * 32 / kThreads; u++) { const int i = threadIdx.x + u * kThreads; v[u] = value(i & 31, i >> 5); }     // all loads in flight at once
+#pragma unroll
+  for (int u = 0; u < K * 32 / kThreads; u++) {
+    const int i = threadIdx.x + u * kThreads, k = i >> 5, n = i & 31;
     float h, l;
-    split_tf32(value(n, k), h, l);
+    split_tf32(v[u], h, l);
     unsigned char* p = dst + (k >> 2) * kWCH + n * 16 + (k & 3) * 4;
     *reinterpret_cast<float*>(p) = h;
     *reinterpret_cast<float*>(p + 32 * 16) = l;
@@ -144,7 +148,7 @@ constexpr int kFwdX = 16 * kCHS;                                   // one of X_h
 constexpr int kFwdSmem = 2 * kFwdX + 16 * kWCH + 8 * kWCH + 2 * 32 * 4 + (int)sizeof(Ctl);
 int fwd_smem_bytes() { return kFwdSmem; }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const float* __restrict__ filt_k,
                const float* __restrict__ filt_b, const float* __restrict__ res_k, const float* __restrict__ res_b,
                const float* __restrict__ cond_next, int B, int T, int d, int P, int L, int frames) {
@@ -157,10 +161,10 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
   float* s_br = s_bf + 32;
   Ctl* ctl = reinterpret_cast<Ctl*>(s_br + 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 16;        // epilogue: this thread's row (TMEM lane) and channel base
+  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;         // epilogue: this thread's row (TMEM lane) and channel base
   // a[t][n] = sum_kk [tap | cur][t][kk] Wf[kk][n]: B(n, kk) = filt_k[kk * 32 + n]  (filt_k = [tap][cin][cout], tap 0 pairs with x[t-d])
-  stage_weight(WfB, 64, [&](int n, int k) { return filt_k[k * kR + n]; });
-  stage_weight(WrB, 32, [&](int n, int k) { return res_k[k * kR + n]; });
+  stage_weight<64>(WfB, [&](int n, int k) { return filt_k[k * kR + n]; });
+  stage_weight<32>(WrB, [&](int n, int k) { return res_k[k * kR + n]; });
   if (tid < kR) { s_bf[tid] = filt_b[tid]; s_br[tid] = res_b[tid]; }
   const uint32_t tmem = cta_setup(ctl, 2);
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -168,19 +172,31 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
   uint32_t phase = 0;
   const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
   constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
+  // operand rows are loaded coalesced: idx -> (row idx >> 3, 4-channel chunk idx & 7), two per thread
+  float4 pc[2], pt[2];
+  auto load_tile = [&](int tile) {
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
+    const float* xb = x_l + (size_t)b * T * kR;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int idx = tid + i * kThreads, t = t0 + (idx >> 3), c4 = idx & 7;
+      pc[i] = make_float4(0, 0, 0, 0); pt[i] = pc[i];
+      if (t < T) {
+        pc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
+        if (t - d >= 0) pt[i] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
+      }
+    }
+  };
   grid_dependency_wait();
+  if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     const float* xb = x_l + (size_t)b * T * kR;
-    for (int i = 0; i < 4; i++) {
-      const int idx = tid + i * kThreads, r = idx >> 3, c4 = idx & 7, t = t0 + r;
-      float4 cur = make_float4(0, 0, 0, 0), tap = cur;
-      if (t < T) {
-        cur = ldg4(xb + (size_t)t * kR + c4 * 4);
-        if (t - d >= 0) tap = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
-      }
-      split_store4(X_hi + c4 * kCHS + r * 16, X_lo + c4 * kCHS + r * 16, tap);
-      split_store4(X_hi + (8 + c4) * kCHS + r * 16, X_lo + (8 + c4) * kCHS + r * 16, cur);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int idx = tid + i * kThreads, r = idx >> 3, c4 = idx & 7;
+      split_store4(X_hi + c4 * kCHS + r * 16, X_lo + c4 * kCHS + r * 16, pt[i]);
+      split_store4(X_hi + (8 + c4) * kCHS + r * 16, X_lo + (8 + c4) * kCHS + r * 16, pc[i]);
     }
     fence_async_smem();
     __syncthreads();
@@ -193,25 +209,27 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
       issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
       tc_commit(bar);
     }
-    // this thread's row of x_l and of the next layer's conditioning, for the second epilogue (in flight during the GEMMs)
+    // this thread's row of x_l and of the next layer's conditioning for the second epilogue, and the next tile's operand
+    // rows: all in flight during the GEMMs
     const int t = t0 + row;
-    float4 xv[4], cn[4];
+    float4 xv[2], cn[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 2; j++) {
       xv[j] = make_float4(0, 0, 0, 0); cn[j] = xv[j];
       if (t < T) {
         xv[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
         if (cond_next) cn[j] = ldg4(cond_next + ((size_t)b * frames + t / P) * L * kR + cb + 4 * j);
       }
     }
+    if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
     {
-      float a0[16], a1[16], a2[16];
-      tc_ld16(lane_base + cb, a0); tc_ld16(lane_base + 32 + cb, a1); tc_ld16(lane_base + 64 + cb, a2);
+      float a0[8], a1[8], a2[8];
+      tc_ld8(lane_base + cb, a0); tc_ld8(lane_base + 32 + cb, a1); tc_ld8(lane_base + 64 + cb, a2);
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < 2; j++) {
         float4 c;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
@@ -238,13 +256,13 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
     {
-      float r0[16], r1[16], r2[16];
-      tc_ld16(lane_base + 128 + cb, r0); tc_ld16(lane_base + 160 + cb, r1); tc_ld16(lane_base + 192 + cb, r2);
+      float r0[8], r1[8], r2[8];
+      tc_ld8(lane_base + 128 + cb, r0); tc_ld8(lane_base + 160 + cb, r1); tc_ld8(lane_base + 192 + cb, r2);
       tc_wait_ld();
       if (t < T) {
         float* dst = x_next + ((size_t)b * T + t) * kR + cb;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 2; j++) {
           float4 v;
 #pragma unroll
           for (int e = 0; e < 4; e++) {
@@ -287,10 +305,10 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
   float* s_bf = reinterpret_cast<float*>(WrT + 8 * kWCH);
   Ctl* ctl = reinterpret_cast<Ctl*>(s_bf + 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 16;
-  stage_weight(WfB, 64, [&](int n, int k) { return filt_k[k * kR + n]; });
+  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;
+  stage_weight<64>(WfB, [&](int n, int k) { return filt_k[k * kR + n]; });
   // dc[t][k] = sum_n dres[t][n] Wr[k][n]: B(row = k, K index = n) = res_k[k * 32 + n]
-  stage_weight(WrT, 32, [&](int krow, int n) { return res_k[krow * kR + n]; });
+  stage_weight<32>(WrT, [&](int krow, int n) { return res_k[krow * kR + n]; });
   if (tid < kR) s_bf[tid] = filt_b[tid];
   const uint32_t tmem = cta_setup(ctl, 3);
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -298,15 +316,15 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
   uint32_t phase = 0, phase_w = 0;
   const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
   constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
-  float gsum[16];
+  float gsum[8];
 #pragma unroll
-  for (int i = 0; i < 16; i++) gsum[i] = 0.f;
-  float4 xc[4], xt[4], gg[4];
+  for (int i = 0; i < 8; i++) gsum[i] = 0.f;
+  float4 xc[2], xt[2], gg[2];
   auto load_tile = [&](int tile) {
     const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
     const float* xb = x_l + (size_t)b * T * kR;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 2; j++) {
       xc[j] = make_float4(0, 0, 0, 0); xt[j] = xc[j]; gg[j] = xc[j];
       if (t < T) {
         xc[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
@@ -322,7 +340,7 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
     const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
     if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWr has read CT / GT
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 2; j++) {
       const int chunk = (cb >> 2) + j;
       split_store4(X_hi + chunk * kCHS + row * 16, X_lo + chunk * kCHS + row * 16, xt[j]);
       split_store4(X_hi + (8 + chunk) * kCHS + row * 16, X_lo + (8 + chunk) * kCHS + row * 16, xc[j]);
@@ -359,15 +377,15 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
     if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);        // next tile's rows, in flight during the GEMMs
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
-    float da[16];
+    float da[8];
     {
-      float a0[16], a1[16], a2[16], d0[16], d1[16], d2[16];
-      tc_ld16(lane_base + cb, a0); tc_ld16(lane_base + 32 + cb, a1); tc_ld16(lane_base + 64 + cb, a2);
-      tc_ld16(lane_base + 96 + cb, d0); tc_ld16(lane_base + 128 + cb, d1); tc_ld16(lane_base + 160 + cb, d2);
+      float a0[8], a1[8], a2[8], d0[8], d1[8], d2[8];
+      tc_ld8(lane_base + cb, a0); tc_ld8(lane_base + 32 + cb, a1); tc_ld8(lane_base + 64 + cb, a2);
+      tc_ld8(lane_base + 96 + cb, d0); tc_ld8(lane_base + 128 + cb, d1); tc_ld8(lane_base + 160 + cb, d2);
       tc_wait_ld();
       unsigned char* ct = CT + (row >> 2) * kTC64 + (row & 3) * 4;
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
+      for (int i = 0; i < 8; i++) {
         const float f = tanh_ex2((a2[i] + a1[i]) + a0[i] + s_bf[cb + i]);       // recomputed gate (ops.py:28,33,36)
         const float sg = sigmoid_fast(f);
         const float dc = (d2[i] + d1[i]) + d0[i];
@@ -391,36 +409,36 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
     if (t < T) {
       float* dst = da_out + ((size_t)b * T + t) * kR + cb;
 #pragma unroll
-      for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
+      for (int j = 0; j < 2; j++) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
     }
   }
   // ---- per-CTA partial sums: dWr | dbr ----
   float* pp = partial + (size_t)blockIdx.x * (kR * kR + kR);
-  float* red = reinterpret_cast<float*>(G_hi);               // [64][33] floats + [8][16]
+  float* red = reinterpret_cast<float*>(G_hi);               // [64][33] floats + [16][8]
   if (n_done > 0) {
     wait_or_trap(bar_w, phase_w, ctl->abort_words);
     tc_fence_after();
-    float v0[16], v1[16];
-    tc_ld16(lane_base + 192 + cb, v0); tc_ld16(lane_base + 224 + cb, v1);
+    float v0[8], v1[8];
+    tc_ld8(lane_base + 192 + cb, v0); tc_ld8(lane_base + 224 + cb, v1);
     tc_wait_ld();
     if (row < 64) {
 #pragma unroll
-      for (int i = 0; i < 16; i++) red[row * 33 + cb + i] = v0[i] + (row < 32 ? v1[i] : 0.f);     // hi row: hi*hi + hi*lo; lo row: lo*hi
+      for (int i = 0; i < 8; i++) red[row * 33 + cb + i] = v0[i] + (row < 32 ? v1[i] : 0.f);     // hi row: hi*hi + hi*lo; lo row: lo*hi
     }
   }
   float* red2 = red + 64 * 33;
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
+  for (int i = 0; i < 8; i++) {
     float v = gsum[i];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red2[warp * 16 + i] = v;
+    if (lane == 0) red2[warp * 8 + i] = v;
   }
   __syncthreads();
   for (int i = tid; i < kR * kR; i += kThreads) pp[i] = n_done > 0 ? red[(i >> 5) * 33 + (i & 31)] + red[(32 + (i >> 5)) * 33 + (i & 31)] : 0.f;
-  if (tid < kR) {
-    const int h = tid >> 4, e = tid & 15;
-    pp[kR * kR + tid] = (red2[(4 * h) * 16 + e] + red2[(4 * h + 1) * 16 + e]) + (red2[(4 * h + 2) * 16 + e] + red2[(4 * h + 3) * 16 + e]);
+  if (tid < kR) {                                            // channel tid: quarter tid >> 3 = warps 4 (tid >> 3) .. + 3
+    const int w0 = 4 * (tid >> 3), e = tid & 7;
+    pp[kR * kR + tid] = (red2[w0 * 8 + e] + red2[(w0 + 1) * 8 + e]) + (red2[(w0 + 2) * 8 + e] + red2[(w0 + 3) * 8 + e]);
   }
   cta_teardown(tmem);
 }
@@ -447,25 +465,25 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
   Ctl* ctl = reinterpret_cast<Ctl*>(WB + 16 * kWCH);
   float* red = reinterpret_cast<float*>(DA_hi);             // [128][33] floats once the dx GEMM has read DA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 16;
+  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;
   // dx[t][k] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]: B(row = k, K index j) = j < 32 ? W1[k][j] : W0[k][j - 32]
-  stage_weight(WB, 64, [&](int krow, int j) { return j < 32 ? filt_k[kR * kR + krow * kR + j] : filt_k[krow * kR + (j - 32)]; });
+  stage_weight<64>(WB, [&](int krow, int j) { return j < 32 ? filt_k[kR * kR + krow * kR + j] : filt_k[krow * kR + (j - 32)]; });
   const uint32_t tmem = cta_setup(ctl, 2);
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t bar = smem_u32(&ctl->bar_main), bar_w = smem_u32(&ctl->bar_wgrad);
   uint32_t phase = 0, phase_w = 0;
   const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
   constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
-  float dsum[16];
+  float dsum[8];
 #pragma unroll
-  for (int i = 0; i < 16; i++) dsum[i] = 0.f;
-  float4 xc[4], xt[4], dac[4], daf[4];
+  for (int i = 0; i < 8; i++) dsum[i] = 0.f;
+  float4 xc[2], xt[2], dac[2], daf[2];
   auto load_tile = [&](int tile) {
     const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
     const float* xb = x_l + (size_t)b * T * kR;
     const float* db = da_in + (size_t)b * T * kR;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 2; j++) {
       xc[j] = make_float4(0, 0, 0, 0); xt[j] = xc[j]; dac[j] = xc[j]; daf[j] = xc[j];
       if (t < T) {
         xc[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
@@ -483,7 +501,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWf has read DAT / XT
     __syncthreads();                                                                       // and every thread is done with `red`
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 2; j++) {
       const int chunk = (cb >> 2) + j;
       float4 h, l, xth, xtl, xch, xcl;
       split4(dac[j], h, l);
@@ -522,68 +540,68 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       issue_chain(tmem + 128, smem_u32(XT), kTC128, 2 * kTC128, smem_u32(DAT), kTC64, 2 * kTC64, 16, kI64, n_done > 0 ? 1u : 0u);
       tc_commit(bar_w);
     }
-    float4 gv[4];
+    float4 gv[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) gv[j] = t < T ? ldg4(g_in + ((size_t)b * T + t) * kR + cb + 4 * j) : make_float4(0, 0, 0, 0);
+    for (int j = 0; j < 2; j++) gv[j] = t < T ? ldg4(g_in + ((size_t)b * T + t) * kR + cb + 4 * j) : make_float4(0, 0, 0, 0);
     if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
-    float dx[16];
+    float dx[8];
     {
-      float a0[16], a1[16], a2[16];
-      tc_ld16(lane_base + cb, a0); tc_ld16(lane_base + 32 + cb, a1); tc_ld16(lane_base + 64 + cb, a2);
+      float a0[8], a1[8], a2[8];
+      tc_ld8(lane_base + cb, a0); tc_ld8(lane_base + 32 + cb, a1); tc_ld8(lane_base + 64 + cb, a2);
       tc_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; i++) dx[i] = t < T ? fmaf(f4at(gv[i >> 2], i & 3), SRWN_SQRT_HALF, (a2[i] + a1[i]) + a0[i]) : 0.f;
+      for (int i = 0; i < 8; i++) dx[i] = t < T ? fmaf(f4at(gv[i >> 2], i & 3), SRWN_SQRT_HALF, (a2[i] + a1[i]) + a0[i]) : 0.f;
     }
     tc_fence_before();
     if (t < T) {
       float* dst = dx_out + ((size_t)b * T + t) * kR + cb;
 #pragma unroll
-      for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(dx[4 * j], dx[4 * j + 1], dx[4 * j + 2], dx[4 * j + 3]);
+      for (int j = 0; j < 2; j++) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(dx[4 * j], dx[4 * j + 1], dx[4 * j + 2], dx[4 * j + 3]);
     }
     // x_l carries cond_l (model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l
-    if (P % 16 == 0) {
+    if (P % 8 == 0) {
 #pragma unroll
-      for (int i = 0; i < 16; i++) red[row * 33 + cb + i] = dx[i];
+      for (int i = 0; i < 8; i++) red[row * 33 + cb + i] = dx[i];
       __syncthreads();
-      const int ch = tid & 31, part = tid >> 5, tp = t0 + 16 * part;
+      const int ch = tid & 31, part = tid >> 5, tp = t0 + 8 * part;        // 16 parts of 8 rows, each inside one latent frame
       if (tp < T) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; i++) s += red[(16 * part + i) * 33 + ch];
+        for (int i = 0; i < 8; i++) s += red[(8 * part + i) * 33 + ch];
         atomicAdd(dcond + ((size_t)b * frames + tp / P) * kR + ch, s);
       }
     } else if (t < T) {
 #pragma unroll
-      for (int i = 0; i < 16; i++) atomicAdd(dcond + ((size_t)b * frames + t / P) * kR + cb + i, dx[i]);
+      for (int i = 0; i < 8; i++) atomicAdd(dcond + ((size_t)b * frames + t / P) * kR + cb + i, dx[i]);
     }
   }
   // ---- per-CTA partial sums: dWf | dbf ----
   float* pp = partial + (size_t)blockIdx.x * (2 * kR * kR + kR);
   __syncthreads();
-  float* red2 = reinterpret_cast<float*>(DAT);               // [8][16]
+  float* red2 = reinterpret_cast<float*>(DAT);               // [16][8]
   if (n_done > 0) {
     wait_or_trap(bar_w, phase_w, ctl->abort_words);
     tc_fence_after();
-    float v0[16], v1[16];
-    tc_ld16(lane_base + 128 + cb, v0); tc_ld16(lane_base + 160 + cb, v1);
+    float v0[8], v1[8];
+    tc_ld8(lane_base + 128 + cb, v0); tc_ld8(lane_base + 160 + cb, v1);
     tc_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 16; i++) red[row * 33 + cb + i] = v0[i] + (row < 64 ? v1[i] : 0.f);      // hi rows: hi*hi + hi*lo; lo rows: lo*hi
+    for (int i = 0; i < 8; i++) red[row * 33 + cb + i] = v0[i] + (row < 64 ? v1[i] : 0.f);      // hi rows: hi*hi + hi*lo; lo rows: lo*hi
   }
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
+  for (int i = 0; i < 8; i++) {
     float v = dsum[i];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red2[warp * 16 + i] = v;
+    if (lane == 0) red2[warp * 8 + i] = v;
   }
   __syncthreads();
   for (int i = tid; i < 2 * kR * kR; i += kThreads) pp[i] = n_done > 0 ? red[(i >> 5) * 33 + (i & 31)] + red[(64 + (i >> 5)) * 33 + (i & 31)] : 0.f;
   if (tid < kR) {
-    const int h = tid >> 4, e = tid & 15;
-    pp[2 * kR * kR + tid] = (red2[(4 * h) * 16 + e] + red2[(4 * h + 1) * 16 + e]) + (red2[(4 * h + 2) * 16 + e] + red2[(4 * h + 3) * 16 + e]);
+    const int w0 = 4 * (tid >> 3), e = tid & 7;
+    pp[2 * kR * kR + tid] = (red2[w0 * 8 + e] + red2[(w0 + 1) * 8 + e]) + (red2[(w0 + 2) * 8 + e] + red2[(w0 + 3) * 8 + e]);
   }
   cta_teardown(tmem);
 }

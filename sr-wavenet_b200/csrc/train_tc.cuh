@@ -4,7 +4,7 @@
 
 namespace traintc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 int fwd_smem_bytes();
 int gate_smem_bytes();
 int conv_smem_bytes();
