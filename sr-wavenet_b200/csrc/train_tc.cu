@@ -19,6 +19,11 @@
 // 16 * rows + 16 bytes.  [c_hi ; c_lo]^T (M) x [g_hi ; g_lo]^T (N = 64) is again one instruction per 8 time steps for all
 // four partial products, accumulated in TMEM over every tile of the CTA and read once at the end.
 //
+// Global memory is only touched with coalesced accesses (8 consecutive lanes = one 128-byte row: a thread-per-row LDG.128
+// touches 32 lines per instruction and the L1 tag stage, one line per clock, became the bound of the first version);
+// whatever a thread needs per ROW (TMEM lane) goes through shared memory in the operand layout, where both mappings are
+// conflict-free.
+//
 // Operand layouts (no swizzle, K-major, 8 x 16-byte core matrices; cute::UMMA canonical INTERLEAVE layout):
 //   activation operand (rows = time):    (row, ch)  at (ch / 4) * kCHS + row * 16 + (ch % 4) * 4      LBO = kCHS,  SBO = 128
 //   weight operand (rows = out channel): (n, k)     at (k / 4) * kWCH + n * 16 + (k % 4) * 4          LBO = kWCH,  SBO = 128
@@ -141,6 +146,7 @@ __device__ __forceinline__ void stage_weight(unsigned char* dst, F value) {
   }
 }
 
+// coalesced tile access: a thread's element i (i = 0, 1) is row (tid >> 3) + 64 i, 4-channel chunk tid & 7
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
@@ -162,6 +168,7 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
   Ctl* ctl = reinterpret_cast<Ctl*>(s_br + 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;         // epilogue: this thread's row (TMEM lane) and channel base
+  const int rA = tid >> 3, c4 = tid & 7;                                // coalesced access: rows rA, rA + 64, chunk c4
   // a[t][n] = sum_kk [tap | cur][t][kk] Wf[kk][n]: B(n, kk) = filt_k[kk * 32 + n]  (filt_k = [tap][cin][cout], tap 0 pairs with x[t-d])
   stage_weight<64>(WfB, [&](int n, int k) { return filt_k[k * kR + n]; });
   stage_weight<32>(WrB, [&](int n, int k) { return res_k[k * kR + n]; });
@@ -172,14 +179,13 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
   uint32_t phase = 0;
   const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
   constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
-  // operand rows are loaded coalesced: idx -> (row idx >> 3, 4-channel chunk idx & 7), two per thread
   float4 pc[2], pt[2];
   auto load_tile = [&](int tile) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     const float* xb = x_l + (size_t)b * T * kR;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-      const int idx = tid + i * kThreads, t = t0 + (idx >> 3), c4 = idx & 7;
+      const int t = t0 + rA + 64 * i;
       pc[i] = make_float4(0, 0, 0, 0); pt[i] = pc[i];
       if (t < T) {
         pc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
@@ -191,10 +197,9 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
   if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
-    const float* xb = x_l + (size_t)b * T * kR;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-      const int idx = tid + i * kThreads, r = idx >> 3, c4 = idx & 7;
+      const int r = rA + 64 * i;
       split_store4(X_hi + c4 * kCHS + r * 16, X_lo + c4 * kCHS + r * 16, pt[i]);
       split_store4(X_hi + (8 + c4) * kCHS + r * 16, X_lo + (8 + c4) * kCHS + r * 16, pc[i]);
     }
@@ -209,18 +214,13 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
       issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
       tc_commit(bar);
     }
-    // this thread's row of x_l and of the next layer's conditioning for the second epilogue, and the next tile's operand
-    // rows: all in flight during the GEMMs
+    // next layer's conditioning of this thread's row (one line per warp: a tile lies inside few latent frames) and the next
+    // tile's operand rows: in flight during the GEMMs
     const int t = t0 + row;
-    float4 xv[2], cn[2];
+    float4 cn[2];
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      xv[j] = make_float4(0, 0, 0, 0); cn[j] = xv[j];
-      if (t < T) {
-        xv[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
-        if (cond_next) cn[j] = ldg4(cond_next + ((size_t)b * frames + t / P) * L * kR + cb + 4 * j);
-      }
-    }
+    for (int j = 0; j < 2; j++)
+      cn[j] = (t < T && cond_next) ? ldg4(cond_next + ((size_t)b * frames + t / P) * L * kR + cb + 4 * j) : make_float4(0, 0, 0, 0);
     if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
@@ -253,28 +253,39 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
       issue_chain(tmem + 192, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI32, 0);
       tc_commit(bar);
     }
+    // x_l[t] back from its operand image: hi + lo is x to the last bit but one
+    float4 xv[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int chunk = 8 + (cb >> 2) + j;
+      const float4 h = *reinterpret_cast<const float4*>(X_hi + chunk * kCHS + row * 16), l = *reinterpret_cast<const float4*>(X_lo + chunk * kCHS + row * 16);
+      xv[j] = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+    }
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
     {
       float r0[8], r1[8], r2[8];
       tc_ld8(lane_base + 128 + cb, r0); tc_ld8(lane_base + 160 + cb, r1); tc_ld8(lane_base + 192 + cb, r2);
       tc_wait_ld();
-      if (t < T) {
-        float* dst = x_next + ((size_t)b * T + t) * kR + cb;
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-          float4 v;
+      for (int j = 0; j < 2; j++) {
+        float4 v;
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int i = 4 * j + e;
-            const float res = (r2[i] + r1[i]) + r0[i] + s_br[cb + i];           // residual 1x1 (ops.py:39)
-            f4at(v, e) = (f4at(xv[j], e) + res) * SRWN_SQRT_HALF + f4at(cn[j], e);   // ops.py:40, next layer's conditioning (model.py:183)
-          }
-          *reinterpret_cast<float4*>(dst + 4 * j) = v;
+        for (int e = 0; e < 4; e++) {
+          const int i = 4 * j + e;
+          const float res = (r2[i] + r1[i]) + r0[i] + s_br[cb + i];             // residual 1x1 (ops.py:39)
+          f4at(v, e) = (f4at(xv[j], e) + res) * SRWN_SQRT_HALF + f4at(cn[j], e);     // ops.py:40, next layer's conditioning (model.py:183)
         }
+        *reinterpret_cast<float4*>(X_hi + ((cb >> 2) + j) * kCHS + row * 16) = v;     // staged in the (dead) c rows for a coalesced store
       }
     }
     tc_fence_before();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int r = rA + 64 * i, tt = t0 + r;
+      if (tt < T) *reinterpret_cast<float4*>(x_next + ((size_t)b * T + tt) * kR + c4 * 4) = *reinterpret_cast<const float4*>(X_hi + c4 * kCHS + r * 16);
+    }
     __syncthreads();
   }
   cta_teardown(tmem);
@@ -306,6 +317,7 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
   Ctl* ctl = reinterpret_cast<Ctl*>(s_bf + 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;
+  const int rA = tid >> 3, c4 = tid & 7;
   stage_weight<64>(WfB, [&](int n, int k) { return filt_k[k * kR + n]; });
   // dc[t][k] = sum_n dres[t][n] Wr[k][n]: B(row = k, K index = n) = res_k[k * 32 + n]
   stage_weight<32>(WrT, [&](int krow, int n) { return res_k[krow * kR + n]; });
@@ -321,15 +333,16 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
   for (int i = 0; i < 8; i++) gsum[i] = 0.f;
   float4 xc[2], xt[2], gg[2];
   auto load_tile = [&](int tile) {
-    const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     const float* xb = x_l + (size_t)b * T * kR;
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      xc[j] = make_float4(0, 0, 0, 0); xt[j] = xc[j]; gg[j] = xc[j];
+    for (int i = 0; i < 2; i++) {
+      const int t = t0 + rA + 64 * i;
+      xc[i] = make_float4(0, 0, 0, 0); xt[i] = xc[i]; gg[i] = xc[i];
       if (t < T) {
-        xc[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
-        gg[j] = ldg4(g_in + ((size_t)b * T + t) * kR + cb + 4 * j);
-        if (t - d >= 0) xt[j] = ldg4(xb + (size_t)(t - d) * kR + cb + 4 * j);
+        xc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
+        gg[i] = ldg4(g_in + ((size_t)b * T + t) * kR + c4 * 4);
+        if (t - d >= 0) xt[i] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
       }
     }
   };
@@ -337,26 +350,14 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
   int n_done = 0;
   if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n_done++) {
-    const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
-    if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWr has read CT / GT
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const int chunk = (cb >> 2) + j;
-      split_store4(X_hi + chunk * kCHS + row * 16, X_lo + chunk * kCHS + row * 16, xt[j]);
-      split_store4(X_hi + (8 + chunk) * kCHS + row * 16, X_lo + (8 + chunk) * kCHS + row * 16, xc[j]);
-      float4 gs = make_float4(gg[j].x * SRWN_SQRT_HALF, gg[j].y * SRWN_SQRT_HALF, gg[j].z * SRWN_SQRT_HALF, gg[j].w * SRWN_SQRT_HALF);   // dres
-      float4 h, l;
-      split4(gs, h, l);
-      *reinterpret_cast<float4*>(G_hi + chunk * kCHS + row * 16) = h;
-      *reinterpret_cast<float4*>(G_lo + chunk * kCHS + row * 16) = l;
-      unsigned char* gt = GT + (row >> 2) * kTC64 + (row & 3) * 4;
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int n = cb + 4 * j + e;
-        *reinterpret_cast<float*>(gt + n * 16) = f4at(h, e);
-        *reinterpret_cast<float*>(gt + (32 + n) * 16) = f4at(l, e);
-        gsum[4 * j + e] += f4at(gs, e);
-      }
+    for (int i = 0; i < 2; i++) {
+      const int r = rA + 64 * i;
+      split_store4(X_hi + c4 * kCHS + r * 16, X_lo + c4 * kCHS + r * 16, xt[i]);
+      split_store4(X_hi + (8 + c4) * kCHS + r * 16, X_lo + (8 + c4) * kCHS + r * 16, xc[i]);
+      const float4 gs = make_float4(gg[i].x * SRWN_SQRT_HALF, gg[i].y * SRWN_SQRT_HALF, gg[i].z * SRWN_SQRT_HALF, gg[i].w * SRWN_SQRT_HALF);   // dres
+      split_store4(G_hi + c4 * kCHS + r * 16, G_lo + c4 * kCHS + r * 16, gs);
     }
     fence_async_smem();
     __syncthreads();
@@ -375,11 +376,27 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
       tc_commit(bar);
     }
     if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);        // next tile's rows, in flight during the GEMMs
+    // transposed copy of dres (this thread's row) for the weight gradient, while the GEMMs run
+    if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWr has read CT / GT
+    {
+      unsigned char* gt = GT + (row >> 2) * kTC64 + (row & 3) * 4;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int chunk = (cb >> 2) + j;
+        float4 h = *reinterpret_cast<const float4*>(G_hi + chunk * kCHS + row * 16), l = *reinterpret_cast<const float4*>(G_lo + chunk * kCHS + row * 16);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int n = cb + 4 * j + e;
+          *reinterpret_cast<float*>(gt + n * 16) = f4at(h, e);
+          *reinterpret_cast<float*>(gt + (32 + n) * 16) = f4at(l, e);
+          gsum[4 * j + e] += f4at(h, e) + f4at(l, e);
+        }
+      }
+    }
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
-    float da[8];
     {
-      float a0[8], a1[8], a2[8], d0[8], d1[8], d2[8];
+      float a0[8], a1[8], a2[8], d0[8], d1[8], d2[8], da[8];
       tc_ld8(lane_base + cb, a0); tc_ld8(lane_base + 32 + cb, a1); tc_ld8(lane_base + 64 + cb, a2);
       tc_ld8(lane_base + 96 + cb, d0); tc_ld8(lane_base + 128 + cb, d1); tc_ld8(lane_base + 160 + cb, d2);
       tc_wait_ld();
@@ -396,6 +413,10 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
         *reinterpret_cast<float*>(ct + (cb + i) * 16) = h;
         *reinterpret_cast<float*>(ct + (32 + cb + i) * 16) = l;
       }
+      // da staged in the (dead) dres rows for a coalesced store
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+        *reinterpret_cast<float4*>(G_hi + ((cb >> 2) + j) * kCHS + row * 16) = make_float4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
     }
     tc_fence_before();
     fence_async_smem();
@@ -406,11 +427,12 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
       issue_chain(tmem + 192, smem_u32(CT), kTC64, 2 * kTC64, smem_u32(GT), kTC64, 2 * kTC64, 16, kI64, n_done > 0 ? 1u : 0u);
       tc_commit(bar_w);
     }
-    if (t < T) {
-      float* dst = da_out + ((size_t)b * T + t) * kR + cb;
 #pragma unroll
-      for (int j = 0; j < 2; j++) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
+    for (int i = 0; i < 2; i++) {
+      const int r = rA + 64 * i, tt = t0 + r;
+      if (tt < T) *reinterpret_cast<float4*>(da_out + ((size_t)b * T + tt) * kR + c4 * 4) = *reinterpret_cast<const float4*>(G_hi + c4 * kCHS + r * 16);
     }
+    __syncthreads();
   }
   // ---- per-CTA partial sums: dWr | dbr ----
   float* pp = partial + (size_t)blockIdx.x * (kR * kR + kR);
@@ -449,7 +471,8 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
 constexpr int kConvDA = 2 * 16 * kCHS;                      // DA_hi | DA_lo: 8 chunks da[t] | 8 chunks da[t+d]
 constexpr int kConvDAT = 32 * kTC64;                        // [da_hi ; da_lo]^T
 constexpr int kConvXT = 32 * kTC128;                        // [tap_hi ; cur_hi ; tap_lo ; cur_lo]^T
-constexpr int kConvSmem = kConvDA + kConvDAT + kConvXT + 16 * kWCH + (int)sizeof(Ctl);
+constexpr int kConvXR = 16 * kCHS;                          // x rows as loaded (fp32): 8 tap chunks | 8 current chunks
+constexpr int kConvSmem = kConvDA + kConvDAT + kConvXT + kConvXR + 16 * kWCH + (int)sizeof(Ctl);
 int conv_smem_bytes() { return kConvSmem; }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -461,11 +484,13 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
   unsigned char* DA_lo = DA_hi + 16 * kCHS;
   unsigned char* DAT = smem + kConvDA;
   unsigned char* XT = DAT + kConvDAT;
-  unsigned char* WB = XT + kConvXT;
+  unsigned char* XR = XT + kConvXT;
+  unsigned char* WB = XR + kConvXR;
   Ctl* ctl = reinterpret_cast<Ctl*>(WB + 16 * kWCH);
-  float* red = reinterpret_cast<float*>(DA_hi);             // [128][33] floats once the dx GEMM has read DA
+  float* red = reinterpret_cast<float*>(XR);                // [128][33] floats once the transposed copies are made
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;
+  const int rA = tid >> 3, c4 = tid & 7;
   // dx[t][k] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]: B(row = k, K index j) = j < 32 ? W1[k][j] : W0[k][j - 32]
   stage_weight<64>(WB, [&](int krow, int j) { return j < 32 ? filt_k[kR * kR + krow * kR + j] : filt_k[krow * kR + (j - 32)]; });
   const uint32_t tmem = cta_setup(ctl, 2);
@@ -477,19 +502,21 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
   float dsum[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) dsum[i] = 0.f;
-  float4 xc[2], xt[2], dac[2], daf[2];
+  float4 xc[2], xt[2], dac[2], daf[2], gq[2];
   auto load_tile = [&](int tile) {
-    const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRows + row;
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     const float* xb = x_l + (size_t)b * T * kR;
     const float* db = da_in + (size_t)b * T * kR;
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      xc[j] = make_float4(0, 0, 0, 0); xt[j] = xc[j]; dac[j] = xc[j]; daf[j] = xc[j];
+    for (int i = 0; i < 2; i++) {
+      const int t = t0 + rA + 64 * i;
+      xc[i] = make_float4(0, 0, 0, 0); xt[i] = xc[i]; dac[i] = xc[i]; daf[i] = xc[i]; gq[i] = xc[i];
       if (t < T) {
-        xc[j] = ldg4(xb + (size_t)t * kR + cb + 4 * j);
-        dac[j] = ldg4(db + (size_t)t * kR + cb + 4 * j);
-        if (t - d >= 0) xt[j] = ldg4(xb + (size_t)(t - d) * kR + cb + 4 * j);
-        if (t + d < T) daf[j] = ldg4(db + (size_t)(t + d) * kR + cb + 4 * j);
+        xc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
+        dac[i] = ldg4(db + (size_t)t * kR + c4 * 4);
+        gq[i] = ldg4(g_in + ((size_t)b * T + t) * kR + c4 * 4);
+        if (t - d >= 0) xt[i] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
+        if (t + d < T) daf[i] = ldg4(db + (size_t)(t + d) * kR + c4 * 4);
       }
     }
   };
@@ -497,33 +524,16 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
   int n_done = 0;
   if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n_done++) {
-    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows, t = t0 + row;
-    if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWf has read DAT / XT
-    __syncthreads();                                                                       // and every thread is done with `red`
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const int chunk = (cb >> 2) + j;
-      float4 h, l, xth, xtl, xch, xcl;
-      split4(dac[j], h, l);
-      *reinterpret_cast<float4*>(DA_hi + chunk * kCHS + row * 16) = h;
-      *reinterpret_cast<float4*>(DA_lo + chunk * kCHS + row * 16) = l;
-      split_store4(DA_hi + (8 + chunk) * kCHS + row * 16, DA_lo + (8 + chunk) * kCHS + row * 16, daf[j]);
-      split4(xt[j], xth, xtl);
-      split4(xc[j], xch, xcl);
-      unsigned char* dt = DAT + (row >> 2) * kTC64 + (row & 3) * 4;
-      unsigned char* xq = XT + (row >> 2) * kTC128 + (row & 3) * 4;
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int n = cb + 4 * j + e;
-        *reinterpret_cast<float*>(dt + n * 16) = f4at(h, e);
-        *reinterpret_cast<float*>(dt + (32 + n) * 16) = f4at(l, e);
-        *reinterpret_cast<float*>(xq + n * 16) = f4at(xth, e);
-        *reinterpret_cast<float*>(xq + (32 + n) * 16) = f4at(xch, e);
-        *reinterpret_cast<float*>(xq + (64 + n) * 16) = f4at(xtl, e);
-        *reinterpret_cast<float*>(xq + (96 + n) * 16) = f4at(xcl, e);
-        dsum[4 * j + e] += f4at(dac[j], e);
-      }
+    for (int i = 0; i < 2; i++) {
+      const int r = rA + 64 * i;
+      split_store4(DA_hi + c4 * kCHS + r * 16, DA_lo + c4 * kCHS + r * 16, dac[i]);
+      split_store4(DA_hi + (8 + c4) * kCHS + r * 16, DA_lo + (8 + c4) * kCHS + r * 16, daf[i]);
+      *reinterpret_cast<float4*>(XR + c4 * kCHS + r * 16) = xt[i];
+      *reinterpret_cast<float4*>(XR + (8 + c4) * kCHS + r * 16) = xc[i];
     }
+    const float4 g0 = gq[0], g1 = gq[1];                   // this tile's rows of g, for the coalesced epilogue
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -534,37 +544,68 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       tc_fence_after();
       issue_chain(tmem + 64, smem_u32(DA_lo), kCHS, 2 * kCHS, smem_u32(WB), kWCH, 2 * kWCH, 8, kI32, 0);
       tc_commit(bar);
-    } else if (tid == 64) {
+    }
+    if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
+    // transposed copies (this thread's row) for the weight gradient, while the dx GEMMs run
+    if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWf has read DAT / XT
+    {
+      unsigned char* dt = DAT + (row >> 2) * kTC64 + (row & 3) * 4;
+      unsigned char* xq = XT + (row >> 2) * kTC128 + (row & 3) * 4;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int chunk = (cb >> 2) + j;
+        float4 h = *reinterpret_cast<const float4*>(DA_hi + chunk * kCHS + row * 16), l = *reinterpret_cast<const float4*>(DA_lo + chunk * kCHS + row * 16);
+        float4 xth, xtl, xch, xcl;
+        split4(*reinterpret_cast<const float4*>(XR + chunk * kCHS + row * 16), xth, xtl);
+        split4(*reinterpret_cast<const float4*>(XR + (8 + chunk) * kCHS + row * 16), xch, xcl);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int n = cb + 4 * j + e;
+          *reinterpret_cast<float*>(dt + n * 16) = f4at(h, e);
+          *reinterpret_cast<float*>(dt + (32 + n) * 16) = f4at(l, e);
+          *reinterpret_cast<float*>(xq + n * 16) = f4at(xth, e);
+          *reinterpret_cast<float*>(xq + (32 + n) * 16) = f4at(xch, e);
+          *reinterpret_cast<float*>(xq + (64 + n) * 16) = f4at(xtl, e);
+          *reinterpret_cast<float*>(xq + (96 + n) * 16) = f4at(xcl, e);
+          dsum[4 * j + e] += f4at(h, e) + f4at(l, e);
+        }
+      }
+    }
+    fence_async_smem();
+    __syncthreads();                                         // XR is free from here on: it becomes `red`
+    if (tid == 64) {
       // dWf[kk][n] += sum_t [tap | cur][t][kk] da[t][n]: [x_hi ; x_lo]^T (M = 128) x [da_hi ; da_lo]^T (N = 64)
       tc_fence_after();
       issue_chain(tmem + 128, smem_u32(XT), kTC128, 2 * kTC128, smem_u32(DAT), kTC64, 2 * kTC64, 16, kI64, n_done > 0 ? 1u : 0u);
       tc_commit(bar_w);
     }
-    float4 gv[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) gv[j] = t < T ? ldg4(g_in + ((size_t)b * T + t) * kR + cb + 4 * j) : make_float4(0, 0, 0, 0);
-    if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
-    float dx[8];
     {
       float a0[8], a1[8], a2[8];
       tc_ld8(lane_base + cb, a0); tc_ld8(lane_base + 32 + cb, a1); tc_ld8(lane_base + 64 + cb, a2);
       tc_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 8; i++) dx[i] = t < T ? fmaf(f4at(gv[i >> 2], i & 3), SRWN_SQRT_HALF, (a2[i] + a1[i]) + a0[i]) : 0.f;
+      for (int i = 0; i < 8; i++) red[row * 33 + cb + i] = (a2[i] + a1[i]) + a0[i];
     }
     tc_fence_before();
-    if (t < T) {
-      float* dst = dx_out + ((size_t)b * T + t) * kR + cb;
+    __syncthreads();
+    // coalesced: dx = g sqrt(1/2) + (da W1^T + da[t+d] W0^T), stored, and left in `red` for the conditioning gradient
 #pragma unroll
-      for (int j = 0; j < 2; j++) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(dx[4 * j], dx[4 * j + 1], dx[4 * j + 2], dx[4 * j + 3]);
+    for (int i = 0; i < 2; i++) {
+      const int r = rA + 64 * i, tt = t0 + r;
+      const float4 gvv = i == 0 ? g0 : g1;
+      float* rp = red + r * 33 + c4 * 4;
+      float4 v = make_float4(0, 0, 0, 0);
+      if (tt < T) {
+        v = make_float4(fmaf(gvv.x, SRWN_SQRT_HALF, rp[0]), fmaf(gvv.y, SRWN_SQRT_HALF, rp[1]), fmaf(gvv.z, SRWN_SQRT_HALF, rp[2]), fmaf(gvv.w, SRWN_SQRT_HALF, rp[3]));
+        *reinterpret_cast<float4*>(dx_out + ((size_t)b * T + tt) * kR + c4 * 4) = v;
+      }
+      rp[0] = v.x; rp[1] = v.y; rp[2] = v.z; rp[3] = v.w;
     }
+    __syncthreads();
     // x_l carries cond_l (model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l
     if (P % 8 == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) red[row * 33 + cb + i] = dx[i];
-      __syncthreads();
       const int ch = tid & 31, part = tid >> 5, tp = t0 + 8 * part;        // 16 parts of 8 rows, each inside one latent frame
       if (tp < T) {
         float s = 0.f;
@@ -572,15 +613,17 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
         for (int i = 0; i < 8; i++) s += red[(8 * part + i) * 33 + ch];
         atomicAdd(dcond + ((size_t)b * frames + tp / P) * kR + ch, s);
       }
-    } else if (t < T) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) atomicAdd(dcond + ((size_t)b * frames + t / P) * kR + cb + i, dx[i]);
+    } else {
+      for (int i = tid; i < kRows * kR; i += kThreads) {
+        const int tt = t0 + (i >> 5);
+        if (tt < T) atomicAdd(dcond + ((size_t)b * frames + tt / P) * kR + (i & 31), red[(i >> 5) * 33 + (i & 31)]);
+      }
     }
+    __syncthreads();
   }
   // ---- per-CTA partial sums: dWf | dbf ----
   float* pp = partial + (size_t)blockIdx.x * (2 * kR * kR + kR);
-  __syncthreads();
-  float* red2 = reinterpret_cast<float*>(DAT);               // [16][8]
+  float* red2 = reinterpret_cast<float*>(DA_hi);             // [16][8]
   if (n_done > 0) {
     wait_or_trap(bar_w, phase_w, ctl->abort_words);
     tc_fence_after();
