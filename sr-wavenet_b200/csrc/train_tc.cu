@@ -5,8 +5,9 @@
 //   k_bwd_gate_tc    da = dL/da (a = pre-activation of the filter conv), dWr, dbr        (recomputes a, f, c from x_l)
 //   k_bwd_conv_tc    dx_l = g sqrt(1/2) + da W1^T + da[t+d] W0^T, dWf, dbf, dcond_l
 //
-// Tile = 128 time steps = the M of one MMA, 512 threads (thread = (row, quarter of the 32 channels): four warps per
-// scheduler hide the latencies of the epilogue math), one persistent CTA per SM.
+// Tile = 128 time steps = the M of one MMA; 512 worker threads (thread = (row, quarter of the 32 channels): four warps per
+// scheduler hide the latencies of the epilogue math) plus two issuing warps (a tcgen05.mma costs its issuing thread 60-120
+// clocks: 16-40 instructions per tile would otherwise sit on the workers' critical path); one persistent CTA per SM.
 // fp32 grade on TF32 tensor cores: every operand is split x = hi + lo into two TF32 numbers by truncation (x - hi is exact)
 // and a product is hi*hi + hi*lo + lo*hi.  The two terms that share the A operand come out of ONE instruction by stacking
 // [W_hi ; W_lo] along N (N = 64), so a GEMM costs two instruction chains instead of three:
@@ -50,6 +51,18 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// issued by a whole (converged) warp: the instruction itself is predicated on the elected lane, so the descriptors stay in
+// uniform registers and the compiler emits no per-thread election loop around it
+__device__ __forceinline__ void mma_tf32_elect(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+constexpr int kWorkers = 512;                 // warps 0..15: operand staging and epilogues; warp 16: GEMM issue; warp 17: weight-gradient issue
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -89,16 +102,19 @@ __device__ __forceinline__ void wait_or_trap(uint32_t bar, uint32_t parity, vola
 }
 
 struct Ctl {                 // barriers and bookkeeping at the end of dynamic shared memory
-  uint64_t bar_main, bar_wgrad;
+  uint64_t bar_main, bar_wgrad;          // tcgen05.commit: the GEMMs / the weight-gradient GEMM of a tile have retired
+  uint64_t full_main, full_wgrad;        // workers -> issuer warps: the operands are in shared memory
   uint32_t tmem_slot;
   int abort_words[2];
 };
 
-__device__ __forceinline__ uint32_t cta_setup(Ctl* ctl, int main_arrivals) {
+__device__ __forceinline__ uint32_t cta_setup(Ctl* ctl) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    mbar_init(smem_u32(&ctl->bar_main), main_arrivals);
+    mbar_init(smem_u32(&ctl->bar_main), 1);
     mbar_init(smem_u32(&ctl->bar_wgrad), 1);
+    mbar_init(smem_u32(&ctl->full_main), 1);
+    mbar_init(smem_u32(&ctl->full_wgrad), 1);
     ctl->abort_words[0] = ctl->abort_words[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -120,24 +136,25 @@ __device__ __forceinline__ void cta_teardown(uint32_t tmem) {
   }
 }
 
-// one instruction chain: nk K-steps of 8, A and B descriptors advancing by a_adv / b_adv bytes
+// one instruction chain (called by a whole warp): nk K-steps of 8, A and B descriptors advancing by a_adv / b_adv bytes
 __device__ __forceinline__ void issue_chain(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_adv, uint32_t b_addr,
                                             uint32_t b_lbo, uint32_t b_adv, int nk, uint32_t idesc, uint32_t acc_first) {
   const uint64_t da = make_desc(a_addr, a_lbo, 128), db = make_desc(b_addr, b_lbo, 128);
   const uint64_t as = (uint64_t)(a_adv >> 4), bs = (uint64_t)(b_adv >> 4);
 #pragma unroll 4
-  for (int k = 0; k < nk; k++) mma_tf32(d_tmem, da + k * as, db + k * bs, idesc, k > 0 ? 1u : acc_first);
+  for (int k = 0; k < nk; k++) mma_tf32_elect(d_tmem, da + k * as, db + k * bs, idesc, k > 0 ? 1u : acc_first);
 }
 
 // weight operand with the hi part in rows 0..31 and the lo part in rows 32..63: value(n, k) for n, k < 32 / K
 template <int K, typename F>
 __device__ __forceinline__ void stage_weight(unsigned char* dst, F value) {
-  float v[K * 32 / kThreads];
+  if (threadIdx.x >= kWorkers) return;
+  float v[K * 32 / kWorkers];
 #pragma unroll
-  for (int u = 0; u < K * 32 / kThreads; u++) { const int i = threadIdx.x + u * kThreads; v[u] = value(i & 31, i >> 5); }     // all loads in flight at once
+  for (int u = 0; u < K * 32 / kWorkers; u++) { const int i = threadIdx.x + u * kWorkers; v[u] = value(i & 31, i >> 5); }     // all loads in flight at once
 #pragma unroll
-  for (int u = 0; u < K * 32 / kThreads; u++) {
-    const int i = threadIdx.x + u * kThreads, k = i >> 5, n = i & 31;
+  for (int u = 0; u < K * 32 / kWorkers; u++) {
+    const int i = threadIdx.x + u * kWorkers, k = i >> 5, n = i & 31;
     float h, l;
     split_tf32(v[u], h, l);
     unsigned char* p = dst + (k >> 2) * kWCH + n * 16 + (k & 3) * 4;
@@ -166,19 +183,38 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
   float* s_bf = reinterpret_cast<float*>(WrB + 8 * kWCH);
   float* s_br = s_bf + 32;
   Ctl* ctl = reinterpret_cast<Ctl*>(s_br + 32);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;         // epilogue: this thread's row (TMEM lane) and channel base
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int row = (warp & 3) * 32 + lane, cb = ((warp >> 2) & 3) * 8;   // epilogue: this thread's row (TMEM lane) and channel base
   const int rA = tid >> 3, c4 = tid & 7;                                // coalesced access: rows rA, rA + 64, chunk c4
   // a[t][n] = sum_kk [tap | cur][t][kk] Wf[kk][n]: B(n, kk) = filt_k[kk * 32 + n]  (filt_k = [tap][cin][cout], tap 0 pairs with x[t-d])
   stage_weight<64>(WfB, [&](int n, int k) { return filt_k[k * kR + n]; });
   stage_weight<32>(WrB, [&](int n, int k) { return res_k[k * kR + n]; });
   if (tid < kR) { s_bf[tid] = filt_b[tid]; s_br[tid] = res_b[tid]; }
-  const uint32_t tmem = cta_setup(ctl, 2);
+  const uint32_t tmem = cta_setup(ctl);
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t bar = smem_u32(&ctl->bar_main);
+  const uint32_t bar = smem_u32(&ctl->bar_main), full = smem_u32(&ctl->full_main);
   uint32_t phase = 0;
   const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
   constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
+  if (warp >= 16) {
+    if (warp == 16) {                     // GEMM issue: filter conv, then residual 1x1, per tile
+      grid_dependency_wait();
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        wait_or_trap(full, phase, ctl->abort_words); phase ^= 1;
+        tc_fence_after();
+        issue_chain(tmem, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI64, 0);
+        issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
+        tc_commit_elect(bar);
+        wait_or_trap(full, phase, ctl->abort_words); phase ^= 1;
+        tc_fence_after();
+        issue_chain(tmem + 128, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI64, 0);
+        issue_chain(tmem + 192, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI32, 0);
+        tc_commit_elect(bar);
+      }
+    }
+    cta_teardown(tmem);
+    return;
+  }
   float4 pc[2], pt[2];
   auto load_tile = [&](int tile) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
@@ -204,16 +240,8 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
       split_store4(X_hi + (8 + c4) * kCHS + r * 16, X_lo + (8 + c4) * kCHS + r * 16, pc[i]);
     }
     fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_chain(tmem, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI64, 0);
-      tc_commit(bar);
-    } else if (tid == 32) {
-      tc_fence_after();
-      issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
-      tc_commit(bar);
-    }
+    worker_sync();
+    if (tid == 0) mbar_arrive(full);
     // next layer's conditioning of this thread's row (one line per warp: a tile lies inside few latent frames) and the next
     // tile's operand rows: in flight during the GEMMs
     const int t = t0 + row;
@@ -243,16 +271,8 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
     }
     tc_fence_before();
     fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_chain(tmem + 128, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI64, 0);
-      tc_commit(bar);
-    } else if (tid == 32) {
-      tc_fence_after();
-      issue_chain(tmem + 192, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI32, 0);
-      tc_commit(bar);
-    }
+    worker_sync();
+    if (tid == 0) mbar_arrive(full);
     // x_l[t] back from its operand image: hi + lo is x to the last bit but one
     float4 xv[2];
 #pragma unroll
@@ -280,13 +300,13 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
       }
     }
     tc_fence_before();
-    __syncthreads();
+    worker_sync();
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int r = rA + 64 * i, tt = t0 + r;
       if (tt < T) *reinterpret_cast<float4*>(x_next + ((size_t)b * T + tt) * kR + c4 * 4) = *reinterpret_cast<const float4*>(X_hi + c4 * kCHS + r * 16);
     }
-    __syncthreads();
+    worker_sync();
   }
   cta_teardown(tmem);
 }
@@ -315,19 +335,45 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
   unsigned char* WrT = WfB + 16 * kWCH;
   float* s_bf = reinterpret_cast<float*>(WrT + 8 * kWCH);
   Ctl* ctl = reinterpret_cast<Ctl*>(s_bf + 32);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int row = (warp & 3) * 32 + lane, cb = ((warp >> 2) & 3) * 8;
   const int rA = tid >> 3, c4 = tid & 7;
   stage_weight<64>(WfB, [&](int n, int k) { return filt_k[k * kR + n]; });
   // dc[t][k] = sum_n dres[t][n] Wr[k][n]: B(row = k, K index = n) = res_k[k * 32 + n]
   stage_weight<32>(WrT, [&](int krow, int n) { return res_k[krow * kR + n]; });
   if (tid < kR) s_bf[tid] = filt_b[tid];
-  const uint32_t tmem = cta_setup(ctl, 3);
+  const uint32_t tmem = cta_setup(ctl);
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t bar = smem_u32(&ctl->bar_main), bar_w = smem_u32(&ctl->bar_wgrad);
+  const uint32_t full = smem_u32(&ctl->full_main), full_w = smem_u32(&ctl->full_wgrad);
   uint32_t phase = 0, phase_w = 0;
   const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
   constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
+  if (warp >= 16) {
+    grid_dependency_wait();
+    if (warp == 16) {                     // a = [tap | cur] Wf and dc = dres Wr^T
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        wait_or_trap(full, phase, ctl->abort_words); phase ^= 1;
+        tc_fence_after();
+        issue_chain(tmem, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI64, 0);
+        issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
+        issue_chain(tmem + 96, smem_u32(G_hi), kCHS, 2 * kCHS, smem_u32(WrT), kWCH, 2 * kWCH, 4, kI64, 0);
+        issue_chain(tmem + 160, smem_u32(G_lo), kCHS, 2 * kCHS, smem_u32(WrT), kWCH, 2 * kWCH, 4, kI32, 0);
+        tc_commit_elect(bar);
+      }
+    } else if (warp == 17) {              // dWr[k][n] += sum_t c[t][k] dres[t][n]: [c_hi ; c_lo]^T x [g_hi ; g_lo]^T, 16 steps of 8 time steps
+      uint32_t acc = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        wait_or_trap(full_w, phase_w, ctl->abort_words); phase_w ^= 1;
+        tc_fence_after();
+        issue_chain(tmem + 192, smem_u32(CT), kTC64, 2 * kTC64, smem_u32(GT), kTC64, 2 * kTC64, 16, kI64, acc);
+        tc_commit_elect(bar_w);
+        acc = 1;
+      }
+    }
+    cta_teardown(tmem);
+    return;
+  }
   float gsum[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) gsum[i] = 0.f;
@@ -360,21 +406,8 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
       split_store4(G_hi + c4 * kCHS + r * 16, G_lo + c4 * kCHS + r * 16, gs);
     }
     fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_chain(tmem, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI64, 0);
-      tc_commit(bar);
-    } else if (tid == 32) {
-      tc_fence_after();
-      issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
-      tc_commit(bar);
-    } else if (tid == 64) {
-      tc_fence_after();
-      issue_chain(tmem + 96, smem_u32(G_hi), kCHS, 2 * kCHS, smem_u32(WrT), kWCH, 2 * kWCH, 4, kI64, 0);
-      issue_chain(tmem + 160, smem_u32(G_lo), kCHS, 2 * kCHS, smem_u32(WrT), kWCH, 2 * kWCH, 4, kI32, 0);
-      tc_commit(bar);
-    }
+    worker_sync();
+    if (tid == 0) mbar_arrive(full);
     if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);        // next tile's rows, in flight during the GEMMs
     // transposed copy of dres (this thread's row) for the weight gradient, while the GEMMs run
     if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWr has read CT / GT
@@ -420,19 +453,14 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
     }
     tc_fence_before();
     fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      // dWr[k][n] += sum_t c[t][k] dres[t][n]: [c_hi ; c_lo]^T x [g_hi ; g_lo]^T, 16 steps of 8 time steps
-      tc_fence_after();
-      issue_chain(tmem + 192, smem_u32(CT), kTC64, 2 * kTC64, smem_u32(GT), kTC64, 2 * kTC64, 16, kI64, n_done > 0 ? 1u : 0u);
-      tc_commit(bar_w);
-    }
+    worker_sync();
+    if (tid == 0) mbar_arrive(full_w);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int r = rA + 64 * i, tt = t0 + r;
       if (tt < T) *reinterpret_cast<float4*>(da_out + ((size_t)b * T + tt) * kR + c4 * 4) = *reinterpret_cast<const float4*>(G_hi + c4 * kCHS + r * 16);
     }
-    __syncthreads();
+    worker_sync();
   }
   // ---- per-CTA partial sums: dWr | dbr ----
   float* pp = partial + (size_t)blockIdx.x * (kR * kR + kR);
@@ -456,8 +484,8 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red2[warp * 8 + i] = v;
   }
-  __syncthreads();
-  for (int i = tid; i < kR * kR; i += kThreads) pp[i] = n_done > 0 ? red[(i >> 5) * 33 + (i & 31)] + red[(32 + (i >> 5)) * 33 + (i & 31)] : 0.f;
+  worker_sync();
+  for (int i = tid; i < kR * kR; i += kWorkers) pp[i] = n_done > 0 ? red[(i >> 5) * 33 + (i & 31)] + red[(32 + (i >> 5)) * 33 + (i & 31)] : 0.f;
   if (tid < kR) {                                            // channel tid: quarter tid >> 3 = warps 4 (tid >> 3) .. + 3
     const int w0 = 4 * (tid >> 3), e = tid & 7;
     pp[kR * kR + tid] = (red2[w0 * 8 + e] + red2[(w0 + 1) * 8 + e]) + (red2[(w0 + 2) * 8 + e] + red2[(w0 + 3) * 8 + e]);
@@ -488,17 +516,41 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
   unsigned char* WB = XR + kConvXR;
   Ctl* ctl = reinterpret_cast<Ctl*>(WB + 16 * kWCH);
   float* red = reinterpret_cast<float*>(XR);                // [128][33] floats once the transposed copies are made
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = (warp & 3) * 32 + lane, cb = (warp >> 2) * 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int row = (warp & 3) * 32 + lane, cb = ((warp >> 2) & 3) * 8;
   const int rA = tid >> 3, c4 = tid & 7;
   // dx[t][k] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]: B(row = k, K index j) = j < 32 ? W1[k][j] : W0[k][j - 32]
   stage_weight<64>(WB, [&](int krow, int j) { return j < 32 ? filt_k[kR * kR + krow * kR + j] : filt_k[krow * kR + (j - 32)]; });
-  const uint32_t tmem = cta_setup(ctl, 2);
+  const uint32_t tmem = cta_setup(ctl);
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t bar = smem_u32(&ctl->bar_main), bar_w = smem_u32(&ctl->bar_wgrad);
+  const uint32_t full = smem_u32(&ctl->full_main), full_w = smem_u32(&ctl->full_wgrad);
   uint32_t phase = 0, phase_w = 0;
   const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
   constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
+  if (warp >= 16) {
+    grid_dependency_wait();
+    if (warp == 16) {                     // dx = [da | da(t+d)] [W1 ; W0]^T
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        wait_or_trap(full, phase, ctl->abort_words); phase ^= 1;
+        tc_fence_after();
+        issue_chain(tmem, smem_u32(DA_hi), kCHS, 2 * kCHS, smem_u32(WB), kWCH, 2 * kWCH, 8, kI64, 0);
+        issue_chain(tmem + 64, smem_u32(DA_lo), kCHS, 2 * kCHS, smem_u32(WB), kWCH, 2 * kWCH, 8, kI32, 0);
+        tc_commit_elect(bar);
+      }
+    } else if (warp == 17) {              // dWf[kk][n] += sum_t [tap | cur][t][kk] da[t][n]: [x_hi ; x_lo]^T (M = 128) x [da_hi ; da_lo]^T (N = 64)
+      uint32_t acc = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        wait_or_trap(full_w, phase_w, ctl->abort_words); phase_w ^= 1;
+        tc_fence_after();
+        issue_chain(tmem + 128, smem_u32(XT), kTC128, 2 * kTC128, smem_u32(DAT), kTC64, 2 * kTC64, 16, kI64, acc);
+        tc_commit_elect(bar_w);
+        acc = 1;
+      }
+    }
+    cta_teardown(tmem);
+    return;
+  }
   float dsum[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) dsum[i] = 0.f;
@@ -535,16 +587,8 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     }
     const float4 g0 = gq[0], g1 = gq[1];                   // this tile's rows of g, for the coalesced epilogue
     fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_chain(tmem, smem_u32(DA_hi), kCHS, 2 * kCHS, smem_u32(WB), kWCH, 2 * kWCH, 8, kI64, 0);
-      tc_commit(bar);
-    } else if (tid == 32) {
-      tc_fence_after();
-      issue_chain(tmem + 64, smem_u32(DA_lo), kCHS, 2 * kCHS, smem_u32(WB), kWCH, 2 * kWCH, 8, kI32, 0);
-      tc_commit(bar);
-    }
+    worker_sync();
+    if (tid == 0) mbar_arrive(full);
     if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
     // transposed copies (this thread's row) for the weight gradient, while the dx GEMMs run
     if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWf has read DAT / XT
@@ -572,13 +616,8 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       }
     }
     fence_async_smem();
-    __syncthreads();                                         // XR is free from here on: it becomes `red`
-    if (tid == 64) {
-      // dWf[kk][n] += sum_t [tap | cur][t][kk] da[t][n]: [x_hi ; x_lo]^T (M = 128) x [da_hi ; da_lo]^T (N = 64)
-      tc_fence_after();
-      issue_chain(tmem + 128, smem_u32(XT), kTC128, 2 * kTC128, smem_u32(DAT), kTC64, 2 * kTC64, 16, kI64, n_done > 0 ? 1u : 0u);
-      tc_commit(bar_w);
-    }
+    worker_sync();                                           // XR is free from here on: it becomes `red`
+    if (tid == 0) mbar_arrive(full_w);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
     {
@@ -589,7 +628,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       for (int i = 0; i < 8; i++) red[row * 33 + cb + i] = (a2[i] + a1[i]) + a0[i];
     }
     tc_fence_before();
-    __syncthreads();
+    worker_sync();
     // coalesced: dx = g sqrt(1/2) + (da W1^T + da[t+d] W0^T), stored, and left in `red` for the conditioning gradient
 #pragma unroll
     for (int i = 0; i < 2; i++) {
@@ -603,7 +642,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       }
       rp[0] = v.x; rp[1] = v.y; rp[2] = v.z; rp[3] = v.w;
     }
-    __syncthreads();
+    worker_sync();
     // x_l carries cond_l (model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l
     if (P % 8 == 0) {
       const int ch = tid & 31, part = tid >> 5, tp = t0 + 8 * part;        // 16 parts of 8 rows, each inside one latent frame
@@ -614,12 +653,12 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
         atomicAdd(dcond + ((size_t)b * frames + tp / P) * kR + ch, s);
       }
     } else {
-      for (int i = tid; i < kRows * kR; i += kThreads) {
+      for (int i = tid; i < kRows * kR; i += kWorkers) {
         const int tt = t0 + (i >> 5);
         if (tt < T) atomicAdd(dcond + ((size_t)b * frames + tt / P) * kR + (i & 31), red[(i >> 5) * 33 + (i & 31)]);
       }
     }
-    __syncthreads();
+    worker_sync();
   }
   // ---- per-CTA partial sums: dWf | dbf ----
   float* pp = partial + (size_t)blockIdx.x * (2 * kR * kR + kR);
@@ -640,8 +679,8 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red2[warp * 8 + i] = v;
   }
-  __syncthreads();
-  for (int i = tid; i < 2 * kR * kR; i += kThreads) pp[i] = n_done > 0 ? red[(i >> 5) * 33 + (i & 31)] + red[(64 + (i >> 5)) * 33 + (i & 31)] : 0.f;
+  worker_sync();
+  for (int i = tid; i < 2 * kR * kR; i += kWorkers) pp[i] = n_done > 0 ? red[(i >> 5) * 33 + (i & 31)] + red[(64 + (i >> 5)) * 33 + (i & 31)] : 0.f;
   if (tid < kR) {
     const int w0 = 4 * (tid >> 3), e = tid & 7;
     pp[2 * kR * kR + tid] = (red2[w0 * 8 + e] + red2[(w0 + 1) * 8 + e]) + (red2[(w0 + 2) * 8 + e] + red2[(w0 + 3) * 8 + e]);

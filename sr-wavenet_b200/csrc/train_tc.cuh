@@ -4,7 +4,7 @@
 
 namespace traintc {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 576;      // 16 worker warps + 2 issuing warps
 int fwd_smem_bytes();
 int gate_smem_bytes();
 int conv_smem_bytes();
