@@ -69,10 +69,11 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
-// x = hi + lo, both valid TF32 numbers (low 13 mantissa bits clear); x - hi is exact, truncating lo costs 2^-20 |x|
+// x = hi + lo: hi is a valid TF32 number (low 13 mantissa bits clear) and x - hi is exact.  lo is stored with all its bits:
+// the tensor core reads the top 19 of them, and whether it truncates or rounds the rest moves the product by 2^-21 |x| at most.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+  lo = x - hi;
 }
 __device__ __forceinline__ void split4(float4 v, float4& h, float4& l) {
   split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
@@ -273,7 +274,7 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
     fence_async_smem();
     worker_sync();
     if (tid == 0) mbar_arrive(full);
-    // x_l[t] back from its operand image: hi + lo is x to the last bit but one
+    // x_l[t] back from its operand image: hi + lo is x exactly
     float4 xv[2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
