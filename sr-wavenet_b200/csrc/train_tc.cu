@@ -33,6 +33,15 @@
 #include "umma.cuh"
 #include "train_tc.cuh"
 
+#ifdef SRWN_TUNING
+// per-phase clock stamps of CTA 0's worker thread 0 on its fourth tile (tools/tc_trace.py)
+__device__ long long g_tc_trace[3][16];
+#define TC_STAMP(k, it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) == 3) g_tc_trace[k][slot] = clock64(); } while (0)
+extern "C" int srwn_debug_tc_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(g_tc_trace)); }
+#else
+#define TC_STAMP(k, it, slot) do { } while (0)
+#endif
+
 namespace traintc {
 using namespace umma;
 
@@ -273,7 +282,9 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
 #pragma unroll
     for (int j = 0; j < 2; j++)
       cn[j] = (t < T && cond_next) ? ldg4(cond_next + ((size_t)b * frames + t / P) * L * kR + cb + 4 * j) : make_float4(0, 0, 0, 0);
+    TC_STAMP(0, i, 0);
     wait_or_trap(bar_g1, i & 1, ctl->abort_words);
+    TC_STAMP(0, i, 1);
     tc_fence_after();
     {
       float a0[8], a1[8], a2[8];
@@ -292,14 +303,17 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
         split_store4(X_hi + chunk * kCHS + row * 16, X_lo + chunk * kCHS + row * 16, c);
       }
     }
+    TC_STAMP(0, i, 2);
     tc_fence_before();
     fence_async_smem();
     worker_sync();
-    if (tid == 0) mbar_arrive(full_c);                                           // issuer: residual GEMM of tile i
+    if (tid == 0) mbar_arrive(full_c);
+    TC_STAMP(0, i, 3);                                           // issuer: residual GEMM of tile i
     if (i + 1 < n_my) {                                                          // then the filter conv of tile i + 1, from the other buffer
       store_tile(i + 1);
       if (i + 2 < n_my) load_tile(i + 2);
     }
+    TC_STAMP(0, i, 4);
     // x_l[t] back from its operand image: hi + lo is x exactly
     float4 xv[2];
 #pragma unroll
@@ -308,7 +322,9 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
       const float4 h = *reinterpret_cast<const float4*>(X_hi + chunk * kCHS + row * 16), l = *reinterpret_cast<const float4*>(X_lo + chunk * kCHS + row * 16);
       xv[j] = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
     }
+    TC_STAMP(0, i, 5);
     wait_or_trap(bar_g2, i & 1, ctl->abort_words);
+    TC_STAMP(0, i, 6);
     tc_fence_after();
     {
       float r0[8], r1[8], r2[8];
@@ -326,13 +342,16 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
         *reinterpret_cast<float4*>(X_hi + ((cb >> 2) + j) * kCHS + row * 16) = v;     // staged in the (dead) c rows for a coalesced store
       }
     }
+    TC_STAMP(0, i, 7);
     tc_fence_before();
     worker_sync();
+    TC_STAMP(0, i, 8);
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const int r = rA + 64 * u, tt = t0 + r;
       if (tt < T) *reinterpret_cast<float4*>(x_next + ((size_t)b * T + tt) * kR + c4 * 4) = *reinterpret_cast<const float4*>(X_hi + c4 * kCHS + r * 16);
     }
+    TC_STAMP(0, i, 9);
     // the next write to this buffer (the image of tile i + 2) comes after the barrier that ends E1(i + 1)
   }
   cta_teardown(tmem);
@@ -424,6 +443,7 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
   if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n_done++) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
+    TC_STAMP(1, n_done, 0);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int r = rA + 64 * i;
@@ -432,12 +452,15 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
       const float4 gs = make_float4(gg[i].x * SRWN_SQRT_HALF, gg[i].y * SRWN_SQRT_HALF, gg[i].z * SRWN_SQRT_HALF, gg[i].w * SRWN_SQRT_HALF);   // dres
       split_store4(G_hi + c4 * kCHS + r * 16, G_lo + c4 * kCHS + r * 16, gs);
     }
+    TC_STAMP(1, n_done, 1);
     fence_async_smem();
     worker_sync();
     if (tid == 0) mbar_arrive(full);
+    TC_STAMP(1, n_done, 2);
     if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);        // next tile's rows, in flight during the GEMMs
     // transposed copy of dres (this thread's row) for the weight gradient, while the GEMMs run
     if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWr has read CT / GT
+    TC_STAMP(1, n_done, 3);
     {
       unsigned char* gt = GT + (row >> 2) * kTC64 + (row & 3) * 4;
 #pragma unroll
@@ -453,7 +476,9 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
         }
       }
     }
+    TC_STAMP(1, n_done, 4);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
+    TC_STAMP(1, n_done, 5);
     tc_fence_after();
     {
       float a0[8], a1[8], a2[8], d0[8], d1[8], d2[8], da[8];
@@ -478,16 +503,20 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
       for (int j = 0; j < 2; j++)
         *reinterpret_cast<float4*>(G_hi + ((cb >> 2) + j) * kCHS + row * 16) = make_float4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
     }
+    TC_STAMP(1, n_done, 6);
     tc_fence_before();
     fence_async_smem();
     worker_sync();
     if (tid == 0) mbar_arrive(full_w);
+    TC_STAMP(1, n_done, 7);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int r = rA + 64 * i, tt = t0 + r;
       if (tt < T) *reinterpret_cast<float4*>(da_out + ((size_t)b * T + tt) * kR + c4 * 4) = *reinterpret_cast<const float4*>(G_hi + c4 * kCHS + r * 16);
     }
+    TC_STAMP(1, n_done, 8);
     worker_sync();
+    TC_STAMP(1, n_done, 9);
   }
   // ---- per-CTA partial sums: dWr | dbr ----
   float* pp = partial + (size_t)blockIdx.x * (kR * kR + kR);
@@ -604,6 +633,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
   if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n_done++) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
+    TC_STAMP(2, n_done, 0);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int r = rA + 64 * i;
@@ -613,12 +643,15 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       *reinterpret_cast<float4*>(XR + (8 + c4) * kCHS + r * 16) = xc[i];
     }
     const float4 g0 = gq[0], g1 = gq[1];                   // this tile's rows of g, for the coalesced epilogue
+    TC_STAMP(2, n_done, 1);
     fence_async_smem();
     worker_sync();
     if (tid == 0) mbar_arrive(full);
+    TC_STAMP(2, n_done, 2);
     if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
     // transposed copies (this thread's row) for the weight gradient, while the dx GEMMs run
     if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWf has read DAT / XT
+    TC_STAMP(2, n_done, 3);
     {
       unsigned char* dt = DAT + (row >> 2) * kTC64 + (row & 3) * 4;
       unsigned char* xq = XT + (row >> 2) * kTC128 + (row & 3) * 4;
@@ -642,10 +675,13 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
         }
       }
     }
+    TC_STAMP(2, n_done, 4);
     fence_async_smem();
     worker_sync();                                           // XR is free from here on: it becomes `red`
     if (tid == 0) mbar_arrive(full_w);
+    TC_STAMP(2, n_done, 5);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
+    TC_STAMP(2, n_done, 6);
     tc_fence_after();
     {
       float a0[8], a1[8], a2[8];
@@ -654,8 +690,10 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
 #pragma unroll
       for (int i = 0; i < 8; i++) red[row * 33 + cb + i] = (a2[i] + a1[i]) + a0[i];
     }
+    TC_STAMP(2, n_done, 7);
     tc_fence_before();
     worker_sync();
+    TC_STAMP(2, n_done, 8);
     // coalesced: dx = g sqrt(1/2) + (da W1^T + da[t+d] W0^T), stored, and left in `red` for the conditioning gradient
 #pragma unroll
     for (int i = 0; i < 2; i++) {
@@ -669,7 +707,9 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       }
       rp[0] = v.x; rp[1] = v.y; rp[2] = v.z; rp[3] = v.w;
     }
+    TC_STAMP(2, n_done, 9);
     worker_sync();
+    TC_STAMP(2, n_done, 10);
     // x_l carries cond_l (model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l
     if (P % 8 == 0) {
       const int ch = tid & 31, part = tid >> 5, tp = t0 + 8 * part;        // 16 parts of 8 rows, each inside one latent frame
@@ -685,7 +725,9 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
         if (tt < T) atomicAdd(dcond + ((size_t)b * frames + tt / P) * kR + (i & 31), red[(i >> 5) * 33 + (i & 31)]);
       }
     }
+    TC_STAMP(2, n_done, 11);
     worker_sync();
+    TC_STAMP(2, n_done, 12);
   }
   // ---- per-CTA partial sums: dWf | dbf ----
   float* pp = partial + (size_t)blockIdx.x * (2 * kR * kR + kR);
