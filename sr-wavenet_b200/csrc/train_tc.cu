@@ -50,7 +50,7 @@ constexpr int kCHS = kRows * 16 + 16;        // 2064
 constexpr int kTC64 = 64 * 16 + 16;          // 1040
 constexpr int kTC128 = 128 * 16 + 16;        // 2064
 constexpr int kWCH = 64 * 16;                // 1024
-constexpr uint32_t kTmemCols = 512;          // one CTA per SM: the whole tensor memory
+constexpr uint32_t kTmemCols = 256;
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   // cute::UMMA::InstrDescriptor: c = F32 (bit 4), a / b format TF32 = 2 (bits 7, 10), K-major, N >> 3 at 17, M >> 4 at 24
@@ -98,7 +98,16 @@ __device__ __forceinline__ void split_store4(unsigned char* hi, unsigned char* l
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tanh_ex2(float x) { return fmaf(-2.0f, rcp_approx(ex2_approx(x * 2.885390081777927f) + 1.0f), 1.0f); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
+// sigmoid of a number in [-1, 1] (the gate applies it to a tanh): 0.5 + f P(f^2), degree-4 minimax P, 5e-8 absolute -- FMA
+// pipe work instead of two more MUFU operations per element (the epilogues are MUFU-bound: 16 per clock per SM)
+__device__ __forceinline__ float sigmoid_fast(float f) {
+  const float u = f * f;
+  float p = fmaf(u, 1.6739570128265768e-05f, -0.00020698922162409872f);
+  p = fmaf(u, p, 0.0020820044446736574f);
+  p = fmaf(u, p, -0.020833170041441917f);
+  p = fmaf(u, p, 0.25f);
+  return fmaf(f, p, 0.5f);
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float& f4at(float4& v, int e) { return reinterpret_cast<float*>(&v)[e]; }
 
@@ -177,10 +186,7 @@ __device__ __forceinline__ void stage_weight(unsigned char* dst, F value) {
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
-// Two tiles in flight: the operand image and the filter-conv accumulator are double-buffered, so the workers store tile i+1
-// while the residual GEMM of tile i runs, and the filter conv of tile i+1 runs during the second epilogue of tile i.
-//   workers : S(0) | E1(i)  S(i+1)  E2(i) | ...        issuer : G1(0) | G2(i)  G1(i+1) | ...
-constexpr int kFwdX = 2 * 16 * kCHS;                               // X_hi | X_lo of one tile: 8 tap chunks | 8 current chunks each
+constexpr int kFwdX = 16 * kCHS;                                   // one of X_hi / X_lo: 8 tap chunks | 8 current chunks
 constexpr int kFwdSmem = 2 * kFwdX + 16 * kWCH + 8 * kWCH + 2 * 32 * 4 + (int)sizeof(Ctl);
 int fwd_smem_bytes() { return kFwdSmem; }
 
@@ -189,8 +195,9 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
                const float* __restrict__ filt_b, const float* __restrict__ res_k, const float* __restrict__ res_b,
                const float* __restrict__ cond_next, int B, int T, int d, int P, int L, int frames) {
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* Xbuf = smem;                                          // [2][X_hi | X_lo]
-  unsigned char* WfB = smem + 2 * kFwdX;
+  unsigned char* X_hi = smem;
+  unsigned char* X_lo = X_hi + kFwdX;
+  unsigned char* WfB = X_lo + kFwdX;
   unsigned char* WrB = WfB + 16 * kWCH;
   float* s_bf = reinterpret_cast<float*>(WrB + 8 * kWCH);
   float* s_br = s_bf + 32;
@@ -204,116 +211,87 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
   if (tid < kR) { s_bf[tid] = filt_b[tid]; s_br[tid] = res_b[tid]; }
   const uint32_t tmem = cta_setup(ctl);
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t bar_g1 = smem_u32(&ctl->bar_main), bar_g2 = smem_u32(&ctl->bar_wgrad);
-  const uint32_t full_c = smem_u32(&ctl->full_main), full_x = smem_u32(&ctl->full_wgrad);      // workers -> issuer: c stored / operand image stored
+  const uint32_t bar = smem_u32(&ctl->bar_main), full = smem_u32(&ctl->full_main);
+  uint32_t phase = 0;
   const int tiles_per_b = (T + kRows - 1) / kRows, n_tiles = B * tiles_per_b;
-  const int n_my = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   constexpr uint32_t kI64 = idesc_tf32(128, 64), kI32 = idesc_tf32(128, 32);
-  // accumulators: filter conv of tile i at columns 96 (i & 1) (hi*hi | hi*lo | lo*hi), residual 1x1 at columns 192
   if (warp >= 16) {
-    if (warp == 16 && n_my > 0) {
-      uint32_t phc = 0, phx = 0;
-      auto g1 = [&](int i) {
-        const uint32_t xh = smem_u32(Xbuf + (i & 1) * kFwdX), d1 = tmem + 96 * (i & 1);
-        issue_chain(d1, xh, kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI64, 0);
-        issue_chain(d1 + 64, xh + 16 * kCHS, kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
-        tc_commit_elect(bar_g1);
-      };
-      wait_or_trap(full_x, phx, ctl->abort_words); phx ^= 1;
-      tc_fence_after();
-      g1(0);
-      for (int i = 0; i < n_my; i++) {
-        wait_or_trap(full_c, phc, ctl->abort_words); phc ^= 1;       // c of tile i is in the tap rows
+    if (warp == 16) {                     // GEMM issue: filter conv, then residual 1x1, per tile
+      grid_dependency_wait();
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        wait_or_trap(full, phase, ctl->abort_words); phase ^= 1;
         tc_fence_after();
-        const uint32_t xh = smem_u32(Xbuf + (i & 1) * kFwdX);
-        issue_chain(tmem + 192, xh, kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI64, 0);
-        issue_chain(tmem + 256, xh + 16 * kCHS, kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI32, 0);
-        tc_commit_elect(bar_g2);
-        if (i + 1 < n_my) {
-          wait_or_trap(full_x, phx, ctl->abort_words); phx ^= 1;     // operand image of tile i + 1
-          tc_fence_after();
-          g1(i + 1);
-        }
+        issue_chain(tmem, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI64, 0);
+        issue_chain(tmem + 64, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WfB), kWCH, 2 * kWCH, 8, kI32, 0);
+        tc_commit_elect(bar);
+        wait_or_trap(full, phase, ctl->abort_words); phase ^= 1;
+        tc_fence_after();
+        issue_chain(tmem + 128, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI64, 0);
+        issue_chain(tmem + 192, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI32, 0);
+        tc_commit_elect(bar);
       }
     }
     cta_teardown(tmem);
     return;
   }
   float4 pc[2], pt[2];
-  auto load_tile = [&](int i) {
-    const int tile = blockIdx.x + i * gridDim.x, b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
+  auto load_tile = [&](int tile) {
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     const float* xb = x_l + (size_t)b * T * kR;
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int t = t0 + rA + 64 * u;
-      pc[u] = make_float4(0, 0, 0, 0); pt[u] = pc[u];
+    for (int i = 0; i < 2; i++) {
+      const int t = t0 + rA + 64 * i;
+      pc[i] = make_float4(0, 0, 0, 0); pt[i] = pc[i];
       if (t < T) {
-        pc[u] = ldg4(xb + (size_t)t * kR + c4 * 4);
-        if (t - d >= 0) pt[u] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
+        pc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
+        if (t - d >= 0) pt[i] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
       }
     }
   };
-  auto store_tile = [&](int i) {
-    unsigned char* X_hi = Xbuf + (i & 1) * kFwdX;
-    unsigned char* X_lo = X_hi + 16 * kCHS;
+  grid_dependency_wait();
+  if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int r = rA + 64 * u;
-      split_store4(X_hi + c4 * kCHS + r * 16, X_lo + c4 * kCHS + r * 16, pt[u]);
-      split_store4(X_hi + (8 + c4) * kCHS + r * 16, X_lo + (8 + c4) * kCHS + r * 16, pc[u]);
+    for (int i = 0; i < 2; i++) {
+      const int r = rA + 64 * i;
+      split_store4(X_hi + c4 * kCHS + r * 16, X_lo + c4 * kCHS + r * 16, pt[i]);
+      split_store4(X_hi + (8 + c4) * kCHS + r * 16, X_lo + (8 + c4) * kCHS + r * 16, pc[i]);
     }
     fence_async_smem();
     worker_sync();
-    if (tid == 0) mbar_arrive(full_x);
-  };
-  grid_dependency_wait();
-  if (n_my > 0) {
-    load_tile(0);
-    store_tile(0);
-    if (n_my > 1) load_tile(1);
-  }
-  for (int i = 0; i < n_my; i++) {
-    const int tile = blockIdx.x + i * gridDim.x, b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows, t = t0 + row;
-    unsigned char* X_hi = Xbuf + (i & 1) * kFwdX;
-    unsigned char* X_lo = X_hi + 16 * kCHS;
-    const uint32_t d1 = lane_base + 96 * (i & 1), d2 = lane_base + 192;
-    // next layer's conditioning of this thread's row (one line per warp: a tile lies inside few latent frames)
+    if (tid == 0) mbar_arrive(full);
+    // next layer's conditioning of this thread's row (one line per warp: a tile lies inside few latent frames) and the next
+    // tile's operand rows: in flight during the GEMMs
+    const int t = t0 + row;
     float4 cn[2];
 #pragma unroll
     for (int j = 0; j < 2; j++)
       cn[j] = (t < T && cond_next) ? ldg4(cond_next + ((size_t)b * frames + t / P) * L * kR + cb + 4 * j) : make_float4(0, 0, 0, 0);
-    TC_STAMP(0, i, 0);
-    wait_or_trap(bar_g1, i & 1, ctl->abort_words);
-    TC_STAMP(0, i, 1);
+    if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
+    wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
     {
       float a0[8], a1[8], a2[8];
-      tc_ld8(d1 + cb, a0); tc_ld8(d1 + 32 + cb, a1); tc_ld8(d1 + 64 + cb, a2);
+      tc_ld8(lane_base + cb, a0); tc_ld8(lane_base + 32 + cb, a1); tc_ld8(lane_base + 64 + cb, a2);
       tc_wait_ld();
 #pragma unroll
       for (int j = 0; j < 2; j++) {
         float4 c;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const int k = 4 * j + e;
-          const float f = tanh_ex2((a2[k] + a1[k]) + a0[k] + s_bf[cb + k]);     // gate: tanh, sigmoid OF THE TANH, product (ops.py:28,33,36)
+          const int i = 4 * j + e;
+          const float f = tanh_ex2((a2[i] + a1[i]) + a0[i] + s_bf[cb + i]);     // gate: tanh, sigmoid OF THE TANH, product (ops.py:28,33,36)
           f4at(c, e) = f * sigmoid_fast(f);
         }
         const int chunk = (cb >> 2) + j;                                         // c takes over the tap rows (dead after the filter conv)
         split_store4(X_hi + chunk * kCHS + row * 16, X_lo + chunk * kCHS + row * 16, c);
       }
     }
-    TC_STAMP(0, i, 2);
     tc_fence_before();
     fence_async_smem();
     worker_sync();
-    if (tid == 0) mbar_arrive(full_c);
-    TC_STAMP(0, i, 3);                                           // issuer: residual GEMM of tile i
-    if (i + 1 < n_my) {                                                          // then the filter conv of tile i + 1, from the other buffer
-      store_tile(i + 1);
-      if (i + 2 < n_my) load_tile(i + 2);
-    }
-    TC_STAMP(0, i, 4);
+    if (tid == 0) mbar_arrive(full);
     // x_l[t] back from its operand image: hi + lo is x exactly
     float4 xv[2];
 #pragma unroll
@@ -322,37 +300,32 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
       const float4 h = *reinterpret_cast<const float4*>(X_hi + chunk * kCHS + row * 16), l = *reinterpret_cast<const float4*>(X_lo + chunk * kCHS + row * 16);
       xv[j] = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
     }
-    TC_STAMP(0, i, 5);
-    wait_or_trap(bar_g2, i & 1, ctl->abort_words);
-    TC_STAMP(0, i, 6);
+    wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     tc_fence_after();
     {
       float r0[8], r1[8], r2[8];
-      tc_ld8(d2 + cb, r0); tc_ld8(d2 + 32 + cb, r1); tc_ld8(d2 + 64 + cb, r2);
+      tc_ld8(lane_base + 128 + cb, r0); tc_ld8(lane_base + 160 + cb, r1); tc_ld8(lane_base + 192 + cb, r2);
       tc_wait_ld();
 #pragma unroll
       for (int j = 0; j < 2; j++) {
         float4 v;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const int k = 4 * j + e;
-          const float res = (r2[k] + r1[k]) + r0[k] + s_br[cb + k];             // residual 1x1 (ops.py:39)
+          const int i = 4 * j + e;
+          const float res = (r2[i] + r1[i]) + r0[i] + s_br[cb + i];             // residual 1x1 (ops.py:39)
           f4at(v, e) = (f4at(xv[j], e) + res) * SRWN_SQRT_HALF + f4at(cn[j], e);     // ops.py:40, next layer's conditioning (model.py:183)
         }
         *reinterpret_cast<float4*>(X_hi + ((cb >> 2) + j) * kCHS + row * 16) = v;     // staged in the (dead) c rows for a coalesced store
       }
     }
-    TC_STAMP(0, i, 7);
     tc_fence_before();
     worker_sync();
-    TC_STAMP(0, i, 8);
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int r = rA + 64 * u, tt = t0 + r;
+    for (int i = 0; i < 2; i++) {
+      const int r = rA + 64 * i, tt = t0 + r;
       if (tt < T) *reinterpret_cast<float4*>(x_next + ((size_t)b * T + tt) * kR + c4 * 4) = *reinterpret_cast<const float4*>(X_hi + c4 * kCHS + r * 16);
     }
-    TC_STAMP(0, i, 9);
-    // the next write to this buffer (the image of tile i + 2) comes after the barrier that ends E1(i + 1)
+    worker_sync();
   }
   cta_teardown(tmem);
 }

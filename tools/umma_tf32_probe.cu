@@ -196,17 +196,17 @@ int main() {
     ok &= good;
 
   }
-  // ---- timing of shapes (results of the timed part are not checked) ----
-  for (int f16 = 0; f16 < 2; f16++) for (int M : {128, 64}) for (int N : {32, 64}) for (int alt : {1, 2, 4}) for (int lay = 0; lay < 1; lay++) {
+  // ---- timing of shapes (results of the timed part are not checked): aligned (2048) vs padded (2064) chunk stride ----
+  for (int M : {128}) for (int N : {32, 64}) for (int alt : {1, 4}) for (int lay = 0; lay < 3; lay++) {
     const int K = 64;
-    std::vector<unsigned char> A(128 * K * 4, 0), B(64 * K * 4, 0);
+    std::vector<unsigned char> A(128 * K * 4 + 4096, 0), B(64 * K * 4 + 4096, 0);
     Case c{};
-    if (lay == 0) { c.a_lbo = 128 * 16; c.a_sbo = 128; c.b_lbo = 64 * 16; c.b_sbo = 128; c.a_step = 2 * 128 * 16; c.b_step = 2 * 64 * 16; }
-    else { c.a_lbo = 128; c.a_sbo = K * 4 * 8; c.b_lbo = 128; c.b_sbo = K * 4 * 8; c.a_step = 256; c.b_step = 256; }   // core matrices adjacent along K
-    c.idesc = f16 ? make_idesc(0, M, N) : idesc_tf32(M, N, 0, 0);
-    c.nk = 8; c.alt = alt; c.f16 = f16;
+    const int pad = lay == 0 ? 0 : lay == 1 ? 16 : 64;
+    c.a_lbo = 128 * 16 + pad; c.a_sbo = 128; c.b_lbo = 64 * 16 + pad; c.b_sbo = 128; c.a_step = 2 * (128 * 16 + pad); c.b_step = 2 * (64 * 16 + pad);
+    c.idesc = idesc_tf32(M, N, 0, 0);
+    c.nk = 8; c.alt = alt; c.f16 = 0;
     std::vector<double> ref(M * N, 0.0);
-    char nm[80]; snprintf(nm, sizeof nm, "time %s M%d N%d %s %s", f16 ? "f16 K16" : "tf32 K8", M, N, alt == 1 ? "1 issuing warp" : alt == 2 ? "2 issuing warps" : "4 issuing warps", lay ? "[rowgrp][kchunk]" : "[kchunk][row]");
+    char nm[80]; snprintf(nm, sizeof nm, "time tf32 M%d N%d %d issuing warp(s), chunk stride 16 rows + %d B", M, N, alt, pad);
     run(nm, A, B, c, ref, M, N, 65, 1e30);
   }
   // ---- case 2b: which operand accepts MN-major?  one K step (T = 8) and T = 64 ----
