@@ -1,6 +1,8 @@
-// Student distillation step, device side (fp32): forward that keeps every layer input, and the backward pass
+// Student distillation step, device side (fp32 grade): forward that keeps every layer input, and the backward pass
 // of the IAF flows (model.py:415-535) given the gradient of the loss (model.py:356-379) with respect to the
-// network output.  Layer-at-a-time FFMA kernels; activations and their gradients round-trip HBM in fp32.
+// network output.  Layer at a time; activations and their gradients round-trip HBM in fp32.  The three per-layer
+// kernels are tcgen05 kernels (train_tc.cu); this file holds the elementwise kernels around them, the teacher's
+// fp32-grade layer kernel (mma.sync, with the skip output) and the host sequence.
 //
 //   forward (per flow f):  x_0 = front(x_{f-1}) + cond_0;  x_{l+1} = (x_l + Wr c_l + br) sqrt(1/2) + cond_{l+1},
 //                          c_l = f sigmoid(f), f = tanh(W0 x_l[t-d] + W1 x_l[t] + bf)          (ops.py:23-46, F1-F3)
@@ -35,20 +37,11 @@ __device__ __forceinline__ void grid_dependency_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 // ---- warp-level TF32 tensor-core helpers (mma.sync.m16n8k8, fp32 accumulate) ------------------------------
-// The backward GEMMs are tiny in N and K (32 / 64 channels) and HBM-bound once they leave the FFMA pipe; operands are
-// rounded to TF32 (cvt.rna, 10-bit mantissa) when they are staged in shared memory, products accumulate in fp32.
+// Used by the teacher's fp32-grade layer kernel below (operands pre-split into hi + lo TF32 parts, three MMAs per product).
 // Fragment layouts (g = lane >> 2, q = lane & 3):  A 16x8 row-major: a0 (g, q) a1 (g+8, q) a2 (g, q+4) a3 (g+8, q+4);
 // B 8x8: b0 (k = q, n = g) b1 (k = q+4, n = g);  C 16x8: c0 (g, 2q) c1 (g, 2q+1) c2 (g+8, 2q) c3 (g+8, 2q+1).
-__device__ __forceinline__ float tf32r(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ float4 tf32r4(float4 v) { return make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w)); }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], float a0, float a1, float a2, float a3, float b0, float b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -96,31 +89,6 @@ __device__ __forceinline__ void split_store4(float* h, float* l, float4 v) {
   split_tf32(v.x, vh.x, vl.x); split_tf32(v.y, vh.y, vl.y); split_tf32(v.z, vh.z, vl.z); split_tf32(v.w, vh.w, vl.w);
   *reinterpret_cast<float4*>(h) = vh;
   *reinterpret_cast<float4*>(l) = vl;
-}
-
-// The backward kernels keep their operands in shared memory as plain fp32 and split them in registers when a fragment is
-// loaded: d += a b at fp32 grade = lo*hi + hi*lo + hi*hi (small terms first).  Round 1 rounded the operands to ONE TF32
-// number (2^-11) and recomputed the gate with tanh.approx: the gradients came out 1.4e-3 of each variable's scale off the
-// float64 oracle, above the 1e-4 the fp32 path promises.
-__device__ __forceinline__ void split4(const float (&a)[4], float (&h)[4], float (&l)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; i++) split_tf32(a[i], h[i], l[i]);
-}
-__device__ __forceinline__ void mma_x3(float (&d)[4], const float (&ah)[4], const float (&al)[4], float b0h, float b1h, float b0l, float b1l) {
-  mma_tf32(d, al[0], al[1], al[2], al[3], b0h, b1h);
-  mma_tf32(d, ah[0], ah[1], ah[2], ah[3], b0l, b1l);
-  mma_tf32(d, ah[0], ah[1], ah[2], ah[3], b0h, b1h);
-}
-__device__ __forceinline__ void mma_x3_raw(float (&d)[4], const float (&ah)[4], const float (&al)[4], float b0, float b1) {
-  float b0h, b0l, b1h, b1l;
-  split_tf32(b0, b0h, b0l); split_tf32(b1, b1h, b1l);
-  mma_x3(d, ah, al, b0h, b1h, b0l, b1l);
-}
-// tanh / sigmoid for the recomputed gate: ex2.approx + rcp.approx are good to ~2 ulp, i.e. ~2e-7 absolute on outputs in
-// [-1, 1] (tanh.approx alone is 5e-4)
-__device__ __forceinline__ float tanh_ex2(float x) {
-  const float e = __expf(2.0f * fminf(fmaxf(x, -15.f), 15.f));
-  return 1.0f - 2.0f * __frcp_rn(e + 1.0f);
 }
 
 template <bool SKIP>
@@ -291,266 +259,9 @@ k_fwd_layer(const float* __restrict__ x_l, float* __restrict__ x_next, const flo
   }
 }
 
-// ---- gate backward ------------------------------------------------------------------------------------
-// g = dL/dx_{l+1}; recomputes a, f, c from x_l; writes da = dL/da; accumulates dWr [32][32], dbr [32].
-// Tile = 64 time steps, 8 warps.  Stages 1-2: warp (mt = warp & 3, nh = warp >> 2) owns rows 16 mt.. and channels
-// 16 nh..; stage 3 (dWr = c^T dres over the tile's rows): warp (mi = warp & 1, ni = warp >> 1) owns one 16x8 block.
-struct GateSmem {
-  float a_tap[kTT][kAP], a_cur[kTT][kAP], c[kTT][kAP], g[kTT][kAP];      // fp32 as loaded / computed (split at fragment load)
-  float wf_h[2 * kR][kWP], wf_l[2 * kR][kWP], wr_h[kR][kAP], wr_l[kR][kAP], bf[kR];
-};
-
-__global__ void __launch_bounds__(kThreads, 3)
-k_bwd_gate(const float* __restrict__ x_l, const float* __restrict__ g_in, float* __restrict__ da_out,
-           const float* __restrict__ filt_k, const float* __restrict__ filt_b, const float* __restrict__ res_k,
-           float* __restrict__ partial,            // [gridDim.x][kR*kR + kR]: dWr | dbr
-           int B, int T, int d) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  GateSmem& s = *reinterpret_cast<GateSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  for (int i = tid; i < 2 * kR * kR; i += kThreads) split_tf32(filt_k[i], s.wf_h[i / kR][i % kR], s.wf_l[i / kR][i % kR]);
-  for (int i = tid; i < kR * kR; i += kThreads) split_tf32(res_k[i], s.wr_h[i / kR][i % kR], s.wr_l[i / kR][i % kR]);
-  if (tid < kR) s.bf[tid] = filt_b[tid];
-  const int tiles_per_b = (T + kTT - 1) / kTT;
-  const int n_tiles = B * tiles_per_b;
-  const int mt = warp & 3, nh = warp >> 2, r0 = mt * 16;
-  const int mi = warp & 1, ni = warp >> 1;
-  float gw[4] = {0.f, 0.f, 0.f, 0.f};      // dWr block: rows (k) 16 mi + g (+8), columns (n) 8 ni + 2q (+1)
-  float gb = 0.f;                          // dbr[lane] (warp 0)
-  grid_dependency_wait();
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
-    const float* xb = x_l + (size_t)b * T * kR;
-    const float* gbp = g_in + (size_t)b * T * kR;
-    __syncthreads();
-    for (int i = tid; i < kTT * (kR / 4); i += kThreads) {
-      const int row = i / (kR / 4), c4 = i % (kR / 4);
-      const int t = t0 + row;
-      float4 cur = make_float4(0, 0, 0, 0), tap = cur, gg = cur;
-      if (t < T) {
-        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + c4 * 4);
-        gg = *reinterpret_cast<const float4*>(gbp + (size_t)t * kR + c4 * 4);
-        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + c4 * 4);
-      }
-      gg.x *= SRWN_SQRT_HALF; gg.y *= SRWN_SQRT_HALF; gg.z *= SRWN_SQRT_HALF; gg.w *= SRWN_SQRT_HALF;   // dres
-      *reinterpret_cast<float4*>(&s.a_cur[row][c4 * 4]) = cur;
-      *reinterpret_cast<float4*>(&s.a_tap[row][c4 * 4]) = tap;
-      *reinterpret_cast<float4*>(&s.g[row][c4 * 4]) = gg;
-    }
-    __syncthreads();
-    // stage 1: a = [x[t-d] | x[t]] Wf + bf (ops.py:6-20), f = tanh(a), c = f sigmoid(f) (ops.py:28,33,36)
-    float acc[2][4], fv[2][4], sv[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; nt++) {
-      const int n0 = nh * 16 + nt * 8 + 2 * q;
-      acc[nt][0] = acc[nt][2] = s.bf[n0]; acc[nt][1] = acc[nt][3] = s.bf[n0 + 1];
-    }
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) {
-      const float (*X)[kAP] = ks < 4 ? s.a_tap : s.a_cur;
-      const int kc = (ks & 3) * 8;
-      const float a[4] = {X[r0 + g][kc + q], X[r0 + g + 8][kc + q], X[r0 + g][kc + q + 4], X[r0 + g + 8][kc + q + 4]};
-      float ah[4], al[4];
-      split4(a, ah, al);
-#pragma unroll
-      for (int nt = 0; nt < 2; nt++) {
-        const int n0 = nh * 16 + nt * 8;
-        mma_x3(acc[nt], ah, al, s.wf_h[ks * 8 + q][n0 + g], s.wf_h[ks * 8 + q + 4][n0 + g], s.wf_l[ks * 8 + q][n0 + g], s.wf_l[ks * 8 + q + 4][n0 + g]);
-      }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 2; nt++) {
-      const int n0 = nh * 16 + nt * 8 + 2 * q;
-#pragma unroll
-      // recomputed gate (ex2 / rcp based: ~2e-7 absolute, see tanh_ex2)
-      for (int e = 0; e < 4; e++) { fv[nt][e] = tanh_ex2(acc[nt][e]); sv[nt][e] = sigmoid_fast(fv[nt][e]); }
-      *reinterpret_cast<float2*>(&s.c[r0 + g][n0]) = make_float2(fv[nt][0] * sv[nt][0], fv[nt][1] * sv[nt][1]);
-      *reinterpret_cast<float2*>(&s.c[r0 + g + 8][n0]) = make_float2(fv[nt][2] * sv[nt][2], fv[nt][3] * sv[nt][3]);
-    }
-    // stage 2: dc[t][k] = sum_n dres[t][n] Wr[k][n]  (same (row, channel) positions as a / f)
-    float dc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-    for (int ks = 0; ks < 4; ks++) {
-      const int kc = ks * 8;
-      const float a[4] = {s.g[r0 + g][kc + q], s.g[r0 + g + 8][kc + q], s.g[r0 + g][kc + q + 4], s.g[r0 + g + 8][kc + q + 4]};
-      float ah[4], al[4];
-      split4(a, ah, al);
-#pragma unroll
-      for (int nt = 0; nt < 2; nt++) {
-        const int k0 = nh * 16 + nt * 8;
-        mma_x3(dc[nt], ah, al, s.wr_h[k0 + g][kc + q], s.wr_h[k0 + g][kc + q + 4], s.wr_l[k0 + g][kc + q], s.wr_l[k0 + g][kc + q + 4]);
-      }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 2; nt++) {
-      const int n0 = nh * 16 + nt * 8 + 2 * q;
-      float da[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const float f = fv[nt][e], sg = sv[nt][e];
-        const float df = dc[nt][e] * (sg + f * sg * (1.f - sg));       // d(f sigmoid(f))/df
-        da[e] = df * (1.f - f * f);                                    // tanh'
-      }
-      const int ta = t0 + r0 + g, tb = ta + 8;
-      if (ta < T) *reinterpret_cast<float2*>(da_out + ((size_t)b * T + ta) * kR + n0) = make_float2(da[0], da[1]);
-      if (tb < T) *reinterpret_cast<float2*>(da_out + ((size_t)b * T + tb) * kR + n0) = make_float2(da[2], da[3]);
-    }
-    __syncthreads();
-    // stage 3: dWr[k][n] += sum_t c[t][k] dres[t][n]; dbr[n] += sum_t dres[t][n]   (rows past T hold zeros in g)
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) {
-      const int tq = ks * 8 + q, m0 = mi * 16 + g, n0 = ni * 8 + g;
-      const float a[4] = {s.c[tq][m0], s.c[tq][m0 + 8], s.c[tq + 4][m0], s.c[tq + 4][m0 + 8]};
-      float ah[4], al[4];
-      split4(a, ah, al);
-      mma_x3_raw(gw, ah, al, s.g[tq][n0], s.g[tq + 4][n0]);
-    }
-    if (warp == 0) {
-#pragma unroll 8
-      for (int t = 0; t < kTT; t++) gb += s.g[t][lane];
-    }
-  }
-  float* pp = partial + (size_t)blockIdx.x * (kR * kR + kR);
-  {
-    const int m0 = mi * 16 + g, n0 = ni * 8 + 2 * q;
-    *reinterpret_cast<float2*>(pp + m0 * kR + n0) = make_float2(gw[0], gw[1]);
-    *reinterpret_cast<float2*>(pp + (m0 + 8) * kR + n0) = make_float2(gw[2], gw[3]);
-  }
-  if (warp == 0) pp[kR * kR + lane] = gb;
-}
-
-// ---- conv backward ------------------------------------------------------------------------------------
-// dx_l[t] = g[t] sqrt(1/2) + da[t] W1^T + da[t+d] W0^T;  dWf0 += x_l[t-d]^T da[t], dWf1 += x_l[t]^T da[t],
-// dbf += sum da;  dcond_l[b][t/P] += dx_l[t] (one tile lies inside one latent frame when P % 64 == 0, else atomics).
-// Stage 1: warp (mt, nh) as above; stage 2 (dWf = [x[t-d] | x[t]]^T da): warp (mi = warp & 3, nj = warp >> 2) owns
-// input rows 16 mi.. of the 64 stacked rows and output channels 16 nj...
-struct ConvSmem {
-  float a_tap[kTT][kAP], a_cur[kTT][kAP], da[kTT][kAP], da_f[kTT][kAP];
-  float w0_h[kR][kAP], w0_l[kR][kAP], w1_h[kR][kAP], w1_l[kR][kAP];   // [cin][cout] as stored (read as (cin = g, cout = q)), split
-  float red[4][kR];
-};
-
-__global__ void __launch_bounds__(kThreads)
-k_bwd_conv(const float* __restrict__ x_l, const float* __restrict__ g_in, const float* __restrict__ da_in,
-           float* __restrict__ dx_out, const float* __restrict__ filt_k,
-           float* __restrict__ partial,            // [gridDim.x][2*kR*kR + kR]: dWf | dbf
-           float* __restrict__ dcond,              // [B][frames][kR] for this layer (zero-initialised), atomics
-           int B, int T, int d, int P, int frames) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  for (int i = tid; i < kR * kR; i += kThreads) {
-    split_tf32(filt_k[i], s.w0_h[i / kR][i % kR], s.w0_l[i / kR][i % kR]);
-    split_tf32(filt_k[kR * kR + i], s.w1_h[i / kR][i % kR], s.w1_l[i / kR][i % kR]);
-  }
-  const int tiles_per_b = (T + kTT - 1) / kTT;
-  const int n_tiles = B * tiles_per_b;
-  const int mt = warp & 3, nh = warp >> 2, r0 = mt * 16;
-  const int mi = warp & 3, nj = warp >> 2;
-  float gw[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // dWf block: rows 16 mi + g (+8), columns 16 nj + 8 nt + 2q (+1)
-  float gb = 0.f;
-  grid_dependency_wait();
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kTT;
-    const float* xb = x_l + (size_t)b * T * kR;
-    const float* db = da_in + (size_t)b * T * kR;
-    __syncthreads();
-    for (int i = tid; i < kTT * (kR / 4); i += kThreads) {
-      const int row = i / (kR / 4), c4 = i % (kR / 4);
-      const int t = t0 + row;
-      float4 cur = make_float4(0, 0, 0, 0), tap = cur, a = cur, af = cur;
-      if (t < T) {
-        cur = *reinterpret_cast<const float4*>(xb + (size_t)t * kR + c4 * 4);
-        a = *reinterpret_cast<const float4*>(db + (size_t)t * kR + c4 * 4);
-        if (t - d >= 0) tap = *reinterpret_cast<const float4*>(xb + (size_t)(t - d) * kR + c4 * 4);
-        if (t + d < T) af = *reinterpret_cast<const float4*>(db + (size_t)(t + d) * kR + c4 * 4);
-      }
-      *reinterpret_cast<float4*>(&s.a_cur[row][c4 * 4]) = cur;
-      *reinterpret_cast<float4*>(&s.a_tap[row][c4 * 4]) = tap;
-      *reinterpret_cast<float4*>(&s.da[row][c4 * 4]) = a;
-      *reinterpret_cast<float4*>(&s.da_f[row][c4 * 4]) = af;
-    }
-    __syncthreads();
-    // stage 1: dx[t][k] = sum_n da[t][n] W1[k][n] + da[t+d][n] W0[k][n]
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) {
-      const float (*A)[kAP] = ks < 4 ? s.da : s.da_f;
-      const float (*Wh)[kAP] = ks < 4 ? s.w1_h : s.w0_h;
-      const float (*Wl)[kAP] = ks < 4 ? s.w1_l : s.w0_l;
-      const int kc = (ks & 3) * 8;
-      const float a[4] = {A[r0 + g][kc + q], A[r0 + g + 8][kc + q], A[r0 + g][kc + q + 4], A[r0 + g + 8][kc + q + 4]};
-      float ah[4], al[4];
-      split4(a, ah, al);
-#pragma unroll
-      for (int nt = 0; nt < 2; nt++) {
-        const int k0 = nh * 16 + nt * 8;
-        mma_x3(acc[nt], ah, al, Wh[k0 + g][kc + q], Wh[k0 + g][kc + q + 4], Wl[k0 + g][kc + q], Wl[k0 + g][kc + q + 4]);
-      }
-    }
-    const int ta = t0 + r0 + g, tb = ta + 8;
-#pragma unroll
-    for (int nt = 0; nt < 2; nt++) {
-      const int n0 = nh * 16 + nt * 8 + 2 * q;
-      float2 va = make_float2(0.f, 0.f), vb = va;
-      if (ta < T) {
-        const size_t at = ((size_t)b * T + ta) * kR + n0;
-        const float2 gg = *reinterpret_cast<const float2*>(g_in + at);
-        va = make_float2(fmaf(gg.x, SRWN_SQRT_HALF, acc[nt][0]), fmaf(gg.y, SRWN_SQRT_HALF, acc[nt][1]));
-        *reinterpret_cast<float2*>(dx_out + at) = va;
-      }
-      if (tb < T) {
-        const size_t at = ((size_t)b * T + tb) * kR + n0;
-        const float2 gg = *reinterpret_cast<const float2*>(g_in + at);
-        vb = make_float2(fmaf(gg.x, SRWN_SQRT_HALF, acc[nt][2]), fmaf(gg.y, SRWN_SQRT_HALF, acc[nt][3]));
-        *reinterpret_cast<float2*>(dx_out + at) = vb;
-      }
-      if (P % kTT == 0) {                   // the tile lies inside one latent frame: sum its rows first
-        float sx = va.x + vb.x, sy = va.y + vb.y;
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
-        if (g == 0) { s.red[mt][n0] = sx; s.red[mt][n0 + 1] = sy; }
-      } else {
-        if (ta < T) { atomicAdd(dcond + ((size_t)b * frames + ta / P) * kR + n0, va.x); atomicAdd(dcond + ((size_t)b * frames + ta / P) * kR + n0 + 1, va.y); }
-        if (tb < T) { atomicAdd(dcond + ((size_t)b * frames + tb / P) * kR + n0, vb.x); atomicAdd(dcond + ((size_t)b * frames + tb / P) * kR + n0 + 1, vb.y); }
-      }
-    }
-    if (P % kTT == 0) {
-      __syncthreads();
-      if (warp == 0 && t0 < T)
-        atomicAdd(dcond + ((size_t)b * frames + t0 / P) * kR + lane, (s.red[0][lane] + s.red[1][lane]) + (s.red[2][lane] + s.red[3][lane]));
-    }
-    // stage 2: dWf[k][n] += sum_t A[t][k] da[t][n] with A = [tap | cur] (rows past T hold zeros in da)
-    {
-      const float (*X)[kAP] = mi < 2 ? s.a_tap : s.a_cur;
-      const int m0 = (mi & 1) * 16 + g;
-#pragma unroll
-      for (int ks = 0; ks < 8; ks++) {
-        const int tq = ks * 8 + q;
-        const float a[4] = {X[tq][m0], X[tq][m0 + 8], X[tq + 4][m0], X[tq + 4][m0 + 8]};
-        float ah[4], al[4];
-        split4(a, ah, al);
-#pragma unroll
-        for (int nt = 0; nt < 2; nt++) {
-          const int n0 = nj * 16 + nt * 8 + g;
-          mma_x3_raw(gw[nt], ah, al, s.da[tq][n0], s.da[tq + 4][n0]);
-        }
-      }
-    }
-    if (warp == 0) {
-#pragma unroll 8
-      for (int t = 0; t < kTT; t++) gb += s.da[t][lane];
-    }
-  }
-  float* pp = partial + (size_t)blockIdx.x * (2 * kR * kR + kR);
-#pragma unroll
-  for (int nt = 0; nt < 2; nt++) {
-    const int m0 = mi * 16 + g, n0 = nj * 16 + nt * 8 + 2 * q;
-    *reinterpret_cast<float2*>(pp + m0 * kR + n0) = make_float2(gw[nt][0], gw[nt][1]);
-    *reinterpret_cast<float2*>(pp + (m0 + 8) * kR + n0) = make_float2(gw[nt][2], gw[nt][3]);
-  }
-  if (warp == 0) pp[2 * kR * kR + lane] = gb;
-}
+// The per-layer kernels of the student's training pass (forward keeping activations, gate backward, conv backward) live in
+// train_tc.cu (tcgen05 kind::tf32); k_fwd_layer<true> above remains for the teacher's fp32-grade path, whose layers also
+// produce the skip output.
 
 // sums `rows` partial rows (row pitch `pitch`) of width w1 + w2 into dst1 [w1] and dst2 [w2] (+=) in a fixed order:
 // 32 columns per CTA, the rows split over the 8 warps (independent loads in flight), then a fixed-order sum of the 8 parts

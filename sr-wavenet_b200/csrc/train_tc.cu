@@ -119,7 +119,6 @@ __device__ __forceinline__ void grid_dependency_wait() {
 __device__ __forceinline__ void wait_or_trap(uint32_t bar, uint32_t parity, volatile int* abort_words) {
   if (!mbar_wait(bar, parity, abort_words, 1, 4000000000LL)) __trap();
 }
-
 struct Ctl {                 // barriers and bookkeeping at the end of dynamic shared memory
   uint64_t bar_main, bar_wgrad;          // tcgen05.commit: the GEMMs / the weight-gradient GEMM of a tile have retired
   uint64_t full_main, full_wgrad;        // workers -> issuer warps: the operands are in shared memory
@@ -385,8 +384,19 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         wait_or_trap(full_w, phase_w, ctl->abort_words); phase_w ^= 1;
         tc_fence_after();
+#ifdef SRWN_TUNING
+        const bool stamp = blockIdx.x == 0 && (tile - (int)blockIdx.x) / (int)gridDim.x == 3 && (threadIdx.x & 31) == 0;
+        if (stamp) g_tc_trace[1][12] = clock64();
+#endif
         issue_chain(tmem + 192, smem_u32(CT), kTC64, 2 * kTC64, smem_u32(GT), kTC64, 2 * kTC64, 16, kI64, acc);
         tc_commit_elect(bar_w);
+#ifdef SRWN_TUNING
+        if (stamp) g_tc_trace[1][13] = clock64();
+        if (blockIdx.x == 0 && (tile - (int)blockIdx.x) / (int)gridDim.x == 3) {      // how long the 16 instructions take to retire under load
+          wait_or_trap(bar_w, phase_w ^ 1, ctl->abort_words);
+          if (stamp) g_tc_trace[1][14] = clock64();
+        }
+#endif
         acc = 1;
       }
     }
