@@ -695,12 +695,28 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     TC_STAMP(2, n_done, 10);
     // x_l carries cond_l (model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l
     if (P % 8 == 0) {
-      const int ch = tid & 31, part = tid >> 5, tp = t0 + 8 * part;        // 16 parts of 8 rows, each inside one latent frame
-      if (tp < T) {
-        float s = 0.f;
+      // fixed summation order and ONE atomic per (latent frame, channel) and tile: with P = 128 the frame's sum is a single
+      // add onto zero, with P = 256 a commutative pair -- fp32 atomics from 16 parts in arrival order made this gradient
+      // irreproducible where the rows of dx cancel (4e-3 of the gradient's scale at 4x64000)
+      const int ch = tid & 31, part = tid >> 5;                             // 16 parts of 8 rows, each inside one latent frame
+      float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) s += red[(8 * part + i) * 33 + ch];
-        atomicAdd(dcond + ((size_t)b * frames + tp / P) * kR + ch, s);
+      for (int i = 0; i < 8; i++) s += red[(8 * part + i) * 33 + ch];
+      float* ps = reinterpret_cast<float*>(DA_lo);                          // free since the dx GEMM retired
+      ps[part * 32 + ch] = s;
+      worker_sync();
+      if (tid < 32) {
+        float acc = 0.f;
+        int cur = -1;
+        for (int q = 0; q < 16; q++) {
+          const int tp = t0 + 8 * q;
+          if (tp >= T) break;
+          const int f = tp / P;
+          if (f != cur && cur >= 0) { atomicAdd(dcond + ((size_t)b * frames + cur) * kR + ch, acc); acc = 0.f; }
+          cur = f;
+          acc += ps[q * 32 + ch];
+        }
+        if (cur >= 0) atomicAdd(dcond + ((size_t)b * frames + cur) * kR + ch, acc);
       }
     } else {
       for (int i = tid; i < kRows * kR; i += kWorkers) {

@@ -129,6 +129,9 @@ def test_distillation_gradient_is_additive_over_shards_4x64000(srwn):
     tl = (rng.normal(0, 1, size=(B, T, 4 * M)) * 0.5).astype(np.float32)
     loss, _, ent, g = s.loss_and_grads(z, truth, enc, teacher_logits=tl)
     g = g.clone()
+    # every reduction of the backward pass has a fixed order (the conditioning gradient included: one add per frame and tile)
+    _, _, _, g_again = s.loss_and_grads(z, truth, enc, teacher_logits=tl)
+    assert torch.equal(g, g_again), "distillation gradient is not reproducible run to run"
     parts, losses = [], []
     for sl in (slice(0, 2), slice(2, 4)):
         l_i, _, _, g_i = s.loss_and_grads(z[sl], truth[sl], enc[sl], teacher_logits=tl[sl], batch_norm=B)
