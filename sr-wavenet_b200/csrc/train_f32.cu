@@ -555,6 +555,9 @@ static TrainWs carve_train(const srwn_ctx* c, int B, int T, void* ws, size_t cap
   const size_t n = (size_t)B * T, L = c->cfg.n_layers, F = c->cfg.num_flows, frames = T / c->cfg.pool_stride;
   r.grid = 3 * (c->sm_count > 0 ? c->sm_count : 148);     // elementwise kernels of the step (heads, front)
   r.grid_tc = c->sm_count > 0 ? c->sm_count : 148;         // tensor-core layer kernels: one persistent CTA per SM (shared memory)
+#ifdef SRWN_TC_GRID
+  r.grid_tc = SRWN_TC_GRID;                                // tuning builds: few CTAs, so that small test shapes give every CTA several tiles
+#endif
   r.acts = w.take<float>(F * (L + 1) * n * kR);
   r.cond = w.take<float>((size_t)B * frames * L * kR);
   r.scales = w.take<float>(F * n);
@@ -586,6 +589,9 @@ static cudaError_t launch_dependent(void (*kern)(KArgs...), int grid, int block,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef SRWN_NO_PDL
+  cfg.numAttrs = 0;                        // tuning builds: plain stream order
+#endif
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 

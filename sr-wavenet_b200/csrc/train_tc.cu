@@ -332,10 +332,10 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
 // =====================================================================================================================
 // gate backward
 // =====================================================================================================================
-constexpr int kGateX = 2 * 16 * kCHS;                       // X_hi | X_lo; [c_hi ; c_lo]^T takes the region over once a is computed
+constexpr int kGateX = 2 * 16 * kCHS;                       // X_hi | X_lo
 constexpr int kGateG = 8 * kCHS;                            // one of G_hi / G_lo
-constexpr int kGateGT = 32 * kTC64;                         // [g_hi ; g_lo]^T
-constexpr int kGateSmem = kGateX + 2 * kGateG + kGateGT + 16 * kWCH + 8 * kWCH + 32 * 4 + (int)sizeof(Ctl);
+constexpr int kGateGT = 32 * kTC64;                         // [g_hi ; g_lo]^T, and the same for [c_hi ; c_lo]^T
+constexpr int kGateSmem = kGateX + 2 * kGateG + 2 * kGateGT + 16 * kWCH + 8 * kWCH + 32 * 4 + (int)sizeof(Ctl);
 int gate_smem_bytes() { return kGateSmem; }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -345,10 +345,13 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* X_hi = smem;
   unsigned char* X_lo = X_hi + 16 * kCHS;
-  unsigned char* CT = smem;                                 // 32 time chunks of 64 rows; the M = 128 instruction reads 1 KB past it (inside X)
   unsigned char* G_hi = smem + kGateX;
   unsigned char* G_lo = G_hi + kGateG;
-  unsigned char* GT = G_lo + kGateG;
+  // its own buffer, not the dead rows of X: the next tile's operand image is stored while the weight-gradient GEMM of this
+  // tile still reads c^T (aliasing X gave wrong dWr as soon as a CTA walked more than one tile).  32 time chunks of 64 rows;
+  // the M = 128 instruction reads 1 KB past the last chunk, into GT
+  unsigned char* CT = G_lo + kGateG;
+  unsigned char* GT = CT + kGateGT;
   unsigned char* WfB = GT + kGateGT;
   unsigned char* WrT = WfB + 16 * kWCH;
   float* s_bf = reinterpret_cast<float*>(WrT + 8 * kWCH);
@@ -696,8 +699,8 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     // x_l carries cond_l (model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l
     if (P % 8 == 0) {
       // fixed summation order and ONE atomic per (latent frame, channel) and tile: with P = 128 the frame's sum is a single
-      // add onto zero, with P = 256 a commutative pair -- fp32 atomics from 16 parts in arrival order made this gradient
-      // irreproducible where the rows of dx cancel (4e-3 of the gradient's scale at 4x64000)
+      // add onto zero, with P = 256 a commutative pair, so the gradient is reproducible bit for bit (16 atomics per frame in
+      // arrival order were not: 3e-7 of the conditioning biases' scale run to run)
       const int ch = tid & 31, part = tid >> 5;                             // 16 parts of 8 rows, each inside one latent frame
       float s = 0.f;
 #pragma unroll
@@ -705,7 +708,12 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       float* ps = reinterpret_cast<float*>(DA_lo);                          // free since the dx GEMM retired
       ps[part * 32 + ch] = s;
       worker_sync();
-      if (tid < 32) {
+      if (tid < 32 && P % kRows == 0) {                                      // the whole tile is one latent frame
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; q++) acc += ps[q * 32 + ch];
+        if (t0 < T) atomicAdd(dcond + ((size_t)b * frames + t0 / P) * kR + ch, acc);
+      } else if (tid < 32) {
         float acc = 0.f;
         int cur = -1;
         for (int q = 0; q < 16; q++) {
