@@ -680,44 +680,49 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     tc_fence_before();
     worker_sync();
     TC_STAMP(2, n_done, 8);
-    // coalesced: dx = g sqrt(1/2) + (da W1^T + da[t+d] W0^T), stored, and left in `red` for the conditioning gradient
+    // coalesced: dx = g sqrt(1/2) + (da W1^T + da[t+d] W0^T), stored; and the conditioning gradient (x_l carries cond_l,
+    // model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l.  Fixed summation order and ONE atomic per
+    // (latent frame, channel) and tile: with P = 128 the frame's sum is a single add onto zero, with P = 256 a commutative
+    // pair, so the gradient is reproducible bit for bit.  A warp holds rows 4 warp .. + 3 (+ 64): lanes of equal chunk are
+    // summed by shuffles, the 32 row groups of the tile by one warp in row order.
+    float* ps = reinterpret_cast<float*>(DA_lo);                            // [32 row groups][32 channels]; free since the dx GEMM retired
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int r = rA + 64 * i, tt = t0 + r;
       const float4 gvv = i == 0 ? g0 : g1;
-      float* rp = red + r * 33 + c4 * 4;
+      const float* rp = red + r * 33 + c4 * 4;
       float4 v = make_float4(0, 0, 0, 0);
       if (tt < T) {
         v = make_float4(fmaf(gvv.x, SRWN_SQRT_HALF, rp[0]), fmaf(gvv.y, SRWN_SQRT_HALF, rp[1]), fmaf(gvv.z, SRWN_SQRT_HALF, rp[2]), fmaf(gvv.w, SRWN_SQRT_HALF, rp[3]));
         *reinterpret_cast<float4*>(dx_out + ((size_t)b * T + tt) * kR + c4 * 4) = v;
       }
-      rp[0] = v.x; rp[1] = v.y; rp[2] = v.z; rp[3] = v.w;
+      if (P % 4 == 0) {
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+          v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+        }
+        if (lane < 8) *reinterpret_cast<float4*>(ps + (16 * i + warp) * 32 + 4 * lane) = v;
+      } else if (tt < T) {                                                   // a row group may straddle frames: per-element atomics
+        float* dp = dcond + ((size_t)b * frames + tt / P) * kR + c4 * 4;
+        atomicAdd(dp, v.x); atomicAdd(dp + 1, v.y); atomicAdd(dp + 2, v.z); atomicAdd(dp + 3, v.w);
+      }
     }
     TC_STAMP(2, n_done, 9);
     worker_sync();
     TC_STAMP(2, n_done, 10);
-    // x_l carries cond_l (model.py:183): dcond_l[b][frame] += sum over the frame's rows of dx_l
-    if (P % 8 == 0) {
-      // fixed summation order and ONE atomic per (latent frame, channel) and tile: with P = 128 the frame's sum is a single
-      // add onto zero, with P = 256 a commutative pair, so the gradient is reproducible bit for bit (16 atomics per frame in
-      // arrival order were not: 3e-7 of the conditioning biases' scale run to run)
-      const int ch = tid & 31, part = tid >> 5;                             // 16 parts of 8 rows, each inside one latent frame
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; i++) s += red[(8 * part + i) * 33 + ch];
-      float* ps = reinterpret_cast<float*>(DA_lo);                          // free since the dx GEMM retired
-      ps[part * 32 + ch] = s;
-      worker_sync();
-      if (tid < 32 && P % kRows == 0) {                                      // the whole tile is one latent frame
+    if (tid < 32 && P % 4 == 0) {
+      const int ch = tid;
+      if (P % kRows == 0) {                                                  // the whole tile is one latent frame
         float acc = 0.f;
 #pragma unroll
-        for (int q = 0; q < 16; q++) acc += ps[q * 32 + ch];
+        for (int q = 0; q < 32; q++) acc += ps[q * 32 + ch];
         if (t0 < T) atomicAdd(dcond + ((size_t)b * frames + t0 / P) * kR + ch, acc);
-      } else if (tid < 32) {
+      } else {
         float acc = 0.f;
         int cur = -1;
-        for (int q = 0; q < 16; q++) {
-          const int tp = t0 + 8 * q;
+        for (int q = 0; q < 32; q++) {
+          const int tp = t0 + 4 * q;                                         // row group q = rows 4 q .. 4 q + 3
           if (tp >= T) break;
           const int f = tp / P;
           if (f != cur && cur >= 0) { atomicAdd(dcond + ((size_t)b * frames + cur) * kR + ch, acc); acc = 0.f; }
@@ -725,11 +730,6 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
           acc += ps[q * 32 + ch];
         }
         if (cur >= 0) atomicAdd(dcond + ((size_t)b * frames + cur) * kR + ch, acc);
-      }
-    } else {
-      for (int i = tid; i < kRows * kR; i += kWorkers) {
-        const int tt = t0 + (i >> 5);
-        if (tt < T) atomicAdd(dcond + ((size_t)b * frames + tt / P) * kR + (i & 31), red[(i >> 5) * 33 + (i & 31)]);
       }
     }
     TC_STAMP(2, n_done, 11);
