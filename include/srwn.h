@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SRWN_ABI_VERSION 6
+#define SRWN_ABI_VERSION 7
 
 enum srwn_status {
   SRWN_OK = 0,
@@ -300,6 +300,14 @@ int srwn_right_shift(const float* x, float* y, int32_t B, int32_t T, int32_t C,
 /* ResizeEmbeddingNearestNeighbor (ops.py:64-74): x [B,L,C] -> y [B,out_size,C]. */
 int srwn_resize_nearest(const float* x, float* y, int32_t B, int32_t L, int32_t C,
                         int32_t out_size, void* stream);
+/* Pieces of the classification / embedding heads WaveNet (model.py:8-72) and SiameseWaveNet (model.py:660-798), which
+ * reuse the residual block: in-place relu (model.py:48,51), tf.nn.pool(AVG, VALID) over `window` time steps
+ * (model.py:55, 711: x [B,T,C] -> y [B,T-window+1,C]), softmax over the channels (model.py:57) and the Euclidean
+ * distance of two embeddings sqrt(1e-8 + sum (a-b)^2) (model.py:735: a, b [B,D] -> d [B]). */
+int srwn_relu(float* x, int64_t n, void* stream);
+int srwn_avg_pool_time(const float* x, float* y, int32_t B, int32_t T, int32_t C, int32_t window, void* stream);
+int srwn_softmax(const float* x, float* y, int64_t rows, int32_t C, void* stream);
+int srwn_pair_distance(const float* a, const float* b, float* d, int32_t B, int32_t D, void* stream);
 /* discretized_mix_logistic_loss (ops.py:124-175): x [B,T], l [B,T,4M];
  * nll_out [B,T] and/or nll_sum [1] (either may be NULL). */
 int srwn_mol_loss(const float* x, const float* l, float* nll_out, float* nll_sum,

@@ -7,5 +7,6 @@ works through the alias module at the repo root.
 from . import _lib, synth, shard  # noqa: F401
 from . import ops, model   # noqa: F401
 from .model import WaveNetAutoEncoder, ParallelWaveNet  # noqa: F401
+from .heads import WaveNet, SiameseWaveNet  # noqa: F401
 
-__all__ = ["ops", "model", "synth", "WaveNetAutoEncoder", "ParallelWaveNet"]
+__all__ = ["ops", "model", "synth", "WaveNetAutoEncoder", "ParallelWaveNet", "WaveNet", "SiameseWaveNet"]

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRWN_LIB") or os.path.join(_HERE, "libsrwn.so")   # SRWN_LIB: tuning builds (tools/exp_build.sh)
 
-ABI_VERSION = 6      # SRWN_ABI_VERSION in include/srwn.h
+ABI_VERSION = 7      # SRWN_ABI_VERSION in include/srwn.h
 OK, ERR_INVALID, ERR_CUDA, ERR_WEIGHTS, ERR_UNSUPPORTED, ERR_WORKSPACE = range(6)
 TEACHER, STUDENT = 0, 1
 FP32, BF16, FP16 = 0, 1, 2
@@ -97,6 +97,10 @@ SIGNATURES = {
     "srwn_residual_dilation_layer": (ctypes.c_int, [_fp] * 9 + [_i32] * 6 + [_vp]),
     "srwn_right_shift": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),
     "srwn_resize_nearest": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),
+    "srwn_relu": (ctypes.c_int, [_fp, _i64, _vp]),
+    "srwn_avg_pool_time": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),
+    "srwn_softmax": (ctypes.c_int, [_fp, _fp, _i64, _i32, _vp]),
+    "srwn_pair_distance": (ctypes.c_int, [_fp, _fp, _fp, _i32, _i32, _vp]),
     "srwn_mol_loss": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _vp]),
     "srwn_mol_sample": (ctypes.c_int, [_fp, _fp, _fp, _fp, _vp, _i32, _i32, _i32, _vp]),
 }

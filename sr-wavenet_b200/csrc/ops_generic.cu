@@ -141,6 +141,79 @@ extern "C" int srwn_resize_nearest(const float* x, float* y, int32_t B, int32_t 
   return SRWN_OK;
 }
 
+// ---- pieces of the classification / embedding heads (model.py:33-57, 692-713): relu, average pooling over a window of time
+// steps (tf.nn.pool AVG, VALID), softmax over the channels, Euclidean distance of two embeddings (model.py:735)
+__global__ void k_relu(float* __restrict__ x, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = fmaxf(x[i], 0.f);
+}
+extern "C" int srwn_relu(float* x, int64_t n, void* stream) {
+  if (!x || n < 0) return srwn_fail(SRWN_ERR_INVALID, "srwn_relu: bad argument");
+  if (n == 0) return SRWN_OK;
+  k_relu<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+// y[b][o][c] = mean over w < window of x[b][o + w][c]; one CTA per (o, b), the threads split the window, fixed-order sum
+__global__ void __launch_bounds__(256) k_avg_pool_time(const float* __restrict__ x, float* __restrict__ y, int T, int C, int window, int out) {
+  extern __shared__ double s_part[];                 // [parts][C]
+  const int o = blockIdx.x, b = blockIdx.y, parts = blockDim.x / C > 0 ? blockDim.x / C : 1;
+  const int c = threadIdx.x % C, part = threadIdx.x / C;
+  if (part < parts && threadIdx.x < parts * C) {
+    double acc = 0.0;
+    for (int w = part; w < window; w += parts) acc += (double)x[((size_t)b * T + o + w) * C + c];
+    s_part[part * C + c] = acc;
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+    double t = 0.0;
+    for (int k = 0; k < parts; k++) t += s_part[k * C + cc];
+    y[((size_t)b * out + o) * C + cc] = (float)(t / window);
+  }
+}
+extern "C" int srwn_avg_pool_time(const float* x, float* y, int32_t B, int32_t T, int32_t C, int32_t window, void* stream) {
+  if (!x || !y) return srwn_fail(SRWN_ERR_INVALID, "srwn_avg_pool_time: null argument");
+  if (B < 1 || T < 1 || C < 1 || C > 256 || window < 1 || window > T || B > 65535)
+    return srwn_fail(SRWN_ERR_INVALID, "srwn_avg_pool_time: needs 1 <= window <= T, 1 <= C <= 256");
+  const int out = T - window + 1, parts = 256 / C > 0 ? 256 / C : 1;
+  k_avg_pool_time<<<dim3(out, B), 256, (size_t)parts * C * sizeof(double), (cudaStream_t)stream>>>(x, y, T, C, window, out);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+__global__ void k_softmax_rows(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int C) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* xr = x + r * C;
+  float m = xr[0];
+  for (int c = 1; c < C; c++) m = fmaxf(m, xr[c]);
+  float sum = 0.f;
+  for (int c = 0; c < C; c++) sum += expf(xr[c] - m);
+  for (int c = 0; c < C; c++) y[r * C + c] = expf(xr[c] - m) / sum;
+}
+extern "C" int srwn_softmax(const float* x, float* y, int64_t rows, int32_t C, void* stream) {
+  if (!x || !y || rows < 1 || C < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_softmax: bad argument");
+  k_softmax_rows<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, y, rows, C);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+// d[b] = sqrt(1e-8 + sum_k (a[b][k] - c[b][k])^2)   (model.py:735, the 1e-8 keeps the gradient finite)
+__global__ void k_pair_distance(const float* __restrict__ a, const float* __restrict__ c, float* __restrict__ d, int B, int D) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int k = 0; k < D; k++) { const float t = a[(size_t)b * D + k] - c[(size_t)b * D + k]; s = fmaf(t, t, s); }
+  d[b] = sqrtf(1e-8f + s);
+}
+extern "C" int srwn_pair_distance(const float* a, const float* b, float* d, int32_t B, int32_t D, void* stream) {
+  if (!a || !b || !d || B < 1 || D < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_pair_distance: bad argument");
+  k_pair_distance<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, b, d, B, D);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
 extern "C" int srwn_mol_loss(const float* x, const float* l, float* nll_out, float* nll_sum, int32_t B,
                              int32_t T, int32_t M, void* stream) {
   if (!x || !l || (!nll_out && !nll_sum)) return srwn_fail(SRWN_ERR_INVALID, "srwn_mol_loss: null argument");

@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), "libsrwn.so does not export %s" % n
         assert n in _lib.SIGNATURES, "ctypes binding misses %s" % n
-    assert lib.srwn_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.srwn_abi_version() == _lib.ABI_VERSION == 7
 
 
 def test_binding_has_no_undeclared_symbols(lib):
