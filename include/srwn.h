@@ -110,6 +110,9 @@ int srwn_commit_weights(srwn_handle_t h, void* stream);
  * aborted (a bounded on-device pipeline wait expired; outputs are then invalid). */
 int srwn_check_async_error(srwn_handle_t h, int32_t op, int32_t B, int32_t T, int32_t precision,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* The abort words only (pinned host memory), without synchronising any stream: for callers that keep several launches in
+ * flight and have already waited on an event for the launch they ask about.  Does not clear the error. */
+int srwn_peek_async_error(srwn_handle_t h);
 /* Synchronises `stream` and reports (then clears) the abort words of the fused-kernel calls issued on this handle so far
  * (a bounded on-device pipeline wait expired; the outputs of that call are invalid).  The words live in pinned host
  * memory: once a launch has aborted, every later call on the handle is refused with SRWN_ERR_CUDA until this function

@@ -57,6 +57,7 @@ SIGNATURES = {
     "srwn_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32),
                                            ctypes.POINTER(ctypes.c_char_p)]),
     "srwn_check_async_error": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "srwn_peek_async_error": (ctypes.c_int, [_vp]),
     "srwn_supports": (ctypes.c_int, [_vp, _i32, _i32]),
     "srwn_workspace_bytes": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, ctypes.POINTER(_sz)]),
     "srwn_teacher_logits": (ctypes.c_int, [_vp, _fp, _fp, _fp, _i32, _i32, _i32, _vp, _sz, _vp]),

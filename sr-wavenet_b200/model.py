@@ -463,6 +463,87 @@ class WaveNetAutoEncoder(_CheckpointMixin):
                                             None, None, B, T, prec, ws, wsn, _stream()))
         return self._finish(out, on_dev, _lib.OP_TEACHER_NLL, B, T, prec)
 
+    def nll_stream(self, batches, precision=None, depth=2):
+        """Scores a sequence of host batches: ``batches`` yields ``(inputs [B,T], encoding [B,T/P,C])`` (NumPy arrays or CPU
+        tensors, pinned or not); yields one float per batch, in order -- the value ``nll(inputs, encoding)`` returns.
+        Throughput path of a scoring service: the upload of batch i+1 runs on a copy stream while batch i is scored, and the
+        4-byte result of batch i is read back while batch i+1 runs, so a step costs max(copy, kernel) instead of their sum.
+        ``depth`` device-side input slots (>= 2)."""
+        eng = self._eng
+        prec = self._prec(precision)
+        depth = max(2, int(depth))
+        compute = torch.cuda.current_stream()
+        copy = getattr(self, "_copy_stream", None) or torch.cuda.Stream()
+        self._copy_stream = copy
+        slots = [dict(x=None, e=None, px=None, pe=None, up=torch.cuda.Event(), used=torch.cuda.Event(), done=torch.cuda.Event(),
+                      out=torch.empty(1, dtype=torch.float32, device="cuda"), host=torch.empty(1, dtype=torch.float32, pin_memory=True))
+                 for _ in range(depth)]
+
+        def host32(a):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+            return t.float().contiguous()
+
+        def upload(slot, batch):
+            x, e = host32(batch[0]), host32(_with_conditions(batch[1], None, self.condition_size))
+            if slot["x"] is None or slot["x"].shape != x.shape or slot["e"].shape != e.shape:
+                slot["x"] = torch.empty(x.shape, dtype=torch.float32, device="cuda")
+                slot["e"] = torch.empty(e.shape, dtype=torch.float32, device="cuda")
+                slot["px"] = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+                slot["pe"] = torch.empty(e.shape, dtype=torch.float32, pin_memory=True)
+            slot["used"].synchronize() if slot.get("busy") else None      # the kernel that read this slot last has finished
+            src_x, src_e = x, e
+            if not x.is_pinned():
+                slot["px"].copy_(x); src_x = slot["px"]
+            if not e.is_pinned():
+                slot["pe"].copy_(e); src_e = slot["pe"]
+            with torch.cuda.stream(copy):
+                slot["x"].copy_(src_x, non_blocking=True)
+                slot["e"].copy_(src_e, non_blocking=True)
+                slot["up"].record(copy)
+
+        def launch(slot):
+            B, T = slot["x"].shape
+            self._check(slot["e"], B, T)
+            ws, wsn = eng.workspace(_lib.OP_TEACHER_NLL, B, T, prec)
+            compute.wait_event(slot["up"])
+            _lib.check(eng.lib.srwn_teacher_nll(eng.h, slot["x"].data_ptr(), slot["e"].data_ptr(), slot["x"].data_ptr(), None,
+                                                slot["out"].data_ptr(), None, B, T, prec, ws, wsn, compute.cuda_stream))
+            slot["used"].record(compute)
+            slot["host"].copy_(slot["out"], non_blocking=True)
+            slot["done"].record(compute)
+            slot["busy"], slot["shape"] = True, (B, T)
+
+        def collect(slot):
+            slot["done"].synchronize()
+            if prec != _lib.FP32:                      # abort words of that launch, without draining the launches behind it
+                _lib.check(eng.lib.srwn_peek_async_error(eng.h))
+            return float(slot["host"][0])
+
+        it = iter(batches)
+        pending = []                                  # slots launched, oldest first
+        i = 0
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        upload(slots[0], first)
+        nxt = 0
+        while nxt is not None:
+            cur = slots[nxt]
+            launch(cur)
+            pending.append(cur)
+            i += 1
+            try:
+                batch = next(it)
+                if len(pending) == depth:             # every slot is in flight: hand the oldest result out before reusing its slot
+                    yield collect(pending.pop(0))
+                nxt = i % depth
+                upload(slots[nxt], batch)
+            except StopIteration:
+                nxt = None
+        for slot in pending:
+            yield collect(slot)
+
     def reconstruct_with_encoding(self, inputs, encoding, conditions=None, u1=None, u2=None,
                                   precision=None):
         """model.py:264-270 -> [B,T]: one teacher-forced pass + parallel sampling from the logits

@@ -378,3 +378,24 @@ def test_device_resident_path(srwn):
     b = t.get_logits(torch.from_numpy(x).cuda(), torch.from_numpy(enc).cuda())
     assert isinstance(b, torch.Tensor) and b.is_cuda
     np.testing.assert_array_equal(b.cpu().numpy(), a)
+
+
+def test_nll_stream_matches_nll_batch_by_batch(srwn):
+    """The pipelined scoring call (uploads on a copy stream, results read back one batch late) returns, in order, exactly
+    what the synchronous call returns for each batch -- pinned and pageable inputs, batches of different content, 1 and 5
+    batches, empty sequence."""
+    dil, T = [1, 2, 4, 8, 16, 32], 1024
+    t = srwn.WaveNetAutoEncoder(input_size=T, condition_size=0, num_mixtures=5, dilations=dil, skip_channels=128,
+                                latent_channels=32, pool_stride=128)
+    t.set_weights(synth.make_teacher_weights(dil))
+    batches = []
+    for k in range(5):
+        x, e = synth.synthetic_audio(3, T, seed=50 + k), synth.synthetic_encoding(3, T // 128, seed=70 + k)
+        batches.append((torch.from_numpy(x).pin_memory(), torch.from_numpy(e).pin_memory()) if k % 2 else (x, e))
+    for prec in ("fp32", "fp16"):
+        ref = [t.nll(np.asarray(x), np.asarray(e), precision=prec) for x, e in batches]
+        got = list(t.nll_stream(iter(batches), precision=prec))
+        assert got == ref, (prec, got, ref)
+        assert list(t.nll_stream(batches[:1], precision=prec)) == ref[:1]
+        assert list(t.nll_stream([], precision=prec)) == []
+        assert list(t.nll_stream(batches, precision=prec, depth=3)) == ref
