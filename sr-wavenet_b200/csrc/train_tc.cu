@@ -12,8 +12,9 @@
 // and a product is hi*hi + hi*lo + lo*hi.  The two terms that share the A operand come out of ONE instruction by stacking
 // [W_hi ; W_lo] along N (N = 64), so a GEMM costs two instruction chains instead of three:
 //     D[:, 0:32] = A_hi W_hi    D[:, 32:64] = A_hi W_lo    D[:, 64:96] = A_lo W_hi      (summed by the epilogue)
-// The chains are issued by different warps (an instruction costs its issuing thread ~60-120 clk, the pipe ~47-57 clk:
-// tools/umma_tf32_probe.cu) into separate accumulator columns, because instructions of different threads are not ordered.
+// The two chains write separate accumulator columns (the first instruction of each overwrites), so they need no order
+// between them; the pipe takes ~47 (N = 32) / ~57 (N = 64) clocks per instruction (tools/umma_tf32_probe.cu) -- the time to
+// read its 5-6 KB of operands from shared memory, which is what bounds these kernels.
 // Weight gradients contract over TIME: both operands are needed transposed, [channel][time].  MN-major TF32 operands only
 // exist for the 128B_BASE32B swizzle (the probe's no-swizzle MN-major descriptors return zeros), so the threads write
 // transposed copies themselves: thread = row, the 32 lanes of a warp hit 32 different banks with a chunk stride of
@@ -55,10 +56,6 @@ constexpr uint32_t kTmemCols = 256;
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   // cute::UMMA::InstrDescriptor: c = F32 (bit 4), a / b format TF32 = 2 (bits 7, 10), K-major, N >> 3 at 17, M >> 4 at 24
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 // issued by a whole (converged) warp: the instruction itself is predicated on the elected lane, so the descriptors stay in
 // uniform registers and the compiler emits no per-thread election loop around it
