@@ -407,23 +407,28 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
 #pragma unroll
   for (int i = 0; i < 8; i++) gsum[i] = 0.f;
   float4 xc[2], xt[2], gg[2];
-  auto load_tile = [&](int tile) {
+  // the next tile's rows are fetched in two portions at different points of the tile: all SMs run in step, one burst of every
+  // load saturates HBM for ~2000 clocks and the LSU queue stalls the issuing warps for that long
+  auto load_tile = [&](int tile, int part) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     const float* xb = x_l + (size_t)b * T * kR;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int t = t0 + rA + 64 * i;
-      xc[i] = make_float4(0, 0, 0, 0); xt[i] = xc[i]; gg[i] = xc[i];
-      if (t < T) {
-        xc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
-        gg[i] = ldg4(g_in + ((size_t)b * T + t) * kR + c4 * 4);
-        if (t - d >= 0) xt[i] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
+      if (part == 0) {
+        xc[i] = make_float4(0, 0, 0, 0); xt[i] = xc[i];
+        if (t < T) {
+          xc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
+          if (t - d >= 0) xt[i] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
+        }
+      } else {
+        gg[i] = t < T ? ldg4(g_in + ((size_t)b * T + t) * kR + c4 * 4) : make_float4(0, 0, 0, 0);
       }
     }
   };
   grid_dependency_wait();
   int n_done = 0;
-  if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
+  if ((int)blockIdx.x < n_tiles) { load_tile(blockIdx.x, 0); load_tile(blockIdx.x, 1); }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n_done++) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     TC_STAMP(1, n_done, 0);
@@ -440,7 +445,8 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
     worker_sync();
     if (tid == 0) mbar_arrive(full);
     TC_STAMP(1, n_done, 2);
-    if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);        // next tile's rows, in flight during the GEMMs
+    const bool more = tile + (int)gridDim.x < n_tiles;
+    if (more) load_tile(tile + gridDim.x, 0);                                // next tile's x rows, in flight during the GEMMs
     // transposed copy of dres (this thread's row) for the weight gradient, while the GEMMs run
     if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWr has read CT / GT
     TC_STAMP(1, n_done, 3);
@@ -459,6 +465,7 @@ k_bwd_gate_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, flo
         }
       }
     }
+    if (more) load_tile(tile + gridDim.x, 1);                                // and its g rows (this tile's are consumed)
     TC_STAMP(1, n_done, 4);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     TC_STAMP(1, n_done, 5);
@@ -594,26 +601,34 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
 #pragma unroll
   for (int i = 0; i < 8; i++) dsum[i] = 0.f;
   float4 xc[2], xt[2], dac[2], daf[2], gq[2];
-  auto load_tile = [&](int tile) {
+  // the next tile's rows are fetched in three portions at different points of the tile (see k_bwd_gate_tc)
+  auto load_tile = [&](int tile, int part) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     const float* xb = x_l + (size_t)b * T * kR;
     const float* db = da_in + (size_t)b * T * kR;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int t = t0 + rA + 64 * i;
-      xc[i] = make_float4(0, 0, 0, 0); xt[i] = xc[i]; dac[i] = xc[i]; daf[i] = xc[i]; gq[i] = xc[i];
-      if (t < T) {
-        xc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
-        dac[i] = ldg4(db + (size_t)t * kR + c4 * 4);
-        gq[i] = ldg4(g_in + ((size_t)b * T + t) * kR + c4 * 4);
-        if (t - d >= 0) xt[i] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
-        if (t + d < T) daf[i] = ldg4(db + (size_t)(t + d) * kR + c4 * 4);
+      if (part == 0) {
+        xc[i] = make_float4(0, 0, 0, 0); xt[i] = xc[i];
+        if (t < T) {
+          xc[i] = ldg4(xb + (size_t)t * kR + c4 * 4);
+          if (t - d >= 0) xt[i] = ldg4(xb + (size_t)(t - d) * kR + c4 * 4);
+        }
+      } else if (part == 1) {
+        dac[i] = make_float4(0, 0, 0, 0); daf[i] = dac[i];
+        if (t < T) {
+          dac[i] = ldg4(db + (size_t)t * kR + c4 * 4);
+          if (t + d < T) daf[i] = ldg4(db + (size_t)(t + d) * kR + c4 * 4);
+        }
+      } else {
+        gq[i] = t < T ? ldg4(g_in + ((size_t)b * T + t) * kR + c4 * 4) : make_float4(0, 0, 0, 0);
       }
     }
   };
   grid_dependency_wait();
   int n_done = 0;
-  if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x);
+  if ((int)blockIdx.x < n_tiles) { load_tile(blockIdx.x, 0); load_tile(blockIdx.x, 1); load_tile(blockIdx.x, 2); }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, n_done++) {
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRows;
     TC_STAMP(2, n_done, 0);
@@ -631,7 +646,8 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     worker_sync();
     if (tid == 0) mbar_arrive(full);
     TC_STAMP(2, n_done, 2);
-    if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x);
+    const bool more = tile + (int)gridDim.x < n_tiles;
+    if (more) load_tile(tile + gridDim.x, 0);
     // transposed copies (this thread's row) for the weight gradient, while the dx GEMMs run
     if (n_done > 0) { wait_or_trap(bar_w, phase_w, ctl->abort_words); phase_w ^= 1; }      // the previous tile's dWf has read DAT / XT
     TC_STAMP(2, n_done, 3);
@@ -662,6 +678,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     fence_async_smem();
     worker_sync();                                           // XR is free from here on: it becomes `red`
     if (tid == 0) mbar_arrive(full_w);
+    if (more) load_tile(tile + gridDim.x, 1);
     TC_STAMP(2, n_done, 5);
     wait_or_trap(bar, phase, ctl->abort_words); phase ^= 1;
     TC_STAMP(2, n_done, 6);
@@ -675,6 +692,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     }
     TC_STAMP(2, n_done, 7);
     tc_fence_before();
+    if (more) load_tile(tile + gridDim.x, 2);
     worker_sync();
     TC_STAMP(2, n_done, 8);
     // coalesced: dx = g sqrt(1/2) + (da W1^T + da[t+d] W0^T), stored; and the conditioning gradient (x_l carries cond_l,
