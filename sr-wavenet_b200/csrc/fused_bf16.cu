@@ -494,6 +494,11 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
         const uint32_t wb_lo0 = (sbase + SmemMap::wst) >> 4;
         const uint32_t ab_lo = ((sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes) >> 4) + ((uint32_t)kTile << 16);
         const uint32_t d_conv = tmem + m * 160, d_skip = tmem + m * 160 + 32;
+#ifndef SRWN_STUDENT_TMEM_A
+#define SRWN_STUDENT_TMEM_A 1
+#endif
+        constexpr bool kTmemA = !TEACHER && SRWN_STUDENT_TMEM_A;       // teacher: the 128 skip columns leave no room
+        const uint32_t d_cop = d_skip; (void)d_cop;
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
         {
@@ -588,9 +593,17 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
 #endif
             }
           }
-          store_row_packed(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, w16);
-          tc_fence_before();
-          LOOP_FENCE();
+          if constexpr (kTmemA) {
+            // the gate output as the A operand of the residual GEMM in tensor memory (student: the skip columns of the tile
+            // are free): no shared-memory store, no proxy fence, and the MMA reads no A tile from shared memory
+            tc_st16(d_cop + lane_addr, w16);
+            tc_wait_st();
+            tc_fence_before();
+          } else {
+            store_row_packed(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, w16);
+            tc_fence_before();
+            LOOP_FENCE();
+          }
           TRACE(m, l, 5);
           next_ok = group_sync_and(m, next_ok);         // true: every polling warp saw both conditions
           TRACE(m, l, 6);
@@ -613,8 +626,13 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
               tc_commit(bar(BAR_D2 + m));
 #else
               // residual first (it is what the layer chain waits for); the skip sum accumulates in TMEM behind it
-              tc_mma<0>(d_conv, desc_from_lo(ab_lo), desc_from_lo(b2_lo), id32);
-              tc_mma<1>(d_conv, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows), id32);
+              if constexpr (kTmemA) {
+                tc_mma_ts<0>(d_conv, d_cop, desc_from_lo(b2_lo), id32);
+                tc_mma_ts<1>(d_conv, d_cop + 8, desc_from_lo(b2_lo + 2 * wrs_rows), id32);
+              } else {
+                tc_mma<0>(d_conv, desc_from_lo(ab_lo), desc_from_lo(b2_lo), id32);
+                tc_mma<1>(d_conv, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows), id32);
+              }
               tc_commit(bar(BAR_D2 + m));
               if (TEACHER && !warm && !(SRWN_EXP & 8)) {
                 tc_mma_dyn(d_skip, desc_from_lo(ab_lo), desc_from_lo(b2_lo + 32), id128, l > 0 ? 1u : 0u);
