@@ -63,6 +63,17 @@ __device__ __forceinline__ void mma_tf32_elect(uint32_t d_tmem, uint64_t a, uint
   asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// the same with the A operand in tensor memory (row = lane, one TF32 element per column: K = 8 is 8 columns)
+__device__ __forceinline__ void mma_tf32_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
                "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
@@ -160,6 +171,14 @@ __device__ __forceinline__ void issue_chain(uint32_t d_tmem, uint32_t a_addr, ui
   for (int k = 0; k < nk; k++) mma_tf32_elect(d_tmem, da + k * as, db + k * bs, idesc, k > 0 ? 1u : acc_first);
 }
 
+// a chain whose A operand lives in tensor memory: K step k reads columns a_tmem + 8 k .. + 7
+__device__ __forceinline__ void issue_chain_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t b_lbo, uint32_t b_adv,
+                                               int nk, uint32_t idesc, uint32_t acc_first) {
+  const uint64_t db = make_desc(b_addr, b_lbo, 128), bs = (uint64_t)(b_adv >> 4);
+#pragma unroll 4
+  for (int k = 0; k < nk; k++) mma_tf32_ts_elect(d_tmem, a_tmem + 8 * k, db + k * bs, idesc, k > 0 ? 1u : acc_first);
+}
+
 // weight operand with the hi part in rows 0..31 and the lo part in rows 32..63: value(n, k) for n, k < 32 / K
 template <int K, typename F>
 __device__ __forceinline__ void stage_weight(unsigned char* dst, F value) {
@@ -222,8 +241,9 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
         tc_commit_elect(bar);
         wait_or_trap(full, phase, ctl->abort_words); phase ^= 1;
         tc_fence_after();
-        issue_chain(tmem + 128, smem_u32(X_hi), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI64, 0);
-        issue_chain(tmem + 192, smem_u32(X_lo), kCHS, 2 * kCHS, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI32, 0);
+        // residual 1x1: c = (c_hi, c_lo) is the A operand, written to tensor memory by the row threads (columns 96.., 224..)
+        issue_chain_ts(tmem + 128, tmem + 96, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI64, 0);
+        issue_chain_ts(tmem + 192, tmem + 224, smem_u32(WrB), kWCH, 2 * kWCH, 4, kI32, 0);
         tc_commit_elect(bar);
       }
     }
@@ -271,21 +291,19 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
       float a0[8], a1[8], a2[8];
       tc_ld8(lane_base + cb, a0); tc_ld8(lane_base + 32 + cb, a1); tc_ld8(lane_base + 64 + cb, a2);
       tc_wait_ld();
+      // gate: tanh, sigmoid OF THE TANH, product (ops.py:28,33,36); c goes to tensor memory as the A operand of the residual
+      // GEMM (no shared-memory image, no proxy fence, and the GEMM reads no A tile from shared memory)
+      float ch[8], cl[8];
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
-        float4 c;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int i = 4 * j + e;
-          const float f = tanh_ex2((a2[i] + a1[i]) + a0[i] + s_bf[cb + i]);     // gate: tanh, sigmoid OF THE TANH, product (ops.py:28,33,36)
-          f4at(c, e) = f * sigmoid_fast(f);
-        }
-        const int chunk = (cb >> 2) + j;                                         // c takes over the tap rows (dead after the filter conv)
-        split_store4(X_hi + chunk * kCHS + row * 16, X_lo + chunk * kCHS + row * 16, c);
+      for (int i = 0; i < 8; i++) {
+        const float f = tanh_ex2((a2[i] + a1[i]) + a0[i] + s_bf[cb + i]);
+        split_tf32(f * sigmoid_fast(f), ch[i], cl[i]);
       }
+      tc_st8(lane_base + 96 + cb, ch);
+      tc_st8(lane_base + 224 + cb, cl);
+      tc_wait_st();
     }
     tc_fence_before();
-    fence_async_smem();
     worker_sync();
     if (tid == 0) mbar_arrive(full);
     // x_l[t] back from its operand image: hi + lo is x exactly
@@ -311,7 +329,7 @@ k_fwd_layer_tc(const float* __restrict__ x_l, float* __restrict__ x_next, const 
           const float res = (r2[i] + r1[i]) + r0[i] + s_br[cb + i];             // residual 1x1 (ops.py:39)
           f4at(v, e) = (f4at(xv[j], e) + res) * SRWN_SQRT_HALF + f4at(cn[j], e);     // ops.py:40, next layer's conditioning (model.py:183)
         }
-        *reinterpret_cast<float4*>(X_hi + ((cb >> 2) + j) * kCHS + row * 16) = v;     // staged in the (dead) c rows for a coalesced store
+        *reinterpret_cast<float4*>(X_hi + ((cb >> 2) + j) * kCHS + row * 16) = v;     // staged in the (dead) tap rows for a coalesced store
       }
     }
     tc_fence_before();
