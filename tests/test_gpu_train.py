@@ -135,8 +135,8 @@ def test_distill_loss_glue(srwn):
 def test_gradients_match_oracle(srwn, cfg):
     if cfg == "small":
         dil, F, C, P, M, B, T = [1, 2, 4, 3], 2, 8, 64, 3, 3, 832     # ragged: T not a multiple of the 128-row tile
-    elif cfg == "many_tiles":                                         # 300 tiles: every CTA walks two or three (accumulators,
-        dil, F, C, P, M, B, T = [1, 2, 16, 512, 4], 1, 4, 512, 3, 2, 19200     # buffers and barriers live across tiles), 4 tiles per frame
+    elif cfg == "many_tiles":                                         # 304 tiles: every CTA walks two or three (accumulators,
+        dil, F, C, P, M, B, T = [1, 2, 16, 512, 4], 1, 4, 512, 3, 2, 19456     # buffers and barriers live across tiles), 4 tiles per frame
     elif cfg == "odd_stride":                                         # frames that straddle row groups: the per-element path of dcond
         dil, F, C, P, M, B, T = [1, 3], 1, 3, 6, 3, 1, 1026
     else:
