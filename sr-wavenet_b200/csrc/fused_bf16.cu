@@ -120,6 +120,7 @@ enum Bar {
   BAR_G1 = 18,     // [2] MMA -> loader/tile groups: all filter-conv MMAs of the layer retired (3 commits)
   BAR_HDD = 20,    // [3] MMA -> tile group: head accumulator ready
   BAR_TAIL = 23,   // loader -> tile groups: a pruned warm-up chunk may write the ring behind its last layer
+  BAR_C2 = 24,     // [3] MMA -> tile groups: the residual and skip MMAs of a tile-layer retired, its TMEM operand region is free
 };
 
 using namespace umma;
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
   if (tid == 0) {
     for (int i = 0; i < 3; i++) {
       mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_D2 + i), 1); mbar_init(bar(BAR_HDD + i), 1);
+      mbar_init(bar(BAR_C2 + i), 1);
       mbar_init(bar(BAR_HD + 2 * i), kTile); mbar_init(bar(BAR_HD + 2 * i + 1), kTile);
     }
     for (int i = 0; i < 2; i++) {
@@ -497,8 +499,17 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
 #ifndef SRWN_STUDENT_TMEM_A
 #define SRWN_STUDENT_TMEM_A 1
 #endif
-        constexpr bool kTmemA = !TEACHER && SRWN_STUDENT_TMEM_A;       // teacher: the 128 skip columns leave no room
-        const uint32_t d_cop = d_skip; (void)d_cop;
+#ifndef SRWN_TEACHER_TMEM_A
+#define SRWN_TEACHER_TMEM_A 1
+#endif
+        // The gate output as a TMEM operand of the residual (and skip) GEMM.  Student: the tile's unused skip columns.
+        // Teacher: 3 x 160 columns leave 32, i.e. TWO 16-column operand regions for three tiles; a region is live from the gate
+        // epilogue until the tile's residual + skip MMAs retire (a few hundred clocks of the ~3000 a layer takes), and the
+        // tiles run ~1000 clocks apart, so use g = 3 * (layers done) + m takes region g & 1 after waiting (almost never) for
+        // use g - 2 to retire (BAR_C2 of tile (m + 1) % 3).
+        constexpr bool kTmemAT = TEACHER && SRWN_TEACHER_TMEM_A;
+        constexpr bool kTmemA = (!TEACHER && SRWN_STUDENT_TMEM_A) || kTmemAT;
+        uint32_t d_cop = d_skip;
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
         {
@@ -594,8 +605,14 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             }
           }
           if constexpr (kTmemA) {
-            // the gate output as the A operand of the residual GEMM in tensor memory (student: the skip columns of the tile
-            // are free): no shared-memory store, no proxy fence, and the MMA reads no A tile from shared memory
+            // the gate output as the A operand of the residual GEMM in tensor memory: no shared-memory store, no proxy fence,
+            // and the MMA reads no A tile from shared memory
+            if constexpr (kTmemAT) {
+              const int cuse = lay_base + l, prev = m == 2 ? cuse : cuse - 1;
+              d_cop = tmem + 480 + 16 * ((cuse + m) & 1);
+              if (prev >= 0) alive = mbar_wait(bar(BAR_C2 + (m + 1) % 3), (uint32_t)(prev & 1), abort_flag, 0x2800000 | (m << 8) | l, p.wait_limit) && alive;
+              tc_fence_after();
+            }
             tc_st16(d_cop + lane_addr, w16);
             tc_wait_st();
             tc_fence_before();
@@ -635,9 +652,15 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
               }
               tc_commit(bar(BAR_D2 + m));
               if (TEACHER && !warm && !(SRWN_EXP & 8)) {
-                tc_mma_dyn(d_skip, desc_from_lo(ab_lo), desc_from_lo(b2_lo + 32), id128, l > 0 ? 1u : 0u);
-                tc_mma<1>(d_skip, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
+                if constexpr (kTmemAT) {
+                  tc_mma_ts_dyn(d_skip, d_cop, desc_from_lo(b2_lo + 32), id128, l > 0 ? 1u : 0u);
+                  tc_mma_ts<1>(d_skip, d_cop + 8, desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
+                } else {
+                  tc_mma_dyn(d_skip, desc_from_lo(ab_lo), desc_from_lo(b2_lo + 32), id128, l > 0 ? 1u : 0u);
+                  tc_mma<1>(d_skip, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
+                }
               }
+              if constexpr (kTmemAT) tc_commit(bar(BAR_C2 + m));          // the operand region of this tile-layer is free
 #endif
               tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
             }
