@@ -120,7 +120,9 @@ enum Bar {
   BAR_G1 = 18,     // [2] MMA -> loader/tile groups: all filter-conv MMAs of the layer retired (3 commits)
   BAR_HDD = 20,    // [3] MMA -> tile group: head accumulator ready
   BAR_TAIL = 23,   // loader -> tile groups: a pruned warm-up chunk may write the ring behind its last layer
-  BAR_C2 = 24,     // [3] MMA -> tile groups: the residual and skip MMAs of a tile-layer retired, its TMEM operand region is free
+  BAR_C2 = 24,     // [3 tiles][2 layer parities] MMA -> tile groups: the residual and skip MMAs of a tile-layer retired, its TMEM
+                   // operand region is free.  Two barriers per tile: a leading tile may be two layers ahead of the one that asks, and
+                   // a single barrier's parity could not tell "retired two layers ago" from "not yet"
 };
 
 using namespace umma;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
   if (tid == 0) {
     for (int i = 0; i < 3; i++) {
       mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_D2 + i), 1); mbar_init(bar(BAR_HDD + i), 1);
-      mbar_init(bar(BAR_C2 + i), 1);
+      mbar_init(bar(BAR_C2 + 2 * i), 1); mbar_init(bar(BAR_C2 + 2 * i + 1), 1);
       mbar_init(bar(BAR_HD + 2 * i), kTile); mbar_init(bar(BAR_HD + 2 * i + 1), kTile);
     }
     for (int i = 0; i < 2; i++) {
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             if constexpr (kTmemAT) {
               const int cuse = lay_base + l, prev = m == 2 ? cuse : cuse - 1;
               d_cop = tmem + 480 + 16 * ((cuse + m) & 1);
-              if (prev >= 0) alive = mbar_wait(bar(BAR_C2 + (m + 1) % 3), (uint32_t)(prev & 1), abort_flag, 0x2800000 | (m << 8) | l, p.wait_limit) && alive;
+              if (prev >= 0) alive = mbar_wait(bar(BAR_C2 + 2 * ((m + 1) % 3) + (prev & 1)), (uint32_t)((prev >> 1) & 1), abort_flag, 0x2800000 | (m << 8) | l, p.wait_limit) && alive;
               tc_fence_after();
             }
             tc_st16(d_cop + lane_addr, w16);
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
                   tc_mma<1>(d_skip, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
                 }
               }
-              if constexpr (kTmemAT) tc_commit(bar(BAR_C2 + m));          // the operand region of this tile-layer is free
+              if constexpr (kTmemAT) tc_commit(bar(BAR_C2 + 2 * m + ((lay_base + l) & 1)));      // the operand region of this tile-layer is free
 #endif
               tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
             }
