@@ -5,5 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 mkdir -p tools/exp
 C=sr-wavenet_b200/csrc
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DSRWN_EXP=$1 -c $C/fused_bf16.cu -o tools/exp/fused_$2.o
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o tools/exp/libsrwn_$2.so $C/api.o $C/stack_f32.o $C/mol.o $C/ops_generic.o $C/ar_generate.o $C/ar_mma.o $C/train_f32.o tools/exp/fused_$2.o -lcudart_static -ldl -lrt -lpthread
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DSRWN_TUNING -DSRWN_EXP=$1 -c $C/fused_bf16.cu -o tools/exp/fused_$2.o
+objs=""
+for f in api stack_f32 mol ops_generic ar_generate ar_mma train_f32 train_tc stft_loss encoder random; do objs="$objs $C/$f.o"; done
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o tools/exp/libsrwn_$2.so $objs tools/exp/fused_$2.o -lcudart_static -ldl -lrt -lpthread
