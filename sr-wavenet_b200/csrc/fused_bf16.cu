@@ -560,14 +560,17 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             const int rows = ring_rows_of((int)dl, m);
             if (rows) ring_rows_done(ringcnt + 4 * m, (uint32_t)rows);
           }
-          if (issuer) {                                 // the whole warp, converged: the elected lane issues (umma.cuh)
+          if (issuer) {
             tc_fence_after();
-            tc_mma_e<0>(d_conv, desc_from_lo(hb_lo - dl), desc_from_lo(b1_lo), id32);
-            tc_mma_e<1>(d_conv, desc_from_lo(hb_lo - dl + 2 * kRows), desc_from_lo(b1_lo + 64), id32);
-            tc_mma_e<1>(d_conv, desc_from_lo(hb_lo), desc_from_lo(b1_lo + 128), id32);
-            tc_mma_e<1>(d_conv, desc_from_lo(hb_lo + 2 * kRows), desc_from_lo(b1_lo + 192), id32);
-            tc_commit_e(bar(BAR_D1 + m));
-            tc_commit_e(bar(BAR_G1 + s));               // 3 arrivals (one per tile) complete the phase
+            if (leader) {
+              tc_mma<0>(d_conv, desc_from_lo(hb_lo - dl), desc_from_lo(b1_lo), id32);
+              tc_mma<1>(d_conv, desc_from_lo(hb_lo - dl + 2 * kRows), desc_from_lo(b1_lo + 64), id32);
+              tc_mma<1>(d_conv, desc_from_lo(hb_lo), desc_from_lo(b1_lo + 128), id32);
+              tc_mma<1>(d_conv, desc_from_lo(hb_lo + 2 * kRows), desc_from_lo(b1_lo + 192), id32);
+              tc_commit(bar(BAR_D1 + m));
+              tc_commit(bar(BAR_G1 + s));               // 3 arrivals (one per tile) complete the phase
+            }
+            __syncwarp();
           }
           TRACE(m, l, 2);
           // while the GEMM runs: poll the two conditions the next operand store depends on
@@ -623,19 +626,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
           TRACE(m, l, 5);
           next_ok = group_sync_and(m, next_ok);         // true: every polling warp saw both conditions
           TRACE(m, l, 6);
-          if (issuer && kTmemA && !(SRWN_EXP & 32)) {    // the whole warp, converged: the elected lane issues (umma.cuh)
-            tc_fence_after();
-            // residual first (it is what the layer chain waits for); the skip sum accumulates in TMEM behind it
-            tc_mma_ts_e<0>(d_conv, d_cop, desc_from_lo(b2_lo), id32);
-            tc_mma_ts_e<1>(d_conv, d_cop + 8, desc_from_lo(b2_lo + 2 * wrs_rows), id32);
-            tc_commit_e(bar(BAR_D2 + m));
-            if (TEACHER && !warm && !(SRWN_EXP & 8)) {
-              tc_mma_ts_e_dyn(d_skip, d_cop, desc_from_lo(b2_lo + 32), id128, l > 0 ? 1u : 0u);
-              tc_mma_ts_e<1>(d_skip, d_cop + 8, desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
-            }
-            if constexpr (kTmemAT) tc_commit_e(bar(BAR_C2 + 2 * m + ((lay_base + l) & 1)));      // the operand region of this tile-layer is free
-            tc_commit_e(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
-          } else if (issuer) {
+          if (issuer) {
             tc_fence_after();
             if (leader) {
 #if SRWN_EXP & 32

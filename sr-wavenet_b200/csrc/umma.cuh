@@ -100,30 +100,6 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// ---- the same instructions issued by a whole (converged) warp: the election happens inside the asm block, so the operands
-// stay in uniform registers and the compiler emits no per-thread election loop around each instruction (issued from one
-// thread of a divergent branch a tcgen05 instruction costs ~60-120 clocks, see tools/umma_tf32_probe.cu)
-template <int ACC>
-__device__ __forceinline__ void tc_mma_e(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc) {
-  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "n"(ACC) : "memory");
-}
-template <int ACC>
-__device__ __forceinline__ void tc_mma_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc) {
-  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "n"(ACC) : "memory");
-}
-__device__ __forceinline__ void tc_mma_ts_e_dyn(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tc_commit_e(uint32_t bar) {
-  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle canonical layout: 8-row x 16-byte core matrices; rows 16 B apart,
