@@ -166,9 +166,6 @@ __device__ __forceinline__ void store_row_packed(uint8_t* buf, int rows_per_kc, 
         make_uint4(w[kc * 4 + 0], w[kc * 4 + 1], w[kc * 4 + 2], w[kc * 4 + 3]);
 }
 
-#ifndef SRWN_SPLIT_ISSUE
-#define SRWN_SPLIT_ISSUE 1   // teacher: the skip MMAs of a tile-layer are issued by a second warp of the tile group (SMSP 3)
-#endif
 #ifndef SRWN_EXP
 #define SRWN_EXP 0      // tuning experiments (compile-time; non-zero values give wrong results, timing only)
 #endif
@@ -275,11 +272,11 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
   if (tid == 0) {
     for (int i = 0; i < 3; i++) {
       mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_D2 + i), 1); mbar_init(bar(BAR_HDD + i), 1);
-      mbar_init(bar(BAR_C2 + 2 * i), (TEACHER && SRWN_SPLIT_ISSUE) ? 2 : 1); mbar_init(bar(BAR_C2 + 2 * i + 1), (TEACHER && SRWN_SPLIT_ISSUE) ? 2 : 1);
+      mbar_init(bar(BAR_C2 + 2 * i), 1); mbar_init(bar(BAR_C2 + 2 * i + 1), 1);
       mbar_init(bar(BAR_HD + 2 * i), kTile); mbar_init(bar(BAR_HD + 2 * i + 1), kTile);
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), (TEACHER && SRWN_SPLIT_ISSUE) ? 2 * kTiles : kTiles);
+      mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), kTiles);
       mbar_init(bar(BAR_HALO + i), 1); mbar_init(bar(BAR_G1 + i), kTiles);
     }
     mbar_init(bar(BAR_TAIL), 1);
@@ -514,8 +511,6 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
         // use g - 2 to retire (BAR_C2 of tile (m + 1) % 3).
         constexpr bool kTmemAT = TEACHER && SRWN_TEACHER_TMEM_A;
         constexpr bool kTmemA = (!TEACHER && SRWN_STUDENT_TMEM_A) || kTmemAT;
-        constexpr bool kSplitIssue = kTmemAT && SRWN_SPLIT_ISSUE;
-        static_assert(!(TEACHER && SRWN_SPLIT_ISSUE) || kTmemAT, "the split issue needs the TMEM operand (barrier counts)");
         uint32_t d_cop = d_skip;
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
@@ -658,7 +653,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
                 tc_mma<1>(d_conv, desc_from_lo(ab_lo + 2 * kTile), desc_from_lo(b2_lo + 2 * wrs_rows), id32);
               }
               tc_commit(bar(BAR_D2 + m));
-              if (TEACHER && !warm && !(SRWN_EXP & 8) && !kSplitIssue) {
+              if (TEACHER && !warm && !(SRWN_EXP & 8)) {
                 if constexpr (kTmemAT) {
                   tc_mma_ts_dyn(d_skip, d_cop, desc_from_lo(b2_lo + 32), id128, l > 0 ? 1u : 0u);
                   tc_mma_ts<1>(d_skip, d_cop + 8, desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
@@ -669,26 +664,9 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
               }
               if constexpr (kTmemAT) tc_commit(bar(BAR_C2 + 2 * m + ((lay_base + l) & 1)));      // the operand region of this tile-layer is free
 #endif
-              tc_commit(bar(BAR_WEMPTY + s));           // 3 (6 with the split issue) arrivals free the weight stage
+              tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
             }
             __syncwarp();
-          }
-          if constexpr (kSplitIssue) {
-            // the skip GEMM is off the layer chain: a second warp of the group (on SMSP 3, where no tile issues its chain
-            // MMAs) issues it, so the chain's issuer is back in the epilogue ~200 clocks earlier.  Both issuers commit to the
-            // barriers that release the operand region and the weight stage.
-            if (gw == 3) {
-              tc_fence_after();
-              if (elected) {
-                if (!warm && !(SRWN_EXP & 8)) {
-                  tc_mma_ts_dyn(d_skip, d_cop, desc_from_lo(b2_lo + 32), id128, l > 0 ? 1u : 0u);
-                  tc_mma_ts<1>(d_skip, d_cop + 8, desc_from_lo(b2_lo + 2 * wrs_rows + 32), id128);
-                }
-                tc_commit(bar(BAR_C2 + 2 * m + ((lay_base + l) & 1)));
-                tc_commit(bar(BAR_WEMPTY + s));
-              }
-              __syncwarp();
-            }
           }
           TRACE(m, l, 7);
 
