@@ -538,6 +538,12 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
           if (rc >= kChunk - d0) store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);     // published at the top of layer 0
         }
 
+#if defined(SRWN_TUNING) && defined(SRWN_STAGGER)
+        if (m > 0) {                                    // tuning experiment: start tile m a fraction of a layer behind tile m - 1
+          const long long t_go = clock64() + (long long)m * SRWN_STAGGER;
+          while (clock64() < t_go) {}
+        }
+#endif
         for (int l = 0; l < Lc; l++) {
           const int s = l & 1, sn = s ^ 1;
           const uint32_t ph = (lay_base + l) & 1, phs = (U0(s) + (l >> 1)) & 1;
