@@ -729,6 +729,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
         v = make_float4(fmaf(gvv.x, SRWN_SQRT_HALF, rp[0]), fmaf(gvv.y, SRWN_SQRT_HALF, rp[1]), fmaf(gvv.z, SRWN_SQRT_HALF, rp[2]), fmaf(gvv.w, SRWN_SQRT_HALF, rp[3]));
         *reinterpret_cast<float4*>(dx_out + ((size_t)b * T + tt) * kR + c4 * 4) = v;
       }
+      TC_STAMP(2, n_done, 13 + i);
       if (P % 4 == 0) {
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {
