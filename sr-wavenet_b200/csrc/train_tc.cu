@@ -658,6 +658,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       *reinterpret_cast<float4*>(XR + c4 * kCHS + r * 16) = xt[i];
       *reinterpret_cast<float4*>(XR + (8 + c4) * kCHS + r * 16) = xc[i];
     }
+    const float4 g0 = gq[0], g1 = gq[1];                   // this tile's rows of g, for the coalesced epilogue
     TC_STAMP(2, n_done, 1);
     fence_async_smem();
     worker_sync();
@@ -709,6 +710,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
     }
     TC_STAMP(2, n_done, 7);
     tc_fence_before();
+    if (more) load_tile(tile + gridDim.x, 2);
     worker_sync();
     TC_STAMP(2, n_done, 8);
     // coalesced: dx = g sqrt(1/2) + (da W1^T + da[t+d] W0^T), stored; and the conditioning gradient (x_l carries cond_l,
@@ -720,7 +722,7 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const int r = rA + 64 * i, tt = t0 + r;
-      const float4 gvv = gq[i];                                            // this tile's rows of g (fetched one tile ahead)
+      const float4 gvv = i == 0 ? g0 : g1;
       const float* rp = red + r * 33 + c4 * 4;
       float4 v = make_float4(0, 0, 0, 0);
       if (tt < T) {
@@ -741,8 +743,6 @@ k_bwd_conv_tc(const float* __restrict__ x_l, const float* __restrict__ g_in, con
       }
     }
     TC_STAMP(2, n_done, 9);
-    // the next tile's g rows only now: behind the dx stores in the load / store queue, not in front of them
-    if (more) load_tile(tile + gridDim.x, 2);
     worker_sync();
     TC_STAMP(2, n_done, 10);
     if (tid < 32 && P % 4 == 0) {
