@@ -297,6 +297,13 @@ int srwn_residual_dilation_layer(const float* x, const float* filt_k, const floa
                                  float* dense, float* skip, int32_t B, int32_t T,
                                  int32_t R, int32_t S, int32_t K, int32_t dilation,
                                  void* stream);
+/* tf.layers.conv1d(padding='SAME', strides=1) of the non-causal layers (ResidualDilationLayerNC, ops.py:48-57): x [B,T,Cin],
+ * filters [K,Cin,Cout], bias [Cout] or NULL -> y [B,T,Cout]; (K-1)/2 taps reach back, the rest forward (TensorFlow's padding).
+ * flags: bit 0 = relu on the input, bit 1 = relu on the output. */
+int srwn_conv1d_same(const float* x, const float* filters, const float* bias, float* y, int32_t B, int32_t T,
+                     int32_t Cin, int32_t Cout, int32_t K, int32_t flags, void* stream);
+/* log_prob_from_logits (reduce = 0: y [rows,C]) and log_sum_exp (reduce = 1: y [rows]) over the last axis (ops.py:111-122). */
+int srwn_log_softmax(const float* x, float* y, int64_t rows, int32_t C, int32_t reduce, void* stream);
 /* RightShift (ops.py:78-80). */
 int srwn_right_shift(const float* x, float* y, int32_t B, int32_t T, int32_t C,
                      int32_t shift, void* stream);

@@ -96,6 +96,8 @@ SIGNATURES = {
     "srwn_encoder_last_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "srwn_dilated_causal_conv1d": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "srwn_residual_dilation_layer": (ctypes.c_int, [_fp] * 9 + [_i32] * 6 + [_vp]),
+    "srwn_conv1d_same": (ctypes.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "srwn_log_softmax": (ctypes.c_int, [_fp, _fp, _i64, _i32, _i32, _vp]),
     "srwn_right_shift": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),
     "srwn_resize_nearest": (ctypes.c_int, [_fp, _fp, _i32, _i32, _i32, _i32, _vp]),
     "srwn_relu": (ctypes.c_int, [_fp, _i64, _vp]),

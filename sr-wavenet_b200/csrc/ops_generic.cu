@@ -35,6 +35,59 @@ extern "C" int srwn_dilated_causal_conv1d(const float* x, const float* filters, 
   return SRWN_OK;
 }
 
+// tf.layers.conv1d(padding='SAME', strides=1) as the non-causal layers use it (ops.py:48-57): TensorFlow pads
+// (K - 1) / 2 on the left and the rest on the right, so out[b,t,co] = bias[co] + sum_k sum_ci act(x[b, t + k - (K-1)/2, ci]) w[k,ci,co];
+// flags: bit 0 = relu on the input (ops.py:49,52), bit 1 = relu on the output
+__global__ void k_conv_same(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                            float* __restrict__ y, int T, int Cin, int Cout, int K, int flags) {
+  const int b = blockIdx.y;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * Cout) return;
+  const int t = (int)(idx / Cout), co = (int)(idx % Cout), left = (K - 1) / 2;
+  float acc = bias ? bias[co] : 0.f;
+  for (int k = 0; k < K; k++) {
+    const int tt = t + k - left;
+    if (tt < 0 || tt >= T) continue;
+    const float* xr = x + ((size_t)b * T + tt) * Cin;
+    const float* wk = w + (size_t)k * Cin * Cout + co;
+    if (flags & 1) { for (int ci = 0; ci < Cin; ci++) acc = fmaf(fmaxf(xr[ci], 0.f), wk[(size_t)ci * Cout], acc); }
+    else { for (int ci = 0; ci < Cin; ci++) acc = fmaf(xr[ci], wk[(size_t)ci * Cout], acc); }
+  }
+  y[((size_t)b * T + t) * Cout + co] = (flags & 2) ? fmaxf(acc, 0.f) : acc;
+}
+
+extern "C" int srwn_conv1d_same(const float* x, const float* filters, const float* bias, float* y, int32_t B, int32_t T,
+                                int32_t Cin, int32_t Cout, int32_t K, int32_t flags, void* stream) {
+  if (!x || !filters || !y) return srwn_fail(SRWN_ERR_INVALID, "srwn_conv1d_same: null argument");
+  if (B < 0 || T < 0 || Cin < 1 || Cout < 1 || K < 1 || B > 65535) return srwn_fail(SRWN_ERR_INVALID, "srwn_conv1d_same: bad shape");
+  if (B == 0 || T == 0) return SRWN_OK;
+  dim3 grid((unsigned)(((int64_t)T * Cout + 255) / 256), B);
+  k_conv_same<<<grid, 256, 0, (cudaStream_t)stream>>>(x, filters, bias, y, T, Cin, Cout, K, flags);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
+// ops.py:111-122: log_prob_from_logits (mode 0: y [rows][C] = x - max - log sum exp(x - max)) and log_sum_exp
+// (mode 1: y [rows] = max + log sum exp(x - max)) over the last axis
+__global__ void k_log_softmax_rows(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int C, int mode) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* xr = x + r * C;
+  float m = xr[0];
+  for (int c = 1; c < C; c++) m = fmaxf(m, xr[c]);
+  float sum = 0.f;
+  for (int c = 0; c < C; c++) sum += expf(xr[c] - m);
+  const float ls = logf(sum);
+  if (mode == 1) { y[r] = m + ls; return; }
+  for (int c = 0; c < C; c++) y[r * C + c] = xr[c] - m - ls;
+}
+extern "C" int srwn_log_softmax(const float* x, float* y, int64_t rows, int32_t C, int32_t reduce, void* stream) {
+  if (!x || !y || rows < 1 || C < 1) return srwn_fail(SRWN_ERR_INVALID, "srwn_log_softmax: bad argument");
+  k_log_softmax_rows<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, y, rows, C, reduce ? 1 : 0);
+  SRWN_LAUNCH_CHECK();
+  return SRWN_OK;
+}
+
 // ops.py:23-46 for generic R / S / K.  8 time steps per CTA; gate activations staged in smem.
 constexpr int kGenRows = 8;
 __global__ void __launch_bounds__(128)

@@ -151,6 +151,50 @@ def ResidualDilationLayer(inputs, kernel_size, dilation_channels, skip_channels,
     return dense, skip
 
 
+def ResidualDilationLayerNC(inputs, kernel_size, dilation_channels, skip_channels, dilation_rate=1,
+                            name='', dtype=torch.float32, use_bias=True):
+    """ops.py:48-57 -> (residual, skip): relu -> conv1d(kernel_size, SAME) -> relu -> two 1x1 convs.  Like the reference,
+    ``dilation_rate`` and ``use_bias`` are accepted and ignored (``tf.layers.conv1d`` is called without a dilation and with
+    its default bias), and the block returns the residual itself, not ``inputs + residual``.  The teacher's encoder runs
+    this block in its own tcgen05 kernel (csrc/encoder.cu); this is the shape-generic building block."""
+    x = _prep(inputs, "inputs")
+    B, T, cin = x.shape
+    lib = _lib.load()
+    with variable_scope(name + '_NC'):
+        with variable_scope(_unique_layer_name('conv1d')):
+            k0 = get_variable('kernel', [kernel_size, cin, dilation_channels], "xavier", dtype)
+            b0 = get_variable('bias', [dilation_channels], "zeros", dtype)
+    with variable_scope(_unique_layer_name('conv1d')):
+        rk = get_variable('kernel', [1, dilation_channels, dilation_channels], "xavier", dtype)
+        rb = get_variable('bias', [dilation_channels], "zeros", dtype)
+    with variable_scope(_unique_layer_name('conv1d')):
+        sk = get_variable('kernel', [1, dilation_channels, skip_channels], "xavier", dtype)
+        sb = get_variable('bias', [skip_channels], "zeros", dtype)
+    h = torch.empty(B, T, dilation_channels, dtype=torch.float32, device=x.device)
+    _lib.check(lib.srwn_conv1d_same(_ptr(x), _ptr(k0), _ptr(b0), _ptr(h), B, T, cin, dilation_channels, kernel_size, 3, _stream()))
+    residual = torch.empty(B, T, dilation_channels, dtype=torch.float32, device=x.device)
+    skip = torch.empty(B, T, skip_channels, dtype=torch.float32, device=x.device)
+    _lib.check(lib.srwn_conv1d_same(_ptr(h), _ptr(rk), _ptr(rb), _ptr(residual), B, T, dilation_channels, dilation_channels, 1, 0, _stream()))
+    _lib.check(lib.srwn_conv1d_same(_ptr(h), _ptr(sk), _ptr(sb), _ptr(skip), B, T, dilation_channels, skip_channels, 1, 0, _stream()))
+    return residual, skip
+
+
+def log_prob_from_logits(x):
+    """ops.py:111-115: numerically stable log-softmax over the last axis."""
+    t = _prep(x, "x")
+    y = torch.empty_like(t)
+    _lib.check(_lib.load().srwn_log_softmax(_ptr(t), _ptr(y), t.numel() // t.shape[-1], t.shape[-1], 0, _stream()))
+    return y
+
+
+def log_sum_exp(x):
+    """ops.py:117-122: numerically stable log-sum-exp over the last axis (which it removes)."""
+    t = _prep(x, "x")
+    y = torch.empty(t.shape[:-1], dtype=torch.float32, device=t.device)
+    _lib.check(_lib.load().srwn_log_softmax(_ptr(t), _ptr(y), t.numel() // t.shape[-1], t.shape[-1], 1, _stream()))
+    return y
+
+
 def ResizeEmbeddingNearestNeighbor(inputs, output_size):
     """ops.py:64-74: [B,L,C] -> [B,output_size,C], nearest neighbour, align_corners=False."""
     x = _prep(inputs, "inputs")

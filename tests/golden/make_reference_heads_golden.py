@@ -64,6 +64,30 @@ def compute():
     out['si_loss'] = np.asarray(sess.run(s.loss, {s.inputs_left: xl, s.inputs_right: xr, s.labels: labels}))
     out.update({'si_xl': xl, 'si_xr': xr, 'si_labels': labels, 'si_names': np.array(sorted(w))})
     out.update({'si_w/' + k: v for k, v in w.items()})
+    # ---- the remaining building blocks of ops.py: the non-causal block (ops.py:48-57) and the two log helpers (ops.py:111-122)
+    _, rops, _ = refshim.load()
+    for K in (2, 3):
+        g = tf.Graph()
+        with refshim.quiet(), g.as_default():
+            with tf.variable_scope('NCtest'):
+                xin = tf.placeholder(tf.float32, [None, None, 5])
+                res, skip = rops.ResidualDilationLayerNC(xin, K, dilation_channels=6, skip_channels=4, dilation_rate=7, name='blk')
+            variables = tf.get_collection(tf.GraphKeys.TRAINABLE_VARIABLES, 'NCtest')
+        w = seeded_weights(variables, 300 + K)
+        refshim.set_variables(g, {k: v.astype(np.float64) for k, v in w.items()}, strict_prefix='NCtest/')
+        x = rng.normal(0, 1, size=(2, 37, 5)).astype(np.float32)
+        with tf.Session(graph=g).as_default() as sess:
+            r, sk = sess.run([res, skip], {xin: x})
+        out.update({'nc%d_x' % K: x, 'nc%d_residual' % K: r, 'nc%d_skip' % K: sk, 'nc%d_names' % K: np.array(sorted(w))})
+        out.update({'nc%d_w/' % K + k: v for k, v in w.items()})
+    g = tf.Graph()
+    with g.as_default():
+        xin = tf.placeholder(tf.float32, [None, None, 7])
+        lp, lse = rops.log_prob_from_logits(xin), rops.log_sum_exp(xin)
+    x = (rng.normal(0, 3, size=(2, 5, 7)) + 40.0).astype(np.float32)          # shifted: the helpers exist for exactly this
+    with tf.Session(graph=g).as_default() as sess:
+        a, b = sess.run([lp, lse], {xin: x})
+    out.update({'lse_x': x, 'lse_log_prob': a, 'lse_log_sum_exp': b})
     return out
 
 

@@ -55,3 +55,33 @@ def test_siamese_checkpoint_roundtrip(lib, tmp_path):
     assert other.load(None, str(tmp_path)) is True
     np.testing.assert_array_equal(other.get_embedding(None, g["si_xl"]), si.get_embedding(None, g["si_xl"]))
     assert other.load(None, str(tmp_path / "missing")) is None
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_noncausal_block_matches_reference(lib, K):
+    """ResidualDilationLayerNC (ops.py:48-57): same variable names as the reference's graph, residual and skip within 1e-4."""
+    from sr_wavenet_b200 import ops
+    g = _fixture()
+    ops.reset_variables()
+    x = g["nc%d_x" % K]
+    with ops.variable_scope("NCtest"):
+        ops.ResidualDilationLayerNC(x, K, dilation_channels=6, skip_channels=4, dilation_rate=7, name="blk")      # creates the variables
+    assert sorted(ops.global_variables()) == [str(n) for n in g["nc%d_names" % K]]
+    for n in ops.global_variables():
+        ops._variables[n] = torch.from_numpy(np.ascontiguousarray(g["nc%d_w/%s" % (K, n)])).cuda()
+    ops._layer_counts.clear()
+    with ops.variable_scope("NCtest"):
+        res, skip = ops.ResidualDilationLayerNC(x, K, dilation_channels=6, skip_channels=4, dilation_rate=7, name="blk")
+    _close(res.cpu().numpy(), g["nc%d_residual" % K], "NC block residual, K = %d" % K)
+    _close(skip.cpu().numpy(), g["nc%d_skip" % K], "NC block skip, K = %d" % K)
+    ops.reset_variables()
+
+
+def test_log_helpers_match_reference(lib):
+    """log_prob_from_logits / log_sum_exp (ops.py:111-122) on logits shifted by +40."""
+    from sr_wavenet_b200 import ops
+    g = _fixture()
+    _close(ops.log_prob_from_logits(g["lse_x"]).cpu().numpy(), g["lse_log_prob"], "log_prob_from_logits")
+    lse = ops.log_sum_exp(g["lse_x"])
+    assert tuple(lse.shape) == g["lse_log_sum_exp"].shape
+    _close(lse.cpu().numpy(), g["lse_log_sum_exp"], "log_sum_exp")
