@@ -526,23 +526,30 @@ class WaveNetAutoEncoder(_CheckpointMixin):
             first = next(it)
         except StopIteration:
             return
-        upload(slots[0], first)
-        nxt = 0
-        while nxt is not None:
-            cur = slots[nxt]
-            launch(cur)
-            pending.append(cur)
-            i += 1
-            try:
-                batch = next(it)
-                if len(pending) == depth:             # every slot is in flight: hand the oldest result out before reusing its slot
-                    yield collect(pending.pop(0))
-                nxt = i % depth
-                upload(slots[nxt], batch)
-            except StopIteration:
-                nxt = None
-        for slot in pending:
-            yield collect(slot)
+        try:
+            upload(slots[0], first)
+            nxt = 0
+            while nxt is not None:
+                cur = slots[nxt]
+                launch(cur)
+                pending.append(cur)
+                i += 1
+                try:
+                    batch = next(it)
+                    if len(pending) == depth:         # every slot is in flight: hand the oldest result out before reusing its slot
+                        yield collect(pending.pop(0))
+                    nxt = i % depth
+                    upload(slots[nxt], batch)
+                except StopIteration:
+                    nxt = None
+            while pending:
+                yield collect(pending.pop(0))
+        finally:
+            # the slots' device buffers go back to the allocator when this frame dies: nothing on the copy stream (or, when
+            # the consumer stopped early or an error came up, on the compute stream) may still be using them
+            copy.synchronize()
+            if pending:
+                compute.synchronize()
 
     def reconstruct_with_encoding(self, inputs, encoding, conditions=None, u1=None, u2=None,
                                   precision=None):

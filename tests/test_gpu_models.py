@@ -399,3 +399,20 @@ def test_nll_stream_matches_nll_batch_by_batch(srwn):
         assert list(t.nll_stream(batches[:1], precision=prec)) == ref[:1]
         assert list(t.nll_stream([], precision=prec)) == []
         assert list(t.nll_stream(batches, precision=prec, depth=3)) == ref
+
+
+def test_nll_stream_survives_an_early_stop(srwn):
+    """A consumer that stops after the first result (generator closed with work in flight) leaves the handle usable."""
+    dil, T = [1, 2, 4, 8], 512
+    t = srwn.WaveNetAutoEncoder(input_size=T, condition_size=0, num_mixtures=5, dilations=dil, skip_channels=128,
+                                latent_channels=32, pool_stride=128)
+    t.set_weights(synth.make_teacher_weights(dil))
+    batches = [(synth.synthetic_audio(2, T, seed=k), synth.synthetic_encoding(2, T // 128, seed=9 + k)) for k in range(4)]
+    ref = [t.nll(x, e) for x, e in batches]
+    gen = t.nll_stream(iter(batches))
+    assert next(gen) == ref[0]
+    gen.close()
+    assert list(t.nll_stream(batches)) == ref
+    with pytest.raises(ValueError):
+        list(t.nll_stream([(batches[0][0], batches[0][1][:, :1])]))          # encoding of the wrong length: refused, nothing hangs
+    assert t.nll(*batches[1]) == ref[1]
