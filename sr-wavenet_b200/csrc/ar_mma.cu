@@ -60,7 +60,8 @@ struct Smem {
   static constexpr int xslot = flags + kMaxL * 4;           // x[t] of the 8 utterances, chain warp 0 -> chain warps 1..3
   static constexpr int qofs = xslot + 64;                   // queue slot byte offsets, [2 step parities][kMaxL] ints
   static constexpr int tmem = qofs + 2 * kMaxL * 4;         // TMEM base address (tcgen05.alloc)
-  static constexpr int total = tmem + 16;
+  static constexpr int hslot = (tmem + 16 + 15) / 16 * 16;  // residual-stream image of the current layer: [lane][4 x b32], one word per chain warp
+  static constexpr int total = hslot + kSlotBytes;
 };
 static_assert(Smem::total <= 232448, "shared memory budget");
 
@@ -168,6 +169,15 @@ __device__ __forceinline__ void tmem_wait_ld(float2 (&v)[4]) {
                :: "memory");
 }
 constexpr int kTmemCols = 256;                 // (kMaxL + 1) * 8 = 248 columns used
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float2& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld2(float2& v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v.x), "+f"(v.y) :: "memory");
+}
+#ifndef SRWN_AR_SPLIT_RES
+#define SRWN_AR_SPLIT_RES 1     // 1: chain warp j computes only n-tile j of the residual conv and the warps exchange the stream image
+#endif
 
 #ifdef SRWN_AR_TIMING
 __device__ __forceinline__ long long clk_after(uint32_t dep) {      // clock read ordered after the value `dep` is ready
@@ -347,6 +357,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
 #pragma unroll
       for (int i = 0; i < 4; i++) hA[i] = pack_h2(h[i][0], h[i][1]);
       hB[0] = pack_h2(h[2][0], h[2][1]); hB[1] = pack_h2(h[3][0], h[3][1]);
+#if SRWN_AR_SPLIT_RES
+      float hj0 = j == 0 ? h[0][0] : j == 1 ? h[1][0] : j == 2 ? h[2][0] : h[3][0];      // this warp's part of the fp32 stream
+      float hj1 = j == 0 ? h[0][1] : j == 1 ? h[1][1] : j == 2 ? h[2][1] : h[3][1];
+#endif
       // filter-conv B fragments of this warp's n-tile: [taps k-tiles 0,1 | current k-tiles 2,3]
       uint4 wft = lds128_ro(sbase + Smem::chain + lane * 16 + (2 * j) * 512);
       uint4 wfc = lds128_ro(sbase + Smem::chain + lane * 16 + (2 * j + 1) * 512);
@@ -357,8 +371,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
       auto layer = [&](const int l, Pre& S) {
         const uint32_t wl = sbase + Smem::chain + l * kChainLayerBytes + lane * 16;
         AR_T(t_0, hA[0]);
+#if SRWN_AR_SPLIT_RES
+        float2 cbj;                                      // term added after this layer (index l + 1), this warp's two channels
+        if (l + 1 < L) tmem_ld2(tm + (l + 1) * 8 + 2 * j, cbj);
+#else
         float2 cbn[4];                                   // term added after this layer (index l + 1)
         tmem_ld8(tm + (l + 1) * 8, cbn);
+#endif
         // ---- filter conv (ops.py:6-10), n-tile j: taps (W[0] on h[t-d]) and current (W[1] on h[t]) as two
         //      independent accumulation chains
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -368,9 +387,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         mma8q(acc, S.tap.y, dm[2], S.tap.w, dm[3], wft.z, wft.w);
         AR_T(t_1, S.tap.x);
         AR_T(t_2, __float_as_uint(acc[0] + acc2[0]));
+#if SRWN_AR_SPLIT_RES
+        const uint4 wrj = lds128_ro(wl + 4096 + j * 512); // residual B fragments of n-tile j: land while the gate runs
+#else
         uint4 wr[4];                                     // residual B fragments: land while the gate runs
 #pragma unroll
         for (int i = 0; i < 4; i++) wr[i] = lds128_ro(wl + 4096 + i * 512);
+#endif
         // push h[t] (the slot held h[t-d] until now); every chain warp holds the same image
         if (j == 0) *reinterpret_cast<uint4*>(qbase + S.ofs) = make_uint4(hA[0], hA[2], hA[1], hA[3]);
         if (l + 3 < L) prefetch(S, l + 3, sqt);          // this set's next use: layer l + 3
@@ -388,6 +411,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         chain_sync();                                    // the four words of every lane's slot are in place
         AR_T(t_4, 0u);
         if (j == 0 && lane == 0) mbar_arrive(bar(B_CFULL + l));      // release: the skip warps may read the slot
+#if SRWN_AR_SPLIT_RES
+        // The output of the last layer is not used (model.py:183-190: only the skips reach the head), so its residual conv
+        // is skipped.  Otherwise warp j computes n-tile j of the residual conv (two dependent MMAs instead of eight),
+        // updates its two channels of the fp32 stream and the four warps exchange the 16-bit image through one slot.
+        if (l + 1 < L) {
+          const uint4 cA = lds128(sbase + Smem::cslots + l * kSlotBytes + lane * 16);     // {c n-tile 0, 2, 1, 3}
+          float r[4] = {0.f, 0.f, 0.f, 0.f};
+          mma8q(r, cA.x, cA.y, cA.z, cA.w, wrj.x, wrj.y);
+          mma8q(r, cA.y, dm[4], cA.w, dm[5], wrj.z, wrj.w);
+          tmem_wait_ld2(cbj);
+          hj0 = fmaf(hj0 + r[0], SRWN_SQRT_HALF, cbj.x);
+          hj1 = fmaf(hj1 + r[1], SRWN_SQRT_HALF, cbj.y);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + Smem::hslot + lane * 16 + cpos), "r"(pack_h2(hj0, hj1)) : "memory");
+          chain_sync();
+          const uint4 hq = lds128(sbase + Smem::hslot + lane * 16);                       // {h n-tile 0, 2, 1, 3}
+          hA[0] = hq.x; hA[2] = hq.y; hA[1] = hq.z; hA[3] = hq.w; hB[0] = hq.y; hB[1] = hq.w;
+        }
+        AR_T(t_5, hA[0] ^ hA[3]);
+#else
         const uint4 cA = lds128(sbase + Smem::cslots + l * kSlotBytes + lane * 16);     // {c n-tile 0, 2, 1, 3}
         // ---- residual 1x1 (ops.py:39) and dense = (inputs + residual) * sqrt(1/2) (ops.py:40); the folded
         //      term carries sqrt(1/2)*bias and the next layer's conditioning (model.py:183)
@@ -406,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_ar_mma(const Params p) {
         for (int i = 0; i < 4; i++) hA[i] = pack_h2(h[i][0], h[i][1]);
         hB[0] = pack_h2(h[2][0], h[2][1]); hB[1] = pack_h2(h[3][0], h[3][1]);
         AR_T(t_5, hA[0] ^ hA[3]);
+#endif
         AR_ACC(tl_top, t_1 - t_0); AR_ACC(tl_conv, t_2 - t_1); AR_ACC(tl_gate, t_3 - t_2); AR_ACC(tl_sync, t_4 - t_3); AR_ACC(tl_res, t_5 - t_4);
       };
       {
