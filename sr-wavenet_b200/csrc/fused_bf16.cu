@@ -867,12 +867,13 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
 }
 
 // sums the per-CTA partial log-likelihoods in a fixed order (deterministic for a given partition)
+// (one warp: lane i adds partials i, i + 32, ... in ascending order, then a fixed shuffle tree -- the loads of a single
+// thread walking all partials were a 9 us dependent chain)
 __global__ void k_sum_partials(const double* __restrict__ part, int n, float* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double tot = 0;
-    for (int i = 0; i < n; i++) tot += part[i];
-    *out = (float)tot;
-  }
+  double tot = 0;
+  for (int i = threadIdx.x; i < n; i += 32) tot += part[i];
+  for (int s = 16; s >= 1; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
+  if (threadIdx.x == 0) *out = (float)tot;
 }
 
 // cb[b][frame][0] = front bias + cond_0; cb[..][l+1] = sqrt(1/2)*res_bias_l + cond_{l+1} (0 past the last layer)
@@ -896,35 +897,71 @@ __global__ void k_fold_bias(const float* __restrict__ cond, const float* __restr
 #endif
 // 8 rows per CTA re-read the 127 KB of conditioning weights from L2 2000 times at 32x64000 (61 us); 32 rows: 4x less
 constexpr int kCondRows = SRWN_COND_ROWS;
-__global__ void __launch_bounds__(256, 2)
+constexpr int kCondThreads = 512;
+// Register-blocked: a thread owns 4 consecutive output channels of one (layer, frame-half) for kCondRows / 2 frames, so one
+// 16-byte weight load and one broadcast 16-byte read of the encodings feed 16 FMAs each (the first version issued one
+// shared-memory read per FMA and was bound by that pipe).  The sum over the conditioning channels runs in ascending
+// order from the folded bias, as before: results are bit-identical.
+__global__ void __launch_bounds__(kCondThreads, 1)
 k_cond_fold(const float* __restrict__ enc, const float* __restrict__ cond_k, const float* __restrict__ cond_b,
             const float* __restrict__ front_b, const float* __restrict__ res_b, float* __restrict__ cb,
             int BF, int L, int C) {
-  __shared__ float s_enc[kCondRows][kMaxCond];
+  constexpr int RH = kCondRows / 2;
+  __shared__ __align__(16) float s_enc[kCondRows][kMaxCond];
   const int bf0 = blockIdx.x * kCondRows;
-  for (int i = threadIdx.x; i < kCondRows * C; i += blockDim.x) {
-    const int r = i / C, c = i % C;
-    s_enc[r][c] = bf0 + r < BF ? enc[(size_t)(bf0 + r) * C + c] : 0.f;
+  for (int i = threadIdx.x; i < kCondRows * kMaxCond; i += blockDim.x) {
+    const int r = i / kMaxCond, c = i % kMaxCond;
+    s_enc[r][c] = (bf0 + r < BF && c < C) ? enc[(size_t)(bf0 + r) * C + c] : 0.f;
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < (L + 1) * 32; o += blockDim.x) {
-    const int l = o / 32, j = o % 32;
-    float acc[kCondRows];
-    const float base = (l < L ? cond_b[l * 32 + j] : 0.f) + (l == 0 ? front_b[j] : SRWN_SQRT_HALF * res_b[(l - 1) * 32 + j]);
+  const int half = threadIdx.x / (kCondThreads / 2), r0 = half * RH;
+  for (int g = threadIdx.x % (kCondThreads / 2); g < (L + 1) * 8; g += kCondThreads / 2) {
+    const int l = g / 8, j = (g % 8) * 4, o = l * 32 + j;
+    float4 base;
+    {
+      const float4 cbv = l < L ? *reinterpret_cast<const float4*>(cond_b + l * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (l == 0) {
+        const float4 f = *reinterpret_cast<const float4*>(front_b + j);
+        base = make_float4(cbv.x + f.x, cbv.y + f.y, cbv.z + f.z, cbv.w + f.w);
+      } else {
+        const float4 rb = *reinterpret_cast<const float4*>(res_b + (l - 1) * 32 + j);
+        base = make_float4(cbv.x + SRWN_SQRT_HALF * rb.x, cbv.y + SRWN_SQRT_HALF * rb.y, cbv.z + SRWN_SQRT_HALF * rb.z, cbv.w + SRWN_SQRT_HALF * rb.w);
+      }
+    }
+    float4 acc[RH];
 #pragma unroll
-    for (int r = 0; r < kCondRows; r++) acc[r] = base;
+    for (int r = 0; r < RH; r++) acc[r] = base;
     if (l < L) {
       const float* wk = cond_k + (size_t)l * C * 32 + j;
-#pragma unroll 2
-      for (int c = 0; c < C; c++) {
-        const float w = __ldg(wk + (size_t)c * 32);
+      const int C4 = C & ~3;
+      for (int c = 0; c < C4; c += 4) {
+        float4 w[4];
 #pragma unroll
-        for (int r = 0; r < kCondRows; r++) acc[r] = fmaf(s_enc[r][c], w, acc[r]);
+        for (int k = 0; k < 4; k++) w[k] = __ldg(reinterpret_cast<const float4*>(wk + (size_t)(c + k) * 32));
+#pragma unroll
+        for (int r = 0; r < RH; r++) {
+          const float4 e = *reinterpret_cast<const float4*>(&s_enc[r0 + r][c]);
+          const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            acc[r].x = fmaf(ev[k], w[k].x, acc[r].x); acc[r].y = fmaf(ev[k], w[k].y, acc[r].y);
+            acc[r].z = fmaf(ev[k], w[k].z, acc[r].z); acc[r].w = fmaf(ev[k], w[k].w, acc[r].w);
+          }
+        }
+      }
+      for (int c = C4; c < C; c++) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wk + (size_t)c * 32));
+#pragma unroll
+        for (int r = 0; r < RH; r++) {
+          const float e = s_enc[r0 + r][c];
+          acc[r].x = fmaf(e, w.x, acc[r].x); acc[r].y = fmaf(e, w.y, acc[r].y);
+          acc[r].z = fmaf(e, w.z, acc[r].z); acc[r].w = fmaf(e, w.w, acc[r].w);
+        }
       }
     }
 #pragma unroll
-    for (int r = 0; r < kCondRows; r++)
-      if (bf0 + r < BF) cb[(size_t)(bf0 + r) * (L + 1) * 32 + o] = acc[r];
+    for (int r = 0; r < RH; r++)
+      if (bf0 + r0 + r < BF) *reinterpret_cast<float4*>(cb + (size_t)(bf0 + r0 + r) * (L + 1) * 32 + o) = acc[r];
   }
 }
 
@@ -1179,7 +1216,7 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   const float* sw = stack_w(c, stack);
   int rc = sticky_error(c);
   if (rc) return rc;
-  k_cond_fold<<<(B * frames + kCondRows - 1) / kCondRows, 256, 0, st>>>(enc, sw + c->off.cond_k, sw + c->off.cond_b,
+  k_cond_fold<<<(B * frames + kCondRows - 1) / kCondRows, kCondThreads, 0, st>>>(enc, sw + c->off.cond_k, sw + c->off.cond_b,
                                                                         sw + c->off.front_b, sw + c->off.res_b, w.cb,
                                                                         B * frames, L, c->cfg.cond_channels);
   SRWN_LAUNCH_CHECK();
