@@ -42,10 +42,16 @@ __global__ void k_cond(const float* __restrict__ enc, const float* __restrict__ 
 namespace fused {
 
 constexpr int kTile = 128;
-constexpr int kTiles = 3;
-constexpr int kChunk = kTile * kTiles;          // 384 time steps per chunk
+// Tiles (independent layer chains) per chunk.  Teacher: 3 -- a tile holds 128 fp32 skip-sum columns + 32 accumulator columns
+// of the 512 TMEM columns.  Student: 4 -- a flow has no skip path (48 columns per tile), so what limits it is the register
+// file: 17-18 warps leave 96 registers per thread (ptxas: 28 bytes of spills), and one more chain per SM hides more of the
+// per-tile latency chain than the narrower register budget costs.
+#ifndef SRWN_STUDENT_TILES
+#define SRWN_STUDENT_TILES 4
+#endif
+__host__ __device__ constexpr int tiles_of(bool teacher) { return teacher ? 3 : SRWN_STUDENT_TILES; }
+__host__ __device__ constexpr int chunk_of(bool teacher) { return kTile * tiles_of(teacher); }     // time steps per chunk
 constexpr int kHalo = 512;                      // largest dilation the layout supports
-constexpr int kRows = kHalo + kChunk;           // rows per activation buffer
 constexpr int kMaxLayers = 40;
 constexpr int kMaxSeg = 8;
 
@@ -89,41 +95,48 @@ struct Params {
 };
 
 // ---- shared memory map ------------------------------------------------------------------
-struct SmemMap {
-  static constexpr int hbuf = 0;                                  // 2 x [4][kRows][16 B]
-  static constexpr int hbuf_bytes = 4 * kRows * 16;               // 57344
-  static constexpr int cbuf = hbuf + 2 * hbuf_bytes;              // 3 x [4][128][16 B]
+template <bool TEACHER>
+struct SmemMapT {
+  static constexpr int NT = tiles_of(TEACHER);
+  static constexpr int rows = kHalo + NT * kTile;                 // rows per activation buffer
+  static constexpr int hbuf = 0;                                  // 2 x [4][rows][16 B]
+  static constexpr int hbuf_bytes = 4 * rows * 16;                // 57344 (teacher) / 65536 (student)
+  static constexpr int cbuf = hbuf + 2 * hbuf_bytes;              // NT x [4][128][16 B]
   static constexpr int cbuf_bytes = 4 * kTile * 16;               // 8192
-  static constexpr int wst = cbuf + kTiles * cbuf_bytes;          // 2 stages
-  static constexpr int wst_bytes = kWfBytes + kWrsTeacher;        // 14336
-  static constexpr int head = wst + 2 * wst_bytes;                // H1 | H2 (teacher)
-  static constexpr int bias = head + kH1Bytes + kH2Bytes;         // [kMaxLayers][32] filter bias fp32
+  static constexpr int wst = cbuf + NT * cbuf_bytes;              // 2 stages
+  static constexpr int wst_bytes = kWfBytes + (TEACHER ? kWrsTeacher : kWrsStudent);   // 14336 / 6144
+  static constexpr int head = wst + 2 * wst_bytes;                // H1 | H2 (teacher only)
+  static constexpr int bias = head + (TEACHER ? kH1Bytes + kH2Bytes : 0);   // [kMaxLayers][32] filter bias fp32
   static constexpr int hbias = bias + kMaxLayers * 32 * 4;        // skip_b_sum[128] | h1_b[128] | h2_b[32] | flow hk[64] hb[2]
   static constexpr int front = hbias + (128 + 128 + 32 + 64 + 4) * 4;   // fk[64]
-  static constexpr int cbs = front + 64 * 4;                      // [3 tiles][kMaxLayers+1][32] folded bias + conditioning of the chunk
-  static constexpr int bars = cbs + kTiles * (kMaxLayers + 1) * 32 * 4;
-  static constexpr int n_bars = 32;
-  static constexpr int misc = bars + n_bars * 8;                  // [0] tmem ptr, [8] abort flag + code, [16..28) ring-row counters
+  static constexpr int cbs = front + 64 * 4;                      // [NT tiles][kMaxLayers+1][32] folded bias + conditioning of the chunk
+  static constexpr int bars = cbs + NT * (kMaxLayers + 1) * 32 * 4;
+  static constexpr int n_bars = 40;
+  static constexpr int misc = bars + n_bars * 8;                  // [0] tmem ptr, [8] abort flag + code, [16..16+4NT) ring-row counters
   static constexpr int total = misc + 64;
 };
-static_assert(SmemMap::total <= 232448, "shared memory budget");
+static_assert(SmemMapT<true>::total <= 232448 && SmemMapT<false>::total <= 232448, "shared memory budget");
 // A3/A4 (head operands, 3 x 32 KB) overlay the two activation buffers
-static_assert(kTiles * 16 * kTile * 16 <= 2 * SmemMap::hbuf_bytes, "head operand overlay");
+static_assert(3 * 16 * kTile * 16 <= 2 * SmemMapT<true>::hbuf_bytes, "head operand overlay");
 
-enum Bar {
-  BAR_D1 = 0,      // [3] MMA -> tile group: filter-conv accumulator ready (tcgen05.commit)
-  BAR_D2 = 3,      // [3] MMA -> tile group: residual accumulator ready (tcgen05.commit)
-  BAR_HD = 6,      // [3 tiles][2 layer parities] tile group -> higher tiles: input rows of a layer stored (128 arrivals)
-  BAR_WFULL = 12,  // [2] loader -> tile groups: layer weights landed (tx bytes)
-  BAR_WEMPTY = 14, // [2] MMA -> loader: all residual/skip MMAs of the layer retired (3 commits)
-  BAR_HALO = 16,   // [2] loader -> tile groups: halo rows of the layer landed
-  BAR_G1 = 18,     // [2] MMA -> loader/tile groups: all filter-conv MMAs of the layer retired (3 commits)
-  BAR_HDD = 20,    // [3] MMA -> tile group: head accumulator ready
-  BAR_TAIL = 23,   // loader -> tile groups: a pruned warm-up chunk may write the ring behind its last layer
-  BAR_C2 = 24,     // [3 tiles][2 layer parities] MMA -> tile groups: the residual and skip MMAs of a tile-layer retired, its TMEM
-                   // operand region is free.  Two barriers per tile: a leading tile may be two layers ahead of the one that asks, and
-                   // a single barrier's parity could not tell "retired two layers ago" from "not yet"
+// mbarrier indices for NT tiles
+template <int NT>
+struct BarT {
+  static constexpr int D1 = 0;              // [NT] MMA -> tile group: filter-conv accumulator ready (tcgen05.commit)
+  static constexpr int D2 = NT;             // [NT] MMA -> tile group: residual accumulator ready (tcgen05.commit)
+  static constexpr int HD = 2 * NT;         // [NT tiles][2 layer parities] tile group -> higher tiles: input rows of a layer stored (128 arrivals)
+  static constexpr int WFULL = 4 * NT;      // [2] loader -> tile groups: layer weights landed (tx bytes)
+  static constexpr int WEMPTY = WFULL + 2;  // [2] MMA -> loader: all residual/skip MMAs of the layer retired (NT commits)
+  static constexpr int HALO = WFULL + 4;    // [2] loader -> tile groups: halo rows of the layer landed
+  static constexpr int G1 = WFULL + 6;      // [2] MMA -> loader/tile groups: all filter-conv MMAs of the layer retired (NT commits)
+  static constexpr int HDD = WFULL + 8;     // [NT] MMA -> tile group: head accumulator ready
+  static constexpr int TAIL = HDD + NT;     // loader -> tile groups: a pruned warm-up chunk may write the ring behind its last layer
+  static constexpr int C2 = TAIL + 1;       // [NT tiles][2 layer parities] MMA -> tile groups: the residual and skip MMAs of a tile-layer retired, its TMEM
+                                            // operand region is free.  Two barriers per tile: a leading tile may be two layers ahead of the one that asks, and
+                                            // a single barrier's parity could not tell "retired two layers ago" from "not yet"
+  static constexpr int count = C2 + 2 * NT;
 };
+static_assert(BarT<3>::count <= 40 && BarT<4>::count <= 40, "barrier slots");
 
 using namespace umma;
 
@@ -190,8 +203,8 @@ __device__ __forceinline__ void store_row_packed(uint8_t* buf, int rows_per_kc, 
 // belongs to tile (j+q+1)%3, so that tile m's MMA-issuing warp is the highest warp id of SMSP m (the
 // arbiter prefers high warp ids, and tcgen05 issue from a busy SMSP is what the layer chain waits on).
 constexpr int kLoadWarp = 0;
-constexpr int kPubWarp = 13;                       // exists only in the hand-off instantiation (G > 1)
-__host__ __device__ constexpr int threads_of(bool handoff) { return (handoff ? 14 : 13) * 32; }
+// warps: loader | 4 per tile | publisher (exists only in the hand-off instantiation, G > 1)
+__host__ __device__ constexpr int threads_of(bool handoff, int nt) { return (1 + 4 * nt + (handoff ? 1 : 0)) * 32; }
 
 // ---- cross-CTA ring hand-off ------------------------------------------------------------------------
 // consumer: chunk n waits until flags[l] >= n (rings of chunks 0..n-1 published), then orders its bulk loads (async proxy)
@@ -237,9 +250,9 @@ __device__ __forceinline__ bool flag_wait(const uint32_t* f, uint32_t need, vola
 __device__ __forceinline__ void ring_rows_done(uint32_t counter_addr, uint32_t rows) {
   asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(counter_addr), "r"(rows) : "memory");
 }
-// rows of ring r (dilation d) that tile group m writes: chunk rows rc in [kChunk - d, kChunk) that fall into tile m
-__device__ __forceinline__ int ring_rows_of(int d, int m) {
-  const int lo = max(kChunk - d, m * kTile), hi = (m + 1) * kTile;
+// rows of ring r (dilation d) that tile group m writes: chunk rows rc in [chunk - d, chunk) that fall into tile m
+__device__ __forceinline__ int ring_rows_of(int d, int m, int chunk) {
+  const int lo = max(chunk - d, m * kTile), hi = (m + 1) * kTile;
   return hi > lo ? hi - lo : 0;
 }
 __device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
@@ -255,14 +268,23 @@ __device__ __forceinline__ void flag_publish(uint32_t* f, uint32_t chunks) {
 // HANDOFF = false (teams of one CTA): the CTA hands its rings to itself across the chunk-end barrier; no flag, counter or
 // publisher code is instantiated and the block has 13 warps.
 template <bool TEACHER, bool FP16, bool HANDOFF>
-__global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p) {
-  constexpr int kThreads = threads_of(HANDOFF);
+__global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_fused(const Params p) {
+  constexpr int NT = tiles_of(TEACHER), CH = NT * kTile;       // tiles and time steps per chunk
+  constexpr int kThreads = threads_of(HANDOFF, NT);
+  constexpr int kPubWarp = 1 + 4 * NT;
+  constexpr int TCOLS = TEACHER ? 160 : 64;                    // TMEM columns per tile
+  using SM = SmemMapT<TEACHER>;
+  constexpr int ROWS = SM::rows;
+  using BR = BarT<NT>;
+  constexpr int BAR_D1 = BR::D1, BAR_D2 = BR::D2, BAR_HD = BR::HD, BAR_WFULL = BR::WFULL, BAR_WEMPTY = BR::WEMPTY, BAR_HALO = BR::HALO,
+                BAR_G1 = BR::G1, BAR_HDD = BR::HDD, BAR_TAIL = BR::TAIL, BAR_C2 = BR::C2;
+  (void)BAR_HDD; (void)BAR_C2; (void)kPubWarp;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
-  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + SmemMap::misc + 8);   // [0] flag [1] code
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SmemMap::misc);
-  auto bar = [&](int i) { return sbase + SmemMap::bars + i * 8; };
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + SM::misc + 8);   // [0] flag [1] code
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::misc);
+  auto bar = [&](int i) { return sbase + SM::bars + i * 8; };
   const int L = p.L;
   constexpr int wrs_bytes = TEACHER ? kWrsTeacher : kWrsStudent;
   constexpr int layer_bytes = kWfBytes + wrs_bytes;
@@ -270,35 +292,35 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < NT; i++) {
       mbar_init(bar(BAR_D1 + i), 1); mbar_init(bar(BAR_D2 + i), 1); mbar_init(bar(BAR_HDD + i), 1);
       mbar_init(bar(BAR_C2 + 2 * i), 1); mbar_init(bar(BAR_C2 + 2 * i + 1), 1);
       mbar_init(bar(BAR_HD + 2 * i), kTile); mbar_init(bar(BAR_HD + 2 * i + 1), kTile);
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), kTiles);
-      mbar_init(bar(BAR_HALO + i), 1); mbar_init(bar(BAR_G1 + i), kTiles);
+      mbar_init(bar(BAR_WFULL + i), 1); mbar_init(bar(BAR_WEMPTY + i), NT);
+      mbar_init(bar(BAR_HALO + i), 1); mbar_init(bar(BAR_G1 + i), NT);
     }
     mbar_init(bar(BAR_TAIL), 1);
     abort_flag[0] = 0; abort_flag[1] = 0;
-    for (int i = 0; i < 3; i++) reinterpret_cast<volatile uint32_t*>(smem + SmemMap::misc + 16)[i] = 0;
+    for (int i = 0; i < NT; i++) reinterpret_cast<volatile uint32_t*>(smem + SM::misc + 16)[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {  // resident constants: biases, front conv, head weights (plain loads; made visible below)
     const uint8_t* pk_ = p.packed;
     const size_t off_fixed = (size_t)L * layer_bytes;     // [filter bias L*32 f32][front 96 f32 -> 64 used][head...]
     const float* fbias = reinterpret_cast<const float*>(pk_ + off_fixed);
-    float* s_bias = reinterpret_cast<float*>(smem + SmemMap::bias);
+    float* s_bias = reinterpret_cast<float*>(smem + SM::bias);
     for (int i = tid; i < L * 32; i += kThreads) s_bias[i] = fbias[i];
     const float* ffront = fbias + kMaxLayers * 32;
-    float* s_front = reinterpret_cast<float*>(smem + SmemMap::front);
+    float* s_front = reinterpret_cast<float*>(smem + SM::front);
     for (int i = tid; i < 64; i += kThreads) s_front[i] = ffront[i];
     const float* fhb = ffront + 64;
-    float* s_hb = reinterpret_cast<float*>(smem + SmemMap::hbias);
+    float* s_hb = reinterpret_cast<float*>(smem + SM::hbias);
     for (int i = tid; i < 128 + 128 + 32 + 64 + 4; i += kThreads) s_hb[i] = fhb[i];
     if (TEACHER) {
       const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(fhb + 128 + 128 + 32 + 64 + 4));
-      uint4* dst = reinterpret_cast<uint4*>(smem + SmemMap::head);
+      uint4* dst = reinterpret_cast<uint4*>(smem + SM::head);
       for (int i = tid; i < (kH1Bytes + kH2Bytes) / 16; i += kThreads) dst[i] = src[i];
     }
   }
@@ -317,7 +339,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
   const int nseg = p.nseg[team];
   uint8_t* ring = p.rings + (size_t)team * p.ring_bytes_per_team;
   uint32_t* flags = p.flags + (size_t)team * kMaxLayers;
-  const uint32_t ringcnt = sbase + SmemMap::misc + 16;   // [3] ring rows written so far by tile group m (monotonic)
+  const uint32_t ringcnt = sbase + SM::misc + 16;   // [3] ring rows written so far by tile group m (monotonic)
   uint32_t pub_expect = 0;                              // publisher lane m: rows group m has to have written
   int seq = 0;                                          // chunk sequence number inside the piece
 #ifndef SRWN_VAR
@@ -333,17 +355,17 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
 
   for (int si = 0; si < nseg; si++) {
     const Seg sg = segs[si];
-    for (int t0 = sg.t_start; t0 < sg.t_end; t0 += kChunk) {
+    for (int t0 = sg.t_start; t0 < sg.t_end; t0 += CH) {
       const int n = seq++;
       if (n % G != member) continue;                    // another member of the team runs this chunk
-      const bool warm = TEACHER ? (t0 + kChunk <= sg.t_out) : false;   // student chunks always need h (cheap)
+      const bool warm = TEACHER ? (t0 + CH <= sg.t_out) : false;   // student chunks always need h (cheap)
       const bool do_head = TEACHER && !warm;
       // A warm-up chunk only feeds the rings: layer l's output h_{l+1} is needed on the rsuf[l+1] rows before the first
       // output row t_out (h_{l+1}[t] reads h_l[t] and h_l[t - d_l]), so a chunk that ends `dist` rows before t_out runs
       // the layers with rsuf[l+1] > dist and nothing deeper; rows outside that cone hold garbage nobody reads.
       int Lc = L;
-      if (t0 + kChunk <= sg.t_out) {
-        const int dist = sg.t_out - (t0 + kChunk);
+      if (t0 + CH <= sg.t_out) {
+        const int dist = sg.t_out - (t0 + CH);
         Lc = 0;
         while (Lc < L && p.rsuf[Lc + 1] > dist) Lc++;
         if (Lc < 1) Lc = 1;
@@ -375,7 +397,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
           have_next = false;
           const int d = p.dil[l];
           const uint8_t* rl = ring + p.ring_off[l];
-          const uint32_t dst0 = sbase + SmemMap::hbuf + s * SmemMap::hbuf_bytes;
+          const uint32_t dst0 = sbase + SM::hbuf + s * SM::hbuf_bytes;
           const int slot0 = (int)((unsigned)t0 % (unsigned)d);   // (t0 - d + i) mod d == (t0 + i) mod d
           if (t0 - d >= sg.t_start) {
             // every halo row exists: per 16-byte K chunk the ring is one or two contiguous pieces, moved by
@@ -385,7 +407,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
               const uint32_t n1 = (uint32_t)(d - slot0) * 16, n2 = (uint32_t)slot0 * 16;
 #pragma unroll
               for (int kc = 0; kc < 4; kc++) {
-                const uint32_t dst = dst0 + (uint32_t)(kc * kRows + kHalo - d) * 16;
+                const uint32_t dst = dst0 + (uint32_t)(kc * ROWS + kHalo - d) * 16;
                 const uint8_t* src = rl + (size_t)kc * d * 16;
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(dst), "l"(src + (size_t)slot0 * 16), "r"(n1), "r"(bar(BAR_HALO + s)) : "memory");
@@ -399,7 +421,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             // segment start: rows before it are the zero padding of ops.py:9
             for (int kc = 0; kc < 4; kc++) {
               for (int i = lane; i < d; i += 32) {
-                const uint32_t dst = dst0 + (uint32_t)(kc * kRows + kHalo - d + i) * 16;
+                const uint32_t dst = dst0 + (uint32_t)(kc * ROWS + kHalo - d + i) * 16;
                 if (t0 - d + i >= sg.t_start) {
                   int slot = slot0 + i; if (slot >= d) slot -= d;
                   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rl + ((size_t)kc * d + slot) * 16) : "memory");
@@ -420,7 +442,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
           if (lane == 0) {
             mbar_expect_tx(bar(BAR_WFULL + s), layer_bytes);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(sbase + SmemMap::wst + s * SmemMap::wst_bytes),
+                         ::"r"(sbase + SM::wst + s * SM::wst_bytes),
                            "l"(p.packed + (size_t)l * layer_bytes), "r"(layer_bytes), "r"(bar(BAR_WFULL + s)) : "memory");
           }
           TRACE(6, l, 1);
@@ -435,12 +457,12 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
       } else if (HANDOFF && warp == kPubWarp) {
         // ================= publisher: ring l of this chunk is complete -> flags[l] = n + 1 ========================
         // Rings written by this chunk: 0 (front conv) and l+1 by the residual epilogue of layer l < Lc (l+1 < L).  Lane m
-        // follows tile group m: ring r is written by the rows rc >= kChunk - d_r, i.e. a known number of rows per group.
+        // follows tile group m: ring r is written by the rows rc >= CH - d_r, i.e. a known number of rows per group.
         const int last = Lc < L - 1 ? Lc : L - 1;
         bool ok = handoff && !(SRWN_VAR & 4);
         for (int r = 0; r <= last && ok; r++) {
-          if (lane < kTiles && !(SRWN_VAR & 1)) {
-            const int rows = ring_rows_of(p.dil[r], lane);
+          if (lane < NT && !(SRWN_VAR & 1)) {
+            const int rows = ring_rows_of(p.dil[r], lane, CH);
             if (rows) {
               pub_expect += (uint32_t)rows;
               if ((int32_t)(ld_acquire_cta_shared(ringcnt + 4 * lane) - pub_expect) < 0) {
@@ -468,7 +490,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
         // gate epilogue -> group barrier -> residual GEMM (2 MMAs, committed first) + skip GEMM (2 MMAs,
         // accumulating in TMEM, off the critical path) -> residual epilogue -> next layer's rows.
         // All control flow is uniform across the group (an aborted wait keeps walking the barriers).
-        const int gw = warp & 3, m = (((warp - 1) >> 2) + gw + 1) % 3;
+        const int gw = warp & 3, m = (((warp - 1) >> 2) + gw + 1) % NT;
         // MMA issue is spread over SMSPs: tile m's issuer is its warp on SMSP m (tcgen05 instructions
         // serialise within an SMSP)
         const bool issuer = gw == m;
@@ -480,11 +502,11 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
         int frame = (t0 + m * kTile) / p.P;
         if (frame > p.frames - 1) frame = p.frames - 1;
         const float* cb_g = p.cb + ((size_t)sg.b * p.frames + frame) * (size_t)(L + 1) * 32;
-        float* cb = reinterpret_cast<float*>(smem + SmemMap::cbs) + m * (kMaxLayers + 1) * 32;
+        float* cb = reinterpret_cast<float*>(smem + SM::cbs) + m * (kMaxLayers + 1) * 32;
         for (int i = row; i < (L + 1) * 32; i += kTile) cb[i] = __ldg(cb_g + i);   // one latent frame per tile
         group_sync(m);
-        const float* s_bias = reinterpret_cast<const float*>(smem + SmemMap::bias);
-        const float* s_front = reinterpret_cast<const float*>(smem + SmemMap::front);
+        const float* s_bias = reinterpret_cast<const float*>(smem + SM::bias);
+        const float* s_front = reinterpret_cast<const float*>(smem + SM::front);
         const int rc = m * kTile + row;                 // row inside the chunk
         f2_t h2[16];                                    // fp32 residual stream of this row, packed pairs
         float v[32];
@@ -494,10 +516,10 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
         constexpr uint32_t fmt = FP16 ? 0u : 1u;
         constexpr uint32_t id32 = make_idesc(fmt, 128, 32), id128 = make_idesc(fmt, 128, 128), id160 = make_idesc(fmt, 128, 160); (void)id160;
         // descriptor low words that do not depend on the layer
-        const uint32_t hb_lo0 = ((sbase + SmemMap::hbuf) >> 4) + (uint32_t)(kHalo + m * kTile) + ((uint32_t)kRows << 16);
-        const uint32_t wb_lo0 = (sbase + SmemMap::wst) >> 4;
-        const uint32_t ab_lo = ((sbase + SmemMap::cbuf + m * SmemMap::cbuf_bytes) >> 4) + ((uint32_t)kTile << 16);
-        const uint32_t d_conv = tmem + m * 160, d_skip = tmem + m * 160 + 32;
+        const uint32_t hb_lo0 = ((sbase + SM::hbuf) >> 4) + (uint32_t)(kHalo + m * kTile) + ((uint32_t)ROWS << 16);
+        const uint32_t wb_lo0 = (sbase + SM::wst) >> 4;
+        const uint32_t ab_lo = ((sbase + SM::cbuf + m * SM::cbuf_bytes) >> 4) + ((uint32_t)kTile << 16);
+        const uint32_t d_conv = tmem + m * TCOLS, d_skip = tmem + m * TCOLS + 32;
 #ifndef SRWN_STUDENT_TMEM_A
 #define SRWN_STUDENT_TMEM_A 1
 #endif
@@ -531,11 +553,11 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             w16[j] = pack2<FP16>(a, b);
           }
           alive = mbar_wait(bar(BAR_HALO + 0), U0(0) & 1, abort_flag, 0x2000000 | (m << 8), p.wait_limit);      // ring 0 was read for this chunk
-          store_row_packed(smem + SmemMap::hbuf, kRows, kHalo + rc, w16);
+          store_row_packed(smem + SM::hbuf, ROWS, kHalo + rc, w16);
           const int d0 = p.dil[0];
           fence_async_smem();
           mbar_arrive(bar(BAR_HD + 2 * m + 0));
-          if (rc >= kChunk - d0) store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);     // published at the top of layer 0
+          if (rc >= CH - d0) store_row_packed(ring + p.ring_off[0], d0, t % d0, w16);     // published at the top of layer 0
         }
 
 #if defined(SRWN_TUNING) && defined(SRWN_STAGGER)
@@ -549,30 +571,33 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
           const uint32_t ph = (lay_base + l) & 1, phs = (U0(s) + (l >> 1)) & 1;
           TRACE(m, l, 0);
           // ---- filter-conv GEMM: K = 64, steps 0,1 = tap rows (W[0], d rows earlier), 2,3 = current rows (W[1])
-          const uint32_t hb_lo = hb_lo0 + (uint32_t)(s * (SmemMap::hbuf_bytes >> 4));
-          const uint32_t wb_lo = wb_lo0 + (uint32_t)(s * (SmemMap::wst_bytes >> 4));
+          const uint32_t hb_lo = hb_lo0 + (uint32_t)(s * (SM::hbuf_bytes >> 4));
+          const uint32_t wb_lo = wb_lo0 + (uint32_t)(s * (SM::wst_bytes >> 4));
           const uint32_t dl = (uint32_t)p.dil[l];
           const uint32_t b1_lo = wb_lo + (32u << 16);
           const uint32_t b2_lo = wb_lo + (kWfBytes >> 4) + ((uint32_t)wrs_rows << 16);
           // the conditions the GEMM depends on are checked by different warps in parallel; the group
           // barrier then publishes them (and this tile's operand rows) to the issuing lane
-          if (gw == ((m + 3) & 3)) alive = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l, p.wait_limit) && alive;
+          if (gw == ((m + 3) & 3)) {
+            alive = mbar_wait(bar(BAR_WFULL + s), phs, abort_flag, 0x3000000 | (m << 8) | l, p.wait_limit) && alive;
+            if (NT > 3 && m >= 3) alive = mbar_wait(bar(BAR_HD + 2 * (m - 3) + s), phs, abort_flag, 0x3300000 | (m << 8) | l, p.wait_limit) && alive;
+          }
           if (gw == ((m + 1) & 3) && m >= 1) alive = mbar_wait(bar(BAR_HD + 2 * (m - 1) + s), phs, abort_flag, 0x3100000 | (m << 8) | l, p.wait_limit) && alive;
           if (gw == ((m + 2) & 3) && m >= 2) alive = mbar_wait(bar(BAR_HD + 2 * (m - 2) + s), phs, abort_flag, 0x3200000 | (m << 8) | l, p.wait_limit) && alive;
           group_sync(m);
           TRACE(m, l, 1);
           // ring l of this chunk (front conv / residual epilogue of layer l-1) is complete for this group: tell the publisher
           if (handoff && !(SRWN_VAR & 1) && gw == (m == 0 ? 1 : 0) && lane == 0) {       // a low row of the tile: it writes ring rows only for the largest dilations, so the release rarely waits for stores of its own
-            const int rows = ring_rows_of((int)dl, m);
+            const int rows = ring_rows_of((int)dl, m, CH);
             if (rows) ring_rows_done(ringcnt + 4 * m, (uint32_t)rows);
           }
           if (issuer) {
             tc_fence_after();
             if (leader) {
               tc_mma<0>(d_conv, desc_from_lo(hb_lo - dl), desc_from_lo(b1_lo), id32);
-              tc_mma<1>(d_conv, desc_from_lo(hb_lo - dl + 2 * kRows), desc_from_lo(b1_lo + 64), id32);
+              tc_mma<1>(d_conv, desc_from_lo(hb_lo - dl + 2 * ROWS), desc_from_lo(b1_lo + 64), id32);
               tc_mma<1>(d_conv, desc_from_lo(hb_lo), desc_from_lo(b1_lo + 128), id32);
-              tc_mma<1>(d_conv, desc_from_lo(hb_lo + 2 * kRows), desc_from_lo(b1_lo + 192), id32);
+              tc_mma<1>(d_conv, desc_from_lo(hb_lo + 2 * ROWS), desc_from_lo(b1_lo + 192), id32);
               tc_commit(bar(BAR_D1 + m));
               tc_commit(bar(BAR_G1 + s));               // 3 arrivals (one per tile) complete the phase
             }
@@ -625,7 +650,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             tc_wait_st();
             tc_fence_before();
           } else {
-            store_row_packed(smem + SmemMap::cbuf + m * SmemMap::cbuf_bytes, kTile, row, w16);
+            store_row_packed(smem + SM::cbuf + m * SM::cbuf_bytes, kTile, row, w16);
             tc_fence_before();
             LOOP_FENCE();
           }
@@ -702,7 +727,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
                 alive = mbar_wait(bar(BAR_HALO + sn), (U0(sn) + ((l + 1) >> 1)) & 1, abort_flag, 0x2400000 | (m << 8) | l, p.wait_limit) && alive;
               }
               TRACE(m, l, 10);
-              store_row_packed(smem + SmemMap::hbuf + sn * SmemMap::hbuf_bytes, kRows, kHalo + rc, w16);
+              store_row_packed(smem + SM::hbuf + sn * SM::hbuf_bytes, ROWS, kHalo + rc, w16);
               tc_fence_before();
               LOOP_FENCE();
               mbar_arrive(bar(BAR_HD + 2 * m + sn));
@@ -712,7 +737,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
             }
             // history for the next chunk (read by the loader after the chunk-end barrier)
             const int dn = p.dil[l + 1];
-            if (rc >= kChunk - dn) store_row_packed(ring + p.ring_off[l + 1], dn, t % dn, w16);   // published at the top of layer l+1
+            if (rc >= CH - dn) store_row_packed(ring + p.ring_off[l + 1], dn, t % dn, w16);   // published at the top of layer l+1
             TRACE(m, l, 11);
           } else {
             tc_fence_before();
@@ -721,9 +746,9 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
 
         if (TEACHER) {
           if (do_head) {
-            const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
-            uint8_t* a3 = smem + SmemMap::hbuf + m * (16 * kTile * 16);
-            const uint32_t a3_lo = ((sbase + SmemMap::hbuf + m * (16 * kTile * 16)) >> 4) + ((uint32_t)kTile << 16);
+            const float* s_hb = reinterpret_cast<const float*>(smem + SM::hbias);
+            uint8_t* a3 = smem + SM::hbuf + m * (16 * kTile * 16);
+            const uint32_t a3_lo = ((sbase + SM::hbuf + m * (16 * kTile * 16)) >> 4) + ((uint32_t)kTile << 16);
             // all filter-conv MMAs of the last layer retired -> both activation buffers are free
             alive = mbar_wait(bar(BAR_G1 + ((L - 1) & 1)), (U0((L - 1) & 1) + ((L - 1) >> 1)) & 1, abort_flag, 0x2500000 | (m << 8), p.wait_limit) && alive;
             // the skip accumulator is complete once this tile's last skip MMA retired (WEMPTY commit of the last layer)
@@ -746,7 +771,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
               if (issuer) {
                 tc_fence_after();
                 if (leader && !*abort_flag) {
-                  const uint32_t wlo = ((sbase + SmemMap::head + (hs == 0 ? 0 : kH1Bytes)) >> 4) + ((uint32_t)(hs == 0 ? 128 : 32) << 16);
+                  const uint32_t wlo = ((sbase + SM::head + (hs == 0 ? 0 : kH1Bytes)) >> 4) + ((uint32_t)(hs == 0 ? 128 : 32) << 16);
                   const int nrows = hs == 0 ? 128 : 32;
 #pragma unroll
                   for (int j = 0; j < 8; j++)
@@ -797,7 +822,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
         } else {
           // student flow head: relu -> 1x1 R->2; scale = exp(p0), mean = p1; out = x*scale + mean
           // (model.py:451-452, 479-482)
-          const float* s_hb = reinterpret_cast<const float*>(smem + SmemMap::hbias);
+          const float* s_hb = reinterpret_cast<const float*>(smem + SM::hbias);
           const float* hk = s_hb + 288;
           float p0 = 0.f, p1 = 0.f;
 #pragma unroll
@@ -820,10 +845,10 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
         }
       }
       if (handoff && !(SRWN_VAR & 1) && Lc < L && warp != kLoadWarp && warp != kPubWarp) {        // pruned warm-up chunk: ring Lc was written behind the last layer
-        const int gw = warp & 3, m = (((warp - 1) >> 2) + gw + 1) % 3;
+        const int gw = warp & 3, m = (((warp - 1) >> 2) + gw + 1) % NT;
         group_sync(m);
         if (gw == (m == 0 ? 1 : 0) && lane == 0) {
-          const int rows = ring_rows_of(p.dil[Lc], m);
+          const int rows = ring_rows_of(p.dil[Lc], m, CH);
           if (rows) ring_rows_done(ringcnt + 4 * m, (uint32_t)rows);
         }
       }
@@ -842,13 +867,13 @@ __global__ void __launch_bounds__(threads_of(HANDOFF), 1) k_fused(const Params p
 
   // ---- teardown ------------------------------------------------------------------------------
   if (TEACHER && p.nll_partial) {
-    double* s_red = reinterpret_cast<double*>(smem + SmemMap::cbuf);     // reuse (everything is quiescent)
+    double* s_red = reinterpret_cast<double*>(smem + SM::cbuf);     // reuse (everything is quiescent)
     for (int s = 16; s >= 1; s >>= 1) nll_acc += __shfl_xor_sync(0xffffffffu, nll_acc, s);
     if (lane == 0) s_red[warp] = nll_acc;
     __syncthreads();
     if (tid == 0) {
       double tot = 0;
-      for (int w = 1; w <= 12; w++) tot += s_red[w];   // tile-group warps only
+      for (int w = 1; w <= 4 * NT; w++) tot += s_red[w];   // tile-group warps only
       p.nll_partial[blockIdx.x] = tot;
     }
   }
@@ -1061,7 +1086,7 @@ struct Partition { std::vector<Seg> segs; std::vector<int> nseg; int teams, G; d
 // warm_cost[k] = cost (in full chunks) of the k warm-up chunks nearest the first output row: a warm-up chunk skips the skip
 // GEMM and the head and runs only the layers inside the dependency cone (k_fused: rsuf[l+1] > dist); a fixed part per chunk
 // (front conv, conditioning loads, chunk barrier) plus a part proportional to the layers it runs
-static bool try_partition(int B, int T, const std::vector<double>& warm_cost, int teams, double budget, Partition* out) {
+static bool try_partition(int B, int T, int kChunk, const std::vector<double>& warm_cost, int teams, double budget, Partition* out) {
   const int warm_chunks = (int)warm_cost.size() - 1;
   const int NC = (T + kChunk - 1) / kChunk;
   std::vector<Seg> segs((size_t)teams * kMaxSeg);
@@ -1091,16 +1116,16 @@ static bool try_partition(int B, int T, const std::vector<double>& warm_cost, in
   return true;
 }
 
-static Partition partition_for(int B, int T, const std::vector<double>& warm_cost, int teams) {
+static Partition partition_for(int B, int T, int kChunk, const std::vector<double>& warm_cost, int teams) {
   const int warm_chunks = (int)warm_cost.size() - 1;
   const long long total = (long long)B * ((T + kChunk - 1) / kChunk);
   double lo = (double)total / teams, hi = lo + warm_chunks + 2;
   Partition best;
-  while (!try_partition(B, T, warm_cost, teams, hi, &best)) hi *= 1.5;
+  while (!try_partition(B, T, kChunk, warm_cost, teams, hi, &best)) hi *= 1.5;
   for (int it = 0; it < 24; it++) {
     const double mid = 0.5 * (lo + hi);
     Partition cand;
-    if (try_partition(B, T, warm_cost, teams, mid, &cand)) { hi = mid; best = cand; } else lo = mid;
+    if (try_partition(B, T, kChunk, warm_cost, teams, mid, &cand)) { hi = mid; best = cand; } else lo = mid;
   }
   best.cost = hi;
   return best;
@@ -1112,7 +1137,7 @@ static Partition partition_for(int B, int T, const std::vector<double>& warm_cos
 // least G lags.  Larger G shares the mid-utterance warm-up between more CTAs; `force_G` > 0 overrides the choice.
 constexpr double kLagLayers = 1.5;
 constexpr int kMaxTeam = 18;
-static Partition make_partition(int B, int T, const std::vector<int>& dilations, int grid, int force_G) {
+static Partition make_partition(int B, int T, int kChunk, const std::vector<int>& dilations, int grid, int force_G) {
   const int NC = (T + kChunk - 1) / kChunk;
   const int L = (int)dilations.size();
   std::vector<int> rsuf(L + 1, 0);
@@ -1132,7 +1157,7 @@ static Partition make_partition(int B, int T, const std::vector<int>& dilations,
     int teams = grid / G;
     if ((long long)teams > total) teams = (int)total;
     if (teams < 1) continue;
-    Partition cand = partition_for(B, T, warm_cost, teams);
+    Partition cand = partition_for(B, T, kChunk, warm_cost, teams);
     const double lag = kLagLayers / L;
     const double period = std::max(1.0, G * lag);
     // measured (profiles/r02d_handoff_variants.log, r02e_team_sizes.log): a chunk costs about 10 % more with the hand-off
@@ -1190,12 +1215,12 @@ static int launch_fused(srwn_ctx* c, const Params& p, int grid, int fp16, cudaSt
   if (!fp16) return srwn_fail(SRWN_ERR_UNSUPPORTED, "the fused kernel is built for fp16 operands only (bf16 misses the 2e-2 logit bound)");
   const bool handoff = p.G > 1;
   auto kern = handoff ? k_fused<TEACHER, true, true> : k_fused<TEACHER, true, false>;
-  SRWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemMap::total));
+  SRWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemMapT<TEACHER>::total));
   // the members of a team wait on one another's ring flags: the launch must be co-resident (grid <= SM count, one CTA
   // per SM), which a cooperative launch guarantees or refuses
   Params pl = p;
   void* args[] = {&pl};
-  SRWN_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads_of(handoff)), args, SmemMap::total, st));
+  SRWN_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads_of(handoff, tiles_of(TEACHER))), args, SmemMapT<TEACHER>::total, st));
   SRWN_LAUNCH_CHECK();
   return SRWN_OK;
 }
@@ -1224,7 +1249,7 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   if (first && (c->part_B != B || c->part_T != T || c->part_team_req != c->team_size)) {
     // the work partition depends on (B, T) and the team size only: built once, kept on the device next to the handle.
     // The staging vector belongs to the handle (a copy from pageable memory returns once the bytes are staged).
-    Partition part = make_partition(B, T, c->dilations, c->sm_count, c->team_size);
+    Partition part = make_partition(B, T, chunk_of(c->cfg.kind == SRWN_TEACHER), c->dilations, c->sm_count, c->team_size);
     c->part_host.assign(seg_bytes + n_bytes, 0);
     memcpy(c->part_host.data(), part.segs.data(), std::min(seg_bytes, part.segs.size() * sizeof(Seg)));
     memcpy(c->part_host.data() + seg_bytes, part.nseg.data(), std::min(n_bytes, part.nseg.size() * sizeof(int)));
