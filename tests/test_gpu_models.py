@@ -416,3 +416,24 @@ def test_nll_stream_survives_an_early_stop(srwn):
     with pytest.raises(ValueError):
         list(t.nll_stream([(batches[0][0], batches[0][1][:, :1])]))          # encoding of the wrong length: refused, nothing hangs
     assert t.nll(*batches[1]) == ref[1]
+
+
+@pytest.mark.parametrize("C", [1, 6, 7, 13])
+def test_conditioning_channel_counts_not_multiples_of_four(srwn, C):
+    """The conditioning fold of the 16-bit path (fused::k_cond_fold) reads the encoding four channels at a time with a
+    remainder loop: latent sizes that are not multiples of four, teacher (model.py:180) and student (model.py:431), on a
+    length that spans several chunks and ends inside a latent frame's tile."""
+    dil = [1, 2, 4, 8, 16, 32, 1, 2, 4, 8]
+    B, T, P = 3, 1664, 128
+    x, enc = synth.synthetic_audio(B, T, seed=11), synth.synthetic_encoding(B, T // P, C, seed=12)
+    t, w = _teacher(srwn, dil, C=C, M=5, P=P, seed=31)
+    ref = orc.teacher_decoder_logits(f64(w), x.astype(np.float64), enc.astype(np.float64), dil, P)
+    for prec in t.available_precisions():
+        logits = t.get_logits(x, enc, precision=prec)
+        assert np.abs(logits - ref).max() <= _tol(ref, prec), (prec, C)
+    s, ws = _student(srwn, dil, 2, C=C, P=P, seed=32)
+    z = synth.logistic_noise(B, T, seed=13)
+    rs = orc.student_network(f64(ws), z.astype(np.float64), enc.astype(np.float64), dil, P, 2)
+    for prec in s.available_precisions():
+        r = s.forward_all(z, enc, precision=prec)
+        assert np.abs(r["out"] - rs["out"][:, :, 0]).max() <= STUDENT_TOL[prec], (prec, C)
