@@ -1,8 +1,8 @@
 // Fused residual-stack kernel on tcgen05 tensor cores (sm_100a), 16-bit operands, fp32 accumulate.
 //
 // One persistent, warp-specialised CTA per SM streams a contiguous piece of the (utterance, time)
-// line in chunks of 384 time steps (3 MMA tiles of 128 rows = TMEM lanes).  For a chunk, ALL
-// layers run on-chip:
+// line in chunks of NT MMA tiles of 128 rows (= TMEM lanes): 384 time steps for the teacher (NT = 3), 512 for the
+// student (NT = 4, tiles_of()).  For a chunk, ALL layers run on-chip:
 //   * the residual stream lives in fp32 registers of the epilogue thread that owns the row,
 //   * its 16-bit image (the conv operand) lives in shared memory in the UMMA canonical K-major
 //     no-swizzle layout [k-chunk][row][8 elems]; the dilated tap of layer l is the SAME buffer
@@ -12,9 +12,9 @@
 //   * the skip sum over layers accumulates in TMEM (128 fp32 columns per tile) and never leaves
 //     the SM; the output head (relu, 1x1 S->S, relu, 1x1 S->4M) and the mixture-of-logistics
 //     likelihood run from TMEM as the chunk's epilogue.
-// Warp roles: warps 0-11 = three epilogue warpgroups (one per tile; tcgen05.ld -> gate math ->
-// 16-bit operand stores), warp 12 = MMA issuer (event driven, one elected thread) + TMEM owner,
-// warp 13 = loader (cp.async.bulk weights per layer, cp.async ring -> halo rows).
+// Warp roles: warp 0 = loader (cp.async.bulk weights and ring -> halo rows per layer) + TMEM owner, warps 1..4 NT = NT tile
+// groups of four warps (tcgen05.ld -> gate math -> operand stores; one elected lane per group issues the tile's MMAs),
+// last warp (hand-off instantiation only) = publisher of the ring flags.
 // Work decomposition: the (utterance, chunk) line is cut into contiguous pieces, one per TEAM of G CTAs; the members
 // of a team take the piece's chunks round-robin (member j: chunks j, j+G, ...).  Chunk n+1 needs, per layer, the last
 // d_l input rows of chunk n (the history ring): the team shares one ring block in global memory (L2 resident) and chunk
@@ -198,9 +198,9 @@ __device__ __forceinline__ void store_row_packed(uint8_t* buf, int rows_per_kc, 
 #endif
 
 // ---- the kernel --------------------------------------------------------------------------
-// 14 warps: warp 0 = loader + TMEM owner, warps 1..12 = three tile groups of four warps, one warp per
-// SMSP (row = TMEM lane = 32*(warp&3) + lane), warp 13 = publisher of the ring flags (off the layer chain).  Warp w sits on SMSP q = w&3 at level j = (w-1)/4 and
-// belongs to tile (j+q+1)%3, so that tile m's MMA-issuing warp is the highest warp id of SMSP m (the
+// 2 + 4 NT warps (teacher 14, student 18): warp 0 = loader + TMEM owner, warps 1..4 NT = NT tile groups of four warps, one warp per
+// SMSP (row = TMEM lane = 32*(warp&3) + lane), warp 4 NT + 1 = publisher of the ring flags (off the layer chain).  Warp w sits on SMSP q = w&3 at level j = (w-1)/4 and
+// belongs to tile (j+q+1)%NT, so that tile m's MMA-issuing warp is the highest warp id of SMSP m (the
 // arbiter prefers high warp ids, and tcgen05 issue from a busy SMSP is what the layer chain waits on).
 constexpr int kLoadWarp = 0;
 // warps: loader | 4 per tile | publisher (exists only in the hand-off instantiation, G > 1)
