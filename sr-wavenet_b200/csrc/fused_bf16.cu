@@ -918,20 +918,27 @@ __global__ void k_fold_bias(const float* __restrict__ cond, const float* __restr
 // conditioning weights are read once per kCondRows frames:
 // cb[bf][l] = enc[bf] @ Wc_l + bc_l + (l == 0 ? front_b : sqrt(1/2) res_b[l-1]);  cb[bf][L] = sqrt(1/2) res_b[L-1]
 #ifndef SRWN_COND_ROWS
-#define SRWN_COND_ROWS 32
+#define SRWN_COND_ROWS 16
 #endif
-// 8 rows per CTA re-read the 127 KB of conditioning weights from L2 2000 times at 32x64000 (61 us); 32 rows: 4x less
+// 16 frames per CTA of 256 threads, two CTAs per SM: one computes while the other stores (a 512-thread CTA with 32 frames
+// runs its FMA phase and its 127 KB of stores one after the other: 14.07 -> 14.00 ms per student step at 64x64000)
 constexpr int kCondRows = SRWN_COND_ROWS;
-constexpr int kCondThreads = 512;
+constexpr int kCondRowsPerThread = 16;
+constexpr int kCondThreads = 256 * (kCondRows / kCondRowsPerThread);     // 248 of every 256 threads own a (layer, 4-channel) group
+static_assert(kCondRows % kCondRowsPerThread == 0 && kCondRows >= kCondRowsPerThread, "SRWN_COND_ROWS is a multiple of 16");
 // Register-blocked: a thread owns 4 consecutive output channels of one (layer, frame-half) for kCondRows / 2 frames, so one
 // 16-byte weight load and one broadcast 16-byte read of the encodings feed 16 FMAs each (the first version issued one
 // shared-memory read per FMA and was bound by that pipe).  The sum over the conditioning channels runs in ascending
-// order from the folded bias, as before: results are bit-identical.
-__global__ void __launch_bounds__(kCondThreads, 1)
+// order from the folded bias, as before: results are bit-identical.  The student's flows (stacks) are folded by one launch.
+__global__ void __launch_bounds__(kCondThreads, 512 / kCondThreads)
 k_cond_fold(const float* __restrict__ enc, const float* __restrict__ cond_k, const float* __restrict__ cond_b,
             const float* __restrict__ front_b, const float* __restrict__ res_b, float* __restrict__ cb,
-            int BF, int L, int C) {
-  constexpr int RH = kCondRows / 2;
+            int BF, int L, int C, size_t w_stride, size_t cb_stride) {
+  constexpr int RH = kCondRowsPerThread;
+  {                                                   // blockIdx.y = stack (student flow): same layout, `w_stride` floats further
+    const size_t wo = (size_t)blockIdx.y * w_stride;
+    cond_k += wo; cond_b += wo; front_b += wo; res_b += wo; cb += (size_t)blockIdx.y * cb_stride;
+  }
   __shared__ __align__(16) float s_enc[kCondRows][kMaxCond];
   const int bf0 = blockIdx.x * kCondRows;
   for (int i = threadIdx.x; i < kCondRows * kMaxCond; i += blockDim.x) {
@@ -939,8 +946,8 @@ k_cond_fold(const float* __restrict__ enc, const float* __restrict__ cond_k, con
     s_enc[r][c] = (bf0 + r < BF && c < C) ? enc[(size_t)(bf0 + r) * C + c] : 0.f;
   }
   __syncthreads();
-  const int half = threadIdx.x / (kCondThreads / 2), r0 = half * RH;
-  for (int g = threadIdx.x % (kCondThreads / 2); g < (L + 1) * 8; g += kCondThreads / 2) {
+  const int half = threadIdx.x / 256, r0 = half * RH;
+  for (int g = threadIdx.x % 256; g < (L + 1) * 8; g += 256) {
     const int l = g / 8, j = (g % 8) * 4, o = l * 32 + j;
     float4 base;
     {
@@ -1169,7 +1176,7 @@ static Partition make_partition(int B, int T, int kChunk, const std::vector<int>
 }
 
 struct FusedWs {
-  float *cond, *cb; uint8_t* rings; uint32_t* flags; double* partial;
+  float* cb; uint8_t* rings; uint32_t* flags; double* partial;
 #ifdef SRWN_TUNING
   long long* trace;
 #endif
@@ -1182,10 +1189,10 @@ static FusedWs carve_fused(const srwn_ctx* c, int B, int T, void* ws, size_t cap
   FusedWs r{};
   const size_t frames = T / c->cfg.pool_stride, L = c->cfg.n_layers, n = (size_t)B * T;
   const int grid = c->sm_count > 0 ? c->sm_count : 148;
-  r.cond = w.take<float>((size_t)B * frames * L * 32);
-  r.cb = w.take<float>((size_t)B * frames * (L + 1) * 32);
+  const size_t nst = c->cfg.kind == SRWN_STUDENT ? (size_t)c->cfg.num_flows : 1;   // stacks folded / flagged up front
+  r.cb = w.take<float>((size_t)B * frames * (L + 1) * 32 * nst);
   r.rings = w.take<uint8_t>((size_t)grid * ((size_t)c->sum_dilation * 64 + 256));     // one block per team, at most `grid` teams
-  r.flags = w.take<uint32_t>((size_t)grid * kMaxLayers);
+  r.flags = w.take<uint32_t>((size_t)grid * kMaxLayers * nst);
   r.partial = w.take<double>(grid);
 #ifdef SRWN_TUNING
   r.trace = w.take<long long>(7 * kMaxLayers * 12);
@@ -1241,10 +1248,19 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   const float* sw = stack_w(c, stack);
   int rc = sticky_error(c);
   if (rc) return rc;
-  k_cond_fold<<<(B * frames + kCondRows - 1) / kCondRows, kCondThreads, 0, st>>>(enc, sw + c->off.cond_k, sw + c->off.cond_b,
-                                                                        sw + c->off.front_b, sw + c->off.res_b, w.cb,
-                                                                        B * frames, L, c->cfg.cond_channels);
-  SRWN_LAUNCH_CHECK();
+  // conditioning of every stack and the ring flags of every launch are prepared by the first call of a sequence (the
+  // student's flows then launch back to back)
+  const int nst = c->cfg.kind == SRWN_STUDENT ? c->cfg.num_flows : 1;
+  const size_t cb_stride = (size_t)B * frames * (L + 1) * 32, flag_stride = (size_t)c->sm_count * kMaxLayers;
+  if (first) {
+    const float* s0 = stack_w(c, 0);
+    k_cond_fold<<<dim3((B * frames + kCondRows - 1) / kCondRows, nst), kCondThreads, 0, st>>>(
+        enc, s0 + c->off.cond_k, s0 + c->off.cond_b, s0 + c->off.front_b, s0 + c->off.res_b, w.cb, B * frames, L,
+        c->cfg.cond_channels, c->stack_floats, cb_stride);
+    SRWN_LAUNCH_CHECK();
+    SRWN_CUDA(cudaMemsetAsync(w.flags, 0, flag_stride * nst * sizeof(uint32_t), st));
+  }
+  (void)sw;
   const size_t seg_bytes = (size_t)c->sm_count * kMaxSeg * sizeof(Seg), n_bytes = (size_t)c->sm_count * sizeof(int);
   if (first && (c->part_B != B || c->part_T != T || c->part_team_req != c->team_size)) {
     // the work partition depends on (B, T) and the team size only: built once, kept on the device next to the handle.
@@ -1258,11 +1274,10 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
     c->part_teams = part.teams; c->part_G = part.G;
   }
   *grid = c->part_teams * c->part_G;
-  SRWN_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)c->sm_count * kMaxLayers * sizeof(uint32_t), st));
   memset(p, 0, sizeof(*p));
   const size_t img = stack_image_bytes(c);
   p->packed = (const uint8_t*)c->d_packed + ((size_t)(fp16 ? 1 : 0) * c->n_stacks + stack) * img;
-  p->cb = w.cb; p->rings = w.rings; p->flags = w.flags; p->err = c->h_err; p->G = c->part_G;
+  p->cb = w.cb + (size_t)stack * cb_stride; p->rings = w.rings; p->flags = w.flags + (size_t)stack * flag_stride; p->err = c->h_err; p->G = c->part_G;
   p->wait_limit = c->wait_limit_clocks;
   p->segs = reinterpret_cast<const Seg*>(c->d_part);
   p->nseg = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(c->d_part) + seg_bytes);
