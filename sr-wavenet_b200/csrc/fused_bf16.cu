@@ -523,6 +523,12 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
 #ifndef SRWN_STUDENT_TMEM_A
 #define SRWN_STUDENT_TMEM_A 1
 #endif
+#ifndef SRWN_STUDENT_LATE_WEMPTY
+#define SRWN_STUDENT_LATE_WEMPTY 1
+#endif
+#ifndef SRWN_STUDENT_LATE_G1
+#define SRWN_STUDENT_LATE_G1 1
+#endif
 #ifndef SRWN_TEACHER_TMEM_A
 #define SRWN_TEACHER_TMEM_A 1
 #endif
@@ -534,6 +540,12 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
         constexpr bool kTmemAT = TEACHER && SRWN_TEACHER_TMEM_A;
         constexpr bool kTmemA = (!TEACHER && SRWN_STUDENT_TMEM_A) || kTmemAT;
         uint32_t d_cop = d_skip;
+        // student: a plain mbarrier arrive by a warp that does not issue, once it has seen the tile's commit barrier complete, can
+        // stand in for the issuing lane's SECOND tcgen05.commit of a GEMM (same MMAs covered).  Measured per instantiation
+        // (alternating runs, 8x64000 with teams of 9 / 64x64000 with one CTA per piece): for BAR_WEMPTY behind the residual
+        // GEMM 0.534 -> 0.500 ms with the hand-off, +0.5 % without; for BAR_G1 behind the filter conv 0.500 -> 0.526 ms with the
+        // hand-off, 3.421 -> 3.400 ms without.  Each instantiation takes the one that pays.  (Teacher: neither does.)
+        constexpr bool kLateG1 = !TEACHER && !HANDOFF && SRWN_STUDENT_LATE_G1;
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
         {
@@ -599,7 +611,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
               tc_mma<1>(d_conv, desc_from_lo(hb_lo), desc_from_lo(b1_lo + 128), id32);
               tc_mma<1>(d_conv, desc_from_lo(hb_lo + 2 * ROWS), desc_from_lo(b1_lo + 192), id32);
               tc_commit(bar(BAR_D1 + m));
-              tc_commit(bar(BAR_G1 + s));               // 3 arrivals (one per tile) complete the phase
+              if constexpr (!kLateG1) tc_commit(bar(BAR_G1 + s));               // NT arrivals (one per tile) complete the phase
             }
             __syncwarp();
           }
@@ -615,6 +627,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
 
           // ---- gate: tanh, sigmoid of the tanh, product (ops.py:28,33,36) ----
           alive = mbar_wait(bar(BAR_D1 + m), ph, abort_flag, 0x2100000 | (m << 8) | l, p.wait_limit) && alive;
+          if (kLateG1 && gw == ((m + 2) & 3) && lane == 0) mbar_arrive(bar(BAR_G1 + s));      // the tile's filter-conv MMAs retired (D1): same signal, no second commit
           TRACE(m, l, 3);
           tc_fence_after();
           tc_ld32(d_conv + lane_addr, v);
@@ -695,7 +708,11 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
               }
               if constexpr (kTmemAT) tc_commit(bar(BAR_C2 + 2 * m + ((lay_base + l) & 1)));      // the operand region of this tile-layer is free
 #endif
-              tc_commit(bar(BAR_WEMPTY + s));           // 3 arrivals free the weight stage
+#if SRWN_STUDENT_LATE_WEMPTY
+              if constexpr (TEACHER || !HANDOFF) tc_commit(bar(BAR_WEMPTY + s));           // NT arrivals free the weight stage
+#else
+              tc_commit(bar(BAR_WEMPTY + s));           // NT arrivals free the weight stage
+#endif
             }
             __syncwarp();
           }
@@ -703,6 +720,13 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
 
           // ---- residual: dense = (inputs + residual) * sqrt(1/2) (ops.py:39-40), next conditioning ----
           alive = mbar_wait(bar(BAR_D2 + m), ph, abort_flag, 0x2200000 | (m << 8) | l, p.wait_limit) && alive;
+#if SRWN_STUDENT_LATE_WEMPTY
+          // student, hand-off instantiation: the residual MMAs are the only readers of the weight stage and they have retired
+          // (D2), so a plain arrive by a warp that does not issue replaces the issuing lane's second tcgen05.commit.  Measured
+          // in alternating runs: 0.534 -> 0.500 ms per flow launch at 8x64000 (teams of 9); without the hand-off (64x64000,
+          // one CTA per piece) the same change is 0.5 % slower, so that instantiation keeps the commit.
+          if (!TEACHER && HANDOFF && gw == ((m + 1) & 3) && lane == 0) mbar_arrive(bar(BAR_WEMPTY + s));
+#endif
           TRACE(m, l, 8);
           tc_fence_after();
           tc_ld32(d_conv + lane_addr, v);
