@@ -1171,7 +1171,7 @@ static Partition partition_for(int B, int T, int kChunk, const std::vector<doubl
 // least G lags.  Larger G shares the mid-utterance warm-up between more CTAs; `force_G` > 0 overrides the choice.
 constexpr double kLagLayers = 1.5;
 constexpr int kMaxTeam = 18;
-static Partition make_partition(int B, int T, int kChunk, const std::vector<int>& dilations, int grid, int force_G) {
+static Partition make_partition(int B, int T, int kChunk, double handoff_cost, const std::vector<int>& dilations, int grid, int force_G) {
   const int NC = (T + kChunk - 1) / kChunk;
   const int L = (int)dilations.size();
   std::vector<int> rsuf(L + 1, 0);
@@ -1194,9 +1194,10 @@ static Partition make_partition(int B, int T, int kChunk, const std::vector<int>
     Partition cand = partition_for(B, T, kChunk, warm_cost, teams);
     const double lag = kLagLayers / L;
     const double period = std::max(1.0, G * lag);
-    // measured (profiles/r02d_handoff_variants.log, r02e_team_sizes.log): a chunk costs about 10 % more with the hand-off
-    // (flag waits of the loader, row counting) than without
-    const double time = (cand.cost / G + (G > 1 ? 0.5 : 0.0)) * period * (G > 1 ? 1.10 : 1.0) + (G - 1) * lag;
+    // measured (profiles/r02d_handoff_variants.log, r02e_team_sizes.log): a teacher chunk costs about 10 % more with the
+    // hand-off (flag waits of the loader, row counting) than without; a student chunk about 4 % since its weight stage is
+    // released by a plain arrive (32x64000: 1.825 ms with one CTA per piece, 1.725 ms with teams of 4)
+    const double time = (cand.cost / G + (G > 1 ? 0.5 : 0.0)) * period * (G > 1 ? handoff_cost : 1.0) + (G - 1) * lag;
     if (time < best_time) { best_time = time; best = cand; best.G = G; }
   }
   return best;
@@ -1292,7 +1293,8 @@ static int prepare(srwn_ctx* c, int stack, const float* enc, int B, int T, const
   if (first && (c->part_B != B || c->part_T != T || c->part_team_req != c->team_size)) {
     // the work partition depends on (B, T) and the team size only: built once, kept on the device next to the handle.
     // The staging vector belongs to the handle (a copy from pageable memory returns once the bytes are staged).
-    Partition part = make_partition(B, T, chunk_of(c->cfg.kind == SRWN_TEACHER), c->dilations, c->sm_count, c->team_size);
+    const bool teacher = c->cfg.kind == SRWN_TEACHER;
+    Partition part = make_partition(B, T, chunk_of(teacher), teacher ? 1.10 : 1.04, c->dilations, c->sm_count, c->team_size);
     c->part_host.assign(seg_bytes + n_bytes, 0);
     memcpy(c->part_host.data(), part.segs.data(), std::min(seg_bytes, part.segs.size() * sizeof(Seg)));
     memcpy(c->part_host.data() + seg_bytes, part.nseg.data(), std::min(n_bytes, part.nseg.size() * sizeof(int)));
