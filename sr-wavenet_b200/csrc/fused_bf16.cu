@@ -548,7 +548,8 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
         // (alternating runs, 8x64000 with teams of 9 / 64x64000 with one CTA per piece): for BAR_WEMPTY behind the residual
         // GEMM 0.534 -> 0.500 ms with the hand-off, +0.5 % without; for BAR_G1 behind the filter conv 0.500 -> 0.526 ms with the
         // hand-off, 3.421 -> 3.400 ms without.  Each instantiation takes the one that pays.  (Teacher: neither does.)
-        constexpr bool kLateG1 = !HANDOFF && (TEACHER ? SRWN_TEACHER_LATE_G1 : SRWN_STUDENT_LATE_G1);
+        constexpr bool kLateG1 = TEACHER ? ((SRWN_TEACHER_LATE_G1 == 1 && !HANDOFF) || (SRWN_TEACHER_LATE_G1 == 2 && HANDOFF))
+                                         : (!HANDOFF && SRWN_STUDENT_LATE_G1);
 
         // front: RightShift + K=2 causal conv on one channel (model.py:172-173), + bias + conditioning
         {
