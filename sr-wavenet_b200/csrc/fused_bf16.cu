@@ -526,6 +526,10 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
 #ifndef SRWN_STUDENT_LATE_WEMPTY
 #define SRWN_STUDENT_LATE_WEMPTY 1
 #endif
+#ifndef SRWN_LATE_WARP
+#define SRWN_LATE_WARP 1        // which warp of the tile group (relative to the issuer) arrives for it: 1 or 2 measure the same
+                                // (0.500 ms per flow at 8x64000), 3 -- the warp that waits for the next weight stage -- 0.533 ms
+#endif
 #ifndef SRWN_STUDENT_LATE_G1
 #define SRWN_STUDENT_LATE_G1 1
 #endif
@@ -729,7 +733,7 @@ __global__ void __launch_bounds__(threads_of(HANDOFF, tiles_of(TEACHER)), 1) k_f
           // (D2), so a plain arrive by a warp that does not issue replaces the issuing lane's second tcgen05.commit.  Measured
           // in alternating runs: 0.534 -> 0.500 ms per flow launch at 8x64000 (teams of 9); without the hand-off (64x64000,
           // one CTA per piece) the same change is 0.5 % slower, so that instantiation keeps the commit.
-          if (!TEACHER && HANDOFF && gw == ((m + 1) & 3) && lane == 0) mbar_arrive(bar(BAR_WEMPTY + s));
+          if (!TEACHER && HANDOFF && gw == ((m + SRWN_LATE_WARP) & 3) && lane == 0) mbar_arrive(bar(BAR_WEMPTY + s));
 #endif
           TRACE(m, l, 8);
           tc_fence_after();
